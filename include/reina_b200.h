@@ -1,0 +1,260 @@
+/*
+ * reina_b200.h — C ABI of the B200-native path-tracing core for Reina.
+ *
+ * This is the drop-in boundary for ONE hot path of AlexanderJCS/reina-vk:
+ *     scene hand-off -> trace + shade + accumulate one sample batch -> bloom + tonemap -> read back.
+ * Everything the reference binds to its ray-tracing descriptor set is passed here as plain host
+ * pointers and counts; the library copies them to the GPU, builds its own 8-wide BVH (the reference lets the
+ * Vulkan driver build BLAS/TLAS) and runs hand-written sm_100a kernels.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   RB200InstanceProperties      <- polyglot/raytrace.h:18-41     (byte-for-byte, 120 B)
+ *   RB200RtPushConsts            <- polyglot/raytrace.h:43-54     (byte-for-byte, 160 B)
+ *   RB200BloomPushConsts         <- polyglot/bloom.h:4-8
+ *   RB200TonemappingPushConsts   <- polyglot/tonemapping.h:4-6
+ *   RB200InstanceData            <- src/scene/Instances.h:15-27 == shaders/raytrace/nee.h.glsl:11-22 (112 B)
+ *   RB200Instance                <- the TLAS record, src/tools/vktools.cpp:464-488 + src/graphics/Blas.cpp:34-39
+ *   RB200SceneDesc               <- descriptor bindings 2..11,13 written in src/Reina.cpp:394-407
+ *   rb200_scene_create           <- Scene::build, src/scene/Scene.cpp:56-125 (BLAS/TLAS build replaced by LBVH->BVH8)
+ *   rb200_render_batch           <- Reina::traceRays, src/Reina.cpp:425-470 (vkCmdTraceRaysKHR(W,H,1))
+ *   rb200_postprocess            <- Reina::applyBloom + applyTonemapping, src/Reina.cpp:472-577
+ *   rb200_read_ldr               <- save(), src/Reina.cpp:19-47 (RGBA8, row 0 = top, stride 4*W)
+ *
+ * Error convention: the reference throws std::runtime_error and main() prints what() (src/main.cpp:6-14).
+ * Nothing is thrown across this boundary: every call returns RB200_OK (0) or a negative status and
+ * rb200_last_error() returns the message of the last failure on the calling thread.
+ *
+ * Threading: a context is not re-entrant (the reference has one queue and one command buffer in flight,
+ * src/Reina.cpp:327-328). Work is enqueued on the context's CUDA stream; rb200_read_* synchronise.
+ */
+#ifndef REINA_B200_H
+#define REINA_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#  define RB200_API __attribute__((visibility("default")))
+#else
+#  define RB200_API
+#endif
+
+/* ------------------------------------------------------------------------------------------------ */
+/* status codes                                                                                      */
+/* ------------------------------------------------------------------------------------------------ */
+enum {
+    RB200_OK = 0,
+    RB200_ERR_INVALID_ARGUMENT = -1,
+    RB200_ERR_CUDA = -2,
+    RB200_ERR_NO_EMITTER = -3,   /* "Scene must have at least one emissive object" (src/scene/Instances.cpp:125-127); only with NEE */
+    RB200_ERR_OUT_OF_MEMORY = -4,
+    RB200_ERR_NO_DEVICE = -5
+};
+
+/* context flags */
+enum {
+    RB200_FLAG_NEE = 1u << 0,        /* enable next-event estimation + MIS (compiled out in the shipped reference:
+                                        shaders/raytrace/raytrace.rgen.glsl:145-146). Off = as-shipped behaviour. */
+    RB200_FLAG_ACCUM_SUM = 1u << 1,  /* keep the SUM of per-batch pixel means instead of the running mean of
+                                        raytrace.rgen.glsl:277-284; used when the sample batches are split over
+                                        several GPUs and reduced once (see rb200_resolve_sum). */
+    RB200_FLAG_COUNT_BVH = 1u << 2   /* counting build: also count wide-node visits and triangle tests per ray */
+};
+
+/* ------------------------------------------------------------------------------------------------ */
+/* PODs shared with the reference (GLSL "scalar" layout == C packed-by-4)                            */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct RB200InstanceProperties {   /* polyglot/raytrace.h:18-41 */
+    uint32_t indicesOffset;          /*   0 */
+    float    albedo[3];              /*   4 */
+    float    emission[3];            /*  16 */
+    uint32_t tbnsIndicesOffset;      /*  28 */
+    uint32_t texIndicesOffset;       /*  32  0xFFFFFFFF = model has no UVs */
+    float    roughness;              /*  36 */
+    float    ior;                    /*  40 */
+    uint32_t interpNormals;          /*  44  C++ bool + 3 pad == GLSL 4-byte bool; only != 0 is tested */
+    float    absorption;             /*  48 */
+    int32_t  textureID;              /*  52 */
+    int32_t  normalMapTexID;         /*  56 */
+    int32_t  bumpMapTexID;           /*  60 */
+    uint32_t cullBackface;           /*  64 */
+    float    anisotropic;            /*  68 */
+    float    subsurface;             /*  72 */
+    float    clearcoatGloss;         /*  76 */
+    float    sheenTint[3];           /*  80 */
+    float    specularTint[3];        /*  92 */
+    float    metallic;               /* 104 */
+    float    clearcoat;              /* 108 */
+    float    specularTransmission;   /* 112 */
+    float    sheen;                  /* 116 */
+} RB200InstanceProperties;           /* 120 bytes */
+
+typedef struct RB200RtPushConsts {   /* polyglot/raytrace.h:43-54 */
+    float    invView[16];            /*   0  column-major (glm) */
+    float    invProjection[16];      /*  64  column-major (glm) */
+    uint32_t sampleBatch;            /* 128  caller owns the sequencing (src/Reina.cpp:431-432) */
+    float    totalEmissiveWeight;    /* 132 */
+    float    focusDist;              /* 136 */
+    float    defocusMultiplier;      /* 140  already divided by 100 (src/Reina.cpp:150) */
+    float    directClamp;            /* 144 */
+    float    indirectClamp;          /* 148  pushed but never read by any shader; kept for layout */
+    uint32_t samplesPerPixel;        /* 152 */
+    uint32_t maxBounces;             /* 156 */
+} RB200RtPushConsts;                 /* 160 bytes */
+
+typedef struct RB200BloomPushConsts {      /* polyglot/bloom.h:4-8 */
+    float radius;      /* percent of the image dimension AND the Gaussian sigma (blurCommon.h.glsl:23-31) */
+    float threshold;
+    float intensity;
+} RB200BloomPushConsts;
+
+typedef struct RB200TonemappingPushConsts { /* polyglot/tonemapping.h:4-6 */
+    float exposure;
+} RB200TonemappingPushConsts;
+
+typedef struct RB200InstanceData {   /* src/scene/Instances.h:15-27, alignas(16) */
+    float    transform[16];          /*   0  column-major object->world */
+    uint32_t materialOffset;         /*  64 */
+    uint32_t cdfRangeStart;          /*  68 */
+    uint32_t cdfRangeEnd;            /*  72  inclusive */
+    uint32_t indexOffset;            /*  76 */
+    float    emission[3];            /*  80 */
+    float    weight;                 /*  92 */
+    float    area;                   /*  96 */
+    uint32_t cullBackface;           /* 100  bool + pad */
+    float    padding[2];             /* 104 */
+} RB200InstanceData;                 /* 112 bytes */
+
+/* One TLAS instance record: what vktools::createTlas hands the driver per instance. */
+typedef struct RB200Instance {
+    float    transform[16];          /* column-major glm::mat4 object->world (Instance::getTransform) */
+    uint32_t instancePropertiesID;   /* gl_InstanceCustomIndexEXT */
+    uint32_t materialIdx;            /* SBT hit-group offset: 0 lambertian, 1 metal, 2 dielectric, 3 disney */
+    uint32_t indexOffset;            /* ModelRange.indexOffset: first entry of this model in `indices` */
+    uint32_t triangleCount;          /* ModelRange.indexCount (already /3, src/scene/Models.cpp:52) */
+} RB200Instance;                     /* 80 bytes */
+
+typedef struct RB200Texture {        /* src/graphics/Image.cpp:43-86: RGBA8 UNORM, no sRGB decode, one mip */
+    const uint8_t* rgba8;            /* row 0 first, 4*width bytes per row, already flipped as the caller wants */
+    uint32_t width;
+    uint32_t height;
+} RB200Texture;
+
+/* The tables the reference binds in Reina::writeDescriptorSets (src/Reina.cpp:394-407). Host pointers.
+ * The library copies everything during rb200_scene_create; the caller may free them afterwards. */
+typedef struct RB200SceneDesc {
+    const float*    vertices;        uint32_t numVertices;       /* binding 2: float4 per vertex (w = 1) */
+    const uint32_t* indices;         uint32_t numIndices;        /* binding 3: global vertex ids */
+    const RB200InstanceProperties* instanceProperties; uint32_t numInstanceProperties; /* binding 4 */
+    const float*    tbns;            uint32_t numTbns;           /* binding 5: 9 floats, column-major [T,B,N] */
+    const uint32_t* tbnIndices;      uint32_t numTbnIndices;     /* binding 6 */
+    const RB200InstanceData* emissiveMetadata; uint32_t numEmissive;  /* binding 7 (may be 0 without NEE) */
+    const float*    cdfTriangles;    uint32_t numCdfTriangles;   /* binding 8 */
+    const float*    cdfInstances;    uint32_t numCdfInstances;   /* binding 9 payload (the {count,total} header
+                                                                    is numCdfInstances / RtPushConsts.totalEmissiveWeight) */
+    const float*    texCoords;       uint32_t numTexCoords;      /* binding 10: float2 per entry */
+    const uint32_t* texIndices;      uint32_t numTexIndices;     /* binding 11 */
+    const RB200Texture* textures;    uint32_t numTextures;       /* binding 13 */
+    const RB200Instance* instances;  uint32_t numInstances;      /* replaces binding 1 (the TLAS) */
+} RB200SceneDesc;
+
+typedef struct RB200Context RB200Context;
+typedef struct RB200Scene   RB200Scene;
+
+/* Counters of the last rb200_render_batch (and cumulative since context creation). */
+typedef struct RB200Stats {
+    uint64_t extendRays;     /* closest-hit rays traced */
+    uint64_t shadowRays;     /* any-hit rays traced */
+    uint64_t paths;          /* camera paths started */
+    uint64_t nodeVisits;     /* wide-node visits   (only with RB200_FLAG_COUNT_BVH) */
+    uint64_t triTests;       /* triangle tests     (only with RB200_FLAG_COUNT_BVH) */
+    uint64_t waves;          /* wavefront iterations executed */
+    uint64_t kernelLaunches; /* kernels launched by the library */
+} RB200Stats;
+
+typedef struct RB200BvhInfo {
+    uint32_t numTriangles;
+    uint32_t numWideNodes;
+    uint32_t maxDepth;
+    uint32_t reserved;
+    uint64_t nodeBytes;
+    uint64_t triangleBytes;
+    uint64_t hash;           /* FNV-1a over the node and triangle arrays: equal across runs/GPUs (deterministic build) */
+    float    buildMs;        /* device time of the build */
+    float    sceneMin[3];
+    float    sceneMax[3];
+} RB200BvhInfo;
+
+/* One primary-ray hit, for parity checks against the oracle (north_star: prim ids equal, t within 1e-5). */
+typedef struct RB200PrimaryHit {
+    float    t;              /* < 0 : miss */
+    float    u, v;           /* barycentric weights of vertex 1 and 2 */
+    uint32_t instance;       /* index into RB200SceneDesc.instances */
+    uint32_t primitive;      /* triangle index within the model (gl_PrimitiveID) */
+} RB200PrimaryHit;
+
+/* ------------------------------------------------------------------------------------------------ */
+/* entry points                                                                                      */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* Library/ABI version (major<<16 | minor). */
+RB200_API uint32_t rb200_version(void);
+
+/* Message of the last error on this thread ("" if none). Never NULL. */
+RB200_API const char* rb200_last_error(void);
+
+/* Create a render context of fixed size on CUDA device `device` (src/Reina.cpp:54-55,76-80: the reference
+ * fixes W x H at construction). `flags` = RB200_FLAG_*. */
+RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, uint32_t flags, RB200Context** out);
+RB200_API int rb200_context_destroy(RB200Context* ctx);
+
+/* Use an externally owned cudaStream_t (e.g. the harness's stream) instead of the context's own. */
+RB200_API int rb200_context_set_stream(RB200Context* ctx, void* cuda_stream);
+
+/* Copy the scene tables to the device and build the acceleration structure (LBVH -> 8-wide compressed BVH).
+ * The scene is immutable afterwards (the reference never updates an acceleration structure). */
+RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* desc, RB200Scene** out);
+RB200_API int rb200_scene_destroy(RB200Scene* scene);
+RB200_API int rb200_scene_bvh_info(const RB200Scene* scene, RB200BvhInfo* out);
+
+/* Trace + shade + accumulate one sample batch (pc->samplesPerPixel samples per pixel, <= pc->maxBounces
+ * segments each). pc->sampleBatch == 0 overwrites the HDR image, > 0 folds into the running average
+ * (raytrace.rgen.glsl:277-284). Asynchronous on the context stream. */
+RB200_API int rb200_render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc);
+
+/* With RB200_FLAG_ACCUM_SUM: turn the accumulated sum of `numBatches` batch means into the mean image. */
+RB200_API int rb200_resolve_sum(RB200Context* ctx, uint32_t numBatches);
+
+/* Bloom (blurX with threshold -> blurY -> combine) and ACES tonemap into the RGBA8 image. */
+RB200_API int rb200_postprocess(RB200Context* ctx, const RB200BloomPushConsts* bloom,
+                                const RB200TonemappingPushConsts* tonemap);
+
+/* Read-back (synchronises the stream). `rgba8`: W*H*4 bytes, row 0 = top. `rgba32f`: W*H*4 floats. */
+RB200_API int rb200_read_ldr(RB200Context* ctx, uint8_t* rgba8);
+RB200_API int rb200_read_hdr(RB200Context* ctx, float* rgba32f);
+/* Replace the HDR accumulation image (resume / post-processing parity on identical input). */
+RB200_API int rb200_write_hdr(RB200Context* ctx, const float* rgba32f);
+/* Device pointer of the float4 HDR accumulation image (for a collective over NVLink issued by the harness). */
+RB200_API int rb200_hdr_device_ptr(RB200Context* ctx, void** out_device_ptr);
+
+/* Primary-ray closest hits for batch `pc->sampleBatch`, first sample of each pixel (W*H records). */
+RB200_API int rb200_trace_primary(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc,
+                                  RB200PrimaryHit* out_hits);
+
+/* Closest-hit / any-hit queries on caller-supplied rays (n rays; origins/directions as xyz triples;
+ * tmax per ray). `any_hit` != 0 -> only hit.t >= 0 / < 0 is meaningful. Used by traversal parity tests
+ * and the traversal micro-benchmark. Host pointers. */
+RB200_API int rb200_trace_rays(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* origins,
+                               const float* directions, const float* tmax, int any_hit, RB200PrimaryHit* out_hits);
+
+RB200_API int rb200_get_stats(RB200Context* ctx, RB200Stats* last_batch, RB200Stats* cumulative);
+RB200_API int rb200_synchronize(RB200Context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REINA_B200_H */

@@ -1,0 +1,129 @@
+"""reina-vk_b200 — B200-native path-tracing core for Reina (AlexanderJCS/reina-vk).
+
+The product is csrc/librb200.so: hand-written sm_100a CUDA kernels (LBVH -> 8-wide BVH builder, wavefront
+extend / shade / shadow tracer, Disney / Lambertian / metal / dielectric shading, accumulate, bloom, tonemap) behind
+the C ABI of include/reina_b200.h. This package is the host-side mirror of the reference's scene layer plus a thin
+ctypes binding; it contains no CPU rendering path and refuses to work without the CUDA library.
+
+Import with importlib (the directory name carries the reference's hyphen):
+    rb = importlib.import_module("reina-vk_b200")
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi, camera, configs, meshes, scene
+from .abi import (RB200_FLAG_ACCUM_SUM, RB200_FLAG_COUNT_BVH, RB200_FLAG_NEE, BloomPushConsts, RB200Error,
+                  RtPushConsts, TonemappingPushConsts, load_library)
+from .scene import Material, ModelData, Scene, SceneTables
+
+__all__ = ["Renderer", "Material", "ModelData", "Scene", "SceneTables", "RtPushConsts", "BloomPushConsts",
+           "TonemappingPushConsts", "RB200_FLAG_NEE", "RB200_FLAG_ACCUM_SUM", "RB200_FLAG_COUNT_BVH", "RB200Error",
+           "abi", "camera", "configs", "meshes", "scene", "load_library"]
+
+
+class _DevicePtr:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class Renderer:
+    """One render context + one scene: the calls Reina's frame loop makes (src/Reina.cpp:296-392) —
+    traceRays() -> applyBloom() -> applyTonemapping() -> save() — against the C ABI."""
+
+    def __init__(self, width, height, tables, flags=0, device=0, stream=None):
+        self.lib = load_library()
+        self.width, self.height, self.flags = width, height, flags
+        self._ctx = C.c_void_p()
+        abi.check(self.lib, self.lib.rb200_context_create(width, height, device, flags, C.byref(self._ctx)))
+        if stream is not None:
+            abi.check(self.lib, self.lib.rb200_context_set_stream(self._ctx, C.c_void_p(stream)))
+        self._scene = C.c_void_p()
+        self.tables = tables
+        desc = tables.desc()
+        try:
+            abi.check(self.lib, self.lib.rb200_scene_create(self._ctx, C.byref(desc), C.byref(self._scene)))
+        except Exception:
+            self.lib.rb200_context_destroy(self._ctx)
+            self._ctx = None
+            raise
+
+    # -- the hot path ------------------------------------------------------------------------------------
+    def render_batch(self, pc):
+        abi.check(self.lib, self.lib.rb200_render_batch(self._ctx, self._scene, C.byref(pc)))
+
+    def resolve_sum(self, num_batches):
+        abi.check(self.lib, self.lib.rb200_resolve_sum(self._ctx, num_batches))
+
+    def postprocess(self, bloom=None, tonemap=None):
+        d = camera.DEFAULTS
+        bloom = bloom or BloomPushConsts(d["bloom_radius"], d["bloom_threshold"], d["bloom_intensity"])
+        tonemap = tonemap or TonemappingPushConsts(d["exposure"])
+        abi.check(self.lib, self.lib.rb200_postprocess(self._ctx, C.byref(bloom), C.byref(tonemap)))
+
+    def read_hdr(self, out=None):
+        out = np.empty((self.height, self.width, 4), np.float32) if out is None else out
+        abi.check(self.lib, self.lib.rb200_read_hdr(self._ctx, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def read_ldr(self, out=None):
+        out = np.empty((self.height, self.width, 4), np.uint8) if out is None else out
+        abi.check(self.lib, self.lib.rb200_read_ldr(self._ctx, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def write_hdr(self, img):
+        img = np.ascontiguousarray(img, np.float32)
+        assert img.shape == (self.height, self.width, 4)
+        abi.check(self.lib, self.lib.rb200_write_hdr(self._ctx, img.ctypes.data_as(C.c_void_p)))
+
+    def hdr_device_array(self):
+        p = C.c_void_p()
+        abi.check(self.lib, self.lib.rb200_hdr_device_ptr(self._ctx, C.byref(p)))
+        return _DevicePtr(p.value, (self.height, self.width, 4))
+
+    # -- parity / measurement helpers --------------------------------------------------------------------
+    def trace_primary(self, pc):
+        hits = np.empty(self.width * self.height, dtype=np.dtype(abi.PrimaryHit))
+        abi.check(self.lib, self.lib.rb200_trace_primary(self._ctx, self._scene, C.byref(pc),
+                                                         hits.ctypes.data_as(C.c_void_p)))
+        return hits
+
+    def trace_rays(self, origins, directions, tmax, any_hit=False):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(tmax, np.float32), (o.shape[0],)), np.float32)
+        hits = np.empty(o.shape[0], dtype=np.dtype(abi.PrimaryHit))
+        abi.check(self.lib, self.lib.rb200_trace_rays(self._ctx, self._scene, o.shape[0], o.ctypes.data_as(C.c_void_p),
+                                                      d.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p),
+                                                      1 if any_hit else 0, hits.ctypes.data_as(C.c_void_p)))
+        return hits
+
+    def bvh_info(self):
+        info = abi.BvhInfo()
+        abi.check(self.lib, self.lib.rb200_scene_bvh_info(self._scene, C.byref(info)))
+        return info.as_dict()
+
+    def stats(self):
+        last, cum = abi.Stats(), abi.Stats()
+        abi.check(self.lib, self.lib.rb200_get_stats(self._ctx, C.byref(last), C.byref(cum)))
+        return last.as_dict(), cum.as_dict()
+
+    def synchronize(self):
+        abi.check(self.lib, self.lib.rb200_synchronize(self._ctx))
+
+    def close(self):
+        if getattr(self, "_scene", None):
+            self.lib.rb200_scene_destroy(self._scene)
+            self._scene = None
+        if getattr(self, "_ctx", None):
+            self.lib.rb200_context_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
