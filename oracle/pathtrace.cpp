@@ -552,7 +552,7 @@ void render_rows(const Scene& s, uint32_t W, uint32_t H, uint32_t flags, const R
                 starting_ray(pc, (float)x, (float)y, (float)W, (float)H, pld.rngState, &o, &d);
                 if (counters) counters->paths++;
                 vec3 c = trace_segments(s, pc, nee, pld, o, d, counters);
-                c = rb_clamp3(c, 0.0f, pc.directClamp);
+                c = rb_clamp3_keepnan(c, 0.0f, pc.directClamp);
                 if (rb_anynan3(c)) continue;
                 actual++;
                 sum = sum + c;

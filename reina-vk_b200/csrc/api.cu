@@ -1,0 +1,304 @@
+// api.cu — the extern "C" boundary declared in include/reina_b200.h.
+#include "context.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+namespace rb200 {
+
+static thread_local std::string g_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+template <class T> static int upload(RB200Scene* sc, const T* host, size_t count, const T** dev, cudaStream_t s) {
+    T* d = nullptr;
+    const size_t bytes = (count ? count : 1) * sizeof(T);
+    RB_CUDA(cudaMalloc((void**)&d, bytes));
+    sc->allocations.push_back(d);
+    if (count) RB_CUDA(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    else RB_CUDA(cudaMemsetAsync(d, 0, bytes, s));
+    *dev = d;
+    return RB200_OK;
+}
+
+template <class T> static int ctx_alloc(RB200Context* c, T** p, size_t count) {
+    RB_CUDA(cudaMalloc((void**)p, (count ? count : 1) * sizeof(T)));
+    c->allocations.push_back(*p);
+    return RB200_OK;
+}
+
+static int validate_desc(const RB200SceneDesc* d) {
+    if (!d->vertices || !d->indices || !d->instanceProperties || !d->instances || d->numInstances == 0) {
+        set_error("scene description lacks vertices / indices / instanceProperties / instances");
+        return RB200_ERR_INVALID_ARGUMENT;
+    }
+    if (!d->tbns || !d->tbnIndices) { set_error("scene description lacks the TBN tables (bindings 5, 6)"); return RB200_ERR_INVALID_ARGUMENT; }
+    for (uint32_t i = 0; i < d->numInstances; i++) {
+        const RB200Instance& in = d->instances[i];
+        if (in.instancePropertiesID >= d->numInstanceProperties) { set_error("instance %u: instancePropertiesID out of range", i); return RB200_ERR_INVALID_ARGUMENT; }
+        if ((uint64_t)in.indexOffset + 3ull * in.triangleCount > d->numIndices) { set_error("instance %u: index range out of bounds", i); return RB200_ERR_INVALID_ARGUMENT; }
+        const RB200InstanceProperties& p = d->instanceProperties[in.instancePropertiesID];
+        if (p.textureID >= (int)d->numTextures || p.normalMapTexID >= (int)d->numTextures || p.bumpMapTexID >= (int)d->numTextures) {
+            set_error("instance %u: texture id out of range", i); return RB200_ERR_INVALID_ARGUMENT;
+        }
+        if (p.bumpMapTexID >= 0) { set_error("instance %u: parallax bump mapping (bumpMapTexID) is not implemented", i); return RB200_ERR_INVALID_ARGUMENT; }
+        if ((uint64_t)p.tbnsIndicesOffset + 3ull * in.triangleCount > d->numTbnIndices) { set_error("instance %u: TBN index range out of bounds", i); return RB200_ERR_INVALID_ARGUMENT; }
+        if (p.texIndicesOffset != 0xFFFFFFFFu && (uint64_t)p.texIndicesOffset + 3ull * in.triangleCount > d->numTexIndices) {
+            set_error("instance %u: texcoord index range out of bounds", i); return RB200_ERR_INVALID_ARGUMENT;
+        }
+    }
+    for (uint32_t i = 0; i < d->numIndices; i++) if (d->indices[i] >= d->numVertices) { set_error("vertex index %u out of range", i); return RB200_ERR_INVALID_ARGUMENT; }
+    for (uint32_t i = 0; i < d->numTbnIndices; i++) if (d->tbnIndices[i] >= d->numTbns) { set_error("TBN index %u out of range", i); return RB200_ERR_INVALID_ARGUMENT; }
+    if (d->numTexCoords) for (uint32_t i = 0; i < d->numTexIndices; i++)
+        if (d->texIndices[i] != 0xFFFFFFFFu && d->texIndices[i] >= d->numTexCoords) { set_error("texcoord index %u out of range", i); return RB200_ERR_INVALID_ARGUMENT; }
+    for (uint32_t i = 0; i < d->numEmissive; i++) {
+        const RB200InstanceData& e = d->emissiveMetadata[i];
+        if (e.cdfRangeEnd >= d->numCdfTriangles || e.cdfRangeStart > e.cdfRangeEnd) { set_error("emissive %u: CDF range out of bounds", i); return RB200_ERR_INVALID_ARGUMENT; }
+    }
+    if (d->numEmissive != d->numCdfInstances) { set_error("numEmissive != numCdfInstances"); return RB200_ERR_INVALID_ARGUMENT; }
+    return RB200_OK;
+}
+
+} // namespace rb200
+
+using namespace rb200;
+
+extern "C" {
+
+RB200_API uint32_t rb200_version(void) { return (1u << 16) | 0u; }
+
+RB200_API const char* rb200_last_error(void) { return g_error.c_str(); }
+
+RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, uint32_t flags, RB200Context** out) {
+    if (!out || width == 0 || height == 0 || (uint64_t)width * height > 0x7FFFFFFFull) { set_error("invalid context size"); return RB200_ERR_INVALID_ARGUMENT; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device available (this library has no CPU path)"); return RB200_ERR_NO_DEVICE; }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(device));
+    RB200Context* c = new RB200Context();
+    c->width = width; c->height = height; c->flags = flags; c->device = device;
+    cudaDeviceProp prop;
+    RB_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->numSMs = prop.multiProcessorCount;
+    RB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->ownStream = true;
+    const size_t N = (size_t)width * height;
+    WaveParams& P = c->wp;
+    P.W = width; P.H = height; P.N = (uint32_t)N; P.flags = flags;
+    int rc;
+#define A(ptr, n) if ((rc = ctx_alloc(c, &(ptr), (n))) != RB200_OK) return rc
+    A(P.rayO, N); A(P.rayD, N); A(P.hit, N); A(P.thr, N); A(P.rad, N); A(P.sum, N); A(P.st, N);
+    A(P.shO, N); A(P.shD, N); A(P.shA, N); A(P.shB, N); A(P.shT, N);
+    A(P.rayQ[0], N); A(P.rayQ[1], N);
+    for (int m = 0; m < 5; m++) A(P.matQ[m], N);
+    A(P.endQ, N); A(P.counters, 2 * CNT_SET); A(P.stats, ST_COUNT); A(c->statsSnap, ST_COUNT);
+    A(P.image, N); A(c->ping, N); A(c->pong, N); A(c->ldr, N);
+#undef A
+    RB_CUDA(cudaMemsetAsync(P.stats, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
+    RB_CUDA(cudaMemsetAsync(c->statsSnap, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
+    RB_CUDA(cudaMemsetAsync(P.image, 0, N * sizeof(float4), c->stream));
+    RB_CUDA(cudaMemsetAsync(c->ldr, 0, N * sizeof(uchar4), c->stream));
+    RB_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return RB200_OK;
+}
+
+RB200_API int rb200_context_destroy(RB200Context* ctx) {
+    if (!ctx) return RB200_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (void* p : ctx->allocations) cudaFree(p);
+    if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RB200_OK;
+}
+
+RB200_API int rb200_context_set_stream(RB200Context* ctx, void* cuda_stream) {
+    if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->ownStream = false;
+    return RB200_OK;
+}
+
+RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB200Scene** out) {
+    if (!ctx || !d || !out) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    int rc = validate_desc(d);
+    if (rc != RB200_OK) return rc;
+    if ((ctx->flags & RB200_FLAG_NEE) && d->numEmissive == 0) {
+        set_error("Scene must have at least one emissive object");   // src/scene/Instances.cpp:125-127
+        return RB200_ERR_NO_EMITTER;
+    }
+    RB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    RB200Scene* sc = new RB200Scene();
+    sc->ctx = ctx;
+    DeviceScene& D = sc->dev;
+#define U(field, host, count) if ((rc = upload(sc, host, (size_t)(count), &D.field, s)) != RB200_OK) { rb200_scene_destroy(sc); return rc; }
+    U(vertices, reinterpret_cast<const float4*>(d->vertices), d->numVertices);
+    U(indices, d->indices, d->numIndices);
+    U(props, d->instanceProperties, d->numInstanceProperties);
+    U(tbns, d->tbns, 9 * (size_t)d->numTbns);
+    U(tbnIndices, d->tbnIndices, d->numTbnIndices);
+    U(emissive, d->emissiveMetadata, d->numEmissive);
+    U(cdfTriangles, d->cdfTriangles, d->numCdfTriangles);
+    U(cdfInstances, d->cdfInstances, d->numCdfInstances);
+    U(texCoords, reinterpret_cast<const float2*>(d->texCoords), d->numTexCoords);
+    U(texIndices, d->texIndices, d->numTexIndices);
+    U(instances, d->instances, d->numInstances);
+#undef U
+    D.numCdfInstances = d->numCdfInstances;
+    D.numInstances = d->numInstances;
+    sc->numEmissive = d->numEmissive;
+    sc->hostInstances.assign(d->instances, d->instances + d->numInstances);
+
+    // textures: RGBA8 UNORM cudaArrays behind texture objects (point sampled; the bilinear REPEAT filter is applied in fp32)
+    std::vector<uint2> sizes;
+    for (uint32_t i = 0; i < d->numTextures; i++) {
+        const RB200Texture& t = d->textures[i];
+        if (!t.rgba8 || t.width == 0 || t.height == 0) { set_error("texture %u is empty", i); rb200_scene_destroy(sc); return RB200_ERR_INVALID_ARGUMENT; }
+        cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr;
+        RB_CUDA(cudaMallocArray(&arr, &fmt, t.width, t.height));
+        sc->texArrays.push_back(arr);
+        RB_CUDA(cudaMemcpy2DToArrayAsync(arr, 0, 0, t.rgba8, (size_t)t.width * 4, (size_t)t.width * 4, t.height, cudaMemcpyHostToDevice, s));
+        cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+        cudaTextureDesc td; memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+        cudaTextureObject_t obj;
+        RB_CUDA(cudaCreateTextureObject(&obj, &rd, &td, nullptr));
+        sc->texObjects.push_back(obj);
+        sizes.push_back(make_uint2(t.width, t.height));
+    }
+    if ((rc = upload(sc, sc->texObjects.data(), sc->texObjects.size(), &D.textures, s)) != RB200_OK) { rb200_scene_destroy(sc); return rc; }
+    if ((rc = upload(sc, sizes.data(), sizes.size(), &D.texSizes, s)) != RB200_OK) { rb200_scene_destroy(sc); return rc; }
+    RB_CUDA(cudaStreamSynchronize(s));   // host staging vectors go out of scope below
+
+    BuildInput bi{D.vertices, D.indices, D.instances, &sc->hostInstances, d->numInstances};
+    rc = build_bvh(bi, s, &sc->bvh, &ctx->launches);
+    if (rc != RB200_OK) { rb200_scene_destroy(sc); return rc; }
+    if (sc->bvh.maxDepth > (uint32_t)36) { set_error("BVH depth %u exceeds the traversal stack", sc->bvh.maxDepth); rb200_scene_destroy(sc); return RB200_ERR_INVALID_ARGUMENT; }
+    D.nodes = sc->bvh.nodes; D.tris = sc->bvh.tris; D.numTris = sc->bvh.numTris;
+    *out = sc;
+    return RB200_OK;
+}
+
+RB200_API int rb200_scene_destroy(RB200Scene* sc) {
+    if (!sc) return RB200_OK;
+    if (sc->ctx) { cudaSetDevice(sc->ctx->device); cudaStreamSynchronize(sc->ctx->stream); }
+    for (cudaTextureObject_t t : sc->texObjects) cudaDestroyTextureObject(t);
+    for (cudaArray_t a : sc->texArrays) cudaFreeArray(a);
+    for (void* p : sc->allocations) cudaFree(p);
+    free_bvh(&sc->bvh);
+    delete sc;
+    return RB200_OK;
+}
+
+RB200_API int rb200_scene_bvh_info(const RB200Scene* scene, RB200BvhInfo* out) {
+    if (!scene || !out) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB200Scene* sc = const_cast<RB200Scene*>(scene);
+    if (!sc->hashValid) {
+        int rc = hash_bvh(sc->bvh, sc->ctx->stream, &sc->hash);
+        if (rc != RB200_OK) return rc;
+        sc->hashValid = true;
+    }
+    memset(out, 0, sizeof(*out));
+    out->numTriangles = sc->bvh.numTris; out->numWideNodes = sc->bvh.numNodes; out->maxDepth = sc->bvh.maxDepth;
+    out->nodeBytes = (uint64_t)sc->bvh.numNodes * sizeof(WideNode);
+    out->triangleBytes = (uint64_t)sc->bvh.numTris * sizeof(TriRecord);
+    out->hash = sc->hash; out->buildMs = sc->bvh.buildMs;
+    for (int a = 0; a < 3; a++) { out->sceneMin[a] = sc->bvh.sceneMin[a]; out->sceneMax[a] = sc->bvh.sceneMax[a]; }
+    return RB200_OK;
+}
+
+RB200_API int rb200_render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc) {
+    if (!ctx || !scene || !pc) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    if (scene->ctx != ctx) { set_error("scene belongs to another context"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
+    return render_batch(ctx, scene, pc);
+}
+
+RB200_API int rb200_resolve_sum(RB200Context* ctx, uint32_t numBatches) {
+    if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
+    return resolve_sum(ctx, numBatches);
+}
+
+RB200_API int rb200_postprocess(RB200Context* ctx, const RB200BloomPushConsts* bloom, const RB200TonemappingPushConsts* tm) {
+    if (!ctx || !bloom || !tm) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    if (!(bloom->radius > 0.0f)) { set_error("bloom radius must be > 0"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
+    return postprocess(ctx, bloom, tm);
+}
+
+RB200_API int rb200_read_ldr(RB200Context* ctx, uint8_t* rgba8) {
+    if (!ctx || !rgba8) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaMemcpyAsync(rgba8, ctx->ldr, (size_t)ctx->width * ctx->height * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RB200_OK;
+}
+
+RB200_API int rb200_read_hdr(RB200Context* ctx, float* rgba32f) {
+    if (!ctx || !rgba32f) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaMemcpyAsync(rgba32f, ctx->wp.image, (size_t)ctx->width * ctx->height * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RB200_OK;
+}
+
+RB200_API int rb200_write_hdr(RB200Context* ctx, const float* rgba32f) {
+    if (!ctx || !rgba32f) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaMemcpyAsync(ctx->wp.image, rgba32f, (size_t)ctx->width * ctx->height * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RB200_OK;
+}
+
+RB200_API int rb200_hdr_device_ptr(RB200Context* ctx, void** out_device_ptr) {
+    if (!ctx || !out_device_ptr) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    *out_device_ptr = ctx->wp.image;
+    return RB200_OK;
+}
+
+RB200_API int rb200_trace_primary(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc, RB200PrimaryHit* out_hits) {
+    if (!ctx || !scene || !pc || !out_hits) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
+    return trace_primary(ctx, scene, pc, out_hits);
+}
+
+RB200_API int rb200_trace_rays(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* origins, const float* directions,
+                               const float* tmax, int any_hit, RB200PrimaryHit* out_hits) {
+    if (!ctx || !scene || (n && (!origins || !directions || !tmax || !out_hits))) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
+    return trace_rays(ctx, scene, n, origins, directions, tmax, any_hit, out_hits);
+}
+
+RB200_API int rb200_get_stats(RB200Context* ctx, RB200Stats* last_batch, RB200Stats* cumulative) {
+    if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
+    unsigned long long now[ST_COUNT], snap[ST_COUNT];
+    RB_CUDA(cudaMemcpyAsync(now, ctx->wp.stats, sizeof(now), cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(cudaMemcpyAsync(snap, ctx->statsSnap, sizeof(snap), cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    RB200Stats& L = ctx->last; RB200Stats& Cm = ctx->cumulative;
+    L.extendRays = now[ST_EXTEND] - snap[ST_EXTEND]; L.shadowRays = now[ST_SHADOW] - snap[ST_SHADOW];
+    L.paths = now[ST_PATHS] - snap[ST_PATHS]; L.nodeVisits = now[ST_NODES] - snap[ST_NODES]; L.triTests = now[ST_TRIS] - snap[ST_TRIS];
+    Cm.extendRays = now[ST_EXTEND]; Cm.shadowRays = now[ST_SHADOW]; Cm.paths = now[ST_PATHS];
+    Cm.nodeVisits = now[ST_NODES]; Cm.triTests = now[ST_TRIS]; Cm.kernelLaunches = ctx->launches;
+    if (last_batch) *last_batch = L;
+    if (cumulative) *cumulative = Cm;
+    return RB200_OK;
+}
+
+RB200_API int rb200_synchronize(RB200Context* ctx) {
+    if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RB200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,89 @@
+// common.cuh — shared declarations of the CUDA library (librb200.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/reina_b200.h"
+#include "rb_math.h"
+#include "rb_vec.h"
+#include "rb_tri.h"
+
+namespace rb200 {
+
+void set_error(const char* fmt, ...);
+
+#define RB_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            rb200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return RB200_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// 8-wide compressed BVH (Ylitie, Karras, Laine 2017 layout): 80-byte nodes, 48-byte triangles
+// ---------------------------------------------------------------------------------------------------
+struct alignas(16) WideNode {
+    float px, py, pz;        // origin of the quantisation grid = node AABB min
+    uint8_t ex, ey, ez;      // biased fp32 exponents of the per-axis grid step
+    uint8_t imask;           // bit s set: slot s holds an internal child
+    uint32_t childBase;      // index of the first internal child (children are contiguous, in slot order)
+    uint32_t triBase;        // index of the first triangle referenced by this node's leaf slots
+    uint8_t meta[8];         // per slot: internal -> (1<<5) | (24+slot); leaf -> (unary count << 5) | tri offset; 0 = empty
+    uint8_t qlox[8], qloy[8];
+    uint8_t qloz[8], qhix[8];
+    uint8_t qhiy[8], qhiz[8];
+};
+static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
+
+// triangle record in leaf order: three float4, w lanes carry ids
+//   v0.w = primitive id within the model, v1.w = instance index, v2.w = global primitive id (tie-break key)
+struct alignas(16) TriRecord { float4 v0, v1, v2; };
+static_assert(sizeof(TriRecord) == 48, "TriRecord must be 48 bytes");
+
+struct Bvh {
+    WideNode* nodes = nullptr;
+    TriRecord* tris = nullptr;
+    uint32_t numNodes = 0, numTris = 0, maxDepth = 0;
+    float buildMs = 0.f;
+    float sceneMin[3] = {0, 0, 0}, sceneMax[3] = {0, 0, 0};
+};
+
+// Scene tables resident in HBM (bindings 2..11, 13 of the reference + the BVH replacing binding 1)
+struct DeviceScene {
+    const float4* vertices;
+    const uint32_t* indices;
+    const RB200InstanceProperties* props;
+    const float* tbns;               // 9 floats per entry
+    const uint32_t* tbnIndices;
+    const RB200InstanceData* emissive;
+    const float* cdfTriangles;
+    const float* cdfInstances;
+    uint32_t numCdfInstances;
+    const float2* texCoords;
+    const uint32_t* texIndices;
+    const RB200Instance* instances;
+    const cudaTextureObject_t* textures;
+    const uint2* texSizes;
+    const WideNode* nodes;
+    const TriRecord* tris;
+    uint32_t numInstances, numTris;
+};
+
+struct BuildInput {
+    const float4* vertices;
+    const uint32_t* indices;
+    const RB200Instance* d_instances;
+    const std::vector<RB200Instance>* h_instances;
+    uint32_t numInstances;
+};
+
+// bvh_build.cu
+int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* launches);
+int hash_bvh(const Bvh& bvh, cudaStream_t stream, uint64_t* hash);
+void free_bvh(Bvh* b);
+
+} // namespace rb200

@@ -1,0 +1,74 @@
+// context.cuh — host-side objects behind the opaque RB200Context / RB200Scene handles.
+#pragma once
+#include "common.cuh"
+
+struct RB200Scene {
+    RB200Context* ctx = nullptr;
+    rb200::DeviceScene dev{};
+    rb200::Bvh bvh{};
+    std::vector<void*> allocations;           // device buffers owned by the scene
+    std::vector<cudaArray_t> texArrays;
+    std::vector<cudaTextureObject_t> texObjects;
+    std::vector<RB200Instance> hostInstances;
+    uint32_t numEmissive = 0;
+    uint64_t hash = 0;
+    bool hashValid = false;
+};
+
+namespace rb200 {
+
+// counters of one wave parity set
+enum { CNT_RAYS = 0, CNT_MAT0 = 1, CNT_MISS = 5, CNT_SHADOW = 6, CNT_END = 7, CNT_SET = 8 };
+// device statistics (unsigned long long each)
+enum { ST_EXTEND = 0, ST_SHADOW = 1, ST_PATHS = 2, ST_NODES = 3, ST_TRIS = 4, ST_COUNT = 8 };
+
+// path flags kept in PathState.st.y (low byte); the traced-segment counter lives in bits 8..31
+enum { F_INSIDE = 1u, F_FIRST = 2u, F_PREVSKIP = 4u };
+
+struct WaveParams {
+    DeviceScene S;
+    RB200RtPushConsts pc;
+    uint32_t W, H, N, flags;
+    float4* rayO;      // xyz origin
+    float4* rayD;      // xyz direction (not necessarily unit)
+    uint4* hit;        // x = bits(b1), y = bits(b2), z = primitive, w = instance
+    float4* thr;       // xyz throughput, w = accumulatedDistance
+    float4* rad;       // xyz radiance of the current path
+    float4* sum;       // xyz summed sample colours of this batch, w = bits(actualSamples)
+    uint4* st;         // x = rng state, y = flags | segments << 8, z = sample index
+    float4 *shO, *shD, *shA, *shB, *shT;   // shadow-ray records (compacted): origin/tmax, dir/slot, D/wNEE, E*wBRDF, throughput
+    uint32_t* rayQ[2];
+    uint32_t* matQ[5]; // 0..3 materials, 4 = miss
+    uint32_t* endQ;
+    uint32_t* counters;            // [2][CNT_SET]
+    unsigned long long* stats;     // [ST_COUNT]
+    float4* image;                 // HDR accumulation image
+};
+
+} // namespace rb200
+
+struct RB200Context {
+    uint32_t width = 0, height = 0, flags = 0;
+    int device = 0;
+    int numSMs = 148;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    rb200::WaveParams wp{};
+    std::vector<void*> allocations;
+    float4 *ping = nullptr, *pong = nullptr;   // bloom work images
+    uchar4* ldr = nullptr;
+    RB200Stats last{}, cumulative{};
+    unsigned long long* statsSnap = nullptr;   // device copy of wp.stats taken at the start of the last batch
+    uint64_t launches = 0;                     // kernels launched by this context (all entry points)
+};
+
+namespace rb200 {
+// wavefront.cu
+int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc);
+int trace_primary(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc, RB200PrimaryHit* out);
+int trace_rays(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* o, const float* d, const float* tmax,
+               int any, RB200PrimaryHit* out);
+int resolve_sum(RB200Context* ctx, uint32_t numBatches);
+// post.cu
+int postprocess(RB200Context* ctx, const RB200BloomPushConsts* bloom, const RB200TonemappingPushConsts* tm);
+} // namespace rb200

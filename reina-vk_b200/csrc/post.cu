@@ -1,0 +1,165 @@
+// post.cu — bloom (thresholded blur X, blur Y) and fused combine + ACES-fitted tonemap.
+//
+// Replaces Reina::applyBloom / applyTonemapping (src/Reina.cpp:472-577), i.e. the compute shaders
+//   shaders/postprocessing/bloom/blurCommon.h.glsl:15-56 (blurX.comp.glsl:7-9 threshold on, blurY.comp.glsl:7-9 off)
+//   shaders/postprocessing/bloom/combine.comp.glsl:15-27
+//   shaders/postprocessing/tonemap/tonemapping.comp.glsl:17-84
+// Reference quirk kept: the Gaussian sigma is the radius *percent* value while the loop spans
+// +-3 * radius% * dimension taps and weightSum accumulates every tap, in or out of the image. Weights underflow
+// to exactly 0 beyond |i| ~ 13.2 sigma (rb_exp flushes below 2^-126), and adding 0-weighted taps changes neither
+// the colour sum nor weightSum, so only the +-R taps with non-zero weight are visited — in the same ascending
+// order as the shader's loop, which keeps the fp32 sums bit-identical to the oracle.
+// Tiles are staged in shared memory with 128-bit loads; thresholded / out-of-image taps are staged as zeros.
+#include "context.cuh"
+
+namespace rb200 {
+
+static constexpr int BX_TILE = 256;      // blur X: pixels of one row per block
+static constexpr int BY_W = 32;          // blur Y: tile width
+static constexpr int BY_H = 128;         // blur Y: tile height (rows per block)
+static constexpr int BY_THREADS = 256;
+
+__device__ __forceinline__ float gauss(float x, float sigma) { return rb_exp(-x * x / (2.0f * sigma * sigma)); }
+
+__global__ void __launch_bounds__(BX_TILE) k_blur_x(const float4* __restrict__ in, float4* __restrict__ out, int W, int H,
+                                                    int R, float sigma, float threshold) {
+    extern __shared__ float4 smem[];
+    float* wts = reinterpret_cast<float*>(smem);              // 2R+1 weights (padded to a multiple of 4 floats)
+    float4* tile = smem + ((2 * R + 1 + 3) / 4);              // BX_TILE + 2R pixels
+    const int y = blockIdx.y;
+    const int x0 = blockIdx.x * BX_TILE;
+    for (int i = threadIdx.x; i <= 2 * R; i += BX_TILE) wts[i] = gauss((float)(i - R), sigma);
+    for (int i = threadIdx.x; i < BX_TILE + 2 * R; i += BX_TILE) {
+        const int x = x0 - R + i;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x >= 0 && x < W) {
+            p = in[(size_t)y * W + x];
+            const float lum = p.x * 0.299f + p.y * 0.587f + p.z * 0.114f;
+            if (lum < threshold) p = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        tile[i] = p;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x >= W) return;
+    float cr = 0.f, cg = 0.f, cb = 0.f, ws = 0.f;
+    for (int i = 0; i <= 2 * R; i++) {
+        const float w = wts[i];
+        const float4 p = tile[threadIdx.x + i];
+        ws += w;
+        cr += p.x * w; cg += p.y * w; cb += p.z * w;
+    }
+    if (ws < 0.0001f) { cr = cg = cb = 0.f; } else { cr /= ws; cg /= ws; cb /= ws; }
+    out[(size_t)y * W + x] = make_float4(cr, cg, cb, 1.f);
+}
+
+__global__ void __launch_bounds__(BY_THREADS) k_blur_y(const float4* __restrict__ in, float4* __restrict__ out, int W, int H,
+                                                       int R, float sigma) {
+    extern __shared__ float4 smem[];
+    float* wts = reinterpret_cast<float*>(smem);
+    float4* tile = smem + ((2 * R + 1 + 3) / 4);              // (BY_H + 2R) rows x BY_W
+    const int x0 = blockIdx.x * BY_W, y0 = blockIdx.y * BY_H;
+    const int tx = threadIdx.x % BY_W, ty = threadIdx.x / BY_W;     // 32 x 8
+    for (int i = threadIdx.x; i <= 2 * R; i += BY_THREADS) wts[i] = gauss((float)(i - R), sigma);
+    const int rows = BY_H + 2 * R;
+    for (int r = ty; r < rows; r += BY_THREADS / BY_W) {
+        const int y = y0 - R + r, x = x0 + tx;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < H && x < W) p = in[(size_t)y * W + x];
+        tile[r * BY_W + tx] = p;
+    }
+    __syncthreads();
+    const int x = x0 + tx;
+    if (x >= W) return;
+    for (int oy = ty; oy < BY_H; oy += BY_THREADS / BY_W) {
+        const int y = y0 + oy;
+        if (y >= H) break;
+        float cr = 0.f, cg = 0.f, cb = 0.f, ws = 0.f;
+        for (int i = 0; i <= 2 * R; i++) {
+            const float w = wts[i];
+            const float4 p = tile[(oy + i) * BY_W + tx];
+            ws += w;
+            cr += p.x * w; cg += p.y * w; cb += p.z * w;
+        }
+        if (ws < 0.0001f) { cr = cg = cb = 0.f; } else { cr /= ws; cg /= ws; cb /= ws; }
+        out[(size_t)y * W + x] = make_float4(cr, cg, cb, 1.f);
+    }
+}
+
+// tonemapping.comp.glsl:34-39
+__device__ __forceinline__ float rrt_odt_fit(float v) {
+    const float a = v * (v + 0.0245786f) - 0.000090537f;
+    const float b = v * (0.983729f * v + 0.4329510f) + 0.238081f;
+    return a / b;
+}
+
+// combine (rt + bloom * intensity) followed by exposure, ACES input matrix, RRT/ODT fit, ACES output matrix, clamp,
+// UNORM8 store. `c * M` in the shader is row-vector times matrix: component j = dot(c, column j).
+__device__ __forceinline__ uint32_t combine_tonemap(const float4 rt, const float4 bl, float intensity, float e) {
+    const rb_v3 hdr = rb_mk3(rt.x + bl.x * intensity, rt.y + bl.y * intensity, rt.z + bl.z * intensity);
+    const rb_v3 c = rb_mk3(hdr.x * e, hdr.y * e, hdr.z * e);
+    rb_v3 a = rb_mk3(rb_dot(c, rb_mk3(0.59719f, 0.35458f, 0.04823f)), rb_dot(c, rb_mk3(0.07600f, 0.90834f, 0.01566f)),
+                     rb_dot(c, rb_mk3(0.02840f, 0.13383f, 0.83777f)));
+    a = rb_mk3(rrt_odt_fit(a.x), rrt_odt_fit(a.y), rrt_odt_fit(a.z));
+    rb_v3 o = rb_mk3(rb_dot(a, rb_mk3(1.60475f, -0.53108f, -0.07367f)), rb_dot(a, rb_mk3(-0.10208f, 1.10813f, -0.00605f)),
+                     rb_dot(a, rb_mk3(-0.00327f, -0.07276f, 1.07602f)));
+    o = rb_clamp3(o, 0.0f, 1.0f);
+    const uint32_t r = (uint32_t)(int)rintf(o.x * 255.0f), g = (uint32_t)(int)rintf(o.y * 255.0f), b = (uint32_t)(int)rintf(o.z * 255.0f);
+    return r | (g << 8) | (b << 16) | (255u << 24);
+}
+
+__global__ void __launch_bounds__(256) k_combine_tonemap(const float4* __restrict__ rt, const float4* __restrict__ bloom,
+                                                         uint32_t* __restrict__ ldr, uint32_t n, float intensity, float exposure) {
+    const float e = rb_exp2(exposure);
+    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (i4 >= n) return;
+    if (i4 + 4u <= n) {
+        uint4 o;
+        o.x = combine_tonemap(rt[i4 + 0], bloom[i4 + 0], intensity, e);
+        o.y = combine_tonemap(rt[i4 + 1], bloom[i4 + 1], intensity, e);
+        o.z = combine_tonemap(rt[i4 + 2], bloom[i4 + 2], intensity, e);
+        o.w = combine_tonemap(rt[i4 + 3], bloom[i4 + 3], intensity, e);
+        *reinterpret_cast<uint4*>(ldr + i4) = o;
+    } else {
+        for (uint32_t i = i4; i < n; i++) ldr[i] = combine_tonemap(rt[i], bloom[i], intensity, e);
+    }
+}
+
+// number of taps on each side with a non-zero weight: the same fp32 expression rb_exp sees, evaluated on the host
+static int effective_radius(int k, float sigma) {
+    int R = 0;
+    for (int i = 0; i <= k; i++) {
+        const float x = (float)i;
+        const float arg = -x * x / (2.0f * sigma * sigma);
+        if (arg < -87.3f) break;
+        R = i;
+    }
+    return R;
+}
+
+int postprocess(RB200Context* ctx, const RB200BloomPushConsts* bloom, const RB200TonemappingPushConsts* tm) {
+    const int W = (int)ctx->width, H = (int)ctx->height;
+    cudaStream_t s = ctx->stream;
+    const float4* rt = ctx->wp.image;
+    // blurCommon.h.glsl:23-24
+    const float radiusPxX = (float)W * bloom->radius / 100.0f, radiusPxY = (float)H * bloom->radius / 100.0f;
+    const int kX = (int)(radiusPxX * 3.0f + 0.5f), kY = (int)(radiusPxY * 3.0f + 0.5f);
+    const int RX = effective_radius(kX, bloom->radius), RY = effective_radius(kY, bloom->radius);
+
+    const size_t smX = (size_t)(((2 * RX + 1 + 3) / 4) + BX_TILE + 2 * RX) * sizeof(float4);
+    const size_t smY = (size_t)(((2 * RY + 1 + 3) / 4) + (BY_H + 2 * RY) * BY_W) * sizeof(float4);
+    if (smX > 200 * 1024 || smY > 200 * 1024) { set_error("bloom radius too large for the shared-memory tiles"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaFuncSetAttribute(k_blur_x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smX));
+    RB_CUDA(cudaFuncSetAttribute(k_blur_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smY));
+    dim3 gx((W + BX_TILE - 1) / BX_TILE, H), gy((W + BY_W - 1) / BY_W, (H + BY_H - 1) / BY_H);
+    k_blur_x<<<gx, BX_TILE, smX, s>>>(rt, ctx->ping, W, H, RX, bloom->radius, bloom->threshold);
+    k_blur_y<<<gy, BY_THREADS, smY, s>>>(ctx->ping, ctx->pong, W, H, RY, bloom->radius);
+    const uint32_t n = (uint32_t)W * (uint32_t)H;
+    k_combine_tonemap<<<(n / 4 + 256) / 256, 256, 0, s>>>(rt, ctx->pong, reinterpret_cast<uint32_t*>(ctx->ldr), n,
+                                                          bloom->intensity, tm->exposure);
+    ctx->launches += 3;
+    RB_CUDA(cudaGetLastError());
+    return RB200_OK;
+}
+
+} // namespace rb200

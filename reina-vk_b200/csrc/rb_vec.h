@@ -56,6 +56,12 @@ RB_HD rb_v3 rb_mix3v(rb_v3 a, rb_v3 b, rb_v3 t) {
 RB_HD rb_v3 rb_clamp3(rb_v3 a, float lo, float hi) {
     return rb_mk3(rb_clamp(a.x, lo, hi), rb_clamp(a.y, lo, hi), rb_clamp(a.z, lo, hi));
 }
+/* Per-sample clamp of raytrace.rgen.glsl:266. GLSL leaves clamp(NaN) undefined; the reference relies on NaN
+ * samples surviving it so that the isnan() test at :268-271 can drop them, so NaN is passed through here. */
+RB_HD float rb_clamp_keepnan(float x, float lo, float hi) { return x != x ? x : fminf(fmaxf(x, lo), hi); }
+RB_HD rb_v3 rb_clamp3_keepnan(rb_v3 a, float lo, float hi) {
+    return rb_mk3(rb_clamp_keepnan(a.x, lo, hi), rb_clamp_keepnan(a.y, lo, hi), rb_clamp_keepnan(a.z, lo, hi));
+}
 RB_HD bool rb_anynan3(rb_v3 a) { return a.x != a.x || a.y != a.y || a.z != a.z; }
 
 /* M * v (columns c0..c2) */

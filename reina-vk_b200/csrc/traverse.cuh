@@ -1,0 +1,149 @@
+// traverse.cuh — stack-based traversal of the 8-wide compressed BVH (closest hit and any hit).
+//
+// Software replacement for the fixed-function traversal behind traceRayEXT in the reference
+// (shaders/raytrace/raytrace.rgen.glsl:110-122: opaque, tmin 0, tmax 1e4, closest hit;
+//  shaders/raytrace/nee.h.glsl:126-144: opaque | terminateOnFirstHit | skipClosestHit, tmax dist - 0.001).
+//
+// One ray per thread. A stack entry is a "group": (base index, bit mask). Node groups carry the hit mask of the
+// internal children of one wide node in bits 24..31 (already permuted by the ray octant so that the highest set bit
+// is the nearest child) and the node's imask in bits 0..7; triangle groups carry up to 24 triangle bits.
+// Child boxes are tested directly in the quantised grid: t = q * (2^e / d) + (p - o) / d, one fma per plane.
+// Every plane is pushed outwards by a slack that bounds the fp32 rounding of that expression and the few-ulp
+// acceptance band of the watertight triangle test, so a triangle the test accepts is never culled by a box.
+// Closest-hit rule: smallest t, ties -> smallest global primitive id; boxes are culled with <= so ties are visited.
+#pragma once
+#include "common.cuh"
+
+namespace rb200 {
+
+struct RayHit {
+    float t, b1, b2;
+    uint32_t tri;      // index into Bvh::tris, 0xFFFFFFFF = miss
+    uint32_t gid;
+};
+
+static constexpr int TRAV_STACK = 40;
+
+// per byte: 0xFF if bit 7 is set, else 0x00 (prmt's sign-replicate mode; __byte_perm only honours 3 selector bits)
+__device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0, 0x0000ba98;" : "=r"(r) : "r"(x));
+    return r;
+}
+__device__ __forceinline__ float byte_f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
+
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ void traverse(const WideNode* __restrict__ nodes, const TriRecord* __restrict__ tris,
+                                         const rb_v3 o, const rb_v3 d, const float tmax, RayHit& best,
+                                         uint32_t& nodeVisits, uint32_t& triTests, const bool dbg = false) {
+    best.t = tmax; best.b1 = 0.f; best.b2 = 0.f; best.tri = 0xFFFFFFFFu; best.gid = 0xFFFFFFFFu;
+
+    const float ooeps = 8.2718061e-25f;   // 2^-80: keeps 1/d finite for axis-parallel rays (box tests only)
+    const float idx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+    const float idy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+    const float idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+    const uint32_t oct_inv = (idx < 0.f ? 0u : 4u) | (idy < 0.f ? 0u : 2u) | (idz < 0.f ? 0u : 1u);
+    const uint32_t oct_inv4 = oct_inv * 0x01010101u;
+    const rb_ray_shear shear = rb_ray_prepare(d);
+
+    uint2 stack[TRAV_STACK];
+    int sp = 0;
+    uint2 ngroup = make_uint2(0u, 0x80000000u);
+    uint2 tgroup = make_uint2(0u, 0u);
+
+    for (;;) {
+        if (ngroup.y > 0x00FFFFFFu) {
+            const uint32_t hits = ngroup.y;
+            const uint32_t bitIndex = 31u - (uint32_t)__clz(hits);
+            const uint32_t base = ngroup.x;
+            ngroup.y &= ~(1u << bitIndex);
+            if (ngroup.y > 0x00FFFFFFu) { stack[sp++] = ngroup; }
+            const uint32_t slot = (bitIndex - 24u) ^ oct_inv;
+            const uint32_t rel = __popc(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
+            const float4* np = reinterpret_cast<const float4*>(nodes + (base + rel));
+            const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            if (COUNT) nodeVisits++;
+            if (dbg) printf("node %u (base %u rel %u slot %u bit %u) hits %08x p=(%g %g %g) e=%08x childBase %u triBase %u meta %08x %08x\n", base + rel, base, rel, slot, bitIndex, hits, n0.x, n0.y, n0.z, __float_as_uint(n0.w), __float_as_uint(n1.x), __float_as_uint(n1.y), __float_as_uint(n1.z), __float_as_uint(n1.w));
+
+            const uint32_t eim = __float_as_uint(n0.w);
+            const float sx = __uint_as_float((eim & 0xFFu) << 23) * idx;
+            const float sy = __uint_as_float(((eim >> 8) & 0xFFu) << 23) * idy;
+            const float sz = __uint_as_float(((eim >> 16) & 0xFFu) << 23) * idz;
+            const float cx = (n0.x - o.x) * idx, cy = (n0.y - o.y) * idy, cz = (n0.z - o.z) * idz;
+            const float eps = 9.5367431640625e-07f;   // 2^-20
+            const float kx = eps * fmaf(255.0f, fabsf(sx), fabsf(cx));
+            const float ky = eps * fmaf(255.0f, fabsf(sy), fabsf(cy));
+            const float kz = eps * fmaf(255.0f, fabsf(sz), fabsf(cz));
+            const float cnx = cx - kx, cfx = cx + kx, cny = cy - ky, cfy = cy + ky, cnz = cz - kz, cfz = cz + kz;
+
+            ngroup.x = __float_as_uint(n1.x);
+            tgroup.x = __float_as_uint(n1.y);
+            uint32_t hitmask = 0u;
+            const float tcur = best.t;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const uint32_t meta4 = __float_as_uint(half == 0 ? n1.z : n1.w);
+                const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                const uint32_t innerMask4 = sign_extend_s8x4(isInner4 << 3);
+                const uint32_t bitIndex4 = (meta4 ^ (oct_inv4 & innerMask4)) & 0x1F1F1F1Fu;
+                const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+                const uint32_t qlox = __float_as_uint(half == 0 ? n2.x : n2.y);
+                const uint32_t qloy = __float_as_uint(half == 0 ? n2.z : n2.w);
+                const uint32_t qloz = __float_as_uint(half == 0 ? n3.x : n3.y);
+                const uint32_t qhix = __float_as_uint(half == 0 ? n3.z : n3.w);
+                const uint32_t qhiy = __float_as_uint(half == 0 ? n4.x : n4.y);
+                const uint32_t qhiz = __float_as_uint(half == 0 ? n4.z : n4.w);
+                const uint32_t nx = idx < 0.f ? qhix : qlox, fx = idx < 0.f ? qlox : qhix;
+                const uint32_t ny = idy < 0.f ? qhiy : qloy, fy = idy < 0.f ? qloy : qhiy;
+                const uint32_t nz = idz < 0.f ? qhiz : qloz, fz = idz < 0.f ? qloz : qhiz;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float t0x = fmaf(byte_f(nx, j), sx, cnx), t1x = fmaf(byte_f(fx, j), sx, cfx);
+                    const float t0y = fmaf(byte_f(ny, j), sy, cny), t1y = fmaf(byte_f(fy, j), sy, cfy);
+                    const float t0z = fmaf(byte_f(nz, j), sz, cnz), t1z = fmaf(byte_f(fz, j), sz, cfz);
+                    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+                    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tcur));
+                    if (dbg) printf("   child %d: x[%g %g] y[%g %g] z[%g %g] tn %g tf %g q=(%u..%u, %u..%u, %u..%u)\n", half * 4 + j, t0x, t1x, t0y, t1y, t0z, t1z, tn, tf, (qlox >> (8 * j)) & 255, (qhix >> (8 * j)) & 255, (qloy >> (8 * j)) & 255, (qhiy >> (8 * j)) & 255, (qloz >> (8 * j)) & 255, (qhiz >> (8 * j)) & 255);
+                    if (tn <= tf) {
+                        const uint32_t cb = (childBits4 >> (8 * j)) & 0xFFu;
+                        const uint32_t bi = (bitIndex4 >> (8 * j)) & 0xFFu;
+                        hitmask |= cb << bi;
+                    }
+                }
+            }
+            if (dbg) printf("   hitmask %08x\n", hitmask);
+            ngroup.y = (hitmask & 0xFF000000u) | (eim >> 24);
+            tgroup.y = hitmask & 0x00FFFFFFu;
+        } else {
+            tgroup = ngroup;
+            ngroup = make_uint2(0u, 0u);
+        }
+
+        while (tgroup.y != 0u) {
+            const uint32_t ti = 31u - (uint32_t)__clz(tgroup.y);
+            tgroup.y &= ~(1u << ti);
+            const uint32_t triIdx = tgroup.x + ti;
+            const float4* tp = reinterpret_cast<const float4*>(tris + triIdx);
+            const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            if (COUNT) triTests++;
+            float t, b1, b2;
+            if (dbg) printf("   tri %u gid %u\n", triIdx, __float_as_uint(c.w));
+            if (rb_tri_intersect(o, shear, rb_mk3(a.x, a.y, a.z), rb_mk3(b.x, b.y, b.z), rb_mk3(c.x, c.y, c.z), &t, &b1, &b2)) {
+                if (t > 0.0f && t < tmax) {
+                    const uint32_t gid = __float_as_uint(c.w);
+                    if (ANY) { best.t = t; best.tri = triIdx; best.gid = gid; return; }
+                    if (t < best.t || (t == best.t && gid < best.gid)) {
+                        best.t = t; best.b1 = b1; best.b2 = b2; best.tri = triIdx; best.gid = gid;
+                    }
+                }
+            }
+        }
+
+        if (ngroup.y <= 0x00FFFFFFu) {
+            if (sp == 0) break;
+            ngroup = stack[--sp];
+        }
+    }
+}
+
+} // namespace rb200

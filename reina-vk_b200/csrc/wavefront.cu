@@ -1,0 +1,619 @@
+// wavefront.cu — the wavefront path tracer: generate -> { extend -> shade_<material> / miss -> shadow -> finish }*.
+//
+// Replaces the single vkCmdTraceRaysKHR(W,H,1) of Reina::traceRays (src/Reina.cpp:425-470) whose raygen shader
+// runs the whole bounce loop per pixel (shaders/raytrace/raytrace.rgen.glsl:97-184, 250-285). Here a pixel owns a
+// path-state slot; every wave advances all live paths by one segment:
+//   extend        closest hit for every queued ray, then the slot is binned by the hit instance's material
+//   shade_<m>     the closest-hit shader of material m + the raygen bookkeeping that follows traceRayEXT
+//   miss          sky radiance, path ends
+//   shadow        any-hit visibility for this wave's light samples, folds the NEE term into the path radiance
+//   finish        end of path: clamp, drop NaN, add to the pixel's batch sum; next sample of the pixel re-uses the
+//                 slot (the RNG stream is one per (pixel, batch) and continues across samples, rgen.glsl:259,264),
+//                 the last sample writes the running average into the HDR image (rgen.glsl:277-284)
+// Queues are compacted with warp-aggregated atomics; their order is irrelevant to the result because every slot is
+// private to its pixel. Draw order of the RNG follows SURVEY.md Appendix A exactly.
+#include "context.cuh"
+#include "traverse.cuh"
+#include "shade.cuh"
+
+namespace rb200 {
+
+static constexpr int BLOCK = 256;
+
+// ---------------------------------------------------------------------------------------------------
+// queue helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void queue_push(uint32_t* __restrict__ q, uint32_t* counter, uint32_t value) {
+    const uint32_t active = __activemask();
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs(active) - 1;
+    const uint32_t rank = __popc(active & ((1u << lane) - 1u));
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(active));
+    base = __shfl_sync(active, base, leader);
+    q[base + rank] = value;
+}
+
+__device__ __forceinline__ uint32_t queue_reserve(uint32_t* counter) {
+    const uint32_t active = __activemask();
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs(active) - 1;
+    const uint32_t rank = __popc(active & ((1u << lane) - 1u));
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(active));
+    base = __shfl_sync(active, base, leader);
+    return base + rank;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// camera (raytrace.rgen.glsl:34-41, 194-247)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void m4_mul_v4(const float* m, float v0, float v1, float v2, float v3, float out[4]) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) out[r] = m[r] * v0 + m[4 + r] * v1 + m[8 + r] * v2 + m[12 + r] * v3;
+}
+
+__device__ void starting_ray(const RB200RtPushConsts& pc, float px, float py, float resx, float resy, uint32_t& rng,
+                             rb_v3& origin, rb_v3& dir) {
+    // randomGaussian (:34-41)
+    const float u1 = rb_max(1e-5f, rb_random(&rng));
+    const float u2 = rb_random(&rng);
+    const float r = sqrtf(-2.0f * rb_log(u1));
+    const float theta = (2.0f * RB_PI) * u2;
+    float sn, cs; rb_sincos(theta, &sn, &cs);
+    const float cx = px + 0.5f + 0.375f * (r * cs);
+    const float cy = py + 0.5f + 0.375f * (r * sn);
+    const float ndcx = (cx / resx) * 2.0f - 1.0f;
+    const float ndcy = -((cy / resy) * 2.0f - 1.0f);
+    float view[4]; m4_mul_v4(pc.invProjection, ndcx, ndcy, -1.0f, 1.0f, view);
+    const rb_v3 viewDir = rb_normalize(rb_mk3(view[0] / view[3], view[1] / view[3], view[2] / view[3]));
+    float wd[4]; m4_mul_v4(pc.invView, viewDir.x, viewDir.y, viewDir.z, 0.0f, wd);
+    const rb_v3 rayDirection = rb_normalize(rb_mk3(wd[0], wd[1], wd[2]));
+    const rb_v3 camPos = rb_mk3(pc.invView[12], pc.invView[13], pc.invView[14]);
+    const rb_v3 focalPoint = camPos + rayDirection * pc.focusDist;
+    // randomInUnitHexagon works on a COPY of the state (:194): the draws are not consumed
+    uint32_t tmp = rng;
+    const float sqrt3 = 1.73205080757f;
+    float hx, hy;
+    do {
+        hx = 2.0f * rb_random(&tmp) - 1.0f;
+        hy = (rb_random(&tmp) - 0.5f) * sqrt3;
+    } while (fabsf(hy) > (sqrt3 * 0.5f) || (sqrt3 * fabsf(hx) + fabsf(hy)) > sqrt3);
+    const float lx = hx * pc.defocusMultiplier, ly = hy * pc.defocusMultiplier;
+    const rb_v3 right = rb_normalize(rb_mk3(pc.invView[0], pc.invView[1], pc.invView[2]));
+    const rb_v3 up = rb_normalize(rb_mk3(pc.invView[4], pc.invView[5], pc.invView[6]));
+    const rb_v3 offset = right * lx + up * ly;
+    origin = camPos + offset;
+    dir = rb_normalize(focalPoint - origin);
+}
+
+// start (or restart) the path of a slot: traceSegments' locals (rgen.glsl:98-104)
+__device__ __forceinline__ void begin_path(const WaveParams& P, uint32_t slot, uint32_t& rng, uint32_t sampleIdx) {
+    const uint32_t x = slot % P.W, y = slot / P.W;
+    rb_v3 o, d;
+    starting_ray(P.pc, (float)x, (float)y, (float)P.W, (float)P.H, rng, o, d);
+    P.rayO[slot] = make_float4(o.x, o.y, o.z, 0.f);
+    P.rayD[slot] = make_float4(d.x, d.y, d.z, 0.f);
+    P.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);     // throughput 1, accumulatedDistance 0 (documented deviation)
+    P.rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    P.st[slot] = make_uint4(rng, F_FIRST, sampleIdx, 0u);
+}
+
+__global__ void __launch_bounds__(BLOCK) k_generate(WaveParams P) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot == 0) atomicAdd(&P.stats[ST_PATHS], (unsigned long long)P.N);
+    if (slot >= P.N) return;
+    const uint32_t x = slot % P.W, y = slot / P.W;
+    uint32_t rng = (P.pc.sampleBatch * P.H + y) * P.W + x;       // rgen.glsl:259
+    P.sum[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+    begin_path(P, slot, rng, 0u);
+    P.rayQ[0][slot] = slot;
+    if (slot == 0) P.counters[CNT_RAYS] = P.N;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// extend
+// ---------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(BLOCK) k_extend(WaveParams P, int parity) {
+    uint32_t* cnt = P.counters + parity * CNT_SET;
+    const uint32_t n = cnt[CNT_RAYS];
+    const uint32_t* __restrict__ q = P.rayQ[parity];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_EXTEND], (unsigned long long)n);
+    uint32_t nodeVisits = 0, triTests = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = q[i];
+        const float4 o = P.rayO[slot], d = P.rayD[slot];
+        RayHit h;
+        traverse<false, COUNT>(P.S.nodes, P.S.tris, rb_mk3(o.x, o.y, o.z), rb_mk3(d.x, d.y, d.z), 10000.0f, h, nodeVisits, triTests);
+        uint32_t bin = 4;
+        if (h.tri != 0xFFFFFFFFu) {
+            const float4* tp = reinterpret_cast<const float4*>(P.S.tris + h.tri);
+            const uint32_t prim = __float_as_uint(__ldg(tp).w);
+            const uint32_t inst = __float_as_uint(__ldg(tp + 1).w);
+            P.hit[slot] = make_uint4(__float_as_uint(h.b1), __float_as_uint(h.b2), prim, inst);
+            const uint32_t m = __ldg(&P.S.instances[inst].materialIdx);
+            bin = m > 3u ? 3u : m;
+        }
+        // bin the slot by material (warp-aggregated per bin)
+#pragma unroll
+        for (uint32_t b = 0; b < 5; b++)
+            if (bin == b) queue_push(P.matQ[b], &cnt[CNT_MAT0 + b], slot);
+    }
+    if (COUNT) {
+        atomicAdd(&P.stats[ST_NODES], (unsigned long long)nodeVisits);
+        atomicAdd(&P.stats[ST_TRIS], (unsigned long long)triTests);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// shade
+// ---------------------------------------------------------------------------------------------------
+struct ShadeOut {
+    rb_v3 color, albedo, emission, newO, newD, normal;
+    float pdf;
+    bool skip, inside;
+};
+
+// closestHitCommon.h.glsl:185-193
+__device__ __forceinline__ void do_skip(ShadeOut& o, const Surf& s, rb_v3 rayDir) {
+    o.newO = rb_offset_along_normal(s.worldPosition, -s.worldNormal);
+    o.newD = rayDir;
+    o.skip = true;
+}
+
+// cull / UV wrap + range skip / normal map / albedo texture with stochastic alpha
+// (lambertian.rchit.glsl:15-56, metal.rchit.glsl:12-48, disney.rchit.glsl:40-84)
+template <bool UV_RANGE_SKIP>
+__device__ __forceinline__ bool surface_prologue(const WaveParams& P, const RB200InstanceProperties* props, const Surf& s,
+                                                 const rb_m3* tbn, rb_v3 rayDir, uint32_t& rng, ShadeOut& o, rb_v3& wn, rb_v3& col) {
+    if (__ldg(&props->cullBackface) != 0u && !s.frontFace) { do_skip(o, s, rayDir); return false; }
+    const rb_v2 uv = rb_mk2(rb_fract_mod1(s.uv.x), rb_fract_mod1(s.uv.y));
+    if (UV_RANGE_SKIP && (uv.x < 0.0f || uv.x > 1.0f || uv.y < 0.0f || uv.y > 1.0f)) { do_skip(o, s, rayDir); return false; }
+    wn = s.worldNormal;
+    const int nm = __ldg(&props->normalMapTexID);
+    if (nm >= 0) {
+        const float4 t = sample_texture(P.S, nm, uv);
+        rb_v3 tn = rb_mk3(t.x * 2.0f - 1.0f, t.y * 2.0f - 1.0f, t.z * 2.0f - 1.0f);
+        tn.y = tn.y * -1.0f;
+        wn = rb_normalize(rb_m3_mul(*tbn, tn));
+    }
+    col = ld3(props->albedo);
+    const int tid = __ldg(&props->textureID);
+    if (tid >= 0) {
+        const float4 t = sample_texture(P.S, tid, uv);
+        if (t.w < 0.999f && rb_random(&rng) > t.w) { do_skip(o, s, rayDir); return false; }
+        col = col * rb_mk3(t.x, t.y, t.z);
+    }
+    return true;
+}
+
+template <int MAT>
+__device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t slot, uint32_t* cnt, uint32_t* cntNext, int parity) {
+    const float4 ro4 = P.rayO[slot], rd4 = P.rayD[slot];
+    const rb_v3 rayOrigin = rb_mk3(ro4.x, ro4.y, ro4.z), rayDir = rb_mk3(rd4.x, rd4.y, rd4.z);
+    uint4 st = P.st[slot];
+    float4 T4 = P.thr[slot];
+    rb_v3 T = rb_mk3(T4.x, T4.y, T4.z);
+    float accDist = T4.w;
+    uint32_t rng = st.x;
+    uint32_t flags = st.y & 0xFFu;
+    uint32_t segments = st.y >> 8;
+    const bool nee = (P.flags & RB200_FLAG_NEE) != 0u;
+
+    if (MAT == 4) {
+        // miss shader + raygen's sky branch (rgen.glsl:138-141): radiance += sky * throughput, path ends
+        const float4 L4 = P.rad[slot];
+        const rb_v3 L = rb_mk3(L4.x, L4.y, L4.z) + sky_color(rayDir) * T;
+        P.rad[slot] = make_float4(L.x, L.y, L.z, 0.f);
+        queue_push(P.endQ, &cnt[CNT_END], slot);
+        return;
+    }
+
+    const uint4 h = P.hit[slot];
+    const float a1 = __uint_as_float(h.x), a2 = __uint_as_float(h.y);
+    const RB200Instance* inst = &P.S.instances[h.w];
+    const RB200InstanceProperties* props = &P.S.props[__ldg(&inst->instancePropertiesID)];
+    const bool prevInside = (flags & F_INSIDE) != 0u;
+
+    Surf s;
+    const bool hasNormalMap = __ldg(&props->normalMapTexID) >= 0;
+    if (MAT == 3) hit_info<true>(P.S, inst, props, h.z, a1, a2, rayDir, s);
+    else if (hasNormalMap) hit_info<true>(P.S, inst, props, h.z, a1, a2, rayDir, s);
+    else hit_info<false>(P.S, inst, props, h.z, a1, a2, rayDir, s);
+
+    ShadeOut o;
+    o.skip = false; o.pdf = 0.0f; o.inside = prevInside;
+    o.color = o.albedo = o.emission = o.normal = rb_splat3(0.0f);
+    bool didRefract = false;   // always false when NEE sees it (disney.rchit.glsl:187)
+    rb_v3 wn, col;
+
+    if (MAT == 0) {           // lambertian.rchit.glsl:11-78
+        if (surface_prologue<true>(P, props, s, &s.tbn, rayDir, rng, o, wn, col)) {
+            o.color = col; o.albedo = col; o.emission = ld3(props->emission);
+            o.newO = rb_offset_along_normal(s.worldPosition, s.worldNormalGeometry);
+            o.newD = diffuse_reflection(wn, rng);
+            o.inside = false; o.normal = wn;
+            o.pdf = rb_max(rb_dot(wn, o.newD), 0.0f) / RB_PI;
+            accDist = 0.0f;
+        }
+    } else if (MAT == 1) {    // metal.rchit.glsl:7-70
+        if (surface_prologue<false>(P, props, s, &s.tbn, rayDir, rng, o, wn, col)) {
+            o.color = col; o.albedo = col; o.emission = ld3(props->emission);
+            o.newO = rb_offset_along_normal(s.worldPosition, s.worldNormalGeometry);
+            o.newD = fuzzy_reflection(rayDir, wn, __ldg(&props->roughness), rng);
+            o.inside = false; o.normal = wn; o.pdf = 0.0f;
+            accDist = 0.0f;
+        }
+    } else if (MAT == 2) {    // dielectric.rchit.glsl:40-113
+        const float ior = __ldg(&props->ior), rough = __ldg(&props->roughness);
+        const float ri = s.frontFace ? 1.0f / ior : ior;
+        const rb_v3 unitDir = rb_normalize(rayDir);
+        const float cosTheta = rb_min(rb_dot(-unitDir, s.worldNormal), 1.0f);
+        const float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
+        const bool cannotRefract = ri * sinTheta > 1.0f;
+        const float reflectivity = schlick(cosTheta, ri);
+        const rb_v2 uv = rb_mk2(rb_fract_mod1(s.uv.x), rb_fract_mod1(s.uv.y));
+        rb_v3 albedo = ld3(props->albedo);
+        const int tid = __ldg(&props->textureID);
+        if (tid >= 0) { const float4 t = sample_texture(P.S, tid, uv); albedo = albedo * rb_mk3(t.x, t.y, t.z); }
+        wn = s.worldNormal;
+        if (hasNormalMap) {
+            const float4 t = sample_texture(P.S, __ldg(&props->normalMapTexID), uv);
+            rb_v3 tn = rb_mk3(t.x * 2.0f - 1.0f, t.y * 2.0f - 1.0f, t.z * 2.0f - 1.0f);
+            tn.y = tn.y * -1.0f;
+            wn = rb_normalize(rb_m3_mul(s.tbn, tn));
+        }
+        if (cannotRefract || reflectivity > rb_random(&rng)) {
+            o.newD = fuzzy_reflection(unitDir, wn, rough, rng);
+            o.color = rb_splat3(1.0f);
+            o.newO = rb_offset_along_normal(s.worldPosition, s.worldNormalGeometry);
+        } else {
+            o.inside = s.frontFace;
+            const rb_v3 refr = rb_refract(unitDir, wn, ri);
+            o.newD = refr + random_unit_vec(rng) * rough;
+            o.color = albedo;
+            o.newO = offset_for_dielectric(s.worldPosition, s.worldNormalGeometry, unitDir);
+        }
+        if (prevInside) accDist += rb_length(s.worldPosition - rayOrigin);
+        else accDist += 0.0f;
+        if (prevInside && !o.inside) {     // leaving the medium: Beer's law in metres (:89-100)
+            const float a = rb_exp(-__ldg(&props->absorption) * accDist);
+            o.color = rb_splat3(1.0f) * a;
+            o.color = o.color * albedo;
+            accDist = 0.0f;
+        }
+        o.albedo = o.color; o.emission = ld3(props->emission); o.normal = wn; o.pdf = 0.0f;
+    } else {                  // disney.rchit.glsl:36-198
+        if (surface_prologue<true>(P, props, s, &s.tbn, rayDir, rng, o, wn, col)) {
+            const float ior = __ldg(&props->ior);
+            const float eta = s.frontFace ? 1.0f / ior : ior;
+            const DisneyP dp = load_disney(props, col, eta);
+            bool choseGlass = false;
+            const rb_v3 wi = -rayDir;     // not normalised, as in the reference
+            const rb_v3 wo = disney_sample(s.tbn, dp, wn, wi, &didRefract, &choseGlass, rng);
+            const rb_v3 hv = rb_normalize(wo + wi);
+            float pdf;
+            const rb_v3 f = disney_eval(s.tbn, dp, didRefract, wn, wi, wo, hv, &pdf);
+            const float cosI = rb_max(rb_dot(wn, wo), 0.0f);
+            o.color = (f * cosI) / pdf;
+            o.albedo = col; o.pdf = pdf; o.emission = ld3(props->emission);
+            o.newO = offset_for_dielectric(s.worldPosition, s.worldNormalGeometry, wo);
+            o.newD = wo; o.normal = wn; o.inside = choseGlass;
+            if (o.inside) accDist += rb_length(s.worldPosition - rayOrigin);
+            else accDist = 0.0f;
+        }
+    }
+
+    // ---- what raygen does after traceRayEXT returns (rgen.glsl:124-181) ----
+    P.rayO[slot] = make_float4(o.newO.x, o.newO.y, o.newO.z, 0.f);
+    P.rayD[slot] = make_float4(o.newD.x, o.newD.y, o.newD.z, 0.f);
+    const bool leftDielectric = !o.inside && prevInside;
+    segments += 1u;
+    uint32_t newFlags = (flags & (F_FIRST | F_PREVSKIP)) | (o.inside ? F_INSIDE : 0u);
+    if (!o.skip) {
+        if (!o.inside) {
+            const rb_v3 indirect = o.emission;
+            const bool skipNEE = !nee || (MAT != 0 && MAT != 3);
+            if (skipNEE) {
+                const float4 L4 = P.rad[slot];
+                const rb_v3 combined = rb_splat3(0.0f) * 0.0f + indirect * 1.0f;
+                const rb_v3 L = rb_mk3(L4.x, L4.y, L4.z) + combined * T;
+                P.rad[slot] = make_float4(L.x, L.y, L.z, 0.f);
+            } else {
+                // directLight (rgen.glsl:43-95) up to the visibility test, which the shadow stage resolves
+                const LightSample target = random_emissive_point(P.S, P.pc.totalEmissiveWeight, rng);
+                const rb_v3 toLight = target.point - o.newO;
+                const rb_v3 direction = rb_normalize(toLight);
+                const float dist = rb_length(toLight);
+                const float pdfNEE = target.pdf * dist * dist / rb_max(rb_dot(target.normal, -direction), 0.0001f);
+                rb_v3 brdf;
+                if (MAT == 0) {
+                    brdf = o.albedo / RB_PI;
+                } else {
+                    const rb_v3 wi = -rayDir;
+                    const rb_v3 hv = rb_normalize(direction + wi);
+                    const DisneyP dp = load_disney(props, o.albedo, 0.0f);     // pld.eta was overwritten with 0
+                    float ignorePdf;
+                    brdf = disney_eval(s.tbn, dp, false, o.normal, wi, direction, hv, &ignorePdf);
+                }
+                float cosThetai = rb_dot(o.normal, direction);
+                cosThetai = target.cullBackface ? rb_max(cosThetai, 0.0f) : fabsf(cosThetai);
+                float geomNum = rb_dot(target.normal, -direction);
+                geomNum = target.cullBackface ? rb_max(geomNum, 0.0f) : fabsf(geomNum);
+                const float geom = geomNum / (dist * dist);
+                const rb_v3 D = (((target.emission * brdf) * cosThetai) * geom) / target.pdf;
+                const float pdfBRDF = o.pdf;
+                float wNEE, wBRDF;
+                if ((flags & F_FIRST) || (flags & F_PREVSKIP) || leftDielectric) { wNEE = 1.0f; wBRDF = 1.0f; }
+                else if (segments == P.pc.maxBounces) { wNEE = 0.0f; wBRDF = pdfBRDF * pdfBRDF / (pdfBRDF * pdfBRDF + pdfNEE * pdfNEE); }
+                else {
+                    wNEE = pdfNEE * pdfNEE / (pdfNEE * pdfNEE + pdfBRDF * pdfBRDF);
+                    wBRDF = pdfBRDF * pdfBRDF / (pdfBRDF * pdfBRDF + pdfNEE * pdfNEE);
+                }
+                const rb_v3 Bv = indirect * wBRDF;
+                const uint32_t k = queue_reserve(&cnt[CNT_SHADOW]);
+                P.shO[k] = make_float4(o.newO.x, o.newO.y, o.newO.z, dist - 0.001f);
+                P.shD[k] = make_float4(direction.x, direction.y, direction.z, __uint_as_float(slot));
+                P.shA[k] = make_float4(D.x, D.y, D.z, wNEE);
+                P.shB[k] = make_float4(Bv.x, Bv.y, Bv.z, 0.f);
+                P.shT[k] = make_float4(T.x, T.y, T.z, 0.f);
+            }
+            if (skipNEE) newFlags |= F_PREVSKIP; else newFlags &= ~F_PREVSKIP;
+            T = T * o.color;
+        }
+        newFlags &= ~F_FIRST;
+    }
+    P.thr[slot] = make_float4(T.x, T.y, T.z, accDist);
+    P.st[slot] = make_uint4(rng, newFlags | (segments << 8), st.z, st.w);
+    if (segments < P.pc.maxBounces) queue_push(P.rayQ[parity ^ 1], &cntNext[CNT_RAYS], slot);
+    else queue_push(P.endQ, &cnt[CNT_END], slot);
+}
+
+template <int MAT>
+__global__ void __launch_bounds__(BLOCK) k_shade(WaveParams P, int parity) {
+    uint32_t* cnt = P.counters + parity * CNT_SET;
+    uint32_t* cntNext = P.counters + (parity ^ 1) * CNT_SET;
+    const uint32_t n = cnt[CNT_MAT0 + MAT];
+    const uint32_t* __restrict__ q = P.matQ[MAT];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        shade_slot<MAT>(P, q[i], cnt, cntNext, parity);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// shadow: shadowRayOccluded (nee.h.glsl:126-144) + the radiance update of rgen.glsl:174-177
+// ---------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(BLOCK) k_shadow(WaveParams P, int parity) {
+    uint32_t* cnt = P.counters + parity * CNT_SET;
+    const uint32_t n = cnt[CNT_SHADOW];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_SHADOW], (unsigned long long)n);
+    uint32_t nodeVisits = 0, triTests = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o = P.shO[i], d = P.shD[i];
+        RayHit h;
+        traverse<true, COUNT>(P.S.nodes, P.S.tris, rb_mk3(o.x, o.y, o.z), rb_mk3(d.x, d.y, d.z), o.w, h, nodeVisits, triTests);
+        const bool occluded = h.tri != 0xFFFFFFFFu;
+        const float4 A = P.shA[i], B = P.shB[i], T = P.shT[i];
+        const uint32_t slot = __float_as_uint(d.w);
+        const rb_v3 direct = occluded ? rb_splat3(0.0f) : rb_mk3(A.x, A.y, A.z);
+        const rb_v3 combined = direct * A.w + rb_mk3(B.x, B.y, B.z);
+        const float4 L4 = P.rad[slot];
+        const rb_v3 L = rb_mk3(L4.x, L4.y, L4.z) + combined * rb_mk3(T.x, T.y, T.z);
+        P.rad[slot] = make_float4(L.x, L.y, L.z, 0.f);
+    }
+    if (COUNT) {
+        atomicAdd(&P.stats[ST_NODES], (unsigned long long)nodeVisits);
+        atomicAdd(&P.stats[ST_TRIS], (unsigned long long)triTests);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// finish: end of a path (rgen.glsl:264-284)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_finish(WaveParams P, int parity) {
+    uint32_t* cnt = P.counters + parity * CNT_SET;
+    uint32_t* cntNext = P.counters + (parity ^ 1) * CNT_SET;
+    const uint32_t n = cnt[CNT_END];
+    uint32_t started = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = P.endQ[i];
+        const float4 L4 = P.rad[slot];
+        const rb_v3 c = rb_clamp3_keepnan(rb_mk3(L4.x, L4.y, L4.z), 0.0f, P.pc.directClamp);
+        float4 s4 = P.sum[slot];
+        uint32_t actual = __float_as_uint(s4.w);
+        if (!rb_anynan3(c)) { actual += 1u; s4.x += c.x; s4.y += c.y; s4.z += c.z; }
+        uint4 st = P.st[slot];
+        const uint32_t sampleIdx = st.z + 1u;
+        if (sampleIdx < P.pc.samplesPerPixel) {
+            P.sum[slot] = make_float4(s4.x, s4.y, s4.z, __uint_as_float(actual));
+            uint32_t rng = st.x;
+            begin_path(P, slot, rng, sampleIdx);
+            started++;
+            queue_push(P.rayQ[parity ^ 1], &cntNext[CNT_RAYS], slot);
+        } else {
+            float4* px = &P.image[slot];
+            if (actual == 0u) {
+                // documented deviation: the reference writes 0/0 and poisons the pixel; batch 0 writes black,
+                // later batches keep the previous value, sum mode adds nothing
+                if (!(P.flags & RB200_FLAG_ACCUM_SUM) && P.pc.sampleBatch == 0u) *px = make_float4(0.f, 0.f, 0.f, 1.f);
+            } else {
+                rb_v3 fin = rb_mk3(s4.x, s4.y, s4.z) / (float)actual;
+                if (P.flags & RB200_FLAG_ACCUM_SUM) {
+                    const float4 prev = *px;
+                    *px = make_float4(prev.x + fin.x, prev.y + fin.y, prev.z + fin.z, 1.f);
+                } else {
+                    if (P.pc.sampleBatch > 0u) {
+                        const float4 prev = *px;
+                        fin = (rb_mk3(prev.x, prev.y, prev.z) * (float)P.pc.sampleBatch + fin) / (float)(P.pc.sampleBatch + 1u);
+                    }
+                    *px = make_float4(fin.x, fin.y, fin.z, 1.f);
+                }
+            }
+        }
+    }
+    if (started) atomicAdd(&P.stats[ST_PATHS], (unsigned long long)started);
+}
+
+__global__ void k_resolve_sum(float4* image, uint32_t n, float inv) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 v = image[i];
+    image[i] = make_float4(v.x * inv, v.y * inv, v.z * inv, 1.f);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+template <class K> static int persistent_grid(K kernel, int numSMs) {
+    int perSM = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, BLOCK, 0) != cudaSuccess || perSM < 1) perSM = 1;
+    return numSMs * perSM;
+}
+
+int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc) {
+    WaveParams& P = ctx->wp;
+    if (pc->samplesPerPixel == 0 || pc->maxBounces == 0) { set_error("samplesPerPixel and maxBounces must be > 0"); return RB200_ERR_INVALID_ARGUMENT; }
+    if ((ctx->flags & RB200_FLAG_NEE) && scene->numEmissive == 0) {
+        set_error("Scene must have at least one emissive object");   // src/scene/Instances.cpp:125-127
+        return RB200_ERR_NO_EMITTER;
+    }
+    P.S = scene->dev;
+    P.pc = *pc;
+    cudaStream_t s = ctx->stream;
+    const bool count = (ctx->flags & RB200_FLAG_COUNT_BVH) != 0;
+
+    static int gExtend = 0, gExtendC = 0, gShadow = 0, gShadowC = 0, gShade[5] = {0, 0, 0, 0, 0}, gFinish = 0;
+    if (!gExtend) {
+        gExtend = persistent_grid(k_extend<false>, ctx->numSMs);
+        gExtendC = persistent_grid(k_extend<true>, ctx->numSMs);
+        gShadow = persistent_grid(k_shadow<false>, ctx->numSMs);
+        gShadowC = persistent_grid(k_shadow<true>, ctx->numSMs);
+        gShade[0] = persistent_grid(k_shade<0>, ctx->numSMs);
+        gShade[1] = persistent_grid(k_shade<1>, ctx->numSMs);
+        gShade[2] = persistent_grid(k_shade<2>, ctx->numSMs);
+        gShade[3] = persistent_grid(k_shade<3>, ctx->numSMs);
+        gShade[4] = persistent_grid(k_shade<4>, ctx->numSMs);
+        gFinish = persistent_grid(k_finish, ctx->numSMs);
+    }
+
+    // snapshot of the cumulative device counters at batch start (device-to-device: no host synchronisation here;
+    // rb200_get_stats resolves "last batch" = cumulative - snapshot after synchronising)
+    RB_CUDA(cudaMemcpyAsync(ctx->statsSnap, P.stats, ST_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+    RB_CUDA(cudaMemsetAsync(P.counters, 0, 2 * CNT_SET * sizeof(uint32_t), s));
+    uint64_t nl = 0;
+    k_generate<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(P); nl++;
+    const uint32_t maxWaves = pc->samplesPerPixel * pc->maxBounces;
+    for (uint32_t w = 0; w < maxWaves; w++) {
+        const int p = (int)(w & 1u);
+        RB_CUDA(cudaMemsetAsync(P.counters + (p ^ 1) * CNT_SET, 0, CNT_SET * sizeof(uint32_t), s));
+        if (count) k_extend<true><<<gExtendC, BLOCK, 0, s>>>(P, p); else k_extend<false><<<gExtend, BLOCK, 0, s>>>(P, p);
+        k_shade<4><<<gShade[4], BLOCK, 0, s>>>(P, p);
+        k_shade<0><<<gShade[0], BLOCK, 0, s>>>(P, p);
+        k_shade<1><<<gShade[1], BLOCK, 0, s>>>(P, p);
+        k_shade<2><<<gShade[2], BLOCK, 0, s>>>(P, p);
+        k_shade<3><<<gShade[3], BLOCK, 0, s>>>(P, p);
+        if (ctx->flags & RB200_FLAG_NEE) {
+            if (count) k_shadow<true><<<gShadowC, BLOCK, 0, s>>>(P, p); else k_shadow<false><<<gShadow, BLOCK, 0, s>>>(P, p);
+            nl++;
+        }
+        k_finish<<<gFinish, BLOCK, 0, s>>>(P, p);
+        nl += 7;
+    }
+    RB_CUDA(cudaGetLastError());
+    ctx->last.waves = maxWaves;
+    ctx->last.kernelLaunches = nl;
+    ctx->cumulative.waves += maxWaves;
+    ctx->launches += nl;
+    return RB200_OK;
+}
+
+int resolve_sum(RB200Context* ctx, uint32_t numBatches) {
+    if (numBatches == 0) { set_error("numBatches must be > 0"); return RB200_ERR_INVALID_ARGUMENT; }
+    WaveParams& P = ctx->wp;
+    k_resolve_sum<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, ctx->stream>>>(P.image, P.N, 1.0f / (float)numBatches);
+    ctx->launches++;
+    RB_CUDA(cudaGetLastError());
+    return RB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// parity / measurement entry points: plain closest-hit and any-hit queries
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_primary_rays(WaveParams P, float4* o, float4* d) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= P.N) return;
+    const uint32_t x = slot % P.W, y = slot / P.W;
+    uint32_t rng = (P.pc.sampleBatch * P.H + y) * P.W + x;
+    rb_v3 ro, rd;
+    starting_ray(P.pc, (float)x, (float)y, (float)P.W, (float)P.H, rng, ro, rd);
+    o[slot] = make_float4(ro.x, ro.y, ro.z, 10000.0f);
+    d[slot] = make_float4(rd.x, rd.y, rd.z, 0.f);
+}
+
+__device__ int g_dbgRay = -1;
+
+template <bool ANY>
+__global__ void __launch_bounds__(BLOCK) k_trace_query(const WideNode* nodes, const TriRecord* tris, uint32_t n,
+                                                       const float4* __restrict__ o, const float4* __restrict__ d,
+                                                       RB200PrimaryHit* __restrict__ out) {
+    uint32_t nv = 0, tt = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 ro = o[i], rd = d[i];
+        RayHit h;
+        traverse<ANY, false>(nodes, tris, rb_mk3(ro.x, ro.y, ro.z), rb_mk3(rd.x, rd.y, rd.z), ro.w, h, nv, tt, (int)i == g_dbgRay);
+        RB200PrimaryHit r;
+        r.u = h.b1; r.v = h.b2;
+        if (h.tri != 0xFFFFFFFFu) {
+            const float4* tp = reinterpret_cast<const float4*>(tris + h.tri);
+            r.t = h.t;
+            r.primitive = __float_as_uint(__ldg(tp).w);
+            r.instance = __float_as_uint(__ldg(tp + 1).w);
+        } else { r.t = -1.0f; r.u = r.v = 0.f; r.primitive = r.instance = 0xFFFFFFFFu; }
+        out[i] = r;
+    }
+}
+
+static int run_query(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float4* dO, const float4* dD, int any,
+                     RB200PrimaryHit* out) {
+    RB200PrimaryHit* dOut;
+    RB_CUDA(cudaMalloc(&dOut, (size_t)n * sizeof(RB200PrimaryHit)));
+    const int grid = (int)std::min<uint64_t>((n + BLOCK - 1) / BLOCK, (uint64_t)ctx->numSMs * 8);
+    if (const char* e = getenv("RB200_DEBUG_RAY")) { int v = atoi(e); cudaMemcpyToSymbol(g_dbgRay, &v, sizeof(int)); }
+    if (any) k_trace_query<true><<<grid, BLOCK, 0, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut);
+    else k_trace_query<false><<<grid, BLOCK, 0, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut);
+    ctx->launches++;
+    RB_CUDA(cudaGetLastError());
+    RB_CUDA(cudaMemcpyAsync(out, dOut, (size_t)n * sizeof(RB200PrimaryHit), cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dOut);
+    return RB200_OK;
+}
+
+int trace_primary(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc, RB200PrimaryHit* out) {
+    WaveParams& P = ctx->wp;
+    P.S = scene->dev; P.pc = *pc;
+    k_primary_rays<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, ctx->stream>>>(P, P.shO, P.shD);
+    ctx->launches++;
+    return run_query(ctx, scene, P.N, P.shO, P.shD, 0, out);
+}
+
+int trace_rays(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* o, const float* d, const float* tmax,
+               int any, RB200PrimaryHit* out) {
+    if (n == 0) return RB200_OK;
+    std::vector<float4> ho(n), hd(n);
+    for (uint32_t i = 0; i < n; i++) {
+        ho[i] = make_float4(o[3 * i], o[3 * i + 1], o[3 * i + 2], tmax[i]);
+        hd[i] = make_float4(d[3 * i], d[3 * i + 1], d[3 * i + 2], 0.f);
+    }
+    float4 *dO, *dD;
+    RB_CUDA(cudaMalloc(&dO, (size_t)n * sizeof(float4)));
+    RB_CUDA(cudaMalloc(&dD, (size_t)n * sizeof(float4)));
+    RB_CUDA(cudaMemcpyAsync(dO, ho.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(cudaMemcpyAsync(dD, hd.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = run_query(ctx, scene, n, dO, dD, any, out);
+    cudaFree(dO); cudaFree(dD);
+    return rc;
+}
+
+} // namespace rb200
