@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 path-tracing core.
+
+Metric (BASELINE.json): Mrays/s (primary + bounce + shadow rays actually traced, counted by device counters) on the
+Stanford-Dragon-class scene (procedural stand-in, 871,414 triangles, Disney BSDF, NEE + MIS) at 1920x1080.
+One "step" = one rb200_render_batch call = one sample batch of the whole frame (samples_per_pixel = 8 and
+max_bounces = 16, the reference's config/config.toml defaults) — i.e. one vkCmdTraceRaysKHR(W,H,1) of the reference.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA arm (under torchrun for N > 1)
+  python bench.py --impl reference [--steps K] [--warmup W]      the reference's algorithm on the host cores (oracle)
+
+Multi-GPU: sample split — rank r renders batches r, r+N, ... with the unmodified seed formula into a
+local SUM image; one NCCL reduce of the float4 images to rank 0 closes the timed region. Weak scaling: every rank
+renders K batches.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, SPP, BOUNCES = 1920, 1080, 8, 16
+METRIC = "Mrays/s (primary+bounce+shadow), Stanford Dragon stand-in 1080p"
+
+
+def build_workload(rb, small=False):
+    if small:   # debugging aid only (RB200_BENCH_SMALL=1); never used for reported numbers
+        return rb.configs.dragon(480, 270, n_along=1500, n_ring=16, samples_per_pixel=SPP, max_bounces=BOUNCES)
+    return rb.configs.dragon(WIDTH, HEIGHT, samples_per_pixel=SPP, max_bounces=BOUNCES)
+
+
+def config_dict(wl, extra=None):
+    d = {"workload": "C3 dragon stand-in (torus-knot tube + value-noise displacement), Disney BSDF, NEE+MIS, showroom + light panel",
+         "triangles": wl.tables.num_triangles(), "width": wl.width, "height": wl.height,
+         "samples_per_pixel_per_step": SPP, "max_bounces": BOUNCES,
+         "l2_policy": "inputs larger than L2: every wave sweeps the 2.07M-slot path state (~0.6 GB); the ~55 MB BVH is "
+                      "meant to stay L2-resident"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1])); mx.append(float(f[2]))
+                for n, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(rb, wl, seconds_hint=20.0):
+    """Oracle (CPU restatement of the reference's shaders) on all host cores, bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    sw, sh = 480, 270
+    osc = ol.OracleScene(wl.tables)
+    pc = wl.push_constants(0, samples_per_pixel=1)
+    # same camera, reduced resolution
+    from importlib import import_module
+    cam = import_module("reina-vk_b200").camera
+    kw = dict(wl.pc_kwargs); kw["samples_per_pixel"] = 1
+    rays, t_total, b = 0, 0.0, 0
+    while t_total < seconds_hint and b < 64:
+        pc = cam.push_constants(sw, sh, total_emissive_weight=wl.tables.totalEmissiveWeight, sample_batch=b, **kw)
+        t0 = time.time()
+        _, cnt = osc.render_batch(sw, sh, rb.RB200_FLAG_NEE, pc)
+        t_total += time.time() - t0
+        rays += cnt["extendRays"] + cnt["shadowRays"]
+        b += 1
+    osc.close()
+    return {"value": rays / t_total / 1e6, "unit": "Mrays/s", "cores": ol.NTHREADS, "kind": "port",
+            "sample": f"same scene and camera at {sw}x{sh}, 1 spp x {b} batches, {BOUNCES} bounces, NEE on "
+                      f"({rays} rays in {t_total:.1f} s)"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own algorithm for this path on the host cores. The reference itself (Vulkan
+    RT + GLSL) cannot be built or run in this image (no Vulkan loader / ICD / glslc), so this arm times the oracle —
+    its line-by-line CPU restatement — with every host thread."""
+    if rank != 0:
+        return 0
+    rb = importlib.import_module("reina-vk_b200")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    wl = build_workload(rb, small=bool(os.environ.get("RB200_BENCH_SMALL")))
+    sw, sh = 480, 270
+    kw = dict(wl.pc_kwargs); kw["samples_per_pixel"] = 1
+    osc = ol.OracleScene(wl.tables)
+
+    def step(b):
+        pc = rb.camera.push_constants(sw, sh, total_emissive_weight=wl.tables.totalEmissiveWeight, sample_batch=b, **kw)
+        _, cnt = osc.render_batch(sw, sh, rb.RB200_FLAG_NEE, pc)
+        return cnt["extendRays"] + cnt["shadowRays"]
+    for w in range(args.warmup):
+        step(w)
+    t0 = time.time()
+    rays = sum(step(args.warmup + k) for k in range(args.steps))
+    dt = time.time() - t0
+    val = rays / dt / 1e6
+    sample = f"each step = one 1-spp batch of the same scene/camera at {sw}x{sh} ({BOUNCES} bounces, NEE on)"
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": config_dict(wl, {"reference_sample": sample}),
+           "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": ol.NTHREADS, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: reina-vk_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    rb = importlib.import_module("reina-vk_b200")
+    wl = build_workload(rb, small=bool(os.environ.get("RB200_BENCH_SMALL")))
+    stream = torch.cuda.Stream()
+    flags = rb.RB200_FLAG_NEE | (rb.RB200_FLAG_ACCUM_SUM if world > 1 else 0)
+    t0 = time.time()
+    r = rb.Renderer(wl.width, wl.height, wl.tables, flags=flags, device=local_rank, stream=stream.cuda_stream)
+    r.synchronize()
+    scene_create_s = time.time() - t0
+    bvh = r.bvh_info()
+    hdr_t = torch.as_tensor(r.hdr_device_array(), device=f"cuda:{local_rank}") if world > 1 else None
+
+    def batch_index(i):       # rank r renders batches r, r + N, r + 2N, ...
+        return rank + i * world
+
+    K, Wm = args.steps, args.warmup
+    with torch.cuda.stream(stream):
+        for i in range(Wm):
+            r.render_batch(wl.push_constants(batch_index(i)))
+        if world > 1:
+            dist.reduce(hdr_t.clone(), dst=0, op=dist.ReduceOp.SUM)      # warm NCCL up, result discarded
+        r.synchronize()
+        _, cum0 = r.stats()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for i in range(K):
+            r.render_batch(wl.push_constants(batch_index(Wm + i)))
+        if world > 1:
+            dist.reduce(hdr_t, dst=0, op=dist.ReduceOp.SUM)              # the one collective of the path
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = ev0.elapsed_time(ev1)
+        clocks = sampler.stop() if rank == 0 else None
+        _, cum1 = r.stats()
+    rays = (cum1["extendRays"] - cum0["extendRays"]) + (cum1["shadowRays"] - cum0["shadowRays"])
+    launches = cum1["kernelLaunches"] - cum0["kernelLaunches"]
+    if world > 1:
+        t = torch.tensor([ms], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        c = torch.tensor([rays, launches], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        rays, launches = int(c[0].item()), int(c[1].item())
+    value = rays / (ms * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers: push constants in, bloom + tonemap, RGBA8 frame out ----
+    ldr_host = np.empty((wl.height, wl.width, 4), np.uint8)
+    with torch.cuda.stream(stream):
+        r.synchronize()
+        _, c0 = r.stats()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(K):
+            r.render_batch(wl.push_constants(batch_index(Wm + K + i)))
+            r.postprocess()
+            r.read_ldr(ldr_host)          # device -> host copy of the frame, synchronises
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_e2e = e0.elapsed_time(e1)
+        _, c1 = r.stats()
+    rays_e2e = (c1["extendRays"] - c0["extendRays"]) + (c1["shadowRays"] - c0["shadowRays"])
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+        c = torch.tensor([rays_e2e], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        rays_e2e = int(c[0].item())
+    e2e = {"value": rays_e2e / (ms_e2e * 1e-3) / 1e6, "unit": "Mrays/s",
+           "h2d_bytes_per_step": C.sizeof(rb.abi.RtPushConsts) + C.sizeof(rb.abi.BloomPushConsts) + C.sizeof(rb.abi.TonemappingPushConsts),
+           "d2h_bytes_per_step": int(ldr_host.nbytes), "ms_per_step": ms_e2e / K,
+           "note": "per step: rb200_render_batch(host push constants) + rb200_postprocess + rb200_read_ldr(host RGBA8 frame); "
+                   "scene upload + BVH build happen once (scene_create_s)"}
+    r.close()
+
+    out = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
+           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": config_dict(wl, {"parallelism": f"sample-split x{world}", "nee": True}),
+           "spp_per_s": SPP * K * world / (ms * 1e-3), "rays_per_step": rays / K / world,
+           "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+           "bvh": {k: bvh[k] for k in ("numTriangles", "numWideNodes", "maxDepth", "nodeBytes", "triangleBytes", "buildMs")},
+           "scene_create_s": scene_create_s}
+
+    if rank == 0 and world == 1 and not args.no_roofline:
+        out["roofline"] = roofline(rb, wl, local_rank, stream)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(rb, wl)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def roofline(rb, wl, device, stream):
+    """Dominant kernel = k_extend (closest-hit traversal). Algorithmic bytes per ray:
+    80 * N_node + 48 * N_tri + 32 (ray in) + 16 (hit out), N_node / N_tri measured by a counting build of the same kernel
+    on the same batch; time = sum of the kernel's launch durations (CUDA events on the launching stream)."""
+    peak, peak_src = measured_peak_hbm()
+    res = {"bound": "hbm", "kernel": "k_extend", "unit": "GB/s", "peak": peak, "peak_source": peak_src}
+    pc = wl.push_constants(1000)
+    # timing pass (events around every kernel; no counters)
+    rt = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE | rb.RB200_FLAG_TIME_KERNELS, device=device,
+                     stream=stream.cuda_stream)
+    for _ in range(2):
+        rt.render_batch(pc)
+    kt = rt.kernel_times()
+    last_t, _ = rt.stats()
+    rt.close()
+    # counting pass
+    rc = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE | rb.RB200_FLAG_COUNT_BVH, device=device,
+                     stream=stream.cuda_stream)
+    rc.render_batch(pc)
+    last_c, _ = rc.stats()
+    rc.close()
+    n_rays = last_c["extendRays"] + last_c["shadowRays"]
+    n_node = last_c["nodeVisits"] / n_rays
+    n_tri = last_c["triTests"] / n_rays
+    bytes_per_ray = 80.0 * n_node + 48.0 * n_tri + 32.0 + 16.0
+    ext_bytes = bytes_per_ray * last_t["extendRays"]
+    achieved = ext_bytes / (kt["extendMs"] * 1e-3) / 1e9
+    total_ms = kt["generateMs"] + kt["extendMs"] + sum(kt["shadeMs"]) + kt["shadowMs"] + kt["finishMs"]
+    traffic = None
+    try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if present
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["k_extend_dram_bytes_per_launch"]
+    except Exception:
+        pass
+    res.update({"achieved": achieved, "frac": achieved / peak, "traffic": traffic,
+                "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri,
+                "extend_rays_per_batch": last_t["extendRays"], "extend_launches": kt["extendLaunches"],
+                "extend_ms_per_batch": kt["extendMs"], "avg_launch_ms": kt["extendMs"] / max(1, kt["extendLaunches"]),
+                "extend_mrays_s": last_t["extendRays"] / (kt["extendMs"] * 1e-3) / 1e6,
+                "shadow_mrays_s": (last_t["shadowRays"] / (kt["shadowMs"] * 1e-3) / 1e6) if kt["shadowMs"] > 0 else None,
+                "kernel_ms_per_batch": {"generate": kt["generateMs"], "extend": kt["extendMs"], "shade_lambertian": kt["shadeMs"][0],
+                                        "shade_metal": kt["shadeMs"][1], "shade_dielectric": kt["shadeMs"][2],
+                                        "shade_disney": kt["shadeMs"][3], "miss": kt["shadeMs"][4], "shadow": kt["shadowMs"],
+                                        "finish": kt["finishMs"]},
+                "extend_share_of_step": kt["extendMs"] / total_ms if total_ms > 0 else None,
+                "note": "BVH traversal is an L2-resident pointer chase: the fraction is algorithmic bytes over the measured "
+                        "HBM copy bandwidth, the only bandwidth peak MEASURED_PEAKS.json provides"})
+    return res
+
+
+if __name__ == "__main__":
+    sys.exit(main())

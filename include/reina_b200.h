@@ -62,7 +62,9 @@ enum {
     RB200_FLAG_ACCUM_SUM = 1u << 1,  /* keep the SUM of per-batch pixel means instead of the running mean of
                                         raytrace.rgen.glsl:277-284; used when the sample batches are split over
                                         several GPUs and reduced once (see rb200_resolve_sum). */
-    RB200_FLAG_COUNT_BVH = 1u << 2   /* counting build: also count wide-node visits and triangle tests per ray */
+    RB200_FLAG_COUNT_BVH = 1u << 2,  /* counting build: also count wide-node visits and triangle tests per ray */
+    RB200_FLAG_TIME_KERNELS = 1u << 3 /* bracket every kernel of rb200_render_batch with CUDA events (per-class device
+                                        times for the roofline report; serialises nothing but adds event overhead) */
 };
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -176,6 +178,12 @@ typedef struct RB200Stats {
     uint64_t kernelLaunches; /* kernels launched by the library */
 } RB200Stats;
 
+/* Device time per kernel class of the last rb200_render_batch (needs RB200_FLAG_TIME_KERNELS). */
+typedef struct RB200KernelTimes {
+    float    generateMs, extendMs, shadeMs[5] /* lambertian, metal, dielectric, disney, miss */, shadowMs, finishMs;
+    uint32_t extendLaunches, shadeLaunches, shadowLaunches, finishLaunches;
+} RB200KernelTimes;
+
 typedef struct RB200BvhInfo {
     uint32_t numTriangles;
     uint32_t numWideNodes;
@@ -252,6 +260,7 @@ RB200_API int rb200_trace_rays(RB200Context* ctx, const RB200Scene* scene, uint3
                                const float* directions, const float* tmax, int any_hit, RB200PrimaryHit* out_hits);
 
 RB200_API int rb200_get_stats(RB200Context* ctx, RB200Stats* last_batch, RB200Stats* cumulative);
+RB200_API int rb200_get_kernel_times(RB200Context* ctx, RB200KernelTimes* out);
 RB200_API int rb200_synchronize(RB200Context* ctx);
 
 #ifdef __cplusplus

@@ -13,12 +13,13 @@ import ctypes as C
 import numpy as np
 
 from . import abi, camera, configs, meshes, scene
-from .abi import (RB200_FLAG_ACCUM_SUM, RB200_FLAG_COUNT_BVH, RB200_FLAG_NEE, BloomPushConsts, RB200Error,
+from .abi import (RB200_FLAG_ACCUM_SUM, RB200_FLAG_COUNT_BVH, RB200_FLAG_NEE, RB200_FLAG_TIME_KERNELS, BloomPushConsts, RB200Error,
                   RtPushConsts, TonemappingPushConsts, load_library)
 from .scene import Material, ModelData, Scene, SceneTables
 
 __all__ = ["Renderer", "Material", "ModelData", "Scene", "SceneTables", "RtPushConsts", "BloomPushConsts",
-           "TonemappingPushConsts", "RB200_FLAG_NEE", "RB200_FLAG_ACCUM_SUM", "RB200_FLAG_COUNT_BVH", "RB200Error",
+           "TonemappingPushConsts", "RB200_FLAG_NEE", "RB200_FLAG_ACCUM_SUM", "RB200_FLAG_COUNT_BVH", "RB200_FLAG_TIME_KERNELS",
+           "RB200Error",
            "abi", "camera", "configs", "meshes", "scene", "load_library"]
 
 
@@ -110,6 +111,11 @@ class Renderer:
         last, cum = abi.Stats(), abi.Stats()
         abi.check(self.lib, self.lib.rb200_get_stats(self._ctx, C.byref(last), C.byref(cum)))
         return last.as_dict(), cum.as_dict()
+
+    def kernel_times(self):
+        kt = abi.KernelTimes()
+        abi.check(self.lib, self.lib.rb200_get_kernel_times(self._ctx, C.byref(kt)))
+        return kt.as_dict()
 
     def synchronize(self):
         abi.check(self.lib, self.lib.rb200_synchronize(self._ctx))

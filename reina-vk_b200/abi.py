@@ -14,6 +14,7 @@ RB200_OK = 0
 RB200_FLAG_NEE = 1 << 0
 RB200_FLAG_ACCUM_SUM = 1 << 1
 RB200_FLAG_COUNT_BVH = 1 << 2
+RB200_FLAG_TIME_KERNELS = 1 << 3
 
 
 class InstanceProperties(C.Structure):
@@ -108,6 +109,18 @@ class BvhInfo(C.Structure):
         return d
 
 
+class KernelTimes(C.Structure):
+    _fields_ = [("generateMs", C.c_float), ("extendMs", C.c_float), ("shadeMs", C.c_float * 5), ("shadowMs", C.c_float),
+                ("finishMs", C.c_float), ("extendLaunches", C.c_uint32), ("shadeLaunches", C.c_uint32),
+                ("shadowLaunches", C.c_uint32), ("finishLaunches", C.c_uint32)]
+
+    def as_dict(self):
+        return {"generateMs": self.generateMs, "extendMs": self.extendMs, "shadeMs": list(self.shadeMs),
+                "shadowMs": self.shadowMs, "finishMs": self.finishMs, "extendLaunches": self.extendLaunches,
+                "shadeLaunches": self.shadeLaunches, "shadowLaunches": self.shadowLaunches,
+                "finishLaunches": self.finishLaunches}
+
+
 class PrimaryHit(C.Structure):
     _fields_ = [("t", C.c_float), ("u", C.c_float), ("v", C.c_float), ("instance", C.c_uint32),
                 ("primitive", C.c_uint32)]
@@ -140,6 +153,7 @@ SYMBOLS = {
     "rb200_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_void_p]),
     "rb200_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats), C.POINTER(Stats)]),
+    "rb200_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(KernelTimes)]),
     "rb200_synchronize": (C.c_int, [C.c_void_p]),
 }
 

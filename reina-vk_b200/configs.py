@@ -68,7 +68,7 @@ def bunny(width=1920, height=1080, levels=6, nee=True, samples_per_pixel=1, max_
                                                                interpNormals=True))
     s.addInstance(blob, translate((0.35, 0.3, -0.1)), Material(**GLASS))
     tables = s.build(require_emitter=nee)
-    pc = dict(pos=(-1.6899, 0.317017 + 0.4, 1.6386), look=(0.0, 0.35, 0.0), fovy_deg=25.0,
+    pc = dict(pos=(-1.6899, 0.317017 + 0.4, -1.6386), look=(0.0, 0.35, 0.0), fovy_deg=25.0,
               samples_per_pixel=samples_per_pixel, max_bounces=max_bounces)
     return Workload("bunny", tables, width, height, pc, nee, 256, "stand-in geometry")
 
@@ -76,7 +76,8 @@ def bunny(width=1920, height=1080, levels=6, nee=True, samples_per_pixel=1, max_
 def dragon(width=1920, height=1080, n_along=10627, n_ring=41, nee=True, samples_per_pixel=8, max_bounces=16):
     """C3 (headline): Stanford-dragon stand-in — torus-knot tube with noise displacement, 871,414 triangles by
     default — Disney BSDF (albedo (0.6,0.3,0.8), roughness 0.3, metallic 0.8, clearcoat 1, ior 1.5) in the
-    showroom, default camera of src/Reina.cpp:138-140, 1080p, 16 bounces, NEE on."""
+    showroom, the default camera of src/Reina.cpp:138-140 mirrored to the open (-z) side of the cyclorama and raised,
+    1080p, 16 bounces, NEE on."""
     s = Scene()
     _showroom_scene(s)
     knot = meshes.torus_knot(n_along=n_along, n_ring=n_ring, fit=((0.0, 0.62, 0.0), 1.15))
@@ -84,7 +85,7 @@ def dragon(width=1920, height=1080, n_along=10627, n_ring=41, nee=True, samples_
                                       metallic=0.8, clearcoat=1.0, clearcoatGloss=0.5, sheenTint=(1, 1, 1),
                                       specularTint=(1, 1, 1)))
     tables = s.build(require_emitter=nee)
-    pc = dict(pos=(-1.6899, 0.317017 + 0.5, 1.6386), look=(0.0, 0.6, 0.0), fovy_deg=30.0,
+    pc = dict(pos=(-1.6899, 0.317017 + 0.5, -1.6386), look=(0.0, 0.6, 0.0), fovy_deg=30.0,
               samples_per_pixel=samples_per_pixel, max_bounces=max_bounces)
     return Workload("dragon", tables, width, height, pc, nee, 1024, "stand-in geometry")
 
@@ -146,7 +147,7 @@ def plant(width=1920, height=1080, n_leaves=16000, nee=True, samples_per_pixel=1
                                np.array(tris, np.uint32))
     s.addObject(leaves, IDENT, Material(materialIdx=0, albedo=(0.9, 0.9, 0.9), textureID=leaf_tex, interpNormals=False))
     tables = s.build(require_emitter=nee)
-    pc = dict(pos=(-1.6899, 0.317017 + 0.5, 1.6386), look=(0.0, 0.55, 0.0), fovy_deg=30.0,
+    pc = dict(pos=(-1.6899, 0.317017 + 0.5, -1.6386), look=(0.0, 0.55, 0.0), fovy_deg=30.0,
               samples_per_pixel=samples_per_pixel, max_bounces=max_bounces)
     return Workload("plant", tables, width, height, pc, nee, 256, "stand-in geometry")
 
@@ -168,7 +169,7 @@ def showroom_mixed(width=3840, height=2160, levels=6, nee=True, samples_per_pixe
                                                              interpNormals=True, specularTransmission=0.9,
                                                              sheenTint=(1, 1, 1), specularTint=(1, 1, 1)))
     tables = s.build(require_emitter=nee)
-    pc = dict(pos=(-1.6899, 0.317017 + 0.5, 1.6386), look=(0.0, 0.4, 0.0), fovy_deg=30.0,
+    pc = dict(pos=(-1.6899, 0.317017 + 0.5, -1.6386), look=(0.0, 0.4, 0.0), fovy_deg=30.0,
               samples_per_pixel=samples_per_pixel, max_bounces=max_bounces)
     return Workload("showroom_mixed", tables, width, height, pc, nee, 4096, "stand-in geometry")
 

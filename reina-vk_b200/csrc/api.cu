@@ -295,6 +295,24 @@ RB200_API int rb200_get_stats(RB200Context* ctx, RB200Stats* last_batch, RB200St
     return RB200_OK;
 }
 
+RB200_API int rb200_get_kernel_times(RB200Context* ctx, RB200KernelTimes* out) {
+    if (!ctx || !out) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    if (!(ctx->flags & RB200_FLAG_TIME_KERNELS)) { set_error("context was not created with RB200_FLAG_TIME_KERNELS"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    memset(out, 0, sizeof(*out));
+    for (size_t i = 0; i < ctx->evClass.size(); i++) {
+        float ms = 0.f;
+        RB_CUDA(cudaEventElapsedTime(&ms, ctx->evPool[2 * i], ctx->evPool[2 * i + 1]));
+        const int c = ctx->evClass[i];
+        if (c == 0) out->generateMs += ms;
+        else if (c == 1) { out->extendMs += ms; out->extendLaunches++; }
+        else if (c >= 2 && c <= 6) { out->shadeMs[c - 2] += ms; out->shadeLaunches++; }
+        else if (c == 7) { out->shadowMs += ms; out->shadowLaunches++; }
+        else { out->finishMs += ms; out->finishLaunches++; }
+    }
+    return RB200_OK;
+}
+
 RB200_API int rb200_synchronize(RB200Context* ctx) {
     if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
     RB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -60,6 +60,10 @@ struct RB200Context {
     RB200Stats last{}, cumulative{};
     unsigned long long* statsSnap = nullptr;   // device copy of wp.stats taken at the start of the last batch
     uint64_t launches = 0;                     // kernels launched by this context (all entry points)
+    // RB200_FLAG_TIME_KERNELS: event pairs recorded around the kernels of the last batch, tagged by class
+    std::vector<cudaEvent_t> evPool;
+    std::vector<int> evClass;                  // class of pair i (events 2i, 2i+1): 0 generate, 1 extend, 2..6 shade, 7 shadow, 8 finish
+    size_t evUsed = 0;
 };
 
 namespace rb200 {

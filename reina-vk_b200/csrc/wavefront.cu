@@ -502,22 +502,39 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
     RB_CUDA(cudaMemcpyAsync(ctx->statsSnap, P.stats, ST_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
     RB_CUDA(cudaMemsetAsync(P.counters, 0, 2 * CNT_SET * sizeof(uint32_t), s));
     uint64_t nl = 0;
-    k_generate<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(P); nl++;
+    const bool timed = (ctx->flags & RB200_FLAG_TIME_KERNELS) != 0;
+    ctx->evUsed = 0; ctx->evClass.clear();
+    auto tic = [&](int cls) {
+        if (!timed) return;
+        while (ctx->evPool.size() < ctx->evUsed + 2) { cudaEvent_t e; cudaEventCreate(&e); ctx->evPool.push_back(e); }
+        ctx->evClass.push_back(cls);
+        cudaEventRecord(ctx->evPool[ctx->evUsed], s);
+    };
+    auto toc = [&]() {
+        if (!timed) return;
+        cudaEventRecord(ctx->evPool[ctx->evUsed + 1], s);
+        ctx->evUsed += 2;
+    };
+    tic(0); k_generate<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(P); toc(); nl++;
     const uint32_t maxWaves = pc->samplesPerPixel * pc->maxBounces;
     for (uint32_t w = 0; w < maxWaves; w++) {
         const int p = (int)(w & 1u);
         RB_CUDA(cudaMemsetAsync(P.counters + (p ^ 1) * CNT_SET, 0, CNT_SET * sizeof(uint32_t), s));
+        tic(1);
         if (count) k_extend<true><<<gExtendC, BLOCK, 0, s>>>(P, p); else k_extend<false><<<gExtend, BLOCK, 0, s>>>(P, p);
-        k_shade<4><<<gShade[4], BLOCK, 0, s>>>(P, p);
-        k_shade<0><<<gShade[0], BLOCK, 0, s>>>(P, p);
-        k_shade<1><<<gShade[1], BLOCK, 0, s>>>(P, p);
-        k_shade<2><<<gShade[2], BLOCK, 0, s>>>(P, p);
-        k_shade<3><<<gShade[3], BLOCK, 0, s>>>(P, p);
+        toc();
+        tic(6); k_shade<4><<<gShade[4], BLOCK, 0, s>>>(P, p); toc();
+        tic(2); k_shade<0><<<gShade[0], BLOCK, 0, s>>>(P, p); toc();
+        tic(3); k_shade<1><<<gShade[1], BLOCK, 0, s>>>(P, p); toc();
+        tic(4); k_shade<2><<<gShade[2], BLOCK, 0, s>>>(P, p); toc();
+        tic(5); k_shade<3><<<gShade[3], BLOCK, 0, s>>>(P, p); toc();
         if (ctx->flags & RB200_FLAG_NEE) {
+            tic(7);
             if (count) k_shadow<true><<<gShadowC, BLOCK, 0, s>>>(P, p); else k_shadow<false><<<gShadow, BLOCK, 0, s>>>(P, p);
+            toc();
             nl++;
         }
-        k_finish<<<gFinish, BLOCK, 0, s>>>(P, p);
+        tic(8); k_finish<<<gFinish, BLOCK, 0, s>>>(P, p); toc();
         nl += 7;
     }
     RB_CUDA(cudaGetLastError());
