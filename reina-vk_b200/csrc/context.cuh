@@ -18,7 +18,7 @@ struct RB200Scene {
 namespace rb200 {
 
 // counters of one wave parity set
-enum { CNT_RAYS = 0, CNT_MAT0 = 1, CNT_MISS = 5, CNT_SHADOW = 6, CNT_END = 7, CNT_SET = 8 };
+enum { CNT_RAYS = 0, CNT_MAT0 = 1, CNT_MISS = 5, CNT_SHADOW = 6, CNT_END = 7, CNT_CURSOR_EXTEND = 8, CNT_CURSOR_SHADOW = 9, CNT_SET = 12 };
 // device statistics (unsigned long long each)
 enum { ST_EXTEND = 0, ST_SHADOW = 1, ST_PATHS = 2, ST_NODES = 3, ST_TRIS = 4, ST_COUNT = 8 };
 

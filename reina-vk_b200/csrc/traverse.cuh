@@ -4,13 +4,16 @@
 // (shaders/raytrace/raytrace.rgen.glsl:110-122: opaque, tmin 0, tmax 1e4, closest hit;
 //  shaders/raytrace/nee.h.glsl:126-144: opaque | terminateOnFirstHit | skipClosestHit, tmax dist - 0.001).
 //
-// One ray per thread. A stack entry is a "group": (base index, bit mask). Node groups carry the hit mask of the
+// One ray per lane. A stack entry is a "group": (base index, bit mask). Node groups carry the hit mask of the
 // internal children of one wide node in bits 24..31 (already permuted by the ray octant so that the highest set bit
 // is the nearest child) and the node's imask in bits 0..7; triangle groups carry up to 24 triangle bits.
 // Child boxes are tested directly in the quantised grid: t = q * (2^e / d) + (p - o) / d, one fma per plane.
 // Every plane is pushed outwards by a slack that bounds the fp32 rounding of that expression and the few-ulp
 // acceptance band of the watertight triangle test, so a triangle the test accepts is never culled by a box.
 // Closest-hit rule: smallest t, ties -> smallest global primitive id; boxes are culled with <= so ties are visited.
+//
+// The traversal is exposed as a resumable state machine (Traversal::step = one wide node + its triangles) so that
+// the persistent kernels can interleave ray fetching with traversal at warp level (see trace_queue()).
 #pragma once
 #include "common.cuh"
 
@@ -33,25 +36,34 @@ __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
 __device__ __forceinline__ float byte_f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
 
 template <bool ANY, bool COUNT>
-__device__ __forceinline__ void traverse(const WideNode* __restrict__ nodes, const TriRecord* __restrict__ tris,
-                                         const rb_v3 o, const rb_v3 d, const float tmax, RayHit& best,
-                                         uint32_t& nodeVisits, uint32_t& triTests, const bool dbg = false) {
-    best.t = tmax; best.b1 = 0.f; best.b2 = 0.f; best.tri = 0xFFFFFFFFu; best.gid = 0xFFFFFFFFu;
-
-    const float ooeps = 8.2718061e-25f;   // 2^-80: keeps 1/d finite for axis-parallel rays (box tests only)
-    const float idx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
-    const float idy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
-    const float idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
-    const uint32_t oct_inv = (idx < 0.f ? 0u : 4u) | (idy < 0.f ? 0u : 2u) | (idz < 0.f ? 0u : 1u);
-    const uint32_t oct_inv4 = oct_inv * 0x01010101u;
-    const rb_ray_shear shear = rb_ray_prepare(d);
-
+struct Traversal {
+    rb_v3 o;
+    float idx, idy, idz, tmax;
+    rb_ray_shear shear;
+    uint32_t oct_inv;
+    uint2 ngroup, tgroup;
+    int sp;
+    RayHit best;
     uint2 stack[TRAV_STACK];
-    int sp = 0;
-    uint2 ngroup = make_uint2(0u, 0x80000000u);
-    uint2 tgroup = make_uint2(0u, 0u);
 
-    for (;;) {
+    __device__ __forceinline__ void init(const rb_v3 org, const rb_v3 d, const float tmax_) {
+        o = org; tmax = tmax_;
+        best.t = tmax_; best.b1 = 0.f; best.b2 = 0.f; best.tri = 0xFFFFFFFFu; best.gid = 0xFFFFFFFFu;
+        const float ooeps = 8.2718061e-25f;   // 2^-80: keeps 1/d finite for axis-parallel rays (box tests only)
+        idx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+        idy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+        idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+        oct_inv = (idx < 0.f ? 0u : 4u) | (idy < 0.f ? 0u : 2u) | (idz < 0.f ? 0u : 1u);
+        shear = rb_ray_prepare(d);
+        sp = 0;
+        ngroup = make_uint2(0u, 0x80000000u);
+        tgroup = make_uint2(0u, 0u);
+    }
+
+    // One unit of work: pop the nearest pending child and test its 8 children, then this node's triangles.
+    // Returns true when the ray is finished (result in `best`).
+    __device__ __forceinline__ bool step(const WideNode* __restrict__ nodes, const TriRecord* __restrict__ tris,
+                                         uint32_t& nodeVisits, uint32_t& triTests) {
         if (ngroup.y > 0x00FFFFFFu) {
             const uint32_t hits = ngroup.y;
             const uint32_t bitIndex = 31u - (uint32_t)__clz(hits);
@@ -63,7 +75,6 @@ __device__ __forceinline__ void traverse(const WideNode* __restrict__ nodes, con
             const float4* np = reinterpret_cast<const float4*>(nodes + (base + rel));
             const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
             if (COUNT) nodeVisits++;
-            if (dbg) printf("node %u (base %u rel %u slot %u bit %u) hits %08x p=(%g %g %g) e=%08x childBase %u triBase %u meta %08x %08x\n", base + rel, base, rel, slot, bitIndex, hits, n0.x, n0.y, n0.z, __float_as_uint(n0.w), __float_as_uint(n1.x), __float_as_uint(n1.y), __float_as_uint(n1.z), __float_as_uint(n1.w));
 
             const uint32_t eim = __float_as_uint(n0.w);
             const float sx = __uint_as_float((eim & 0xFFu) << 23) * idx;
@@ -75,6 +86,7 @@ __device__ __forceinline__ void traverse(const WideNode* __restrict__ nodes, con
             const float ky = eps * fmaf(255.0f, fabsf(sy), fabsf(cy));
             const float kz = eps * fmaf(255.0f, fabsf(sz), fabsf(cz));
             const float cnx = cx - kx, cfx = cx + kx, cny = cy - ky, cfy = cy + ky, cnz = cz - kz, cfz = cz + kz;
+            const uint32_t oct_inv4 = oct_inv * 0x01010101u;
 
             ngroup.x = __float_as_uint(n1.x);
             tgroup.x = __float_as_uint(n1.y);
@@ -103,7 +115,6 @@ __device__ __forceinline__ void traverse(const WideNode* __restrict__ nodes, con
                     const float t0z = fmaf(byte_f(nz, j), sz, cnz), t1z = fmaf(byte_f(fz, j), sz, cfz);
                     const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
                     const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tcur));
-                    if (dbg) printf("   child %d: x[%g %g] y[%g %g] z[%g %g] tn %g tf %g q=(%u..%u, %u..%u, %u..%u)\n", half * 4 + j, t0x, t1x, t0y, t1y, t0z, t1z, tn, tf, (qlox >> (8 * j)) & 255, (qhix >> (8 * j)) & 255, (qloy >> (8 * j)) & 255, (qhiy >> (8 * j)) & 255, (qloz >> (8 * j)) & 255, (qhiz >> (8 * j)) & 255);
                     if (tn <= tf) {
                         const uint32_t cb = (childBits4 >> (8 * j)) & 0xFFu;
                         const uint32_t bi = (bitIndex4 >> (8 * j)) & 0xFFu;
@@ -111,7 +122,6 @@ __device__ __forceinline__ void traverse(const WideNode* __restrict__ nodes, con
                     }
                 }
             }
-            if (dbg) printf("   hitmask %08x\n", hitmask);
             ngroup.y = (hitmask & 0xFF000000u) | (eim >> 24);
             tgroup.y = hitmask & 0x00FFFFFFu;
         } else {
@@ -127,11 +137,10 @@ __device__ __forceinline__ void traverse(const WideNode* __restrict__ nodes, con
             const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
             if (COUNT) triTests++;
             float t, b1, b2;
-            if (dbg) printf("   tri %u gid %u\n", triIdx, __float_as_uint(c.w));
             if (rb_tri_intersect(o, shear, rb_mk3(a.x, a.y, a.z), rb_mk3(b.x, b.y, b.z), rb_mk3(c.x, c.y, c.z), &t, &b1, &b2)) {
                 if (t > 0.0f && t < tmax) {
                     const uint32_t gid = __float_as_uint(c.w);
-                    if (ANY) { best.t = t; best.tri = triIdx; best.gid = gid; return; }
+                    if (ANY) { best.t = t; best.tri = triIdx; best.gid = gid; return true; }
                     if (t < best.t || (t == best.t && gid < best.gid)) {
                         best.t = t; best.b1 = b1; best.b2 = b2; best.tri = triIdx; best.gid = gid;
                     }
@@ -140,10 +149,68 @@ __device__ __forceinline__ void traverse(const WideNode* __restrict__ nodes, con
         }
 
         if (ngroup.y <= 0x00FFFFFFu) {
-            if (sp == 0) break;
+            if (sp == 0) return true;
             ngroup = stack[--sp];
         }
+        return false;
     }
+};
+
+// Warp-cooperative persistent trace loop. Every lane owns at most one ray; when fewer than REFILL lanes of the warp
+// are busy, the idle lanes pull the next rays from the queue (one aggregated atomic per refill), so lanes whose
+// rays finish early do not idle until the slowest ray of the warp is done. All 32 lanes stay in the loop.
+//   fetch(i)      -> load ray i into (o, d, tmax); called for i < n
+//   commit(i, h)  -> consume the finished ray i
+template <bool ANY, bool COUNT, class Fetch, class Commit>
+__device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, const TriRecord* __restrict__ tris,
+                                            uint32_t n, uint32_t* cursor, Fetch fetch, Commit commit,
+                                            uint32_t& nodeVisits, uint32_t& triTests) {
+    constexpr int REFILL = 22;     // refill when fewer than this many lanes are busy
+    constexpr int CHUNK = 4;       // wide-node steps between refill checks
+    const uint32_t lane = threadIdx.x & 31u;
+    Traversal<ANY, COUNT> tr;
+    bool has = false;
+    bool exhausted = false;
+    uint32_t rayIdx = 0;
+    for (;;) {
+        uint32_t busy = __ballot_sync(0xffffffffu, has);
+        if (!exhausted && __popc(busy) < REFILL) {
+            const uint32_t need = ~busy;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!has) {
+                const uint32_t i = base + __popc(need & ((1u << lane) - 1u));
+                if (i < n) {
+                    rb_v3 o, d; float tmax;
+                    fetch(i, o, d, tmax);
+                    tr.init(o, d, tmax);
+                    rayIdx = i; has = true;
+                }
+            }
+            if (base + (uint32_t)__popc(need) >= n) exhausted = true;
+            busy = __ballot_sync(0xffffffffu, has);
+        }
+        if (busy == 0u) break;
+        if (has) {
+            bool done = false;
+#pragma unroll 1
+            for (int it = 0; it < CHUNK && !done; it++) done = tr.step(nodes, tris, nodeVisits, triTests);
+            if (done) { commit(rayIdx, tr.best); has = false; }
+        }
+        __syncwarp();
+    }
+}
+
+// plain one-ray traversal (kept for callers that already own one ray per thread)
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ void traverse(const WideNode* __restrict__ nodes, const TriRecord* __restrict__ tris,
+                                         const rb_v3 o, const rb_v3 d, const float tmax, RayHit& best,
+                                         uint32_t& nodeVisits, uint32_t& triTests) {
+    Traversal<ANY, COUNT> tr;
+    tr.init(o, d, tmax);
+    while (!tr.step(nodes, tris, nodeVisits, triTests)) {}
+    best = tr.best;
 }
 
 } // namespace rb200

@@ -121,25 +121,30 @@ __global__ void __launch_bounds__(BLOCK) k_extend(WaveParams P, int parity) {
     const uint32_t* __restrict__ q = P.rayQ[parity];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_EXTEND], (unsigned long long)n);
     uint32_t nodeVisits = 0, triTests = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = q[i];
-        const float4 o = P.rayO[slot], d = P.rayD[slot];
-        RayHit h;
-        traverse<false, COUNT>(P.S.nodes, P.S.tris, rb_mk3(o.x, o.y, o.z), rb_mk3(d.x, d.y, d.z), 10000.0f, h, nodeVisits, triTests);
-        uint32_t bin = 4;
-        if (h.tri != 0xFFFFFFFFu) {
-            const float4* tp = reinterpret_cast<const float4*>(P.S.tris + h.tri);
-            const uint32_t prim = __float_as_uint(__ldg(tp).w);
-            const uint32_t inst = __float_as_uint(__ldg(tp + 1).w);
-            P.hit[slot] = make_uint4(__float_as_uint(h.b1), __float_as_uint(h.b2), prim, inst);
-            const uint32_t m = __ldg(&P.S.instances[inst].materialIdx);
-            bin = m > 3u ? 3u : m;
-        }
-        // bin the slot by material (warp-aggregated per bin)
+    trace_queue<false, COUNT>(
+        P.S.nodes, P.S.tris, n, &cnt[CNT_CURSOR_EXTEND],
+        [&](uint32_t i, rb_v3& o, rb_v3& d, float& tmax) {
+            const uint32_t slot = q[i];
+            const float4 o4 = P.rayO[slot], d4 = P.rayD[slot];
+            o = rb_mk3(o4.x, o4.y, o4.z); d = rb_mk3(d4.x, d4.y, d4.z); tmax = 10000.0f;
+        },
+        [&](uint32_t i, const RayHit& h) {
+            const uint32_t slot = q[i];
+            uint32_t bin = 4;
+            if (h.tri != 0xFFFFFFFFu) {
+                const float4* tp = reinterpret_cast<const float4*>(P.S.tris + h.tri);
+                const uint32_t prim = __float_as_uint(__ldg(tp).w);
+                const uint32_t inst = __float_as_uint(__ldg(tp + 1).w);
+                P.hit[slot] = make_uint4(__float_as_uint(h.b1), __float_as_uint(h.b2), prim, inst);
+                const uint32_t m = __ldg(&P.S.instances[inst].materialIdx);
+                bin = m > 3u ? 3u : m;
+            }
+            // bin the slot by material (warp-aggregated per bin)
 #pragma unroll
-        for (uint32_t b = 0; b < 5; b++)
-            if (bin == b) queue_push(P.matQ[b], &cnt[CNT_MAT0 + b], slot);
-    }
+            for (uint32_t b = 0; b < 5; b++)
+                if (bin == b) queue_push(P.matQ[b], &cnt[CNT_MAT0 + b], slot);
+        },
+        nodeVisits, triTests);
     if (COUNT) {
         atomicAdd(&P.stats[ST_NODES], (unsigned long long)nodeVisits);
         atomicAdd(&P.stats[ST_TRIS], (unsigned long long)triTests);
@@ -389,19 +394,23 @@ __global__ void __launch_bounds__(BLOCK) k_shadow(WaveParams P, int parity) {
     const uint32_t n = cnt[CNT_SHADOW];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_SHADOW], (unsigned long long)n);
     uint32_t nodeVisits = 0, triTests = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o = P.shO[i], d = P.shD[i];
-        RayHit h;
-        traverse<true, COUNT>(P.S.nodes, P.S.tris, rb_mk3(o.x, o.y, o.z), rb_mk3(d.x, d.y, d.z), o.w, h, nodeVisits, triTests);
-        const bool occluded = h.tri != 0xFFFFFFFFu;
-        const float4 A = P.shA[i], B = P.shB[i], T = P.shT[i];
-        const uint32_t slot = __float_as_uint(d.w);
-        const rb_v3 direct = occluded ? rb_splat3(0.0f) : rb_mk3(A.x, A.y, A.z);
-        const rb_v3 combined = direct * A.w + rb_mk3(B.x, B.y, B.z);
-        const float4 L4 = P.rad[slot];
-        const rb_v3 L = rb_mk3(L4.x, L4.y, L4.z) + combined * rb_mk3(T.x, T.y, T.z);
-        P.rad[slot] = make_float4(L.x, L.y, L.z, 0.f);
-    }
+    trace_queue<true, COUNT>(
+        P.S.nodes, P.S.tris, n, &cnt[CNT_CURSOR_SHADOW],
+        [&](uint32_t i, rb_v3& o, rb_v3& d, float& tmax) {
+            const float4 o4 = P.shO[i], d4 = P.shD[i];
+            o = rb_mk3(o4.x, o4.y, o4.z); d = rb_mk3(d4.x, d4.y, d4.z); tmax = o4.w;
+        },
+        [&](uint32_t i, const RayHit& h) {
+            const bool occluded = h.tri != 0xFFFFFFFFu;
+            const float4 A = P.shA[i], B = P.shB[i], T = P.shT[i];
+            const uint32_t slot = __float_as_uint(P.shD[i].w);
+            const rb_v3 direct = occluded ? rb_splat3(0.0f) : rb_mk3(A.x, A.y, A.z);
+            const rb_v3 combined = direct * A.w + rb_mk3(B.x, B.y, B.z);
+            const float4 L4 = P.rad[slot];
+            const rb_v3 L = rb_mk3(L4.x, L4.y, L4.z) + combined * rb_mk3(T.x, T.y, T.z);
+            P.rad[slot] = make_float4(L.x, L.y, L.z, 0.f);
+        },
+        nodeVisits, triTests);
     if (COUNT) {
         atomicAdd(&P.stats[ST_NODES], (unsigned long long)nodeVisits);
         atomicAdd(&P.stats[ST_TRIS], (unsigned long long)triTests);
@@ -568,42 +577,46 @@ __global__ void __launch_bounds__(BLOCK) k_primary_rays(WaveParams P, float4* o,
     d[slot] = make_float4(rd.x, rd.y, rd.z, 0.f);
 }
 
-__device__ int g_dbgRay = -1;
-
 template <bool ANY>
 __global__ void __launch_bounds__(BLOCK) k_trace_query(const WideNode* nodes, const TriRecord* tris, uint32_t n,
                                                        const float4* __restrict__ o, const float4* __restrict__ d,
-                                                       RB200PrimaryHit* __restrict__ out) {
+                                                       RB200PrimaryHit* __restrict__ out, uint32_t* cursor) {
     uint32_t nv = 0, tt = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 ro = o[i], rd = d[i];
-        RayHit h;
-        traverse<ANY, false>(nodes, tris, rb_mk3(ro.x, ro.y, ro.z), rb_mk3(rd.x, rd.y, rd.z), ro.w, h, nv, tt, (int)i == g_dbgRay);
-        RB200PrimaryHit r;
-        r.u = h.b1; r.v = h.b2;
-        if (h.tri != 0xFFFFFFFFu) {
-            const float4* tp = reinterpret_cast<const float4*>(tris + h.tri);
-            r.t = h.t;
-            r.primitive = __float_as_uint(__ldg(tp).w);
-            r.instance = __float_as_uint(__ldg(tp + 1).w);
-        } else { r.t = -1.0f; r.u = r.v = 0.f; r.primitive = r.instance = 0xFFFFFFFFu; }
-        out[i] = r;
-    }
+    trace_queue<ANY, false>(
+        nodes, tris, n, cursor,
+        [&](uint32_t i, rb_v3& ro, rb_v3& rd, float& tmax) {
+            const float4 o4 = o[i], d4 = d[i];
+            ro = rb_mk3(o4.x, o4.y, o4.z); rd = rb_mk3(d4.x, d4.y, d4.z); tmax = o4.w;
+        },
+        [&](uint32_t i, const RayHit& h) {
+            RB200PrimaryHit r;
+            r.u = h.b1; r.v = h.b2;
+            if (h.tri != 0xFFFFFFFFu) {
+                const float4* tp = reinterpret_cast<const float4*>(tris + h.tri);
+                r.t = h.t;
+                r.primitive = __float_as_uint(__ldg(tp).w);
+                r.instance = __float_as_uint(__ldg(tp + 1).w);
+            } else { r.t = -1.0f; r.u = r.v = 0.f; r.primitive = r.instance = 0xFFFFFFFFu; }
+            out[i] = r;
+        },
+        nv, tt);
 }
 
 static int run_query(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float4* dO, const float4* dD, int any,
                      RB200PrimaryHit* out) {
     RB200PrimaryHit* dOut;
+    uint32_t* dCursor;
     RB_CUDA(cudaMalloc(&dOut, (size_t)n * sizeof(RB200PrimaryHit)));
+    RB_CUDA(cudaMalloc(&dCursor, sizeof(uint32_t)));
+    RB_CUDA(cudaMemsetAsync(dCursor, 0, sizeof(uint32_t), ctx->stream));
     const int grid = (int)std::min<uint64_t>((n + BLOCK - 1) / BLOCK, (uint64_t)ctx->numSMs * 8);
-    if (const char* e = getenv("RB200_DEBUG_RAY")) { int v = atoi(e); cudaMemcpyToSymbol(g_dbgRay, &v, sizeof(int)); }
-    if (any) k_trace_query<true><<<grid, BLOCK, 0, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut);
-    else k_trace_query<false><<<grid, BLOCK, 0, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut);
+    if (any) k_trace_query<true><<<grid, BLOCK, 0, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut, dCursor);
+    else k_trace_query<false><<<grid, BLOCK, 0, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut, dCursor);
     ctx->launches++;
     RB_CUDA(cudaGetLastError());
     RB_CUDA(cudaMemcpyAsync(out, dOut, (size_t)n * sizeof(RB200PrimaryHit), cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(dOut);
+    cudaFree(dOut); cudaFree(dCursor);
     return RB200_OK;
 }
 
