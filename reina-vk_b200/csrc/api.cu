@@ -186,7 +186,8 @@ RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB2
     BuildInput bi{D.vertices, D.indices, D.instances, &sc->hostInstances, d->numInstances};
     rc = build_bvh(bi, s, &sc->bvh, &ctx->launches);
     if (rc != RB200_OK) { rb200_scene_destroy(sc); return rc; }
-    if (sc->bvh.maxDepth > (uint32_t)36) { set_error("BVH depth %u exceeds the traversal stack", sc->bvh.maxDepth); rb200_scene_destroy(sc); return RB200_ERR_INVALID_ARGUMENT; }
+    /* TRAV_MAX_DEPTH = 22: the per-lane traversal stack holds at most 2 groups per tree level */
+    if (sc->bvh.maxDepth > (uint32_t)22) { set_error("BVH depth %u exceeds the traversal stack", sc->bvh.maxDepth); rb200_scene_destroy(sc); return RB200_ERR_INVALID_ARGUMENT; }
     D.nodes = sc->bvh.nodes; D.tris = sc->bvh.tris; D.numTris = sc->bvh.numTris;
     *out = sc;
     return RB200_OK;

@@ -16,7 +16,10 @@
 namespace rb200 {
 
 static constexpr uint32_t LEAF_FLAG = 0x80000000u;
-static constexpr int MAX_LEAF_TRIS = 3;
+#ifndef RB_MAX_LEAF_TRIS
+#define RB_MAX_LEAF_TRIS 3
+#endif
+static constexpr int MAX_LEAF_TRIS = RB_MAX_LEAF_TRIS;   // triangles per leaf slot (<= 3: unary count in 3 meta bits)
 
 // ---------------------------------------------------------------------------------------------------
 // helpers

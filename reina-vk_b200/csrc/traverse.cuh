@@ -10,10 +10,14 @@
 // Child boxes are tested directly in the quantised grid: t = q * (2^e / d) + (p - o) / d, one fma per plane.
 // Every plane is pushed outwards by a slack that bounds the fp32 rounding of that expression and the few-ulp
 // acceptance band of the watertight triangle test, so a triangle the test accepts is never culled by a box.
-// Closest-hit rule: smallest t, ties -> smallest global primitive id; boxes are culled with <= so ties are visited.
+// Closest-hit rule: smallest t, ties -> smallest global primitive id; boxes are culled with <= so ties are visited
+// and the result does not depend on the order in which nodes and triangles are processed.
 //
-// The traversal is exposed as a resumable state machine (Traversal::step = one wide node + its triangles) so that
-// the persistent kernels can interleave ray fetching with traversal at warp level (see trace_queue()).
+// Warp organisation (trace_queue): all 32 lanes run one convergent loop; a lane that owns a ray performs RB_CHUNK
+// wide-node steps (each followed by that node's triangle tests), then the warp checks how many lanes are idle and
+// the idle lanes refill from the ray queue with one aggregated atomic, so lanes whose rays finish early do not wait
+// for the slowest ray of the warp. (Measured on B200: warp-level triangle batching / postponing — every variant
+// tried — lost more to waiting lanes and weaker closest-hit culling than it gained in SIMD efficiency.)
 #pragma once
 #include "common.cuh"
 
@@ -25,7 +29,15 @@ struct RayHit {
     uint32_t gid;
 };
 
-static constexpr int TRAV_STACK = 40;
+static constexpr int TRAV_STACK = 48;          // node groups + postponed triangle groups: <= 2 per tree level
+static constexpr uint32_t TRAV_MAX_DEPTH = 22;
+
+#ifndef RB_REFILL
+#define RB_REFILL 32      // refill when fewer than this many lanes own a ray
+#endif
+#ifndef RB_CHUNK
+#define RB_CHUNK 4        // wide-node steps a lane performs between two warp-level refill checks
+#endif
 
 // per byte: 0xFF if bit 7 is set, else 0x00 (prmt's sign-replicate mode; __byte_perm only honours 3 selector bits)
 __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
@@ -33,7 +45,11 @@ __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
     asm("prmt.b32 %0, %1, 0, 0x0000ba98;" : "=r"(r) : "r"(x));
     return r;
 }
-__device__ __forceinline__ float byte_f(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
+// byte j of w as a float without the conversion (XU) pipe: PRMT builds 0x4B0000bb = 2^23 + bb, one exact FADD
+// removes the bias.
+__device__ __forceinline__ float byte_f(uint32_t w, int j) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u + (uint32_t)j)) - 8388608.0f;
+}
 
 template <bool ANY, bool COUNT>
 struct Traversal {
@@ -60,113 +76,111 @@ struct Traversal {
         tgroup = make_uint2(0u, 0u);
     }
 
-    // One unit of work: pop the nearest pending child and test its 8 children, then this node's triangles.
-    // Returns true when the ray is finished (result in `best`).
-    __device__ __forceinline__ bool step(const WideNode* __restrict__ nodes, const TriRecord* __restrict__ tris,
-                                         uint32_t& nodeVisits, uint32_t& triTests) {
-        if (ngroup.y > 0x00FFFFFFu) {
-            const uint32_t hits = ngroup.y;
-            const uint32_t bitIndex = 31u - (uint32_t)__clz(hits);
-            const uint32_t base = ngroup.x;
-            ngroup.y &= ~(1u << bitIndex);
-            if (ngroup.y > 0x00FFFFFFu) { stack[sp++] = ngroup; }
-            const uint32_t slot = (bitIndex - 24u) ^ oct_inv;
-            const uint32_t rel = __popc(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
-            const float4* np = reinterpret_cast<const float4*>(nodes + (base + rel));
-            const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-            if (COUNT) nodeVisits++;
+    __device__ __forceinline__ bool want_node() const { return ngroup.y > 0x00FFFFFFu; }
+    __device__ __forceinline__ bool want_tri() const { return tgroup.y != 0u; }
 
-            const uint32_t eim = __float_as_uint(n0.w);
-            const float sx = __uint_as_float((eim & 0xFFu) << 23) * idx;
-            const float sy = __uint_as_float(((eim >> 8) & 0xFFu) << 23) * idy;
-            const float sz = __uint_as_float(((eim >> 16) & 0xFFu) << 23) * idz;
-            const float cx = (n0.x - o.x) * idx, cy = (n0.y - o.y) * idy, cz = (n0.z - o.z) * idz;
-            const float eps = 9.5367431640625e-07f;   // 2^-20
-            const float kx = eps * fmaf(255.0f, fabsf(sx), fabsf(cx));
-            const float ky = eps * fmaf(255.0f, fabsf(sy), fabsf(cy));
-            const float kz = eps * fmaf(255.0f, fabsf(sz), fabsf(cz));
-            const float cnx = cx - kx, cfx = cx + kx, cny = cy - ky, cfy = cy + ky, cnz = cz - kz, cfz = cz + kz;
-            const uint32_t oct_inv4 = oct_inv * 0x01010101u;
+    // Nothing current: take the next group from the stack. Returns false when the ray is finished.
+    __device__ __forceinline__ bool pop() {
+        if (sp == 0) return false;
+        const uint2 e = stack[--sp];
+        if (e.y > 0x00FFFFFFu) ngroup = e; else tgroup = e;
+        return true;
+    }
 
-            ngroup.x = __float_as_uint(n1.x);
-            tgroup.x = __float_as_uint(n1.y);
-            uint32_t hitmask = 0u;
-            const float tcur = best.t;
+    // Pop the nearest pending child of the current node group and test its 8 children. Pending triangles of the
+    // lane are postponed onto the stack first. Requires want_node().
+    __device__ __forceinline__ void node_step(const WideNode* __restrict__ nodes, uint32_t& nodeVisits) {
+        if (tgroup.y != 0u) stack[sp++] = tgroup;
+        const uint32_t hits = ngroup.y;
+        const uint32_t bitIndex = 31u - (uint32_t)__clz(hits);
+        const uint32_t base = ngroup.x;
+        ngroup.y &= ~(1u << bitIndex);
+        if (ngroup.y > 0x00FFFFFFu) { stack[sp++] = ngroup; }
+        const uint32_t slot = (bitIndex - 24u) ^ oct_inv;
+        const uint32_t rel = __popc(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
+        const float4* np = reinterpret_cast<const float4*>(nodes + (base + rel));
+        const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+        if (COUNT) nodeVisits++;
+
+        const uint32_t eim = __float_as_uint(n0.w);
+        const float sx = __uint_as_float((eim & 0xFFu) << 23) * idx;
+        const float sy = __uint_as_float(((eim >> 8) & 0xFFu) << 23) * idy;
+        const float sz = __uint_as_float(((eim >> 16) & 0xFFu) << 23) * idz;
+        const float cx = (n0.x - o.x) * idx, cy = (n0.y - o.y) * idy, cz = (n0.z - o.z) * idz;
+        const float eps = 9.5367431640625e-07f;   // 2^-20
+        const float kx = eps * fmaf(255.0f, fabsf(sx), fabsf(cx));
+        const float ky = eps * fmaf(255.0f, fabsf(sy), fabsf(cy));
+        const float kz = eps * fmaf(255.0f, fabsf(sz), fabsf(cz));
+        const float cnx = cx - kx, cfx = cx + kx, cny = cy - ky, cfy = cy + ky, cnz = cz - kz, cfz = cz + kz;
+        const uint32_t oct_inv4 = oct_inv * 0x01010101u;
+
+        ngroup.x = __float_as_uint(n1.x);
+        tgroup.x = __float_as_uint(n1.y);
+        uint32_t hitmask = 0u;
+        const float tcur = best.t;
 #pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const uint32_t meta4 = __float_as_uint(half == 0 ? n1.z : n1.w);
-                const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-                const uint32_t innerMask4 = sign_extend_s8x4(isInner4 << 3);
-                const uint32_t bitIndex4 = (meta4 ^ (oct_inv4 & innerMask4)) & 0x1F1F1F1Fu;
-                const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
-                const uint32_t qlox = __float_as_uint(half == 0 ? n2.x : n2.y);
-                const uint32_t qloy = __float_as_uint(half == 0 ? n2.z : n2.w);
-                const uint32_t qloz = __float_as_uint(half == 0 ? n3.x : n3.y);
-                const uint32_t qhix = __float_as_uint(half == 0 ? n3.z : n3.w);
-                const uint32_t qhiy = __float_as_uint(half == 0 ? n4.x : n4.y);
-                const uint32_t qhiz = __float_as_uint(half == 0 ? n4.z : n4.w);
-                const uint32_t nx = idx < 0.f ? qhix : qlox, fx = idx < 0.f ? qlox : qhix;
-                const uint32_t ny = idy < 0.f ? qhiy : qloy, fy = idy < 0.f ? qloy : qhiy;
-                const uint32_t nz = idz < 0.f ? qhiz : qloz, fz = idz < 0.f ? qloz : qhiz;
+        for (int half = 0; half < 2; half++) {
+            const uint32_t meta4 = __float_as_uint(half == 0 ? n1.z : n1.w);
+            const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+            const uint32_t innerMask4 = sign_extend_s8x4(isInner4 << 3);
+            const uint32_t bitIndex4 = (meta4 ^ (oct_inv4 & innerMask4)) & 0x1F1F1F1Fu;
+            const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+            const uint32_t qlox = __float_as_uint(half == 0 ? n2.x : n2.y);
+            const uint32_t qloy = __float_as_uint(half == 0 ? n2.z : n2.w);
+            const uint32_t qloz = __float_as_uint(half == 0 ? n3.x : n3.y);
+            const uint32_t qhix = __float_as_uint(half == 0 ? n3.z : n3.w);
+            const uint32_t qhiy = __float_as_uint(half == 0 ? n4.x : n4.y);
+            const uint32_t qhiz = __float_as_uint(half == 0 ? n4.z : n4.w);
+            const uint32_t nx = idx < 0.f ? qhix : qlox, fx = idx < 0.f ? qlox : qhix;
+            const uint32_t ny = idy < 0.f ? qhiy : qloy, fy = idy < 0.f ? qloy : qhiy;
+            const uint32_t nz = idz < 0.f ? qhiz : qloz, fz = idz < 0.f ? qloz : qhiz;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float t0x = fmaf(byte_f(nx, j), sx, cnx), t1x = fmaf(byte_f(fx, j), sx, cfx);
-                    const float t0y = fmaf(byte_f(ny, j), sy, cny), t1y = fmaf(byte_f(fy, j), sy, cfy);
-                    const float t0z = fmaf(byte_f(nz, j), sz, cnz), t1z = fmaf(byte_f(fz, j), sz, cfz);
-                    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
-                    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tcur));
-                    if (tn <= tf) {
-                        const uint32_t cb = (childBits4 >> (8 * j)) & 0xFFu;
-                        const uint32_t bi = (bitIndex4 >> (8 * j)) & 0xFFu;
-                        hitmask |= cb << bi;
-                    }
-                }
-            }
-            ngroup.y = (hitmask & 0xFF000000u) | (eim >> 24);
-            tgroup.y = hitmask & 0x00FFFFFFu;
-        } else {
-            tgroup = ngroup;
-            ngroup = make_uint2(0u, 0u);
-        }
-
-        while (tgroup.y != 0u) {
-            const uint32_t ti = 31u - (uint32_t)__clz(tgroup.y);
-            tgroup.y &= ~(1u << ti);
-            const uint32_t triIdx = tgroup.x + ti;
-            const float4* tp = reinterpret_cast<const float4*>(tris + triIdx);
-            const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
-            if (COUNT) triTests++;
-            float t, b1, b2;
-            if (rb_tri_intersect(o, shear, rb_mk3(a.x, a.y, a.z), rb_mk3(b.x, b.y, b.z), rb_mk3(c.x, c.y, c.z), &t, &b1, &b2)) {
-                if (t > 0.0f && t < tmax) {
-                    const uint32_t gid = __float_as_uint(c.w);
-                    if (ANY) { best.t = t; best.tri = triIdx; best.gid = gid; return true; }
-                    if (t < best.t || (t == best.t && gid < best.gid)) {
-                        best.t = t; best.b1 = b1; best.b2 = b2; best.tri = triIdx; best.gid = gid;
-                    }
+            for (int j = 0; j < 4; j++) {
+                const float t0x = fmaf(byte_f(nx, j), sx, cnx), t1x = fmaf(byte_f(fx, j), sx, cfx);
+                const float t0y = fmaf(byte_f(ny, j), sy, cny), t1y = fmaf(byte_f(fy, j), sy, cfy);
+                const float t0z = fmaf(byte_f(nz, j), sz, cnz), t1z = fmaf(byte_f(fz, j), sz, cfz);
+                const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+                const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tcur));
+                if (tn <= tf) {
+                    const uint32_t cb = (childBits4 >> (8 * j)) & 0xFFu;
+                    const uint32_t bi = (bitIndex4 >> (8 * j)) & 0xFFu;
+                    hitmask |= cb << bi;
                 }
             }
         }
+        ngroup.y = (hitmask & 0xFF000000u) | (eim >> 24);
+        tgroup.y = hitmask & 0x00FFFFFFu;
+    }
 
-        if (ngroup.y <= 0x00FFFFFFu) {
-            if (sp == 0) return true;
-            ngroup = stack[--sp];
+    // Test one pending triangle. Returns true when an any-hit query is decided. Requires want_tri().
+    __device__ __forceinline__ bool tri_step(const TriRecord* __restrict__ tris, uint32_t& triTests) {
+        const uint32_t ti = 31u - (uint32_t)__clz(tgroup.y);
+        tgroup.y &= ~(1u << ti);
+        const uint32_t triIdx = tgroup.x + ti;
+        const float4* tp = reinterpret_cast<const float4*>(tris + triIdx);
+        const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        if (COUNT) triTests++;
+        float t, b1, b2;
+        if (rb_tri_intersect(o, shear, rb_mk3(a.x, a.y, a.z), rb_mk3(b.x, b.y, b.z), rb_mk3(c.x, c.y, c.z), &t, &b1, &b2)) {
+            if (t > 0.0f && t < tmax) {
+                const uint32_t gid = __float_as_uint(c.w);
+                if (ANY) { best.t = t; best.tri = triIdx; best.gid = gid; return true; }
+                if (t < best.t || (t == best.t && gid < best.gid)) {
+                    best.t = t; best.b1 = b1; best.b2 = b2; best.tri = triIdx; best.gid = gid;
+                }
+            }
         }
         return false;
     }
 };
 
-// Warp-cooperative persistent trace loop. Every lane owns at most one ray; when fewer than REFILL lanes of the warp
-// are busy, the idle lanes pull the next rays from the queue (one aggregated atomic per refill), so lanes whose
-// rays finish early do not idle until the slowest ray of the warp is done. All 32 lanes stay in the loop.
+// Warp-cooperative persistent trace loop (see the header comment).
 //   fetch(i)      -> load ray i into (o, d, tmax); called for i < n
 //   commit(i, h)  -> consume the finished ray i
 template <bool ANY, bool COUNT, class Fetch, class Commit>
 __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, const TriRecord* __restrict__ tris,
                                             uint32_t n, uint32_t* cursor, Fetch fetch, Commit commit,
                                             uint32_t& nodeVisits, uint32_t& triTests) {
-    constexpr int REFILL = 22;     // refill when fewer than this many lanes are busy
-    constexpr int CHUNK = 4;       // wide-node steps between refill checks
     const uint32_t lane = threadIdx.x & 31u;
     Traversal<ANY, COUNT> tr;
     bool has = false;
@@ -174,7 +188,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
     uint32_t rayIdx = 0;
     for (;;) {
         uint32_t busy = __ballot_sync(0xffffffffu, has);
-        if (!exhausted && __popc(busy) < REFILL) {
+        if (!exhausted && __popc(busy) < RB_REFILL) {
             const uint32_t need = ~busy;
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(need));
@@ -192,24 +206,35 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
             busy = __ballot_sync(0xffffffffu, has);
         }
         if (busy == 0u) break;
+
         if (has) {
             bool done = false;
 #pragma unroll 1
-            for (int it = 0; it < CHUNK && !done; it++) done = tr.step(nodes, tris, nodeVisits, triTests);
+            for (int it = 0; it < RB_CHUNK && !done; it++) {
+                if (tr.want_node()) tr.node_step(nodes, nodeVisits);
+                while (tr.want_tri()) {
+                    if (tr.tri_step(tris, triTests)) { done = true; break; }
+                }
+                if (!done && !tr.want_node() && !tr.pop()) done = true;
+            }
             if (done) { commit(rayIdx, tr.best); has = false; }
         }
         __syncwarp();
     }
 }
 
-// plain one-ray traversal (kept for callers that already own one ray per thread)
+// plain one-ray traversal (kept for callers that own exactly one ray per thread)
 template <bool ANY, bool COUNT>
 __device__ __forceinline__ void traverse(const WideNode* __restrict__ nodes, const TriRecord* __restrict__ tris,
                                          const rb_v3 o, const rb_v3 d, const float tmax, RayHit& best,
                                          uint32_t& nodeVisits, uint32_t& triTests) {
     Traversal<ANY, COUNT> tr;
     tr.init(o, d, tmax);
-    while (!tr.step(nodes, tris, nodeVisits, triTests)) {}
+    for (;;) {
+        if (tr.want_tri()) { if (tr.tri_step(tris, triTests)) break; }
+        else if (tr.want_node()) tr.node_step(nodes, nodeVisits);
+        else if (!tr.pop()) break;
+    }
     best = tr.best;
 }
 

@@ -1,0 +1,225 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (csrc/librb200.so), against the CPU oracle and the
+committed golden fixtures. Bar: bit-exact — hit primitive ids, hit t, the HDR image, the LDR image and the ray
+counters are identical (the elementary fp32 layer is shared and FMA contraction is off on both sides, see
+rb_math.h). The north_star tolerances (>= 99.99 % primitive ids, t within 1e-5 relative) are therefore met with
+margin; they are asserted too, as the weaker form.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def render_both(ol, rb, wl, flags, batches, check_counters=True):
+    r = rb.Renderer(wl.width, wl.height, wl.tables, flags=flags)
+    sc = ol.OracleScene(wl.tables)
+    hdr_o = np.zeros((wl.height, wl.width, 4), np.float32)
+    for b in range(batches):
+        pc = wl.push_constants(b)
+        r.render_batch(pc)
+        hdr_o, cnt = sc.render_batch(wl.width, wl.height, flags, pc, hdr_o)
+        if check_counters:
+            last, _ = r.stats()
+            assert (last["extendRays"], last["shadowRays"], last["paths"]) == (cnt["extendRays"], cnt["shadowRays"], cnt["paths"])
+    return r, sc, r.read_hdr(), hdr_o
+
+
+def assert_hits_equal(g, o):
+    assert (g["instance"] == o["instance"]).all() and (g["primitive"] == o["primitive"]).all()
+    assert (bits(g["t"]) == bits(o["t"])).all() and (bits(g["u"]) == bits(o["u"])).all() and (bits(g["v"]) == bits(o["v"])).all()
+
+
+@pytest.mark.parametrize("nee", [True, False])
+def test_small_mixed_bit_exact(ol, rb, nee):
+    """Every material (lambertian, metal, dielectric + Beer, Disney with all lobes), albedo / normal / alpha textures,
+    cull and alpha skips, instancing with non-uniform scale, 3 samples per pixel (slot re-use), 2 batches."""
+    wl = rb.configs.small_mixed(120, 90, nee=nee, samples_per_pixel=3, max_bounces=7)
+    flags = rb.RB200_FLAG_NEE if nee else 0
+    r, sc, g, o = render_both(ol, rb, wl, flags, 2)
+    assert (bits(g) == bits(o)).all()
+    r.postprocess()
+    assert (r.read_ldr() == ol.postprocess(o)).all()
+    r.close()
+
+
+@pytest.mark.parametrize("name", ["small_mixed_nee", "small_mixed_shipped", "cornell_nee"])
+def test_against_golden_fixtures(rb, name):
+    import golden.make_golden as mg
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    wl, flags, batches = mg.CASES[name](rb)
+    r = rb.Renderer(wl.width, wl.height, wl.tables, flags=flags)
+    for b in range(batches):
+        r.render_batch(wl.push_constants(b))
+    last, _ = r.stats()
+    assert (bits(r.read_hdr()) == bits(g["hdr"])).all()
+    assert last["extendRays"] == int(g["extend"]) and last["shadowRays"] == int(g["shadow"])
+    r.postprocess()
+    assert (r.read_ldr() == g["ldr"]).all()
+    hits = r.trace_primary(wl.push_constants(0))
+    assert (hits["primitive"] == g["prim"]).all() and (bits(hits["t"]) == bits(g["t"])).all()
+    r.close()
+
+
+def test_cornell_c1_primary_hits_and_image(ol, rb):
+    """BASELINE config C1 at its full 800x600 size: primary hits vs brute force, one 1-spp NEE batch bit-exact."""
+    wl = rb.configs.cornell(800, 600, samples_per_pixel=1, max_bounces=8)
+    r, sc, g, o = render_both(ol, rb, wl, rb.RB200_FLAG_NEE, 1)
+    assert (bits(g) == bits(o)).all()
+    pc = wl.push_constants(0)
+    assert_hits_equal(r.trace_primary(pc), sc.trace_primary(800, 600, pc, brute=True))
+    r.close()
+
+
+def test_traversal_vs_brute_force_random_rays(ol, rb):
+    wl = rb.configs.dragon(64, 48, n_along=1500, n_ring=16)      # 49k triangles
+    r = rb.Renderer(wl.width, wl.height, wl.tables)
+    sc = ol.OracleScene(wl.tables)
+    rng = np.random.RandomState(11)
+    n = 30000
+    o = rng.uniform(-0.95, 0.95, (n, 3)).astype(np.float32) + np.array([0, 1, 0], np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[:200, 0] = 0; d[200:400, 1] = 0; d[400:600, 2] = 0; d[600:700, :2] = 0      # axis-parallel / planar rays
+    g = r.trace_rays(o, d, 1e4)
+    b = sc.trace_rays(o, d, 1e4, brute=True)
+    assert_hits_equal(g, b)
+    # north_star form: ids equal on >= 99.99 %, t within 1e-5 relative
+    same = (g["instance"] == b["instance"]) & (g["primitive"] == b["primitive"])
+    assert same.mean() >= 0.9999
+    hit = b["t"] > 0
+    assert (np.abs(g["t"][hit] - b["t"][hit]) <= 1e-5 * b["t"][hit]).all()
+    tm = rng.uniform(0.02, 2.5, n).astype(np.float32)
+    assert ((r.trace_rays(o, d, tm, any_hit=True)["t"] >= 0) == (sc.trace_rays(o, d, tm, any_hit=True, brute=True)["t"] >= 0)).all()
+    r.close()
+
+
+def test_dragon_full_size_primary_and_one_batch(ol, rb):
+    """The headline workload at full size (871,414-triangle stand-in + showroom, 1920x1080): primary hits of every
+    pixel and a complete 1-spp, 16-bounce NEE batch are bit-identical to the oracle (which uses its own binned-SAH BVH,
+    so this also cross-checks two independent acceleration structures)."""
+    wl = rb.configs.dragon(1920, 1080, samples_per_pixel=1, max_bounces=16)
+    r, sc, g, o = render_both(ol, rb, wl, rb.RB200_FLAG_NEE, 1)
+    eq = (bits(g) == bits(o)).all(axis=2)
+    assert eq.all(), f"{(~eq).sum()} of {eq.size} pixels differ"
+    pc = wl.push_constants(0)
+    assert_hits_equal(r.trace_primary(pc), sc.trace_primary(1920, 1080, pc))
+    info = r.bvh_info()
+    assert info["numTriangles"] == wl.tables.num_triangles() == 872760
+    r.close()
+
+
+def test_bvh_build_is_deterministic(rb):
+    wl = rb.configs.dragon(32, 24, n_along=3000, n_ring=20)
+    hashes = set()
+    for _ in range(3):
+        r = rb.Renderer(wl.width, wl.height, wl.tables)
+        info = r.bvh_info()
+        hashes.add((info["hash"], info["numWideNodes"], info["maxDepth"]))
+        r.close()
+    assert len(hashes) == 1
+
+
+def test_render_is_deterministic_and_size_independent_properties(rb):
+    """Properties that hold at any size: same batch twice -> identical bits; sum mode == mean mode up to fp32 order;
+    ray counters bounded by paths * maxBounces; image finite, alpha 1."""
+    wl = rb.configs.bunny(640, 360, levels=4, samples_per_pixel=2, max_bounces=12)
+    r1 = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE)
+    r2 = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE | rb.RB200_FLAG_ACCUM_SUM)
+    for b in range(3):
+        r1.render_batch(wl.push_constants(b))
+        r2.render_batch(wl.push_constants(b))
+    a = r1.read_hdr()
+    last, cum = r1.stats()
+    assert np.isfinite(a).all() and (a[..., 3] == 1).all() and a[..., :3].min() >= 0
+    assert last["paths"] == 640 * 360 * 2 and last["extendRays"] <= last["paths"] * 12 and last["shadowRays"] <= last["extendRays"]
+    r2.resolve_sum(3)
+    assert np.allclose(r2.read_hdr()[..., :3], a[..., :3], rtol=1e-5, atol=1e-6)
+    r3 = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE)
+    for b in range(3):
+        r3.render_batch(wl.push_constants(b))
+    assert (bits(r3.read_hdr()) == bits(a)).all()
+    for r in (r1, r2, r3):
+        r.close()
+
+
+def test_plant_alpha_and_normal_maps(ol, rb):
+    """C4 feature set (alpha-tested leaf cards consume bounces, normal-mapped Disney pot) at reduced size."""
+    wl = rb.configs.plant(240, 135, n_leaves=1500, samples_per_pixel=2, max_bounces=10)
+    r, sc, g, o = render_both(ol, rb, wl, rb.RB200_FLAG_NEE, 1)
+    assert (bits(g) == bits(o)).all()
+    r.close()
+
+
+def test_edge_cases(ol, rb):
+    # single triangle scene, maxBounces = 1, odd resolution
+    s = rb.Scene()
+    tri = rb.meshes.make_model(np.array([[-1, 0, -1], [1, 0, -1], [0, 0, 1]], np.float32),
+                               np.array([[0, 0], [1, 0], [0.5, 1]], np.float32), np.tile(np.array([[0, 1, 0]], np.float32), (3, 1)),
+                               np.array([[0, 2, 1]], np.uint32))
+    s.addObject(tri, np.eye(4, dtype=np.float32), rb.Material(emission=(2, 3, 4)))
+    t = s.build(require_emitter=True)
+    pcs = rb.camera.push_constants(37, 23, (0, 3, 0.01), (0, 0, 0), 60.0, total_emissive_weight=t.totalEmissiveWeight,
+                                   samples_per_pixel=2, max_bounces=1)
+    r = rb.Renderer(37, 23, t, flags=rb.RB200_FLAG_NEE)
+    sc = ol.OracleScene(t)
+    r.render_batch(pcs)
+    o, _ = sc.render_batch(37, 23, rb.RB200_FLAG_NEE, pcs)
+    assert (bits(r.read_hdr()) == bits(o)).all()
+    assert r.bvh_info()["numWideNodes"] == 1
+    r.close()
+
+
+def test_errors_are_reported_not_thrown(rb):
+    lib = rb.load_library()
+    # NEE without an emitter: the reference throws "Scene must have at least one emissive object"
+    s = rb.Scene()
+    s.addObject(rb.meshes.cornell_box(), np.eye(4, dtype=np.float32), rb.Material(**rb.configs.CORNELL_WALL))
+    t = s.build()
+    with pytest.raises(rb.RB200Error, match="at least one emissive object"):
+        rb.Renderer(32, 32, t, flags=rb.RB200_FLAG_NEE)
+    # without NEE the same scene renders (sky only + walls)
+    r = rb.Renderer(32, 32, t, flags=0)
+    r.render_batch(rb.camera.push_constants(32, 32, (0, 1, 3.9), (0, 1, 0), 40.0, samples_per_pixel=1, max_bounces=2))
+    assert np.isfinite(r.read_hdr()).all()
+    # invalid push constants
+    bad = rb.camera.push_constants(32, 32, (0, 1, 3.9), (0, 1, 0), 40.0, samples_per_pixel=0)
+    with pytest.raises(rb.RB200Error, match="samplesPerPixel"):
+        r.render_batch(bad)
+    r.close()
+    # parallax bump mapping is out of scope: refused loudly, not ignored
+    s2 = rb.Scene()
+    tex = s2.defineTexture(np.full((4, 4, 4), 255, np.uint8))
+    s2.addObject(rb.meshes.cornell_light(), np.eye(4, dtype=np.float32), rb.Material(bumpMapID=tex, **{k: v for k, v in rb.configs.LIGHT.items()}))
+    with pytest.raises(rb.RB200Error, match="bump"):
+        rb.Renderer(16, 16, s2.build())
+    ctx = C.c_void_p()
+    assert lib.rb200_context_create(0, 10, 0, 0, C.byref(ctx)) != 0 and b"invalid" in lib.rb200_last_error()
+
+
+def test_postprocess_full_size_random_input(ol, rb):
+    """Bloom + tonemap at 1920x1080 on a synthetic HDR frame with bright spots: LDR identical to the oracle's 577-tap /
+    325-tap reference loops (the kernel visits only the +-66 taps with non-zero weight)."""
+    rng = np.random.RandomState(2)
+    W, H = 1920, 1080
+    hdr = np.zeros((H, W, 4), np.float32)
+    hdr[..., :3] = rng.uniform(0, 0.9, (H, W, 3)).astype(np.float32) ** 3
+    for _ in range(300):
+        y, x = rng.randint(0, H), rng.randint(0, W)
+        hdr[y:y + 3, x:x + 3, :3] = rng.uniform(2, 90, 3)
+    hdr[..., 3] = 1
+    wl = rb.configs.cornell(W, H)
+    r = rb.Renderer(W, H, wl.tables)
+    r.write_hdr(hdr)
+    r.postprocess()
+    g = r.read_ldr()
+    o = ol.postprocess(hdr)
+    eq = (g == o).all(axis=2)
+    assert eq.all(), f"{(~eq).sum()} LDR pixels differ, max diff {np.abs(g.astype(int) - o.astype(int)).max()}"
+    r.close()

@@ -1,0 +1,137 @@
+"""Known-answer tests pinning the oracle (and the shared elementary layer) to the values derived from the reference's
+GLSL in SURVEY.md Appendix A3. The reference ships no tests or golden vectors (parity unpinned), so these KATs — plus
+independent numpy restatements of the integer-exact pieces below — are what anchors the restatement."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+def np_random(state):
+    """shaders/raytrace/shaderCommon.h.glsl:39-45 in numpy (third, independent statement)."""
+    state = (np.uint64(state) * np.uint64(747796405) + np.uint64(1)) & np.uint64(0xFFFFFFFF)
+    s = int(state)
+    word = (((s >> ((s >> 28) + 4)) ^ s) * 277803737) & 0xFFFFFFFF
+    word = ((word >> 22) ^ word) & 0xFFFFFFFF
+    return s, word, np.float32(np.float32(np.uint32(word)) / np.float32(4294967295.0))
+
+
+def oracle_seq(ol, state, n):
+    st = C.c_uint32(state)
+    return [np.float32(ol.lib().oracle_kat_random(C.byref(st))) for _ in range(n)], st.value
+
+
+def test_rng_known_answers(ol):
+    seq, _ = oracle_seq(ol, 0, 4)
+    assert np.allclose(seq, [0.06468121, 4.9004331e-05, 0.86248976, 0.8270753], rtol=2e-7, atol=0)
+    s, w, _ = np_random(0)
+    assert (s, w) == (0x00000001, 0x108EF29B)
+    s, w, _ = np_random(s)
+    assert (s, w) == (0x2C9277B6, 0x00033628)
+    for seed, expect in ((479999, [0.5611887, 0.60613185, 0.7933254, 0.37940344]),
+                         (2073599, [0.6102007, 0.23335038, 0.50339574, 0.71383315]),
+                         (0xFFFFFFFF, [0.064191855, 0.93543744, 0.32334736, 0.6997081])):
+        seq, _ = oracle_seq(ol, seed, 4)
+        assert np.allclose(seq, expect, rtol=2e-7, atol=0), (seed, seq)
+
+
+def test_rng_matches_numpy_and_shared_layer(ol):
+    rng = np.random.RandomState(0)
+    for seed in [0, 1, 485605, 0xFFFFFFFF] + [int(x) for x in rng.randint(0, 2 ** 32, 50, dtype=np.uint64)]:
+        seq, end = oracle_seq(ol, seed, 16)
+        s = seed
+        for v in seq:
+            s, _, ref = np_random(s)
+            assert v == ref
+        assert end == s
+        st = C.c_uint32(seed)
+        out = np.empty(16, np.float32)
+        ol.lib().oracle_rb_random(C.byref(st), 16, out.ctypes.data_as(C.c_void_p))    # rb_random (kernel side)
+        assert (out == np.array(seq, np.float32)).all() and st.value == end
+
+
+def test_random_can_return_one():
+    # float(w) rounds w >= 2^32 - 128 up to 2^32 and 4294967295.0f is 2^32: random() lies in [0, 1] inclusive
+    assert np.float32(np.uint32(0xFFFFFF80)) / np.float32(4294967295.0) == np.float32(1.0)
+    assert np.float32(np.uint32(0xFFFFFF7F)) / np.float32(4294967295.0) == np.float32(0.99999994)
+
+
+def test_seed_formula_and_lens_draws_not_consumed(ol, rb):
+    wl = rb.configs.cornell(800, 600)
+    pc = wl.push_constants(1)
+    o, d = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    after = C.c_uint32(0)
+    ol.lib().oracle_kat_starting_ray(C.byref(pc), 5, 7, 800, 600, o.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
+                                     C.byref(after))
+    s = (1 * 600 + 7) * 800 + 5
+    assert s == 485605                                   # raytrace.rgen.glsl:259
+    for _ in range(2):                                   # only the two Gaussian draws advance the state (:186,194,234)
+        s, _, _ = np_random(s)
+    assert after.value == s
+    assert abs(np.linalg.norm(d) - 1) < 1e-6 and abs(o[2] - 3.9) < 0.05
+
+
+def test_sky_and_power_heuristic(ol):
+    out = np.zeros(3, np.float32)
+    for y, expect in ((1.0, (0.028, 0.119, 0.14)), (0.0, (0.0175, 0.063, 0.0735)), (-1.0, (0.007, 0.007, 0.007))):
+        d = np.array([np.sqrt(max(0.0, 1 - y * y)), y, 0], np.float32)
+        ol.lib().oracle_kat_sky(d.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        assert np.allclose(out, expect, rtol=1e-5)
+    assert abs(ol.lib().oracle_kat_power_heuristic(0.5, 0.25) - 0.8) < 1e-7        # pdf.h.glsl:4-7
+
+
+def test_tonemap_known_answers(ol):
+    def tm(rgb, exposure=1.0):
+        a = np.array(rgb, np.float32)
+        o = np.zeros(4, np.uint8)
+        ol.lib().oracle_kat_tonemap(a.ctypes.data_as(C.c_void_p), exposure, o.ctypes.data_as(C.c_void_p))
+        return tuple(int(x) for x in o)
+    assert tm((0.18, 0.18, 0.18)) == (68, 68, 68, 255)
+    assert tm((0.5, 0.5, 0.5)) == (158, 158, 158, 255)
+    assert tm((1.0, 1.0, 1.0)) == (205, 205, 205, 255)
+    assert tm((4.0, 0.5, 0.1)) == (255, 184, 94, 255)
+    assert tm((0.0, 0.0, 0.0)) == (0, 0, 0, 255)
+    assert tm((16.0, 16.0, 16.0)) == (255, 255, 255, 255)
+
+
+def np_offset(p, n):
+    """closestHitCommon.h.glsl:156-177 in numpy."""
+    p = np.asarray(p, np.float32); n = np.asarray(n, np.float32)
+    of_i = (np.float32(256.0) * n).astype(np.int32)          # truncation toward zero
+    bits = p.view(np.int32) + np.where(p < 0, -of_i, of_i)
+    p_i = bits.astype(np.int32).view(np.float32)
+    return np.where(np.abs(p) < np.float32(1.0 / 32.0), p + np.float32(1.0 / 65536.0) * n, p_i).astype(np.float32)
+
+
+def test_offset_along_normal_bit_exact(ol):
+    rng = np.random.RandomState(3)
+    pts = np.concatenate([rng.uniform(-3, 3, (200, 3)), rng.uniform(-0.05, 0.05, (200, 3)), rng.uniform(-1e4, 1e4, (50, 3))])
+    for p in pts.astype(np.float32):
+        n = rng.normal(size=3); n = (n / np.linalg.norm(n)).astype(np.float32)
+        out = np.zeros(3, np.float32)
+        ol.lib().oracle_kat_offset(p.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        assert (out.view(np.uint32) == np_offset(p, n).view(np.uint32)).all(), (p, n)
+
+
+@pytest.mark.parametrize("dim,k", [(800, 120), (600, 90), (1920, 288), (1080, 162), (3840, 576), (2160, 324)])
+def test_bloom_half_width(dim, k):
+    # blurCommon.h.glsl:23-24 with radius = 5 (percent)
+    assert int(np.float32(np.float32(dim) * np.float32(5.0) / np.float32(100.0)) * np.float32(3) + np.float32(0.5)) == k
+
+
+def test_bloom_impulse_response(ol, rb):
+    """sigma is the percent value (5), weightSum covers every tap (= sigma*sqrt(2 pi) = 12.5331 once k >= ~30)."""
+    W, H = 200, 160
+    hdr = np.zeros((H, W, 4), np.float32); hdr[..., 3] = 1
+    V = 50.0
+    hdr[80, 100, :3] = V
+    bloom = rb.abi.BloomPushConsts(5.0, 1.0, 0.05)
+    _, comb = ol.postprocess(hdr, bloom=bloom, want_combined=True)
+    S = 12.5331
+    for dx, dy in ((0, 0), (10, 0), (0, 10), (7, -4), (20, 0)):
+        expect = V * np.exp(-dx * dx / 50.0) / S * np.exp(-dy * dy / 50.0) / S * 0.05 + (V if (dx, dy) == (0, 0) else 0)
+        assert abs(comb[80 + dy, 100 + dx, 0] - expect) < 2e-4 * max(1.0, expect), (dx, dy)
+    # below-threshold pixels do not bloom but still count in weightSum
+    hdr2 = hdr.copy(); hdr2[80, 100, :3] = 0.5
+    _, comb2 = ol.postprocess(hdr2, bloom=bloom, want_combined=True)
+    assert comb2[80, 110, 0] == 0.0
