@@ -14,10 +14,11 @@
 // and the result does not depend on the order in which nodes and triangles are processed.
 //
 // Warp organisation (trace_queue): all 32 lanes run one convergent loop; a lane that owns a ray performs RB_CHUNK
-// wide-node steps (each followed by that node's triangle tests), then the warp checks how many lanes are idle and
-// the idle lanes refill from the ray queue with one aggregated atomic, so lanes whose rays finish early do not wait
-// for the slowest ray of the warp. (Measured on B200: warp-level triangle batching / postponing — every variant
-// tried — lost more to waiting lanes and weaker closest-hit culling than it gained in SIMD efficiency.)
+// wide-node steps, then tests the triangles those steps produced in ONE loop (a single node yields ~0.5 triangles,
+// so testing per node leaves ~3 of 32 lanes active; per chunk several times more lanes have work), then the warp
+// checks how many lanes are idle and the idle lanes refill from the ray queue with one aggregated atomic, so lanes
+// whose rays finish early do not wait for the slowest ray of the warp. (Measured on B200: warp-level triangle
+// phases with waiting lanes, and unbounded postponing, lost more than they gained.)
 #pragma once
 #include "common.cuh"
 
@@ -29,14 +30,14 @@ struct RayHit {
     uint32_t gid;
 };
 
-static constexpr int TRAV_STACK = 48;          // node groups + postponed triangle groups: <= 2 per tree level
+static constexpr int TRAV_STACK = 24;          // pending node groups: at most one per tree level
 static constexpr uint32_t TRAV_MAX_DEPTH = 22;
 
 #ifndef RB_REFILL
 #define RB_REFILL 32      // refill when fewer than this many lanes own a ray
 #endif
 #ifndef RB_CHUNK
-#define RB_CHUNK 4        // wide-node steps a lane performs between two warp-level refill checks
+#define RB_CHUNK 8        // wide-node steps a lane performs between two warp-level refill checks (swept 2..24 on B200)
 #endif
 
 // per byte: 0xFF if bit 7 is set, else 0x00 (prmt's sign-replicate mode; __byte_perm only honours 3 selector bits)
@@ -61,6 +62,8 @@ struct Traversal {
     int sp;
     RayHit best;
     uint2 stack[TRAV_STACK];
+    uint2 tstack[RB_CHUNK];   // triangle groups found during the current chunk of node steps, tested together
+    int tsp;
 
     __device__ __forceinline__ void init(const rb_v3 org, const rb_v3 d, const float tmax_) {
         o = org; tmax = tmax_;
@@ -71,26 +74,24 @@ struct Traversal {
         idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
         oct_inv = (idx < 0.f ? 0u : 4u) | (idy < 0.f ? 0u : 2u) | (idz < 0.f ? 0u : 1u);
         shear = rb_ray_prepare(d);
-        sp = 0;
+        sp = 0; tsp = 0;
         ngroup = make_uint2(0u, 0x80000000u);
         tgroup = make_uint2(0u, 0u);
     }
 
     __device__ __forceinline__ bool want_node() const { return ngroup.y > 0x00FFFFFFu; }
-    __device__ __forceinline__ bool want_tri() const { return tgroup.y != 0u; }
+    __device__ __forceinline__ bool want_tri() const { return tgroup.y != 0u || tsp > 0; }
 
-    // Nothing current: take the next group from the stack. Returns false when the ray is finished.
+    // No node group current: take the next one from the stack. Returns false when no node work is left.
     __device__ __forceinline__ bool pop() {
         if (sp == 0) return false;
-        const uint2 e = stack[--sp];
-        if (e.y > 0x00FFFFFFu) ngroup = e; else tgroup = e;
+        ngroup = stack[--sp];
         return true;
     }
 
-    // Pop the nearest pending child of the current node group and test its 8 children. Pending triangles of the
-    // lane are postponed onto the stack first. Requires want_node().
+    // Pop the nearest pending child of the current node group and test its 8 children; the triangles it yields are
+    // queued on tstack (tested later, together with those of the other node steps of the chunk). Requires want_node().
     __device__ __forceinline__ void node_step(const WideNode* __restrict__ nodes, uint32_t& nodeVisits) {
-        if (tgroup.y != 0u) stack[sp++] = tgroup;
         const uint32_t hits = ngroup.y;
         const uint32_t bitIndex = 31u - (uint32_t)__clz(hits);
         const uint32_t base = ngroup.x;
@@ -115,7 +116,6 @@ struct Traversal {
         const uint32_t oct_inv4 = oct_inv * 0x01010101u;
 
         ngroup.x = __float_as_uint(n1.x);
-        tgroup.x = __float_as_uint(n1.y);
         uint32_t hitmask = 0u;
         const float tcur = best.t;
 #pragma unroll
@@ -149,11 +149,12 @@ struct Traversal {
             }
         }
         ngroup.y = (hitmask & 0xFF000000u) | (eim >> 24);
-        tgroup.y = hitmask & 0x00FFFFFFu;
+        if (hitmask & 0x00FFFFFFu) tstack[tsp++] = make_uint2(__float_as_uint(n1.y), hitmask & 0x00FFFFFFu);
     }
 
     // Test one pending triangle. Returns true when an any-hit query is decided. Requires want_tri().
     __device__ __forceinline__ bool tri_step(const TriRecord* __restrict__ tris, uint32_t& triTests) {
+        if (tgroup.y == 0u) tgroup = tstack[--tsp];
         const uint32_t ti = 31u - (uint32_t)__clz(tgroup.y);
         tgroup.y &= ~(1u << ti);
         const uint32_t triIdx = tgroup.x + ti;
@@ -210,13 +211,15 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
         if (has) {
             bool done = false;
 #pragma unroll 1
-            for (int it = 0; it < RB_CHUNK && !done; it++) {
-                if (tr.want_node()) tr.node_step(nodes, nodeVisits);
-                while (tr.want_tri()) {
-                    if (tr.tri_step(tris, triTests)) { done = true; break; }
-                }
-                if (!done && !tr.want_node() && !tr.pop()) done = true;
+            for (int it = 0; it < RB_CHUNK; it++) {
+                if (!tr.want_node() && !tr.pop()) break;
+                tr.node_step(nodes, nodeVisits);
             }
+            // the triangles of the whole chunk in one loop: more lanes have work at the same time
+            while (tr.want_tri()) {
+                if (tr.tri_step(tris, triTests)) { done = true; break; }
+            }
+            if (!done && !tr.want_node() && tr.sp == 0) done = true;
             if (done) { commit(rayIdx, tr.best); has = false; }
         }
         __syncwarp();

@@ -19,6 +19,9 @@
 namespace rb200 {
 
 static constexpr int BLOCK = 256;
+#ifndef RB_TRAV_MINBLOCKS
+#define RB_TRAV_MINBLOCKS 4      // resident blocks per SM the traversal kernels are compiled for (register cap)
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // queue helpers
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(BLOCK) k_generate(WaveParams P) {
 // extend
 // ---------------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(BLOCK) k_extend(WaveParams P, int parity) {
+__global__ void __launch_bounds__(BLOCK, RB_TRAV_MINBLOCKS) k_extend(WaveParams P, int parity) {
     uint32_t* cnt = P.counters + parity * CNT_SET;
     const uint32_t n = cnt[CNT_RAYS];
     const uint32_t* __restrict__ q = P.rayQ[parity];
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(BLOCK) k_shade(WaveParams P, int parity) {
 // shadow: shadowRayOccluded (nee.h.glsl:126-144) + the radiance update of rgen.glsl:174-177
 // ---------------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(BLOCK) k_shadow(WaveParams P, int parity) {
+__global__ void __launch_bounds__(BLOCK, RB_TRAV_MINBLOCKS) k_shadow(WaveParams P, int parity) {
     uint32_t* cnt = P.counters + parity * CNT_SET;
     const uint32_t n = cnt[CNT_SHADOW];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_SHADOW], (unsigned long long)n);
