@@ -4,8 +4,9 @@
  * In the reference this arithmetic lives inside the Vulkan driver / RT cores (traceRayEXT at
  * shaders/raytrace/raytrace.rgen.glsl:110-122 and shaders/raytrace/nee.h.glsl:129-141); Vulkan only promises
  * watertightness, not bit patterns, so the rule is ours to fix:
- *   - the ray is sheared so its dominant axis becomes +z, edge functions U, V, W are evaluated in fp32 with
- *     plain (uncontracted) products so that a shared edge yields exactly opposite values in both triangles;
+ *   - the ray is sheared so its dominant axis becomes +z (each vertex is mapped by the same three row products, so
+ *     the mapping is a function of (vertex, ray) only), edge functions U, V, W are evaluated in fp32 with plain
+ *     (uncontracted) products so that a shared edge yields exactly opposite values in both triangles;
  *   - if any edge function is exactly 0 it is re-evaluated in fp64 (the paper's fallback);
  *   - no back-face culling (the reference culls in its closest-hit shaders, not in traversal);
  *   - t = T / det, barycentrics (b1, b2) = (V, W) / det are the Vulkan hit attributes (weights of v1, v2);
@@ -20,11 +21,15 @@
 #include "rb_vec.h"
 
 struct rb_ray_shear {
-    int kx, ky, kz;
-    float Sx, Sy, Sz;
+    /* rows of the shear+permutation that maps the ray onto +z: x' = mx . p, y' = my . p, z' = mz . p.
+     * mx = e_kx - Sx e_kz, my = e_ky - Sy e_kz, mz = Sz e_kz with kz the dominant axis of the direction
+     * (Woop et al. 2013, eq. 2-3); stored as dense rows so a vertex needs 3 multiply-adds per coordinate and no
+     * per-vertex axis selects. */
+    rb_v3 mx, my, mz;
 };
 
 RB_HD float rb_sel3(rb_v3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+RB_HD rb_v3 rb_axis3(int k, float val) { return rb_mk3(k == 0 ? val : 0.0f, k == 1 ? val : 0.0f, k == 2 ? val : 0.0f); }
 
 RB_HD rb_ray_shear rb_ray_prepare(rb_v3 d) {
     rb_ray_shear s;
@@ -33,26 +38,28 @@ RB_HD rb_ray_shear rb_ray_prepare(rb_v3 d) {
     int kx = kz + 1; if (kx == 3) kx = 0;
     int ky = kx + 1; if (ky == 3) ky = 0;
     float dz = rb_sel3(d, kz);
-    if (dz < 0.0f) { int t = kx; kx = ky; ky = t; }
-    s.kx = kx; s.ky = ky; s.kz = kz;
-    s.Sx = rb_sel3(d, kx) / dz;
-    s.Sy = rb_sel3(d, ky) / dz;
-    s.Sz = 1.0f / dz;
+    if (dz < 0.0f) { int t = kx; kx = ky; ky = t; }     /* keep the winding */
+    const float Sx = rb_sel3(d, kx) / dz;
+    const float Sy = rb_sel3(d, ky) / dz;
+    const float Sz = 1.0f / dz;
+    s.mx = rb_axis3(kx, 1.0f) + rb_axis3(kz, -Sx);
+    s.my = rb_axis3(ky, 1.0f) + rb_axis3(kz, -Sy);
+    s.mz = rb_axis3(kz, Sz);
     return s;
 }
+
+/* m . p with a fixed evaluation order (one multiply, two fused multiply-adds) */
+RB_HD float rb_row3(rb_v3 m, rb_v3 p) { return fmaf(m.z, p.z, fmaf(m.y, p.y, m.x * p.x)); }
 
 /* Returns true when the (infinite) ray line crosses the triangle with det != 0; outputs t, b1, b2. */
 RB_HD bool rb_tri_intersect(rb_v3 org, const rb_ray_shear& s, rb_v3 v0, rb_v3 v1, rb_v3 v2,
                             float* t_out, float* b1_out, float* b2_out) {
-    rb_v3 A = v0 - org, B = v1 - org, C = v2 - org;
-    float Akz = rb_sel3(A, s.kz), Bkz = rb_sel3(B, s.kz), Ckz = rb_sel3(C, s.kz);
-    float Ax = fmaf(-s.Sx, Akz, rb_sel3(A, s.kx));
-    float Ay = fmaf(-s.Sy, Akz, rb_sel3(A, s.ky));
-    float Bx = fmaf(-s.Sx, Bkz, rb_sel3(B, s.kx));
-    float By = fmaf(-s.Sy, Bkz, rb_sel3(B, s.ky));
-    float Cx = fmaf(-s.Sx, Ckz, rb_sel3(C, s.kx));
-    float Cy = fmaf(-s.Sy, Ckz, rb_sel3(C, s.ky));
+    const rb_v3 A = v0 - org, B = v1 - org, C = v2 - org;
+    const float Ax = rb_row3(s.mx, A), Ay = rb_row3(s.my, A);
+    const float Bx = rb_row3(s.mx, B), By = rb_row3(s.my, B);
+    const float Cx = rb_row3(s.mx, C), Cy = rb_row3(s.my, C);
 
+    /* edge functions: plain products and differences, so a shared edge gives exactly opposite values */
     float U = Cx * By - Cy * Bx;
     float V = Ax * Cy - Ay * Cx;
     float W = Bx * Ay - By * Ax;
@@ -67,11 +74,11 @@ RB_HD bool rb_tri_intersect(rb_v3 org, const rb_ray_shear& s, rb_v3 v0, rb_v3 v1
     }
 
     if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
-    float det = U + V + W;
+    const float det = U + V + W;
     if (det == 0.0f) return false;
 
-    float Az = s.Sz * Akz, Bz = s.Sz * Bkz, Cz = s.Sz * Ckz;
-    float T = U * Az + V * Bz + W * Cz;
+    const float Az = rb_row3(s.mz, A), Bz = rb_row3(s.mz, B), Cz = rb_row3(s.mz, C);
+    const float T = U * Az + V * Bz + W * Cz;
     *t_out = T / det;
     *b1_out = V / det;
     *b2_out = W / det;
