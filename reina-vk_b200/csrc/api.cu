@@ -90,17 +90,25 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
     c->ownStream = true;
     const size_t N = (size_t)width * height;
     WaveParams& P = c->wp;
-    P.W = width; P.H = height; P.N = (uint32_t)N; P.flags = flags;
     int rc;
 #define A(ptr, n) if ((rc = ctx_alloc(c, &(ptr), (n))) != RB200_OK) return rc
-    A(P.rayO, N); A(P.rayD, N); A(P.hit, N); A(P.thr, N); A(P.rad, N); A(P.sum, N); A(P.st, N);
-    A(P.shO, N); A(P.shD, N); A(P.shA, N); A(P.shB, N); A(P.shT, N);
-    A(P.rayQ[0], N); A(P.rayQ[1], N);
-    for (int m = 0; m < 5; m++) A(P.matQ[m], N);
-    A(P.endQ, N); A(P.counters, 2 * CNT_SET); A(P.stats, ST_COUNT); A(c->statsSnap, ST_COUNT);
+    for (int lane = 0; lane < 2; lane++) {
+        WaveParams& L = lane == 0 ? c->wp : c->wp1;
+        L.W = width; L.H = height; L.N = (uint32_t)N; L.flags = flags;
+        A(L.rayO, N); A(L.rayD, N); A(L.hit, N); A(L.thr, N); A(L.rad, N); A(L.sum, N); A(L.st, N);
+        A(L.shO, N); A(L.shD, N); A(L.shA, N); A(L.shB, N); A(L.shT, N);
+        A(L.rayQ[0], N); A(L.rayQ[1], N);
+        for (int m = 0; m < 5; m++) A(L.matQ[m], N);
+        A(L.endQ, N); A(L.counters, 2 * CNT_SET); A(L.mean, N); A(L.stats, ST_COUNT);
+        RB_CUDA(cudaMemsetAsync(L.stats, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
+        RB_CUDA(cudaStreamCreateWithFlags(&c->laneStream[lane], cudaStreamNonBlocking));
+        RB_CUDA(cudaEventCreateWithFlags(&c->accumDone[lane], cudaEventDisableTiming));
+    }
+    RB_CUDA(cudaEventCreateWithFlags(&c->frontMark, cudaEventDisableTiming));
+    A(c->statsSnap, ST_COUNT);
     A(P.image, N); A(c->ping, N); A(c->pong, N); A(c->ldr, N);
+    c->wp1.image = P.image;
 #undef A
-    RB_CUDA(cudaMemsetAsync(P.stats, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
     RB_CUDA(cudaMemsetAsync(c->statsSnap, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
     RB_CUDA(cudaMemsetAsync(P.image, 0, N * sizeof(float4), c->stream));
     RB_CUDA(cudaMemsetAsync(c->ldr, 0, N * sizeof(uchar4), c->stream));
@@ -112,8 +120,15 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
 RB200_API int rb200_context_destroy(RB200Context* ctx) {
     if (!ctx) return RB200_OK;
     cudaSetDevice(ctx->device);
+    for (int lane = 0; lane < 2; lane++) if (ctx->laneStream[lane]) cudaStreamSynchronize(ctx->laneStream[lane]);
     cudaStreamSynchronize(ctx->stream);
     for (void* p : ctx->allocations) cudaFree(p);
+    for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
+    for (int lane = 0; lane < 2; lane++) {
+        if (ctx->accumDone[lane]) cudaEventDestroy(ctx->accumDone[lane]);
+        if (ctx->laneStream[lane]) cudaStreamDestroy(ctx->laneStream[lane]);
+    }
+    if (ctx->frontMark) cudaEventDestroy(ctx->frontMark);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RB200_OK;
@@ -121,6 +136,7 @@ RB200_API int rb200_context_destroy(RB200Context* ctx) {
 
 RB200_API int rb200_context_set_stream(RB200Context* ctx, void* cuda_stream) {
     if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
+    for (int lane = 0; lane < 2; lane++) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[lane]));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream;
@@ -282,15 +298,18 @@ RB200_API int rb200_trace_rays(RB200Context* ctx, const RB200Scene* scene, uint3
 
 RB200_API int rb200_get_stats(RB200Context* ctx, RB200Stats* last_batch, RB200Stats* cumulative) {
     if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
-    unsigned long long now[ST_COUNT], snap[ST_COUNT];
-    RB_CUDA(cudaMemcpyAsync(now, ctx->wp.stats, sizeof(now), cudaMemcpyDeviceToHost, ctx->stream));
-    RB_CUDA(cudaMemcpyAsync(snap, ctx->statsSnap, sizeof(snap), cudaMemcpyDeviceToHost, ctx->stream));
+    // per-lane counters hold the lane's last batch; k_accumulate adds them to the cumulative array when the batch ends.
+    // The front-end stream waits for the last batch's accumulation, which is ordered after every earlier batch.
+    unsigned long long lastc[ST_COUNT] = {0}, cum[ST_COUNT];
+    const rb200::WaveParams& lastLane = ((ctx->batchCalls - 1) & 1u) == 0 ? ctx->wp : ctx->wp1;
+    if (ctx->batchCalls > 0) RB_CUDA(cudaMemcpyAsync(lastc, lastLane.stats, sizeof(lastc), cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(cudaMemcpyAsync(cum, ctx->statsSnap, sizeof(cum), cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     RB200Stats& L = ctx->last; RB200Stats& Cm = ctx->cumulative;
-    L.extendRays = now[ST_EXTEND] - snap[ST_EXTEND]; L.shadowRays = now[ST_SHADOW] - snap[ST_SHADOW];
-    L.paths = now[ST_PATHS] - snap[ST_PATHS]; L.nodeVisits = now[ST_NODES] - snap[ST_NODES]; L.triTests = now[ST_TRIS] - snap[ST_TRIS];
-    Cm.extendRays = now[ST_EXTEND]; Cm.shadowRays = now[ST_SHADOW]; Cm.paths = now[ST_PATHS];
-    Cm.nodeVisits = now[ST_NODES]; Cm.triTests = now[ST_TRIS]; Cm.kernelLaunches = ctx->launches;
+    L.extendRays = lastc[ST_EXTEND]; L.shadowRays = lastc[ST_SHADOW];
+    L.paths = lastc[ST_PATHS]; L.nodeVisits = lastc[ST_NODES]; L.triTests = lastc[ST_TRIS];
+    Cm.extendRays = cum[ST_EXTEND]; Cm.shadowRays = cum[ST_SHADOW]; Cm.paths = cum[ST_PATHS];
+    Cm.nodeVisits = cum[ST_NODES]; Cm.triTests = cum[ST_TRIS]; Cm.kernelLaunches = ctx->launches;
     if (last_batch) *last_batch = L;
     if (cumulative) *cumulative = Cm;
     return RB200_OK;

@@ -42,7 +42,8 @@ struct WaveParams {
     uint32_t* endQ;
     uint32_t* counters;            // [2][CNT_SET]
     unsigned long long* stats;     // [ST_COUNT]
-    float4* image;                 // HDR accumulation image
+    float4* mean;                  // per pixel: mean of this batch's valid samples (xyz), w = 1 if any sample was valid
+    float4* image;                 // HDR accumulation image (shared by both lanes)
 };
 
 } // namespace rb200
@@ -51,14 +52,23 @@ struct RB200Context {
     uint32_t width = 0, height = 0, flags = 0;
     int device = 0;
     int numSMs = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;             // front-end stream: API calls are ordered on it (may be the caller's)
     bool ownStream = false;
-    rb200::WaveParams wp{};
+    // Two lanes (path-state sets + internal streams). Consecutive rb200_render_batch calls alternate lanes so the
+    // long, thinly populated tail of one batch overlaps the head of the next; the per-pixel accumulation into the
+    // shared HDR image stays in batch order (k_accumulate of batch b waits for that of batch b-1).
+    rb200::WaveParams wp{};                    // lane 0 (also the scratch of the query entry points)
+    rb200::WaveParams wp1{};                   // lane 1
+    cudaStream_t laneStream[2] = {nullptr, nullptr};
+    cudaEvent_t accumDone[2] = {nullptr, nullptr};
+    cudaEvent_t frontMark = nullptr;
+    uint64_t batchCalls = 0;
     std::vector<void*> allocations;
     float4 *ping = nullptr, *pong = nullptr;   // bloom work images
     uchar4* ldr = nullptr;
     RB200Stats last{}, cumulative{};
-    unsigned long long* statsSnap = nullptr;   // device copy of wp.stats taken at the start of the last batch
+    unsigned long long* statsSnap = nullptr;   // cumulative device counters (each lane's per-batch counters are added
+                                               // by k_accumulate when its batch ends)
     uint64_t launches = 0;                     // kernels launched by this context (all entry points)
     // RB200_FLAG_TIME_KERNELS: event pairs recorded around the kernels of the last batch, tagged by class
     std::vector<cudaEvent_t> evPool;

@@ -444,27 +444,45 @@ __global__ void __launch_bounds__(BLOCK) k_finish(WaveParams P, int parity) {
             started++;
             queue_push(P.rayQ[parity ^ 1], &cntNext[CNT_RAYS], slot);
         } else {
-            float4* px = &P.image[slot];
-            if (actual == 0u) {
-                // documented deviation: the reference writes 0/0 and poisons the pixel; batch 0 writes black,
-                // later batches keep the previous value, sum mode adds nothing
-                if (!(P.flags & RB200_FLAG_ACCUM_SUM) && P.pc.sampleBatch == 0u) *px = make_float4(0.f, 0.f, 0.f, 1.f);
-            } else {
-                rb_v3 fin = rb_mk3(s4.x, s4.y, s4.z) / (float)actual;
-                if (P.flags & RB200_FLAG_ACCUM_SUM) {
-                    const float4 prev = *px;
-                    *px = make_float4(prev.x + fin.x, prev.y + fin.y, prev.z + fin.z, 1.f);
-                } else {
-                    if (P.pc.sampleBatch > 0u) {
-                        const float4 prev = *px;
-                        fin = (rb_mk3(prev.x, prev.y, prev.z) * (float)P.pc.sampleBatch + fin) / (float)(P.pc.sampleBatch + 1u);
-                    }
-                    *px = make_float4(fin.x, fin.y, fin.z, 1.f);
-                }
+            // last sample of the pixel: this batch's mean over the valid samples (rgen.glsl:275); folded into the
+            // image by k_accumulate once the whole batch is done
+            if (actual == 0u) P.mean[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+            else {
+                const rb_v3 fin = rb_mk3(s4.x, s4.y, s4.z) / (float)actual;
+                P.mean[slot] = make_float4(fin.x, fin.y, fin.z, 1.f);
             }
         }
     }
     if (started) atomicAdd(&P.stats[ST_PATHS], (unsigned long long)started);
+}
+
+// rgen.glsl:277-284: running average over batches (or the plain sum with RB200_FLAG_ACCUM_SUM). Runs once per batch,
+// in batch order, after every pixel of the batch has delivered its mean.
+__global__ void __launch_bounds__(BLOCK) k_accumulate(float4* __restrict__ image, const float4* __restrict__ mean, uint32_t n,
+                                                      uint32_t sampleBatch, uint32_t flags,
+                                                      const unsigned long long* __restrict__ laneStats,
+                                                      unsigned long long* __restrict__ cumStats) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ST_COUNT) cumStats[i] += laneStats[i];     // batches are folded one at a time, in order: no race
+    if (i >= n) return;
+    const float4 m = mean[i];
+    if (m.w == 0.f) {
+        // documented deviation: the reference writes 0/0 and poisons the pixel; batch 0 writes black, later batches keep
+        // the previous value, sum mode adds nothing
+        if (!(flags & RB200_FLAG_ACCUM_SUM) && sampleBatch == 0u) image[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+        return;
+    }
+    rb_v3 fin = rb_mk3(m.x, m.y, m.z);
+    if (flags & RB200_FLAG_ACCUM_SUM) {
+        const float4 prev = image[i];
+        image[i] = make_float4(prev.x + fin.x, prev.y + fin.y, prev.z + fin.z, 1.f);
+    } else {
+        if (sampleBatch > 0u) {
+            const float4 prev = image[i];
+            fin = (rb_mk3(prev.x, prev.y, prev.z) * (float)sampleBatch + fin) / (float)(sampleBatch + 1u);
+        }
+        image[i] = make_float4(fin.x, fin.y, fin.z, 1.f);
+    }
 }
 
 __global__ void k_resolve_sum(float4* image, uint32_t n, float inv) {
@@ -484,16 +502,26 @@ template <class K> static int persistent_grid(K kernel, int numSMs) {
 }
 
 int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc) {
-    WaveParams& P = ctx->wp;
     if (pc->samplesPerPixel == 0 || pc->maxBounces == 0) { set_error("samplesPerPixel and maxBounces must be > 0"); return RB200_ERR_INVALID_ARGUMENT; }
     if ((ctx->flags & RB200_FLAG_NEE) && scene->numEmissive == 0) {
         set_error("Scene must have at least one emissive object");   // src/scene/Instances.cpp:125-127
         return RB200_ERR_NO_EMITTER;
     }
+    // Lane selection: consecutive calls alternate between two path-state sets on two internal streams, so the thin
+    // tail of batch b (few live paths, latency-bound launches) overlaps the head of batch b+1.
+    const int lane = (int)(ctx->batchCalls & 1u);
+    const int other = lane ^ 1;
+    const bool hadPrevious = ctx->batchCalls > 0;
+    ctx->batchCalls++;
+    WaveParams& P = lane == 0 ? ctx->wp : ctx->wp1;
     P.S = scene->dev;
     P.pc = *pc;
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = ctx->laneStream[lane];
+    // everything the caller enqueued on the front-end stream before this call (write_hdr, postprocess of the previous
+    // frame, an external reduce of the image ...) must precede this batch's accumulation — not its tracing
+    RB_CUDA(cudaEventRecord(ctx->frontMark, ctx->stream));
     const bool count = (ctx->flags & RB200_FLAG_COUNT_BVH) != 0;
+    if (ctx->flags & RB200_FLAG_TIME_KERNELS) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[other]));   // timing pass: no overlap
 
     static int gExtend = 0, gExtendC = 0, gShadow = 0, gShadowC = 0, gShade[5] = {0, 0, 0, 0, 0}, gFinish = 0;
     if (!gExtend) {
@@ -511,7 +539,7 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
 
     // snapshot of the cumulative device counters at batch start (device-to-device: no host synchronisation here;
     // rb200_get_stats resolves "last batch" = cumulative - snapshot after synchronising)
-    RB_CUDA(cudaMemcpyAsync(ctx->statsSnap, P.stats, ST_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+    RB_CUDA(cudaMemsetAsync(P.stats, 0, ST_COUNT * sizeof(unsigned long long), s));   // this lane's per-batch counters
     RB_CUDA(cudaMemsetAsync(P.counters, 0, 2 * CNT_SET * sizeof(uint32_t), s));
     uint64_t nl = 0;
     const bool timed = (ctx->flags & RB200_FLAG_TIME_KERNELS) != 0;
@@ -549,6 +577,14 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
         tic(8); k_finish<<<gFinish, BLOCK, 0, s>>>(P, p); toc();
         nl += 7;
     }
+    // fold this batch's pixel means into the shared image: after the previous batch's fold and after whatever the
+    // caller had queued on the front-end stream; then let the front-end stream see the result
+    if (hadPrevious) RB_CUDA(cudaStreamWaitEvent(s, ctx->accumDone[other], 0));
+    RB_CUDA(cudaStreamWaitEvent(s, ctx->frontMark, 0));
+    k_accumulate<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(P.image, P.mean, P.N, pc->sampleBatch, ctx->flags, P.stats,
+                                                             ctx->statsSnap); nl++;
+    RB_CUDA(cudaEventRecord(ctx->accumDone[lane], s));
+    RB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->accumDone[lane], 0));
     RB_CUDA(cudaGetLastError());
     ctx->last.waves = maxWaves;
     ctx->last.kernelLaunches = nl;
@@ -608,6 +644,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace_query(const WideNode* nodes, co
 static int run_query(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float4* dO, const float4* dD, int any,
                      RB200PrimaryHit* out) {
     RB200PrimaryHit* dOut;
+    for (int lane = 0; lane < 2; lane++) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[lane]));   // lane 0's arrays are the scratch
     uint32_t* dCursor;
     RB_CUDA(cudaMalloc(&dOut, (size_t)n * sizeof(RB200PrimaryHit)));
     RB_CUDA(cudaMalloc(&dCursor, sizeof(uint32_t)));
@@ -625,6 +662,7 @@ static int run_query(RB200Context* ctx, const RB200Scene* scene, uint32_t n, con
 
 int trace_primary(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc, RB200PrimaryHit* out) {
     WaveParams& P = ctx->wp;
+    for (int lane = 0; lane < 2; lane++) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[lane]));
     P.S = scene->dev; P.pc = *pc;
     k_primary_rays<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, ctx->stream>>>(P, P.shO, P.shD);
     ctx->launches++;
