@@ -453,7 +453,9 @@ __global__ void __launch_bounds__(BLOCK) k_finish(WaveParams P, int parity) {
             }
         }
     }
-    if (started) atomicAdd(&P.stats[ST_PATHS], (unsigned long long)started);
+    // one counter update per warp, not per thread: a same-address 64-bit atomic from every thread serialises in L2
+    const uint32_t warpStarted = __reduce_add_sync(0xffffffffu, started);
+    if ((threadIdx.x & 31u) == 0u && warpStarted) atomicAdd(&P.stats[ST_PATHS], (unsigned long long)warpStarted);
 }
 
 // rgen.glsl:277-284: running average over batches (or the plain sum with RB200_FLAG_ACCUM_SUM). Runs once per batch,
