@@ -253,8 +253,19 @@ def main():
         e0.record(stream)
         for i in range(K):
             r.render_batch(wl.push_constants(batch_index(Wm + K + i)))
-            r.postprocess()
-            r.read_ldr(ldr_host)          # device -> host copy of the frame, synchronises
+            if world > 1:
+                # one presented frame: reduce every rank's SUM image to rank 0, resolve, post-process and read back
+                # there; rank 0 then restores its local sum so that accumulation continues
+                local = hdr_t.clone()
+                dist.reduce(hdr_t, dst=0, op=dist.ReduceOp.SUM)
+                if rank == 0:
+                    r.resolve_sum((Wm + 2 * K + i + 1) * world)
+                    r.postprocess()
+                    r.read_ldr(ldr_host)
+                hdr_t.copy_(local)
+            else:
+                r.postprocess()
+                r.read_ldr(ldr_host)          # device -> host copy of the frame, synchronises
         e1.record(stream)
         torch.cuda.synchronize()
         ms_e2e = e0.elapsed_time(e1)

@@ -188,7 +188,7 @@ typedef struct RB200BvhInfo {
     uint32_t numTriangles;
     uint32_t numWideNodes;
     uint32_t maxDepth;
-    uint32_t reserved;
+    uint32_t reserved;       /* KiB of L2 set aside as persisting for the node+triangle arrays (0 = hint not applied) */
     uint64_t nodeBytes;
     uint64_t triangleBytes;
     uint64_t hash;           /* FNV-1a over the node and triangle arrays: equal across runs/GPUs (deterministic build) */

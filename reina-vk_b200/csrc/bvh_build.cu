@@ -520,8 +520,13 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
     uint32_t* triPrefix;
     RB_CUDA(dalloc(&triPrefix, numNodes));
     k_exclusive_scan<<<1, 1024, 0, stream>>>(nodeTriCount, triPrefix, numNodes, dTotal); nl++;
-    RB_CUDA(dalloc(&out->tris, N));
-    RB_CUDA(dalloc(&out->nodes, numNodes));
+    // nodes and triangles live in ONE allocation so that a single L2 access-policy window can keep the whole
+    // hierarchy resident (see rb200_scene_create)
+    const size_t nodeBytes = ((size_t)numNodes * sizeof(WideNode) + 255) & ~(size_t)255;
+    out->blobBytes = nodeBytes + (size_t)N * sizeof(TriRecord);
+    RB_CUDA(cudaMalloc(&out->blob, out->blobBytes));
+    out->nodes = reinterpret_cast<WideNode*>(out->blob);
+    out->tris = reinterpret_cast<TriRecord*>(reinterpret_cast<char*>(out->blob) + nodeBytes);
     k_place_triangles<<<(numNodes + 127) / 128, 128, 0, stream>>>(nodesTmp, numNodes, triPrefix, slotTriFirst, sorted, out->tris); nl++;
     RB_CUDA(cudaMemcpyAsync(out->nodes, nodesTmp, (size_t)numNodes * sizeof(WideNode), cudaMemcpyDeviceToDevice, stream));
     uint32_t totalTris = 0, hb[6];
@@ -557,9 +562,8 @@ int hash_bvh(const Bvh& bvh, cudaStream_t stream, uint64_t* hash) {
 }
 
 void free_bvh(Bvh* b) {
-    if (b->nodes) cudaFree(b->nodes);
-    if (b->tris) cudaFree(b->tris);
-    b->nodes = nullptr; b->tris = nullptr;
+    if (b->blob) cudaFree(b->blob);
+    b->blob = nullptr; b->nodes = nullptr; b->tris = nullptr;
 }
 
 } // namespace rb200

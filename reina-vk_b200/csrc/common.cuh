@@ -45,6 +45,8 @@ struct alignas(16) TriRecord { float4 v0, v1, v2; };
 static_assert(sizeof(TriRecord) == 48, "TriRecord must be 48 bytes");
 
 struct Bvh {
+    void* blob = nullptr;            // one allocation: nodes, then (256-byte aligned) triangles
+    size_t blobBytes = 0;
     WideNode* nodes = nullptr;
     TriRecord* tris = nullptr;
     uint32_t numNodes = 0, numTris = 0, maxDepth = 0;

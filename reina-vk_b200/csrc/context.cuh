@@ -11,6 +11,7 @@ struct RB200Scene {
     std::vector<cudaTextureObject_t> texObjects;
     std::vector<RB200Instance> hostInstances;
     uint32_t numEmissive = 0;
+    size_t l2PersistBytes = 0;                // L2 set aside as persisting for the BVH (0 = hint not applied)
     uint64_t hash = 0;
     bool hashValid = false;
 };

@@ -46,10 +46,12 @@ __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
     asm("prmt.b32 %0, %1, 0, 0x0000ba98;" : "=r"(r) : "r"(x));
     return r;
 }
-// byte j of w as a float without the conversion (XU) pipe: PRMT builds 0x4B0000bb = 2^23 + bb, one exact FADD
-// removes the bias.
+// byte j of w as the float 2^15 + byte, built by ONE PRMT (0x4700bb00): no conversion-pipe (XU) instruction and no
+// subtraction — the bias is folded into the plane offsets (c' = c - 2^15 * s), whose extra rounding (<= 2^-9 of a
+// grid step) is covered by the slack below.
+static constexpr float BYTE_BIAS = 32768.0f;
 __device__ __forceinline__ float byte_f(uint32_t w, int j) {
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u + (uint32_t)j)) - 8388608.0f;
+    return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404u + ((uint32_t)j << 4)));
 }
 
 template <bool ANY, bool COUNT>
@@ -109,10 +111,14 @@ struct Traversal {
         const float sz = __uint_as_float(((eim >> 16) & 0xFFu) << 23) * idz;
         const float cx = (n0.x - o.x) * idx, cy = (n0.y - o.y) * idy, cz = (n0.z - o.z) * idz;
         const float eps = 9.5367431640625e-07f;   // 2^-20
-        const float kx = eps * fmaf(255.0f, fabsf(sx), fabsf(cx));
-        const float ky = eps * fmaf(255.0f, fabsf(sy), fabsf(cy));
-        const float kz = eps * fmaf(255.0f, fabsf(sz), fabsf(cz));
-        const float cnx = cx - kx, cfx = cx + kx, cny = cy - ky, cfy = cy + ky, cnz = cz - kz, cfz = cz + kz;
+        // slack: 2^-20 * (255 |s| + |c|) bounds the rounding of q*s + c and the acceptance band of the triangle test;
+        // + 2^-9 |s| (= 2^-20 * 2048, here 2305 with margin) bounds the rounding of the biased offsets c - 2^15 s
+        const float kx = eps * fmaf(2560.0f, fabsf(sx), fabsf(cx));
+        const float ky = eps * fmaf(2560.0f, fabsf(sy), fabsf(cy));
+        const float kz = eps * fmaf(2560.0f, fabsf(sz), fabsf(cz));
+        const float cnx = fmaf(-BYTE_BIAS, sx, cx - kx), cfx = fmaf(-BYTE_BIAS, sx, cx + kx);
+        const float cny = fmaf(-BYTE_BIAS, sy, cy - ky), cfy = fmaf(-BYTE_BIAS, sy, cy + ky);
+        const float cnz = fmaf(-BYTE_BIAS, sz, cz - kz), cfz = fmaf(-BYTE_BIAS, sz, cz + kz);
         const uint32_t oct_inv4 = oct_inv * 0x01010101u;
 
         ngroup.x = __float_as_uint(n1.x);
