@@ -13,12 +13,17 @@
 // Closest-hit rule: smallest t, ties -> smallest global primitive id; boxes are culled with <= so ties are visited
 // and the result does not depend on the order in which nodes and triangles are processed.
 //
-// Warp organisation (trace_queue): all 32 lanes run one convergent loop; a lane that owns a ray performs RB_CHUNK
-// wide-node steps, then tests the triangles those steps produced in ONE loop (a single node yields ~0.5 triangles,
-// so testing per node leaves ~3 of 32 lanes active; per chunk several times more lanes have work), then the warp
-// checks how many lanes are idle and the idle lanes refill from the ray queue with one aggregated atomic, so lanes
-// whose rays finish early do not wait for the slowest ray of the warp. (Measured on B200: warp-level triangle
-// phases with waiting lanes, and unbounded postponing, lost more than they gained.)
+// Warp organisation (trace_queue): all 32 lanes run one convergent loop.
+//   1. refill   idle lanes pull the next rays from the queue with one aggregated atomic, so lanes whose rays finish
+//               early do not wait for the slowest ray of the warp;
+//   2. nodes    every lane with a ray performs RB_CHUNK wide-node steps (~23 of 32 lanes active) and queues the
+//               triangle groups they produce;
+//   3. triangles the warp pools ALL queued triangles of its 32 rays in shared memory and tests them 32 at a time,
+//               any lane testing any ray's triangle (ray data is staged in shared memory). A wide node yields ~0.5
+//               triangles, so per-lane triangle loops ran with 3-6 active lanes and were > 1/3 of all issued
+//               instructions; pooled, a chunk's ~90 triangles take 3 rounds instead of ~16 iterations.
+//               Closest hits are merged per ray with a 64-bit shared-memory atomicMin on (t bits << 32 | primitive id),
+//               which is exactly the closest-hit rule above.
 #pragma once
 #include "common.cuh"
 
@@ -37,8 +42,19 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
 #define RB_REFILL 32      // refill when fewer than this many lanes own a ray
 #endif
 #ifndef RB_CHUNK
-#define RB_CHUNK 8        // wide-node steps a lane performs between two warp-level refill checks (swept 2..24 on B200)
+#define RB_CHUNK 6        // wide-node steps a lane performs between two triangle phases (swept 2..24 on B200)
 #endif
+#ifndef RB_WORK_CAP
+#define RB_WORK_CAP 128   // pooled triangles per pass (a chunk produces ~90 per warp; more are handled by extra passes)
+#endif
+
+// per-warp staging area of the pooled triangle phase
+struct WarpShared {
+    float4 ray[32][4];                    // per lane: (o, tmax), shear rows mx, my, mz (rb_tri.h)
+    uint2 work[RB_WORK_CAP];              // (triangle index, owner lane)
+    unsigned long long bestKey[32];       // per owner: min over candidates of (t bits << 32 | global primitive id)
+    float4 payload[32];                   // per owner: b1, b2, bits(triangle index) of the current best
+};
 
 // per byte: 0xFF if bit 7 is set, else 0x00 (prmt's sign-replicate mode; __byte_perm only honours 3 selector bits)
 __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
@@ -58,16 +74,15 @@ template <bool ANY, bool COUNT>
 struct Traversal {
     rb_v3 o;
     float idx, idy, idz, tmax;
-    rb_ray_shear shear;
     uint32_t oct_inv;
     uint2 ngroup, tgroup;
-    int sp;
+    int sp, tsp;
+    uint32_t tcount;              // triangles queued in tgroup + tstack
     RayHit best;
     uint2 stack[TRAV_STACK];
-    uint2 tstack[RB_CHUNK];   // triangle groups found during the current chunk of node steps, tested together
-    int tsp;
+    uint2 tstack[RB_CHUNK];       // triangle groups produced by the node steps of the current chunk
 
-    __device__ __forceinline__ void init(const rb_v3 org, const rb_v3 d, const float tmax_) {
+    __device__ __forceinline__ void init(const rb_v3 org, const rb_v3 d, const float tmax_, float4* rayStage) {
         o = org; tmax = tmax_;
         best.t = tmax_; best.b1 = 0.f; best.b2 = 0.f; best.tri = 0xFFFFFFFFu; best.gid = 0xFFFFFFFFu;
         const float ooeps = 8.2718061e-25f;   // 2^-80: keeps 1/d finite for axis-parallel rays (box tests only)
@@ -75,14 +90,17 @@ struct Traversal {
         idy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
         idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
         oct_inv = (idx < 0.f ? 0u : 4u) | (idy < 0.f ? 0u : 2u) | (idz < 0.f ? 0u : 1u);
-        shear = rb_ray_prepare(d);
-        sp = 0; tsp = 0;
+        const rb_ray_shear sh = rb_ray_prepare(d);
+        rayStage[0] = make_float4(org.x, org.y, org.z, tmax_);
+        rayStage[1] = make_float4(sh.mx.x, sh.mx.y, sh.mx.z, 0.f);
+        rayStage[2] = make_float4(sh.my.x, sh.my.y, sh.my.z, 0.f);
+        rayStage[3] = make_float4(sh.mz.x, sh.mz.y, sh.mz.z, 0.f);
+        sp = 0; tsp = 0; tcount = 0;
         ngroup = make_uint2(0u, 0x80000000u);
         tgroup = make_uint2(0u, 0u);
     }
 
     __device__ __forceinline__ bool want_node() const { return ngroup.y > 0x00FFFFFFu; }
-    __device__ __forceinline__ bool want_tri() const { return tgroup.y != 0u || tsp > 0; }
 
     // No node group current: take the next one from the stack. Returns false when no node work is left.
     __device__ __forceinline__ bool pop() {
@@ -91,8 +109,17 @@ struct Traversal {
         return true;
     }
 
+    // next queued triangle index; requires tcount > 0
+    __device__ __forceinline__ uint32_t take_tri() {
+        if (tgroup.y == 0u) tgroup = tstack[--tsp];
+        const uint32_t ti = 31u - (uint32_t)__clz(tgroup.y);
+        tgroup.y &= ~(1u << ti);
+        tcount--;
+        return tgroup.x + ti;
+    }
+
     // Pop the nearest pending child of the current node group and test its 8 children; the triangles it yields are
-    // queued on tstack (tested later, together with those of the other node steps of the chunk). Requires want_node().
+    // queued on tstack for the warp's pooled triangle phase. Requires want_node().
     __device__ __forceinline__ void node_step(const WideNode* __restrict__ nodes, uint32_t& nodeVisits) {
         const uint32_t hits = ngroup.y;
         const uint32_t bitIndex = 31u - (uint32_t)__clz(hits);
@@ -155,31 +182,15 @@ struct Traversal {
             }
         }
         ngroup.y = (hitmask & 0xFF000000u) | (eim >> 24);
-        if (hitmask & 0x00FFFFFFu) tstack[tsp++] = make_uint2(__float_as_uint(n1.y), hitmask & 0x00FFFFFFu);
-    }
-
-    // Test one pending triangle. Returns true when an any-hit query is decided. Requires want_tri().
-    __device__ __forceinline__ bool tri_step(const TriRecord* __restrict__ tris, uint32_t& triTests) {
-        if (tgroup.y == 0u) tgroup = tstack[--tsp];
-        const uint32_t ti = 31u - (uint32_t)__clz(tgroup.y);
-        tgroup.y &= ~(1u << ti);
-        const uint32_t triIdx = tgroup.x + ti;
-        const float4* tp = reinterpret_cast<const float4*>(tris + triIdx);
-        const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
-        if (COUNT) triTests++;
-        float t, b1, b2;
-        if (rb_tri_intersect(o, shear, rb_mk3(a.x, a.y, a.z), rb_mk3(b.x, b.y, b.z), rb_mk3(c.x, c.y, c.z), &t, &b1, &b2)) {
-            if (t > 0.0f && t < tmax) {
-                const uint32_t gid = __float_as_uint(c.w);
-                if (ANY) { best.t = t; best.tri = triIdx; best.gid = gid; return true; }
-                if (t < best.t || (t == best.t && gid < best.gid)) {
-                    best.t = t; best.b1 = b1; best.b2 = b2; best.tri = triIdx; best.gid = gid;
-                }
-            }
-        }
-        return false;
+        const uint32_t tmask = hitmask & 0x00FFFFFFu;
+        if (tmask) { tstack[tsp++] = make_uint2(__float_as_uint(n1.y), tmask); tcount += (uint32_t)__popc(tmask); }
     }
 };
+
+// t > 0 always, so its bit pattern orders like the value; ties fall to the smaller global primitive id
+__device__ __forceinline__ unsigned long long hit_key(float t, uint32_t gid) {
+    return ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)gid;
+}
 
 // Warp-cooperative persistent trace loop (see the header comment).
 //   fetch(i)      -> load ray i into (o, d, tmax); called for i < n
@@ -187,13 +198,15 @@ struct Traversal {
 template <bool ANY, bool COUNT, class Fetch, class Commit>
 __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, const TriRecord* __restrict__ tris,
                                             uint32_t n, uint32_t* cursor, Fetch fetch, Commit commit,
-                                            uint32_t& nodeVisits, uint32_t& triTests) {
+                                            uint32_t& nodeVisits, uint32_t& triTests, WarpShared& ws) {
     const uint32_t lane = threadIdx.x & 31u;
     Traversal<ANY, COUNT> tr;
+    tr.tcount = 0;
     bool has = false;
     bool exhausted = false;
     uint32_t rayIdx = 0;
     for (;;) {
+        // ---- 1. refill ----
         uint32_t busy = __ballot_sync(0xffffffffu, has);
         if (!exhausted && __popc(busy) < RB_REFILL) {
             const uint32_t need = ~busy;
@@ -205,7 +218,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                 if (i < n) {
                     rb_v3 o, d; float tmax;
                     fetch(i, o, d, tmax);
-                    tr.init(o, d, tmax);
+                    tr.init(o, d, tmax, ws.ray[lane]);
                     rayIdx = i; has = true;
                 }
             }
@@ -214,37 +227,89 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
         }
         if (busy == 0u) break;
 
+        // ---- 2. a chunk of wide-node steps per lane ----
         if (has) {
-            bool done = false;
 #pragma unroll 1
             for (int it = 0; it < RB_CHUNK; it++) {
                 if (!tr.want_node() && !tr.pop()) break;
                 tr.node_step(nodes, nodeVisits);
             }
-            // the triangles of the whole chunk in one loop: more lanes have work at the same time
-            while (tr.want_tri()) {
-                if (tr.tri_step(tris, triTests)) { done = true; break; }
+        }
+
+        // ---- 3. pooled triangle phase ----
+        bool anyHitFound = false;
+        for (;;) {
+            const uint32_t c = has ? tr.tcount : 0u;
+            uint32_t incl = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+                if ((int)lane >= off) incl += v;
             }
-            if (!done && !tr.want_node() && tr.sp == 0) done = true;
-            if (done) { commit(rayIdx, tr.best); has = false; }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total == 0u) break;
+            uint32_t pos = incl - c;
+            const unsigned long long seed = has ? hit_key(tr.best.t, tr.best.gid) : ~0ull;
+            ws.bestKey[lane] = seed;
+            while (has && tr.tcount > 0u && pos < (uint32_t)RB_WORK_CAP) ws.work[pos++] = make_uint2(tr.take_tri(), lane);
+            __syncwarp();
+            const uint32_t count = min(total, (uint32_t)RB_WORK_CAP);
+            for (uint32_t b = 0; b < count; b += 32u) {
+                bool cand = false;
+                unsigned long long mykey = 0ull;
+                uint32_t owner = 0, triIdx = 0;
+                float b1 = 0.f, b2 = 0.f;
+                if (b + lane < count) {
+                    const uint2 item = ws.work[b + lane];
+                    triIdx = item.x; owner = item.y;
+                    const float4 r0 = ws.ray[owner][0], r1 = ws.ray[owner][1], r2 = ws.ray[owner][2], r3 = ws.ray[owner][3];
+                    const float4* tp = reinterpret_cast<const float4*>(tris + triIdx);
+                    const float4 va = __ldg(tp + 0), vb = __ldg(tp + 1), vc = __ldg(tp + 2);
+                    if (COUNT) triTests++;
+                    rb_ray_shear sh;
+                    sh.mx = rb_mk3(r1.x, r1.y, r1.z); sh.my = rb_mk3(r2.x, r2.y, r2.z); sh.mz = rb_mk3(r3.x, r3.y, r3.z);
+                    float t;
+                    if (rb_tri_intersect(rb_mk3(r0.x, r0.y, r0.z), sh, rb_mk3(va.x, va.y, va.z), rb_mk3(vb.x, vb.y, vb.z),
+                                         rb_mk3(vc.x, vc.y, vc.z), &t, &b1, &b2)) {
+                        if (t > 0.0f && t < r0.w) {
+                            mykey = hit_key(t, __float_as_uint(vc.w));
+                            atomicMin(&ws.bestKey[owner], mykey);
+                            cand = true;
+                        }
+                    }
+                }
+                if (!ANY) {
+                    __syncwarp();
+                    if (cand && ws.bestKey[owner] == mykey) ws.payload[owner] = make_float4(b1, b2, __uint_as_float(triIdx), 0.f);
+                }
+            }
+            __syncwarp();
+            if (has) {
+                const unsigned long long k = ws.bestKey[lane];
+                if (k != seed) {
+                    if (ANY) anyHitFound = true;
+                    else {
+                        const float4 p = ws.payload[lane];
+                        tr.best.t = __uint_as_float((uint32_t)(k >> 32)); tr.best.gid = (uint32_t)k;
+                        tr.best.b1 = p.x; tr.best.b2 = p.y; tr.best.tri = __float_as_uint(p.z);
+                    }
+                }
+            }
+            __syncwarp();     // bestKey / work are rewritten by the next pass
+            if (total <= (uint32_t)RB_WORK_CAP) break;
+        }
+
+        // ---- finished rays ----
+        if (has) {
+            if (ANY && anyHitFound) {
+                tr.best.tri = 0u;     // any-hit: only "occluded or not" is meaningful
+                commit(rayIdx, tr.best); has = false; tr.tcount = 0u;
+            } else if (!tr.want_node() && tr.sp == 0 && tr.tcount == 0u) {
+                commit(rayIdx, tr.best); has = false;
+            }
         }
         __syncwarp();
     }
-}
-
-// plain one-ray traversal (kept for callers that own exactly one ray per thread)
-template <bool ANY, bool COUNT>
-__device__ __forceinline__ void traverse(const WideNode* __restrict__ nodes, const TriRecord* __restrict__ tris,
-                                         const rb_v3 o, const rb_v3 d, const float tmax, RayHit& best,
-                                         uint32_t& nodeVisits, uint32_t& triTests) {
-    Traversal<ANY, COUNT> tr;
-    tr.init(o, d, tmax);
-    for (;;) {
-        if (tr.want_tri()) { if (tr.tri_step(tris, triTests)) break; }
-        else if (tr.want_node()) tr.node_step(nodes, nodeVisits);
-        else if (!tr.pop()) break;
-    }
-    best = tr.best;
 }
 
 } // namespace rb200

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(BLOCK, RB_TRAV_MINBLOCKS) k_extend(WaveParams 
     const uint32_t* __restrict__ q = P.rayQ[parity];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_EXTEND], (unsigned long long)n);
     uint32_t nodeVisits = 0, triTests = 0;
+    __shared__ WarpShared ws[BLOCK / 32];
     trace_queue<false, COUNT>(
         P.S.nodes, P.S.tris, n, &cnt[CNT_CURSOR_EXTEND],
         [&](uint32_t i, rb_v3& o, rb_v3& d, float& tmax) {
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(BLOCK, RB_TRAV_MINBLOCKS) k_extend(WaveParams 
             for (uint32_t b = 0; b < 5; b++)
                 if (bin == b) queue_push(P.matQ[b], &cnt[CNT_MAT0 + b], slot);
         },
-        nodeVisits, triTests);
+        nodeVisits, triTests, ws[threadIdx.x >> 5]);
     if (COUNT) {
         atomicAdd(&P.stats[ST_NODES], (unsigned long long)nodeVisits);
         atomicAdd(&P.stats[ST_TRIS], (unsigned long long)triTests);
@@ -397,6 +398,7 @@ __global__ void __launch_bounds__(BLOCK, RB_TRAV_MINBLOCKS) k_shadow(WaveParams 
     const uint32_t n = cnt[CNT_SHADOW];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_SHADOW], (unsigned long long)n);
     uint32_t nodeVisits = 0, triTests = 0;
+    __shared__ WarpShared ws[BLOCK / 32];
     trace_queue<true, COUNT>(
         P.S.nodes, P.S.tris, n, &cnt[CNT_CURSOR_SHADOW],
         [&](uint32_t i, rb_v3& o, rb_v3& d, float& tmax) {
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(BLOCK, RB_TRAV_MINBLOCKS) k_shadow(WaveParams 
             const rb_v3 L = rb_mk3(L4.x, L4.y, L4.z) + combined * rb_mk3(T.x, T.y, T.z);
             P.rad[slot] = make_float4(L.x, L.y, L.z, 0.f);
         },
-        nodeVisits, triTests);
+        nodeVisits, triTests, ws[threadIdx.x >> 5]);
     if (COUNT) {
         atomicAdd(&P.stats[ST_NODES], (unsigned long long)nodeVisits);
         atomicAdd(&P.stats[ST_TRIS], (unsigned long long)triTests);
@@ -623,6 +625,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace_query(const WideNode* nodes, co
                                                        const float4* __restrict__ o, const float4* __restrict__ d,
                                                        RB200PrimaryHit* __restrict__ out, uint32_t* cursor) {
     uint32_t nv = 0, tt = 0;
+    __shared__ WarpShared ws[BLOCK / 32];
     trace_queue<ANY, false>(
         nodes, tris, n, cursor,
         [&](uint32_t i, rb_v3& ro, rb_v3& rd, float& tmax) {
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace_query(const WideNode* nodes, co
             } else { r.t = -1.0f; r.u = r.v = 0.f; r.primitive = r.instance = 0xFFFFFFFFu; }
             out[i] = r;
         },
-        nv, tt);
+        nv, tt, ws[threadIdx.x >> 5]);
 }
 
 static int run_query(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float4* dO, const float4* dD, int any,
