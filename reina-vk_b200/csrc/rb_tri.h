@@ -26,6 +26,7 @@ struct rb_ray_shear {
      * (Woop et al. 2013, eq. 2-3); stored as dense rows so a vertex needs 3 multiply-adds per coordinate and no
      * per-vertex axis selects. */
     rb_v3 mx, my, mz;
+    float Sz; int kz;          /* mz = Sz e_kz, kept so the row can be stored in two words */
 };
 
 RB_HD float rb_sel3(rb_v3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
@@ -45,6 +46,7 @@ RB_HD rb_ray_shear rb_ray_prepare(rb_v3 d) {
     s.mx = rb_axis3(kx, 1.0f) + rb_axis3(kz, -Sx);
     s.my = rb_axis3(ky, 1.0f) + rb_axis3(kz, -Sy);
     s.mz = rb_axis3(kz, Sz);
+    s.Sz = Sz; s.kz = kz;
     return s;
 }
 

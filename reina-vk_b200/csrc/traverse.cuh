@@ -50,7 +50,7 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
 
 // per-warp staging area of the pooled triangle phase
 struct WarpShared {
-    float4 ray[32][4];                    // per lane: (o, tmax), shear rows mx, my, mz (rb_tri.h)
+    float4 ray[32][3];                    // per lane: (o, tmax), (mx, Sz), (my, bits(kz)) — shear rows of rb_tri.h
     uint2 work[RB_WORK_CAP];              // (triangle index, owner lane)
     unsigned long long bestKey[32];       // per owner: min over candidates of (t bits << 32 | global primitive id)
     float4 payload[32];                   // per owner: b1, b2, bits(triangle index) of the current best
@@ -92,9 +92,8 @@ struct Traversal {
         oct_inv = (idx < 0.f ? 0u : 4u) | (idy < 0.f ? 0u : 2u) | (idz < 0.f ? 0u : 1u);
         const rb_ray_shear sh = rb_ray_prepare(d);
         rayStage[0] = make_float4(org.x, org.y, org.z, tmax_);
-        rayStage[1] = make_float4(sh.mx.x, sh.mx.y, sh.mx.z, 0.f);
-        rayStage[2] = make_float4(sh.my.x, sh.my.y, sh.my.z, 0.f);
-        rayStage[3] = make_float4(sh.mz.x, sh.mz.y, sh.mz.z, 0.f);
+        rayStage[1] = make_float4(sh.mx.x, sh.mx.y, sh.mx.z, sh.Sz);
+        rayStage[2] = make_float4(sh.my.x, sh.my.y, sh.my.z, __int_as_float(sh.kz));
         sp = 0; tsp = 0; tcount = 0;
         ngroup = make_uint2(0u, 0x80000000u);
         tgroup = make_uint2(0u, 0u);
@@ -262,12 +261,12 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                 if (b + lane < count) {
                     const uint2 item = ws.work[b + lane];
                     triIdx = item.x; owner = item.y;
-                    const float4 r0 = ws.ray[owner][0], r1 = ws.ray[owner][1], r2 = ws.ray[owner][2], r3 = ws.ray[owner][3];
+                    const float4 r0 = ws.ray[owner][0], r1 = ws.ray[owner][1], r2 = ws.ray[owner][2];
                     const float4* tp = reinterpret_cast<const float4*>(tris + triIdx);
                     const float4 va = __ldg(tp + 0), vb = __ldg(tp + 1), vc = __ldg(tp + 2);
                     if (COUNT) triTests++;
                     rb_ray_shear sh;
-                    sh.mx = rb_mk3(r1.x, r1.y, r1.z); sh.my = rb_mk3(r2.x, r2.y, r2.z); sh.mz = rb_mk3(r3.x, r3.y, r3.z);
+                    sh.mx = rb_mk3(r1.x, r1.y, r1.z); sh.my = rb_mk3(r2.x, r2.y, r2.z); sh.mz = rb_axis3(__float_as_int(r2.w), r1.w);
                     float t;
                     if (rb_tri_intersect(rb_mk3(r0.x, r0.y, r0.z), sh, rb_mk3(va.x, va.y, va.z), rb_mk3(vb.x, vb.y, vb.z),
                                          rb_mk3(vc.x, vc.y, vc.z), &t, &b1, &b2)) {
