@@ -12,7 +12,6 @@
 // min/max), so node and triangle arrays are bit-identical across runs and GPUs (hash exposed in RB200BvhInfo).
 #include "common.cuh"
 #include <algorithm>
-#include <stdlib.h>
 
 namespace rb200 {
 
@@ -434,98 +433,6 @@ __global__ void k_place_triangles(WideNode* nodes, uint32_t numNodes, const uint
     }
 }
 
-
-// ---------------------------------------------------------------------------------------------------
-// EXPERIMENT ONLY (RB200_EXPERIMENT_HOST_SAH=1): binned-SAH binary tree built on the host and fed to the same GPU
-// collapse, to measure how much traversal speed the LBVH's quality leaves on the table. Not a product path.
-// ---------------------------------------------------------------------------------------------------
-namespace {
-struct HostSah {
-    std::vector<TriRecord> tris;          // in: unsorted; out: leaf order
-    std::vector<uint32_t> childL, childR, rFirst, rLast;
-    std::vector<float4> nodeLo, nodeHi, leafLo, leafHi;
-    std::vector<uint32_t> order;
-    std::vector<float> bl, bh, cen;       // per input triangle: box lo/hi, centre (3 each)
-
-    static void grow(float* lo, float* hi, const float* l, const float* h) {
-        for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], l[a]); hi[a] = std::max(hi[a], h[a]); }
-    }
-    static double area(const float* lo, const float* hi) {
-        double dx = (double)hi[0] - lo[0], dy = (double)hi[1] - lo[1], dz = (double)hi[2] - lo[2];
-        return dx < 0 ? 0.0 : dx * dy + dy * dz + dz * dx;
-    }
-    uint32_t build(uint32_t first, uint32_t count) {      // returns a ref
-        if (count == 1) return LEAF_FLAG | first;
-        const uint32_t me = (uint32_t)childL.size();
-        childL.push_back(0); childR.push_back(0); rFirst.push_back(first); rLast.push_back(first + count - 1);
-        nodeLo.push_back(make_float4(0, 0, 0, 0)); nodeHi.push_back(make_float4(0, 0, 0, 0));
-        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f}, clo[3] = {3e38f, 3e38f, 3e38f}, chi[3] = {-3e38f, -3e38f, -3e38f};
-        for (uint32_t i = first; i < first + count; i++) {
-            const uint32_t t = order[i];
-            grow(lo, hi, &bl[3 * t], &bh[3 * t]); grow(clo, chi, &cen[3 * t], &cen[3 * t]);
-        }
-        nodeLo[me] = make_float4(lo[0], lo[1], lo[2], 0); nodeHi[me] = make_float4(hi[0], hi[1], hi[2], 0);
-        const int NB = 16; int bestAxis = -1, bestSplit = -1; double bestCost = 1e300;
-        for (int a = 0; a < 3; a++) {
-            if (!(chi[a] > clo[a])) continue;
-            float blo[NB][3], bhi[NB][3]; uint32_t cnt[NB];
-            for (int b = 0; b < NB; b++) { cnt[b] = 0; for (int k = 0; k < 3; k++) { blo[b][k] = 3e38f; bhi[b][k] = -3e38f; } }
-            const float scale = NB / (chi[a] - clo[a]);
-            for (uint32_t i = first; i < first + count; i++) {
-                const uint32_t t = order[i];
-                const int b = std::min(NB - 1, (int)((cen[3 * t + a] - clo[a]) * scale));
-                grow(blo[b], bhi[b], &bl[3 * t], &bh[3 * t]); cnt[b]++;
-            }
-            double la[NB], ra[NB]; uint32_t lc[NB], rc[NB];
-            float l0[3] = {3e38f, 3e38f, 3e38f}, l1[3] = {-3e38f, -3e38f, -3e38f}, r0[3] = {3e38f, 3e38f, 3e38f}, r1[3] = {-3e38f, -3e38f, -3e38f};
-            uint32_t c0 = 0, c1 = 0;
-            for (int i = 0; i < NB - 1; i++) {
-                grow(l0, l1, blo[i], bhi[i]); c0 += cnt[i]; la[i] = area(l0, l1); lc[i] = c0;
-                grow(r0, r1, blo[NB - 1 - i], bhi[NB - 1 - i]); c1 += cnt[NB - 1 - i]; ra[NB - 2 - i] = area(r0, r1); rc[NB - 2 - i] = c1;
-            }
-            for (int i = 0; i < NB - 1; i++) {
-                if (!lc[i] || !rc[i]) continue;
-                const double cost = la[i] * lc[i] + ra[i] * rc[i];
-                if (cost < bestCost) { bestCost = cost; bestAxis = a; bestSplit = i; }
-            }
-        }
-        uint32_t mid = first + count / 2;
-        if (bestAxis >= 0) {
-            const float scale = NB / (chi[bestAxis] - clo[bestAxis]);
-            auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t t) {
-                return std::min(NB - 1, (int)((cen[3 * t + bestAxis] - clo[bestAxis]) * scale)) <= bestSplit; });
-            const uint32_t m = (uint32_t)(it - order.begin());
-            if (m != first && m != first + count) mid = m;
-        }
-        const uint32_t L = build(first, mid - first), R = build(mid, first + count - mid);
-        childL[me] = L; childR[me] = R;
-        return me;
-    }
-    void run() {
-        const uint32_t n = (uint32_t)tris.size();
-        bl.resize(3 * (size_t)n); bh.resize(3 * (size_t)n); cen.resize(3 * (size_t)n); order.resize(n);
-        for (uint32_t i = 0; i < n; i++) {
-            order[i] = i;
-            const float4 v[3] = {tris[i].v0, tris[i].v1, tris[i].v2};
-            const float xs[3] = {v[0].x, v[1].x, v[2].x}, ys[3] = {v[0].y, v[1].y, v[2].y}, zs[3] = {v[0].z, v[1].z, v[2].z};
-            bl[3 * i] = std::min({xs[0], xs[1], xs[2]}); bh[3 * i] = std::max({xs[0], xs[1], xs[2]});
-            bl[3 * i + 1] = std::min({ys[0], ys[1], ys[2]}); bh[3 * i + 1] = std::max({ys[0], ys[1], ys[2]});
-            bl[3 * i + 2] = std::min({zs[0], zs[1], zs[2]}); bh[3 * i + 2] = std::max({zs[0], zs[1], zs[2]});
-            for (int a = 0; a < 3; a++) cen[3 * i + a] = 0.5f * (bl[3 * i + a] + bh[3 * i + a]);
-        }
-        build(0, n);
-        std::vector<TriRecord> sorted(n);
-        leafLo.resize(n); leafHi.resize(n);
-        for (uint32_t i = 0; i < n; i++) {
-            const uint32_t t = order[i];
-            sorted[i] = tris[t];
-            leafLo[i] = make_float4(bl[3 * t], bl[3 * t + 1], bl[3 * t + 2], 0); leafHi[i] = make_float4(bh[3 * t], bh[3 * t + 1], bh[3 * t + 2], 0);
-        }
-        tris.swap(sorted);
-    }
-};
-} // namespace
-
 // ---------------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------------
@@ -565,26 +472,8 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
 
     const uint32_t B = 256, G = (N + B - 1) / B;
     k_flatten<<<G, B, 0, stream>>>(in.vertices, in.indices, in.d_instances, dPrefix, in.numInstances, N, unsorted, dBounds); nl++;
-    const bool hostSah = getenv("RB200_EXPERIMENT_HOST_SAH") != nullptr && N > 1;
-    if (hostSah) {
-        HostSah h; h.tris.resize(N);
-        RB_CUDA(cudaMemcpyAsync(h.tris.data(), unsorted, (size_t)N * sizeof(TriRecord), cudaMemcpyDeviceToHost, stream));
-        RB_CUDA(cudaStreamSynchronize(stream));
-        h.run();
-        const size_t ni = h.childL.size();
-        RB_CUDA(cudaMemcpy(sorted, h.tris.data(), (size_t)N * sizeof(TriRecord), cudaMemcpyHostToDevice));
-        RB_CUDA(cudaMemcpy(leafLo, h.leafLo.data(), (size_t)N * sizeof(float4), cudaMemcpyHostToDevice));
-        RB_CUDA(cudaMemcpy(leafHi, h.leafHi.data(), (size_t)N * sizeof(float4), cudaMemcpyHostToDevice));
-        RB_CUDA(cudaMemcpy(childL, h.childL.data(), ni * 4, cudaMemcpyHostToDevice));
-        RB_CUDA(cudaMemcpy(childR, h.childR.data(), ni * 4, cudaMemcpyHostToDevice));
-        RB_CUDA(cudaMemcpy(rFirst, h.rFirst.data(), ni * 4, cudaMemcpyHostToDevice));
-        RB_CUDA(cudaMemcpy(rLast, h.rLast.data(), ni * 4, cudaMemcpyHostToDevice));
-        RB_CUDA(cudaMemcpy(nodeLo, h.nodeLo.data(), ni * sizeof(float4), cudaMemcpyHostToDevice));
-        RB_CUDA(cudaMemcpy(nodeHi, h.nodeHi.data(), ni * sizeof(float4), cudaMemcpyHostToDevice));
-    }
     k_morton<<<G, B, 0, stream>>>(unsorted, N, dBounds, keys[0], vals[0]); nl++;
     int cur = 0;
-    if (!hostSah) {
     for (int pass = 0; pass < 8; pass++) {
         k_radix_hist<<<sortBlocks, SORT_BLOCK, 0, stream>>>(keys[cur], N, pass * 8, hist, sortBlocks); nl++;
         k_exclusive_scan<<<1, 1024, 0, stream>>>(hist, histScan, 256u * sortBlocks, nullptr); nl++;
@@ -593,8 +482,7 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
         cur ^= 1;
     }
     k_gather_sorted<<<G, B, 0, stream>>>(unsorted, vals[cur], N, sorted, leafLo, leafHi); nl++;
-    }
-    if (N > 1 && !hostSah) {
+    if (N > 1) {
         k_karras<<<G, B, 0, stream>>>(keys[cur], (int)N, childL, childR, parentInt, parentLeaf, rFirst, rLast); nl++;
         k_refit<<<G, B, 0, stream>>>(N, childL, childR, parentInt, parentLeaf, leafLo, leafHi, nodeLo, nodeHi, flags); nl++;
     }
