@@ -1,0 +1,363 @@
+"""The C++ headless host (reina-vk_b200/host/): SURVEY.md §8(f) row 1.
+
+CPU tests compare the C++ scene layer, OBJ importer, TOML reader, push-constant derivation, PNG writer and save
+policy with the Python host (same reference interfaces: src/scene/Scene.cpp:6-125, src/scene/Models.cpp:117-175,
+src/Reina.cpp:142-155, src/tools/SaveManager.cpp:6-44, src/tools/Clock.cpp:27-40) through the test hooks of
+host/capi.cpp. The GPU test runs the reina_b200 binary end to end and compares its PNG with the frame the Python
+host gets from the same library for the same push constants.
+"""
+import ctypes as C
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "reina-vk_b200", "host")
+
+REFERENCE_SCHEMA = """
+[camera.dof]
+focus_dist = 2.2
+defocus_multiplier = 1.5
+
+[sampling]
+samples_per_pixel = 8
+max_bounces = 16
+direct_clamp = 100
+indirect_clamp = 10
+
+[saving]
+save_on_samples = [64, 256, 1024]
+save_on_times = [60.0]
+
+[postprocessing.bloom]
+radius = 5.0
+threshold = 1.0
+intensity = 0.05
+
+[postprocessing.tonemap]
+exposure = 1
+"""
+
+
+class HostConfig(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("nee", C.c_uint32), ("samplesPerPixel", C.c_uint32),
+                ("maxBounces", C.c_uint32), ("numSaveSamples", C.c_uint32), ("numSaveTimes", C.c_uint32),
+                ("focusDist", C.c_float), ("defocusMultiplier", C.c_float), ("directClamp", C.c_float),
+                ("indirectClamp", C.c_float), ("bloomRadius", C.c_float), ("bloomThreshold", C.c_float),
+                ("bloomIntensity", C.c_float), ("exposure", C.c_float), ("cameraPos", C.c_double * 3),
+                ("cameraLookAt", C.c_double * 3), ("fovYDegrees", C.c_double), ("saveSamples", C.c_int32 * 16),
+                ("saveTimes", C.c_double * 16), ("scene", C.c_char * 64)]
+
+
+@pytest.fixture(scope="module")
+def host(rb):
+    so = os.path.join(HOST, "libreina_host.so")
+    if not os.path.exists(so) or not os.path.exists(os.path.join(HOST, "reina_b200")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "reina-vk_b200", "csrc")], check=True, capture_output=True)
+        subprocess.run(["make", "-C", HOST], check=True, capture_output=True)
+    lib = C.CDLL(so)
+    lib.rbhost_last_error.restype = C.c_char_p
+    lib.rbhost_png_encode.restype = C.c_int64
+    lib.rbhost_png_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]
+    lib.rbhost_tables_free.argtypes = [C.c_void_p]
+    lib.rbhost_tables_desc.argtypes = [C.c_void_p, C.POINTER(rb.abi.SceneDesc), C.POINTER(C.c_float)]
+    lib.rbhost_push_constants.argtypes = [C.c_char_p, C.c_float, C.POINTER(rb.abi.RtPushConsts)]
+    return lib
+
+
+def err(lib):
+    return lib.rbhost_last_error().decode()
+
+
+def arr(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype)
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dtype).itemsize,)).view(dtype).copy()
+
+
+def cpp_tables(lib, rb, handle):
+    """Snapshot the C++ tables behind `handle` as numpy arrays, keyed like SceneTables."""
+    d = rb.abi.SceneDesc()
+    w = C.c_float()
+    assert lib.rbhost_tables_desc(handle, C.byref(d), C.byref(w)) == 0, err(lib)
+    t = dict(
+        vertices=arr(d.vertices, d.numVertices * 4, np.float32), indices=arr(d.indices, d.numIndices, np.uint32),
+        instanceProperties=arr(d.instanceProperties, d.numInstanceProperties * 120, np.uint8),
+        tbns=arr(d.tbns, d.numTbns * 9, np.float32), tbnIndices=arr(d.tbnIndices, d.numTbnIndices, np.uint32),
+        emissive=arr(d.emissiveMetadata, d.numEmissive * 112, np.uint8),
+        cdfTriangles=arr(d.cdfTriangles, d.numCdfTriangles, np.float32),
+        cdfInstances=arr(d.cdfInstances, d.numCdfInstances, np.float32),
+        texCoords=arr(d.texCoords, d.numTexCoords * 2, np.float32), texIndices=arr(d.texIndices, d.numTexIndices, np.uint32),
+        instances=arr(d.instances, d.numInstances * 80, np.uint8), totalEmissiveWeight=w.value,
+        textures=[arr(d.textures[i].rgba8, d.textures[i].width * d.textures[i].height * 4, np.uint8)
+                  .reshape(d.textures[i].height, d.textures[i].width, 4) for i in range(d.numTextures)])
+    return t
+
+
+def py_tables(tb):
+    n_i, n_e, n_p = tb.numInstances, tb.numEmissive, tb.numInstanceProperties
+    return dict(vertices=tb.vertices.reshape(-1), indices=tb.indices, instanceProperties=tb.instanceProperties[:n_p * 120],
+                tbns=tb.tbns, tbnIndices=tb.tbnIndices, emissive=tb.emissive[:n_e * 112], cdfTriangles=tb.cdfTriangles,
+                cdfInstances=tb.cdfInstances, texCoords=tb.texCoords, texIndices=tb.texIndices,
+                instances=tb.instances[:n_i * 80], totalEmissiveWeight=tb.totalEmissiveWeight, textures=tb.textures)
+
+
+def assert_tables_identical(a, b, approx=()):
+    for k in a:
+        if k == "textures":
+            assert len(a[k]) == len(b[k])
+            for x, y in zip(a[k], b[k]):
+                assert x.shape == y.shape and (x == y).all()
+        elif k == "totalEmissiveWeight":
+            assert np.float32(a[k]) == np.float32(b[k])
+        elif k in approx:
+            assert a[k].shape == b[k].shape, k
+            np.testing.assert_allclose(a[k], b[k], rtol=0, atol=2e-7, err_msg=k)
+        else:
+            assert a[k].shape == b[k].shape, k
+            assert a[k].tobytes() == b[k].tobytes(), k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# scene layer
+# ---------------------------------------------------------------------------------------------------------------
+def test_cornell_tables_identical_to_python_host(host, rb):
+    h = C.c_void_p()
+    assert host.rbhost_tables_builtin(b"cornell", 1, C.byref(h)) == 0, err(host)
+    wl = rb.configs.cornell(96, 72, nee=True)
+    assert_tables_identical(cpp_tables(host, rb, h), py_tables(wl.tables))
+    host.rbhost_tables_free(h)
+
+
+def test_cornell_sphere_tables_match_python_host(host, rb):
+    """The sphere goes through sin/cos of two different maths libraries: positions/frames to 2e-7, the rest exact."""
+    h = C.c_void_p()
+    assert host.rbhost_tables_builtin(b"cornell-sphere", 1, C.byref(h)) == 0, err(host)
+    wl = rb.configs.cornell(96, 72, with_sphere=True, nee=True)
+    assert_tables_identical(cpp_tables(host, rb, h), py_tables(wl.tables), approx=("vertices", "tbns", "texCoords"))
+    host.rbhost_tables_free(h)
+
+
+def test_unknown_scene_and_missing_obj_fail_loudly(host):
+    h = C.c_void_p()
+    assert host.rbhost_tables_builtin(b"sponza", 1, C.byref(h)) != 0
+    assert "unknown built-in scene" in err(host)
+    assert host.rbhost_tables_obj(b"/nonexistent/model.obj", 0, 1, C.byref(h)) != 0
+    assert "Could not load model" in err(host)
+
+
+OBJ_FULL = """# cube-ish test asset: quads and a pentagon, v/vt/vn triples, relative indices, shared corners
+v -0.5 -0.5 0.5
+v 0.5 -0.5 0.5
+v 0.5 0.5 0.5
+v -0.5 0.5 0.5
+v -0.5 -0.5 -0.5
+v 0.5 -0.5 -0.5
+v 0.5 0.5 -0.5
+v -0.5 0.5 -0.5
+v 0.0 0.9 0.5   # apex of the pentagon
+vt 0.0 0.0
+vt 1.0 0.0
+vt 1.0 1.0
+vt 0.0 1.0
+vt 0.5 1.25
+vn 0 0 1
+vn 0 0 -1
+vn 1 0 0
+vn -1 0 0
+vn 0.0 0.70710678 0.70710678
+f 1/1/1 2/2/1 3/3/1 9/5/5 4/4/1
+f 6/1/2 5/2/2 8/3/2 7/4/2
+f 2/1/3 6/2/3 7/3/3 3/4/3
+f -5/1/4 -9/2/4 -6/3/4 -2/4/4
+"""
+
+OBJ_BARE = """v 0 0 0
+v 1 0 0
+v 1 1 0.1
+v 0 1 0
+v 0.5 0.5 1
+f 1 2 3 4
+f 1 2 5
+f 2 3 5
+f 3//  4// 5//
+"""
+
+
+@pytest.mark.parametrize("text, light", [(OBJ_FULL, 1), (OBJ_BARE, 0)])
+def test_obj_importer_identical_to_python_importer(host, rb, tmp_path, text, light):
+    import warnings
+    p = tmp_path / "asset.obj"
+    p.write_text(text)
+    h = C.c_void_p()
+    assert host.rbhost_tables_obj(str(p).encode(), 0, light, C.byref(h)) == 0, err(host)
+    s = rb.scene.Scene()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        md = rb.meshes.load_obj(str(p))
+    s.addObject(md, np.eye(4, dtype=np.float32), rb.scene.Material(albedo=(0.8, 0.8, 0.8), interpNormals=True))
+    if light:
+        s.addObject(rb.meshes.cornell_light(), np.eye(4, dtype=np.float32), rb.scene.Material(**rb.configs.LIGHT))
+    assert_tables_identical(cpp_tables(host, rb, h), py_tables(s.build()))
+    host.rbhost_tables_free(h)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# configuration
+# ---------------------------------------------------------------------------------------------------------------
+def test_config_reads_the_reference_schema(host):
+    c = HostConfig()
+    assert host.rbhost_config_parse(REFERENCE_SCHEMA.encode(), C.byref(c)) == 0, err(host)
+    assert (c.samplesPerPixel, c.maxBounces) == (8, 16)
+    assert (c.focusDist, c.defocusMultiplier) == (np.float32(2.2), np.float32(1.5))
+    assert (c.directClamp, c.indirectClamp) == (100.0, 10.0)          # integers convert to float
+    assert (c.bloomRadius, c.bloomThreshold, c.bloomIntensity, c.exposure) == (5.0, 1.0, np.float32(0.05), 1.0)
+    assert list(c.saveSamples[:c.numSaveSamples]) == [64, 256, 1024]
+    assert list(c.saveTimes[:c.numSaveTimes]) == [60.0]
+    assert (c.width, c.height, c.scene) == (800, 600, b"cornell")     # [render] defaults
+
+
+def test_repo_config_file_parses(host):
+    c = HostConfig()
+    text = open(os.path.join(ROOT, "config", "config.toml")).read()
+    assert host.rbhost_config_parse(text.encode(), C.byref(c)) == 0, err(host)
+    assert c.nee == 1 and list(c.cameraPos) == [0.0, 1.0, 3.9] and c.fovYDegrees == 40.0
+
+
+def test_config_every_reference_key_is_required(host):
+    """at_path(...).value<T>().value() on a missing key ends start-up (std::bad_optional_access in the reference)."""
+    keys = ["focus_dist", "defocus_multiplier", "samples_per_pixel", "max_bounces", "direct_clamp", "indirect_clamp",
+            "save_on_samples", "save_on_times", "radius", "threshold", "intensity", "exposure"]
+    for k in keys:
+        text = "\n".join(l for l in REFERENCE_SCHEMA.splitlines() if not l.startswith(k + " "))
+        c = HostConfig()
+        assert host.rbhost_config_parse(text.encode(), C.byref(c)) != 0, k
+        assert "missing key" in err(host) and k in err(host)
+
+
+def test_config_type_rules_and_syntax(host):
+    c = HostConfig()
+    bad = REFERENCE_SCHEMA.replace("samples_per_pixel = 8", "samples_per_pixel = 8.0")     # float -> uint32: refused
+    assert host.rbhost_config_parse(bad.encode(), C.byref(c)) != 0 and "not an integer" in err(host)
+    bad = REFERENCE_SCHEMA.replace("save_on_samples = [64, 256, 1024]", "save_on_samples = 64")
+    assert host.rbhost_config_parse(bad.encode(), C.byref(c)) != 0 and "not an array" in err(host)
+    bad = REFERENCE_SCHEMA.replace("radius = 5.0", "radius = 5.0\nradius = 6.0")
+    assert host.rbhost_config_parse(bad.encode(), C.byref(c)) != 0 and "defined twice" in err(host)
+    bad = REFERENCE_SCHEMA.replace("exposure = 1", "exposure = 1 2")
+    assert host.rbhost_config_parse(bad.encode(), C.byref(c)) != 0 and "line" in err(host)
+    ok = REFERENCE_SCHEMA.replace("save_on_samples = [64, 256, 1024]",
+                                  "save_on_samples = [  # thresholds\n  1_024,\n  64, # small\n  256,\n]")
+    ok += '\n[render]\nwidth = 0x140\nheight = 200\nscene = "cornell-sphere"\nnee = false\ncamera_pos = [1, 2.5, -3e0]\n'
+    assert host.rbhost_config_parse(ok.encode(), C.byref(c)) == 0, err(host)
+    assert list(c.saveSamples[:c.numSaveSamples]) == [1024, 64, 256]
+    assert (c.width, c.height, c.scene, c.nee) == (320, 200, b"cornell-sphere", 0)
+    assert list(c.cameraPos) == [1.0, 2.5, -3.0]
+
+
+def test_push_constants_match_python_host(host, rb):
+    pc = rb.abi.RtPushConsts()
+    text = REFERENCE_SCHEMA + "\n[render]\nwidth = 640\nheight = 360\ncamera_pos = [-1.6899, 0.817017, -1.6386]\n" \
+                              "camera_look_at = [0.0, 0.6, 0.0]\nfov_y_degrees = 30.0\n"
+    assert host.rbhost_push_constants(text.encode(), 7.5, C.byref(pc)) == 0, err(host)
+    ref = rb.camera.push_constants(640, 360, (-1.6899, 0.817017, -1.6386), (0.0, 0.6, 0.0), 30.0, total_emissive_weight=7.5)
+    np.testing.assert_allclose(np.array(pc.invView[:]), np.array(ref.invView[:]), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(np.array(pc.invProjection[:]), np.array(ref.invProjection[:]), rtol=1e-6, atol=1e-6)
+    for f in ("sampleBatch", "totalEmissiveWeight", "focusDist", "defocusMultiplier", "directClamp", "indirectClamp",
+              "samplesPerPixel", "maxBounces"):
+        assert getattr(pc, f) == getattr(ref, f), f
+    assert pc.defocusMultiplier == np.float32(np.float32(1.5) / np.float32(100.0))    # src/Reina.cpp:150
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PNG + save policy
+# ---------------------------------------------------------------------------------------------------------------
+def decode_png(data):
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, chunks = 8, []
+    while pos < len(data):
+        n, typ = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        crc, = struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])
+        assert zlib.crc32(typ + body) == crc, typ
+        chunks.append((typ, body))
+        pos += 12 + n
+    assert [c[0] for c in chunks][0] == b"IHDR" and chunks[-1] == (b"IEND", b"")
+    w, h, depth, ctype, comp, filt, inter = struct.unpack(">IIBBBBB", chunks[0][1])
+    assert (depth, ctype, comp, filt, inter) == (8, 6, 0, 0, 0)
+    raw = zlib.decompress(b"".join(b for t, b in chunks if t == b"IDAT"))
+    rows = np.frombuffer(raw, np.uint8).reshape(h, 1 + 4 * w)
+    assert (rows[:, 0] == 0).all()
+    return rows[:, 1:].reshape(h, w, 4)
+
+
+def test_png_round_trip(host):
+    rng = np.random.default_rng(5)
+    for (h, w) in [(1, 1), (7, 13), (72, 96)]:
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        out = np.zeros(h * w * 4 + 4096, np.uint8)
+        n = host.rbhost_png_encode(img.ctypes.data, w, h, out.ctypes.data, out.size)
+        assert 0 < n <= out.size, err(host)
+        assert (decode_png(out[:n].tobytes()) == img).all()
+    assert host.rbhost_png_encode(None, 0, 0, out.ctypes.data, out.size) < 0 and "Could not save PNG" in err(host)
+
+
+def schedule(host, samples, times, frames, spp, dt):
+    s = (C.c_int32 * max(1, len(samples)))(*samples)
+    t = (C.c_double * max(1, len(times)))(*times)
+    buf = C.create_string_buffer(4096)
+    assert host.rbhost_save_schedule(s, len(samples), t, len(times), frames, spp, C.c_double(dt), buf, 4096) == 0, err(host)
+    return [(int(l.split(":")[0]), l.split(":")[1]) for l in buf.value.decode().splitlines()]
+
+
+def test_save_policy_follows_the_reference_clock(host):
+    """SaveManager fires on `threshold < samples` with Clock's counter, which skips the first frame's samples and is
+    read before markFrame: with 8 spp the 64-sample file is written in frame 10 (0-based), the 256 one in frame 34."""
+    got = schedule(host, [256, 64], [], 40, 8, 0.0)
+    assert got == [(10, "output_64spp.png"), (34, "output_256spp.png")]
+    # one save per frame, samples before times, times named by truncation, strictly-greater comparison
+    got = schedule(host, [8], [0.5, 2.9], 8, 8, 0.5)
+    assert got == [(1, "output_0sec.png"), (3, "output_8spp.png"), (5, "output_2sec.png")]
+    assert schedule(host, [], [], 5, 8, 1.0) == []
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# end to end on the GPU
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_cli_renders_cornell_like_the_python_host(host, rb, tmp_path):
+    cfg = tmp_path / "config.toml"
+    cfg.write_text(REFERENCE_SCHEMA.replace("samples_per_pixel = 8", "samples_per_pixel = 4")
+                   .replace("save_on_samples = [64, 256, 1024]", "save_on_samples = [8]")
+                   .replace("save_on_times = [60.0]", "save_on_times = []")
+                   + "\n[render]\nwidth = 96\nheight = 72\nscene = \"cornell\"\nnee = true\n")
+    out, pcfile = tmp_path / "final.png", tmp_path / "pc.bin"
+    run = subprocess.run([os.path.join(HOST, "reina_b200"), "--config", str(cfg), "--spp", "24", "--out", str(out),
+                          "--outdir", str(tmp_path), "--dump-pc", str(pcfile)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr + run.stdout
+    assert "6 frames, 24 samples per pixel" in run.stdout
+    assert (tmp_path / "output_8spp.png").exists()          # 8 < 4 * (k - 1)  ->  frame 4 of 0..5
+
+    pc = rb.abi.RtPushConsts.from_buffer_copy(pcfile.read_bytes())
+    wl = rb.configs.cornell(96, 72, nee=True)
+    r = rb.Renderer(96, 72, wl.tables, flags=rb.RB200_FLAG_NEE)
+    frames = {}
+    for b in range(6):
+        pc.sampleBatch = b
+        r.render_batch(pc)
+        if b in (4, 5):
+            r.postprocess()
+            frames[b] = r.read_ldr().copy()
+    r.close()
+    assert (decode_png(out.read_bytes()) == frames[5]).all()
+    assert (decode_png((tmp_path / "output_8spp.png").read_bytes()) == frames[4]).all()
+
+
+@pytest.mark.gpu
+def test_cli_reports_errors(host, tmp_path):
+    run = subprocess.run([os.path.join(HOST, "reina_b200"), "--config", str(tmp_path / "absent.toml")],
+                         capture_output=True, text=True)
+    assert run.returncode == 1 and "cannot open" in run.stderr
