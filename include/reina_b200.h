@@ -244,6 +244,16 @@ RB200_API int rb200_postprocess(RB200Context* ctx, const RB200BloomPushConsts* b
 /* Read-back (synchronises the stream). `rgba8`: W*H*4 bytes, row 0 = top. `rgba32f`: W*H*4 floats. */
 RB200_API int rb200_read_ldr(RB200Context* ctx, uint8_t* rgba8);
 RB200_API int rb200_read_hdr(RB200Context* ctx, float* rgba32f);
+/* Pipelined read-back: enqueue the copy of the RGBA8 frame behind the post-processing queued so far and return at
+ * once; rb200_wait_ldr blocks until the most recent such copy has landed. With `rgba8` from rb200_host_alloc (pinned)
+ * the caller can issue rb200_render_batch(i+1) before waiting for frame i, so post-processing and read-back of one
+ * frame overlap the next batch (what a swap chain gives the reference's loop between endSubmit and present,
+ * src/Reina.cpp:380-385). One outstanding copy at a time: wait before issuing the next. */
+RB200_API int rb200_read_ldr_async(RB200Context* ctx, uint8_t* rgba8);
+RB200_API int rb200_wait_ldr(RB200Context* ctx);
+/* Page-locked host memory for the asynchronous read-back (callers without a CUDA runtime of their own). */
+RB200_API int rb200_host_alloc(size_t bytes, void** out);
+RB200_API int rb200_host_free(void* p);
 /* Replace the HDR accumulation image (resume / post-processing parity on identical input). */
 RB200_API int rb200_write_hdr(RB200Context* ctx, const float* rgba32f);
 /* Device pointer of the float4 HDR accumulation image (for a collective over NVLink issued by the harness). */

@@ -38,6 +38,7 @@ class Renderer:
     def __init__(self, width, height, tables, flags=0, device=0, stream=None):
         self.lib = load_library()
         self.width, self.height, self.flags = width, height, flags
+        self._pinned = []
         self._ctx = C.c_void_p()
         abi.check(self.lib, self.lib.rb200_context_create(width, height, device, flags, C.byref(self._ctx)))
         if stream is not None:
@@ -74,6 +75,22 @@ class Renderer:
         out = np.empty((self.height, self.width, 4), np.uint8) if out is None else out
         abi.check(self.lib, self.lib.rb200_read_ldr(self._ctx, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def pinned_frame(self):
+        """A page-locked (H, W, 4) uint8 array from rb200_host_alloc, for read_ldr_async; freed by close()."""
+        p = C.c_void_p()
+        n = self.height * self.width * 4
+        abi.check(self.lib, self.lib.rb200_host_alloc(n, C.byref(p)))
+        self._pinned.append(p)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(self.height, self.width, 4))
+
+    def read_ldr_async(self, out):
+        """Enqueue the frame copy into `out` (use pinned_frame()) and return; wait_ldr() blocks until it landed."""
+        assert out.dtype == np.uint8 and out.shape == (self.height, self.width, 4) and out.flags.c_contiguous
+        abi.check(self.lib, self.lib.rb200_read_ldr_async(self._ctx, out.ctypes.data_as(C.c_void_p)))
+
+    def wait_ldr(self):
+        abi.check(self.lib, self.lib.rb200_wait_ldr(self._ctx))
 
     def write_hdr(self, img):
         img = np.ascontiguousarray(img, np.float32)
@@ -127,6 +144,9 @@ class Renderer:
         if getattr(self, "_ctx", None):
             self.lib.rb200_context_destroy(self._ctx)
             self._ctx = None
+        for p in getattr(self, "_pinned", []):
+            self.lib.rb200_host_free(p)
+        self._pinned = []
 
     def __del__(self):
         try:

@@ -147,6 +147,10 @@ SYMBOLS = {
     "rb200_postprocess": (C.c_int, [C.c_void_p, C.POINTER(BloomPushConsts), C.POINTER(TonemappingPushConsts)]),
     "rb200_read_ldr": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rb200_read_hdr": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rb200_read_ldr_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rb200_wait_ldr": (C.c_int, [C.c_void_p]),
+    "rb200_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "rb200_host_free": (C.c_int, [C.c_void_p]),
     "rb200_write_hdr": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rb200_hdr_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "rb200_trace_primary": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RtPushConsts), C.c_void_p]),

@@ -107,6 +107,7 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
         RB_CUDA(cudaEventCreateWithFlags(&c->accumDone[lane], cudaEventDisableTiming));
     }
     RB_CUDA(cudaEventCreateWithFlags(&c->frontMark, cudaEventDisableTiming));
+    RB_CUDA(cudaEventCreateWithFlags(&c->ldrCopied, cudaEventDisableTiming | cudaEventBlockingSync));
     A(c->statsSnap, ST_COUNT);
     A(P.image, N); A(c->ping, N); A(c->pong, N); A(c->ldr, N);
     c->wp1.image = P.image;
@@ -131,6 +132,7 @@ RB200_API int rb200_context_destroy(RB200Context* ctx) {
         if (ctx->laneStream[lane]) cudaStreamDestroy(ctx->laneStream[lane]);
     }
     if (ctx->frontMark) cudaEventDestroy(ctx->frontMark);
+    if (ctx->ldrCopied) cudaEventDestroy(ctx->ldrCopied);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RB200_OK;
@@ -290,6 +292,36 @@ RB200_API int rb200_read_ldr(RB200Context* ctx, uint8_t* rgba8) {
     if (!ctx || !rgba8) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
     RB_CUDA(cudaMemcpyAsync(rgba8, ctx->ldr, (size_t)ctx->width * ctx->height * 4, cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RB200_OK;
+}
+
+RB200_API int rb200_read_ldr_async(RB200Context* ctx, uint8_t* rgba8) {
+    if (!ctx || !rgba8) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaMemcpyAsync(rgba8, ctx->ldr, (size_t)ctx->width * ctx->height * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(cudaEventRecord(ctx->ldrCopied, ctx->stream));
+    ctx->ldrPending = true;
+    return RB200_OK;
+}
+
+RB200_API int rb200_wait_ldr(RB200Context* ctx) {
+    if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
+    if (!ctx->ldrPending) return RB200_OK;
+    RB_CUDA(cudaEventSynchronize(ctx->ldrCopied));
+    ctx->ldrPending = false;
+    return RB200_OK;
+}
+
+RB200_API int rb200_host_alloc(size_t bytes, void** out) {
+    if (!out || bytes == 0) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error(cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? RB200_ERR_OUT_OF_MEMORY : RB200_ERR_CUDA; }
+    return RB200_OK;
+}
+
+RB200_API int rb200_host_free(void* p) {
+    if (!p) return RB200_OK;
+    RB_CUDA(cudaFreeHost(p));
     return RB200_OK;
 }
 

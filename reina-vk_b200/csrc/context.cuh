@@ -63,6 +63,8 @@ struct RB200Context {
     cudaStream_t laneStream[2] = {nullptr, nullptr};
     cudaEvent_t accumDone[2] = {nullptr, nullptr};
     cudaEvent_t frontMark = nullptr;
+    cudaEvent_t ldrCopied = nullptr;           // completion of the most recent rb200_read_ldr_async
+    bool ldrPending = false;
     uint64_t batchCalls = 0;
     std::vector<void*> allocations;
     float4 *ping = nullptr, *pong = nullptr;   // bloom work images

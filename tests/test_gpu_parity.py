@@ -223,3 +223,32 @@ def test_postprocess_full_size_random_input(ol, rb):
     eq = (g == o).all(axis=2)
     assert eq.all(), f"{(~eq).sum()} LDR pixels differ, max diff {np.abs(g.astype(int) - o.astype(int)).max()}"
     r.close()
+
+
+def test_pipelined_read_back_matches_blocking_read(rb):
+    """rb200_read_ldr_async into rb200_host_alloc memory, waited one batch later, returns the frames a blocking
+    rb200_read_ldr returns (the depth-2 pipeline of bench.py's e2e loop)."""
+    wl = rb.configs.small_mixed(160, 120, nee=True, samples_per_pixel=2, max_bounces=6)
+    r = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE)
+    want = []
+    for b in range(4):
+        r.render_batch(wl.push_constants(b))
+        r.postprocess()
+        want.append(r.read_ldr().copy())
+    r.close()
+    r = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE)
+    frames = [r.pinned_frame(), r.pinned_frame()]
+    got = []
+    for b in range(4):
+        r.render_batch(wl.push_constants(b))
+        r.postprocess()
+        r.wait_ldr()
+        if b:
+            got.append(frames[(b - 1) & 1].copy())
+        r.read_ldr_async(frames[b & 1])
+    r.wait_ldr()
+    got.append(frames[3 & 1].copy())
+    r.wait_ldr()                         # nothing outstanding: returns at once
+    r.close()
+    for a, b in zip(want, got):
+        assert (a == b).all()
