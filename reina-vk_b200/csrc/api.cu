@@ -97,11 +97,11 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
     for (int lane = 0; lane < 2; lane++) {
         WaveParams& L = lane == 0 ? c->wp : c->wp1;
         L.W = width; L.H = height; L.N = (uint32_t)N; L.flags = flags;
-        A(L.rayO, N); A(L.rayD, N); A(L.hit, N); A(L.thr, N); A(L.rad, N); A(L.sum, N); A(L.st, N);
-        A(L.shO, N); A(L.shD, N); A(L.shA, N); A(L.shB, N); A(L.shT, N);
+        A(L.rayO.p, N); A(L.rayD.p, N); A(L.hit.p, N); A(L.thr.p, N); A(L.rad.p, N); A(L.sum.p, N); A(L.st.p, N);
+        A(L.shO.p, N); A(L.shD.p, N); A(L.shA.p, N); A(L.shB.p, N); A(L.shT.p, N);
         A(L.rayQ[0], N); A(L.rayQ[1], N);
         for (int m = 0; m < 5; m++) A(L.matQ[m], N);
-        A(L.endQ, N); A(L.counters, 2 * CNT_SET); A(L.mean, N); A(L.stats, ST_COUNT);
+        A(L.endQ, N); A(L.counters, 2 * CNT_SET); A(L.mean.p, N); A(L.stats, ST_COUNT);
         RB_CUDA(cudaMemsetAsync(L.stats, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
         RB_CUDA(cudaStreamCreateWithFlags(&c->laneStream[lane], cudaStreamNonBlocking));
         RB_CUDA(cudaEventCreateWithFlags(&c->accumDone[lane], cudaEventDisableTiming));
@@ -203,7 +203,14 @@ RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB2
     if ((rc = upload(sc, sizes.data(), sizes.size(), &D.texSizes, s)) != RB200_OK) { rb200_scene_destroy(sc); return rc; }
     RB_CUDA(cudaStreamSynchronize(s));   // host staging vectors go out of scope below
 
-    BuildInput bi{D.vertices, D.indices, D.instances, &sc->hostInstances, d->numInstances};
+    // RB200_BVH_BUILDER=lbvh | ploc selects the binary hierarchy under the collapse (see common.cuh); default ploc
+    int builder = BUILDER_PLOC;
+    if (const char* e = getenv("RB200_BVH_BUILDER")) {
+        if (!strcmp(e, "lbvh")) builder = BUILDER_LBVH;
+        else if (!strcmp(e, "ploc")) builder = BUILDER_PLOC;
+        else { set_error("RB200_BVH_BUILDER must be lbvh or ploc"); rb200_scene_destroy(sc); return RB200_ERR_INVALID_ARGUMENT; }
+    }
+    BuildInput bi{D.vertices, D.indices, D.instances, &sc->hostInstances, d->numInstances, builder};
     rc = build_bvh(bi, s, &sc->bvh, &ctx->launches);
     if (rc != RB200_OK) { rb200_scene_destroy(sc); return rc; }
     /* TRAV_MAX_DEPTH = 22: the per-lane traversal stack holds at most 2 groups per tree level */

@@ -168,25 +168,72 @@ __global__ void k_radix_scatter(const uint64_t* __restrict__ keysIn, const uint3
     }
 }
 
-// single-block exclusive scan of n uint32 (n up to a few million); total written to *total if not null
-__global__ void k_exclusive_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, uint32_t* total) {
-    __shared__ uint32_t part[1024];
-    const uint32_t T = blockDim.x, t = threadIdx.x;
-    const uint32_t chunk = (n + T - 1) / T;
+// Exclusive scans (integer sums: the result does not depend on the order of evaluation).
+// k_scan_small: one block, any n (each thread takes a contiguous chunk); safe in place; total to *total if not null.
+template <class T>
+__global__ void k_scan_small(const T* in, T* out, uint32_t n, T* total) {
+    __shared__ T part[1024];
+    const uint32_t nt = blockDim.x, t = threadIdx.x;
+    const uint32_t chunk = (n + nt - 1) / nt;
     const uint32_t b = min(n, t * chunk), e = min(n, b + chunk);
-    uint32_t s = 0;
+    T s = 0;
     for (uint32_t i = b; i < e; i++) s += in[i];
     part[t] = s;
     __syncthreads();
-    for (uint32_t o = 1; o < T; o <<= 1) {
-        uint32_t v = (t >= o) ? part[t - o] : 0;
+    for (uint32_t o = 1; o < nt; o <<= 1) {
+        T v = (t >= o) ? part[t - o] : T(0);
         __syncthreads();
         part[t] += v;
         __syncthreads();
     }
-    uint32_t run = part[t] - s;
-    if (t == T - 1 && total) *total = part[t];
-    for (uint32_t i = b; i < e; i++) { uint32_t v = in[i]; out[i] = run; run += v; }
+    T run = part[t] - s;
+    if (t == nt - 1 && total) *total = part[t];
+    for (uint32_t i = b; i < e; i++) { T v = in[i]; out[i] = run; run += v; }
+}
+
+// large n: scan tiles of SCAN_TILE items independently, scan the tile sums with k_scan_small, add the offsets back
+static constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <class T>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const T* __restrict__ in, T* __restrict__ out, uint32_t n,
+                                                              T* __restrict__ tileSums) {
+    __shared__ T warpSums[SCAN_THREADS / 32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    T v[SCAN_ITEMS];
+    T sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? in[base + k] : T(0); sum += v[k]; }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    T inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { T up = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += up; }
+    if (lane == 31) warpSums[w] = inc;
+    __syncthreads();
+    T offset = 0;
+    for (int k = 0; k < w; k++) offset += warpSums[k];
+    T run = offset + inc - sum;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = run; run += v[k]; }
+    if (threadIdx.x == SCAN_THREADS - 1) tileSums[blockIdx.x] = run;
+}
+
+template <class T>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(T* __restrict__ out, uint32_t n, const T* __restrict__ tileOffsets) {
+    const T off = tileOffsets[blockIdx.x];
+    const uint32_t base = blockIdx.x * SCAN_TILE;
+    for (uint32_t k = threadIdx.x; k < (uint32_t)SCAN_TILE; k += SCAN_THREADS)
+        if (base + k < n) out[base + k] += off;
+}
+
+// tileScratch: at least (n + SCAN_TILE - 1) / SCAN_TILE entries
+template <class T>
+static void exclusive_scan(const T* in, T* out, uint32_t n, T* total, T* tileScratch, cudaStream_t stream, uint64_t& nl) {
+    if (n <= 2u * SCAN_TILE) { k_scan_small<T><<<1, 1024, 0, stream>>>(in, out, n, total); nl++; return; }
+    const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_tiles<T><<<tiles, SCAN_THREADS, 0, stream>>>(in, out, n, tileScratch);
+    k_scan_small<T><<<1, 1024, 0, stream>>>(tileScratch, tileScratch, tiles, total);
+    k_scan_add<T><<<tiles, SCAN_THREADS, 0, stream>>>(out, n, tileScratch);
+    nl += 3;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -263,6 +310,130 @@ __global__ void k_refit(uint32_t N, const uint32_t* __restrict__ childL, const u
         nodeLo[p] = make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z), 0.f);
         nodeHi[p] = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.f);
         p = parentInt[p];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 4b. PLOC (Meister & Bittner 2018, parallel locally-ordered clustering) as the alternative to Karras + refit:
+// clusters start as the Morton-sorted leaves; every round each cluster looks RB_PLOC_RADIUS positions to either side
+// for the neighbour whose union with it has the smallest surface area, mutually-nearest pairs merge into a new
+// binary node, the array is compacted (order kept) and the round repeats until one cluster is left. Node ids and
+// positions come from prefix sums and ties are broken by index, so the tree is the same on every run.
+// ---------------------------------------------------------------------------------------------------
+#ifndef RB_PLOC_RADIUS
+#define RB_PLOC_RADIUS 16
+#endif
+static constexpr int PLOC_BLOCK = 256;
+static constexpr uint32_t NONE = 0xFFFFFFFFu;
+
+__global__ void __launch_bounds__(PLOC_BLOCK) k_ploc_nearest(uint32_t c, const float4* __restrict__ cLo,
+                                                              const float4* __restrict__ cHi, uint32_t* __restrict__ nn) {
+    constexpr int R = RB_PLOC_RADIUS;
+    __shared__ float4 sLo[PLOC_BLOCK + 2 * R], sHi[PLOC_BLOCK + 2 * R];
+    const int base = (int)(blockIdx.x * PLOC_BLOCK) - R;
+    for (int t = threadIdx.x; t < PLOC_BLOCK + 2 * R; t += PLOC_BLOCK) {
+        const int g = base + t;
+        if (g >= 0 && g < (int)c) { sLo[t] = cLo[g]; sHi[t] = cHi[g]; }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * PLOC_BLOCK + threadIdx.x;
+    if (i >= (int)c) return;
+    const float4 lo = sLo[threadIdx.x + R], hi = sHi[threadIdx.x + R];
+    float best = 3.0e38f;
+    int bj = -1;
+    uint32_t bx = 0xFFFFFFFFu;
+    for (int d = -R; d <= R; d++) {
+        const int j = i + d;
+        if (d == 0 || j < 0 || j >= (int)c) continue;
+        const float4 l2 = sLo[threadIdx.x + R + d], h2 = sHi[threadIdx.x + R + d];
+        const float dx = fmaxf(hi.x, h2.x) - fminf(lo.x, l2.x), dy = fmaxf(hi.y, h2.y) - fminf(lo.y, l2.y),
+                    dz = fmaxf(hi.z, h2.z) - fminf(lo.z, l2.z);
+        const float a = dx * dy + dy * dz + dz * dx;
+        // equal areas (regular grids) go to the partner with the smaller i ^ j: neighbours then pair up (0,1), (2,3), ...
+        // instead of forming one long chain with a single mutual pair per round; the rule is symmetric in i and j, so
+        // the pair that minimises (area, i ^ j) overall is always mutual and every round makes progress
+        const uint32_t x = (uint32_t)i ^ (uint32_t)j;
+        if (a < best || (a == best && x < bx)) { best = a; bj = j; bx = x; }
+    }
+    nn[i] = (uint32_t)bj;
+}
+
+// per cluster: high word 1 = survives this round (not the right half of a merging pair), low word 1 = starts a merge
+__global__ void k_ploc_flags(uint32_t c, const uint32_t* __restrict__ nn, unsigned long long* __restrict__ flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const uint32_t j = nn[i];
+    const bool mutual = nn[j] == i;
+    const unsigned long long valid = (mutual && i > j) ? 0ull : 1ull, merge = (mutual && i < j) ? 1ull : 0ull;
+    flags[i] = (valid << 32) | merge;
+}
+
+__global__ void k_ploc_apply(uint32_t c, const uint32_t* __restrict__ nn, const unsigned long long* __restrict__ scan,
+                             const uint32_t* __restrict__ clIn, const float4* __restrict__ loIn, const float4* __restrict__ hiIn,
+                             uint32_t* __restrict__ clOut, float4* __restrict__ loOut, float4* __restrict__ hiOut,
+                             uint32_t nodeBase, uint32_t* __restrict__ childL, uint32_t* __restrict__ childR,
+                             float4* __restrict__ nodeLo, float4* __restrict__ nodeHi, uint32_t* __restrict__ count,
+                             uint32_t* __restrict__ parentInt, uint32_t* __restrict__ parentLeaf) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const uint32_t j = nn[i];
+    const bool mutual = nn[j] == i;
+    if (mutual && i > j) return;
+    const unsigned long long sc = scan[i];
+    const uint32_t pos = (uint32_t)(sc >> 32);
+    if (!mutual) { clOut[pos] = clIn[i]; loOut[pos] = loIn[i]; hiOut[pos] = hiIn[i]; return; }
+    const uint32_t id = nodeBase + (uint32_t)(sc & 0xFFFFFFFFull);
+    const uint32_t L = clIn[i], R = clIn[j];
+    const float4 a = loIn[i], b = loIn[j], ah = hiIn[i], bh = hiIn[j];
+    const float4 lo = make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z), 0.f);
+    const float4 hi = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.f);
+    childL[id] = L; childR[id] = R;
+    nodeLo[id] = lo; nodeHi[id] = hi;
+    count[id] = ((L & LEAF_FLAG) ? 1u : count[L]) + ((R & LEAF_FLAG) ? 1u : count[R]);
+    if (L & LEAF_FLAG) parentLeaf[L & ~LEAF_FLAG] = id; else parentInt[L] = id;
+    if (R & LEAF_FLAG) parentLeaf[R & ~LEAF_FLAG] = id; else parentInt[R] = id;
+    parentInt[id] = NONE;
+    clOut[pos] = id; loOut[pos] = lo; hiOut[pos] = hi;
+}
+
+__global__ void k_ploc_init(uint32_t N, uint32_t* __restrict__ cl) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) cl[i] = LEAF_FLAG | i;
+}
+
+// depth-first position of every leaf and first/last leaf of every internal node: the number of leaves in the left
+// siblings met on the way up to the root
+__global__ void k_ploc_ranges(uint32_t N, const uint32_t* __restrict__ childL, const uint32_t* __restrict__ parentInt,
+                              const uint32_t* __restrict__ parentLeaf, const uint32_t* __restrict__ count,
+                              uint32_t* __restrict__ rangeFirst, uint32_t* __restrict__ rangeLast, uint32_t* __restrict__ leafPos) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2u * N - 1u) return;
+    const bool leaf = t < N;
+    uint32_t cur = leaf ? (LEAF_FLAG | t) : (t - N);
+    uint32_t p = leaf ? parentLeaf[t] : parentInt[t - N];
+    uint32_t first = 0;
+    while (p != NONE) {
+        const uint32_t L = childL[p];
+        if (L != cur) first += (L & LEAF_FLAG) ? 1u : count[L];
+        cur = p;
+        p = parentInt[p];
+    }
+    if (leaf) leafPos[t] = first;
+    else { rangeFirst[t - N] = first; rangeLast[t - N] = first + count[t - N] - 1u; }
+}
+
+__global__ void k_ploc_permute(uint32_t N, const uint32_t* __restrict__ leafPos, const TriRecord* __restrict__ triIn,
+                               const float4* __restrict__ loIn, const float4* __restrict__ hiIn, TriRecord* __restrict__ triOut,
+                               float4* __restrict__ loOut, float4* __restrict__ hiOut, uint32_t* childL, uint32_t* childR) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) {
+        const uint32_t p = leafPos[i];
+        triOut[p] = triIn[i]; loOut[p] = loIn[i]; hiOut[p] = hiIn[i];
+    }
+    if (i + 1 < N) {      // internal node i: leaf references follow their leaves
+        const uint32_t L = childL[i], R = childR[i];
+        if (L & LEAF_FLAG) childL[i] = LEAF_FLAG | leafPos[L & ~LEAF_FLAG];
+        if (R & LEAF_FLAG) childR[i] = LEAF_FLAG | leafPos[R & ~LEAF_FLAG];
     }
 }
 
@@ -436,7 +607,21 @@ __global__ void k_place_triangles(WideNode* nodes, uint32_t numNodes, const uint
 // ---------------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------------
-template <class T> static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
+// All build temporaries come out of one allocation (about 600 bytes per triangle): ~50 cudaMalloc / cudaFree calls
+// cost several milliseconds of host time, more than the kernels of the build.
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, used = 0;
+    ~Arena() { if (base) cudaFree(base); }
+};
+static thread_local Arena* g_arena = nullptr;
+template <class T> static cudaError_t dalloc(T** p, size_t n) {
+    const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~(size_t)255;
+    if (!g_arena || g_arena->used + bytes > g_arena->cap) return cudaErrorMemoryAllocation;
+    *p = reinterpret_cast<T*>(g_arena->base + g_arena->used);
+    g_arena->used += bytes;
+    return cudaSuccess;
+}
 
 int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* launches) {
     const std::vector<RB200Instance>& hi = *in.h_instances;
@@ -446,6 +631,14 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
     if (N == 0) { set_error("scene has no triangles"); return RB200_ERR_INVALID_ARGUMENT; }
     if (N >= 0x40000000u) { set_error("too many triangles"); return RB200_ERR_INVALID_ARGUMENT; }
 
+    Arena arena;
+    arena.cap = (size_t)N * 640 + prefix.size() * 4 + (1u << 20);
+    if (cudaMalloc((void**)&arena.base, arena.cap) != cudaSuccess) {
+        cudaGetLastError(); arena.base = nullptr;
+        set_error("out of device memory for the BVH build (%zu MiB of temporaries)", arena.cap >> 20);
+        return RB200_ERR_OUT_OF_MEMORY;
+    }
+    g_arena = &arena;
     cudaEvent_t e0, e1;
     RB_CUDA(cudaEventCreate(&e0)); RB_CUDA(cudaEventCreate(&e1));
     RB_CUDA(cudaEventRecord(e0, stream));
@@ -464,6 +657,8 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
     RB_CUDA(dalloc(&keys[0], N)); RB_CUDA(dalloc(&keys[1], N)); RB_CUDA(dalloc(&vals[0], N)); RB_CUDA(dalloc(&vals[1], N));
     const uint32_t sortBlocks = (N + SORT_BLOCK - 1) / SORT_BLOCK;
     RB_CUDA(dalloc(&hist, (size_t)256 * sortBlocks)); RB_CUDA(dalloc(&histScan, (size_t)256 * sortBlocks));
+    uint32_t* scanScratch;
+    RB_CUDA(dalloc(&scanScratch, ((size_t)256 * sortBlocks + N) / SCAN_TILE + 2));
     RB_CUDA(dalloc(&childL, N)); RB_CUDA(dalloc(&childR, N)); RB_CUDA(dalloc(&parentInt, N)); RB_CUDA(dalloc(&parentLeaf, N));
     RB_CUDA(dalloc(&rFirst, N)); RB_CUDA(dalloc(&rLast, N)); RB_CUDA(dalloc(&flags, N));
     RB_CUDA(dalloc(&leafLo, N)); RB_CUDA(dalloc(&leafHi, N)); RB_CUDA(dalloc(&nodeLo, N)); RB_CUDA(dalloc(&nodeHi, N));
@@ -476,15 +671,54 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
     int cur = 0;
     for (int pass = 0; pass < 8; pass++) {
         k_radix_hist<<<sortBlocks, SORT_BLOCK, 0, stream>>>(keys[cur], N, pass * 8, hist, sortBlocks); nl++;
-        k_exclusive_scan<<<1, 1024, 0, stream>>>(hist, histScan, 256u * sortBlocks, nullptr); nl++;
+        exclusive_scan<uint32_t>(hist, histScan, 256u * sortBlocks, nullptr, scanScratch, stream, nl);
         k_radix_scatter<<<sortBlocks, SORT_BLOCK, 0, stream>>>(keys[cur], vals[cur], N, pass * 8, histScan, sortBlocks,
                                                                keys[cur ^ 1], vals[cur ^ 1]); nl++;
         cur ^= 1;
     }
     k_gather_sorted<<<G, B, 0, stream>>>(unsorted, vals[cur], N, sorted, leafLo, leafHi); nl++;
-    if (N > 1) {
+    uint32_t rootRef = LEAF_FLAG | 0u;
+    const TriRecord* leafTris = sorted;          // triangles in the order the binary tree's leaf ranges refer to
+    const float4 *leafLoFinal = leafLo, *leafHiFinal = leafHi;
+    if (N > 1 && in.builder == BUILDER_LBVH) {
         k_karras<<<G, B, 0, stream>>>(keys[cur], (int)N, childL, childR, parentInt, parentLeaf, rFirst, rLast); nl++;
         k_refit<<<G, B, 0, stream>>>(N, childL, childR, parentInt, parentLeaf, leafLo, leafHi, nodeLo, nodeHi, flags); nl++;
+        rootRef = 0u;
+    } else if (N > 1) {
+        uint32_t *cl[2], *nn, *count, *leafPos;
+        float4 *cLo[2], *cHi[2], *permLo, *permHi;
+        unsigned long long *mflags, *mscan, *mtotal, *mscratch;
+        RB_CUDA(dalloc(&cl[0], N)); RB_CUDA(dalloc(&cl[1], N)); RB_CUDA(dalloc(&nn, N)); RB_CUDA(dalloc(&count, N));
+        RB_CUDA(dalloc(&leafPos, N));
+        RB_CUDA(dalloc(&cLo[0], N)); RB_CUDA(dalloc(&cLo[1], N)); RB_CUDA(dalloc(&cHi[0], N)); RB_CUDA(dalloc(&cHi[1], N));
+        RB_CUDA(dalloc(&permLo, N)); RB_CUDA(dalloc(&permHi, N));
+        RB_CUDA(dalloc(&mflags, N)); RB_CUDA(dalloc(&mscan, N)); RB_CUDA(dalloc(&mtotal, 1));
+        RB_CUDA(dalloc(&mscratch, (size_t)N / SCAN_TILE + 2));
+        k_ploc_init<<<G, B, 0, stream>>>(N, cl[0]); nl++;
+        RB_CUDA(cudaMemcpyAsync(cLo[0], leafLo, (size_t)N * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        RB_CUDA(cudaMemcpyAsync(cHi[0], leafHi, (size_t)N * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        uint32_t c = N, nodeBase = 0, rounds = 0;
+        int pc = 0;
+        while (c > 1) {
+            const uint32_t g = (c + PLOC_BLOCK - 1) / PLOC_BLOCK;
+            k_ploc_nearest<<<g, PLOC_BLOCK, 0, stream>>>(c, cLo[pc], cHi[pc], nn); nl++;
+            k_ploc_flags<<<g, PLOC_BLOCK, 0, stream>>>(c, nn, mflags); nl++;
+            exclusive_scan<unsigned long long>(mflags, mscan, c, mtotal, mscratch, stream, nl);
+            k_ploc_apply<<<g, PLOC_BLOCK, 0, stream>>>(c, nn, mscan, cl[pc], cLo[pc], cHi[pc], cl[pc ^ 1], cLo[pc ^ 1], cHi[pc ^ 1],
+                                                       nodeBase, childL, childR, nodeLo, nodeHi, count, parentInt, parentLeaf); nl++;
+            unsigned long long tot = 0;
+            RB_CUDA(cudaMemcpyAsync(&tot, mtotal, sizeof(tot), cudaMemcpyDeviceToHost, stream));
+            RB_CUDA(cudaStreamSynchronize(stream));
+            const uint32_t merges = (uint32_t)(tot & 0xFFFFFFFFull), survivors = (uint32_t)(tot >> 32);
+            if (merges == 0 || survivors != c - merges) { set_error("internal: PLOC round made no progress"); return RB200_ERR_CUDA; }
+            nodeBase += merges; c = survivors; pc ^= 1; rounds++;
+        }
+        if (getenv("RB200_DEBUG_BUILD")) fprintf(stderr, "[rb200] PLOC: %u leaves, %u rounds\n", N, rounds);
+        if (nodeBase != N - 1) { set_error("internal: PLOC built %u of %u nodes", nodeBase, N - 1); return RB200_ERR_CUDA; }
+        rootRef = N - 2;       // the last node created
+        k_ploc_ranges<<<(2 * N - 1 + B - 1) / B, B, 0, stream>>>(N, childL, parentInt, parentLeaf, count, rFirst, rLast, leafPos); nl++;
+        k_ploc_permute<<<G, B, 0, stream>>>(N, leafPos, sorted, leafLo, leafHi, unsorted, permLo, permHi, childL, childR); nl++;
+        leafTris = unsorted; leafLoFinal = permLo; leafHiFinal = permHi;
     }
     RB_CUDA(cudaGetLastError());
 
@@ -495,9 +729,8 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
     RB_CUDA(dalloc(&nodeChildRefs, maxNodes * 8)); RB_CUDA(dalloc(&slotTriFirst, maxNodes * 8));
     RB_CUDA(dalloc(&work[0], maxNodes)); RB_CUDA(dalloc(&work[1], maxNodes)); RB_CUDA(dalloc(&levelPrefix, maxNodes));
     RB_CUDA(dalloc(&dTotal, 1));
-    CollapseArrays A{childL, childR, rFirst, rLast, leafLo, leafHi, nodeLo, nodeHi, nodesTmp, nodeInternalCount, nodeTriCount,
+    CollapseArrays A{childL, childR, rFirst, rLast, leafLoFinal, leafHiFinal, nodeLo, nodeHi, nodesTmp, nodeInternalCount, nodeTriCount,
                      nodeChildRefs, slotTriFirst};
-    uint32_t rootRef = (N > 1) ? 0u : (LEAF_FLAG | 0u);
     RB_CUDA(cudaMemcpyAsync(work[0], &rootRef, 4, cudaMemcpyHostToDevice, stream));
     uint32_t levelBase = 0, levelCount = 1, depth = 0;
     int wcur = 0;
@@ -505,7 +738,7 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
         if ((size_t)levelBase + levelCount > maxNodes) { set_error("internal: wide node overflow"); return RB200_ERR_CUDA; }
         uint32_t g = (levelCount + 127) / 128;
         k_collapse_level<<<g, 128, 0, stream>>>(A, work[wcur], levelCount, levelBase); nl++;
-        k_exclusive_scan<<<1, 1024, 0, stream>>>(nodeInternalCount + levelBase, levelPrefix, levelCount, dTotal); nl++;
+        exclusive_scan<uint32_t>(nodeInternalCount + levelBase, levelPrefix, levelCount, dTotal, scanScratch, stream, nl);
         uint32_t nextBase = levelBase + levelCount;
         k_link_children<<<g, 128, 0, stream>>>(nodesTmp, levelPrefix, nodeInternalCount, nodeChildRefs, levelCount, levelBase,
                                                nextBase, work[wcur ^ 1]); nl++;
@@ -519,7 +752,7 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
     // triangles into leaf order
     uint32_t* triPrefix;
     RB_CUDA(dalloc(&triPrefix, numNodes));
-    k_exclusive_scan<<<1, 1024, 0, stream>>>(nodeTriCount, triPrefix, numNodes, dTotal); nl++;
+    exclusive_scan<uint32_t>(nodeTriCount, triPrefix, numNodes, dTotal, scanScratch, stream, nl);
     // nodes and triangles live in ONE allocation so that a single L2 access-policy window can keep the whole
     // hierarchy resident (see rb200_scene_create)
     const size_t nodeBytes = ((size_t)numNodes * sizeof(WideNode) + 255) & ~(size_t)255;
@@ -527,7 +760,7 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
     RB_CUDA(cudaMalloc(&out->blob, out->blobBytes));
     out->nodes = reinterpret_cast<WideNode*>(out->blob);
     out->tris = reinterpret_cast<TriRecord*>(reinterpret_cast<char*>(out->blob) + nodeBytes);
-    k_place_triangles<<<(numNodes + 127) / 128, 128, 0, stream>>>(nodesTmp, numNodes, triPrefix, slotTriFirst, sorted, out->tris); nl++;
+    k_place_triangles<<<(numNodes + 127) / 128, 128, 0, stream>>>(nodesTmp, numNodes, triPrefix, slotTriFirst, leafTris, out->tris); nl++;
     RB_CUDA(cudaMemcpyAsync(out->nodes, nodesTmp, (size_t)numNodes * sizeof(WideNode), cudaMemcpyDeviceToDevice, stream));
     uint32_t totalTris = 0, hb[6];
     RB_CUDA(cudaMemcpyAsync(&totalTris, dTotal, 4, cudaMemcpyDeviceToHost, stream));
@@ -541,10 +774,7 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
     out->numNodes = numNodes; out->numTris = N; out->maxDepth = depth;
     for (int a = 0; a < 3; a++) { out->sceneMin[a] = ordered_to_float(hb[a]); out->sceneMax[a] = ordered_to_float(hb[3 + a]); }
 
-    void* frees[] = {dPrefix, dBounds, unsorted, sorted, keys[0], keys[1], vals[0], vals[1], hist, histScan, childL, childR,
-                     parentInt, parentLeaf, rFirst, rLast, flags, leafLo, leafHi, nodeLo, nodeHi, nodesTmp, nodeInternalCount,
-                     nodeTriCount, nodeChildRefs, slotTriFirst, work[0], work[1], levelPrefix, dTotal, triPrefix};
-    for (void* p : frees) cudaFree(p);
+    g_arena = nullptr;      // the arena itself is released when `arena` goes out of scope
     if (launches) *launches += nl;
     return RB200_OK;
 }

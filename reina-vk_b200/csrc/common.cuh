@@ -81,7 +81,11 @@ struct BuildInput {
     const RB200Instance* d_instances;
     const std::vector<RB200Instance>* h_instances;
     uint32_t numInstances;
+    int builder;       // BUILDER_*
 };
+// Binary hierarchy under the wide-node collapse: Karras 2012 over the sorted Morton keys (the north-star pipeline) or
+// PLOC clustering of the same sorted leaves (better surface-area cost, a few more milliseconds of build).
+enum { BUILDER_LBVH = 0, BUILDER_PLOC = 1 };
 
 // bvh_build.cu
 int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* launches);

@@ -26,24 +26,54 @@ enum { ST_EXTEND = 0, ST_SHADOW = 1, ST_PATHS = 2, ST_NODES = 3, ST_TRIS = 4, ST
 // path flags kept in PathState.st.y (low byte); the traced-segment counter lives in bits 8..31
 enum { F_INSIDE = 1u, F_FIRST = 2u, F_PREVSKIP = 4u };
 
+// Path-state arrays go through this proxy so that their cache policy is one switch. RB_STREAM_STATE=1 sends them
+// through ld/st.global.cs (evict-first) to keep the per-wave sweep (~0.6 GB at 1080p) from pushing the BVH out of L2.
+// Measured on B200 (dragon, 1080p): traversal +0.8 %, but the shading / finish kernels lose more (lambertian 6.2 ->
+// 7.3 ms, finish 3.6 -> 4.5 ms per batch) because in thin waves the state written by one kernel is still in L2 when
+// the next kernel reads it; net -4.5 %, so the default is plain loads and stores.
+#ifndef RB_STREAM_STATE
+#define RB_STREAM_STATE 0
+#endif
+template <class T> struct StateRef {
+    T* p;
+    __device__ __forceinline__ operator T() const {
+#if RB_STREAM_STATE
+        return __ldcs(p);
+#else
+        return *p;
+#endif
+    }
+    __device__ __forceinline__ void operator=(const T& v) const {
+#if RB_STREAM_STATE
+        __stcs(p, v);
+#else
+        *p = v;
+#endif
+    }
+};
+template <class T> struct StateArr {
+    T* p;
+    __device__ __forceinline__ StateRef<T> operator[](uint32_t i) const { return StateRef<T>{p + i}; }
+};
+
 struct WaveParams {
     DeviceScene S;
     RB200RtPushConsts pc;
     uint32_t W, H, N, flags;
-    float4* rayO;      // xyz origin
-    float4* rayD;      // xyz direction (not necessarily unit)
-    uint4* hit;        // x = bits(b1), y = bits(b2), z = primitive, w = instance
-    float4* thr;       // xyz throughput, w = accumulatedDistance
-    float4* rad;       // xyz radiance of the current path
-    float4* sum;       // xyz summed sample colours of this batch, w = bits(actualSamples)
-    uint4* st;         // x = rng state, y = flags | segments << 8, z = sample index
-    float4 *shO, *shD, *shA, *shB, *shT;   // shadow-ray records (compacted): origin/tmax, dir/slot, D/wNEE, E*wBRDF, throughput
+    StateArr<float4> rayO;      // xyz origin
+    StateArr<float4> rayD;      // xyz direction (not necessarily unit)
+    StateArr<uint4> hit;        // x = bits(b1), y = bits(b2), z = primitive, w = instance
+    StateArr<float4> thr;       // xyz throughput, w = accumulatedDistance
+    StateArr<float4> rad;       // xyz radiance of the current path
+    StateArr<float4> sum;       // xyz summed sample colours of this batch, w = bits(actualSamples)
+    StateArr<uint4> st;         // x = rng state, y = flags | segments << 8, z = sample index
+    StateArr<float4> shO, shD, shA, shB, shT;   // shadow-ray records (compacted): origin/tmax, dir, D/wNEE, E*wBRDF/slot, throughput
     uint32_t* rayQ[2];
     uint32_t* matQ[5]; // 0..3 materials, 4 = miss
     uint32_t* endQ;
     uint32_t* counters;            // [2][CNT_SET]
     unsigned long long* stats;     // [ST_COUNT]
-    float4* mean;                  // per pixel: mean of this batch's valid samples (xyz), w = 1 if any sample was valid
+    StateArr<float4> mean;         // per pixel: mean of this batch's valid samples (xyz), w = 1 if any sample was valid
     float4* image;                 // HDR accumulation image (shared by both lanes)
 };
 

@@ -363,9 +363,9 @@ __device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t s
                 const rb_v3 Bv = indirect * wBRDF;
                 const uint32_t k = queue_reserve(&cnt[CNT_SHADOW]);
                 P.shO[k] = make_float4(o.newO.x, o.newO.y, o.newO.z, dist - 0.001f);
-                P.shD[k] = make_float4(direction.x, direction.y, direction.z, __uint_as_float(slot));
+                P.shD[k] = make_float4(direction.x, direction.y, direction.z, 0.f);
                 P.shA[k] = make_float4(D.x, D.y, D.z, wNEE);
-                P.shB[k] = make_float4(Bv.x, Bv.y, Bv.z, 0.f);
+                P.shB[k] = make_float4(Bv.x, Bv.y, Bv.z, __uint_as_float(slot));
                 P.shT[k] = make_float4(T.x, T.y, T.z, 0.f);
             }
             if (skipNEE) newFlags |= F_PREVSKIP; else newFlags &= ~F_PREVSKIP;
@@ -379,8 +379,14 @@ __device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t s
     else queue_push(P.endQ, &cnt[CNT_END], slot);
 }
 
+#ifndef RB_SHADE_MINBLOCKS
+#define RB_SHADE_MINBLOCKS 1
+#endif
+#ifndef RB_DISNEY_MINBLOCKS
+#define RB_DISNEY_MINBLOCKS 1
+#endif
 template <int MAT>
-__global__ void __launch_bounds__(BLOCK) k_shade(WaveParams P, int parity) {
+__global__ void __launch_bounds__(BLOCK, MAT == 3 ? RB_DISNEY_MINBLOCKS : RB_SHADE_MINBLOCKS) k_shade(WaveParams P, int parity) {
     uint32_t* cnt = P.counters + parity * CNT_SET;
     uint32_t* cntNext = P.counters + (parity ^ 1) * CNT_SET;
     const uint32_t n = cnt[CNT_MAT0 + MAT];
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(BLOCK, RB_TRAV_MINBLOCKS) k_shadow(WaveParams 
         [&](uint32_t i, const RayHit& h) {
             const bool occluded = h.tri != 0xFFFFFFFFu;
             const float4 A = P.shA[i], B = P.shB[i], T = P.shT[i];
-            const uint32_t slot = __float_as_uint(P.shD[i].w);
+            const uint32_t slot = __float_as_uint(B.w);
             const rb_v3 direct = occluded ? rb_splat3(0.0f) : rb_mk3(A.x, A.y, A.z);
             const rb_v3 combined = direct * A.w + rb_mk3(B.x, B.y, B.z);
             const float4 L4 = P.rad[slot];
@@ -585,7 +591,7 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
     // caller had queued on the front-end stream; then let the front-end stream see the result
     if (hadPrevious) RB_CUDA(cudaStreamWaitEvent(s, ctx->accumDone[other], 0));
     RB_CUDA(cudaStreamWaitEvent(s, ctx->frontMark, 0));
-    k_accumulate<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(P.image, P.mean, P.N, pc->sampleBatch, ctx->flags, P.stats,
+    k_accumulate<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(P.image, P.mean.p, P.N, pc->sampleBatch, ctx->flags, P.stats,
                                                              ctx->statsSnap); nl++;
     RB_CUDA(cudaEventRecord(ctx->accumDone[lane], s));
     RB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->accumDone[lane], 0));
@@ -669,9 +675,9 @@ int trace_primary(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushC
     WaveParams& P = ctx->wp;
     for (int lane = 0; lane < 2; lane++) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[lane]));
     P.S = scene->dev; P.pc = *pc;
-    k_primary_rays<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, ctx->stream>>>(P, P.shO, P.shD);
+    k_primary_rays<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, ctx->stream>>>(P, P.shO.p, P.shD.p);
     ctx->launches++;
-    return run_query(ctx, scene, P.N, P.shO, P.shD, 0, out);
+    return run_query(ctx, scene, P.N, P.shO.p, P.shD.p, 0, out);
 }
 
 int trace_rays(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* o, const float* d, const float* tmax,

@@ -115,7 +115,20 @@ def test_dragon_full_size_primary_and_one_batch(ol, rb):
     r.close()
 
 
-def test_bvh_build_is_deterministic(rb):
+@pytest.fixture
+def builder_env():
+    old = os.environ.pop("RB200_BVH_BUILDER", None)
+    yield lambda name: os.environ.__setitem__("RB200_BVH_BUILDER", name)
+    os.environ.pop("RB200_BVH_BUILDER", None)
+    if old is not None:
+        os.environ["RB200_BVH_BUILDER"] = old
+
+
+@pytest.mark.parametrize("builder", ["ploc", "lbvh"])
+def test_bvh_build_is_deterministic(rb, builder_env, builder):
+    """Same input -> byte-identical wide nodes and triangle order (FNV-1a over both arrays), for the default PLOC
+    hierarchy and for the Karras LBVH (RB200_BVH_BUILDER=lbvh); the showroom's regular grids are the tie-heavy case."""
+    builder_env(builder)
     wl = rb.configs.dragon(32, 24, n_along=3000, n_ring=20)
     hashes = set()
     for _ in range(3):
@@ -124,6 +137,49 @@ def test_bvh_build_is_deterministic(rb):
         hashes.add((info["hash"], info["numWideNodes"], info["maxDepth"]))
         r.close()
     assert len(hashes) == 1
+
+
+@pytest.mark.parametrize("builder", ["ploc", "lbvh"])
+def test_both_builders_give_the_reference_hits(ol, rb, builder_env, builder):
+    """The closest-hit rule does not depend on the hierarchy: either builder must reproduce the oracle bit for bit,
+    on random rays against brute force and on a rendered batch."""
+    builder_env(builder)
+    wl = rb.configs.small_mixed(96, 72, nee=True, samples_per_pixel=2, max_bounces=6)
+    r, sc, g, o = render_both(ol, rb, wl, rb.RB200_FLAG_NEE, 1)
+    assert (bits(g) == bits(o)).all()
+    rng = np.random.RandomState(3)
+    n = 8000
+    org = rng.uniform(-1.0, 1.0, (n, 3)).astype(np.float32) + np.array([0, 1, 0], np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    assert_hits_equal(r.trace_rays(org, d, 1e4), sc.trace_rays(org, d, 1e4, brute=True))
+    r.close()
+
+
+def test_degenerate_inputs_for_the_clustering_builder(ol, rb):
+    """Many exactly coincident and exactly regular primitives (every union area ties): the build must terminate in a
+    bounded number of rounds and still index every triangle."""
+    quad = rb.meshes.quad((-1, 0, -1), (1, 0, -1), (1, 0, 1), (-1, 0, 1))
+    s = rb.scene.Scene()
+    oid = s.defineObject(quad)
+    for k in range(300):                  # 300 coincident copies + 300 in a regular row
+        s.addInstance(oid, np.eye(4, dtype=np.float32), rb.scene.Material())
+        s.addInstance(oid, rb.camera.translate((2.0 * k, 0.0, 0.0)), rb.scene.Material())
+    tables = s.build()
+    r = rb.Renderer(16, 16, tables)
+    assert r.bvh_info()["numTriangles"] == 1200
+    sc = ol.OracleScene(tables)
+    rng = np.random.RandomState(5)
+    org = np.stack([rng.uniform(-1, 600, 2000), np.full(2000, 1.0), rng.uniform(-1, 1, 2000)], axis=1).astype(np.float32)
+    d = np.tile(np.array([0.01, -1.0, 0.02], np.float32), (2000, 1))
+    assert_hits_equal(r.trace_rays(org, d, 1e4), sc.trace_rays(org, d, 1e4, brute=True))
+    r.close()
+
+
+def test_unknown_builder_name_is_an_error(rb, builder_env):
+    builder_env("sah")
+    wl = rb.configs.small_mixed(16, 12)
+    with pytest.raises(Exception, match="RB200_BVH_BUILDER"):
+        rb.Renderer(wl.width, wl.height, wl.tables)
 
 
 def test_render_is_deterministic_and_size_independent_properties(rb):
