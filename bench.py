@@ -332,6 +332,11 @@ def roofline(rb, wl, device, stream):
                      stream=stream.cuda_stream)
     rc.render_batch(pc)
     last_c, _ = rc.stats()
+    # the bandwidth that bounds an L2-resident traversal is the L2 gather bandwidth; measure it on a
+    # table the size of this BVH (independent random reads of whole 80-byte records, warm L2)
+    info = rc.bvh_info()
+    table_bytes = int(info["nodeBytes"] + info["triangleBytes"])
+    l2_gather = rc.measure_gather(table_bytes, 80)
     rc.close()
     n_rays = last_c["extendRays"] + last_c["shadowRays"]
     n_node = last_c["nodeVisits"] / n_rays
@@ -356,8 +361,13 @@ def roofline(rb, wl, device, stream):
                                         "shade_disney": kt["shadeMs"][3], "miss": kt["shadeMs"][4], "shadow": kt["shadowMs"],
                                         "finish": kt["finishMs"]},
                 "extend_share_of_step": kt["extendMs"] / total_ms if total_ms > 0 else None,
+                "l2_gather": {"peak": l2_gather, "unit": "GB/s", "frac": achieved / l2_gather, "table_bytes": table_bytes,
+                              "how": "rb200_measure_gather: independent random 80-byte record reads from a warm table of the "
+                                     "BVH's size, measured in this run"},
                 "note": "BVH traversal is an L2-resident pointer chase: the fraction is algorithmic bytes over the measured "
-                        "HBM copy bandwidth, the only bandwidth peak MEASURED_PEAKS.json provides"})
+                        "HBM copy bandwidth, the only bandwidth peak MEASURED_PEAKS.json provides; l2_gather gives the same "
+                        "numerator over the L2 gather bandwidth measured in this run (an upper bound: a traversal's next "
+                        "address depends on the node it just read)"})
     return res
 
 

@@ -273,6 +273,11 @@ RB200_API int rb200_get_stats(RB200Context* ctx, RB200Stats* last_batch, RB200St
 RB200_API int rb200_get_kernel_times(RB200Context* ctx, RB200KernelTimes* out);
 RB200_API int rb200_synchronize(RB200Context* ctx);
 
+/* Measurement aid (the traversal roofline is the L2 gather bandwidth, which MEASURED_PEAKS.json does not
+ * hold): GB/s of independent random reads of whole `recordBytes`-sized records (80 = wide node, 48 = triangle, 16)
+ * from a table of `tableBytes` (make it the size of the BVH so that it is L2-resident the way the BVH is). */
+RB200_API int rb200_measure_gather(RB200Context* ctx, size_t tableBytes, uint32_t recordBytes, float* out_gbps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,6 +134,12 @@ class Renderer:
         abi.check(self.lib, self.lib.rb200_get_kernel_times(self._ctx, C.byref(kt)))
         return kt.as_dict()
 
+    def measure_gather(self, table_bytes, record_bytes=80):
+        """GB/s of independent random record reads from an L2-resident table (the traversal roofline)."""
+        g = C.c_float()
+        abi.check(self.lib, self.lib.rb200_measure_gather(self._ctx, int(table_bytes), int(record_bytes), C.byref(g)))
+        return float(g.value)
+
     def synchronize(self):
         abi.check(self.lib, self.lib.rb200_synchronize(self._ctx))
 

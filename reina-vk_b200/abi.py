@@ -151,6 +151,7 @@ SYMBOLS = {
     "rb200_wait_ldr": (C.c_int, [C.c_void_p]),
     "rb200_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "rb200_host_free": (C.c_int, [C.c_void_p]),
+    "rb200_measure_gather": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_float)]),
     "rb200_write_hdr": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rb200_hdr_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "rb200_trace_primary": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RtPushConsts), C.c_void_p]),

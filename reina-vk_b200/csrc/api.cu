@@ -402,6 +402,69 @@ RB200_API int rb200_get_kernel_times(RB200Context* ctx, RB200KernelTimes* out) {
     return RB200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Roofline denominator for the traversal kernels: how fast can this GPU gather node-sized records from an
+// L2-resident table? Every thread draws independent pseudo-random record indices and reads the whole record with
+// 16-byte loads; nothing depends on the loaded values, so the figure is a bandwidth (an upper bound for a
+// traversal, whose next address depends on the node it just read).
+// ---------------------------------------------------------------------------------------------------
+} // extern "C" (templates need C++ linkage)
+template <int VEC>
+__global__ void __launch_bounds__(256) k_gather_bench(const uint4* __restrict__ table, uint32_t numRecords, uint32_t perThread,
+                                                        uint32_t seed, uint32_t* __restrict__ sink) {
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + seed;
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 4
+    for (uint32_t k = 0; k < perThread; k++) {
+        s = s * 747796405u + 2891336453u;
+        const uint32_t w = ((s >> ((s >> 28) + 4u)) ^ s) * 277803737u;
+        const uint32_t r = (uint32_t)(((unsigned long long)(w ^ (w >> 22)) * numRecords) >> 32);
+        const uint4* p = table + (size_t)r * VEC;
+#pragma unroll
+        for (int j = 0; j < VEC; j++) { const uint4 v = __ldg(p + j); acc.x ^= v.x; acc.y += v.y; acc.z ^= v.z; acc.w += v.w; }
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9E3779B9u) sink[0] = acc.x;     // keeps the loads alive
+}
+extern "C" {
+
+RB200_API int rb200_measure_gather(RB200Context* ctx, size_t tableBytes, uint32_t recordBytes, float* out_gbps) {
+    if (!ctx || !out_gbps) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    if (recordBytes != 80 && recordBytes != 48 && recordBytes != 16) { set_error("recordBytes must be 16, 48 or 80"); return RB200_ERR_INVALID_ARGUMENT; }
+    if (tableBytes < (size_t)recordBytes * 1024 || tableBytes > ((size_t)8 << 30)) { set_error("tableBytes out of range"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t numRecords = (uint32_t)(tableBytes / recordBytes);
+    uint4* table = nullptr; uint32_t* sink = nullptr;
+    if (cudaMalloc(&table, (size_t)numRecords * recordBytes) != cudaSuccess || cudaMalloc(&sink, 4) != cudaSuccess) {
+        cudaGetLastError(); if (table) cudaFree(table);
+        set_error("out of device memory"); return RB200_ERR_OUT_OF_MEMORY;
+    }
+    cudaStream_t s = ctx->stream;
+    cudaMemsetAsync(table, 0x5A, (size_t)numRecords * recordBytes, s);
+    const uint32_t blocks = (uint32_t)ctx->numSMs * 8u, perThread = 256u;
+    auto launch = [&](uint32_t seed) {
+        if (recordBytes == 80) k_gather_bench<5><<<blocks, 256, 0, s>>>(table, numRecords, perThread, seed, sink);
+        else if (recordBytes == 48) k_gather_bench<3><<<blocks, 256, 0, s>>>(table, numRecords, perThread, seed, sink);
+        else k_gather_bench<1><<<blocks, 256, 0, s>>>(table, numRecords, perThread, seed, sink);
+    };
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (uint32_t i = 0; i < 3; i++) launch(i);          // warm-up: pulls the table into L2
+    const int reps = 10;
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < reps; i++) launch(100u + (uint32_t)i);
+    cudaEventRecord(e1, s);
+    cudaError_t err = cudaStreamSynchronize(s);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(table); cudaFree(sink);
+    ctx->launches += 3 + reps;
+    if (err != cudaSuccess || cudaGetLastError() != cudaSuccess || !(ms > 0.f)) { set_error("gather micro-benchmark failed"); return RB200_ERR_CUDA; }
+    const double bytes = (double)reps * blocks * 256.0 * perThread * recordBytes;
+    *out_gbps = (float)(bytes / (ms * 1e-3) / 1e9);
+    return RB200_OK;
+}
+
 RB200_API int rb200_synchronize(RB200Context* ctx) {
     if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
     RB_CUDA(cudaStreamSynchronize(ctx->stream));

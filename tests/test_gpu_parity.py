@@ -308,3 +308,13 @@ def test_pipelined_read_back_matches_blocking_read(rb):
     r.close()
     for a, b in zip(want, got):
         assert (a == b).all()
+
+
+def test_gather_microbenchmark_reports_a_plausible_bandwidth(rb):
+    wl = rb.configs.small_mixed(16, 12)
+    r = rb.Renderer(wl.width, wl.height, wl.tables)
+    g = r.measure_gather(48 << 20, 80)
+    assert 500.0 < g < 100000.0            # GB/s: above HBM-random, below anything an SM array can issue
+    with pytest.raises(Exception, match="recordBytes"):
+        r.measure_gather(48 << 20, 64)
+    r.close()
