@@ -466,13 +466,120 @@ __device__ __forceinline__ uint32_t ref_first(const CollapseArrays& A, uint32_t 
     return (ref & LEAF_FLAG) ? (ref & ~LEAF_FLAG) : A.rangeFirst[ref];
 }
 
-__global__ void k_collapse_level(CollapseArrays A, const uint32_t* __restrict__ work, uint32_t count, uint32_t levelBase) {
+// 6a. SAH-optimal collapse (Ylitie, Karras, Laine 2017, section 3.2): for every binary node n and every i in 1..7,
+// cost[n][i] is the cheapest way to turn n's subtree into at most i children of a wide node:
+//     cost[n][1] = min( area(n) * P(n) * c_prim            (one leaf slot, only if P(n) <= MAX_LEAF_TRIS),
+//                       dist(n, 8) + area(n) * c_node )    (one wide node with up to 8 children)
+//     cost[n][i] = min( dist(n, i), cost[n][i-1] ),   dist(n, j) = min over 0 < k < j of cost[left][k] + cost[right][j-k]
+// computed bottom-up (the second thread to reach a node evaluates it, as in the refit), with the arg-min of every
+// choice kept in dec[n] so that the level-by-level pass below can unfold the decisions. dec[n].x byte i-1 (i = 2..7):
+// 0 = "same as i-1", else k; byte 0: 1 = wide node, 0 = leaf slot; byte 7: the k of dist(n, 8).
+#ifndef RB_COLLAPSE_DP
+#define RB_COLLAPSE_DP 1
+#endif
+#ifndef RB_COST_NODE
+#define RB_COST_NODE 1.0f
+#endif
+#ifndef RB_COST_PRIM
+#define RB_COST_PRIM 0.3f
+#endif
+
+__device__ __forceinline__ void ref_costs(const CollapseArrays& A, const float* __restrict__ cost, uint32_t ref, float c[8]) {
+    if (ref & LEAF_FLAG) {
+        float lo[3], hi[3]; ref_box(A, ref, lo, hi);
+        const float v = box_area(lo, hi) * RB_COST_PRIM;
+#pragma unroll
+        for (int i = 1; i <= 7; i++) c[i] = v;
+    } else {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(cost + (size_t)ref * 8));
+        const float4 b = __ldcg(reinterpret_cast<const float4*>(cost + (size_t)ref * 8) + 1);
+        c[1] = a.x; c[2] = a.y; c[3] = a.z; c[4] = a.w; c[5] = b.x; c[6] = b.y; c[7] = b.z;
+    }
+}
+
+__global__ void k_collapse_cost(uint32_t N, CollapseArrays A, const uint32_t* __restrict__ parentInt,
+                                const uint32_t* __restrict__ parentLeaf, uint32_t* __restrict__ flags, float* cost, uint2* dec) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N || N < 2) return;
+    uint32_t p = parentLeaf[i];
+    while (p != 0xFFFFFFFFu) {
+        __threadfence();
+        if (atomicAdd(&flags[p], 1u) == 0u) return;
+        __threadfence();
+        float cl[8], cr[8];
+        ref_costs(A, cost, A.childL[p], cl);
+        ref_costs(A, cost, A.childR[p], cr);
+        float lo[3], hi[3]; ref_box(A, p, lo, hi);
+        const float area = box_area(lo, hi);
+        const uint32_t P = A.rangeLast[p] - A.rangeFirst[p] + 1u;
+        float dist[9]; uint32_t kk[9];
+#pragma unroll
+        for (int j = 2; j <= 8; j++) {
+            float best = 3.0e38f; uint32_t bk = 1;
+#pragma unroll
+            for (int k = 1; k < j; k++) {
+                if (k > 7 || j - k > 7) continue;
+                const float v = cl[k] + cr[j - k];
+                if (v < best) { best = v; bk = (uint32_t)k; }
+            }
+            dist[j] = best; kk[j] = bk;
+        }
+        const float cLeaf = P <= (uint32_t)MAX_LEAF_TRIS ? area * (float)P * RB_COST_PRIM : 3.0e38f;
+        const float cInt = dist[8] + area * RB_COST_NODE;
+        float c[8];
+        uint32_t d0 = 0u, d1 = 0u;
+        c[1] = fminf(cLeaf, cInt);
+        if (cInt < cLeaf) d0 |= 1u;
+#pragma unroll
+        for (int j = 2; j <= 7; j++) {
+            if (dist[j] < c[j - 1]) { c[j] = dist[j]; if (j <= 4) d0 |= kk[j] << (8 * (j - 1)); else d1 |= kk[j] << (8 * (j - 5)); }
+            else c[j] = c[j - 1];
+        }
+        d1 |= kk[8] << 24;
+        float4* out = reinterpret_cast<float4*>(cost + (size_t)p * 8);
+        out[0] = make_float4(c[1], c[2], c[3], c[4]);
+        out[1] = make_float4(c[5], c[6], c[7], 0.f);
+        dec[p] = make_uint2(d0, d1);
+        p = parentInt[p];
+    }
+}
+
+__device__ __forceinline__ uint32_t dec_byte(uint2 d, int i) { return ((i < 4 ? d.x : d.y) >> (8 * (i & 3))) & 0xFFu; }
+
+__global__ void k_collapse_level(CollapseArrays A, const uint2* __restrict__ dec, const uint32_t* __restrict__ work, uint32_t count,
+                                 uint32_t levelBase) {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= count) return;
     const uint32_t wideIdx = levelBase + w;
     uint32_t refs[8];
+    bool leafSlot[8];
+    int n = 0;
+#if RB_COLLAPSE_DP
+    {
+        // unfold the decisions of k_collapse_cost for the wide node rooted at work[w]: children come out left to right
+        const uint32_t root = work[w];
+        uint32_t sref[16]; int sbud[16]; int top = 0;
+        if (root & LEAF_FLAG) { refs[0] = root; leafSlot[0] = true; n = 1; }
+        else {
+            const uint32_t k8 = dec_byte(dec[root], 7);
+            sref[top] = A.childR[root]; sbud[top++] = 8 - (int)k8;
+            sref[top] = A.childL[root]; sbud[top++] = (int)k8;
+        }
+        while (top > 0) {
+            const uint32_t ref = sref[--top];
+            int j = sbud[top];
+            if (ref & LEAF_FLAG) { refs[n] = ref; leafSlot[n++] = true; continue; }
+            const uint2 d = dec[ref];
+            while (j > 1 && dec_byte(d, j - 1) == 0u) j--;
+            if (j == 1) { refs[n] = ref; leafSlot[n++] = (d.x & 1u) == 0u; continue; }
+            const int k = (int)dec_byte(d, j - 1);
+            sref[top] = A.childR[ref]; sbud[top++] = j - k;
+            sref[top] = A.childL[ref]; sbud[top++] = k;
+        }
+    }
+#else
     float area[8];
-    int n = 1;
+    n = 1;
     refs[0] = work[w];
     {
         float lo[3], hi[3]; ref_box(A, refs[0], lo, hi);
@@ -490,6 +597,8 @@ __global__ void k_collapse_level(CollapseArrays A, const uint32_t* __restrict__ 
         refs[n] = R;    ref_box(A, R, lo, hi); area[n] = (R & LEAF_FLAG) ? -1.0f : box_area(lo, hi);
         n++;
     }
+    for (int j = 0; j < n; j++) leafSlot[j] = (refs[j] & LEAF_FLAG) || ref_count(A, refs[j]) <= (uint32_t)MAX_LEAF_TRIS;
+#endif
     // node bounds = union of children
     float clo[8][3], chi[8][3];
     float nlo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, nhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
@@ -557,7 +666,7 @@ __global__ void k_collapse_level(CollapseArrays A, const uint32_t* __restrict__ 
         node.qlox[s] = q[0]; node.qloy[s] = q[1]; node.qloz[s] = q[2];
         node.qhix[s] = q[3]; node.qhiy[s] = q[4]; node.qhiz[s] = q[5];
         uint32_t cnt = ref_count(A, refs[j]);
-        if ((refs[j] & LEAF_FLAG) || cnt <= (uint32_t)MAX_LEAF_TRIS) {
+        if (leafSlot[j]) {
             uint32_t unary = (1u << cnt) - 1u;      // 1 -> 001, 2 -> 011, 3 -> 111
             node.meta[s] = (uint8_t)((unary << 5) | triOffset);
             A.slotTriFirst[wideIdx * 8 + s] = ref_first(A, refs[j]);
@@ -632,7 +741,7 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
     if (N >= 0x40000000u) { set_error("too many triangles"); return RB200_ERR_INVALID_ARGUMENT; }
 
     Arena arena;
-    arena.cap = (size_t)N * 640 + prefix.size() * 4 + (1u << 20);
+    arena.cap = (size_t)N * 704 + prefix.size() * 4 + (1u << 20);
     if (cudaMalloc((void**)&arena.base, arena.cap) != cudaSuccess) {
         cudaGetLastError(); arena.base = nullptr;
         set_error("out of device memory for the BVH build (%zu MiB of temporaries)", arena.cap >> 20);
@@ -732,12 +841,20 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
     CollapseArrays A{childL, childR, rFirst, rLast, leafLoFinal, leafHiFinal, nodeLo, nodeHi, nodesTmp, nodeInternalCount, nodeTriCount,
                      nodeChildRefs, slotTriFirst};
     RB_CUDA(cudaMemcpyAsync(work[0], &rootRef, 4, cudaMemcpyHostToDevice, stream));
+    float* dpCost = nullptr; uint2* dpDec = nullptr;
+#if RB_COLLAPSE_DP
+    if (N > 1) {
+        RB_CUDA(dalloc(&dpCost, (size_t)N * 8)); RB_CUDA(dalloc(&dpDec, N));
+        RB_CUDA(cudaMemsetAsync(flags, 0, (size_t)N * 4, stream));
+        k_collapse_cost<<<G, B, 0, stream>>>(N, A, parentInt, parentLeaf, flags, dpCost, dpDec); nl++;
+    }
+#endif
     uint32_t levelBase = 0, levelCount = 1, depth = 0;
     int wcur = 0;
     while (levelCount > 0) {
         if ((size_t)levelBase + levelCount > maxNodes) { set_error("internal: wide node overflow"); return RB200_ERR_CUDA; }
         uint32_t g = (levelCount + 127) / 128;
-        k_collapse_level<<<g, 128, 0, stream>>>(A, work[wcur], levelCount, levelBase); nl++;
+        k_collapse_level<<<g, 128, 0, stream>>>(A, dpDec, work[wcur], levelCount, levelBase); nl++;
         exclusive_scan<uint32_t>(nodeInternalCount + levelBase, levelPrefix, levelCount, dTotal, scanScratch, stream, nl);
         uint32_t nextBase = levelBase + levelCount;
         k_link_children<<<g, 128, 0, stream>>>(nodesTmp, levelPrefix, nodeInternalCount, nodeChildRefs, levelCount, levelBase,
