@@ -6,6 +6,7 @@
 #include "config.h"
 #include "host.h"
 #include "png.h"
+#include "texture.h"
 
 using namespace rbhost;
 
@@ -76,7 +77,7 @@ int rbhost_tables_obj(const char* path, uint32_t materialIdx, int addLight, Scen
         m.materialIdx = materialIdx;
         m.albedo = {0.8f, 0.8f, 0.8f};
         m.interpNormals = true;
-        Scene s = make_obj_scene({{path, m}}, addLight != 0);
+        Scene s = make_obj_scene({{path, m, ""}}, addLight != 0);
         *out = new SceneTables(s.build(false));
     });
 }
@@ -99,6 +100,16 @@ int64_t rbhost_png_encode(const uint8_t* rgba, uint32_t width, uint32_t height, 
         std::memcpy(out, png.data(), png.size() < capacity ? png.size() : capacity);
     });
     return n;
+}
+
+// decodes a PNG file to RGBA8; returns 0 and the size, writes at most `capacity` bytes
+int rbhost_png_load(const char* path, int flip, uint8_t* out, uint64_t capacity, uint32_t* width, uint32_t* height) {
+    return guarded([&] {
+        Image8 img = load_png_rgba8(path, flip != 0);
+        *width = uint32_t(img.width);
+        *height = uint32_t(img.height);
+        std::memcpy(out, img.rgba.data(), img.rgba.size() < capacity ? img.rgba.size() : capacity);
+    });
 }
 
 // Drives SaveManager + FrameClock through `frames` frames of `spp` samples, `secondsPerFrame` apart, in the order of

@@ -7,6 +7,7 @@
 #include <stdexcept>
 
 #include "png.h"
+#include "texture.h"
 #include "rh_math.h"
 
 namespace rbhost {
@@ -93,7 +94,9 @@ Scene make_obj_scene(const std::vector<ObjRequest>& objs, bool addLight) {
         if (!hasUv && o.material.materialIdx == 3)
             std::fprintf(stderr, "warning: %s has no texture coordinates; tangents are zero and Disney shading will be NaN on it "
                                  "(same as the reference, src/scene/Models.cpp:144-152)\n", o.path.c_str());
-        s.addObject(md, identity(), o.material);
+        Material m = o.material;
+        if (!o.texturePath.empty()) m.textureID = int(s.defineTexture(load_png_rgba8(o.texturePath, true)));
+        s.addObject(md, identity(), m);
     }
     if (addLight) s.addObject(cornell_light(), identity(), light_material());
     return s;

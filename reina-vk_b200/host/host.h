@@ -43,6 +43,7 @@ Scene make_builtin_scene(const std::string& name);
 struct ObjRequest {
     std::string path;
     Material material;
+    std::string texturePath;     // PNG albedo texture (Scene::defineTexture of a file: flipped vertically), may be empty
 };
 // showroom-less generic scene: every OBJ at identity + the Cornell light panel (so NEE has an emitter)
 Scene make_obj_scene(const std::vector<ObjRequest>& objs, bool addLight);

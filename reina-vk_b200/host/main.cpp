@@ -25,6 +25,7 @@ static void usage() {
         "  --material NAME      material of the following --obj: lambertian | metal | dielectric | disney (default lambertian)\n"
         "  --albedo R,G,B       albedo of the following --obj (default 0.8,0.8,0.8)\n"
         "  --roughness X  --ior X  --metallic X     parameters of the following --obj\n"
+        "  --texture FILE       PNG albedo texture of the following --obj (flipped vertically like the reference's file textures)\n"
         "  --width N --height N image size (overrides [render])\n"
         "  --spp N              stop after N samples per pixel in total\n"
         "  --seconds S          stop after S seconds\n"
@@ -46,6 +47,7 @@ static bool parse_vec3(const char* s, std::array<float, 3>& out) {
 int main(int argc, char** argv) {
     std::string configPath = "config/config.toml", sceneName, finalOut, outDir = ".", dumpPc;
     std::vector<ObjRequest> objs;
+    std::string nextTexture;
     Material nextMat;
     nextMat.albedo = {0.8f, 0.8f, 0.8f};
     nextMat.interpNormals = true;
@@ -64,7 +66,8 @@ int main(int argc, char** argv) {
             if (a == "--help" || a == "-h") { usage(); return 0; }
             else if (a == "--config") configPath = value();
             else if (a == "--scene") sceneName = value();
-            else if (a == "--obj") { objs.push_back({value(), nextMat}); }
+            else if (a == "--obj") { objs.push_back({value(), nextMat, nextTexture}); nextTexture.clear(); }
+            else if (a == "--texture") nextTexture = value();
             else if (a == "--material") {
                 const std::string m = value();
                 if (m == "lambertian") nextMat.materialIdx = 0;

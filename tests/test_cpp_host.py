@@ -325,6 +325,76 @@ def test_save_policy_follows_the_reference_clock(host):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# texture ingest
+# ---------------------------------------------------------------------------------------------------------------
+def png_load(host, path, flip):
+    buf = np.zeros(1 << 20, np.uint8)
+    w, h = C.c_uint32(), C.c_uint32()
+    rc = host.rbhost_png_load(str(path).encode(), int(flip), buf.ctypes.data_as(C.c_void_p), C.c_uint64(buf.size),
+                              C.byref(w), C.byref(h))
+    if rc != 0:
+        raise RuntimeError(err(host))
+    return buf[:w.value * h.value * 4].reshape(h.value, w.value, 4).copy()
+
+
+def test_png_decoder_matches_pil_on_every_colour_type(host, tmp_path):
+    """8-bit RGBA the way stb_image returns it with 4 requested channels (src/graphics/Image.cpp:14-15): grey and
+    palette expanded, tRNS honoured, file textures flipped vertically. PIL writes with adaptive scanline filters."""
+    from PIL import Image
+    rng = np.random.default_rng(9)
+    h, w = 37, 53
+    rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    smooth = (np.add.outer(np.arange(h) * 3, np.arange(w) * 2) % 256).astype(np.uint8)       # exercises Sub/Up/Paeth
+    cases = {
+        "rgba": Image.fromarray(rgba, "RGBA"),
+        "rgb": Image.fromarray(rgba[..., :3].copy(), "RGB"),
+        "grey": Image.fromarray(smooth, "L"),
+        "grey_alpha": Image.fromarray(np.stack([smooth, rgba[..., 3]], axis=2), "LA"),
+        "palette": Image.fromarray(rgba[..., :3].copy(), "RGB").quantize(64),
+        "bilevel": Image.fromarray((smooth > 127).astype(np.uint8) * 255, "L").convert("1"),
+    }
+    for name, im in cases.items():
+        p = tmp_path / f"{name}.png"
+        im.save(p)
+        want = np.asarray(Image.open(p).convert("RGBA"))
+        assert (png_load(host, p, False) == want).all(), name
+        assert (png_load(host, p, True) == want[::-1]).all(), name
+    # palette with per-entry alpha (tRNS)
+    pal = Image.fromarray(rgba[..., :3].copy(), "RGB").quantize(16)
+    p = tmp_path / "palette_trns.png"
+    pal.save(p, transparency=bytes([0, 128, 255, 7] + [255] * 12))
+    assert (png_load(host, p, False) == np.asarray(Image.open(p).convert("RGBA"))).all()
+    # 16-bit grey keeps the high byte
+    g16 = (np.add.outer(np.arange(h), np.arange(w)) * 517 % 65536).astype(np.uint16)
+    p = tmp_path / "grey16.png"
+    Image.fromarray(g16).save(p)
+    got = png_load(host, p, False)
+    assert (got[..., 0] == (g16 >> 8)).all() and (got[..., 3] == 255).all()
+    # our own writer round-trips through our own reader
+    out = np.zeros(h * w * 4 + 4096, np.uint8)
+    n = host.rbhost_png_encode(rgba.ctypes.data, w, h, out.ctypes.data, out.size)
+    (tmp_path / "own.png").write_bytes(out[:n].tobytes())
+    assert (png_load(host, tmp_path / "own.png", False) == rgba).all()
+
+
+def test_png_decoder_refuses_what_it_does_not_support(host, tmp_path):
+    from PIL import Image
+    (tmp_path / "not.png").write_bytes(b"JFIF" * 10)
+    with pytest.raises(RuntimeError, match="Could not load image at path"):
+        png_load(host, tmp_path / "not.png", True)
+    with pytest.raises(RuntimeError, match="Could not load image at path"):
+        png_load(host, tmp_path / "absent.png", True)
+    im = Image.fromarray(np.zeros((8, 8, 3), np.uint8), "RGB")
+    good = tmp_path / "good.png"
+    im.save(good)
+    data = bytearray(good.read_bytes())
+    data[40] ^= 0xFF                                       # corrupt a byte inside a chunk: checksum must catch it
+    (tmp_path / "bad.png").write_bytes(bytes(data))
+    with pytest.raises(RuntimeError, match="checksum|corrupt"):
+        png_load(host, tmp_path / "bad.png", True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # end to end on the GPU
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
@@ -354,6 +424,45 @@ def test_cli_renders_cornell_like_the_python_host(host, rb, tmp_path):
     r.close()
     assert (decode_png(out.read_bytes()) == frames[5]).all()
     assert (decode_png((tmp_path / "output_8spp.png").read_bytes()) == frames[4]).all()
+
+
+@pytest.mark.gpu
+def test_cli_textured_obj_like_the_python_host(host, rb, tmp_path):
+    """--obj + --texture: the C++ importer and PNG decoder feed the same tables as load_obj + a PIL-decoded, vertically
+    flipped texture on the Python side; the rendered frame must be identical."""
+    from PIL import Image
+    (tmp_path / "asset.obj").write_text(OBJ_FULL)
+    rng = np.random.default_rng(21)
+    tex = rng.integers(0, 256, (32, 48, 4), dtype=np.uint8)
+    tex[..., 3] = 255
+    Image.fromarray(tex, "RGBA").save(tmp_path / "tex.png")
+    cfg = tmp_path / "config.toml"
+    cfg.write_text(REFERENCE_SCHEMA.replace("save_on_samples = [64, 256, 1024]", "save_on_samples = []")
+                   .replace("save_on_times = [60.0]", "save_on_times = []")
+                   + "\n[render]\nwidth = 80\nheight = 60\ncamera_pos = [0.4, 0.9, 2.6]\ncamera_look_at = [0.0, 0.1, 0.0]\n")
+    out, pcfile = tmp_path / "final.png", tmp_path / "pc.bin"
+    run = subprocess.run([os.path.join(HOST, "reina_b200"), "--config", str(cfg), "--texture", str(tmp_path / "tex.png"),
+                          "--obj", str(tmp_path / "asset.obj"), "--spp", "16", "--out", str(out), "--dump-pc", str(pcfile),
+                          "--quiet"], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr + run.stdout
+
+    s = rb.scene.Scene()
+    tid = s.defineTexture(np.ascontiguousarray(tex[::-1]))
+    s.addObject(rb.meshes.load_obj(str(tmp_path / "asset.obj")), np.eye(4, dtype=np.float32),
+                rb.scene.Material(albedo=(0.8, 0.8, 0.8), interpNormals=True, textureID=tid))
+    s.addObject(rb.meshes.cornell_light(), np.eye(4, dtype=np.float32), rb.scene.Material(**rb.configs.LIGHT))
+    tables = s.build(require_emitter=True)
+    pc = rb.abi.RtPushConsts.from_buffer_copy(pcfile.read_bytes())
+    r = rb.Renderer(80, 60, tables, flags=rb.RB200_FLAG_NEE)
+    for b in range(2):
+        pc.sampleBatch = b
+        r.render_batch(pc)
+    r.postprocess()
+    want = r.read_ldr().copy()
+    r.close()
+    got = decode_png(out.read_bytes())
+    assert (got == want).all()
+    assert got[..., :3].max() > 0                              # the frame is not empty
 
 
 @pytest.mark.gpu
