@@ -197,8 +197,38 @@ __device__ __forceinline__ bool surface_prologue(const WaveParams& P, const RB20
     return true;
 }
 
+// End of a path (rgen.glsl:264-284): clamp, drop NaN samples, add to the pixel's batch sum; then either restart the
+// slot with the pixel's next sample (returns 1) or store the batch mean of the pixel (returns 0). L is the path's
+// final radiance, st the slot's state record.
+#ifndef RB_FINISH_IN_MISS
+#define RB_FINISH_IN_MISS 1      // sky misses finish their path inside the miss shader instead of going through endQ + k_finish
+#endif
+__device__ __forceinline__ uint32_t finish_slot(const WaveParams& P, const uint32_t slot, const rb_v3 L, const uint4 st,
+                                                uint32_t* cntNext, int parity) {
+    const rb_v3 c = rb_clamp3_keepnan(L, 0.0f, P.pc.directClamp);
+    float4 s4 = P.sum[slot];
+    uint32_t actual = __float_as_uint(s4.w);
+    if (!rb_anynan3(c)) { actual += 1u; s4.x += c.x; s4.y += c.y; s4.z += c.z; }
+    const uint32_t sampleIdx = st.z + 1u;
+    if (sampleIdx < P.pc.samplesPerPixel) {
+        P.sum[slot] = make_float4(s4.x, s4.y, s4.z, __uint_as_float(actual));
+        uint32_t rng = st.x;
+        begin_path(P, slot, rng, sampleIdx);
+        queue_push(P.rayQ[parity ^ 1], &cntNext[CNT_RAYS], slot);
+        return 1u;
+    }
+    // last sample of the pixel: this batch's mean over the valid samples (rgen.glsl:275); folded into the image by
+    // k_accumulate once the whole batch is done
+    if (actual == 0u) P.mean[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    else {
+        const rb_v3 fin = rb_mk3(s4.x, s4.y, s4.z) / (float)actual;
+        P.mean[slot] = make_float4(fin.x, fin.y, fin.z, 1.f);
+    }
+    return 0u;
+}
+
 template <int MAT>
-__device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t slot, uint32_t* cnt, uint32_t* cntNext, int parity) {
+__device__ __forceinline__ uint32_t shade_slot(const WaveParams& P, const uint32_t slot, uint32_t* cnt, uint32_t* cntNext, int parity) {
     const float4 ro4 = P.rayO[slot], rd4 = P.rayD[slot];
     const rb_v3 rayOrigin = rb_mk3(ro4.x, ro4.y, ro4.z), rayDir = rb_mk3(rd4.x, rd4.y, rd4.z);
     uint4 st = P.st[slot];
@@ -214,9 +244,15 @@ __device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t s
         // miss shader + raygen's sky branch (rgen.glsl:138-141): radiance += sky * throughput, path ends
         const float4 L4 = P.rad[slot];
         const rb_v3 L = rb_mk3(L4.x, L4.y, L4.z) + sky_color(rayDir) * T;
+#if RB_FINISH_IN_MISS
+        // nothing else can add to this path (a miss casts no shadow ray, and the previous hit's shadow ray was resolved
+        // in the previous wave), so the path ends here: about 60 % of all path ends skip endQ and k_finish
+        return finish_slot(P, slot, L, st, cntNext, parity);
+#else
         P.rad[slot] = make_float4(L.x, L.y, L.z, 0.f);
         queue_push(P.endQ, &cnt[CNT_END], slot);
-        return;
+        return 0u;
+#endif
     }
 
     const uint4 h = P.hit[slot];
@@ -377,6 +413,7 @@ __device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t s
     P.st[slot] = make_uint4(rng, newFlags | (segments << 8), st.z, st.w);
     if (segments < P.pc.maxBounces) queue_push(P.rayQ[parity ^ 1], &cntNext[CNT_RAYS], slot);
     else queue_push(P.endQ, &cnt[CNT_END], slot);
+    return 0u;
 }
 
 #ifndef RB_SHADE_MINBLOCKS
@@ -391,8 +428,13 @@ __global__ void __launch_bounds__(BLOCK, MAT == 3 ? RB_DISNEY_MINBLOCKS : RB_SHA
     uint32_t* cntNext = P.counters + (parity ^ 1) * CNT_SET;
     const uint32_t n = cnt[CNT_MAT0 + MAT];
     const uint32_t* __restrict__ q = P.matQ[MAT];
+    uint32_t started = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        shade_slot<MAT>(P, q[i], cnt, cntNext, parity);
+        started += shade_slot<MAT>(P, q[i], cnt, cntNext, parity);
+    if (MAT == 4) {      // paths restarted by the miss shader (one counter update per warp)
+        const uint32_t warpStarted = __reduce_add_sync(0xffffffffu, started);
+        if ((threadIdx.x & 31u) == 0u && warpStarted) atomicAdd(&P.stats[ST_PATHS], (unsigned long long)warpStarted);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -439,27 +481,7 @@ __global__ void __launch_bounds__(BLOCK) k_finish(WaveParams P, int parity) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t slot = P.endQ[i];
         const float4 L4 = P.rad[slot];
-        const rb_v3 c = rb_clamp3_keepnan(rb_mk3(L4.x, L4.y, L4.z), 0.0f, P.pc.directClamp);
-        float4 s4 = P.sum[slot];
-        uint32_t actual = __float_as_uint(s4.w);
-        if (!rb_anynan3(c)) { actual += 1u; s4.x += c.x; s4.y += c.y; s4.z += c.z; }
-        uint4 st = P.st[slot];
-        const uint32_t sampleIdx = st.z + 1u;
-        if (sampleIdx < P.pc.samplesPerPixel) {
-            P.sum[slot] = make_float4(s4.x, s4.y, s4.z, __uint_as_float(actual));
-            uint32_t rng = st.x;
-            begin_path(P, slot, rng, sampleIdx);
-            started++;
-            queue_push(P.rayQ[parity ^ 1], &cntNext[CNT_RAYS], slot);
-        } else {
-            // last sample of the pixel: this batch's mean over the valid samples (rgen.glsl:275); folded into the
-            // image by k_accumulate once the whole batch is done
-            if (actual == 0u) P.mean[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-            else {
-                const rb_v3 fin = rb_mk3(s4.x, s4.y, s4.z) / (float)actual;
-                P.mean[slot] = make_float4(fin.x, fin.y, fin.z, 1.f);
-            }
-        }
+        started += finish_slot(P, slot, rb_mk3(L4.x, L4.y, L4.z), P.st[slot], cntNext, parity);
     }
     // one counter update per warp, not per thread: a same-address 64-bit atomic from every thread serialises in L2
     const uint32_t warpStarted = __reduce_add_sync(0xffffffffu, started);
