@@ -738,7 +738,7 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
     for (size_t i = 0; i < hi.size(); i++) prefix[i + 1] = prefix[i] + hi[i].triangleCount;
     const uint32_t N = prefix.back();
     if (N == 0) { set_error("scene has no triangles"); return RB200_ERR_INVALID_ARGUMENT; }
-    if (N >= 0x40000000u) { set_error("too many triangles"); return RB200_ERR_INVALID_ARGUMENT; }
+    if (N >= 0x08000000u) { set_error("too many triangles (limit 2^27: the traversal packs triangle index and lane into 32 bits)"); return RB200_ERR_INVALID_ARGUMENT; }
 
     Arena arena;
     arena.cap = (size_t)N * 704 + prefix.size() * 4 + (1u << 20);

@@ -52,10 +52,20 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
 #define RB_WORK_CAP 128   // pooled triangles per pass (a chunk produces ~90 per warp; more are handled by extra passes)
 #endif
 
+#ifndef RB_SMEM_STACK
+#define RB_SMEM_STACK 0   // entries of the per-lane node stack kept in shared memory (deeper entries stay in local memory).
+                          // Pushes and pops of the local-memory stack are 21 % of the stall samples in r01f, but the
+                          // shared memory this takes comes out of L1: measured on B200, 6 / 8 / 10 entries = -3 / -8 /
+                          // -8 % closest-hit rays/s (10 entries = +20 KB per block, L1 150 -> 70 KB per SM). Off.
+#endif
+
 // per-warp staging area of the pooled triangle phase
 struct WarpShared {
+#if RB_SMEM_STACK > 0
+    uint2 stack[RB_SMEM_STACK][32];       // [entry][lane]: the first RB_SMEM_STACK pending node groups of every lane
+#endif
     float4 ray[32][3];                    // per lane: (o, tmax), (mx, Sz), (my, bits(kz)) — shear rows of rb_tri.h
-    uint2 work[RB_WORK_CAP];              // (triangle index, owner lane)
+    uint32_t work[RB_WORK_CAP];           // triangle index << 5 | owner lane (the build refuses >= 2^27 triangles)
     unsigned long long bestKey[32];       // per owner: min over candidates of (t bits << 32 | global primitive id)
     float4 payload[32];                   // per owner: b1, b2, bits(triangle index) of the current best
 };
@@ -83,8 +93,26 @@ struct Traversal {
     int sp, tsp;
     uint32_t tcount;              // triangles queued in tgroup + tstack
     RayHit best;
-    uint2 stack[TRAV_STACK];
+    uint2 stack[TRAV_STACK - RB_SMEM_STACK];    // overflow of the shared-memory stack (the whole stack if RB_SMEM_STACK == 0)
+    uint2* sstack;                // this lane's column of WarpShared::stack (stride 32 entries)
     uint2 tstack[RB_CHUNK];       // triangle groups produced by the node steps of the current chunk
+
+    __device__ __forceinline__ void push(const uint2 v) {
+#if RB_SMEM_STACK > 0
+        if (sp < RB_SMEM_STACK) sstack[sp * 32] = v; else stack[sp - RB_SMEM_STACK] = v;
+#else
+        stack[sp] = v;
+#endif
+        sp++;
+    }
+    __device__ __forceinline__ uint2 pop_entry() {
+        --sp;
+#if RB_SMEM_STACK > 0
+        return sp < RB_SMEM_STACK ? sstack[sp * 32] : stack[sp - RB_SMEM_STACK];
+#else
+        return stack[sp];
+#endif
+    }
 
     __device__ __forceinline__ void init(const rb_v3 org, const rb_v3 d, const float tmax_, float4* rayStage) {
         o = org; tmax = tmax_;
@@ -108,7 +136,7 @@ struct Traversal {
     // No node group current: take the next one from the stack. Returns false when no node work is left.
     __device__ __forceinline__ bool pop() {
         if (sp == 0) return false;
-        ngroup = stack[--sp];
+        ngroup = pop_entry();
         return true;
     }
 
@@ -129,7 +157,7 @@ struct Traversal {
         const uint32_t bitIndex = 31u - (uint32_t)__clz(hits);
         const uint32_t base = ngroup.x;
         ngroup.y &= ~(1u << bitIndex);
-        if (ngroup.y > 0x00FFFFFFu) { stack[sp++] = ngroup; }
+        if (ngroup.y > 0x00FFFFFFu) push(ngroup);
         const uint32_t slot = (bitIndex - 24u) ^ oct_inv;
         const uint32_t rel = __popc(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
         const float4* np = reinterpret_cast<const float4*>(nodes + (base + rel));
@@ -222,6 +250,11 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
     const uint32_t lane = threadIdx.x & 31u;
     Traversal<ANY, COUNT> tr;
     tr.tcount = 0;
+#if RB_SMEM_STACK > 0
+    tr.sstack = &ws.stack[0][lane];
+#else
+    tr.sstack = nullptr;
+#endif
     bool has = false;
     bool exhausted = false;
     uint32_t rayIdx = 0;
@@ -271,7 +304,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
             uint32_t pos = incl - c;
             const unsigned long long seed = has ? hit_key(tr.best.t, tr.best.gid) : ~0ull;
             ws.bestKey[lane] = seed;
-            while (has && tr.tcount > 0u && pos < (uint32_t)RB_WORK_CAP) ws.work[pos++] = make_uint2(tr.take_tri(), lane);
+            while (has && tr.tcount > 0u && pos < (uint32_t)RB_WORK_CAP) ws.work[pos++] = (tr.take_tri() << 5) | lane;
             __syncwarp();
             const uint32_t count = min(total, (uint32_t)RB_WORK_CAP);
             for (uint32_t b = 0; b < count; b += 32u) {
@@ -280,8 +313,8 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                 uint32_t owner = 0, triIdx = 0;
                 float b1 = 0.f, b2 = 0.f;
                 if (b + lane < count) {
-                    const uint2 item = ws.work[b + lane];
-                    triIdx = item.x; owner = item.y;
+                    const uint32_t item = ws.work[b + lane];
+                    triIdx = item >> 5; owner = item & 31u;
                     const float4 r0 = ws.ray[owner][0], r1 = ws.ray[owner][1], r2 = ws.ray[owner][2];
                     const float4* tp = reinterpret_cast<const float4*>(tris + triIdx);
                     const float4 va = __ldg(tp + 0), vb = __ldg(tp + 1), vc = __ldg(tp + 2);
