@@ -49,9 +49,14 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
                            // measured -5 % on B200 (extend 1426 vs 1504 Mrays/s), kept only as a switch
 #endif
 #ifndef RB_WORK_CAP
-#define RB_WORK_CAP 128   // pooled triangles per pass (a chunk produces ~90 per warp; more are handled by extra passes)
+#define RB_WORK_CAP 256   // pooled triangles per pass (a chunk produces ~90 per warp; more are handled by extra passes).
+                          // 64 / 96 / 128 / 256 entries: -4 / -1 / 0 / +1 % on B200 with 4-byte entries
 #endif
 
+#ifndef RB_TRI_LDCG
+#define RB_TRI_LDCG 0     // 1: triangle records bypass L1 (ld.global.cg): measured -1 % closest-hit, -5 % any-hit on B200
+                          // (neighbouring rays do re-use each other's triangles); ray records through L2 only: no change
+#endif
 #ifndef RB_SMEM_STACK
 #define RB_SMEM_STACK 0   // entries of the per-lane node stack kept in shared memory (deeper entries stay in local memory).
                           // Pushes and pops of the local-memory stack are 21 % of the stall samples in r01f, but the
@@ -281,6 +286,8 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
         if (busy == 0u) break;
 
         // ---- 2. a chunk of wide-node steps per lane ----
+        // (ending the chunk early once fewer than 8 / 16 / 24 lanes still have node work — a warp-uniform loop with a
+        // ballot per step — was measured at -12 / -14 / -18 % closest-hit rays/s: the fixed chunk stays)
         if (has) {
 #pragma unroll 1
             for (int it = 0; it < RB_CHUNK; it++) {
@@ -317,7 +324,12 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                     triIdx = item >> 5; owner = item & 31u;
                     const float4 r0 = ws.ray[owner][0], r1 = ws.ray[owner][1], r2 = ws.ray[owner][2];
                     const float4* tp = reinterpret_cast<const float4*>(tris + triIdx);
+#if RB_TRI_LDCG
+                    // triangles are read about once per ray: keep them out of L1 so that it holds wide nodes
+                    const float4 va = __ldcg(tp + 0), vb = __ldcg(tp + 1), vc = __ldcg(tp + 2);
+#else
                     const float4 va = __ldg(tp + 0), vb = __ldg(tp + 1), vc = __ldg(tp + 2);
+#endif
                     if (COUNT) triTests++;
                     rb_ray_shear sh;
                     sh.mx = rb_mk3(r1.x, r1.y, r1.z); sh.my = rb_mk3(r2.x, r2.y, r2.z); sh.mz = rb_axis3(__float_as_int(r2.w), r1.w);
