@@ -57,18 +57,9 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
 #define RB_TRI_LDCG 0     // 1: triangle records bypass L1 (ld.global.cg): measured -1 % closest-hit, -5 % any-hit on B200
                           // (neighbouring rays do re-use each other's triangles); ray records through L2 only: no change
 #endif
-#ifndef RB_SMEM_STACK
-#define RB_SMEM_STACK 0   // entries of the per-lane node stack kept in shared memory (deeper entries stay in local memory).
-                          // Pushes and pops of the local-memory stack are 21 % of the stall samples in r01f, but the
-                          // shared memory this takes comes out of L1: measured on B200, 6 / 8 / 10 entries = -3 / -8 /
-                          // -8 % closest-hit rays/s (10 entries = +20 KB per block, L1 150 -> 70 KB per SM). Off.
-#endif
 
 // per-warp staging area of the pooled triangle phase
 struct WarpShared {
-#if RB_SMEM_STACK > 0
-    uint2 stack[RB_SMEM_STACK][32];       // [entry][lane]: the first RB_SMEM_STACK pending node groups of every lane
-#endif
     float4 ray[32][3];                    // per lane: (o, tmax), (mx, Sz), (my, bits(kz)) — shear rows of rb_tri.h
     uint32_t work[RB_WORK_CAP];           // triangle index << 5 | owner lane (the build refuses >= 2^27 triangles)
     unsigned long long bestKey[32];       // per owner: min over candidates of (t bits << 32 | global primitive id)
@@ -85,8 +76,13 @@ __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
 // subtraction — the bias is folded into the plane offsets (c' = c - 2^15 * s), whose extra rounding (<= 2^-9 of a
 // grid step) is covered by the slack below.
 static constexpr float BYTE_BIAS = 32768.0f;
-__device__ __forceinline__ float byte_f(uint32_t w, int j) {
-    return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404u + ((uint32_t)j << 4)));
+// The 0x47000000 word comes from constant memory on purpose: with both PRMT inputs known at compile time ptxas keeps
+// the WORD as the immediate and the four selectors in registers, and under the 64-register cap it re-materialises
+// those selectors with an extra move in front of most of the 48 PRMTs of a node step. A run-time word leaves the
+// selector as the immediate: one register, no moves.
+__constant__ uint32_t c_byteBiasWord = 0x47000000u;
+__device__ __forceinline__ float byte_f(uint32_t w, int j, uint32_t biasWord) {
+    return __uint_as_float(__byte_perm(w, biasWord, 0x7404u + ((uint32_t)j << 4)));
 }
 
 template <bool ANY, bool COUNT>
@@ -98,26 +94,15 @@ struct Traversal {
     int sp, tsp;
     uint32_t tcount;              // triangles queued in tgroup + tstack
     RayHit best;
-    uint2 stack[TRAV_STACK - RB_SMEM_STACK];    // overflow of the shared-memory stack (the whole stack if RB_SMEM_STACK == 0)
-    uint2* sstack;                // this lane's column of WarpShared::stack (stride 32 entries)
+    uint2 stack[TRAV_STACK];      // pending node groups (local memory)
     uint2 tstack[RB_CHUNK];       // triangle groups produced by the node steps of the current chunk
 
-    __device__ __forceinline__ void push(const uint2 v) {
-#if RB_SMEM_STACK > 0
-        if (sp < RB_SMEM_STACK) sstack[sp * 32] = v; else stack[sp - RB_SMEM_STACK] = v;
-#else
-        stack[sp] = v;
-#endif
-        sp++;
-    }
-    __device__ __forceinline__ uint2 pop_entry() {
-        --sp;
-#if RB_SMEM_STACK > 0
-        return sp < RB_SMEM_STACK ? sstack[sp * 32] : stack[sp - RB_SMEM_STACK];
-#else
-        return stack[sp];
-#endif
-    }
+    // Measured alternatives for this stack, both slower on B200: (a) the first 6 / 8 / 10 entries in shared memory:
+    // -3 / -8 / -8 % closest-hit rays/s — the shared memory comes out of L1 (150 -> 70 KB per SM at 10 entries) and
+    // the node / triangle stream needs it more; (b) the newest entry cached in registers and refilled from local memory
+    // when consumed: -9 % (two more live registers under the 64-register cap, and the refill is waited for by the very
+    // next push). Pops waiting for their local-memory load are ~12 % of the stall samples of r01f.
+    __device__ __forceinline__ void push(const uint2 v) { stack[sp++] = v; }
 
     __device__ __forceinline__ void init(const rb_v3 org, const rb_v3 d, const float tmax_, float4* rayStage) {
         o = org; tmax = tmax_;
@@ -137,11 +122,12 @@ struct Traversal {
     }
 
     __device__ __forceinline__ bool want_node() const { return ngroup.y > 0x00FFFFFFu; }
+    __device__ __forceinline__ bool stack_empty() const { return sp == 0; }
 
     // No node group current: take the next one from the stack. Returns false when no node work is left.
     __device__ __forceinline__ bool pop() {
         if (sp == 0) return false;
-        ngroup = pop_entry();
+        ngroup = stack[--sp];
         return true;
     }
 
@@ -184,6 +170,7 @@ struct Traversal {
         const float cny = fmaf(-BYTE_BIAS, sy, cy - ky), cfy = fmaf(-BYTE_BIAS, sy, cy + ky);
         const float cnz = fmaf(-BYTE_BIAS, sz, cz - kz), cfz = fmaf(-BYTE_BIAS, sz, cz + kz);
         const uint32_t oct_inv4 = oct_inv * 0x01010101u;
+        const uint32_t kb = c_byteBiasWord;
 
         ngroup.x = __float_as_uint(n1.x);
         uint32_t hitmask = 0u;
@@ -206,9 +193,9 @@ struct Traversal {
             const uint32_t nz = idz < 0.f ? qhiz : qloz, fz = idz < 0.f ? qloz : qhiz;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float t0x = fmaf(byte_f(nx, j), sx, cnx), t1x = fmaf(byte_f(fx, j), sx, cfx);
-                const float t0y = fmaf(byte_f(ny, j), sy, cny), t1y = fmaf(byte_f(fy, j), sy, cfy);
-                const float t0z = fmaf(byte_f(nz, j), sz, cnz), t1z = fmaf(byte_f(fz, j), sz, cfz);
+                const float t0x = fmaf(byte_f(nx, j, kb), sx, cnx), t1x = fmaf(byte_f(fx, j, kb), sx, cfx);
+                const float t0y = fmaf(byte_f(ny, j, kb), sy, cny), t1y = fmaf(byte_f(fy, j, kb), sy, cfy);
+                const float t0z = fmaf(byte_f(nz, j, kb), sz, cnz), t1z = fmaf(byte_f(fz, j, kb), sz, cfz);
                 const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
                 const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tcur));
                 if (tn <= tf) {
@@ -255,11 +242,6 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
     const uint32_t lane = threadIdx.x & 31u;
     Traversal<ANY, COUNT> tr;
     tr.tcount = 0;
-#if RB_SMEM_STACK > 0
-    tr.sstack = &ws.stack[0][lane];
-#else
-    tr.sstack = nullptr;
-#endif
     bool has = false;
     bool exhausted = false;
     uint32_t rayIdx = 0;
@@ -369,7 +351,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
             if (ANY && anyHitFound) {
                 tr.best.tri = 0u;     // any-hit: only "occluded or not" is meaningful
                 commit(rayIdx, tr.best); has = false; tr.tcount = 0u;
-            } else if (!tr.want_node() && tr.sp == 0 && tr.tcount == 0u) {
+            } else if (!tr.want_node() && tr.stack_empty() && tr.tcount == 0u) {
                 commit(rayIdx, tr.best); has = false;
             }
         }
