@@ -175,6 +175,36 @@ def test_degenerate_inputs_for_the_clustering_builder(ol, rb):
     r.close()
 
 
+def test_clustering_builder_on_a_nearest_neighbour_chain(ol, rb):
+    """A row of quads of steadily growing size: every cluster's cheapest partner is its smaller neighbour, so only
+    one pair per row is mutual in a round. Without the pair-by-position fallback this build needs thousands of rounds
+    (one host synchronisation each); with it the round count stays logarithmic."""
+    quad = rb.meshes.quad((-0.5, 0, -0.5), (0.5, 0, -0.5), (0.5, 0, 0.5), (-0.5, 0, 0.5))
+    s = rb.scene.Scene()
+    oid = s.defineObject(quad)
+    x, size = 0.0, 1.0
+    centres = []
+    for k in range(6000):
+        m = rb.camera.compose(rb.camera.translate((x + 0.5 * size, 0.0, 0.0)), rb.camera.scale((size, 1.0, size)))
+        s.addInstance(oid, m, rb.scene.Material())
+        centres.append((x + 0.5 * size, size))
+        x += size * 1.02
+        size *= 1.0007
+    tables = s.build()
+    r = rb.Renderer(16, 16, tables)
+    info = r.bvh_info()
+    assert info["numTriangles"] == 12000
+    assert info["buildMs"] < 150.0, info["buildMs"]
+    sc = ol.OracleScene(tables)
+    rng = np.random.RandomState(8)
+    pick = rng.randint(0, 6000, 3000)
+    org = np.array([[centres[i][0] + rng.uniform(-0.6, 0.6) * centres[i][1], 2.0, rng.uniform(-0.6, 0.6) * centres[i][1]]
+                    for i in pick], np.float32)
+    d = np.tile(np.array([0.0, -1.0, 0.0], np.float32), (3000, 1))
+    assert_hits_equal(r.trace_rays(org, d, 1e4), sc.trace_rays(org, d, 1e4, brute=True))
+    r.close()
+
+
 def test_unknown_builder_name_is_an_error(rb, builder_env):
     builder_env("sah")
     wl = rb.configs.small_mixed(16, 12)
