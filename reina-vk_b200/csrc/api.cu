@@ -97,7 +97,15 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
     for (int lane = 0; lane < 2; lane++) {
         WaveParams& L = lane == 0 ? c->wp : c->wp1;
         L.W = width; L.H = height; L.N = (uint32_t)N; L.flags = flags;
+#if RB_PAIR_STATE
+        // interleaved pairs (see context.cuh): record 2*slot is the first member, 2*slot+1 the second
+        A(L.rayO.p, 2 * N); L.rayD.p = L.rayO.p + 1;
+        A(L.thr.p, 2 * N);  L.st.p = reinterpret_cast<uint4*>(L.thr.p + 1);
+        A(L.hit.p, 2 * N);  L.rad.p = reinterpret_cast<float4*>(L.hit.p + 1);
+        A(L.sum.p, N);
+#else
         A(L.rayO.p, N); A(L.rayD.p, N); A(L.hit.p, N); A(L.thr.p, N); A(L.rad.p, N); A(L.sum.p, N); A(L.st.p, N);
+#endif
         A(L.shO.p, N); A(L.shD.p, N); A(L.shA.p, N); A(L.shB.p, N); A(L.shT.p, N);
         A(L.rayQ[0], N); A(L.rayQ[1], N);
         for (int m = 0; m < 5; m++) A(L.matQ[m], N);

@@ -51,22 +51,29 @@ template <class T> struct StateRef {
 #endif
     }
 };
-template <class T> struct StateArr {
+template <class T, int STRIDE = 1> struct StateArr {
     T* p;
-    __device__ __forceinline__ StateRef<T> operator[](uint32_t i) const { return StateRef<T>{p + i}; }
+    __device__ __forceinline__ StateRef<T> operator[](uint32_t i) const { return StateRef<T>{p + (size_t)i * STRIDE}; }
 };
+// Records that the shading kernels always touch together share one 32-byte DRAM sector per slot: (rayO, rayD),
+// (thr, st), (hit, rad). A material queue holds a scattered subset of the slots, so with one array per record every
+// 16-byte access moved a half-used sector; the shading kernels are bound by DRAM sector throughput (~2.7 TB/s).
+#ifndef RB_PAIR_STATE
+#define RB_PAIR_STATE 1
+#endif
+static constexpr int STATE_STRIDE = RB_PAIR_STATE ? 2 : 1;
 
 struct WaveParams {
     DeviceScene S;
     RB200RtPushConsts pc;
     uint32_t W, H, N, flags;
-    StateArr<float4> rayO;      // xyz origin
-    StateArr<float4> rayD;      // xyz direction (not necessarily unit)
-    StateArr<uint4> hit;        // x = bits(b1), y = bits(b2), z = primitive, w = instance
-    StateArr<float4> thr;       // xyz throughput, w = accumulatedDistance
-    StateArr<float4> rad;       // xyz radiance of the current path
+    StateArr<float4, STATE_STRIDE> rayO;      // xyz origin
+    StateArr<float4, STATE_STRIDE> rayD;      // xyz direction (not necessarily unit)
+    StateArr<uint4, STATE_STRIDE> hit;        // x = bits(b1), y = bits(b2), z = primitive, w = instance
+    StateArr<float4, STATE_STRIDE> thr;       // xyz throughput, w = accumulatedDistance
+    StateArr<float4, STATE_STRIDE> rad;       // xyz radiance of the current path
     StateArr<float4> sum;       // xyz summed sample colours of this batch, w = bits(actualSamples)
-    StateArr<uint4> st;         // x = rng state, y = flags | segments << 8, z = sample index
+    StateArr<uint4, STATE_STRIDE> st;         // x = rng state, y = flags | segments << 8, z = sample index
     StateArr<float4> shO, shD, shA, shB, shT;   // shadow-ray records (compacted): origin/tmax, dir, D/wNEE, E*wBRDF/slot, throughput
     uint32_t* rayQ[2];
     uint32_t* matQ[5]; // 0..3 materials, 4 = miss
