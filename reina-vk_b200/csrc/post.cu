@@ -14,22 +14,63 @@
 
 namespace rb200 {
 
-static constexpr int BX_TILE = 256;      // blur X: pixels of one row per block
-static constexpr int BY_W = 32;          // blur Y: tile width
-static constexpr int BY_H = 128;         // blur Y: tile height (rows per block)
-static constexpr int BY_THREADS = 256;
+#ifndef RB_BLUR_OUT
+#define RB_BLUR_OUT 4
+#endif
+static constexpr int BLUR_OUT = RB_BLUR_OUT;                   // outputs per thread along the blur axis (register blocking)
+static constexpr int BX_THREADS = 512 / BLUR_OUT;
+static constexpr int BX_TILE = BX_THREADS * BLUR_OUT; // blur X: pixels of one row per block
+static constexpr int BY_W = 16;                       // blur Y: tile width
+static constexpr int BY_H = 128;                      // blur Y: tile height (rows per block)
+static constexpr int BY_THREADS = BY_W * (BY_H / BLUR_OUT);
 
 __device__ __forceinline__ float gauss(float x, float sigma) { return rb_exp(-x * x / (2.0f * sigma * sigma)); }
 
-__global__ void __launch_bounds__(BX_TILE) k_blur_x(const float4* __restrict__ in, float4* __restrict__ out, int W, int H,
-                                                    int R, float sigma, float threshold) {
+// Each thread produces BLUR_OUT adjacent outputs along the blur axis: a staged pixel is loaded from shared memory once
+// and used by up to BLUR_OUT outputs (tap i of output o is pixel t = i + o), with the weights sliding through
+// registers. Every output still adds its taps in ascending order, one product and one add per channel, so the sums
+// are the ones the shader's loop produces; weightSum is the same sequence for every output and is formed once.
+// `tile` points at tap 0 of output 0, consecutive pixels along the axis are `stride` entries apart.
+__device__ __forceinline__ void blur_outputs(const float* __restrict__ wts, const float4* __restrict__ tile, int stride, int R,
+                                             float (&cr)[BLUR_OUT], float (&cg)[BLUR_OUT], float (&cb)[BLUR_OUT], float& ws) {
+    const int n = 2 * R + 1;
+    float w[BLUR_OUT];
+#pragma unroll
+    for (int o = 0; o < BLUR_OUT; o++) { w[o] = 0.f; cr[o] = 0.f; cg[o] = 0.f; cb[o] = 0.f; }
+    ws = 0.f;
+    for (int t = 0; t < n + BLUR_OUT - 1; t++) {
+#pragma unroll
+        for (int o = BLUR_OUT - 1; o > 0; o--) w[o] = w[o - 1];
+        w[0] = t < n ? wts[t] : 0.f;
+        if (t < n) ws += w[0];
+        const float4 p = tile[t * stride];
+        if (t >= BLUR_OUT - 1 && t < n) {          // the tap is valid for every output of this thread
+#pragma unroll
+            for (int o = 0; o < BLUR_OUT; o++) { cr[o] += p.x * w[o]; cg[o] += p.y * w[o]; cb[o] += p.z * w[o]; }
+        } else {
+#pragma unroll
+            for (int o = 0; o < BLUR_OUT; o++) {
+                const int i = t - o;
+                if (i >= 0 && i < n) { cr[o] += p.x * w[o]; cg[o] += p.y * w[o]; cb[o] += p.z * w[o]; }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float4 blur_resolve(float cr, float cg, float cb, float ws) {
+    if (ws < 0.0001f) { cr = cg = cb = 0.f; } else { cr /= ws; cg /= ws; cb /= ws; }
+    return make_float4(cr, cg, cb, 1.f);
+}
+
+__global__ void __launch_bounds__(BX_THREADS) k_blur_x(const float4* __restrict__ in, float4* __restrict__ out, int W, int H,
+                                                       int R, float sigma, float threshold) {
     extern __shared__ float4 smem[];
     float* wts = reinterpret_cast<float*>(smem);              // 2R+1 weights (padded to a multiple of 4 floats)
     float4* tile = smem + ((2 * R + 1 + 3) / 4);              // BX_TILE + 2R pixels
     const int y = blockIdx.y;
     const int x0 = blockIdx.x * BX_TILE;
-    for (int i = threadIdx.x; i <= 2 * R; i += BX_TILE) wts[i] = gauss((float)(i - R), sigma);
-    for (int i = threadIdx.x; i < BX_TILE + 2 * R; i += BX_TILE) {
+    for (int i = threadIdx.x; i <= 2 * R; i += BX_THREADS) wts[i] = gauss((float)(i - R), sigma);
+    for (int i = threadIdx.x; i < BX_TILE + 2 * R; i += BX_THREADS) {
         const int x = x0 - R + i;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         if (x >= 0 && x < W) {
@@ -40,17 +81,13 @@ __global__ void __launch_bounds__(BX_TILE) k_blur_x(const float4* __restrict__ i
         tile[i] = p;
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x;
-    if (x >= W) return;
-    float cr = 0.f, cg = 0.f, cb = 0.f, ws = 0.f;
-    for (int i = 0; i <= 2 * R; i++) {
-        const float w = wts[i];
-        const float4 p = tile[threadIdx.x + i];
-        ws += w;
-        cr += p.x * w; cg += p.y * w; cb += p.z * w;
-    }
-    if (ws < 0.0001f) { cr = cg = cb = 0.f; } else { cr /= ws; cg /= ws; cb /= ws; }
-    out[(size_t)y * W + x] = make_float4(cr, cg, cb, 1.f);
+    const int xo = x0 + (int)threadIdx.x * BLUR_OUT;
+    if (xo >= W) return;
+    float cr[BLUR_OUT], cg[BLUR_OUT], cb[BLUR_OUT], ws;
+    blur_outputs(wts, tile + threadIdx.x * BLUR_OUT, 1, R, cr, cg, cb, ws);
+#pragma unroll
+    for (int o = 0; o < BLUR_OUT; o++)
+        if (xo + o < W) out[(size_t)y * W + xo + o] = blur_resolve(cr[o], cg[o], cb[o], ws);
 }
 
 __global__ void __launch_bounds__(BY_THREADS) k_blur_y(const float4* __restrict__ in, float4* __restrict__ out, int W, int H,
@@ -59,31 +96,23 @@ __global__ void __launch_bounds__(BY_THREADS) k_blur_y(const float4* __restrict_
     float* wts = reinterpret_cast<float*>(smem);
     float4* tile = smem + ((2 * R + 1 + 3) / 4);              // (BY_H + 2R) rows x BY_W
     const int x0 = blockIdx.x * BY_W, y0 = blockIdx.y * BY_H;
-    const int tx = threadIdx.x % BY_W, ty = threadIdx.x / BY_W;     // 32 x 8
+    const int tx = threadIdx.x % BY_W, tg = threadIdx.x / BY_W;     // column, group of BLUR_OUT rows
     for (int i = threadIdx.x; i <= 2 * R; i += BY_THREADS) wts[i] = gauss((float)(i - R), sigma);
     const int rows = BY_H + 2 * R;
-    for (int r = ty; r < rows; r += BY_THREADS / BY_W) {
+    for (int r = tg; r < rows; r += BY_THREADS / BY_W) {
         const int y = y0 - R + r, x = x0 + tx;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         if (y >= 0 && y < H && x < W) p = in[(size_t)y * W + x];
         tile[r * BY_W + tx] = p;
     }
     __syncthreads();
-    const int x = x0 + tx;
-    if (x >= W) return;
-    for (int oy = ty; oy < BY_H; oy += BY_THREADS / BY_W) {
-        const int y = y0 + oy;
-        if (y >= H) break;
-        float cr = 0.f, cg = 0.f, cb = 0.f, ws = 0.f;
-        for (int i = 0; i <= 2 * R; i++) {
-            const float w = wts[i];
-            const float4 p = tile[(oy + i) * BY_W + tx];
-            ws += w;
-            cr += p.x * w; cg += p.y * w; cb += p.z * w;
-        }
-        if (ws < 0.0001f) { cr = cg = cb = 0.f; } else { cr /= ws; cg /= ws; cb /= ws; }
-        out[(size_t)y * W + x] = make_float4(cr, cg, cb, 1.f);
-    }
+    const int x = x0 + tx, yo = y0 + tg * BLUR_OUT;
+    if (x >= W || yo >= H) return;
+    float cr[BLUR_OUT], cg[BLUR_OUT], cb[BLUR_OUT], ws;
+    blur_outputs(wts, tile + (tg * BLUR_OUT) * BY_W + tx, BY_W, R, cr, cg, cb, ws);
+#pragma unroll
+    for (int o = 0; o < BLUR_OUT; o++)
+        if (yo + o < H) out[(size_t)(yo + o) * W + x] = blur_resolve(cr[o], cg[o], cb[o], ws);
 }
 
 // tonemapping.comp.glsl:34-39
@@ -152,7 +181,7 @@ int postprocess(RB200Context* ctx, const RB200BloomPushConsts* bloom, const RB20
     RB_CUDA(cudaFuncSetAttribute(k_blur_x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smX));
     RB_CUDA(cudaFuncSetAttribute(k_blur_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smY));
     dim3 gx((W + BX_TILE - 1) / BX_TILE, H), gy((W + BY_W - 1) / BY_W, (H + BY_H - 1) / BY_H);
-    k_blur_x<<<gx, BX_TILE, smX, s>>>(rt, ctx->ping, W, H, RX, bloom->radius, bloom->threshold);
+    k_blur_x<<<gx, BX_THREADS, smX, s>>>(rt, ctx->ping, W, H, RX, bloom->radius, bloom->threshold);
     k_blur_y<<<gy, BY_THREADS, smY, s>>>(ctx->ping, ctx->pong, W, H, RY, bloom->radius);
     const uint32_t n = (uint32_t)W * (uint32_t)H;
     k_combine_tonemap<<<(n / 4 + 256) / 256, 256, 0, s>>>(rt, ctx->pong, reinterpret_cast<uint32_t*>(ctx->ldr), n,
