@@ -22,6 +22,10 @@ static vec4 sample_texture(const Scene& s, int id, vec2 uv) {
     float y = uv.y * (float)tx.h - 0.5f;
     float fx = floorf(x), fy = floorf(y);
     float ax = x - fx, ay = y - fy;
+    // REPEAT addressing of a coordinate no int32 can hold (parallax steps at grazing angles, NaN) is not defined by
+    // the float->int conversion: such a coordinate addresses texel 0 with weight 0 (same rule in the kernels)
+    if (!(fabsf(fx) < 1073741824.0f)) { fx = 0.0f; ax = 0.0f; }
+    if (!(fabsf(fy) < 1073741824.0f)) { fy = 0.0f; ay = 0.0f; }
     int x0 = wrapi((int)fx, (int)tx.w), y0 = wrapi((int)fy, (int)tx.h);
     int x1 = wrapi(x0 + 1, (int)tx.w), y1 = wrapi(y0 + 1, (int)tx.h);
     const uint8_t* p00 = &tx.rgba[4 * ((size_t)y0 * tx.w + x0)];
@@ -163,6 +167,46 @@ static void do_skip(Payload& pld, const HitInfo& h, vec3 rayDir) {
     pld.skip = true;
 }
 
+// texutils.h.glsl:4-41 — steep parallax search (64..512 layers, heightScale 0.2) + linear refinement between the
+// last two layers. rayIn is the normalised world ray direction, T the hit's tangent frame. mix(a, b, t) is
+// a*(1-t) + b*t, "V.xy / V.z * heightScale" associates left to right.
+static vec2 bump_mapping(const Scene& s, vec2 uv, vec3 rayIn, const mat3& T, int heightMap) {
+    const float heightScale = 0.2f, minLayers = 64.0f, maxLayers = 512.0f;
+    const vec3 V = rb_normalize(rb_m3_tmul(T, -rayIn));
+    if (V.z <= 0.0f) return uv;
+    const float a = rb_clamp(V.z, 0.0f, 1.0f);
+    const float numLayers = maxLayers * (1.0f - a) + minLayers * a;
+    const float layerDepth = 1.0f / numLayers;
+    const float Px = (V.x / V.z) * heightScale, Py = (V.y / V.z) * heightScale;
+    const float dU = Px / numLayers, dV = Py / numLayers;
+    float cu = uv.x, cv = uv.y;
+    float depthSum = 0.0f;
+    float h = sample_texture(s, heightMap, rb_mk2(cu, cv)).x * heightScale;
+    while (depthSum < h) {
+        cu = cu - dU; cv = cv - dV;
+        depthSum = depthSum + layerDepth;
+        h = sample_texture(s, heightMap, rb_mk2(cu, cv)).x * heightScale;
+    }
+    const float pu = cu + dU, pv = cv + dV;
+    const float hPrev = sample_texture(s, heightMap, rb_mk2(pu, pv)).x * heightScale;
+    const float sumPrev = depthSum - layerDepth;
+    const float after = h - depthSum;
+    const float before = hPrev - sumPrev;
+    const float weight = after / (after - before);
+    return rb_mk2(pu * (1.0f - weight) + cu * weight, pv * (1.0f - weight) + cv * weight);
+}
+
+// known-answer hook: the parallax search on a caller-provided height map
+void kat_bump(const uint8_t* rgba, uint32_t w, uint32_t h, const float uv[2], const float rayIn[3], const float tbn[9],
+              float out[2]) {
+    Scene s;
+    Scene::Tex t; t.w = w; t.h = h; t.rgba.assign(rgba, rgba + 4 * (size_t)w * h);
+    s.textures.push_back(std::move(t));
+    mat3 T; T.c0 = rb_mk3(tbn[0], tbn[1], tbn[2]); T.c1 = rb_mk3(tbn[3], tbn[4], tbn[5]); T.c2 = rb_mk3(tbn[6], tbn[7], tbn[8]);
+    vec2 r = bump_mapping(s, rb_mk2(uv[0], uv[1]), rb_mk3(rayIn[0], rayIn[1], rayIn[2]), T, 0);
+    out[0] = r.x; out[1] = r.y;
+}
+
 // closestHitCommon.h.glsl:195-205
 static vec3 random_unit_vec(uint32_t& rng) {
     for (;;) {
@@ -193,6 +237,7 @@ static bool surface_prologue(const Scene& s, Payload& pld, const HitInfo& h, con
                              vec3 rayDir, bool uvRangeSkip, vec3* worldNormal, vec3* albedo) {
     if (props.cullBackface != 0u && !h.frontFace) { do_skip(pld, h, rayDir); return false; }
     vec2 uv = rb_mk2(rb_fract_mod1(h.uv.x), rb_fract_mod1(h.uv.y));
+    if (props.bumpMapTexID >= 0) uv = bump_mapping(s, uv, rb_normalize(rayDir), h.tbn, props.bumpMapTexID);
     if (uvRangeSkip && (uv.x < 0.0f || uv.x > 1.0f || uv.y < 0.0f || uv.y > 1.0f)) { do_skip(pld, h, rayDir); return false; }
     vec3 wn = h.worldNormal;
     if (props.normalMapTexID >= 0) {
@@ -267,6 +312,7 @@ static void shade_dielectric(const Scene& s, Payload& pld, const HitInfo& h, con
     const bool previouslyInside = pld.insideDielectric;
 
     vec2 uv = rb_mk2(rb_fract_mod1(h.uv.x), rb_fract_mod1(h.uv.y));
+    if (props.bumpMapTexID >= 0) uv = bump_mapping(s, uv, rb_normalize(rayDir), h.tbn, props.bumpMapTexID);   // :59-61
     vec3 albedo = rb_mk3(props.albedo[0], props.albedo[1], props.albedo[2]);
     if (props.textureID >= 0) {
         vec4 t = sample_texture(s, props.textureID, uv);

@@ -117,6 +117,52 @@ def _bumpy_normal_map(size=256):
     return img
 
 
+def brick_height_map(size=128, rows=4, cols=2, mortar=0.08):
+    """Height map in the spirit of the reference's textures/bricks2/parallax.png (which cannot travel to the GPU box):
+    0 (black) = surface level, 255 = 0.2 uv-units deep. Bricks are shallow, mortar grooves deep, with a smooth ramp
+    between them and a faint ripple so that neighbouring texels differ."""
+    y, x = np.mgrid[0:size, 0:size].astype(np.float32) / size
+    row = np.floor(y * rows)
+    xs = (x + 0.5 * (row % 2) / cols) % 1.0
+    fx = np.abs(((xs * cols) % 1.0) - 0.5) * 2          # 0 at the brick centre, 1 at the joint
+    fy = np.abs(((y * rows) % 1.0) - 0.5) * 2
+    edge = np.maximum(fx - (1 - mortar * cols), (fy - (1 - mortar * rows))) / (mortar * rows)
+    groove = np.clip(edge * 2.0, 0.0, 1.0)
+    ripple = 0.06 * (np.sin(x * 2 * np.pi * 9) * np.cos(y * 2 * np.pi * 7) + 1)
+    hgt = np.clip(0.1 + ripple + 0.8 * groove, 0, 1)
+    img = np.zeros((size, size, 4), np.uint8)
+    img[..., 0] = img[..., 1] = img[..., 2] = np.round(hgt * 255)
+    img[..., 3] = 255
+    return img
+
+
+def parallax(width=160, height=120, nee=True, samples_per_pixel=2, max_bounces=6):
+    """every material with a parallax height map (texutils.h.glsl:4-41) — a Lambertian floor whose
+    shifted UVs leave [0, 1] near the borders (range skip), a metal sphere (no range check: REPEAT addressing), a
+    dielectric sphere and a Disney sphere that combines the height map with a normal map and an albedo texture."""
+    s = Scene()
+    hmap = s.defineTexture(brick_height_map(128))
+    tex = s.defineTexture(meshes.cornell_texture(64, 96))
+    nmap = s.defineTexture(_bumpy_normal_map(64))
+    s.addObject(meshes.cornell_box(), IDENT, Material(**CORNELL_WALL))
+    s.addObject(meshes.cornell_light(), IDENT, Material(**LIGHT))
+    s.addObject(meshes.quad((-0.9, 0.02, 0.9), (0.9, 0.02, 0.9), (0.9, 0.02, -0.9), (-0.9, 0.02, -0.9)), IDENT,
+                Material(materialIdx=0, albedo=(0.8, 0.5, 0.4), textureID=tex, bumpMapID=hmap))
+    sph = s.defineObject(meshes.uv_sphere(24, 12, radius=0.3))
+    s.addInstance(sph, translate((-0.55, 0.32, -0.3)), Material(materialIdx=1, albedo=(0.9, 0.8, 0.5), roughness=0.1,
+                                                                interpNormals=True, textureID=tex, bumpMapID=hmap))
+    glass = dict(GLASS); glass.update(bumpMapID=hmap, textureID=tex)
+    s.addInstance(sph, translate((0.0, 0.32, 0.35)), Material(**glass))
+    s.addInstance(sph, compose(translate((0.55, 0.37, -0.3)), scale((1.0, 1.15, 0.9))),
+                  Material(materialIdx=3, albedo=(0.6, 0.3, 0.8), roughness=0.3, ior=1.5, interpNormals=True,
+                           metallic=0.4, clearcoat=0.5, sheenTint=(1, 1, 1), specularTint=(1, 1, 1),
+                           textureID=tex, normalMapID=nmap, bumpMapID=hmap))
+    tables = s.build(require_emitter=nee)
+    pc = dict(pos=(0.0, 1.3, 3.9), look=(0.0, 0.6, 0.0), fovy_deg=40.0, samples_per_pixel=samples_per_pixel,
+              max_bounces=max_bounces)
+    return Workload("parallax", tables, width, height, pc, nee, 2)
+
+
 def plant(width=1920, height=1080, n_leaves=16000, nee=True, samples_per_pixel=1, max_bounces=16, seed=3):
     """C4: plant-like scene — a normal-mapped Disney pot, a soil disc and ~n_leaves alpha-tested two-triangle leaf cards
     (the reference's plant_* OBJs cannot travel to the GPU box; same feature set: albedo + normal textures,

@@ -49,7 +49,6 @@ static int validate_desc(const RB200SceneDesc* d) {
         if (p.textureID >= (int)d->numTextures || p.normalMapTexID >= (int)d->numTextures || p.bumpMapTexID >= (int)d->numTextures) {
             set_error("instance %u: texture id out of range", i); return RB200_ERR_INVALID_ARGUMENT;
         }
-        if (p.bumpMapTexID >= 0) { set_error("instance %u: parallax bump mapping (bumpMapTexID) is not implemented", i); return RB200_ERR_INVALID_ARGUMENT; }
         if ((uint64_t)p.tbnsIndicesOffset + 3ull * in.triangleCount > d->numTbnIndices) { set_error("instance %u: TBN index range out of bounds", i); return RB200_ERR_INVALID_ARGUMENT; }
         if (p.texIndicesOffset != 0xFFFFFFFFu && (uint64_t)p.texIndicesOffset + 3ull * in.triangleCount > d->numTexIndices) {
             set_error("instance %u: texcoord index range out of bounds", i); return RB200_ERR_INVALID_ARGUMENT;

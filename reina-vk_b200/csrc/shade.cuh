@@ -42,8 +42,12 @@ __device__ __forceinline__ float4 sample_texture(const DeviceScene& S, int id, r
     const uint2 sz = S.texSizes[id];
     const float x = uv.x * (float)sz.x - 0.5f;
     const float y = uv.y * (float)sz.y - 0.5f;
-    const float fx = floorf(x), fy = floorf(y);
-    const float ax = x - fx, ay = y - fy;
+    float fx = floorf(x), fy = floorf(y);
+    float ax = x - fx, ay = y - fy;
+    // a coordinate no int32 can hold (parallax steps at grazing angles, NaN) addresses texel 0 with weight 0: cvt
+    // saturates on the GPU and does not on the host, so the rule is spelled out (same rule in the oracle)
+    if (!(fabsf(fx) < 1073741824.0f)) { fx = 0.0f; ax = 0.0f; }
+    if (!(fabsf(fy) < 1073741824.0f)) { fy = 0.0f; ay = 0.0f; }
     const int x0 = wrapi((int)fx, (int)sz.x), y0 = wrapi((int)fy, (int)sz.y);
     const int x1 = wrapi(x0 + 1, (int)sz.x), y1 = wrapi(y0 + 1, (int)sz.y);
     const uchar4 p00 = tex2D<uchar4>(tex, x0 + 0.5f, y0 + 0.5f);
@@ -62,6 +66,53 @@ __device__ __forceinline__ float4 sample_texture(const DeviceScene& S, int id, r
     RB_BILERP(x) RB_BILERP(y) RB_BILERP(z) RB_BILERP(w)
 #undef RB_BILERP
     return r;
+}
+
+// red channel only (height maps), same arithmetic as sample_texture's .x
+__device__ __forceinline__ float sample_texture_r(const cudaTextureObject_t tex, const uint2 sz, float u, float v) {
+    const float x = u * (float)sz.x - 0.5f;
+    const float y = v * (float)sz.y - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float ax = x - fx, ay = y - fy;
+    if (!(fabsf(fx) < 1073741824.0f)) { fx = 0.0f; ax = 0.0f; }
+    if (!(fabsf(fy) < 1073741824.0f)) { fy = 0.0f; ay = 0.0f; }
+    const int x0 = wrapi((int)fx, (int)sz.x), y0 = wrapi((int)fy, (int)sz.y);
+    const int x1 = wrapi(x0 + 1, (int)sz.x), y1 = wrapi(y0 + 1, (int)sz.y);
+    const float c00 = (float)tex2D<uchar4>(tex, x0 + 0.5f, y0 + 0.5f).x / 255.0f;
+    const float c10 = (float)tex2D<uchar4>(tex, x1 + 0.5f, y0 + 0.5f).x / 255.0f;
+    const float c01 = (float)tex2D<uchar4>(tex, x0 + 0.5f, y1 + 0.5f).x / 255.0f;
+    const float c11 = (float)tex2D<uchar4>(tex, x1 + 0.5f, y1 + 0.5f).x / 255.0f;
+    const float top = c00 * (1.0f - ax) + c10 * ax;
+    const float bot = c01 * (1.0f - ax) + c11 * ax;
+    return top * (1.0f - ay) + bot * ay;
+}
+
+// texutils.h.glsl:4-41 — parallax mapping: march the view ray through 64..512 depth layers of the height map (more
+// layers at grazing angles), stop at the first layer below the surface, interpolate between the last two layers.
+// Every lane walks its own number of layers (at most 0.2 * 512 + 1 steps, the height is at most heightScale).
+__device__ __noinline__ rb_v2 bump_mapping_search(const cudaTextureObject_t tex, const uint2 sz, rb_v2 uv, rb_v3 V) {
+    const float heightScale = 0.2f;
+    if (V.z <= 0.0f) return uv;
+    const float numLayers = rb_mix(512.0f, 64.0f, rb_clamp(V.z, 0.0f, 1.0f));
+    const float layerDepth = 1.0f / numLayers;
+    const rb_v2 delta = rb_mk2(((V.x / V.z) * heightScale) / numLayers, ((V.y / V.z) * heightScale) / numLayers);
+    rb_v2 curr = uv;
+    float depthSum = 0.0f;
+    float h = sample_texture_r(tex, sz, curr.x, curr.y) * heightScale;
+    while (depthSum < h) {
+        curr = curr - delta;
+        depthSum += layerDepth;
+        h = sample_texture_r(tex, sz, curr.x, curr.y) * heightScale;
+    }
+    const rb_v2 prev = curr + delta;
+    const float hPrev = sample_texture_r(tex, sz, prev.x, prev.y) * heightScale;
+    const float after = h - depthSum;
+    const float before = hPrev - (depthSum - layerDepth);
+    const float weight = after / (after - before);
+    return rb_mk2(rb_mix(prev.x, curr.x, weight), rb_mix(prev.y, curr.y, weight));
+}
+__device__ __forceinline__ rb_v2 bump_mapping(const DeviceScene& S, rb_v2 uv, rb_v3 rayIn, const rb_m3& T, int heightMap) {
+    return bump_mapping_search(S.textures[heightMap], S.texSizes[heightMap], uv, rb_normalize(rb_m3_tmul(T, -rayIn)));
 }
 
 // closestHitCommon.h.glsl:52-148

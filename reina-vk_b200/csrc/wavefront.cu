@@ -177,7 +177,9 @@ template <bool UV_RANGE_SKIP>
 __device__ __forceinline__ bool surface_prologue(const WaveParams& P, const RB200InstanceProperties* props, const Surf& s,
                                                  const rb_m3* tbn, rb_v3 rayDir, uint32_t& rng, ShadeOut& o, rb_v3& wn, rb_v3& col) {
     if (__ldg(&props->cullBackface) != 0u && !s.frontFace) { do_skip(o, s, rayDir); return false; }
-    const rb_v2 uv = rb_mk2(rb_fract_mod1(s.uv.x), rb_fract_mod1(s.uv.y));
+    rb_v2 uv = rb_mk2(rb_fract_mod1(s.uv.x), rb_fract_mod1(s.uv.y));
+    const int bm = __ldg(&props->bumpMapTexID);
+    if (bm >= 0) uv = bump_mapping(P.S, uv, rb_normalize(rayDir), *tbn, bm);
     if (UV_RANGE_SKIP && (uv.x < 0.0f || uv.x > 1.0f || uv.y < 0.0f || uv.y > 1.0f)) { do_skip(o, s, rayDir); return false; }
     wn = s.worldNormal;
     const int nm = __ldg(&props->normalMapTexID);
@@ -263,8 +265,9 @@ __device__ __forceinline__ uint32_t shade_slot(const WaveParams& P, const uint32
 
     Surf s;
     const bool hasNormalMap = __ldg(&props->normalMapTexID) >= 0;
+    const bool needTbn = hasNormalMap || __ldg(&props->bumpMapTexID) >= 0;     // the parallax search runs in tangent space
     if (MAT == 3) hit_info<true>(P.S, inst, props, h.z, a1, a2, rayDir, s);
-    else if (hasNormalMap) hit_info<true>(P.S, inst, props, h.z, a1, a2, rayDir, s);
+    else if (needTbn) hit_info<true>(P.S, inst, props, h.z, a1, a2, rayDir, s);
     else hit_info<false>(P.S, inst, props, h.z, a1, a2, rayDir, s);
 
     ShadeOut o;
@@ -298,7 +301,9 @@ __device__ __forceinline__ uint32_t shade_slot(const WaveParams& P, const uint32
         const float sinTheta = sqrtf(1.0f - cosTheta * cosTheta);
         const bool cannotRefract = ri * sinTheta > 1.0f;
         const float reflectivity = schlick(cosTheta, ri);
-        const rb_v2 uv = rb_mk2(rb_fract_mod1(s.uv.x), rb_fract_mod1(s.uv.y));
+        rb_v2 uv = rb_mk2(rb_fract_mod1(s.uv.x), rb_fract_mod1(s.uv.y));
+        const int bm = __ldg(&props->bumpMapTexID);
+        if (bm >= 0) uv = bump_mapping(P.S, uv, unitDir, s.tbn, bm);     // dielectric.rchit.glsl:59-61
         rb_v3 albedo = ld3(props->albedo);
         const int tid = __ldg(&props->textureID);
         if (tid >= 0) { const float4 t = sample_texture(P.S, tid, uv); albedo = albedo * rb_mk3(t.x, t.y, t.z); }

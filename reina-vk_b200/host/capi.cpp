@@ -77,7 +77,7 @@ int rbhost_tables_obj(const char* path, uint32_t materialIdx, int addLight, Scen
         m.materialIdx = materialIdx;
         m.albedo = {0.8f, 0.8f, 0.8f};
         m.interpNormals = true;
-        Scene s = make_obj_scene({{path, m, ""}}, addLight != 0);
+        Scene s = make_obj_scene({{path, m, "", "", ""}}, addLight != 0);
         *out = new SceneTables(s.build(false));
     });
 }

@@ -44,6 +44,8 @@ struct ObjRequest {
     std::string path;
     Material material;
     std::string texturePath;     // PNG albedo texture (Scene::defineTexture of a file: flipped vertically), may be empty
+    std::string normalMapPath;   // PNG tangent-space normal map -> Material::normalMapID, may be empty
+    std::string bumpMapPath;     // PNG height map for parallax mapping -> Material::bumpMapID, may be empty
 };
 // showroom-less generic scene: every OBJ at identity + the Cornell light panel (so NEE has an emitter)
 Scene make_obj_scene(const std::vector<ObjRequest>& objs, bool addLight);

@@ -26,6 +26,8 @@ static void usage() {
         "  --albedo R,G,B       albedo of the following --obj (default 0.8,0.8,0.8)\n"
         "  --roughness X  --ior X  --metallic X     parameters of the following --obj\n"
         "  --texture FILE       PNG albedo texture of the following --obj (flipped vertically like the reference's file textures)\n"
+        "  --normal-map FILE    PNG tangent-space normal map of the following --obj\n"
+        "  --bump-map FILE      PNG height map of the following --obj (parallax mapping; black = surface, white = deepest)\n"
         "  --width N --height N image size (overrides [render])\n"
         "  --spp N              stop after N samples per pixel in total\n"
         "  --seconds S          stop after S seconds\n"
@@ -47,7 +49,7 @@ static bool parse_vec3(const char* s, std::array<float, 3>& out) {
 int main(int argc, char** argv) {
     std::string configPath = "config/config.toml", sceneName, finalOut, outDir = ".", dumpPc;
     std::vector<ObjRequest> objs;
-    std::string nextTexture;
+    std::string nextTexture, nextNormalMap, nextBumpMap;
     Material nextMat;
     nextMat.albedo = {0.8f, 0.8f, 0.8f};
     nextMat.interpNormals = true;
@@ -66,8 +68,13 @@ int main(int argc, char** argv) {
             if (a == "--help" || a == "-h") { usage(); return 0; }
             else if (a == "--config") configPath = value();
             else if (a == "--scene") sceneName = value();
-            else if (a == "--obj") { objs.push_back({value(), nextMat, nextTexture}); nextTexture.clear(); }
+            else if (a == "--obj") {
+                objs.push_back({value(), nextMat, nextTexture, nextNormalMap, nextBumpMap});
+                nextTexture.clear(); nextNormalMap.clear(); nextBumpMap.clear();
+            }
             else if (a == "--texture") nextTexture = value();
+            else if (a == "--normal-map") nextNormalMap = value();
+            else if (a == "--bump-map") nextBumpMap = value();
             else if (a == "--material") {
                 const std::string m = value();
                 if (m == "lambertian") nextMat.materialIdx = 0;

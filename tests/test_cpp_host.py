@@ -428,28 +428,36 @@ def test_cli_renders_cornell_like_the_python_host(host, rb, tmp_path):
 
 @pytest.mark.gpu
 def test_cli_textured_obj_like_the_python_host(host, rb, tmp_path):
-    """--obj + --texture: the C++ importer and PNG decoder feed the same tables as load_obj + a PIL-decoded, vertically
-    flipped texture on the Python side; the rendered frame must be identical."""
+    """--obj + --texture / --normal-map / --bump-map: the C++ importer and PNG decoder feed the same tables as load_obj +
+    PIL-decoded, vertically flipped textures on the Python side (albedo, tangent-space normals, parallax height map);
+    the rendered frame must be identical."""
     from PIL import Image
     (tmp_path / "asset.obj").write_text(OBJ_FULL)
     rng = np.random.default_rng(21)
     tex = rng.integers(0, 256, (32, 48, 4), dtype=np.uint8)
     tex[..., 3] = 255
     Image.fromarray(tex, "RGBA").save(tmp_path / "tex.png")
+    nmap = rb.configs._bumpy_normal_map(32)
+    hmap = rb.configs.brick_height_map(32)
+    Image.fromarray(nmap, "RGBA").save(tmp_path / "nmap.png")
+    Image.fromarray(hmap[..., 0], "L").save(tmp_path / "hmap.png")          # greyscale PNG: expanded to RGBA by the ingest
     cfg = tmp_path / "config.toml"
     cfg.write_text(REFERENCE_SCHEMA.replace("save_on_samples = [64, 256, 1024]", "save_on_samples = []")
                    .replace("save_on_times = [60.0]", "save_on_times = []")
                    + "\n[render]\nwidth = 80\nheight = 60\ncamera_pos = [0.4, 0.9, 2.6]\ncamera_look_at = [0.0, 0.1, 0.0]\n")
     out, pcfile = tmp_path / "final.png", tmp_path / "pc.bin"
     run = subprocess.run([os.path.join(HOST, "reina_b200"), "--config", str(cfg), "--texture", str(tmp_path / "tex.png"),
+                          "--normal-map", str(tmp_path / "nmap.png"), "--bump-map", str(tmp_path / "hmap.png"),
                           "--obj", str(tmp_path / "asset.obj"), "--spp", "16", "--out", str(out), "--dump-pc", str(pcfile),
                           "--quiet"], capture_output=True, text=True)
     assert run.returncode == 0, run.stderr + run.stdout
 
     s = rb.scene.Scene()
     tid = s.defineTexture(np.ascontiguousarray(tex[::-1]))
+    nid = s.defineTexture(np.ascontiguousarray(nmap[::-1]))
+    hid = s.defineTexture(np.ascontiguousarray(hmap[::-1]))
     s.addObject(rb.meshes.load_obj(str(tmp_path / "asset.obj")), np.eye(4, dtype=np.float32),
-                rb.scene.Material(albedo=(0.8, 0.8, 0.8), interpNormals=True, textureID=tid))
+                rb.scene.Material(albedo=(0.8, 0.8, 0.8), interpNormals=True, textureID=tid, normalMapID=nid, bumpMapID=hid))
     s.addObject(rb.meshes.cornell_light(), np.eye(4, dtype=np.float32), rb.scene.Material(**rb.configs.LIGHT))
     tables = s.build(require_emitter=True)
     pc = rb.abi.RtPushConsts.from_buffer_copy(pcfile.read_bytes())

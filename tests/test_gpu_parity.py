@@ -50,7 +50,40 @@ def test_small_mixed_bit_exact(ol, rb, nee):
     r.close()
 
 
-@pytest.mark.parametrize("name", ["small_mixed_nee", "small_mixed_shipped", "cornell_nee"])
+@pytest.mark.parametrize("nee", [True, False])
+def test_parallax_bump_mapping_bit_exact(ol, rb, nee):
+    """SURVEY 8f rank 4, texutils.h.glsl:4-41: the per-lane parallax search (64..512 layers) on all four materials —
+    Lambertian floor with UV range skips, metal with REPEAT addressing, dielectric, Disney with height + normal +
+    albedo maps — bit-identical to the oracle, 3 samples per pixel, 2 batches."""
+    wl = rb.configs.parallax(200, 150, nee=nee, samples_per_pixel=3, max_bounces=7)
+    flags = rb.RB200_FLAG_NEE if nee else 0
+    r, sc, g, o = render_both(ol, rb, wl, flags, 2)
+    assert (bits(g) == bits(o)).all()
+    r.close()
+
+
+def test_parallax_grazing_view_bit_exact(ol, rb):
+    """Camera almost in the plane of a parallax-mapped metal floor: V.z -> 0 makes the UV step huge (REPEAT addressing
+    far outside [0, 1], coordinates beyond int32 address texel 0 by the documented rule) and the search walks up to
+    0.2 * 512 layers per hit."""
+    s = rb.Scene()
+    hmap = s.defineTexture(rb.configs.brick_height_map(64))
+    tex = s.defineTexture(rb.meshes.cornell_texture(64, 96))
+    s.addObject(rb.meshes.cornell_light(), np.eye(4, dtype=np.float32), rb.Material(**rb.configs.LIGHT))
+    s.addObject(rb.meshes.quad((-40, 0, 40), (40, 0, 40), (40, 0, -40), (-40, 0, -40), uv=((0, 0), (60, 0), (60, 60), (0, 60))),
+                np.eye(4, dtype=np.float32), rb.Material(materialIdx=1, albedo=(0.9, 0.9, 0.9), roughness=0.2, textureID=tex, bumpMapID=hmap))
+    t = s.build(require_emitter=True)
+    pc = rb.camera.push_constants(160, 90, (0.0, 0.004, 3.0), (0.0, 0.0, -30.0), 50.0, samples_per_pixel=2, max_bounces=4)
+    r = rb.Renderer(160, 90, t, flags=rb.RB200_FLAG_NEE)
+    sc = ol.OracleScene(t)
+    r.render_batch(pc)
+    o, cnt = sc.render_batch(160, 90, rb.RB200_FLAG_NEE, pc)
+    last, _ = r.stats()
+    assert (bits(r.read_hdr()) == bits(o)).all() and last["extendRays"] == cnt["extendRays"]
+    r.close()
+
+
+@pytest.mark.parametrize("name", ["small_mixed_nee", "small_mixed_shipped", "cornell_nee", "parallax_nee"])
 def test_against_golden_fixtures(rb, name):
     import golden.make_golden as mg
     g = np.load(os.path.join(GOLD, name + ".npz"))
@@ -279,11 +312,11 @@ def test_errors_are_reported_not_thrown(rb):
     with pytest.raises(rb.RB200Error, match="samplesPerPixel"):
         r.render_batch(bad)
     r.close()
-    # parallax bump mapping is out of scope: refused loudly, not ignored
+    # a texture id beyond the texture table is refused (albedo, normal map and height map alike)
     s2 = rb.Scene()
-    tex = s2.defineTexture(np.full((4, 4, 4), 255, np.uint8))
-    s2.addObject(rb.meshes.cornell_light(), np.eye(4, dtype=np.float32), rb.Material(bumpMapID=tex, **{k: v for k, v in rb.configs.LIGHT.items()}))
-    with pytest.raises(rb.RB200Error, match="bump"):
+    s2.defineTexture(np.full((4, 4, 4), 255, np.uint8))
+    s2.addObject(rb.meshes.cornell_light(), np.eye(4, dtype=np.float32), rb.Material(bumpMapID=3, **{k: v for k, v in rb.configs.LIGHT.items()}))
+    with pytest.raises(rb.RB200Error, match="texture id out of range"):
         rb.Renderer(16, 16, s2.build())
     ctx = C.c_void_p()
     assert lib.rb200_context_create(0, 10, 0, 0, C.byref(ctx)) != 0 and b"invalid" in lib.rb200_last_error()

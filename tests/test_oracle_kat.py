@@ -135,3 +135,89 @@ def test_bloom_impulse_response(ol, rb):
     hdr2 = hdr.copy(); hdr2[80, 100, :3] = 0.5
     _, comb2 = ol.postprocess(hdr2, bloom=bloom, want_combined=True)
     assert comb2[80, 110, 0] == 0.0
+
+
+# ---- parallax bump mapping (texutils.h.glsl:4-41), numpy float32 restatement ------------------------------------
+F = np.float32
+
+
+def np_texture_r(img, u, v):
+    """Bilinear, REPEAT, UNORM8, LOD 0: red channel."""
+    h, w = img.shape[:2]
+    x = F(F(u) * F(w)) - F(0.5); y = F(F(v) * F(h)) - F(0.5)
+    fx, fy = np.floor(x), np.floor(y)
+    ax, ay = F(x - fx), F(y - fy)
+    x0, y0 = int(fx) % w, int(fy) % h
+    x1, y1 = (x0 + 1) % w, (y0 + 1) % h
+    c = lambda yy, xx: F(F(img[yy, xx, 0]) / F(255.0))
+    top = F(F(c(y0, x0) * F(F(1) - ax)) + F(c(y0, x1) * ax))
+    bot = F(F(c(y1, x0) * F(F(1) - ax)) + F(c(y1, x1) * ax))
+    return F(F(top * F(F(1) - ay)) + F(bot * ay))
+
+
+def np_bump(img, uv, ray_in, T):
+    hs = F(0.2)
+    m = -np.asarray(ray_in, np.float32)
+    V = np.array([F(F(F(T[c][0] * m[0]) + F(T[c][1] * m[1])) + F(T[c][2] * m[2])) for c in range(3)], np.float32)
+    inv = F(F(1) / np.sqrt(F(F(F(V[0] * V[0]) + F(V[1] * V[1])) + F(V[2] * V[2]))))
+    V = (V * inv).astype(np.float32)
+    if V[2] <= 0:
+        return F(uv[0]), F(uv[1]), 0
+    a = min(max(V[2], F(0)), F(1))
+    layers = F(F(F(512) * F(F(1) - a)) + F(F(64) * a))
+    depth = F(F(1) / layers)
+    du = F(F(F(V[0] / V[2]) * hs) / layers); dv = F(F(F(V[1] / V[2]) * hs) / layers)
+    cu, cv, s, steps = F(uv[0]), F(uv[1]), F(0), 0
+    h = F(np_texture_r(img, cu, cv) * hs)
+    while s < h:
+        cu = F(cu - du); cv = F(cv - dv); s = F(s + depth); steps += 1
+        h = F(np_texture_r(img, cu, cv) * hs)
+    pu, pv = F(cu + du), F(cv + dv)
+    hp = F(np_texture_r(img, pu, pv) * hs)
+    after = F(h - s); before = F(hp - F(s - depth))
+    wgt = F(after / F(after - before))
+    mix = lambda p, c: F(F(p * F(F(1) - wgt)) + F(c * wgt))
+    return mix(pu, cu), mix(pv, cv), steps
+
+
+def test_parallax_bump_mapping_matches_numpy(ol, rb):
+    img = rb.configs.brick_height_map(64)
+    rng = np.random.RandomState(11)
+    total_steps = 0
+    for k in range(300):
+        # an orthonormal tangent frame, columns T B N, and a ray arriving from the N side (or not: V.z <= 0 returns uv)
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        T = [q[:, 0].astype(np.float32), q[:, 1].astype(np.float32), q[:, 2].astype(np.float32)]
+        graze = rng.uniform(0.02, 1.0)
+        d = -(graze * q[:, 2] + rng.normal(size=3) * 0.7)
+        if k % 10 == 0:
+            d = -d
+        d = (d / np.linalg.norm(d)).astype(np.float32)
+        uv = rng.uniform(0, 1, 2).astype(np.float32)
+        tbn = np.concatenate(T).astype(np.float32)
+        out = np.zeros(2, np.float32)
+        ol.lib().oracle_kat_bump(img.ctypes.data_as(C.c_void_p), 64, 64, uv.ctypes.data_as(C.c_void_p),
+                                 d.ctypes.data_as(C.c_void_p), tbn.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        eu, ev, steps = np_bump(img, uv, d, T)
+        total_steps += steps
+        assert out[0].view(np.uint32) == np.float32(eu).view(np.uint32) and out[1].view(np.uint32) == np.float32(ev).view(np.uint32), (k, out, eu, ev)
+    assert total_steps > 1000        # the search really walked layers
+
+
+def test_parallax_flat_height_map_is_identity_at_zero_height(ol):
+    # h = 0 everywhere: the loop never runs, weight = -0/(0 - layerDepth) = -0... and mix returns prevUV = uv + deltaUV
+    img = np.zeros((8, 8, 4), np.uint8)
+    tbn = np.eye(3, dtype=np.float32).reshape(-1)
+    uv = np.array([0.25, 0.5], np.float32)
+    d = np.array([0.0, 0.0, -1.0], np.float32)             # head-on: V = (0, 0, 1), deltaUV = 0
+    out = np.zeros(2, np.float32)
+    ol.lib().oracle_kat_bump(img.ctypes.data_as(C.c_void_p), 8, 8, uv.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
+                             tbn.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert (out == uv).all()
+    # white height map, 45 degrees in the tangent x-z plane: P = V.xy / V.z * 0.2 spans the full depth range [0, 1] and
+    # the height is scaled by 0.2 as well, so the ray meets the surface after 0.2 of P: uv.x moves by -0.2 * 0.2
+    img[...] = 255
+    d = np.array([-1.0, 0.0, -1.0], np.float32) / np.float32(np.sqrt(2))
+    ol.lib().oracle_kat_bump(img.ctypes.data_as(C.c_void_p), 8, 8, uv.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
+                             tbn.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert abs(out[0] - (0.25 - 0.2 * 0.2)) < 2e-3 and out[1] == np.float32(0.5)

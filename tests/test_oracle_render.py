@@ -107,7 +107,25 @@ def test_light_sampling_hits_the_light(ol, rb):
     assert (hit["instance"] == 1).all()
 
 
-@pytest.mark.parametrize("name", ["small_mixed_nee", "small_mixed_shipped", "cornell_nee"])
+def test_parallax_height_map_changes_only_bumped_surfaces(ol, rb):
+    """texutils.h.glsl:4-41: with bumpMapTexID the UV used for the albedo / normal fetch is shifted along the view
+    ray; a height map of 0 (surface level everywhere) shifts by exactly one layer step, a real one moves the texture
+    and pushes UVs near the border out of [0, 1] (lambertian / disney then skip the hit)."""
+    wl = rb.configs.parallax(64, 48, samples_per_pixel=2, max_bounces=4)
+    sc = ol.OracleScene(wl.tables)
+    pc = wl.push_constants(0)
+    a, ca = sc.render_batch(64, 48, rb.RB200_FLAG_NEE, pc, threads=1)
+    b, cb = sc.render_batch(64, 48, rb.RB200_FLAG_NEE, pc, threads=5)
+    assert (bits(a) == bits(b)).all() and ca == cb and np.isfinite(a).all()
+    # same tables without the height maps
+    t2 = rb.configs.parallax(64, 48, samples_per_pixel=2, max_bounces=4).tables
+    t2.instanceProperties.view(np.int32).reshape(-1, 30)[:, 15] = -1        # bumpMapTexID, byte offset 60 of 120
+    c, cc = ol.OracleScene(t2).render_batch(64, 48, rb.RB200_FLAG_NEE, pc)
+    changed = (bits(a) != bits(c)).any(axis=2)
+    assert 0.05 < changed.mean() < 0.95          # the bumped surfaces (and what reflects them) changed, the far walls' first hits did not
+
+
+@pytest.mark.parametrize("name", ["small_mixed_nee", "small_mixed_shipped", "cornell_nee", "parallax_nee"])
 def test_golden_fixtures(ol, rb, name):
     """tests/golden/*.npz were written by tests/golden/make_golden.py from the oracle; they pin it against drift
     (the reference has no fixtures of its own). The CUDA path is checked against the same files in test_gpu_parity."""
