@@ -242,11 +242,13 @@ def main():
     value = rays / (ms * 1e-3) / 1e6
 
     # ---- end to end through the C ABI with host buffers: push constants in, bloom + tonemap, RGBA8 frame out ----
-    # Single GPU: a depth-2 software pipeline, as a display loop runs it — frame i's bloom + tonemap + device->host copy
-    # are queued behind batch i and the host only blocks on frame i-1 before queueing batch i+1, so the thin tail of
-    # one batch overlaps the head of the next; every step still copies its inputs in and reads one frame out, and the
-    # last frame is drained inside the timed region.
-    frames = [r.pinned_frame(), r.pinned_frame()]
+    # Single GPU: a software pipeline as deep as the context's lanes (rb200_pipeline_depth), as a display loop with
+    # that many frames in flight runs it — frame i's bloom + tonemap + device->host copy are queued behind batch i and
+    # the host only blocks on frame i-depth+1 before queueing batch i+1, so the thin tails of the batches in flight
+    # overlap the head of the next; every step still copies its inputs in and reads one frame out, and the last frames
+    # are drained inside the timed region.
+    depth = r.pipeline_depth()
+    frames = [r.pinned_frame() for _ in range(depth)]
     ldr_host = frames[0]
     with torch.cuda.stream(stream):
         r.synchronize()
@@ -270,8 +272,8 @@ def main():
                 hdr_t.copy_(local)
             else:
                 r.postprocess()
-                r.wait_ldr()                              # frame i-1 is on the host now
-                r.read_ldr_async(frames[i & 1])           # frame i follows batch i on the device
+                r.wait_ldr(depth - 1)                     # frame i-depth is on the host now: its buffer is free again
+                r.read_ldr_async(frames[i % depth])       # frame i follows batch i on the device
         r.wait_ldr()
         e1.record(stream)
         torch.cuda.synchronize()
@@ -289,7 +291,7 @@ def main():
            "h2d_bytes_per_step": C.sizeof(rb.abi.RtPushConsts) + C.sizeof(rb.abi.BloomPushConsts) + C.sizeof(rb.abi.TonemappingPushConsts),
            "d2h_bytes_per_step": int(ldr_host.nbytes), "ms_per_step": ms_e2e / K,
            "note": "per step: rb200_render_batch(host push constants) + rb200_postprocess + RGBA8 frame to pinned host memory "
-                   "(rb200_read_ldr_async, waited one step later: depth-2 pipeline, drained inside the timed region); "
+                   "(rb200_read_ldr_async, %d frames in flight = rb200_pipeline_depth, drained inside the timed region); " % depth +
                    "scene upload + BVH build happen once (scene_create_s)"}
     r.close()
 

@@ -248,9 +248,14 @@ RB200_API int rb200_read_hdr(RB200Context* ctx, float* rgba32f);
  * once; rb200_wait_ldr blocks until the most recent such copy has landed. With `rgba8` from rb200_host_alloc (pinned)
  * the caller can issue rb200_render_batch(i+1) before waiting for frame i, so post-processing and read-back of one
  * frame overlap the next batch (what a swap chain gives the reference's loop between endSubmit and present,
- * src/Reina.cpp:380-385). One outstanding copy at a time: wait before issuing the next. */
+ * src/Reina.cpp:380-385). Several copies may be outstanding, each into its own host frame: rb200_wait_ldr_pending
+ * blocks until at most `max_pending` of them (the most recent ones) are still in flight, rb200_wait_ldr until none is.
+ * rb200_pipeline_depth: how many batches the context keeps in flight (its path-state lanes); a frame loop that keeps
+ * that many frames outstanding never drains the device. */
 RB200_API int rb200_read_ldr_async(RB200Context* ctx, uint8_t* rgba8);
 RB200_API int rb200_wait_ldr(RB200Context* ctx);
+RB200_API int rb200_wait_ldr_pending(RB200Context* ctx, uint32_t max_pending);
+RB200_API uint32_t rb200_pipeline_depth(void);
 /* Page-locked host memory for the asynchronous read-back (callers without a CUDA runtime of their own). */
 RB200_API int rb200_host_alloc(size_t bytes, void** out);
 RB200_API int rb200_host_free(void* p);

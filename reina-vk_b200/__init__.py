@@ -89,8 +89,13 @@ class Renderer:
         assert out.dtype == np.uint8 and out.shape == (self.height, self.width, 4) and out.flags.c_contiguous
         abi.check(self.lib, self.lib.rb200_read_ldr_async(self._ctx, out.ctypes.data_as(C.c_void_p)))
 
-    def wait_ldr(self):
-        abi.check(self.lib, self.lib.rb200_wait_ldr(self._ctx))
+    def wait_ldr(self, max_pending=0):
+        """Block until at most `max_pending` read_ldr_async copies (the most recent ones) are still in flight."""
+        abi.check(self.lib, self.lib.rb200_wait_ldr_pending(self._ctx, max_pending))
+
+    def pipeline_depth(self):
+        """Batches the context keeps in flight (path-state lanes): the frame-loop depth that never drains the device."""
+        return int(self.lib.rb200_pipeline_depth())
 
     def write_hdr(self, img):
         img = np.ascontiguousarray(img, np.float32)

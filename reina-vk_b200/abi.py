@@ -149,6 +149,8 @@ SYMBOLS = {
     "rb200_read_hdr": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rb200_read_ldr_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rb200_wait_ldr": (C.c_int, [C.c_void_p]),
+    "rb200_wait_ldr_pending": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "rb200_pipeline_depth": (C.c_uint32, []),
     "rb200_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "rb200_host_free": (C.c_int, [C.c_void_p]),
     "rb200_measure_gather": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_float)]),

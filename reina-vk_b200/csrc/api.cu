@@ -93,10 +93,14 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
     WaveParams& P = c->wp;
     int rc;
 #define A(ptr, n) if ((rc = ctx_alloc(c, &(ptr), (n))) != RB200_OK) return rc
-    for (int lane = 0; lane < 2; lane++) {
-        WaveParams& L = lane == 0 ? c->wp : c->wp1;
+    for (int lane = 0; lane < RB_LANES; lane++) {
+        WaveParams& L = c->lanes[lane];
         L.W = width; L.H = height; L.N = (uint32_t)N; L.flags = flags;
-#if RB_PAIR_STATE
+#if RB_PAIR_STATE == 2
+        // one 128-byte line per slot: float4 records 0..7 = rayO, rayD, thr, st, hit, rad, sum, (spare)
+        A(L.rayO.p, 8 * N); L.rayD.p = L.rayO.p + 1; L.thr.p = L.rayO.p + 2; L.st.p = reinterpret_cast<uint4*>(L.rayO.p + 3);
+        L.hit.p = reinterpret_cast<uint4*>(L.rayO.p + 4); L.rad.p = L.rayO.p + 5; L.sum.p = L.rayO.p + 6;
+#elif RB_PAIR_STATE
         // interleaved pairs (see context.cuh): record 2*slot is the first member, 2*slot+1 the second
         A(L.rayO.p, 2 * N); L.rayD.p = L.rayO.p + 1;
         A(L.thr.p, 2 * N);  L.st.p = reinterpret_cast<uint4*>(L.thr.p + 1);
@@ -114,10 +118,9 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
         RB_CUDA(cudaEventCreateWithFlags(&c->accumDone[lane], cudaEventDisableTiming));
     }
     RB_CUDA(cudaEventCreateWithFlags(&c->frontMark, cudaEventDisableTiming));
-    RB_CUDA(cudaEventCreateWithFlags(&c->ldrCopied, cudaEventDisableTiming | cudaEventBlockingSync));
     A(c->statsSnap, ST_COUNT);
     A(P.image, N); A(c->ping, N); A(c->pong, N); A(c->ldr, N);
-    c->wp1.image = P.image;
+    for (int lane = 1; lane < RB_LANES; lane++) c->lanes[lane].image = P.image;
 #undef A
     RB_CUDA(cudaMemsetAsync(c->statsSnap, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
     RB_CUDA(cudaMemsetAsync(P.image, 0, N * sizeof(float4), c->stream));
@@ -130,16 +133,17 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
 RB200_API int rb200_context_destroy(RB200Context* ctx) {
     if (!ctx) return RB200_OK;
     cudaSetDevice(ctx->device);
-    for (int lane = 0; lane < 2; lane++) if (ctx->laneStream[lane]) cudaStreamSynchronize(ctx->laneStream[lane]);
+    for (int lane = 0; lane < RB_LANES; lane++) if (ctx->laneStream[lane]) cudaStreamSynchronize(ctx->laneStream[lane]);
     cudaStreamSynchronize(ctx->stream);
     for (void* p : ctx->allocations) cudaFree(p);
     for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
-    for (int lane = 0; lane < 2; lane++) {
+    for (int lane = 0; lane < RB_LANES; lane++) {
         if (ctx->accumDone[lane]) cudaEventDestroy(ctx->accumDone[lane]);
         if (ctx->laneStream[lane]) cudaStreamDestroy(ctx->laneStream[lane]);
     }
     if (ctx->frontMark) cudaEventDestroy(ctx->frontMark);
-    if (ctx->ldrCopied) cudaEventDestroy(ctx->ldrCopied);
+    for (cudaEvent_t e : ctx->ldrPendingEvents) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ldrEventPool) cudaEventDestroy(e);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RB200_OK;
@@ -147,7 +151,7 @@ RB200_API int rb200_context_destroy(RB200Context* ctx) {
 
 RB200_API int rb200_context_set_stream(RB200Context* ctx, void* cuda_stream) {
     if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
-    for (int lane = 0; lane < 2; lane++) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[lane]));
+    for (int lane = 0; lane < RB_LANES; lane++) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[lane]));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream;
@@ -243,8 +247,9 @@ RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB2
                 attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
                 attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
                 bool ok = true;
-                for (cudaStream_t st : {ctx->laneStream[0], ctx->laneStream[1], ctx->stream})
-                    ok &= cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+                for (int lane = 0; lane < RB_LANES; lane++)
+                    ok &= cudaStreamSetAttribute(ctx->laneStream[lane], cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+                ok &= cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
                 if (ok) sc->l2PersistBytes = setAside;
             }
         }
@@ -312,18 +317,28 @@ RB200_API int rb200_read_ldr(RB200Context* ctx, uint8_t* rgba8) {
 RB200_API int rb200_read_ldr_async(RB200Context* ctx, uint8_t* rgba8) {
     if (!ctx || !rgba8) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
     RB_CUDA(cudaMemcpyAsync(rgba8, ctx->ldr, (size_t)ctx->width * ctx->height * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    RB_CUDA(cudaEventRecord(ctx->ldrCopied, ctx->stream));
-    ctx->ldrPending = true;
+    cudaEvent_t e;
+    if (!ctx->ldrEventPool.empty()) { e = ctx->ldrEventPool.back(); ctx->ldrEventPool.pop_back(); }
+    else RB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+    ctx->ldrPendingEvents.push_back(e);
+    RB_CUDA(cudaEventRecord(e, ctx->stream));
     return RB200_OK;
 }
 
-RB200_API int rb200_wait_ldr(RB200Context* ctx) {
+RB200_API int rb200_wait_ldr_pending(RB200Context* ctx, uint32_t max_pending) {
     if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
-    if (!ctx->ldrPending) return RB200_OK;
-    RB_CUDA(cudaEventSynchronize(ctx->ldrCopied));
-    ctx->ldrPending = false;
+    while (ctx->ldrPendingEvents.size() > max_pending) {
+        cudaEvent_t e = ctx->ldrPendingEvents.front();
+        ctx->ldrPendingEvents.erase(ctx->ldrPendingEvents.begin());
+        ctx->ldrEventPool.push_back(e);
+        RB_CUDA(cudaEventSynchronize(e));
+    }
     return RB200_OK;
 }
+
+RB200_API int rb200_wait_ldr(RB200Context* ctx) { return rb200_wait_ldr_pending(ctx, 0); }
+
+RB200_API uint32_t rb200_pipeline_depth(void) { return RB_LANES; }
 
 RB200_API int rb200_host_alloc(size_t bytes, void** out) {
     if (!out || bytes == 0) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
@@ -377,7 +392,7 @@ RB200_API int rb200_get_stats(RB200Context* ctx, RB200Stats* last_batch, RB200St
     // per-lane counters hold the lane's last batch; k_accumulate adds them to the cumulative array when the batch ends.
     // The front-end stream waits for the last batch's accumulation, which is ordered after every earlier batch.
     unsigned long long lastc[ST_COUNT] = {0}, cum[ST_COUNT];
-    const rb200::WaveParams& lastLane = ((ctx->batchCalls - 1) & 1u) == 0 ? ctx->wp : ctx->wp1;
+    const rb200::WaveParams& lastLane = ctx->lanes[ctx->batchCalls > 0 ? (ctx->batchCalls - 1) % RB_LANES : 0];
     if (ctx->batchCalls > 0) RB_CUDA(cudaMemcpyAsync(lastc, lastLane.stats, sizeof(lastc), cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(cudaMemcpyAsync(cum, ctx->statsSnap, sizeof(cum), cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -55,13 +55,18 @@ template <class T, int STRIDE = 1> struct StateArr {
     T* p;
     __device__ __forceinline__ StateRef<T> operator[](uint32_t i) const { return StateRef<T>{p + (size_t)i * STRIDE}; }
 };
-// Records that the shading kernels always touch together share one 32-byte DRAM sector per slot: (rayO, rayD),
-// (thr, st), (hit, rad). A material queue holds a scattered subset of the slots, so with one array per record every
-// 16-byte access moved a half-used sector; the shading kernels are bound by DRAM sector throughput (~2.7 TB/s).
+// Path-state layout (RB_PAIR_STATE). A material queue holds a scattered subset of the slots and the shading kernels
+// are bound by DRAM sector throughput (~2.5 TB/s), so what a kernel touches for one slot should sit together:
+//   0  one array per record: every 16-byte access moved a half-used 32-byte sector;
+//   1  interleaved pairs, one sector per slot: (rayO, rayD), (thr, st), (hit, rad): +4 % rays/s over 0;
+//   2  one 128-byte line per slot: rayO, rayD | thr, st | hit, rad | sum, spare — a shading kernel's three sectors
+//      are one DRAM burst: Disney 8.0 -> 7.5 ms, Lambertian 5.6 -> 5.3 ms per batch, shadow 18.0 -> 18.2 ms,
+//      +2.2 % rays/s over 1 on B200 (headline scene). Default.
 #ifndef RB_PAIR_STATE
-#define RB_PAIR_STATE 1
+#define RB_PAIR_STATE 2
 #endif
-static constexpr int STATE_STRIDE = RB_PAIR_STATE ? 2 : 1;
+static constexpr int STATE_STRIDE = RB_PAIR_STATE == 2 ? 8 : (RB_PAIR_STATE ? 2 : 1);
+static constexpr int SUM_STRIDE = RB_PAIR_STATE == 2 ? 8 : 1;
 
 struct WaveParams {
     DeviceScene S;
@@ -72,7 +77,7 @@ struct WaveParams {
     StateArr<uint4, STATE_STRIDE> hit;        // x = bits(b1), y = bits(b2), z = primitive, w = instance
     StateArr<float4, STATE_STRIDE> thr;       // xyz throughput, w = accumulatedDistance
     StateArr<float4, STATE_STRIDE> rad;       // xyz radiance of the current path
-    StateArr<float4> sum;       // xyz summed sample colours of this batch, w = bits(actualSamples)
+    StateArr<float4, SUM_STRIDE> sum;       // xyz summed sample colours of this batch, w = bits(actualSamples)
     StateArr<uint4, STATE_STRIDE> st;         // x = rng state, y = flags | segments << 8, z = sample index
     StateArr<float4> shO, shD, shA, shB, shT;   // shadow-ray records (compacted): origin/tmax, dir, D/wNEE, E*wBRDF/slot, throughput
     uint32_t* rayQ[2];
@@ -86,22 +91,30 @@ struct WaveParams {
 
 } // namespace rb200
 
+// Number of batches in flight. A batch's waves thin out (at 1080p, 8 spp x 16 bounces: wave 40 of 128 carries 8 % of
+// the paths, wave 64 0.2 %) but a thin wave still costs 50-170 us of dependent-fetch latency per kernel; with more
+// lanes more of those tails run beside another batch's full waves. 0.5 GB of path state per lane at 1080p.
+// Headline scene on B200, device-resident loop: 1 / 2 / 3 / 4 / 6 lanes = 1478 / 1798 / 1891 / 1955 / 1985 Mrays/s.
+#ifndef RB_LANES
+#define RB_LANES 4
+#endif
+
 struct RB200Context {
     uint32_t width = 0, height = 0, flags = 0;
     int device = 0;
     int numSMs = 148;
     cudaStream_t stream = nullptr;             // front-end stream: API calls are ordered on it (may be the caller's)
     bool ownStream = false;
-    // Two lanes (path-state sets + internal streams). Consecutive rb200_render_batch calls alternate lanes so the
-    // long, thinly populated tail of one batch overlaps the head of the next; the per-pixel accumulation into the
-    // shared HDR image stays in batch order (k_accumulate of batch b waits for that of batch b-1).
-    rb200::WaveParams wp{};                    // lane 0 (also the scratch of the query entry points)
-    rb200::WaveParams wp1{};                   // lane 1
-    cudaStream_t laneStream[2] = {nullptr, nullptr};
-    cudaEvent_t accumDone[2] = {nullptr, nullptr};
+    // RB_LANES lanes (path-state sets + internal streams). Consecutive rb200_render_batch calls rotate through the
+    // lanes so the long, thinly populated tail of one batch overlaps the heads of the next ones; the per-pixel
+    // accumulation into the shared HDR image stays in batch order (k_accumulate of batch b waits for that of b-1).
+    rb200::WaveParams lanes[RB_LANES]{};       // lanes[0] is also the scratch of the query entry points
+    rb200::WaveParams& wp = lanes[0];
+    cudaStream_t laneStream[RB_LANES] = {};
+    cudaEvent_t accumDone[RB_LANES] = {};
     cudaEvent_t frontMark = nullptr;
-    cudaEvent_t ldrCopied = nullptr;           // completion of the most recent rb200_read_ldr_async
-    bool ldrPending = false;
+    std::vector<cudaEvent_t> ldrPendingEvents; // completion events of the outstanding rb200_read_ldr_async copies, oldest first
+    std::vector<cudaEvent_t> ldrEventPool;
     uint64_t batchCalls = 0;
     std::vector<void*> allocations;
     float4 *ping = nullptr, *pong = nullptr;   // bloom work images

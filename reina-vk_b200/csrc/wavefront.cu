@@ -544,13 +544,13 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
         set_error("Scene must have at least one emissive object");   // src/scene/Instances.cpp:125-127
         return RB200_ERR_NO_EMITTER;
     }
-    // Lane selection: consecutive calls alternate between two path-state sets on two internal streams, so the thin
-    // tail of batch b (few live paths, latency-bound launches) overlaps the head of batch b+1.
-    const int lane = (int)(ctx->batchCalls & 1u);
-    const int other = lane ^ 1;
+    // Lane selection: consecutive calls rotate through RB_LANES path-state sets on as many internal streams, so the
+    // thin tail of batch b (few live paths, latency-bound launches) overlaps the heads of the following batches.
+    const int lane = (int)(ctx->batchCalls % RB_LANES);
+    const int other = (lane + RB_LANES - 1) % RB_LANES;        // the lane of the previous batch
     const bool hadPrevious = ctx->batchCalls > 0;
     ctx->batchCalls++;
-    WaveParams& P = lane == 0 ? ctx->wp : ctx->wp1;
+    WaveParams& P = ctx->lanes[lane];
     P.S = scene->dev;
     P.pc = *pc;
     cudaStream_t s = ctx->laneStream[lane];
@@ -558,7 +558,8 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
     // frame, an external reduce of the image ...) must precede this batch's accumulation — not its tracing
     RB_CUDA(cudaEventRecord(ctx->frontMark, ctx->stream));
     const bool count = (ctx->flags & RB200_FLAG_COUNT_BVH) != 0;
-    if (ctx->flags & RB200_FLAG_TIME_KERNELS) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[other]));   // timing pass: no overlap
+    if (ctx->flags & RB200_FLAG_TIME_KERNELS)      // timing pass: no overlap
+        for (int l = 0; l < RB_LANES; l++) if (l != lane) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[l]));
 
     static int gExtend = 0, gExtendC = 0, gShadow = 0, gShadowC = 0, gShade[5] = {0, 0, 0, 0, 0}, gFinish = 0;
     if (!gExtend) {
@@ -594,6 +595,10 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
     };
     tic(0); k_generate<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(P); toc(); nl++;
     const uint32_t maxWaves = pc->samplesPerPixel * pc->maxBounces;
+    // developer aid: RB200_WAVE_LOG=<file> (with RB200_FLAG_TIME_KERNELS) writes one CSV row per wave — queue counters
+    // and the device time of every kernel — for the last batch rendered; it synchronises after every wave
+    const char* waveLogPath = timed ? getenv("RB200_WAVE_LOG") : nullptr;
+    std::vector<uint32_t> waveCounters;
     for (uint32_t w = 0; w < maxWaves; w++) {
         const int p = (int)(w & 1u);
         RB_CUDA(cudaMemsetAsync(P.counters + (p ^ 1) * CNT_SET, 0, CNT_SET * sizeof(uint32_t), s));
@@ -613,10 +618,36 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
         }
         tic(8); k_finish<<<gFinish, BLOCK, 0, s>>>(P, p); toc();
         nl += 7;
+        if (waveLogPath) {
+            waveCounters.resize((size_t)(w + 1) * CNT_SET);
+            RB_CUDA(cudaMemcpyAsync(&waveCounters[(size_t)w * CNT_SET], P.counters + p * CNT_SET, CNT_SET * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToHost, s));
+            RB_CUDA(cudaStreamSynchronize(s));
+        }
+    }
+    if (waveLogPath) {
+        if (FILE* f = fopen(waveLogPath, "w")) {
+            fprintf(f, "wave,rays,lambertian,metal,dielectric,disney,miss,shadow,end,extend_us,miss_us,lambertian_us,metal_us,dielectric_us,disney_us,shadow_us,finish_us\n");
+            size_t e = 2;      // event pair 0 is k_generate
+            for (uint32_t w = 0; w < maxWaves; w++) {
+                const uint32_t* c = &waveCounters[(size_t)w * CNT_SET];
+                fprintf(f, "%u,%u,%u,%u,%u,%u,%u,%u,%u", w, c[CNT_RAYS], c[CNT_MAT0], c[CNT_MAT0 + 1], c[CNT_MAT0 + 2], c[CNT_MAT0 + 3],
+                        c[CNT_MISS], c[CNT_SHADOW], c[CNT_END]);
+                const int perWave = (ctx->flags & RB200_FLAG_NEE) ? 8 : 7;
+                for (int k = 0; k < perWave; k++, e += 2) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, ctx->evPool[e], ctx->evPool[e + 1]);
+                    fprintf(f, ",%.1f", ms * 1000.f);
+                    if (k == 5 && perWave == 7) fprintf(f, ",0.0");
+                }
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
     }
     // fold this batch's pixel means into the shared image: after the previous batch's fold and after whatever the
     // caller had queued on the front-end stream; then let the front-end stream see the result
-    if (hadPrevious) RB_CUDA(cudaStreamWaitEvent(s, ctx->accumDone[other], 0));
+    if (hadPrevious && other != lane) RB_CUDA(cudaStreamWaitEvent(s, ctx->accumDone[other], 0));
     RB_CUDA(cudaStreamWaitEvent(s, ctx->frontMark, 0));
     k_accumulate<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(P.image, P.mean.p, P.N, pc->sampleBatch, ctx->flags, P.stats,
                                                              ctx->statsSnap); nl++;
@@ -682,7 +713,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace_query(const WideNode* nodes, co
 static int run_query(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float4* dO, const float4* dD, int any,
                      RB200PrimaryHit* out) {
     RB200PrimaryHit* dOut;
-    for (int lane = 0; lane < 2; lane++) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[lane]));   // lane 0's arrays are the scratch
+    for (int lane = 0; lane < RB_LANES; lane++) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[lane]));   // lane 0's arrays are the scratch
     uint32_t* dCursor;
     RB_CUDA(cudaMalloc(&dOut, (size_t)n * sizeof(RB200PrimaryHit)));
     RB_CUDA(cudaMalloc(&dCursor, sizeof(uint32_t)));
@@ -700,7 +731,7 @@ static int run_query(RB200Context* ctx, const RB200Scene* scene, uint32_t n, con
 
 int trace_primary(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc, RB200PrimaryHit* out) {
     WaveParams& P = ctx->wp;
-    for (int lane = 0; lane < 2; lane++) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[lane]));
+    for (int lane = 0; lane < RB_LANES; lane++) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[lane]));
     P.S = scene->dev; P.pc = *pc;
     k_primary_rays<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, ctx->stream>>>(P, P.shO.p, P.shD.p);
     ctx->launches++;

@@ -373,6 +373,41 @@ def test_pipelined_read_back_matches_blocking_read(rb):
         assert (a == b).all()
 
 
+def test_frame_loop_as_deep_as_the_lanes_matches_blocking_read(rb):
+    """rb200_pipeline_depth frames in flight (one per path-state lane), each read into its own pinned frame and waited
+    for with rb200_wait_ldr_pending(depth - 1): the frames equal those of a blocking loop, over more batches than
+    there are lanes (every lane and every frame buffer is re-used)."""
+    wl = rb.configs.small_mixed(160, 120, nee=True, samples_per_pixel=2, max_bounces=6)
+    r = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE)
+    depth = r.pipeline_depth()
+    assert 1 <= depth <= 16
+    nb = 2 * depth + 3
+    want = []
+    for b in range(nb):
+        r.render_batch(wl.push_constants(b))
+        r.postprocess()
+        want.append(r.read_ldr().copy())
+    hdr_want = r.read_hdr().copy()
+    r.close()
+    r = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE)
+    frames = [r.pinned_frame() for _ in range(depth)]
+    got = {}
+    for b in range(nb):
+        r.render_batch(wl.push_constants(b))
+        r.postprocess()
+        r.wait_ldr(depth - 1)
+        if b >= depth:
+            got[b - depth] = frames[b % depth].copy()      # frame b-depth has landed; its buffer is re-used now
+        r.read_ldr_async(frames[b % depth])
+    r.wait_ldr()
+    for b in range(max(0, nb - depth), nb):
+        got[b] = frames[b % depth].copy()
+    assert (bits(r.read_hdr()) == bits(hdr_want)).all()
+    r.close()
+    for b in range(nb):
+        assert (want[b] == got[b]).all(), b
+
+
 def test_gather_microbenchmark_reports_a_plausible_bandwidth(rb):
     wl = rb.configs.small_mixed(16, 12)
     r = rb.Renderer(wl.width, wl.height, wl.tables)
