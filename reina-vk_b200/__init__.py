@@ -12,7 +12,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import abi, camera, configs, meshes, scene
+from . import abi, camera, configs, gltf, meshes, scene
 from .abi import (RB200_FLAG_ACCUM_SUM, RB200_FLAG_COUNT_BVH, RB200_FLAG_NEE, RB200_FLAG_TIME_KERNELS, BloomPushConsts, RB200Error,
                   RtPushConsts, TonemappingPushConsts, load_library)
 from .scene import Material, ModelData, Scene, SceneTables
@@ -20,7 +20,7 @@ from .scene import Material, ModelData, Scene, SceneTables
 __all__ = ["Renderer", "Material", "ModelData", "Scene", "SceneTables", "RtPushConsts", "BloomPushConsts",
            "TonemappingPushConsts", "RB200_FLAG_NEE", "RB200_FLAG_ACCUM_SUM", "RB200_FLAG_COUNT_BVH", "RB200_FLAG_TIME_KERNELS",
            "RB200Error",
-           "abi", "camera", "configs", "meshes", "scene", "load_library"]
+           "abi", "camera", "configs", "gltf", "meshes", "scene", "load_library"]
 
 
 class _DevicePtr:

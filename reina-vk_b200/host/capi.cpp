@@ -4,6 +4,7 @@
 #include <string>
 
 #include "config.h"
+#include "gltf.h"
 #include "host.h"
 #include "png.h"
 #include "texture.h"
@@ -79,6 +80,13 @@ int rbhost_tables_obj(const char* path, uint32_t materialIdx, int addLight, Scen
         m.interpNormals = true;
         Scene s = make_obj_scene({{path, m, "", "", ""}}, addLight != 0);
         *out = new SceneTables(s.build(false));
+    });
+}
+
+int rbhost_tables_gltf(const char* path, int requireEmitter, SceneTables** out) {
+    return guarded([&] {
+        Scene s = load_gltf_scene(path);
+        *out = new SceneTables(s.build(requireEmitter != 0));
     });
 }
 

@@ -7,6 +7,7 @@
 #include <stdexcept>
 
 #include "png.h"
+#include "gltf.h"
 #include "texture.h"
 #include "rh_math.h"
 
@@ -101,6 +102,17 @@ Scene make_obj_scene(const std::vector<ObjRequest>& objs, bool addLight) {
         s.addObject(md, identity(), m);
     }
     if (addLight) s.addObject(cornell_light(), identity(), light_material());
+    return s;
+}
+
+Scene make_gltf_scene(const std::string& path, bool addLightIfDark) {
+    bool emits = false;
+    Scene s = load_gltf_scene(path, &emits);
+    if (!emits && addLightIfDark) {
+        std::fprintf(stderr, "warning: %s has no emissive material; adding the Cornell light panel so that next-event "
+                             "estimation has an emitter\n", path.c_str());
+        s.addObject(cornell_light(), identity(), light_material());
+    }
     return s;
 }
 

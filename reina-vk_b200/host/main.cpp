@@ -22,6 +22,8 @@ static void usage() {
         "  --config FILE        TOML configuration (default: config/config.toml)\n"
         "  --scene NAME         built-in scene: cornell | cornell-sphere (overrides [render].scene)\n"
         "  --obj FILE           render this OBJ instead of a built-in scene (repeatable); the Cornell light panel is added\n"
+        "  --gltf FILE          render the default scene of a glTF 2.0 file (.gltf or .glb), the reference's default scene path;\n"
+        "                       when none of its materials emits and NEE is on, the Cornell light panel is added\n"
         "  --material NAME      material of the following --obj: lambertian | metal | dielectric | disney (default lambertian)\n"
         "  --albedo R,G,B       albedo of the following --obj (default 0.8,0.8,0.8)\n"
         "  --roughness X  --ior X  --metallic X     parameters of the following --obj\n"
@@ -47,7 +49,7 @@ static bool parse_vec3(const char* s, std::array<float, 3>& out) {
 }
 
 int main(int argc, char** argv) {
-    std::string configPath = "config/config.toml", sceneName, finalOut, outDir = ".", dumpPc;
+    std::string configPath = "config/config.toml", sceneName, finalOut, outDir = ".", dumpPc, gltfPath;
     std::vector<ObjRequest> objs;
     std::string nextTexture, nextNormalMap, nextBumpMap;
     Material nextMat;
@@ -72,6 +74,7 @@ int main(int argc, char** argv) {
                 objs.push_back({value(), nextMat, nextTexture, nextNormalMap, nextBumpMap});
                 nextTexture.clear(); nextNormalMap.clear(); nextBumpMap.clear();
             }
+            else if (a == "--gltf") gltfPath = value();
             else if (a == "--texture") nextTexture = value();
             else if (a == "--normal-map") nextNormalMap = value();
             else if (a == "--bump-map") nextBumpMap = value();
@@ -108,7 +111,10 @@ int main(int argc, char** argv) {
         if (nee >= 0) cfg.nee = nee != 0;
         if (spp < 0 || seconds < 0) throw std::runtime_error("--spp and --seconds must not be negative");
 
-        Scene scene = objs.empty() ? make_builtin_scene(cfg.scene) : make_obj_scene(objs, true);
+        if (!gltfPath.empty() && !objs.empty()) throw std::runtime_error("--gltf and --obj cannot be combined");
+        Scene scene = !gltfPath.empty() ? make_gltf_scene(gltfPath, cfg.nee)
+                      : objs.empty()    ? make_builtin_scene(cfg.scene)
+                                        : make_obj_scene(objs, true);
         SceneTables tables = scene.build(cfg.nee);
         RB200RtPushConsts pc = make_push_constants(cfg, tables.totalEmissiveWeight);
         if (!dumpPc.empty()) {

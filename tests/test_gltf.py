@@ -1,0 +1,172 @@
+"""glTF 2.0 / GLB scene import: the Python mirror (reina-vk_b200/gltf.py) and the C++ host
+(reina-vk_b200/host/gltf.cpp) of reina::scene::gltf (src/scene/gltf/gltfloader.cpp:72-456) on assets written by
+tests/gltf_fixture.py. CPU: what the importer produces (objects, instances, materials, textures, transforms), that
+both importers hand identical tables to rb200_scene_create, and the reference's error messages. GPU: the reina_b200
+binary renders --gltf to the same frame the Python host gets from the same library."""
+import ctypes as C
+import importlib
+import json
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import gltf_fixture as gf
+from test_cpp_host import HOST, REFERENCE_SCHEMA, assert_tables_identical, cpp_tables, decode_png, err, host, py_tables  # noqa: F401
+
+
+@pytest.fixture(scope="module")
+def gl(rb):
+    return importlib.import_module("reina-vk_b200.gltf")
+
+
+@pytest.mark.filterwarnings("ignore:falling back to UV")
+def test_glb_import_follows_the_reference_stages(rb, gl, tmp_path):
+    path, imgs = gf.build(tmp_path)
+    sc = gl.loadScene(path)
+    # meshes 0, 1 (two primitives), 2 are used by the default scene; mesh 3 belongs to another scene
+    assert len(sc.modelRanges) == 4
+    tris = [r.indexCount for r in sc.modelRanges]
+    assert tris[0] == 32 and tris[1] + tris[2] == 16 * 10 * 2 - 2 * 16 and tris[3] == 2
+    # instances in depth-first node order: floor, ball (2 primitives), ball2 (2 primitives), lamp
+    assert [i[2] for i in sc.instancesToCreate] == [0, 1, 2, 1, 2, 3]
+    tiles, glass, none_, _, _, lamp = sc.materials
+    f32 = lambda *v: tuple(float(np.float32(x)) for x in v)
+    assert all(m.materialIdx == 3 and m.interpNormals and m.bumpMapID == -1 for m in sc.materials)
+    assert tiles.albedo == f32(0.9, 0.8, 0.7) and tiles.roughness == f32(0.7)[0] and tiles.metallic == f32(0.1)[0]   # 0.95 clamped to 0.7
+    assert (tiles.textureID, tiles.normalMapID, tiles.cullBackface) == (0, 1, False)                                 # doubleSided
+    assert glass.roughness == f32(0.1)[0] and glass.ior == f32(1.33)[0] and glass.specularTransmission == f32(0.8)[0]  # 0.02 clamped up
+    assert glass.cullBackface is False                                       # transmission switches culling off
+    assert (none_.albedo, none_.roughness, none_.ior, none_.cullBackface, none_.metallic) == ((1.0, 1.0, 1.0), 0.0, 1.5, False, 0.0)
+    assert lamp.emission == f32(12.5, 0.9 * 12.5, 0.8 * 12.5) or np.allclose(lamp.emission, (12.5, 11.25, 10.0), rtol=1e-6)
+    assert lamp.metallic == 1.0 and lamp.roughness == f32(0.7)[0]            # glTF defaults 1.0 / 1.0 (clamped)
+    # embedded images are not flipped (src/graphics/Image.cpp:28)
+    assert (sc.texturesToCreate[0] == imgs["tex0"]).all() and (sc.texturesToCreate[1] == imgs["nmap"]).all()
+    # world transform of "ball": root (T * R) * local (T * S), checked against numpy in float64
+    a = 0.2
+    R = np.array([[np.cos(2 * a), 0, np.sin(2 * a), 0], [0, 1, 0, 0], [-np.sin(2 * a), 0, np.cos(2 * a), 0], [0, 0, 0, 1]])
+    T0 = np.eye(4); T0[:3, 3] = (0, 0.1, 0)
+    T1 = np.eye(4); T1[:3, 3] = (-0.5, 0.42, 0.1)
+    S1 = np.diag([1.0, 1.3, 0.8, 1.0])
+    want = (T0 @ R @ T1 @ S1).T.astype(np.float32)        # glm layout m[c][r]
+    np.testing.assert_allclose(sc.instancesToCreate[1][3], want, rtol=0, atol=1e-6)
+    t = sc.build(require_emitter=True)
+    assert t.numEmissive == 1 and t.num_triangles() == 32 + 2 * (tris[1] + tris[2]) + 2
+    # de-quantised UVs of the floor: ushort / 65535
+    uv = t.texCoords.reshape(-1, 2)[:25]
+    assert uv.min() == 0.0 and uv.max() == 1.0 and np.allclose(uv[1], (0.25, 0.0), atol=1e-4)
+    # TANGENT w = -1: bitangent = cross(n, t) * w = cross((0,1,0), (1,0,0)) * -1 = (0, 0, 1)
+    assert (t.tbns.reshape(-1, 3, 3)[0] == np.array([[1, 0, 0], [0, 0, 1], [0, 1, 0]], np.float32)).all()
+
+
+@pytest.mark.filterwarnings("ignore:falling back to UV")
+def test_external_gltf_equals_glb_except_for_the_flipped_file_texture(rb, gl, tmp_path):
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    p_glb, imgs = gf.build(tmp_path / "a", external=False)
+    p_ext, _ = gf.build(tmp_path / "b", external=True)
+    a = py_tables(gl.loadScene(p_glb).build(require_emitter=True))
+    b = py_tables(gl.loadScene(p_ext).build(require_emitter=True))
+    # file textures are flipped vertically on load (stbi_set_flip_vertically_on_load(true), Image.cpp:14), data-URI
+    # and buffer-view images are not (:28)
+    assert (b["textures"][0] == imgs["tex0"][::-1]).all() and (b["textures"][1] == imgs["nmap"]).all()
+    b["textures"][0] = a["textures"][0]
+    assert_tables_identical(a, b)
+
+
+@pytest.mark.filterwarnings("ignore:falling back to UV")
+@pytest.mark.parametrize("external", [False, True])
+def test_cpp_importer_tables_identical_to_python(host, rb, gl, tmp_path, external):
+    path, _ = gf.build(tmp_path, external=external)
+    host.rbhost_tables_gltf.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    h = C.c_void_p()
+    assert host.rbhost_tables_gltf(path.encode(), 1, C.byref(h)) == 0, err(host)
+    assert_tables_identical(cpp_tables(host, rb, h), py_tables(gl.loadScene(path).build(require_emitter=True)))
+    host.rbhost_tables_free(h)
+
+
+def _write_gltf(tmp_path, doc, name="bad.gltf"):
+    p = tmp_path / name
+    p.write_text(json.dumps(doc))
+    return str(p)
+
+
+def test_errors_match_the_reference_messages(host, rb, gl, tmp_path):
+    host.rbhost_tables_gltf.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+
+    def both(path, needle):
+        with pytest.raises(RuntimeError, match=needle):
+            gl.loadScene(path).build()
+        h = C.c_void_p()
+        assert host.rbhost_tables_gltf(path.encode(), 0, C.byref(h)) != 0 and needle in err(host), err(host)
+    both(str(tmp_path / "absent.glb"), "Failed to find glTF file")
+    both(_write_gltf(tmp_path, {"asset": {"version": "2.0"}}), "No scenes supplied in gLTF file")
+    (tmp_path / "junk.gltf").write_text("{ not json")
+    both(str(tmp_path / "junk.gltf"), "Failed to parse glTF")
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    import base64
+    uri = "data:application/octet-stream;base64," + base64.b64encode(tri.tobytes()).decode()
+    doc = {"asset": {"version": "2.0"}, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+           "meshes": [{"primitives": [{"attributes": {"POSITION": 0}}]}],
+           "buffers": [{"byteLength": 36, "uri": uri}], "bufferViews": [{"buffer": 0, "byteLength": 36}],
+           "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}]}
+    both(_write_gltf(tmp_path, doc, "nonormal.gltf"), "Meshes without vertex normals are not supported")
+    doc["meshes"][0]["primitives"][0]["attributes"]["NORMAL"] = 0
+    doc["meshes"][0]["primitives"][0]["mode"] = 1
+    both(_write_gltf(tmp_path, doc, "lines.gltf"), "only TRIANGLES primitives are supported")
+    doc["meshes"][0]["primitives"][0]["mode"] = 4
+    doc["accessors"][0]["count"] = 4
+    both(_write_gltf(tmp_path, doc, "overrun.gltf"), "reads past its buffer view")
+    doc["accessors"][0]["count"] = 3
+    doc["images"] = [{"uri": "data:image/jpeg;base64," + base64.b64encode(b"\xff\xd8\xff\xe0" + b"0" * 32).decode()}]
+    both(_write_gltf(tmp_path, doc, "jpeg.gltf"), "only PNG textures are supported")
+    # a truncated GLB
+    glb, _ = gf.build(tmp_path)
+    raw = open(glb, "rb").read()
+    (tmp_path / "cut.glb").write_bytes(raw[: len(raw) // 2])
+    both(str(tmp_path / "cut.glb"), "Failed to parse glTF")
+    (tmp_path / "v1.glb").write_bytes(b"glTF" + struct.pack("<II", 1, 20) + b"\0" * 8)
+    both(str(tmp_path / "v1.glb"), "unsupported GLB version")
+
+
+@pytest.mark.filterwarnings("ignore:falling back to UV")
+def test_oracle_renders_the_imported_scene(ol, rb, gl, tmp_path):
+    """The imported tables are a valid scene for the path tracer: finite image, light reaches the floor."""
+    path, _ = gf.build(tmp_path)
+    t = gl.loadScene(path).build(require_emitter=True)
+    pc = rb.camera.push_constants(64, 48, (0.0, 1.3, 3.4), (0.0, 0.4, 0.0), 40.0, total_emissive_weight=t.totalEmissiveWeight,
+                                  samples_per_pixel=4, max_bounces=5)
+    hdr, cnt = ol.OracleScene(t).render_batch(64, 48, rb.RB200_FLAG_NEE, pc)
+    assert np.isfinite(hdr).all() and hdr[30:, :, :3].mean() > 0.01 and cnt["shadowRays"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.filterwarnings("ignore:falling back to UV")
+def test_cli_renders_glb_like_the_python_host(host, ol, rb, gl, tmp_path):
+    """reina_b200 --gltf scene.glb: the frame equals the one the Python host renders from its own import of the same
+    file through the same library, and the HDR image of that scene is bit-identical to the oracle's."""
+    path, _ = gf.build(tmp_path)
+    cfg = tmp_path / "config.toml"
+    cfg.write_text(REFERENCE_SCHEMA.replace("save_on_samples = [64, 256, 1024]", "save_on_samples = []")
+                   .replace("save_on_times = [60.0]", "save_on_times = []")
+                   + "\n[render]\nwidth = 96\nheight = 72\ncamera_pos = [0.0, 1.3, 3.4]\ncamera_look_at = [0.0, 0.4, 0.0]\n")
+    out, pcfile = tmp_path / "final.png", tmp_path / "pc.bin"
+    run = subprocess.run([os.path.join(HOST, "reina_b200"), "--config", str(cfg), "--gltf", path, "--spp", "16", "--out", str(out),
+                          "--dump-pc", str(pcfile), "--quiet"], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr + run.stdout
+    tables = gl.loadScene(path).build(require_emitter=True)
+    pc = rb.abi.RtPushConsts.from_buffer_copy(pcfile.read_bytes())
+    r = rb.Renderer(96, 72, tables, flags=rb.RB200_FLAG_NEE)
+    sc = ol.OracleScene(tables)
+    hdr_o = np.zeros((72, 96, 4), np.float32)
+    for b in range(2):
+        pc.sampleBatch = b
+        r.render_batch(pc)
+        hdr_o, _ = sc.render_batch(96, 72, rb.RB200_FLAG_NEE, pc, hdr_o)
+    assert (r.read_hdr().view(np.uint32) == hdr_o.view(np.uint32)).all()
+    r.postprocess()
+    want = r.read_ldr().copy()
+    r.close()
+    got = decode_png(out.read_bytes())
+    assert (got == want).all() and got[..., :3].max() > 0
