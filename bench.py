@@ -222,7 +222,10 @@ def main():
         for i in range(K):
             r.render_batch(wl.push_constants(batch_index(Wm + i)))
         if world > 1:
-            dist.reduce(hdr_t, dst=0, op=dist.ReduceOp.SUM)              # the one collective of the path
+            # the one collective of the path: every rank's SUM image (a stream-ordered snapshot, so the accumulation
+            # images stay per-rank sums and later frames can be presented from them) reduced to rank 0
+            reduced = hdr_t.clone()
+            dist.reduce(reduced, dst=0, op=dist.ReduceOp.SUM)
         ev1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -258,18 +261,21 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        snaps = [torch.empty_like(hdr_t) for _ in range(depth)] if world > 1 else None
         for i in range(K):
             r.render_batch(wl.push_constants(batch_index(Wm + K + i)))
             if world > 1:
-                # one presented frame: reduce every rank's SUM image to rank 0, resolve, post-process and read back
-                # there; rank 0 then restores its local sum so that accumulation continues
-                local = hdr_t.clone()
-                dist.reduce(hdr_t, dst=0, op=dist.ReduceOp.SUM)
+                # one presented frame per step: snapshot this rank's SUM image behind batch i (stream-ordered, no host
+                # wait), reduce the snapshots to rank 0 (the one collective of the path), and let rank 0 resolve +
+                # bloom + tonemap the reduced copy (rb200_present_sum) and read the frame back asynchronously. The
+                # accumulation images are never touched, so the lanes keep running under the reduce.
+                snap = snaps[i % depth]
+                snap.copy_(hdr_t)
+                dist.reduce(snap, dst=0, op=dist.ReduceOp.SUM)
                 if rank == 0:
-                    r.resolve_sum((Wm + 2 * K + i + 1) * world)
-                    r.postprocess()
-                    r.read_ldr(ldr_host)
-                hdr_t.copy_(local)
+                    r.present_sum((Wm + 2 * K + i + 1) * world, snap.data_ptr())
+                    r.wait_ldr(depth - 1)
+                    r.read_ldr_async(frames[i % depth])
             else:
                 r.postprocess()
                 r.wait_ldr(depth - 1)                     # frame i-depth is on the host now: its buffer is free again
@@ -290,7 +296,10 @@ def main():
     e2e = {"value": rays_e2e / (ms_e2e * 1e-3) / 1e6, "unit": "Mrays/s",
            "h2d_bytes_per_step": C.sizeof(rb.abi.RtPushConsts) + C.sizeof(rb.abi.BloomPushConsts) + C.sizeof(rb.abi.TonemappingPushConsts),
            "d2h_bytes_per_step": int(ldr_host.nbytes), "ms_per_step": ms_e2e / K,
-           "note": "per step: rb200_render_batch(host push constants) + rb200_postprocess + RGBA8 frame to pinned host memory "
+           "note": ("per step and rank: rb200_render_batch(host push constants), snapshot of the SUM image, NCCL reduce to rank 0; "
+                    "rank 0: rb200_present_sum (resolve + bloom + tonemap of the reduced copy) + RGBA8 frame to pinned host memory "
+                    if world > 1 else
+                    "per step: rb200_render_batch(host push constants) + rb200_postprocess + RGBA8 frame to pinned host memory ") +
                    "(rb200_read_ldr_async, %d frames in flight = rb200_pipeline_depth, drained inside the timed region); " % depth +
                    "scene upload + BVH build happen once (scene_create_s)"}
     r.close()

@@ -241,6 +241,14 @@ RB200_API int rb200_resolve_sum(RB200Context* ctx, uint32_t numBatches);
 RB200_API int rb200_postprocess(RB200Context* ctx, const RB200BloomPushConsts* bloom,
                                 const RB200TonemappingPushConsts* tonemap);
 
+/* Present a frame from a SUM image without touching the context's accumulation image: resolve `device_sum_rgba32f`
+ * (W*H*4 floats in DEVICE memory: the sum of `numBatches` batch means, e.g. the NCCL reduce of every rank's
+ * rb200_hdr_device_ptr image into a separate buffer; NULL = this context's own image) into a staging image with the
+ * arithmetic of rb200_resolve_sum, then bloom + tonemap into the RGBA8 frame. Asynchronous on the context stream, so a
+ * multi-GPU frame loop needs no host synchronisation between the reduce and the read-back. */
+RB200_API int rb200_present_sum(RB200Context* ctx, const void* device_sum_rgba32f, uint32_t numBatches,
+                                const RB200BloomPushConsts* bloom, const RB200TonemappingPushConsts* tonemap);
+
 /* Read-back (synchronises the stream). `rgba8`: W*H*4 bytes, row 0 = top. `rgba32f`: W*H*4 floats. */
 RB200_API int rb200_read_ldr(RB200Context* ctx, uint8_t* rgba8);
 RB200_API int rb200_read_hdr(RB200Context* ctx, float* rgba32f);

@@ -66,6 +66,15 @@ class Renderer:
         tonemap = tonemap or TonemappingPushConsts(d["exposure"])
         abi.check(self.lib, self.lib.rb200_postprocess(self._ctx, C.byref(bloom), C.byref(tonemap)))
 
+    def present_sum(self, num_batches, device_ptr=None, bloom=None, tonemap=None):
+        """Resolve a SUM image (a device pointer, e.g. the NCCL-reduced copy of every rank's image; None = this context's
+        own) into a staging image and bloom + tonemap it into the RGBA8 frame; the accumulation image is untouched."""
+        d = camera.DEFAULTS
+        bloom = bloom or BloomPushConsts(d["bloom_radius"], d["bloom_threshold"], d["bloom_intensity"])
+        tonemap = tonemap or TonemappingPushConsts(d["exposure"])
+        abi.check(self.lib, self.lib.rb200_present_sum(self._ctx, C.c_void_p(device_ptr) if device_ptr else None, num_batches,
+                                                       C.byref(bloom), C.byref(tonemap)))
+
     def read_hdr(self, out=None):
         out = np.empty((self.height, self.width, 4), np.float32) if out is None else out
         abi.check(self.lib, self.lib.rb200_read_hdr(self._ctx, out.ctypes.data_as(C.c_void_p)))

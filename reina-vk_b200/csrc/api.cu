@@ -307,6 +307,15 @@ RB200_API int rb200_postprocess(RB200Context* ctx, const RB200BloomPushConsts* b
     return postprocess(ctx, bloom, tm);
 }
 
+RB200_API int rb200_present_sum(RB200Context* ctx, const void* device_sum_rgba32f, uint32_t numBatches,
+                                const RB200BloomPushConsts* bloom, const RB200TonemappingPushConsts* tm) {
+    if (!ctx || !bloom || !tm) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    if (numBatches == 0) { set_error("numBatches must be > 0"); return RB200_ERR_INVALID_ARGUMENT; }
+    if (!(bloom->radius > 0.0f)) { set_error("bloom radius must be > 0"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
+    return present_sum(ctx, static_cast<const float4*>(device_sum_rgba32f), numBatches, bloom, tm);
+}
+
 RB200_API int rb200_read_ldr(RB200Context* ctx, uint8_t* rgba8) {
     if (!ctx || !rgba8) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
     RB_CUDA(cudaMemcpyAsync(rgba8, ctx->ldr, (size_t)ctx->width * ctx->height * 4, cudaMemcpyDeviceToHost, ctx->stream));

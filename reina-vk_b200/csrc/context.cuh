@@ -118,6 +118,7 @@ struct RB200Context {
     uint64_t batchCalls = 0;
     std::vector<void*> allocations;
     float4 *ping = nullptr, *pong = nullptr;   // bloom work images
+    float4* resolved = nullptr;                // rb200_present_sum: mean image of a SUM image (allocated on first use)
     uchar4* ldr = nullptr;
     RB200Stats last{}, cumulative{};
     unsigned long long* statsSnap = nullptr;   // cumulative device counters (each lane's per-batch counters are added
@@ -137,5 +138,8 @@ int trace_rays(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const flo
                int any, RB200PrimaryHit* out);
 int resolve_sum(RB200Context* ctx, uint32_t numBatches);
 // post.cu
-int postprocess(RB200Context* ctx, const RB200BloomPushConsts* bloom, const RB200TonemappingPushConsts* tm);
+int postprocess(RB200Context* ctx, const RB200BloomPushConsts* bloom, const RB200TonemappingPushConsts* tm,
+                const float4* source = nullptr);      // source: HDR image to post-process (default: the context's)
+int present_sum(RB200Context* ctx, const float4* deviceSum, uint32_t numBatches, const RB200BloomPushConsts* bloom,
+                const RB200TonemappingPushConsts* tm);
 } // namespace rb200

@@ -166,10 +166,33 @@ static int effective_radius(int k, float sigma) {
     return R;
 }
 
-int postprocess(RB200Context* ctx, const RB200BloomPushConsts* bloom, const RB200TonemappingPushConsts* tm) {
+// the mean image of a SUM image: v * (1 / numBatches), the arithmetic of k_resolve_sum (wavefront.cu), into `dst`
+__global__ void k_resolve_into(const float4* __restrict__ src, float4* __restrict__ dst, uint32_t n, float inv) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = src[i];
+    dst[i] = make_float4(v.x * inv, v.y * inv, v.z * inv, 1.f);
+}
+
+int present_sum(RB200Context* ctx, const float4* deviceSum, uint32_t numBatches, const RB200BloomPushConsts* bloom,
+                const RB200TonemappingPushConsts* tm) {
+    const uint32_t n = ctx->width * ctx->height;
+    if (!ctx->resolved) {
+        cudaError_t e = cudaMalloc(&ctx->resolved, (size_t)n * sizeof(float4));
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (resolved image)"); return RB200_ERR_OUT_OF_MEMORY; }
+        ctx->allocations.push_back(ctx->resolved);
+    }
+    k_resolve_into<<<(n + 255) / 256, 256, 0, ctx->stream>>>(deviceSum ? deviceSum : ctx->wp.image, ctx->resolved, n,
+                                                              1.0f / (float)numBatches);
+    ctx->launches++;
+    RB_CUDA(cudaGetLastError());
+    return postprocess(ctx, bloom, tm, ctx->resolved);
+}
+
+int postprocess(RB200Context* ctx, const RB200BloomPushConsts* bloom, const RB200TonemappingPushConsts* tm, const float4* source) {
     const int W = (int)ctx->width, H = (int)ctx->height;
     cudaStream_t s = ctx->stream;
-    const float4* rt = ctx->wp.image;
+    const float4* rt = source ? source : ctx->wp.image;
     // blurCommon.h.glsl:23-24
     const float radiusPxX = (float)W * bloom->radius / 100.0f, radiusPxY = (float)H * bloom->radius / 100.0f;
     const int kX = (int)(radiusPxX * 3.0f + 0.5f), kY = (int)(radiusPxY * 3.0f + 0.5f);

@@ -408,6 +408,30 @@ def test_frame_loop_as_deep_as_the_lanes_matches_blocking_read(rb):
         assert (want[b] == got[b]).all(), b
 
 
+def test_present_sum_equals_resolve_then_postprocess(rb):
+    """rb200_present_sum (multi-GPU frame loop: resolve + bloom + tonemap of a SUM image into the frame, accumulation
+    image untouched) gives the frame of rb200_resolve_sum + rb200_postprocess, for the context's own image and for an
+    external device buffer holding the same sum."""
+    import torch
+    wl = rb.configs.small_mixed(160, 120, nee=True, samples_per_pixel=2, max_bounces=6)
+    flags = rb.RB200_FLAG_NEE | rb.RB200_FLAG_ACCUM_SUM
+    r = rb.Renderer(wl.width, wl.height, wl.tables, flags=flags)
+    for b in range(3):
+        r.render_batch(wl.push_constants(b))
+    summed = r.read_hdr().copy()
+    r.present_sum(3)
+    own = r.read_ldr().copy()
+    assert (bits(r.read_hdr()) == bits(summed)).all()            # the accumulation image is still the sum
+    ext = torch.as_tensor(r.hdr_device_array(), device="cuda:0").clone()
+    r.present_sum(3, ext.data_ptr())
+    external = r.read_ldr().copy()
+    r.resolve_sum(3)
+    r.postprocess()
+    want = r.read_ldr().copy()
+    r.close()
+    assert (own == want).all() and (external == want).all() and want[..., :3].max() > 0
+
+
 def test_gather_microbenchmark_reports_a_plausible_bandwidth(rb):
     wl = rb.configs.small_mixed(16, 12)
     r = rb.Renderer(wl.width, wl.height, wl.tables)
