@@ -117,9 +117,14 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
         RB_CUDA(cudaStreamCreateWithFlags(&c->laneStream[lane], cudaStreamNonBlocking));
         RB_CUDA(cudaEventCreateWithFlags(&c->accumDone[lane], cudaEventDisableTiming));
     }
+    preload_wave_kernels();
+    preload_post_kernels();
     RB_CUDA(cudaEventCreateWithFlags(&c->frontMark, cudaEventDisableTiming));
     A(c->statsSnap, ST_COUNT);
     A(P.image, N); A(c->ping, N); A(c->pong, N); A(c->ldr, N);
+    // rb200_present_sum's staging image: allocated here in sum mode (cudaMalloc synchronises the device, which would
+    // drain the lanes if it happened on the first presented frame), on first use otherwise
+    if (flags & RB200_FLAG_ACCUM_SUM) A(c->resolved, N);
     for (int lane = 1; lane < RB_LANES; lane++) c->lanes[lane].image = P.image;
 #undef A
     RB_CUDA(cudaMemsetAsync(c->statsSnap, 0, ST_COUNT * sizeof(unsigned long long), c->stream));

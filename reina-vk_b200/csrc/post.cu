@@ -174,13 +174,24 @@ __global__ void k_resolve_into(const float4* __restrict__ src, float4* __restric
     dst[i] = make_float4(v.x * inv, v.y * inv, v.z * inv, 1.f);
 }
 
+// CUDA loads a kernel's code on its first launch, and that load waits for the device to go idle: with several batches
+// in flight the first presented frame would stall the host for a whole pipeline depth. Load everything up front.
+void preload_post_kernels() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_blur_x);
+    cudaFuncGetAttributes(&a, k_blur_y);
+    cudaFuncGetAttributes(&a, k_combine_tonemap);
+    cudaFuncGetAttributes(&a, k_resolve_into);
+    cudaGetLastError();
+}
+
 int present_sum(RB200Context* ctx, const float4* deviceSum, uint32_t numBatches, const RB200BloomPushConsts* bloom,
                 const RB200TonemappingPushConsts* tm) {
     const uint32_t n = ctx->width * ctx->height;
     if (!ctx->resolved) {
         cudaError_t e = cudaMalloc(&ctx->resolved, (size_t)n * sizeof(float4));
         if (e != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (resolved image)"); return RB200_ERR_OUT_OF_MEMORY; }
-        ctx->allocations.push_back(ctx->resolved);
+        ctx->allocations.push_back(ctx->resolved);     // (contexts created with RB200_FLAG_ACCUM_SUM own it from the start)
     }
     k_resolve_into<<<(n + 255) / 256, 256, 0, ctx->stream>>>(deviceSum ? deviceSum : ctx->wp.image, ctx->resolved, n,
                                                               1.0f / (float)numBatches);

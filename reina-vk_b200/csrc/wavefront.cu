@@ -538,6 +538,20 @@ template <class K> static int persistent_grid(K kernel, int numSMs) {
     return numSMs * perSM;
 }
 
+// see preload_post_kernels (post.cu)
+void preload_wave_kernels() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_generate);
+    cudaFuncGetAttributes(&a, k_extend<false>); cudaFuncGetAttributes(&a, k_extend<true>);
+    cudaFuncGetAttributes(&a, k_shadow<false>); cudaFuncGetAttributes(&a, k_shadow<true>);
+    cudaFuncGetAttributes(&a, k_shade<0>); cudaFuncGetAttributes(&a, k_shade<1>); cudaFuncGetAttributes(&a, k_shade<2>);
+    cudaFuncGetAttributes(&a, k_shade<3>); cudaFuncGetAttributes(&a, k_shade<4>);
+    cudaFuncGetAttributes(&a, k_finish);
+    cudaFuncGetAttributes(&a, k_accumulate);
+    cudaFuncGetAttributes(&a, k_resolve_sum);
+    cudaGetLastError();
+}
+
 int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc) {
     if (pc->samplesPerPixel == 0 || pc->maxBounces == 0) { set_error("samplesPerPixel and maxBounces must be > 0"); return RB200_ERR_INVALID_ARGUMENT; }
     if ((ctx->flags & RB200_FLAG_NEE) && scene->numEmissive == 0) {
