@@ -116,7 +116,10 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
         RB_CUDA(cudaMemsetAsync(L.stats, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
         RB_CUDA(cudaStreamCreateWithFlags(&c->laneStream[lane], cudaStreamNonBlocking));
         RB_CUDA(cudaEventCreateWithFlags(&c->accumDone[lane], cudaEventDisableTiming));
+        RB_CUDA(cudaEventCreateWithFlags(&c->staggerEv[lane], cudaEventDisableTiming));
     }
+    c->staggerWave = RB_STAGGER_WAVE;
+    if (const char* e = getenv("RB200_STAGGER_WAVE")) c->staggerWave = atoi(e);
     preload_wave_kernels();
     preload_post_kernels();
     RB_CUDA(cudaEventCreateWithFlags(&c->frontMark, cudaEventDisableTiming));
@@ -143,6 +146,8 @@ RB200_API int rb200_context_destroy(RB200Context* ctx) {
     for (void* p : ctx->allocations) cudaFree(p);
     for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
     for (int lane = 0; lane < RB_LANES; lane++) {
+        if (ctx->waveGraph[lane]) cudaGraphExecDestroy(ctx->waveGraph[lane]);
+        if (ctx->staggerEv[lane]) cudaEventDestroy(ctx->staggerEv[lane]);
         if (ctx->accumDone[lane]) cudaEventDestroy(ctx->accumDone[lane]);
         if (ctx->laneStream[lane]) cudaStreamDestroy(ctx->laneStream[lane]);
     }

@@ -589,6 +589,9 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
         gFinish = persistent_grid(k_finish, ctx->numSMs);
     }
 
+    // lane stagger (see RB200Context::staggerWave): start behind wave `staggerWave` of the previous batch
+    if (ctx->staggerWave >= 0 && hadPrevious && other != lane && !(ctx->flags & RB200_FLAG_TIME_KERNELS))
+        RB_CUDA(cudaStreamWaitEvent(s, ctx->staggerEv[other], 0));
     // snapshot of the cumulative device counters at batch start (device-to-device: no host synchronisation here;
     // rb200_get_stats resolves "last batch" = cumulative - snapshot after synchronising)
     RB_CUDA(cudaMemsetAsync(P.stats, 0, ST_COUNT * sizeof(unsigned long long), s));   // this lane's per-batch counters
@@ -613,31 +616,71 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
     // and the device time of every kernel — for the last batch rendered; it synchronises after every wave
     const char* waveLogPath = timed ? getenv("RB200_WAVE_LOG") : nullptr;
     std::vector<uint32_t> waveCounters;
-    for (uint32_t w = 0; w < maxWaves; w++) {
-        const int p = (int)(w & 1u);
-        RB_CUDA(cudaMemsetAsync(P.counters + (p ^ 1) * CNT_SET, 0, CNT_SET * sizeof(uint32_t), s));
-        tic(1);
-        if (count) k_extend<true><<<gExtendC, BLOCK, 0, s>>>(P, p); else k_extend<false><<<gExtend, BLOCK, 0, s>>>(P, p);
-        toc();
-        tic(6); k_shade<4><<<gShade[4], BLOCK, 0, s>>>(P, p); toc();
-        tic(2); k_shade<0><<<gShade[0], BLOCK, 0, s>>>(P, p); toc();
-        tic(3); k_shade<1><<<gShade[1], BLOCK, 0, s>>>(P, p); toc();
-        tic(4); k_shade<2><<<gShade[2], BLOCK, 0, s>>>(P, p); toc();
-        tic(5); k_shade<3><<<gShade[3], BLOCK, 0, s>>>(P, p); toc();
-        if (ctx->flags & RB200_FLAG_NEE) {
-            tic(7);
-            if (count) k_shadow<true><<<gShadowC, BLOCK, 0, s>>>(P, p); else k_shadow<false><<<gShadow, BLOCK, 0, s>>>(P, p);
+    const bool nee = (ctx->flags & RB200_FLAG_NEE) != 0;
+    const uint32_t staggerWant = ctx->staggerWave < 0 ? 0u : ctx->staggerWave > 0 ? (uint32_t)ctx->staggerWave : std::max(1u, maxWaves * 5u / 32u);
+    const uint32_t staggerAt = timed ? 0u : std::min(staggerWant, maxWaves);
+    bool capturing = false;
+    auto launch_waves = [&]() -> int {
+        for (uint32_t w = 0; w < maxWaves; w++) {
+            const int p = (int)(w & 1u);
+            RB_CUDA(cudaMemsetAsync(P.counters + (p ^ 1) * CNT_SET, 0, CNT_SET * sizeof(uint32_t), s));
+            tic(1);
+            if (count) k_extend<true><<<gExtendC, BLOCK, 0, s>>>(P, p); else k_extend<false><<<gExtend, BLOCK, 0, s>>>(P, p);
             toc();
-            nl++;
+            tic(6); k_shade<4><<<gShade[4], BLOCK, 0, s>>>(P, p); toc();
+            tic(2); k_shade<0><<<gShade[0], BLOCK, 0, s>>>(P, p); toc();
+            tic(3); k_shade<1><<<gShade[1], BLOCK, 0, s>>>(P, p); toc();
+            tic(4); k_shade<2><<<gShade[2], BLOCK, 0, s>>>(P, p); toc();
+            tic(5); k_shade<3><<<gShade[3], BLOCK, 0, s>>>(P, p); toc();
+            if (nee) {
+                tic(7);
+                if (count) k_shadow<true><<<gShadowC, BLOCK, 0, s>>>(P, p); else k_shadow<false><<<gShadow, BLOCK, 0, s>>>(P, p);
+                toc();
+            }
+            tic(8); k_finish<<<gFinish, BLOCK, 0, s>>>(P, p); toc();
+            if (staggerAt && w + 1 == staggerAt)
+                RB_CUDA(cudaEventRecordWithFlags(ctx->staggerEv[lane], s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+            if (waveLogPath) {
+                waveCounters.resize((size_t)(w + 1) * CNT_SET);
+                RB_CUDA(cudaMemcpyAsync(&waveCounters[(size_t)w * CNT_SET], P.counters + p * CNT_SET, CNT_SET * sizeof(uint32_t),
+                                        cudaMemcpyDeviceToHost, s));
+                RB_CUDA(cudaStreamSynchronize(s));
+            }
         }
-        tic(8); k_finish<<<gFinish, BLOCK, 0, s>>>(P, p); toc();
-        nl += 7;
-        if (waveLogPath) {
-            waveCounters.resize((size_t)(w + 1) * CNT_SET);
-            RB_CUDA(cudaMemcpyAsync(&waveCounters[(size_t)w * CNT_SET], P.counters + p * CNT_SET, CNT_SET * sizeof(uint32_t),
-                                    cudaMemcpyDeviceToHost, s));
-            RB_CUDA(cudaStreamSynchronize(s));
+        return RB200_OK;
+    };
+    nl += (uint64_t)maxWaves * (nee ? 8u : 7u);
+    static const bool graphsOff = getenv("RB200_NO_GRAPH") != nullptr;
+    if (timed || count || graphsOff) {
+        const int rc = launch_waves();
+        if (rc != RB200_OK) return rc;
+    } else {
+        // the wave loop as one graph launch: ~1150 stream operations per batch become one, and the device-side gap
+        // between the dependent kernels of a thin wave shrinks
+        WaveParams key = P;
+        key.pc.sampleBatch = 0u;
+        if (!ctx->waveGraph[lane] || ctx->waveGraphWaves[lane] != (maxWaves | (staggerAt << 16)) || memcmp(&key, &ctx->waveGraphKey[lane], sizeof(WaveParams)) != 0) {
+            if (ctx->waveGraph[lane]) { cudaGraphExecDestroy(ctx->waveGraph[lane]); ctx->waveGraph[lane] = nullptr; }
+            cudaGraph_t g = nullptr;
+            RB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            capturing = true;
+            const int rc = launch_waves();
+            capturing = false;
+            const cudaError_t ce = cudaStreamEndCapture(s, &g);
+            if (rc != RB200_OK || ce != cudaSuccess || !g) {
+                cudaGetLastError();
+                if (g) cudaGraphDestroy(g);
+                set_error("CUDA graph capture of the wave loop failed: %s", cudaGetErrorString(ce));
+                return RB200_ERR_CUDA;
+            }
+            const cudaError_t ie = cudaGraphInstantiate(&ctx->waveGraph[lane], g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { cudaGetLastError(); ctx->waveGraph[lane] = nullptr; set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return RB200_ERR_CUDA; }
+            memcpy(&ctx->waveGraphKey[lane], &key, sizeof(WaveParams));
+            ctx->waveGraphWaves[lane] = maxWaves | (staggerAt << 16);
+            ctx->graphCaptures++;
         }
+        RB_CUDA(cudaGraphLaunch(ctx->waveGraph[lane], s));
     }
     if (waveLogPath) {
         if (FILE* f = fopen(waveLogPath, "w")) {
