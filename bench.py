@@ -380,6 +380,16 @@ def roofline(rb, wl, device, stream):
                                         "shade_disney": kt["shadeMs"][3], "miss": kt["shadeMs"][4], "shadow": kt["shadowMs"],
                                         "finish": kt["finishMs"]},
                 "extend_share_of_step": kt["extendMs"] / total_ms if total_ms > 0 else None,
+                # the same figure over the launches whose ray queue held >= half the pixels ("full waves", where the
+                # kernel is throughput-bound; the thin waves behind them are bound by the latency of their longest ray
+                # and run beside other lanes' full waves)
+                "full_waves": ({"launches": kt["extendFullLaunches"], "rays": kt["extendFullRays"], "ms": kt["extendFullMs"],
+                                "extend_mrays_s": kt["extendFullRays"] / (kt["extendFullMs"] * 1e-3) / 1e6,
+                                "achieved": bytes_per_ray * kt["extendFullRays"] / (kt["extendFullMs"] * 1e-3) / 1e9,
+                                "frac": bytes_per_ray * kt["extendFullRays"] / (kt["extendFullMs"] * 1e-3) / 1e9 / peak,
+                                "share_of_extend_rays": kt["extendFullRays"] / max(1, last_t["extendRays"]),
+                                "shadow_mrays_s": (kt["shadowFullRays"] / (kt["shadowFullMs"] * 1e-3) / 1e6) if kt["shadowFullMs"] > 0 else None}
+                               if kt["extendFullMs"] > 0 else None),
                 "l2_gather": {"peak": l2_gather, "unit": "GB/s", "frac": achieved / l2_gather, "table_bytes": table_bytes,
                               "how": "rb200_measure_gather: independent random 80-byte record reads from a warm table of the "
                                      "BVH's size, measured in this run"},

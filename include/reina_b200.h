@@ -182,6 +182,11 @@ typedef struct RB200Stats {
 typedef struct RB200KernelTimes {
     float    generateMs, extendMs, shadeMs[5] /* lambertian, metal, dielectric, disney, miss */, shadowMs, finishMs;
     uint32_t extendLaunches, shadeLaunches, shadowLaunches, finishLaunches;
+    /* the same split by occupancy: launches whose ray queue held at least half the image's pixels ("full waves", where
+     * the kernel is throughput-bound) — the rest of a batch's launches are thin waves bound by single-ray latency */
+    float    extendFullMs, shadowFullMs;
+    uint32_t extendFullLaunches, shadowFullLaunches;
+    uint64_t extendFullRays, shadowFullRays;
 } RB200KernelTimes;
 
 typedef struct RB200BvhInfo {

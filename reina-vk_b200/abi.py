@@ -112,13 +112,17 @@ class BvhInfo(C.Structure):
 class KernelTimes(C.Structure):
     _fields_ = [("generateMs", C.c_float), ("extendMs", C.c_float), ("shadeMs", C.c_float * 5), ("shadowMs", C.c_float),
                 ("finishMs", C.c_float), ("extendLaunches", C.c_uint32), ("shadeLaunches", C.c_uint32),
-                ("shadowLaunches", C.c_uint32), ("finishLaunches", C.c_uint32)]
+                ("shadowLaunches", C.c_uint32), ("finishLaunches", C.c_uint32),
+                ("extendFullMs", C.c_float), ("shadowFullMs", C.c_float), ("extendFullLaunches", C.c_uint32),
+                ("shadowFullLaunches", C.c_uint32), ("extendFullRays", C.c_uint64), ("shadowFullRays", C.c_uint64)]
 
     def as_dict(self):
         return {"generateMs": self.generateMs, "extendMs": self.extendMs, "shadeMs": list(self.shadeMs),
                 "shadowMs": self.shadowMs, "finishMs": self.finishMs, "extendLaunches": self.extendLaunches,
                 "shadeLaunches": self.shadeLaunches, "shadowLaunches": self.shadowLaunches,
-                "finishLaunches": self.finishLaunches}
+                "finishLaunches": self.finishLaunches, "extendFullMs": self.extendFullMs, "shadowFullMs": self.shadowFullMs,
+                "extendFullLaunches": self.extendFullLaunches, "shadowFullLaunches": self.shadowFullLaunches,
+                "extendFullRays": self.extendFullRays, "shadowFullRays": self.shadowFullRays}
 
 
 class PrimaryHit(C.Structure):

@@ -152,6 +152,7 @@ RB200_API int rb200_context_destroy(RB200Context* ctx) {
         if (ctx->laneStream[lane]) cudaStreamDestroy(ctx->laneStream[lane]);
     }
     if (ctx->frontMark) cudaEventDestroy(ctx->frontMark);
+    if (ctx->waveCountsDev) cudaFree(ctx->waveCountsDev);
     for (cudaEvent_t e : ctx->ldrPendingEvents) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ldrEventPool) cudaEventDestroy(e);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -199,6 +200,9 @@ RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB2
     D.numInstances = d->numInstances;
     sc->numEmissive = d->numEmissive;
     sc->hostInstances.assign(d->instances, d->instances + d->numInstances);
+    sc->dev.materialMask = 0u;
+    for (const RB200Instance& in : sc->hostInstances) sc->dev.materialMask |= 1u << (in.materialIdx > 3u ? 3u : in.materialIdx);   // as k_extend bins
+    sc->dev.pad_ = 0u;
 
     // textures: RGBA8 UNORM cudaArrays behind texture objects (point sampled; the bilinear REPEAT filter is applied in fp32)
     std::vector<uint2> sizes;
@@ -430,14 +434,29 @@ RB200_API int rb200_get_kernel_times(RB200Context* ctx, RB200KernelTimes* out) {
     if (!(ctx->flags & RB200_FLAG_TIME_KERNELS)) { set_error("context was not created with RB200_FLAG_TIME_KERNELS"); return RB200_ERR_INVALID_ARGUMENT; }
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     memset(out, 0, sizeof(*out));
+    std::vector<uint32_t> waveCounts((size_t)ctx->waveCountsWaves * 2, 0u);
+    if (ctx->waveCountsDev && ctx->waveCountsWaves)
+        RB_CUDA(cudaMemcpy(waveCounts.data(), ctx->waveCountsDev, waveCounts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    const uint32_t half = ctx->width * ctx->height / 2u;
+    uint32_t extendWave = 0, shadowWave = 0;
     for (size_t i = 0; i < ctx->evClass.size(); i++) {
         float ms = 0.f;
         RB_CUDA(cudaEventElapsedTime(&ms, ctx->evPool[2 * i], ctx->evPool[2 * i + 1]));
         const int c = ctx->evClass[i];
         if (c == 0) out->generateMs += ms;
-        else if (c == 1) { out->extendMs += ms; out->extendLaunches++; }
+        else if (c == 1) {
+            out->extendMs += ms; out->extendLaunches++;
+            const uint32_t n = extendWave < ctx->waveCountsWaves ? waveCounts[2 * (size_t)extendWave] : 0u;
+            if (n >= half) { out->extendFullMs += ms; out->extendFullLaunches++; out->extendFullRays += n; }
+            extendWave++;
+        }
         else if (c >= 2 && c <= 6) { out->shadeMs[c - 2] += ms; out->shadeLaunches++; }
-        else if (c == 7) { out->shadowMs += ms; out->shadowLaunches++; }
+        else if (c == 7) {
+            out->shadowMs += ms; out->shadowLaunches++;
+            const uint32_t n = shadowWave < ctx->waveCountsWaves ? waveCounts[2 * (size_t)shadowWave + 1] : 0u;
+            if (n >= half) { out->shadowFullMs += ms; out->shadowFullLaunches++; out->shadowFullRays += n; }
+            shadowWave++;
+        }
         else { out->finishMs += ms; out->finishLaunches++; }
     }
     return RB200_OK;

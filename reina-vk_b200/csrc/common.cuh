@@ -73,6 +73,8 @@ struct DeviceScene {
     const WideNode* nodes;
     const TriRecord* tris;
     uint32_t numInstances, numTris;
+    uint32_t materialMask;           // bit m: some instance is shaded by material kernel m (0..3); host-side launch filter
+    uint32_t pad_;
 };
 
 struct BuildInput {

@@ -146,6 +146,9 @@ struct RB200Context {
     std::vector<cudaEvent_t> evPool;
     std::vector<int> evClass;                  // class of pair i (events 2i, 2i+1): 0 generate, 1 extend, 2..6 shade, 7 shadow, 8 finish
     size_t evUsed = 0;
+    uint32_t* waveCountsDev = nullptr;         // timing pass: per wave (rays extended, shadow rays), copied from the lane counters
+    uint32_t waveCountsWaves = 0;              // waves of the last timed batch
+    uint32_t waveCountsCap = 0;
 };
 
 namespace rb200 {

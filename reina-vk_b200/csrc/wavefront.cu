@@ -617,10 +617,20 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
     const char* waveLogPath = timed ? getenv("RB200_WAVE_LOG") : nullptr;
     std::vector<uint32_t> waveCounters;
     const bool nee = (ctx->flags & RB200_FLAG_NEE) != 0;
+    if (timed) {
+        if (ctx->waveCountsCap < maxWaves) {
+            if (ctx->waveCountsDev) cudaFree(ctx->waveCountsDev);
+            ctx->waveCountsDev = nullptr; ctx->waveCountsCap = 0;
+            RB_CUDA(cudaMalloc(&ctx->waveCountsDev, (size_t)maxWaves * 2 * sizeof(uint32_t)));
+            ctx->waveCountsCap = maxWaves;
+        }
+        ctx->waveCountsWaves = maxWaves;
+    }
     const uint32_t staggerWant = ctx->staggerWave < 0 ? 0u : ctx->staggerWave > 0 ? (uint32_t)ctx->staggerWave : std::max(1u, maxWaves * 5u / 32u);
     const uint32_t staggerAt = timed ? 0u : std::min(staggerWant, maxWaves);
     bool capturing = false;
-    auto launch_waves = [&]() -> int {
+    const uint32_t mats = P.S.materialMask & 15u;
+    auto launch_waves_on = [&](WaveParams& P, cudaStream_t s, int lane) -> int {
         for (uint32_t w = 0; w < maxWaves; w++) {
             const int p = (int)(w & 1u);
             RB_CUDA(cudaMemsetAsync(P.counters + (p ^ 1) * CNT_SET, 0, CNT_SET * sizeof(uint32_t), s));
@@ -628,16 +638,21 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
             if (count) k_extend<true><<<gExtendC, BLOCK, 0, s>>>(P, p); else k_extend<false><<<gExtend, BLOCK, 0, s>>>(P, p);
             toc();
             tic(6); k_shade<4><<<gShade[4], BLOCK, 0, s>>>(P, p); toc();
-            tic(2); k_shade<0><<<gShade[0], BLOCK, 0, s>>>(P, p); toc();
-            tic(3); k_shade<1><<<gShade[1], BLOCK, 0, s>>>(P, p); toc();
-            tic(4); k_shade<2><<<gShade[2], BLOCK, 0, s>>>(P, p); toc();
-            tic(5); k_shade<3><<<gShade[3], BLOCK, 0, s>>>(P, p); toc();
+            // a material no instance uses has an empty queue in every wave: its kernel is not launched
+            if (mats & 1u) { tic(2); k_shade<0><<<gShade[0], BLOCK, 0, s>>>(P, p); toc(); }
+            if (mats & 2u) { tic(3); k_shade<1><<<gShade[1], BLOCK, 0, s>>>(P, p); toc(); }
+            if (mats & 4u) { tic(4); k_shade<2><<<gShade[2], BLOCK, 0, s>>>(P, p); toc(); }
+            if (mats & 8u) { tic(5); k_shade<3><<<gShade[3], BLOCK, 0, s>>>(P, p); toc(); }
             if (nee) {
                 tic(7);
                 if (count) k_shadow<true><<<gShadowC, BLOCK, 0, s>>>(P, p); else k_shadow<false><<<gShadow, BLOCK, 0, s>>>(P, p);
                 toc();
             }
             tic(8); k_finish<<<gFinish, BLOCK, 0, s>>>(P, p); toc();
+            if (timed && ctx->waveCountsDev) {      // CNT_RAYS / CNT_SHADOW of this wave, device to device: no host wait
+                RB_CUDA(cudaMemcpyAsync(ctx->waveCountsDev + 2 * w, P.counters + p * CNT_SET + CNT_RAYS, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+                RB_CUDA(cudaMemcpyAsync(ctx->waveCountsDev + 2 * w + 1, P.counters + p * CNT_SET + CNT_SHADOW, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+            }
             if (staggerAt && w + 1 == staggerAt)
                 RB_CUDA(cudaEventRecordWithFlags(ctx->staggerEv[lane], s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
             if (waveLogPath) {
@@ -649,7 +664,8 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
         }
         return RB200_OK;
     };
-    nl += (uint64_t)maxWaves * (nee ? 8u : 7u);
+    auto launch_waves = [&]() -> int { return launch_waves_on(P, s, lane); };
+    nl += (uint64_t)maxWaves * ((nee ? 4u : 3u) + (uint32_t)__builtin_popcount(mats));
     static const bool graphsOff = getenv("RB200_NO_GRAPH") != nullptr;
     if (timed || count || graphsOff) {
         const int rc = launch_waves();
@@ -657,28 +673,43 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
     } else {
         // the wave loop as one graph launch: ~1150 stream operations per batch become one, and the device-side gap
         // between the dependent kernels of a thin wave shrinks
-        WaveParams key = P;
-        key.pc.sampleBatch = 0u;
-        if (!ctx->waveGraph[lane] || ctx->waveGraphWaves[lane] != (maxWaves | (staggerAt << 16)) || memcmp(&key, &ctx->waveGraphKey[lane], sizeof(WaveParams)) != 0) {
-            if (ctx->waveGraph[lane]) { cudaGraphExecDestroy(ctx->waveGraph[lane]); ctx->waveGraph[lane] = nullptr; }
-            cudaGraph_t g = nullptr;
-            RB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            capturing = true;
-            const int rc = launch_waves();
-            capturing = false;
-            const cudaError_t ce = cudaStreamEndCapture(s, &g);
-            if (rc != RB200_OK || ce != cudaSuccess || !g) {
-                cudaGetLastError();
-                if (g) cudaGraphDestroy(g);
-                set_error("CUDA graph capture of the wave loop failed: %s", cudaGetErrorString(ce));
-                return RB200_ERR_CUDA;
+        // (Re)capture when the arguments changed. Every lane is captured at once — the other lanes' graphs differ only in
+        // their buffers — so the cost (a few ms per lane) falls on one call instead of on the first call of each lane.
+        const uint32_t wavesKey = maxWaves | (staggerAt << 16);
+        {
+            WaveParams key = P;
+            key.pc.sampleBatch = 0u;
+            if (!ctx->waveGraph[lane] || ctx->waveGraphWaves[lane] != wavesKey || memcmp(&key, &ctx->waveGraphKey[lane], sizeof(WaveParams)) != 0) {
+                const int laneNow = lane;
+                for (int l = 0; l < RB_LANES; l++) {
+                    WaveParams& PL = ctx->lanes[l];
+                    PL.S = P.S; PL.pc = P.pc;
+                    WaveParams k2 = PL;
+                    k2.pc.sampleBatch = 0u;
+                    if (ctx->waveGraph[l] && ctx->waveGraphWaves[l] == wavesKey && memcmp(&k2, &ctx->waveGraphKey[l], sizeof(WaveParams)) == 0) continue;
+                    if (ctx->waveGraph[l]) { cudaGraphExecDestroy(ctx->waveGraph[l]); ctx->waveGraph[l] = nullptr; }
+                    cudaGraph_t g = nullptr;
+                    cudaStream_t sl = ctx->laneStream[l];
+                    RB_CUDA(cudaStreamBeginCapture(sl, cudaStreamCaptureModeThreadLocal));
+                    capturing = true;
+                    const int rc = launch_waves_on(PL, sl, l);
+                    capturing = false;
+                    const cudaError_t ce = cudaStreamEndCapture(sl, &g);
+                    if (rc != RB200_OK || ce != cudaSuccess || !g) {
+                        cudaGetLastError();
+                        if (g) cudaGraphDestroy(g);
+                        set_error("CUDA graph capture of the wave loop failed: %s", cudaGetErrorString(ce));
+                        return RB200_ERR_CUDA;
+                    }
+                    const cudaError_t ie = cudaGraphInstantiate(&ctx->waveGraph[l], g, 0);
+                    cudaGraphDestroy(g);
+                    if (ie != cudaSuccess) { cudaGetLastError(); ctx->waveGraph[l] = nullptr; set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return RB200_ERR_CUDA; }
+                    memcpy(&ctx->waveGraphKey[l], &k2, sizeof(WaveParams));
+                    ctx->waveGraphWaves[l] = wavesKey;
+                    ctx->graphCaptures++;
+                }
+                (void)laneNow;
             }
-            const cudaError_t ie = cudaGraphInstantiate(&ctx->waveGraph[lane], g, 0);
-            cudaGraphDestroy(g);
-            if (ie != cudaSuccess) { cudaGetLastError(); ctx->waveGraph[lane] = nullptr; set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return RB200_ERR_CUDA; }
-            memcpy(&ctx->waveGraphKey[lane], &key, sizeof(WaveParams));
-            ctx->waveGraphWaves[lane] = maxWaves | (staggerAt << 16);
-            ctx->graphCaptures++;
         }
         RB_CUDA(cudaGraphLaunch(ctx->waveGraph[lane], s));
     }
@@ -690,14 +721,17 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
                 const uint32_t* c = &waveCounters[(size_t)w * CNT_SET];
                 fprintf(f, "%u,%u,%u,%u,%u,%u,%u,%u,%u", w, c[CNT_RAYS], c[CNT_MAT0], c[CNT_MAT0 + 1], c[CNT_MAT0 + 2], c[CNT_MAT0 + 3],
                         c[CNT_MISS], c[CNT_SHADOW], c[CNT_END]);
-                const int perWave = (ctx->flags & RB200_FLAG_NEE) ? 8 : 7;
-                for (int k = 0; k < perWave; k++, e += 2) {
+                // event classes: 1 extend, 6 miss, 2..5 materials, 7 shadow, 8 finish; columns in that order
+                float us[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                for (;;) {
+                    const int cls = ctx->evClass[e / 2];
                     float ms = 0.f;
                     cudaEventElapsedTime(&ms, ctx->evPool[e], ctx->evPool[e + 1]);
-                    fprintf(f, ",%.1f", ms * 1000.f);
-                    if (k == 5 && perWave == 7) fprintf(f, ",0.0");
+                    us[cls] = ms * 1000.f;
+                    e += 2;
+                    if (cls == 8) break;
                 }
-                fprintf(f, "\n");
+                fprintf(f, ",%.1f,%.1f,%.1f,%.1f,%.1f,%.1f,%.1f,%.1f\n", us[1], us[6], us[2], us[3], us[4], us[5], us[7], us[8]);
             }
             fclose(f);
         }
