@@ -455,6 +455,35 @@ def test_frame_loop_as_deep_as_the_lanes_matches_blocking_read(rb):
         assert (want[b] == got[b]).all(), b
 
 
+def test_camera_and_sampling_changes_between_batches(ol, rb):
+    """The wave loop of a lane is a cached CUDA graph whose kernel arguments hold the push constants: moving the
+    camera, changing samplesPerPixel / maxBounces or the focus distance between rb200_render_batch calls must be
+    picked up (the reference restarts at sampleBatch 0 after a camera move, src/Reina.cpp:302-309). Every variant on
+    one long-lived context, more calls than lanes, each compared with the oracle."""
+    wl = rb.configs.small_mixed(96, 72, nee=True, samples_per_pixel=2, max_bounces=6)
+    r = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE)
+    sc = ol.OracleScene(wl.tables)
+    tew = wl.tables.totalEmissiveWeight
+    variants = [dict(pos=(0.0, 1.0, 3.9), look=(0.0, 1.0, 0.0), samples_per_pixel=2, max_bounces=6),
+                dict(pos=(0.6, 1.2, 3.5), look=(0.0, 0.9, 0.0), samples_per_pixel=2, max_bounces=6),      # camera move
+                dict(pos=(0.6, 1.2, 3.5), look=(0.0, 0.9, 0.0), samples_per_pixel=3, max_bounces=6),      # more samples
+                dict(pos=(0.6, 1.2, 3.5), look=(0.0, 0.9, 0.0), samples_per_pixel=3, max_bounces=4),      # fewer bounces
+                dict(pos=(0.6, 1.2, 3.5), look=(0.0, 0.9, 0.0), samples_per_pixel=3, max_bounces=4, focus_dist=3.0),
+                dict(pos=(0.0, 1.0, 3.9), look=(0.0, 1.0, 0.0), samples_per_pixel=2, max_bounces=6)]      # back to the first
+    for v in variants:
+        kw = {k: x for k, x in v.items() if k not in ("pos", "look")}
+        hdr_o = np.zeros((wl.height, wl.width, 4), np.float32)
+        for b in range(2):          # sampleBatch 0 overwrites the image, 1 folds into it
+            pc = rb.camera.push_constants(wl.width, wl.height, v["pos"], v["look"], 40.0, total_emissive_weight=tew,
+                                          sample_batch=b, **kw)
+            r.render_batch(pc)
+            hdr_o, cnt = sc.render_batch(wl.width, wl.height, rb.RB200_FLAG_NEE, pc, hdr_o)
+        last, _ = r.stats()
+        assert (bits(r.read_hdr()) == bits(hdr_o)).all(), v
+        assert (last["extendRays"], last["shadowRays"]) == (cnt["extendRays"], cnt["shadowRays"]), v
+    r.close()
+
+
 def test_present_sum_equals_resolve_then_postprocess(rb):
     """rb200_present_sum (multi-GPU frame loop: resolve + bloom + tonemap of a SUM image into the frame, accumulation
     image untouched) gives the frame of rb200_resolve_sum + rb200_postprocess, for the context's own image and for an
