@@ -228,6 +228,14 @@ RB200_API int rb200_context_destroy(RB200Context* ctx);
 /* Use an externally owned cudaStream_t (e.g. the harness's stream) instead of the context's own. */
 RB200_API int rb200_context_set_stream(RB200Context* ctx, void* cuda_stream);
 
+/* Interleaved-tile partition for several GPUs in latency mode: this context traces only the pixels of
+ * the tileSize x tileSize tiles whose row-major index is congruent to tileRank modulo tileCount, every batch of them,
+ * and leaves all other pixels of its image untouched (zero after a rb200_write_hdr of zeros / in a fresh context).
+ * Because every pixel is still accumulated by one context in batch order, the sum (ncclReduce) of the ranks' images is
+ * bit-identical to the single-GPU image; bloom needs the whole image and runs on the root after the reduce.
+ * tileCount = 1 (the default) renders the whole image. Takes effect with the next rb200_render_batch. */
+RB200_API int rb200_context_set_tiles(RB200Context* ctx, uint32_t tileRank, uint32_t tileCount, uint32_t tileSize);
+
 /* Copy the scene tables to the device and build the acceleration structure (LBVH -> 8-wide compressed BVH).
  * The scene is immutable afterwards (the reference never updates an acceleration structure). */
 RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* desc, RB200Scene** out);

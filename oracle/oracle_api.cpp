@@ -57,16 +57,27 @@ ORACLE_API int oracle_scene_destroy(void* scene) { delete (Scene*)scene; return 
 ORACLE_API uint32_t oracle_scene_num_triangles(void* scene) { return (uint32_t)((Scene*)scene)->tris.size(); }
 
 // One sample batch over the whole image (raytrace.rgen.glsl:250-285), rows interleaved over `threads` threads.
+// tileCount > 1: only the pixels of the tiles (tileSize x tileSize, row-major index) congruent to tileRank.
+ORACLE_API int oracle_render_batch_tiles(void* scene, uint32_t W, uint32_t H, uint32_t flags, const RB200RtPushConsts* pc,
+                                         float* hdr, int threads, OracleCounters* counters, uint32_t tileRank,
+                                         uint32_t tileCount, uint32_t tileSize);
 ORACLE_API int oracle_render_batch(void* scene, uint32_t W, uint32_t H, uint32_t flags, const RB200RtPushConsts* pc,
                                    float* hdr, int threads, OracleCounters* counters) {
+    return oracle_render_batch_tiles(scene, W, H, flags, pc, hdr, threads, counters, 0, 1, 32);
+}
+ORACLE_API int oracle_render_batch_tiles(void* scene, uint32_t W, uint32_t H, uint32_t flags, const RB200RtPushConsts* pc,
+                                         float* hdr, int threads, OracleCounters* counters, uint32_t tileRank,
+                                         uint32_t tileCount, uint32_t tileSize) {
     Scene* s = (Scene*)scene;
     if (!s || !pc || !hdr) return -1;
+    if (tileCount == 0 || tileRank >= tileCount || tileSize == 0) return -1;
+    TilePartition tiles; tiles.rank = tileRank; tiles.count = tileCount; tiles.size = tileSize;
     if ((flags & RB200_FLAG_NEE) && s->cdfTriangles.empty()) return RB200_ERR_NO_EMITTER;
     if (threads < 1) threads = 1;
     std::vector<Counters> cnt((size_t)threads);
     std::vector<std::thread> pool;
     for (int t = 0; t < threads; t++)
-        pool.emplace_back([&, t]() { render_rows(*s, W, H, flags, *pc, hdr, (uint32_t)t, H, (uint32_t)threads, &cnt[(size_t)t]); });
+        pool.emplace_back([&, t]() { render_rows(*s, W, H, flags, *pc, hdr, (uint32_t)t, H, (uint32_t)threads, &cnt[(size_t)t], tiles); });
     for (auto& th : pool) th.join();
     if (counters) {
         counters->extendRays = counters->shadowRays = counters->paths = 0;

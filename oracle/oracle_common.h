@@ -90,8 +90,10 @@ static inline float rnd(uint32_t& state) {
 struct Counters { uint64_t extendRays = 0, shadowRays = 0, paths = 0; };
 
 // pathtrace.cpp
+struct TilePartition { uint32_t rank = 0, count = 1, size = 32; };
 void render_rows(const Scene& s, uint32_t W, uint32_t H, uint32_t flags, const RB200RtPushConsts& pc,
-                 float* hdr, uint32_t y0, uint32_t y1, uint32_t ystep, Counters* counters);
+                 float* hdr, uint32_t y0, uint32_t y1, uint32_t ystep, Counters* counters,
+                 const TilePartition& tiles = TilePartition());
 
 } // namespace oracle
 #endif

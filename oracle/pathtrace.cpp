@@ -584,11 +584,15 @@ void starting_ray(const RB200RtPushConsts& pc, float px, float py, float resx, f
 
 // raytrace.rgen.glsl:250-285 for rows y0, y0+ystep, ... < y1
 void render_rows(const Scene& s, uint32_t W, uint32_t H, uint32_t flags, const RB200RtPushConsts& pc,
-                 float* hdr, uint32_t y0, uint32_t y1, uint32_t ystep, Counters* counters) {
+                 float* hdr, uint32_t y0, uint32_t y1, uint32_t ystep, Counters* counters, const TilePartition& tiles) {
     const bool nee = (flags & RB200_FLAG_NEE) != 0;
     const bool sumMode = (flags & RB200_FLAG_ACCUM_SUM) != 0;
+    const uint32_t tilesX = tiles.size ? (W + tiles.size - 1) / tiles.size : 0;
     for (uint32_t y = y0; y < y1; y += ystep) {
         for (uint32_t x = 0; x < W; x++) {
+            // interleaved-tile partition: a rank renders the tiles whose row-major index is congruent
+            // to its rank and leaves every other pixel untouched
+            if (tiles.count > 1 && ((y / tiles.size) * tilesX + x / tiles.size) % tiles.count != tiles.rank) continue;
             Payload pld;
             pld.rngState = (pc.sampleBatch * H + y) * W + x;
             int actual = 0;

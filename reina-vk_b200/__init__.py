@@ -53,6 +53,10 @@ class Renderer:
             self._ctx = None
             raise
 
+    def set_tiles(self, tile_rank, tile_count, tile_size=32):
+        """Interleaved-tile partition (latency mode over several GPUs): trace only this rank's tiles from now on."""
+        abi.check(self.lib, self.lib.rb200_context_set_tiles(self._ctx, tile_rank, tile_count, tile_size))
+
     # -- the hot path ------------------------------------------------------------------------------------
     def render_batch(self, pc):
         abi.check(self.lib, self.lib.rb200_render_batch(self._ctx, self._scene, C.byref(pc)))

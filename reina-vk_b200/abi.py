@@ -152,6 +152,7 @@ SYMBOLS = {
     "rb200_read_ldr": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rb200_read_hdr": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rb200_read_ldr_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rb200_context_set_tiles": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "rb200_present_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(BloomPushConsts), C.POINTER(TonemappingPushConsts)]),
     "rb200_wait_ldr": (C.c_int, [C.c_void_p]),
     "rb200_wait_ldr_pending": (C.c_int, [C.c_void_p, C.c_uint32]),

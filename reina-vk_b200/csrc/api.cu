@@ -96,6 +96,7 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
     for (int lane = 0; lane < RB_LANES; lane++) {
         WaveParams& L = c->lanes[lane];
         L.W = width; L.H = height; L.N = (uint32_t)N; L.flags = flags;
+        L.tileRank = 0; L.tileCount = 1; L.tileSize = 32; L.tilesX = (width + 31u) / 32u;
 #if RB_PAIR_STATE == 2
         // one 128-byte line per slot: float4 records 0..7 = rayO, rayD, thr, st, hit, rad, sum, (spare)
         A(L.rayO.p, 8 * N); L.rayD.p = L.rayO.p + 1; L.thr.p = L.rayO.p + 2; L.st.p = reinterpret_cast<uint4*>(L.rayO.p + 3);
@@ -319,6 +320,16 @@ RB200_API int rb200_postprocess(RB200Context* ctx, const RB200BloomPushConsts* b
     if (!(bloom->radius > 0.0f)) { set_error("bloom radius must be > 0"); return RB200_ERR_INVALID_ARGUMENT; }
     RB_CUDA(cudaSetDevice(ctx->device));
     return postprocess(ctx, bloom, tm);
+}
+
+RB200_API int rb200_context_set_tiles(RB200Context* ctx, uint32_t tileRank, uint32_t tileCount, uint32_t tileSize) {
+    if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
+    if (tileCount == 0 || tileRank >= tileCount || tileSize == 0) { set_error("invalid tile partition: need tileRank < tileCount and tileSize > 0"); return RB200_ERR_INVALID_ARGUMENT; }
+    for (int lane = 0; lane < RB_LANES; lane++) {
+        WaveParams& L = ctx->lanes[lane];
+        L.tileRank = tileRank; L.tileCount = tileCount; L.tileSize = tileSize; L.tilesX = (ctx->width + tileSize - 1u) / tileSize;
+    }
+    return RB200_OK;
 }
 
 RB200_API int rb200_present_sum(RB200Context* ctx, const void* device_sum_rgba32f, uint32_t numBatches,

@@ -72,6 +72,7 @@ struct WaveParams {
     DeviceScene S;
     RB200RtPushConsts pc;
     uint32_t W, H, N, flags;
+    uint32_t tileRank, tileCount, tileSize, tilesX;   // interleaved-tile partition (rb200_context_set_tiles); tileCount 1 = whole image
     StateArr<float4, STATE_STRIDE> rayO;      // xyz origin
     StateArr<float4, STATE_STRIDE> rayD;      // xyz direction (not necessarily unit)
     StateArr<uint4, STATE_STRIDE> hit;        // x = bits(b1), y = bits(b2), z = primitive, w = instance

@@ -104,14 +104,30 @@ __device__ __forceinline__ void begin_path(const WaveParams& P, uint32_t slot, u
 
 __global__ void __launch_bounds__(BLOCK) k_generate(WaveParams P) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot == 0) atomicAdd(&P.stats[ST_PATHS], (unsigned long long)P.N);
+    if (P.tileCount <= 1u) {
+        if (slot == 0) atomicAdd(&P.stats[ST_PATHS], (unsigned long long)P.N);
+        if (slot >= P.N) return;
+        const uint32_t x = slot % P.W, y = slot / P.W;
+        uint32_t rng = (P.pc.sampleBatch * P.H + y) * P.W + x;       // rgen.glsl:259
+        P.sum[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+        begin_path(P, slot, rng, 0u);
+        P.rayQ[0][slot] = slot;
+        if (slot == 0) P.counters[CNT_RAYS] = P.N;
+        return;
+    }
+    // interleaved-tile partition (latency mode): this context traces the pixels of the tiles whose
+    // row-major index is congruent to tileRank; the other pixels are not touched (mean.w < 0 makes k_accumulate
+    // skip them), so the partial images of all ranks add up to the single-GPU image bit for bit
     if (slot >= P.N) return;
     const uint32_t x = slot % P.W, y = slot / P.W;
-    uint32_t rng = (P.pc.sampleBatch * P.H + y) * P.W + x;       // rgen.glsl:259
+    const bool mine = ((y / P.tileSize) * P.tilesX + x / P.tileSize) % P.tileCount == P.tileRank;
+    if (!mine) { P.mean[slot] = make_float4(0.f, 0.f, 0.f, -1.f); return; }     // w < 0: not this rank's pixel
+    uint32_t rng = (P.pc.sampleBatch * P.H + y) * P.W + x;
     P.sum[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
     begin_path(P, slot, rng, 0u);
-    P.rayQ[0][slot] = slot;
-    if (slot == 0) P.counters[CNT_RAYS] = P.N;
+    const uint32_t active = __activemask();
+    queue_push(P.rayQ[0], &P.counters[CNT_RAYS], slot);
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(active) - 1)) atomicAdd(&P.stats[ST_PATHS], (unsigned long long)__popc(active));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -503,6 +519,7 @@ __global__ void __launch_bounds__(BLOCK) k_accumulate(float4* __restrict__ image
     if (i < ST_COUNT) cumStats[i] += laneStats[i];     // batches are folded one at a time, in order: no race
     if (i >= n) return;
     const float4 m = mean[i];
+    if (m.w < 0.f) return;       // tile partition: another rank's pixel
     if (m.w == 0.f) {
         // documented deviation: the reference writes 0/0 and poisons the pixel; batch 0 writes black, later batches keep
         // the previous value, sum mode adds nothing

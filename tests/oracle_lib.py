@@ -41,6 +41,9 @@ def lib():
         _lib.oracle_scene_num_triangles.restype = C.c_uint32
         _lib.oracle_render_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(abi.RtPushConsts),
                                              C.c_void_p, C.c_int, C.POINTER(OracleCounters)]
+        _lib.oracle_render_batch_tiles.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(abi.RtPushConsts),
+                                                   C.c_void_p, C.c_int, C.POINTER(OracleCounters), C.c_uint32, C.c_uint32,
+                                                   C.c_uint32]
         _lib.oracle_trace_primary.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(abi.RtPushConsts), C.c_void_p,
                                               C.c_int, C.c_int]
         _lib.oracle_trace_rays.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
@@ -76,12 +79,13 @@ class OracleScene:
     def num_triangles(self):
         return lib().oracle_scene_num_triangles(self._h)
 
-    def render_batch(self, width, height, flags, pc, hdr=None, threads=NTHREADS):
+    def render_batch(self, width, height, flags, pc, hdr=None, threads=NTHREADS, tiles=(0, 1, 32)):
+        """tiles = (rank, count, tileSize): render only this rank's interleaved tiles, others untouched."""
         if hdr is None:
             hdr = np.zeros((height, width, 4), np.float32)
         cnt = OracleCounters()
-        rc = lib().oracle_render_batch(self._h, width, height, flags, C.byref(pc), hdr.ctypes.data_as(C.c_void_p),
-                                       threads, C.byref(cnt))
+        rc = lib().oracle_render_batch_tiles(self._h, width, height, flags, C.byref(pc), hdr.ctypes.data_as(C.c_void_p),
+                                             threads, C.byref(cnt), tiles[0], tiles[1], tiles[2])
         assert rc == 0, rc
         return hdr, {"extendRays": cnt.extendRays, "shadowRays": cnt.shadowRays, "paths": cnt.paths}
 

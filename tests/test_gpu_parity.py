@@ -484,6 +484,44 @@ def test_camera_and_sampling_changes_between_batches(ol, rb):
     r.close()
 
 
+@pytest.mark.parametrize("count,tile", [(2, 32), (3, 16), (8, 32)])
+def test_interleaved_tiles_add_up_to_the_single_gpu_image_bit_for_bit(ol, rb, count, tile):
+    """SURVEY 8e, latency mode: rank r of N traces the tiles whose row-major index is congruent to r (every batch of
+    them, running average) and leaves the other pixels at zero; the SUM over ranks (what one ncclReduce computes) is
+    bit-identical to the image of one context rendering everything — x + 0 = x — and each rank's image equals the
+    oracle's rendering of the same partition. Ray counters add up too."""
+    wl = rb.configs.small_mixed(200, 150, nee=True, samples_per_pixel=2, max_bounces=6)
+    flags = rb.RB200_FLAG_NEE
+    whole = rb.Renderer(wl.width, wl.height, wl.tables, flags=flags)
+    for b in range(3):
+        whole.render_batch(wl.push_constants(b))
+    want = whole.read_hdr().copy()
+    _, cw = whole.stats()
+    whole.close()
+    sc = ol.OracleScene(wl.tables)
+    total = np.zeros_like(want)
+    rays = 0
+    for rank in range(count):
+        r = rb.Renderer(wl.width, wl.height, wl.tables, flags=flags)
+        r.set_tiles(rank, count, tile)
+        o = np.zeros_like(want)
+        for b in range(3):
+            pc = wl.push_constants(b)
+            r.render_batch(pc)
+            o, _ = sc.render_batch(wl.width, wl.height, flags, pc, o, tiles=(rank, count, tile))
+        part = r.read_hdr()
+        assert (bits(part) == bits(o)).all(), rank
+        _, c = r.stats()
+        rays += c["extendRays"] + c["shadowRays"]
+        total += part                          # disjoint supports: an exact sum
+        r.close()
+    assert (bits(total[..., :3]) == bits(want[..., :3])).all()
+    assert (total[..., 3] == 1).all()
+    assert rays == cw["extendRays"] + cw["shadowRays"]
+    with pytest.raises(rb.RB200Error, match="tile partition"):
+        rb.Renderer(16, 16, wl.tables).set_tiles(2, 2, 32)
+
+
 def test_present_sum_equals_resolve_then_postprocess(rb):
     """rb200_present_sum (multi-GPU frame loop: resolve + bloom + tonemap of a SUM image into the frame, accumulation
     image untouched) gives the frame of rb200_resolve_sum + rb200_postprocess, for the context's own image and for an
