@@ -440,11 +440,14 @@ __device__ __forceinline__ uint32_t shade_slot(const WaveParams& P, const uint32
 #ifndef RB_SHADE_MINBLOCKS
 #define RB_SHADE_MINBLOCKS 1
 #endif
+#ifndef RB_SHADE_BLOCK
+#define RB_SHADE_BLOCK 128       // threads per block of the shading kernels (85-119 registers: smaller blocks pack an SM's register file better)
+#endif
 #ifndef RB_DISNEY_MINBLOCKS
 #define RB_DISNEY_MINBLOCKS 1
 #endif
 template <int MAT>
-__global__ void __launch_bounds__(BLOCK, MAT == 3 ? RB_DISNEY_MINBLOCKS : RB_SHADE_MINBLOCKS) k_shade(WaveParams P, int parity) {
+__global__ void __launch_bounds__(RB_SHADE_BLOCK, MAT == 3 ? RB_DISNEY_MINBLOCKS : RB_SHADE_MINBLOCKS) k_shade(WaveParams P, int parity) {
     uint32_t* cnt = P.counters + parity * CNT_SET;
     uint32_t* cntNext = P.counters + (parity ^ 1) * CNT_SET;
     const uint32_t n = cnt[CNT_MAT0 + MAT];
@@ -549,9 +552,9 @@ __global__ void k_resolve_sum(float4* image, uint32_t n, float inv) {
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-template <class K> static int persistent_grid(K kernel, int numSMs) {
+template <class K> static int persistent_grid(K kernel, int numSMs, int block = BLOCK) {
     int perSM = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, BLOCK, 0) != cudaSuccess || perSM < 1) perSM = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, block, 0) != cudaSuccess || perSM < 1) perSM = 1;
     return numSMs * perSM;
 }
 
@@ -598,11 +601,11 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
         gExtendC = persistent_grid(k_extend<true>, ctx->numSMs);
         gShadow = persistent_grid(k_shadow<false>, ctx->numSMs);
         gShadowC = persistent_grid(k_shadow<true>, ctx->numSMs);
-        gShade[0] = persistent_grid(k_shade<0>, ctx->numSMs);
-        gShade[1] = persistent_grid(k_shade<1>, ctx->numSMs);
-        gShade[2] = persistent_grid(k_shade<2>, ctx->numSMs);
-        gShade[3] = persistent_grid(k_shade<3>, ctx->numSMs);
-        gShade[4] = persistent_grid(k_shade<4>, ctx->numSMs);
+        gShade[0] = persistent_grid(k_shade<0>, ctx->numSMs, RB_SHADE_BLOCK);
+        gShade[1] = persistent_grid(k_shade<1>, ctx->numSMs, RB_SHADE_BLOCK);
+        gShade[2] = persistent_grid(k_shade<2>, ctx->numSMs, RB_SHADE_BLOCK);
+        gShade[3] = persistent_grid(k_shade<3>, ctx->numSMs, RB_SHADE_BLOCK);
+        gShade[4] = persistent_grid(k_shade<4>, ctx->numSMs, RB_SHADE_BLOCK);
         gFinish = persistent_grid(k_finish, ctx->numSMs);
     }
 
@@ -654,12 +657,12 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
             tic(1);
             if (count) k_extend<true><<<gExtendC, BLOCK, 0, s>>>(P, p); else k_extend<false><<<gExtend, BLOCK, 0, s>>>(P, p);
             toc();
-            tic(6); k_shade<4><<<gShade[4], BLOCK, 0, s>>>(P, p); toc();
+            tic(6); k_shade<4><<<gShade[4], RB_SHADE_BLOCK, 0, s>>>(P, p); toc();
             // a material no instance uses has an empty queue in every wave: its kernel is not launched
-            if (mats & 1u) { tic(2); k_shade<0><<<gShade[0], BLOCK, 0, s>>>(P, p); toc(); }
-            if (mats & 2u) { tic(3); k_shade<1><<<gShade[1], BLOCK, 0, s>>>(P, p); toc(); }
-            if (mats & 4u) { tic(4); k_shade<2><<<gShade[2], BLOCK, 0, s>>>(P, p); toc(); }
-            if (mats & 8u) { tic(5); k_shade<3><<<gShade[3], BLOCK, 0, s>>>(P, p); toc(); }
+            if (mats & 1u) { tic(2); k_shade<0><<<gShade[0], RB_SHADE_BLOCK, 0, s>>>(P, p); toc(); }
+            if (mats & 2u) { tic(3); k_shade<1><<<gShade[1], RB_SHADE_BLOCK, 0, s>>>(P, p); toc(); }
+            if (mats & 4u) { tic(4); k_shade<2><<<gShade[2], RB_SHADE_BLOCK, 0, s>>>(P, p); toc(); }
+            if (mats & 8u) { tic(5); k_shade<3><<<gShade[3], RB_SHADE_BLOCK, 0, s>>>(P, p); toc(); }
             if (nee) {
                 tic(7);
                 if (count) k_shadow<true><<<gShadowC, BLOCK, 0, s>>>(P, p); else k_shadow<false><<<gShadow, BLOCK, 0, s>>>(P, p);
