@@ -58,8 +58,21 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
                           // (neighbouring rays do re-use each other's triangles); ray records through L2 only: no change
 #endif
 
+// Where a lane keeps the triangle groups its node steps produce during a chunk (at most RB_CHUNK of them): in local
+// memory, where lanes at different fill levels touch different rows (one L1 wavefront per lane and access), or in shared
+// memory as [entry][lane] (conflict-free, 2 wavefronts per warp access, but 12 KB per block taken from L1).
+// Bit 0: any-hit kernels, bit 1: closest-hit kernels. Measured on B200 (headline scene, per batch): any-hit 18.2 -> 17.0
+// ms, closest-hit 33.5 -> 33.8 ms (it spills 20 bytes under the 64-register cap and misses the L1 space more).
+#ifndef RB_TSTACK_SHARED
+#define RB_TSTACK_SHARED 1
+#endif
+template <bool ANY> struct TStackShared { static constexpr bool value = ((RB_TSTACK_SHARED >> (ANY ? 0 : 1)) & 1) != 0; };
+
 // per-warp staging area of the pooled triangle phase
-struct WarpShared {
+template <bool TSTACK> struct WarpTStack { };
+template <> struct WarpTStack<true> { uint2 tstack[RB_CHUNK][32]; };    // per lane: triangle groups of the current chunk
+template <bool ANY>
+struct WarpShared : WarpTStack<TStackShared<ANY>::value> {
     float4 ray[32][3];                    // per lane: (o, tmax), (mx, Sz), (my, bits(kz)) — shear rows of rb_tri.h
     uint32_t work[RB_WORK_CAP];           // triangle index << 5 | owner lane (the build refuses >= 2^27 triangles)
     unsigned long long bestKey[32];       // per owner: min over candidates of (t bits << 32 | global primitive id)
@@ -95,7 +108,12 @@ struct Traversal {
     uint32_t tcount;              // triangles queued in tgroup + tstack
     RayHit best;
     uint2 stack[TRAV_STACK];      // pending node groups (local memory)
-    uint2 tstack[RB_CHUNK];       // triangle groups produced by the node steps of the current chunk
+    // triangle groups produced by the node steps of the current chunk (see RB_TSTACK_SHARED)
+    uint2 tstackLocal[TStackShared<ANY>::value ? 1 : RB_CHUNK];
+    __device__ __forceinline__ uint2& tst(WarpShared<ANY>& ws, int k) {
+        if constexpr (TStackShared<ANY>::value) return ws.tstack[k][threadIdx.x & 31u];
+        else return tstackLocal[k];
+    }
 
     // Measured alternatives for this stack, both slower on B200: (a) the first 6 / 8 / 10 entries in shared memory:
     // -3 / -8 / -8 % closest-hit rays/s — the shared memory comes out of L1 (150 -> 70 KB per SM at 10 entries) and
@@ -132,8 +150,8 @@ struct Traversal {
     }
 
     // next queued triangle index; requires tcount > 0
-    __device__ __forceinline__ uint32_t take_tri() {
-        if (tgroup.y == 0u) tgroup = tstack[--tsp];
+    __device__ __forceinline__ uint32_t take_tri(WarpShared<ANY>& ws) {
+        if (tgroup.y == 0u) tgroup = tst(ws, --tsp);
         const uint32_t ti = 31u - (uint32_t)__clz(tgroup.y);
         tgroup.y &= ~(1u << ti);
         tcount--;
@@ -143,7 +161,7 @@ struct Traversal {
     // Pop the nearest pending child of the current node group and test its 8 children; the triangles it yields are
     // queued on tstack for the warp's pooled triangle phase. Requires want_node().
     __device__ __forceinline__ void node_step(const WideNode* __restrict__ nodes, const TriRecord* __restrict__ tris_for_prefetch,
-                                              uint32_t& nodeVisits) {
+                                              uint32_t& nodeVisits, WarpShared<ANY>& ws) {
         const uint32_t hits = ngroup.y;
         const uint32_t bitIndex = 31u - (uint32_t)__clz(hits);
         const uint32_t base = ngroup.x;
@@ -207,7 +225,7 @@ struct Traversal {
         }
         ngroup.y = (hitmask & 0xFF000000u) | (eim >> 24);
         const uint32_t tmask = hitmask & 0x00FFFFFFu;
-        if (tmask) { tstack[tsp++] = make_uint2(__float_as_uint(n1.y), tmask); tcount += (uint32_t)__popc(tmask); }
+        if (tmask) { tst(ws, tsp++) = make_uint2(__float_as_uint(n1.y), tmask); tcount += (uint32_t)__popc(tmask); }
 #if RB_PREFETCH
         // pull what this ray touches next towards L1 while other warps run: the nearest hit child node and the first
         // queued triangle (the traversal kernels stall mostly on these dependent fetches)
@@ -238,10 +256,11 @@ __device__ __forceinline__ unsigned long long hit_key(float t, uint32_t gid) {
 template <bool ANY, bool COUNT, class Fetch, class Commit>
 __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, const TriRecord* __restrict__ tris,
                                             uint32_t n, uint32_t* cursor, Fetch fetch, Commit commit,
-                                            uint32_t& nodeVisits, uint32_t& triTests, WarpShared& ws) {
+                                            uint32_t& nodeVisits, uint32_t& triTests, WarpShared<ANY>& ws) {
     const uint32_t lane = threadIdx.x & 31u;
     Traversal<ANY, COUNT> tr;
     tr.tcount = 0;
+
     bool has = false;
     bool exhausted = false;
     uint32_t rayIdx = 0;
@@ -274,7 +293,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
 #pragma unroll 1
             for (int it = 0; it < RB_CHUNK; it++) {
                 if (!tr.want_node() && !tr.pop()) break;
-                tr.node_step(nodes, tris, nodeVisits);
+                tr.node_step(nodes, tris, nodeVisits, ws);
             }
         }
 
@@ -293,7 +312,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
             uint32_t pos = incl - c;
             const unsigned long long seed = has ? hit_key(tr.best.t, tr.best.gid) : ~0ull;
             ws.bestKey[lane] = seed;
-            while (has && tr.tcount > 0u && pos < (uint32_t)RB_WORK_CAP) ws.work[pos++] = (tr.take_tri() << 5) | lane;
+            while (has && tr.tcount > 0u && pos < (uint32_t)RB_WORK_CAP) ws.work[pos++] = (tr.take_tri(ws) << 5) | lane;
             __syncwarp();
             const uint32_t count = min(total, (uint32_t)RB_WORK_CAP);
             for (uint32_t b = 0; b < count; b += 32u) {

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(BLOCK, RB_TRAV_MINBLOCKS) k_extend(WaveParams 
     const uint32_t* __restrict__ q = P.rayQ[parity];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_EXTEND], (unsigned long long)n);
     uint32_t nodeVisits = 0, triTests = 0;
-    __shared__ WarpShared ws[BLOCK / 32];
+    __shared__ WarpShared<false> ws[BLOCK / 32];
     trace_queue<false, COUNT>(
         P.S.nodes, P.S.tris, n, &cnt[CNT_CURSOR_EXTEND],
         [&](uint32_t i, rb_v3& o, rb_v3& d, float& tmax) {
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(BLOCK, RB_TRAV_MINBLOCKS) k_shadow(WaveParams 
     const uint32_t n = cnt[CNT_SHADOW];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_SHADOW], (unsigned long long)n);
     uint32_t nodeVisits = 0, triTests = 0;
-    __shared__ WarpShared ws[BLOCK / 32];
+    __shared__ WarpShared<true> ws[BLOCK / 32];
     trace_queue<true, COUNT>(
         P.S.nodes, P.S.tris, n, &cnt[CNT_CURSOR_SHADOW],
         [&](uint32_t i, rb_v3& o, rb_v3& d, float& tmax) {
@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace_query(const WideNode* nodes, co
                                                        const float4* __restrict__ o, const float4* __restrict__ d,
                                                        RB200PrimaryHit* __restrict__ out, uint32_t* cursor) {
     uint32_t nv = 0, tt = 0;
-    __shared__ WarpShared ws[BLOCK / 32];
+    __shared__ WarpShared<ANY> ws[BLOCK / 32];
     trace_queue<ANY, false>(
         nodes, tris, n, cursor,
         [&](uint32_t i, rb_v3& ro, rb_v3& rd, float& tmax) {
