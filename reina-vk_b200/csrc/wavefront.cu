@@ -19,8 +19,11 @@
 namespace rb200 {
 
 static constexpr int BLOCK = 256;
+#ifndef RB_TRAV_BLOCK
+#define RB_TRAV_BLOCK 256        // threads per block of k_extend / k_shadow (with RB_TRAV_MINBLOCKS: 1024 threads per SM at 64 registers)
+#endif
 #ifndef RB_TRAV_MINBLOCKS
-#define RB_TRAV_MINBLOCKS 4      // resident blocks per SM the traversal kernels are compiled for (register cap)
+#define RB_TRAV_MINBLOCKS (1024 / RB_TRAV_BLOCK)      // resident blocks per SM the traversal kernels are compiled for (register cap)
 #endif
 
 // ---------------------------------------------------------------------------------------------------
@@ -134,13 +137,13 @@ __global__ void __launch_bounds__(BLOCK) k_generate(WaveParams P) {
 // extend
 // ---------------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(BLOCK, RB_TRAV_MINBLOCKS) k_extend(WaveParams P, int parity) {
+__global__ void __launch_bounds__(RB_TRAV_BLOCK, RB_TRAV_MINBLOCKS) k_extend(WaveParams P, int parity) {
     uint32_t* cnt = P.counters + parity * CNT_SET;
     const uint32_t n = cnt[CNT_RAYS];
     const uint32_t* __restrict__ q = P.rayQ[parity];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_EXTEND], (unsigned long long)n);
     uint32_t nodeVisits = 0, triTests = 0;
-    __shared__ WarpShared<false> ws[BLOCK / 32];
+    __shared__ WarpShared<false> ws[RB_TRAV_BLOCK / 32];
     trace_queue<false, COUNT>(
         P.S.nodes, P.S.tris, n, &cnt[CNT_CURSOR_EXTEND],
         [&](uint32_t i, rb_v3& o, rb_v3& d, float& tmax) {
@@ -465,12 +468,12 @@ __global__ void __launch_bounds__(RB_SHADE_BLOCK, MAT == 3 ? RB_DISNEY_MINBLOCKS
 // shadow: shadowRayOccluded (nee.h.glsl:126-144) + the radiance update of rgen.glsl:174-177
 // ---------------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(BLOCK, RB_TRAV_MINBLOCKS) k_shadow(WaveParams P, int parity) {
+__global__ void __launch_bounds__(RB_TRAV_BLOCK, RB_TRAV_MINBLOCKS) k_shadow(WaveParams P, int parity) {
     uint32_t* cnt = P.counters + parity * CNT_SET;
     const uint32_t n = cnt[CNT_SHADOW];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_SHADOW], (unsigned long long)n);
     uint32_t nodeVisits = 0, triTests = 0;
-    __shared__ WarpShared<true> ws[BLOCK / 32];
+    __shared__ WarpShared<true> ws[RB_TRAV_BLOCK / 32];
     trace_queue<true, COUNT>(
         P.S.nodes, P.S.tris, n, &cnt[CNT_CURSOR_SHADOW],
         [&](uint32_t i, rb_v3& o, rb_v3& d, float& tmax) {
@@ -597,10 +600,10 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
 
     static int gExtend = 0, gExtendC = 0, gShadow = 0, gShadowC = 0, gShade[5] = {0, 0, 0, 0, 0}, gFinish = 0;
     if (!gExtend) {
-        gExtend = persistent_grid(k_extend<false>, ctx->numSMs);
-        gExtendC = persistent_grid(k_extend<true>, ctx->numSMs);
-        gShadow = persistent_grid(k_shadow<false>, ctx->numSMs);
-        gShadowC = persistent_grid(k_shadow<true>, ctx->numSMs);
+        gExtend = persistent_grid(k_extend<false>, ctx->numSMs, RB_TRAV_BLOCK);
+        gExtendC = persistent_grid(k_extend<true>, ctx->numSMs, RB_TRAV_BLOCK);
+        gShadow = persistent_grid(k_shadow<false>, ctx->numSMs, RB_TRAV_BLOCK);
+        gShadowC = persistent_grid(k_shadow<true>, ctx->numSMs, RB_TRAV_BLOCK);
         gShade[0] = persistent_grid(k_shade<0>, ctx->numSMs, RB_SHADE_BLOCK);
         gShade[1] = persistent_grid(k_shade<1>, ctx->numSMs, RB_SHADE_BLOCK);
         gShade[2] = persistent_grid(k_shade<2>, ctx->numSMs, RB_SHADE_BLOCK);
@@ -655,7 +658,7 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
             const int p = (int)(w & 1u);
             RB_CUDA(cudaMemsetAsync(P.counters + (p ^ 1) * CNT_SET, 0, CNT_SET * sizeof(uint32_t), s));
             tic(1);
-            if (count) k_extend<true><<<gExtendC, BLOCK, 0, s>>>(P, p); else k_extend<false><<<gExtend, BLOCK, 0, s>>>(P, p);
+            if (count) k_extend<true><<<gExtendC, RB_TRAV_BLOCK, 0, s>>>(P, p); else k_extend<false><<<gExtend, RB_TRAV_BLOCK, 0, s>>>(P, p);
             toc();
             tic(6); k_shade<4><<<gShade[4], RB_SHADE_BLOCK, 0, s>>>(P, p); toc();
             // a material no instance uses has an empty queue in every wave: its kernel is not launched
@@ -665,7 +668,7 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
             if (mats & 8u) { tic(5); k_shade<3><<<gShade[3], RB_SHADE_BLOCK, 0, s>>>(P, p); toc(); }
             if (nee) {
                 tic(7);
-                if (count) k_shadow<true><<<gShadowC, BLOCK, 0, s>>>(P, p); else k_shadow<false><<<gShadow, BLOCK, 0, s>>>(P, p);
+                if (count) k_shadow<true><<<gShadowC, RB_TRAV_BLOCK, 0, s>>>(P, p); else k_shadow<false><<<gShadow, RB_TRAV_BLOCK, 0, s>>>(P, p);
                 toc();
             }
             tic(8); k_finish<<<gFinish, BLOCK, 0, s>>>(P, p); toc();
