@@ -58,21 +58,42 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
                           // (neighbouring rays do re-use each other's triangles); ray records through L2 only: no change
 #endif
 
-// Where a lane keeps the triangle groups its node steps produce during a chunk (at most RB_CHUNK of them): in local
-// memory, where lanes at different fill levels touch different rows (one L1 wavefront per lane and access), or in shared
-// memory as [entry][lane] (conflict-free, 2 wavefronts per warp access, but 12 KB per block taken from L1).
-// Bit 0: any-hit kernels, bit 1: closest-hit kernels. Measured on B200 (headline scene, per batch): any-hit 18.2 -> 17.0
-// ms, closest-hit 33.5 -> 33.8 ms (it spills 20 bytes under the 64-register cap and misses the L1 space more).
+// Where a lane keeps (a) the triangle groups its node steps produce during a chunk (at most RB_CHUNK) and (b) its stack
+// of pending node groups. In local memory, lanes at different fill levels touch different rows — one L1 wavefront per
+// lane and access; local memory was half of the traversal kernels' L1 data-pipe wavefronts (the busiest unit, 67 % of its
+// peak) and its lines compete with nodes and triangles for L1. In shared memory as [entry][lane] an access is
+// conflict-free (2 wavefronts per warp), at 256 B per entry and warp taken from L1.
+// Measured on B200 (headline scene, ms per batch, 4 lanes; Mrays/s of the whole step):
+//   everything local                                        extend 33.5  shadow 18.2   1962
+//   (a) shared, any-hit only                                       33.4         17.0   1972
+//   (a) shared any-hit + first 4 of (b) shared any-hit             33.5         15.7   1986
+//   ... + first 4 / 6 of (b) shared closest-hit, (a) local         33.8 / 33.3  15.7   2003 / 2025
+//   (a) and first 4 of (b) shared in both kernels (default)        29.4         15.7   2232
+//   ... first 6 of (b) in closest-hit (50.6 KB per block)          30.1         15.6   2090
+//   first 6 / 8 of (b) any-hit (> 48 KB per block)                 33.3         16.7   1835
+// Either half alone does nothing for the closest-hit kernel (the other half keeps L1 busy); blocks beyond ~47 KB leave
+// no shared memory for the other lanes' kernels and the step slows down although the kernel itself does not.
+// RB_TSTACK_SHARED: bit 0 any-hit kernels, bit 1 closest-hit kernels.
 #ifndef RB_TSTACK_SHARED
-#define RB_TSTACK_SHARED 1
+#define RB_TSTACK_SHARED 3
 #endif
 template <bool ANY> struct TStackShared { static constexpr bool value = ((RB_TSTACK_SHARED >> (ANY ? 0 : 1)) & 1) != 0; };
+// The first RB_STACK_SHARED_* entries of the node-group stack live in shared memory, deeper ones in local memory.
+#ifndef RB_STACK_SHARED_ANY
+#define RB_STACK_SHARED_ANY 4
+#endif
+#ifndef RB_STACK_SHARED_CLOSEST
+#define RB_STACK_SHARED_CLOSEST 4
+#endif
+template <bool ANY> struct StackShared { static constexpr int value = ANY ? RB_STACK_SHARED_ANY : RB_STACK_SHARED_CLOSEST; };
 
 // per-warp staging area of the pooled triangle phase
 template <bool TSTACK> struct WarpTStack { };
 template <> struct WarpTStack<true> { uint2 tstack[RB_CHUNK][32]; };    // per lane: triangle groups of the current chunk
+template <int K> struct WarpStack { uint2 nstack[K][32]; };
+template <> struct WarpStack<0> { };
 template <bool ANY>
-struct WarpShared : WarpTStack<TStackShared<ANY>::value> {
+struct WarpShared : WarpTStack<TStackShared<ANY>::value>, WarpStack<StackShared<ANY>::value> {
     float4 ray[32][3];                    // per lane: (o, tmax), (mx, Sz), (my, bits(kz)) — shear rows of rb_tri.h
     uint32_t work[RB_WORK_CAP];           // triangle index << 5 | owner lane (the build refuses >= 2^27 triangles)
     unsigned long long bestKey[32];       // per owner: min over candidates of (t bits << 32 | global primitive id)
@@ -115,12 +136,16 @@ struct Traversal {
         else return tstackLocal[k];
     }
 
-    // Measured alternatives for this stack, both slower on B200: (a) the first 6 / 8 / 10 entries in shared memory:
-    // -3 / -8 / -8 % closest-hit rays/s — the shared memory comes out of L1 (150 -> 70 KB per SM at 10 entries) and
-    // the node / triangle stream needs it more; (b) the newest entry cached in registers and refilled from local memory
-    // when consumed: -9 % (two more live registers under the 64-register cap, and the refill is waited for by the very
-    // next push). Pops waiting for their local-memory load are ~12 % of the stall samples of r01f.
-    __device__ __forceinline__ void push(const uint2 v) { stack[sp++] = v; }
+    // History: with the triangle-group list still in local memory, putting the first 6 / 8 / 10 entries of this stack in
+    // shared memory measured -3 / -8 / -8 % (closest hit) and a register-cached top entry -9 %; together with a shared
+    // triangle-group list the first 4 entries in shared memory give +17 % (see RB_TSTACK_SHARED above).
+    __device__ __forceinline__ void push(const uint2 v, WarpShared<ANY>& ws) {
+        constexpr int K = StackShared<ANY>::value;
+        if constexpr (K > 0) {
+            if (sp < K) ws.nstack[sp][threadIdx.x & 31u] = v; else stack[sp - K] = v;
+            sp++;
+        } else stack[sp++] = v;
+    }
 
     __device__ __forceinline__ void init(const rb_v3 org, const rb_v3 d, const float tmax_, float4* rayStage) {
         o = org; tmax = tmax_;
@@ -143,9 +168,12 @@ struct Traversal {
     __device__ __forceinline__ bool stack_empty() const { return sp == 0; }
 
     // No node group current: take the next one from the stack. Returns false when no node work is left.
-    __device__ __forceinline__ bool pop() {
+    __device__ __forceinline__ bool pop(WarpShared<ANY>& ws) {
         if (sp == 0) return false;
-        ngroup = stack[--sp];
+        constexpr int K = StackShared<ANY>::value;
+        --sp;
+        if constexpr (K > 0) { if (sp < K) ngroup = ws.nstack[sp][threadIdx.x & 31u]; else ngroup = stack[sp - K]; }
+        else ngroup = stack[sp];
         return true;
     }
 
@@ -166,7 +194,7 @@ struct Traversal {
         const uint32_t bitIndex = 31u - (uint32_t)__clz(hits);
         const uint32_t base = ngroup.x;
         ngroup.y &= ~(1u << bitIndex);
-        if (ngroup.y > 0x00FFFFFFu) push(ngroup);
+        if (ngroup.y > 0x00FFFFFFu) push(ngroup, ws);
         const uint32_t slot = (bitIndex - 24u) ^ oct_inv;
         const uint32_t rel = __popc(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
         const float4* np = reinterpret_cast<const float4*>(nodes + (base + rel));
@@ -292,7 +320,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
         if (has) {
 #pragma unroll 1
             for (int it = 0; it < RB_CHUNK; it++) {
-                if (!tr.want_node() && !tr.pop()) break;
+                if (!tr.want_node() && !tr.pop(ws)) break;
                 tr.node_step(nodes, tris, nodeVisits, ws);
             }
         }

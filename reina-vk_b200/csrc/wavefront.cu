@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(RB_TRAV_BLOCK, RB_TRAV_MINBLOCKS) k_extend(Wav
     const uint32_t* __restrict__ q = P.rayQ[parity];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_EXTEND], (unsigned long long)n);
     uint32_t nodeVisits = 0, triTests = 0;
-    __shared__ WarpShared<false> ws[RB_TRAV_BLOCK / 32];
+    extern __shared__ __align__(16) unsigned char rb_dyn_smem[];      // WarpShared<false>[RB_TRAV_BLOCK / 32]: may exceed the 48 KB static limit
+    WarpShared<false>* ws = reinterpret_cast<WarpShared<false>*>(rb_dyn_smem);
     trace_queue<false, COUNT>(
         P.S.nodes, P.S.tris, n, &cnt[CNT_CURSOR_EXTEND],
         [&](uint32_t i, rb_v3& o, rb_v3& d, float& tmax) {
@@ -473,7 +474,8 @@ __global__ void __launch_bounds__(RB_TRAV_BLOCK, RB_TRAV_MINBLOCKS) k_shadow(Wav
     const uint32_t n = cnt[CNT_SHADOW];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_SHADOW], (unsigned long long)n);
     uint32_t nodeVisits = 0, triTests = 0;
-    __shared__ WarpShared<true> ws[RB_TRAV_BLOCK / 32];
+    extern __shared__ __align__(16) unsigned char rb_dyn_smem[];      // WarpShared<true>[RB_TRAV_BLOCK / 32]
+    WarpShared<true>* ws = reinterpret_cast<WarpShared<true>*>(rb_dyn_smem);
     trace_queue<true, COUNT>(
         P.S.nodes, P.S.tris, n, &cnt[CNT_CURSOR_SHADOW],
         [&](uint32_t i, rb_v3& o, rb_v3& d, float& tmax) {
@@ -555,11 +557,14 @@ __global__ void k_resolve_sum(float4* image, uint32_t n, float inv) {
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-template <class K> static int persistent_grid(K kernel, int numSMs, int block = BLOCK) {
+template <class K> static int persistent_grid(K kernel, int numSMs, int block = BLOCK, size_t dynSmem = 0) {
     int perSM = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, block, 0) != cudaSuccess || perSM < 1) perSM = 1;
+    if (dynSmem) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, block, dynSmem) != cudaSuccess || perSM < 1) perSM = 1;
     return numSMs * perSM;
 }
+static constexpr size_t SMEM_EXTEND = sizeof(WarpShared<false>) * (RB_TRAV_BLOCK / 32);
+static constexpr size_t SMEM_SHADOW = sizeof(WarpShared<true>) * (RB_TRAV_BLOCK / 32);
 
 // see preload_post_kernels (post.cu)
 void preload_wave_kernels() {
@@ -600,10 +605,10 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
 
     static int gExtend = 0, gExtendC = 0, gShadow = 0, gShadowC = 0, gShade[5] = {0, 0, 0, 0, 0}, gFinish = 0;
     if (!gExtend) {
-        gExtend = persistent_grid(k_extend<false>, ctx->numSMs, RB_TRAV_BLOCK);
-        gExtendC = persistent_grid(k_extend<true>, ctx->numSMs, RB_TRAV_BLOCK);
-        gShadow = persistent_grid(k_shadow<false>, ctx->numSMs, RB_TRAV_BLOCK);
-        gShadowC = persistent_grid(k_shadow<true>, ctx->numSMs, RB_TRAV_BLOCK);
+        gExtend = persistent_grid(k_extend<false>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_EXTEND);
+        gExtendC = persistent_grid(k_extend<true>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_EXTEND);
+        gShadow = persistent_grid(k_shadow<false>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_SHADOW);
+        gShadowC = persistent_grid(k_shadow<true>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_SHADOW);
         gShade[0] = persistent_grid(k_shade<0>, ctx->numSMs, RB_SHADE_BLOCK);
         gShade[1] = persistent_grid(k_shade<1>, ctx->numSMs, RB_SHADE_BLOCK);
         gShade[2] = persistent_grid(k_shade<2>, ctx->numSMs, RB_SHADE_BLOCK);
@@ -658,7 +663,7 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
             const int p = (int)(w & 1u);
             RB_CUDA(cudaMemsetAsync(P.counters + (p ^ 1) * CNT_SET, 0, CNT_SET * sizeof(uint32_t), s));
             tic(1);
-            if (count) k_extend<true><<<gExtendC, RB_TRAV_BLOCK, 0, s>>>(P, p); else k_extend<false><<<gExtend, RB_TRAV_BLOCK, 0, s>>>(P, p);
+            if (count) k_extend<true><<<gExtendC, RB_TRAV_BLOCK, SMEM_EXTEND, s>>>(P, p); else k_extend<false><<<gExtend, RB_TRAV_BLOCK, SMEM_EXTEND, s>>>(P, p);
             toc();
             tic(6); k_shade<4><<<gShade[4], RB_SHADE_BLOCK, 0, s>>>(P, p); toc();
             // a material no instance uses has an empty queue in every wave: its kernel is not launched
@@ -668,7 +673,7 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
             if (mats & 8u) { tic(5); k_shade<3><<<gShade[3], RB_SHADE_BLOCK, 0, s>>>(P, p); toc(); }
             if (nee) {
                 tic(7);
-                if (count) k_shadow<true><<<gShadowC, RB_TRAV_BLOCK, 0, s>>>(P, p); else k_shadow<false><<<gShadow, RB_TRAV_BLOCK, 0, s>>>(P, p);
+                if (count) k_shadow<true><<<gShadowC, RB_TRAV_BLOCK, SMEM_SHADOW, s>>>(P, p); else k_shadow<false><<<gShadow, RB_TRAV_BLOCK, SMEM_SHADOW, s>>>(P, p);
                 toc();
             }
             tic(8); k_finish<<<gFinish, BLOCK, 0, s>>>(P, p); toc();
@@ -803,7 +808,8 @@ __global__ void __launch_bounds__(BLOCK) k_trace_query(const WideNode* nodes, co
                                                        const float4* __restrict__ o, const float4* __restrict__ d,
                                                        RB200PrimaryHit* __restrict__ out, uint32_t* cursor) {
     uint32_t nv = 0, tt = 0;
-    __shared__ WarpShared<ANY> ws[BLOCK / 32];
+    extern __shared__ __align__(16) unsigned char rb_dyn_smem[];      // WarpShared<ANY>[BLOCK / 32]
+    WarpShared<ANY>* ws = reinterpret_cast<WarpShared<ANY>*>(rb_dyn_smem);
     trace_queue<ANY, false>(
         nodes, tris, n, cursor,
         [&](uint32_t i, rb_v3& ro, rb_v3& rd, float& tmax) {
@@ -833,8 +839,11 @@ static int run_query(RB200Context* ctx, const RB200Scene* scene, uint32_t n, con
     RB_CUDA(cudaMalloc(&dCursor, sizeof(uint32_t)));
     RB_CUDA(cudaMemsetAsync(dCursor, 0, sizeof(uint32_t), ctx->stream));
     const int grid = (int)std::min<uint64_t>((n + BLOCK - 1) / BLOCK, (uint64_t)ctx->numSMs * 8);
-    if (any) k_trace_query<true><<<grid, BLOCK, 0, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut, dCursor);
-    else k_trace_query<false><<<grid, BLOCK, 0, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut, dCursor);
+    constexpr size_t smAny = sizeof(WarpShared<true>) * (BLOCK / 32), smClosest = sizeof(WarpShared<false>) * (BLOCK / 32);
+    RB_CUDA(cudaFuncSetAttribute(k_trace_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smAny));
+    RB_CUDA(cudaFuncSetAttribute(k_trace_query<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smClosest));
+    if (any) k_trace_query<true><<<grid, BLOCK, smAny, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut, dCursor);
+    else k_trace_query<false><<<grid, BLOCK, smClosest, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut, dCursor);
     ctx->launches++;
     RB_CUDA(cudaGetLastError());
     RB_CUDA(cudaMemcpyAsync(out, dOut, (size_t)n * sizeof(RB200PrimaryHit), cudaMemcpyDeviceToHost, ctx->stream));
