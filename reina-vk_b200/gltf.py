@@ -24,7 +24,7 @@ an accident of that call, not a specification. Rules of this importer where the 
   * TANGENT absent: per-vertex tangent frames from the UV derivatives, the importer's own rule (meshes._tangent_frames);
   * TRS node transforms are composed in float64 (T * R * S, quaternion -> matrix by the standard formula), products
     are accumulated in float64 in a fixed order and rounded to float32 once per instance;
-  * images: PNG only (the texture ingest decodes PNG; JPEG is refused loudly);
+  * images: PNG and baseline JPEG (progressive / CMYK JPEG are refused loudly);
   * primitive modes other than TRIANGLES and sparse accessors are refused loudly.
 The C++ host (host/gltf.cpp) implements the same rules; tests/test_gltf.py checks both yield identical tables.
 """
@@ -279,11 +279,16 @@ def addMeshesToScene(scene, meshIdToPrimitives):
     return {mi: [scene.defineObject(p.toModelData()) for p in prims] for mi, prims in meshIdToPrimitives.items()}
 
 
-def _decode_png(data, flip, name):
+def _decode_image(data, flip, name):
+    """PNG or baseline JPEG, by signature (the C++ host decodes both itself: host/texture.cpp, host/jpeg.cpp; its JPEG
+    path follows the IJG integer pipeline, i.e. it yields PIL's bytes)."""
     from PIL import Image
-    if data[:8] != b"\x89PNG\r\n\x1a\n":
-        raise RuntimeError("Could not load image at path: " + name + ": not a PNG (only PNG textures are supported)")
-    img = np.asarray(Image.open(io.BytesIO(data)).convert("RGBA"), np.uint8)
+    if data[:8] != b"\x89PNG\r\n\x1a\n" and data[:3] != b"\xff\xd8\xff":
+        raise RuntimeError("Could not load image at path: " + name + ": neither a PNG nor a JPEG file")
+    im = Image.open(io.BytesIO(data))
+    if im.format == "JPEG" and (im.mode == "CMYK" or getattr(im, "info", {}).get("progressive")):
+        raise RuntimeError("Could not load image at path: " + name + ": unsupported JPEG (progressive or CMYK)")
+    img = np.asarray(im.convert("RGBA"), np.uint8)
     return np.ascontiguousarray(img[::-1] if flip else img)
 
 
@@ -297,14 +302,14 @@ def addTexturesToScene(asset, scene):
             if not os.path.exists(p):
                 raise RuntimeError("Could not load image at path: " + p)
             with open(p, "rb") as f:
-                ids[i] = scene.defineTexture(_decode_png(f.read(), True, p))
+                ids[i] = scene.defineTexture(_decode_image(f.read(), True, p))
         elif "uri" in img:
-            ids[i] = scene.defineTexture(_decode_png(_decode_data_uri(img["uri"]), False, "image %d" % i))
+            ids[i] = scene.defineTexture(_decode_image(_decode_data_uri(img["uri"]), False, "image %d" % i))
         elif "bufferView" in img:
             bv = doc["bufferViews"][img["bufferView"]]
             buf = asset.buffers[bv["buffer"]]
             off = int(bv.get("byteOffset", 0))
-            ids[i] = scene.defineTexture(_decode_png(buf[off: off + int(bv["byteLength"])], False, "image %d" % i))
+            ids[i] = scene.defineTexture(_decode_image(buf[off: off + int(bv["byteLength"])], False, "image %d" % i))
         else:
             raise RuntimeError("Could not parse texture; internal gLTF data type not supported")
     return ids

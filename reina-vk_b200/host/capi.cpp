@@ -120,6 +120,16 @@ int rbhost_png_load(const char* path, int flip, uint8_t* out, uint64_t capacity,
     });
 }
 
+// decodes a PNG or JPEG file (by signature) to RGBA8
+int rbhost_image_load(const char* path, int flip, uint8_t* out, uint64_t capacity, uint32_t* width, uint32_t* height) {
+    return guarded([&] {
+        Image8 img = load_image_rgba8(path, flip != 0);
+        *width = uint32_t(img.width);
+        *height = uint32_t(img.height);
+        std::memcpy(out, img.rgba.data(), img.rgba.size() < capacity ? img.rgba.size() : capacity);
+    });
+}
+
 // Drives SaveManager + FrameClock through `frames` frames of `spp` samples, `secondsPerFrame` apart, in the order of
 // the render loop (save check, then markFrame). Writes "frame:filename\n" lines into `out`.
 int rbhost_save_schedule(const int32_t* saveSamples, uint32_t nSamples, const double* saveTimes, uint32_t nTimes,

@@ -545,10 +545,7 @@ std::map<long, int> add_textures(const Asset& a, Scene& scene) {
         const Json& img = images->at(i);
         const std::string name = "image " + std::to_string(i);
         auto decode = [&](const uint8_t* data, size_t size, bool flip, const std::string& nm) {
-            static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
-            if (size < 8 || std::memcmp(data, sig, 8) != 0)
-                throw std::runtime_error("Could not load image at path: " + nm + ": not a PNG (only PNG textures are supported)");
-            return decode_png_rgba8(data, size, flip, nm);
+            return decode_image_rgba8(data, size, flip, nm);      // PNG or baseline JPEG, by signature
         };
         if (const Json* uri = img.find("uri")) {
             const std::string& u = uri->string();

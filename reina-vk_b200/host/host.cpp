@@ -96,9 +96,9 @@ Scene make_obj_scene(const std::vector<ObjRequest>& objs, bool addLight) {
             std::fprintf(stderr, "warning: %s has no texture coordinates; tangents are zero and Disney shading will be NaN on it "
                                  "(same as the reference, src/scene/Models.cpp:144-152)\n", o.path.c_str());
         Material m = o.material;
-        if (!o.texturePath.empty()) m.textureID = int(s.defineTexture(load_png_rgba8(o.texturePath, true)));
-        if (!o.normalMapPath.empty()) m.normalMapID = int(s.defineTexture(load_png_rgba8(o.normalMapPath, true)));
-        if (!o.bumpMapPath.empty()) m.bumpMapID = int(s.defineTexture(load_png_rgba8(o.bumpMapPath, true)));
+        if (!o.texturePath.empty()) m.textureID = int(s.defineTexture(load_image_rgba8(o.texturePath, true)));
+        if (!o.normalMapPath.empty()) m.normalMapID = int(s.defineTexture(load_image_rgba8(o.normalMapPath, true)));
+        if (!o.bumpMapPath.empty()) m.bumpMapID = int(s.defineTexture(load_image_rgba8(o.bumpMapPath, true)));
         s.addObject(md, identity(), m);
     }
     if (addLight) s.addObject(cornell_light(), identity(), light_material());

@@ -27,9 +27,9 @@ static void usage() {
         "  --material NAME      material of the following --obj: lambertian | metal | dielectric | disney (default lambertian)\n"
         "  --albedo R,G,B       albedo of the following --obj (default 0.8,0.8,0.8)\n"
         "  --roughness X  --ior X  --metallic X     parameters of the following --obj\n"
-        "  --texture FILE       PNG albedo texture of the following --obj (flipped vertically like the reference's file textures)\n"
-        "  --normal-map FILE    PNG tangent-space normal map of the following --obj\n"
-        "  --bump-map FILE      PNG height map of the following --obj (parallax mapping; black = surface, white = deepest)\n"
+        "  --texture FILE       PNG / JPEG albedo texture of the following --obj (flipped vertically like the reference's file textures)\n"
+        "  --normal-map FILE    PNG / JPEG tangent-space normal map of the following --obj\n"
+        "  --bump-map FILE      PNG / JPEG height map of the following --obj (parallax mapping; black = surface, white = deepest)\n"
         "  --width N --height N image size (overrides [render])\n"
         "  --spp N              stop after N samples per pixel in total\n"
         "  --seconds S          stop after S seconds\n"

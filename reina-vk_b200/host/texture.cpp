@@ -165,4 +165,18 @@ Image8 load_png_rgba8(const std::string& path, bool flip) {
     return decode_png_rgba8(bytes.data(), bytes.size(), flip, path);
 }
 
+Image8 decode_image_rgba8(const uint8_t* data, size_t size, bool flip, const std::string& name) {
+    if (looks_like_jpeg(data, size)) return decode_jpeg_rgba8(data, size, flip, name);
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1A, '\n'};
+    if (size >= 8 && std::memcmp(data, sig, 8) == 0) return decode_png_rgba8(data, size, flip, name);
+    fail(name, "neither a PNG nor a JPEG file");
+}
+
+Image8 load_image_rgba8(const std::string& path, bool flip) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("Could not load image at path: " + path);
+    std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    return decode_image_rgba8(bytes.data(), bytes.size(), flip, path);
+}
+
 }  // namespace rbhost

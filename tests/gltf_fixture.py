@@ -83,7 +83,14 @@ class _Bin:
         return len(self.accessors) - 1
 
 
-def build(tmp_path, external=False):
+def _jpeg_bytes(img, **kw):
+    from PIL import Image
+    b = io.BytesIO()
+    Image.fromarray(img[..., :3], "RGB").save(b, format="JPEG", **kw)
+    return b.getvalue()
+
+
+def build(tmp_path, external=False, jpeg=False):
     """Writes scene.glb (external=False) or scene.gltf + scene.bin + tex0.png (external=True) and returns the path."""
     rng = np.random.RandomState(4)
     B = _Bin()
@@ -120,7 +127,11 @@ def build(tmp_path, external=False):
     nmap = np.zeros((32, 32, 4), np.uint8)
     nmap[..., 0] = 128 + 60 * np.sin(x * 12); nmap[..., 1] = 128 + 60 * np.cos(y * 12); nmap[..., 2] = 230; nmap[..., 3] = 255
     images = []
-    if external:
+    if external and jpeg:       # a JPEG file (4:2:0, flipped on load) and a data-URI JPEG (4:4:4, not flipped)
+        (tmp_path / "tex0.jpg").write_bytes(_jpeg_bytes(tex0, quality=85, subsampling=2))
+        images.append({"uri": "tex0.jpg"})
+        images.append({"uri": "data:image/jpeg;base64," + base64.b64encode(_jpeg_bytes(nmap, quality=95, subsampling=0)).decode()})
+    elif external:
         (tmp_path / "tex0.png").write_bytes(_png_bytes(tex0))
         images.append({"uri": "tex0.png"})
         images.append({"uri": "data:image/png;base64," + base64.b64encode(_png_bytes(nmap)).decode()})

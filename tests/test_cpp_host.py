@@ -426,6 +426,66 @@ def test_cli_renders_cornell_like_the_python_host(host, rb, tmp_path):
     assert (decode_png((tmp_path / "output_8spp.png").read_bytes()) == frames[4]).all()
 
 
+def _image_load(host, path, flip=0):
+    host.rbhost_image_load.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    buf = np.zeros(512 * 512 * 4, np.uint8)
+    w, h = C.c_uint32(), C.c_uint32()
+    if host.rbhost_image_load(str(path).encode(), flip, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(w), C.byref(h)) != 0:
+        raise RuntimeError(err(host))
+    return buf[: w.value * h.value * 4].reshape(h.value, w.value, 4).copy()
+
+
+def test_jpeg_decoder_matches_pil_byte_for_byte(host, tmp_path):
+    """host/jpeg.cpp (baseline Huffman JPEG: IJG integer IDCT, fancy chroma upsampling, fixed-point YCbCr -> RGB) against
+    PIL / libjpeg-turbo: identical bytes for 4:4:4, 4:2:2 and 4:2:0, odd sizes down to 1x1, optimised Huffman tables,
+    restart intervals, grayscale, quality 1..100; file textures flipped vertically like the reference's."""
+    from PIL import Image
+    rng = np.random.default_rng(5)
+
+    def picture(w, h):
+        y, x = np.mgrid[0:h, 0:w]
+        img = np.zeros((h, w, 3), np.uint8)
+        img[..., 0] = (128 + 100 * np.sin(x / 7.0) * np.cos(y / 11.0)).astype(np.uint8)
+        img[..., 1] = ((x * 5 + y * 3) % 256).astype(np.uint8)
+        img[..., 2] = (rng.integers(0, 128, (h, w)) + ((x // 8 + y // 8) % 2) * 100).astype(np.uint8)
+        return img
+    p = tmp_path / "t.jpg"
+    cases = 0
+    for (w, h) in [(64, 48), (37, 29), (16, 16), (1, 1), (3, 5), (130, 67), (17, 33)]:
+        for sub in (0, 1, 2):
+            for kw in (dict(quality=30), dict(quality=75, optimize=True), dict(quality=95, restart_marker_blocks=2), dict(quality=100)):
+                Image.fromarray(picture(w, h)).save(p, subsampling=sub, **kw)
+                want = np.asarray(Image.open(p).convert("RGBA"))
+                assert (_image_load(host, p) == want).all(), (w, h, sub, kw)
+                cases += 1
+        Image.fromarray(picture(w, h)[..., 0]).save(p, quality=80)                 # grayscale
+        assert (_image_load(host, p) == np.asarray(Image.open(p).convert("RGBA"))).all()
+    assert cases == 84
+    Image.fromarray(picture(40, 30)).save(p, quality=90)
+    assert (_image_load(host, p, flip=1) == np.asarray(Image.open(p).convert("RGBA"))[::-1]).all()
+    # the same entry point still decodes PNG
+    q = tmp_path / "t.png"
+    Image.fromarray(picture(20, 10)).save(q)
+    assert (_image_load(host, q) == np.asarray(Image.open(q).convert("RGBA"))).all()
+
+
+def test_jpeg_decoder_refuses_what_it_does_not_support(host, tmp_path):
+    from PIL import Image
+    img = np.random.default_rng(1).integers(0, 256, (24, 24, 3), dtype=np.uint8)
+    p = tmp_path / "bad.jpg"
+    Image.fromarray(img).save(p, progressive=True)
+    with pytest.raises(RuntimeError, match="Could not load image at path: .*progressive JPEG is not supported"):
+        _image_load(host, p)
+    Image.fromarray(img).convert("CMYK").save(p)
+    with pytest.raises(RuntimeError, match="only grayscale and 3-component JPEG"):
+        _image_load(host, p)
+    p.write_bytes(b"GIF89a" + bytes(64))
+    with pytest.raises(RuntimeError, match="neither a PNG nor a JPEG"):
+        _image_load(host, p)
+    with pytest.raises(RuntimeError, match="Could not load image at path"):
+        _image_load(host, tmp_path / "absent.jpg")
+
+
 @pytest.mark.gpu
 def test_cli_textured_obj_like_the_python_host(host, rb, tmp_path):
     """--obj + --texture / --normal-map / --bump-map: the C++ importer and PNG decoder feed the same tables as load_obj +

@@ -86,6 +86,20 @@ def test_cpp_importer_tables_identical_to_python(host, rb, gl, tmp_path, externa
     host.rbhost_tables_free(h)
 
 
+@pytest.mark.filterwarnings("ignore:falling back to UV")
+def test_jpeg_textures_give_identical_tables_too(host, rb, gl, tmp_path):
+    """Most real .glb files embed JPEG images: the C++ host decodes baseline JPEG itself (host/jpeg.cpp, the IJG integer
+    pipeline) and must hand over the same texels PIL gives the Python host."""
+    path, _ = gf.build(tmp_path, external=True, jpeg=True)
+    host.rbhost_tables_gltf.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    h = C.c_void_p()
+    assert host.rbhost_tables_gltf(path.encode(), 1, C.byref(h)) == 0, err(host)
+    py = py_tables(gl.loadScene(path).build(require_emitter=True))
+    assert py["textures"][0].shape == (16, 24, 4) and py["textures"][0][..., :3].std() > 10
+    assert_tables_identical(cpp_tables(host, rb, h), py)
+    host.rbhost_tables_free(h)
+
+
 def _write_gltf(tmp_path, doc, name="bad.gltf"):
     p = tmp_path / name
     p.write_text(json.dumps(doc))
@@ -119,8 +133,8 @@ def test_errors_match_the_reference_messages(host, rb, gl, tmp_path):
     doc["accessors"][0]["count"] = 4
     both(_write_gltf(tmp_path, doc, "overrun.gltf"), "reads past its buffer view")
     doc["accessors"][0]["count"] = 3
-    doc["images"] = [{"uri": "data:image/jpeg;base64," + base64.b64encode(b"\xff\xd8\xff\xe0" + b"0" * 32).decode()}]
-    both(_write_gltf(tmp_path, doc, "jpeg.gltf"), "only PNG textures are supported")
+    doc["images"] = [{"uri": "data:image/gif;base64," + base64.b64encode(b"GIF89a" + b"0" * 32).decode()}]
+    both(_write_gltf(tmp_path, doc, "gif.gltf"), "neither a PNG nor a JPEG file")
     # a truncated GLB
     glb, _ = gf.build(tmp_path)
     raw = open(glb, "rb").read()
