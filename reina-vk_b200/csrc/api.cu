@@ -242,6 +242,25 @@ RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB2
     /* TRAV_MAX_DEPTH = 22: the per-lane traversal stack holds at most 2 groups per tree level */
     if (sc->bvh.maxDepth > (uint32_t)22) { set_error("BVH depth %u exceeds the traversal stack", sc->bvh.maxDepth); rb200_scene_destroy(sc); return RB200_ERR_INVALID_ARGUMENT; }
     D.nodes = sc->bvh.nodes; D.tris = sc->bvh.tris; D.numTris = sc->bvh.numTris;
+    D.shadeBase = nullptr; D.shadeFrame = nullptr;
+#if RB_SHADE_RECORDS
+    {   // per-triangle shading records in leaf order (common.cuh): 192 bytes per triangle
+        float4 *base = nullptr, *frame = nullptr;
+        const size_t n = std::max<size_t>(D.numTris, 1);
+        if (cudaMalloc(&base, n * 4 * sizeof(float4)) != cudaSuccess || cudaMalloc(&frame, n * 8 * sizeof(float4)) != cudaSuccess) {
+            cudaGetLastError();
+            if (base) cudaFree(base);
+            set_error("out of device memory (shading records)");
+            rb200_scene_destroy(sc);
+            return RB200_ERR_OUT_OF_MEMORY;
+        }
+        sc->allocations.push_back(base); sc->allocations.push_back(frame);
+        if ((rc = build_shade_records(D, base, frame, s)) != RB200_OK) { rb200_scene_destroy(sc); return rc; }
+        ctx->launches++;
+        D.shadeBase = base; D.shadeFrame = frame;
+        RB_CUDA(cudaStreamSynchronize(s));
+    }
+#endif
 
     // Optional (RB200_L2_PERSIST=1): pin the hierarchy in L2 with a persisting access-policy window over the
     // node+triangle allocation. Every wave streams ~0.6 GB of path state through the 126 MB L2 and evicts about a

@@ -75,7 +75,19 @@ struct DeviceScene {
     uint32_t numInstances, numTris;
     uint32_t materialMask;           // bit m: some instance is shaded by material kernel m (0..3); host-side launch filter
     uint32_t pad_;
+    // Per-triangle shading records in leaf order (index = TriRecord index), built once at scene creation: the floats
+    // getObjectHitInfo gathers through three levels of indirection (instance -> properties -> index tables -> vertex /
+    // frame / uv tables), laid out contiguously. shadeBase: 4 float4 per triangle = object-space v0.xyz|uv0.x,
+    // v1.xyz|uv0.y, v2.xyz|uv1.x, (uv1.y, uv2.x, uv2.y, 0). shadeFrame: 8 float4 = n0.xyz|t0.x, n1.xyz|t0.y,
+    // n2.xyz|t0.z, t1.xyz|b0.x, t2.xyz|b0.y, b1.xyz|b0.z, b2.xyz|0, pad (n / t / b = columns 2 / 0 / 1 of the vertex
+    // TBNs). Null when RB_SHADE_RECORDS is 0.
+    const float4* shadeBase;
+    const float4* shadeFrame;
 };
+
+#ifndef RB_SHADE_RECORDS
+#define RB_SHADE_RECORDS 1
+#endif
 
 struct BuildInput {
     const float4* vertices;

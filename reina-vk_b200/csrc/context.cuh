@@ -162,6 +162,7 @@ int resolve_sum(RB200Context* ctx, uint32_t numBatches);
 // post.cu
 int postprocess(RB200Context* ctx, const RB200BloomPushConsts* bloom, const RB200TonemappingPushConsts* tm,
                 const float4* source = nullptr);      // source: HDR image to post-process (default: the context's)
+int build_shade_records(const DeviceScene& S, float4* base, float4* frame, cudaStream_t stream);
 void preload_post_kernels();
 void preload_wave_kernels();
 int present_sum(RB200Context* ctx, const float4* deviceSum, uint32_t numBatches, const RB200BloomPushConsts* bloom,

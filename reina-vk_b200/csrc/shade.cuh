@@ -174,6 +174,66 @@ __device__ __forceinline__ void hit_info(const DeviceScene& S, const RB200Instan
     }
 }
 
+#if RB_SHADE_RECORDS
+// The same reconstruction from the per-triangle shading record (DeviceScene::shadeBase / shadeFrame): identical
+// floats, identical arithmetic and order, one or two contiguous reads instead of a three-level gather.
+// `tri` is the triangle's slot in leaf order (RayHit::tri), which k_extend stores in the hit record.
+template <bool NEED_TBN>
+__device__ __forceinline__ void hit_info_rec(const DeviceScene& S, const RB200Instance* inst, const RB200InstanceProperties* props,
+                                             uint32_t tri, float a1, float a2, rb_v3 rayDir, Surf& r) {
+    const float4* sb = S.shadeBase + 4 * (size_t)tri;
+    const float4 r0 = __ldg(sb), r1 = __ldg(sb + 1), r2 = __ldg(sb + 2), r3 = __ldg(sb + 3);
+    const rb_v3 v0 = rb_mk3(r0.x, r0.y, r0.z), v1 = rb_mk3(r1.x, r1.y, r1.z), v2 = rb_mk3(r2.x, r2.y, r2.z);
+    const float bx = 1.0f - a1 - a2, by = a1, bz = a2;
+    float M16[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) M16[k] = __ldg(&inst->transform[k]);
+
+    const rb_v3 objectPosition = v0 * bx + v1 * by + v2 * bz;
+    r.worldPosition = rb_m4_point(M16, objectPosition);
+    const rb_v3 ngObj = rb_normalize(rb_cross(v1 - v0, v2 - v0));
+    const bool interp = __ldg(&props->interpNormals) != 0u;
+    float4 f0, f1, f2, f3, f4, f5, f6;
+    rb_v3 c2_0, c2_1, c2_2;
+    if (interp || NEED_TBN) {
+        const float4* sf = S.shadeFrame + 8 * (size_t)tri;
+        f0 = __ldg(sf); f1 = __ldg(sf + 1); f2 = __ldg(sf + 2);
+        if (NEED_TBN) { f3 = __ldg(sf + 3); f4 = __ldg(sf + 4); f5 = __ldg(sf + 5); f6 = __ldg(sf + 6); }
+        c2_0 = rb_mk3(f0.x, f0.y, f0.z); c2_1 = rb_mk3(f1.x, f1.y, f1.z); c2_2 = rb_mk3(f2.x, f2.y, f2.z);
+    }
+    rb_v3 nObj;
+    if (!interp) nObj = ngObj;
+    else nObj = rb_normalize(rb_normalize(c2_0) * bx + rb_normalize(c2_1) * by + rb_normalize(c2_2) * bz);
+
+    if (__ldg(&props->texIndicesOffset) == 0xFFFFFFFFu) r.uv = rb_mk2(0.0f, 0.0f);
+    else r.uv = rb_mk2(r0.w, r1.w) * bx + rb_mk2(r2.w, r3.x) * by + rb_mk2(r3.y, r3.z) * bz;
+
+    const rb_m3 M = rb_m4_upper3(M16);
+    r.worldNormal = rb_normalize(rb_m3_mul(M, nObj));
+    r.worldNormalGeometry = rb_normalize(rb_m3_mul(M, ngObj));
+    r.frontFace = rb_dot(rayDir, r.worldNormalGeometry) < 0.0f;
+    r.worldNormal = rb_faceforward(r.worldNormal, rayDir, r.worldNormalGeometry);
+    r.worldNormalGeometry = rb_faceforward(r.worldNormalGeometry, rayDir, r.worldNormalGeometry);
+
+    if (NEED_TBN) {
+        const rb_v3 t0 = rb_mk3(f0.w, f1.w, f2.w), t1 = rb_mk3(f3.x, f3.y, f3.z), t2 = rb_mk3(f4.x, f4.y, f4.z);
+        const rb_v3 b0 = rb_mk3(f3.w, f4.w, f5.w), b1 = rb_mk3(f5.x, f5.y, f5.z), b2 = rb_mk3(f6.x, f6.y, f6.z);
+        rb_v3 tangent = rb_normalize(t0 * bx + t1 * by + t2 * bz);
+        rb_v3 bitangent = rb_normalize(b0 * bx + b1 * by + b2 * bz);
+        rb_v3 normal = rb_normalize(c2_0 * bx + c2_1 * by + c2_2 * bz);
+        const rb_m3 Nm = rb_m3_inverse_transpose(M);
+        rb_v3 worldT = rb_normalize(rb_m3_mul(M, tangent));
+        rb_v3 worldB = rb_normalize(rb_m3_mul(M, bitangent));
+        rb_v3 worldN = rb_normalize(rb_m3_mul(Nm, normal));
+        worldT = rb_normalize(worldT - worldN * rb_dot(worldN, worldT));
+        worldB = rb_normalize(worldB - worldN * rb_dot(worldN, worldB));
+        r.tbn.c0 = worldT;
+        r.tbn.c1 = worldB * -1.0f;
+        r.tbn.c2 = worldN * (r.frontFace ? 1.0f : -1.0f);
+    }
+}
+#endif
+
 // dielectric.rchit.glsl:14-38 / disney.rchit.glsl:10-34
 __device__ __forceinline__ rb_v3 offset_for_dielectric(rb_v3 p, rb_v3 n, rb_v3 rayDir) {
     return rb_offset_along_normal(p, (rb_dot(n, rayDir) < 0.0f) ? -n : n);

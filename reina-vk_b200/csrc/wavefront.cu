@@ -157,7 +157,11 @@ __global__ void __launch_bounds__(RB_TRAV_BLOCK, RB_TRAV_MINBLOCKS) k_extend(Wav
             uint32_t bin = 4;
             if (h.tri != 0xFFFFFFFFu) {
                 const float4* tp = reinterpret_cast<const float4*>(P.S.tris + h.tri);
+#if RB_SHADE_RECORDS
+                const uint32_t prim = h.tri;       // the shading kernels read the per-triangle record of this slot
+#else
                 const uint32_t prim = __float_as_uint(__ldg(tp).w);
+#endif
                 const uint32_t inst = __float_as_uint(__ldg(tp + 1).w);
                 P.hit[slot] = make_uint4(__float_as_uint(h.b1), __float_as_uint(h.b2), prim, inst);
                 const uint32_t m = __ldg(&P.S.instances[inst].materialIdx);
@@ -286,9 +290,15 @@ __device__ __forceinline__ uint32_t shade_slot(const WaveParams& P, const uint32
     Surf s;
     const bool hasNormalMap = __ldg(&props->normalMapTexID) >= 0;
     const bool needTbn = hasNormalMap || __ldg(&props->bumpMapTexID) >= 0;     // the parallax search runs in tangent space
+#if RB_SHADE_RECORDS
+    if (MAT == 3) hit_info_rec<true>(P.S, inst, props, h.z, a1, a2, rayDir, s);
+    else if (needTbn) hit_info_rec<true>(P.S, inst, props, h.z, a1, a2, rayDir, s);
+    else hit_info_rec<false>(P.S, inst, props, h.z, a1, a2, rayDir, s);
+#else
     if (MAT == 3) hit_info<true>(P.S, inst, props, h.z, a1, a2, rayDir, s);
     else if (needTbn) hit_info<true>(P.S, inst, props, h.z, a1, a2, rayDir, s);
     else hit_info<false>(P.S, inst, props, h.z, a1, a2, rayDir, s);
+#endif
 
     ShadeOut o;
     o.skip = false; o.pdf = 0.0f; o.inside = prevInside;
@@ -565,6 +575,49 @@ template <class K> static int persistent_grid(K kernel, int numSMs, int block = 
 }
 static constexpr size_t SMEM_EXTEND = sizeof(WarpShared<false>) * (RB_TRAV_BLOCK / 32);
 static constexpr size_t SMEM_SHADOW = sizeof(WarpShared<true>) * (RB_TRAV_BLOCK / 32);
+
+// Per-triangle shading records (DeviceScene::shadeBase / shadeFrame): one thread per triangle slot copies exactly the
+// floats hit_info() would gather for that triangle.
+__global__ void k_build_shade_records(DeviceScene S, float4* __restrict__ base, float4* __restrict__ frame) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S.numTris) return;
+    const float4* tp = reinterpret_cast<const float4*>(S.tris + t);
+    const uint32_t prim = __float_as_uint(tp[0].w), inst = __float_as_uint(tp[1].w);
+    const RB200InstanceProperties* props = &S.props[S.instances[inst].instancePropertiesID];
+    const uint32_t ib = 3u * prim + props->indicesOffset;
+    const float4 v0 = S.vertices[S.indices[ib]], v1 = S.vertices[S.indices[ib + 1]], v2 = S.vertices[S.indices[ib + 2]];
+    float2 q0 = make_float2(0.f, 0.f), q1 = q0, q2 = q0;
+    if (props->texIndicesOffset != 0xFFFFFFFFu) {
+        const uint32_t xb = 3u * prim + props->texIndicesOffset;
+        q0 = S.texCoords[S.texIndices[xb]]; q1 = S.texCoords[S.texIndices[xb + 1]]; q2 = S.texCoords[S.texIndices[xb + 2]];
+    }
+    float4* b = base + 4 * (size_t)t;
+    b[0] = make_float4(v0.x, v0.y, v0.z, q0.x);
+    b[1] = make_float4(v1.x, v1.y, v1.z, q0.y);
+    b[2] = make_float4(v2.x, v2.y, v2.z, q1.x);
+    b[3] = make_float4(q1.y, q2.x, q2.y, 0.f);
+    const uint32_t tb = 3u * prim + props->tbnsIndicesOffset;
+    const float* m0 = S.tbns + 9 * (size_t)S.tbnIndices[tb];
+    const float* m1 = S.tbns + 9 * (size_t)S.tbnIndices[tb + 1];
+    const float* m2 = S.tbns + 9 * (size_t)S.tbnIndices[tb + 2];
+    // TBN entry: columns T (0..2), B (3..5), N (6..8)
+    float4* f = frame + 8 * (size_t)t;
+    f[0] = make_float4(m0[6], m0[7], m0[8], m0[0]);
+    f[1] = make_float4(m1[6], m1[7], m1[8], m0[1]);
+    f[2] = make_float4(m2[6], m2[7], m2[8], m0[2]);
+    f[3] = make_float4(m1[0], m1[1], m1[2], m0[3]);
+    f[4] = make_float4(m2[0], m2[1], m2[2], m0[4]);
+    f[5] = make_float4(m1[3], m1[4], m1[5], m0[5]);
+    f[6] = make_float4(m2[3], m2[4], m2[5], 0.f);
+    f[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+int build_shade_records(const DeviceScene& S, float4* base, float4* frame, cudaStream_t stream) {
+    if (S.numTris == 0) return RB200_OK;
+    k_build_shade_records<<<(S.numTris + 255) / 256, 256, 0, stream>>>(S, base, frame);
+    RB_CUDA(cudaGetLastError());
+    return RB200_OK;
+}
 
 // see preload_post_kernels (post.cu)
 void preload_wave_kernels() {
