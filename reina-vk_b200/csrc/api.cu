@@ -188,6 +188,15 @@ RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB2
     U(vertices, reinterpret_cast<const float4*>(d->vertices), d->numVertices);
     U(indices, d->indices, d->numIndices);
     U(props, d->instanceProperties, d->numInstanceProperties);
+    D.instProps = nullptr;
+#if RB_INST_RECORDS
+    {   // the properties of every instance, by instance index (validate_desc checked instancePropertiesID)
+        std::vector<RB200InstanceProperties> perInstance(d->numInstances);
+        for (uint32_t i = 0; i < d->numInstances; i++) perInstance[i] = d->instanceProperties[d->instances[i].instancePropertiesID];
+        U(instProps, perInstance.data(), perInstance.size());
+        RB_CUDA(cudaStreamSynchronize(s));      // perInstance goes out of scope
+    }
+#endif
     U(tbns, d->tbns, 9 * (size_t)d->numTbns);
     U(tbnIndices, d->tbnIndices, d->numTbnIndices);
     U(emissive, d->emissiveMetadata, d->numEmissive);

@@ -83,10 +83,17 @@ struct DeviceScene {
     // TBNs). Null when RB_SHADE_RECORDS is 0.
     const float4* shadeBase;
     const float4* shadeFrame;
+    // InstanceProperties by INSTANCE index (a copy of props[instances[i].instancePropertiesID]): the material kernels
+    // fetch the instance record and its properties side by side instead of one after the other. Null when
+    // RB_INST_RECORDS is 0.
+    const RB200InstanceProperties* instProps;
 };
 
 #ifndef RB_SHADE_RECORDS
 #define RB_SHADE_RECORDS 1
+#endif
+#ifndef RB_INST_RECORDS
+#define RB_INST_RECORDS 1
 #endif
 
 struct BuildInput {

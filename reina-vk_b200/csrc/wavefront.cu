@@ -284,7 +284,11 @@ __device__ __forceinline__ uint32_t shade_slot(const WaveParams& P, const uint32
     const uint4 h = P.hit[slot];
     const float a1 = __uint_as_float(h.x), a2 = __uint_as_float(h.y);
     const RB200Instance* inst = &P.S.instances[h.w];
+#if RB_INST_RECORDS
+    const RB200InstanceProperties* props = &P.S.instProps[h.w];
+#else
     const RB200InstanceProperties* props = &P.S.props[__ldg(&inst->instancePropertiesID)];
+#endif
     const bool prevInside = (flags & F_INSIDE) != 0u;
 
     Surf s;
