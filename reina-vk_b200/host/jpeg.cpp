@@ -39,7 +39,7 @@ struct Component {
     int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0;
     int width = 0, height = 0;            // downsampled size in samples
     int stride = 0, rows = 0;             // plane size, padded to whole MCUs
-    int pred = 0;
+    int64_t pred = 0;
     std::vector<uint8_t> plane;
 };
 
@@ -92,50 +92,55 @@ inline int extend(int v, int n) { return v < (1 << (n - 1)) ? v - (1 << n) + 1 :
 
 inline uint8_t clamp8(int v) { return uint8_t(v < 0 ? 0 : v > 255 ? 255 : v); }
 
-inline int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+// de-quantised coefficients of a valid 8-bit file stay within +-2^15; corrupt data may not
+inline int clamp_coef(int64_t v) { return int(v < -(1 << 24) ? -(1 << 24) : v > (1 << 24) ? (1 << 24) : v); }
 
-// jpeg_idct_islow (IJG jidctint.c): CONST_BITS 13, PASS1_BITS 2
+// jpeg_idct_islow (IJG jidctint.c): CONST_BITS 13, PASS1_BITS 2. 64-bit intermediates: identical to the 32-bit original
+// on every valid file, and free of signed overflow on corrupt ones (coefficients are clamped to +-2^24 by the caller).
 void idct_islow(const int* coef, uint8_t* out, int stride) {
+    using I = int64_t;
+    auto descale = [](I x, int n) -> I { return (x + (I(1) << (n - 1))) >> n; };
+    auto clamp8 = [](I v) -> uint8_t { return uint8_t(v < 0 ? 0 : v > 255 ? 255 : v); };
     enum { C_0_298 = 2446, C_0_390 = 3196, C_0_541 = 4433, C_0_765 = 6270, C_0_899 = 7373, C_1_175 = 9633, C_1_501 = 12299,
            C_1_847 = 15137, C_1_961 = 16069, C_2_053 = 16819, C_2_562 = 20995, C_3_072 = 25172 };
-    int ws[64];
+    I ws[64];
     for (int c = 0; c < 8; c++) {
         const int* in = coef + c;
-        int z2 = in[16], z3 = in[48];
-        int z1 = (z2 + z3) * C_0_541;
-        int tmp2 = z1 + z3 * (-C_1_847);
-        int tmp3 = z1 + z2 * C_0_765;
+        I z2 = in[16], z3 = in[48];
+        I z1 = (z2 + z3) * C_0_541;
+        I tmp2 = z1 + z3 * (-C_1_847);
+        I tmp3 = z1 + z2 * C_0_765;
         z2 = in[0]; z3 = in[32];
-        int tmp0 = (z2 + z3) * 8192;
-        int tmp1 = (z2 - z3) * 8192;
-        const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+        I tmp0 = (z2 + z3) * 8192;
+        I tmp1 = (z2 - z3) * 8192;
+        const I tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
         tmp0 = in[56]; tmp1 = in[40]; tmp2 = in[24]; tmp3 = in[8];
         z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
-        int z4 = tmp1 + tmp3;
-        const int z5 = (z3 + z4) * C_1_175;
+        I z4 = tmp1 + tmp3;
+        const I z5 = (z3 + z4) * C_1_175;
         tmp0 *= C_0_298; tmp1 *= C_2_053; tmp2 *= C_3_072; tmp3 *= C_1_501;
         z1 *= -C_0_899; z2 *= -C_2_562; z3 *= -C_1_961; z4 *= -C_0_390;
         z3 += z5; z4 += z5;
         tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
-        int* w = ws + c;
+        I* w = ws + c;
         w[0] = descale(tmp10 + tmp3, 11); w[56] = descale(tmp10 - tmp3, 11);
         w[8] = descale(tmp11 + tmp2, 11); w[48] = descale(tmp11 - tmp2, 11);
         w[16] = descale(tmp12 + tmp1, 11); w[40] = descale(tmp12 - tmp1, 11);
         w[24] = descale(tmp13 + tmp0, 11); w[32] = descale(tmp13 - tmp0, 11);
     }
     for (int r = 0; r < 8; r++) {
-        const int* w = ws + 8 * r;
-        int z2 = w[2], z3 = w[6];
-        int z1 = (z2 + z3) * C_0_541;
-        int tmp2 = z1 + z3 * (-C_1_847);
-        int tmp3 = z1 + z2 * C_0_765;
-        int tmp0 = (w[0] + w[4]) * 8192;
-        int tmp1 = (w[0] - w[4]) * 8192;
-        const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+        const I* w = ws + 8 * r;
+        I z2 = w[2], z3 = w[6];
+        I z1 = (z2 + z3) * C_0_541;
+        I tmp2 = z1 + z3 * (-C_1_847);
+        I tmp3 = z1 + z2 * C_0_765;
+        I tmp0 = (w[0] + w[4]) * 8192;
+        I tmp1 = (w[0] - w[4]) * 8192;
+        const I tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
         tmp0 = w[7]; tmp1 = w[5]; tmp2 = w[3]; tmp3 = w[1];
         z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
-        int z4 = tmp1 + tmp3;
-        const int z5 = (z3 + z4) * C_1_175;
+        I z4 = tmp1 + tmp3;
+        const I z5 = (z3 + z4) * C_1_175;
         tmp0 *= C_0_298; tmp1 *= C_2_053; tmp2 *= C_3_072; tmp3 *= C_1_501;
         z1 *= -C_0_899; z2 *= -C_2_562; z3 *= -C_1_961; z4 *= -C_0_390;
         z3 += z5; z4 += z5;
@@ -330,7 +335,7 @@ Image8 decode_jpeg_rgba8(const uint8_t* data, size_t size, bool flip, const std:
                                 if (t > 11) jfail(name, "corrupt JPEG data: bad DC size");
                                 const int diff = t ? extend(br.get(t), t) : 0;
                                 k->pred += diff;
-                                block[0] = k->pred * q[0];
+                                block[0] = clamp_coef(k->pred * int64_t(q[0]));
                                 for (int i = 1; i < 64;) {
                                     const int rs = decode_symbol(br, ac[k->ta], name);
                                     const int r = rs >> 4, s = rs & 15;
@@ -342,7 +347,7 @@ Image8 decode_jpeg_rgba8(const uint8_t* data, size_t size, bool flip, const std:
                                     i += r;
                                     if (i > 63) jfail(name, "corrupt JPEG data: coefficient index out of range");
                                     const int zz = kZigzag[i];
-                                    block[zz] = extend(br.get(s), s) * q[zz];
+                                    block[zz] = clamp_coef(int64_t(extend(br.get(s), s)) * int64_t(q[zz]));
                                     i++;
                                 }
                                 const int px = (ux * bw + bx) * 8, py = (uy * bh + by) * 8;
