@@ -1,6 +1,6 @@
-"""Robustness of the C++ host's file parsers (PNG inflate / defilter, baseline JPEG, JSON + glTF / GLB): mutated inputs
+"""Robustness of the C++ host's file parsers (PNG inflate / defilter, baseline JPEG, JSON + glTF / GLB, OBJ, the TOML configuration): mutated inputs
 must be either decoded or refused with an exception — never a crash, an out-of-bounds access or undefined behaviour.
-The harness (tools/fuzz_host.cpp) is built with AddressSanitizer + UndefinedBehaviorSanitizer and fed ~1500 mutations
+The harness (tools/fuzz_host.cpp) is built with AddressSanitizer + UndefinedBehaviorSanitizer and fed ~2000 mutations
 (byte flips, truncations, zeroed and inserted runs, 0xFFFFFFFF words) of valid files."""
 import os
 import pathlib
@@ -19,7 +19,7 @@ HOST = ROOT / "reina-vk_b200" / "host"
 @pytest.fixture(scope="module")
 def harness(tmp_path_factory):
     out = tmp_path_factory.mktemp("fuzz") / "fuzz_host"
-    src = [str(ROOT / "tools" / "fuzz_host.cpp")] + [str(HOST / f) for f in ("model.cpp", "scene.cpp", "texture.cpp", "jpeg.cpp", "gltf.cpp", "png.cpp")]
+    src = [str(ROOT / "tools" / "fuzz_host.cpp")] + [str(HOST / f) for f in ("model.cpp", "scene.cpp", "texture.cpp", "jpeg.cpp", "gltf.cpp", "png.cpp", "config.cpp")]
     err = ""
     for cxx in ("/usr/bin/g++", shutil.which("g++"), os.environ.get("CXX"), shutil.which("clang++")):     # the first with sanitizer runtimes
         if not cxx or not os.path.exists(cxx):
@@ -66,7 +66,10 @@ def test_mutated_files_never_crash_the_parsers(harness, tmp_path):
     glb, _ = gf.build(d)
     (d / "ext").mkdir()
     gltf, _ = gf.build(d / "ext", external=True, jpeg=True)
-    seeds = [d / "a.jpg", d / "b.jpg", d / "a.png", d / "c.png", d / "d.png", pathlib.Path(glb), pathlib.Path(gltf)]
+    from test_cpp_host import OBJ_FULL, REFERENCE_SCHEMA
+    (d / "a.obj").write_text(OBJ_FULL)
+    (d / "a.toml").write_text(REFERENCE_SCHEMA + "\n[render]\nwidth = 80\nheight = 60\ncamera_pos = [0.4, 0.9, 2.6]\nscene = \"cornell\"\n")
+    seeds = [d / "a.jpg", d / "b.jpg", d / "a.png", d / "c.png", d / "d.png", pathlib.Path(glb), pathlib.Path(gltf), d / "a.obj", d / "a.toml"]
     files = [str(s) for s in seeds]                       # the valid files themselves must decode
     for s in seeds:
         raw = s.read_bytes()
