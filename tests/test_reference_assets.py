@@ -61,3 +61,37 @@ def test_reference_obj_imports_identically_in_both_hosts(host, rb, name, triangl
     host.rbhost_tables_free(h)
     if triangles is not None:
         assert t.num_triangles() == triangles
+
+
+def test_reference_plant_scene_renders_through_the_importers_and_the_oracle(ol, rb):
+    """BASELINE config C4 with the reference's real assets: the four plant OBJs (67,264 triangles) in showroom.obj under
+    cornell_light.obj, leaves with the 2K JPEG albedo + normal textures, pot with the hammered-metal normal map — host
+    importers, table builder and the oracle end to end (the GPU box cannot see these files; there C4 runs on the
+    stand-in geometry of configs.plant)."""
+    from PIL import Image
+    m = lambda n: rb.meshes.load_obj(os.path.join(REF, "models", n))
+    tex = lambda n: np.ascontiguousarray(np.asarray(Image.open(os.path.join(REF, "textures", n)).convert("RGBA"))[::-1])
+    s = rb.Scene()
+    leaf_albedo, leaf_normal, pot_normal = (s.defineTexture(tex(n)) for n in ("qgdpH_2K_Albedo.jpg", "qgdpH_2K_Normal.jpg", "Hammered_Metal_normal.png"))
+    I = np.eye(4, dtype=np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        s.addObject(m("showroom.obj"), I, rb.Material(materialIdx=0, albedo=(0.8, 0.8, 0.8), interpNormals=True))
+        s.addObject(m("cornell_light.obj"), I, rb.Material(**rb.configs.LIGHT))
+        s.addObject(m("plant_pot.obj"), I, rb.Material(materialIdx=3, albedo=(0.72, 0.45, 0.2), roughness=0.4, ior=1.5, interpNormals=True,
+                                                       metallic=0.6, normalMapID=pot_normal, sheenTint=(1, 1, 1), specularTint=(1, 1, 1)))
+        s.addObject(m("plant_soil.obj"), I, rb.Material(materialIdx=0, albedo=(0.25, 0.18, 0.12), interpNormals=True))
+        for n in ("plant_leaves_1.obj", "plant_leaves_2.obj"):
+            s.addObject(m(n), I, rb.Material(materialIdx=0, albedo=(0.9, 0.9, 0.9), textureID=leaf_albedo, normalMapID=leaf_normal, interpNormals=True))
+    t = s.build(require_emitter=True)
+    assert t.num_triangles() == 1176 + 2 + 1408 + 240 + 32808 + 32808
+    W, H = 96, 72
+    pc = rb.camera.push_constants(W, H, (-1.6899, 0.817, -1.6386), (0.0, 0.55, 0.0), 30.0, total_emissive_weight=t.totalEmissiveWeight,
+                                  samples_per_pixel=2, max_bounces=6)
+    sc = ol.OracleScene(t)
+    hdr, cnt = sc.render_batch(W, H, rb.RB200_FLAG_NEE, pc)
+    assert np.isfinite(hdr).all() and cnt["paths"] == W * H * 2 and cnt["shadowRays"] > 0
+    hits = sc.trace_primary(W, H, pc)
+    seen = set(np.unique(hits["instance"][hits["t"] > 0]).tolist())
+    assert {0, 2, 4}.issubset(seen) or {0, 2, 5}.issubset(seen)           # showroom, pot and leaves are in view
+    assert hdr[..., :3].mean() > 1e-3
