@@ -1,4 +1,7 @@
-# debug: per-step host timestamps of the multi-GPU e2e loop (run under torchrun with 2 ranks, or alone)
+"""Developer aid (run on the GPU box, alone or under torchrun with 2 ranks): host-side timestamps of every step of the
+multi-GPU end-to-end frame loop (render_batch / snapshot + reduce / present + wait) and device-side completion times of
+the frames. NO_NCCL=1 skips the reduce. This is how the 170 ms first-frame stall (kernel code loaded on first launch)
+was found; see profiles/r01_summary.md."""
 import os, sys, time, importlib
 import torch, torch.distributed as dist
 sys.path.insert(0, os.getcwd())

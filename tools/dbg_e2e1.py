@@ -1,4 +1,7 @@
-# debug: per-step host timestamps of the single-GPU e2e loop
+"""Developer aid (run on the GPU box): host- and device-side timeline of the single-GPU end-to-end frame loop of
+bench.py (render_batch, postprocess, wait_ldr, read_ldr_async). RB200_NO_GRAPH=1 launches the wave loop kernel by kernel;
+RB200_STAGGER_WAVE=-1 switches the lane stagger gate off. Shows whether the lanes run staggered or in lockstep (frames
+completing in bursts); see profiles/r01_summary.md."""
 import os, sys, time, importlib
 import torch
 sys.path.insert(0, os.getcwd())
