@@ -5,10 +5,13 @@
  * tonemap). Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library; the CUDA library never links or calls it.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures and cannot be
- * built here (Vulkan RT + glslc + Assimp absent), and ray/triangle intersection lives in the Vulkan driver.
- * This restatement is therefore defended line-by-line against the GLSL (every function cites the lines it
- * follows) and pinned only by the known-answer values in SURVEY.md Appendix A3 (tests/test_oracle_kat.py).
+ * PARITY PINNING: the reference ships no tests, golden vectors or fixtures and cannot be
+ * built here (Vulkan RT + glslc + Assimp absent), and ray/triangle intersection lives in the Vulkan driver
+ * (traversal: UNPINNED). What the reference does ship is the compiled SPIR-V of every shader; tests/spirv_interp.py
+ * executes those binaries on the CPU and tests/golden/spirv_*.npz holds their outputs: the parts of this
+ * restatement listed in tests/test_spirv_golden.py are pinned to the reference's compiled code bit for bit. The
+ * rest is defended line-by-line against the GLSL (every function cites the lines it follows) and pinned by the
+ * known-answer values in SURVEY.md Appendix A3 (tests/test_oracle_kat.py).
  *
  * Elementary layer: rb_math.h / rb_vec.h / rb_tri.h (sin, cos, log, exp, acos, vector built-ins, the
  * watertight triangle test) are shared with the kernels on purpose, so that both sides round identically and
