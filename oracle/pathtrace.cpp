@@ -216,10 +216,16 @@ static vec3 random_unit_vec(uint32_t& rng) {
         if (0.0001f < l2 && l2 < 1.0f) return rb_normalize(v);
     }
 }
-// closestHitCommon.h.glsl:211-213
+// closestHitCommon.h.glsl:211-213. The function takes `inout uint rngState` but draws from the GLOBAL pld.rngState;
+// every caller passes pld.rngState itself, so GLSL's copy-in / copy-out writes the value the state had BEFORE the
+// call back over the advanced one: the draws of randomUnitVec are not consumed and the next random() repeats them.
+// (Confirmed by executing the reference's compiled metal.rchit.spv: tests/test_spirv_golden.py.)
 static vec3 fuzzy_reflection(vec3 in, vec3 n, float fuzz, uint32_t& rng) {
+    const uint32_t stateAtCall = rng;
     vec3 r = rb_reflect(rb_normalize(in), rb_normalize(n));
-    return r + random_unit_vec(rng) * fuzz;
+    vec3 out = r + random_unit_vec(rng) * fuzz;
+    rng = stateAtCall;
+    return out;
 }
 // closestHitCommon.h.glsl:215-222
 static vec3 diffuse_reflection(vec3 n, uint32_t& rng) {

@@ -248,9 +248,16 @@ __device__ __forceinline__ rb_v3 random_unit_vec(uint32_t& rng) {
         if (0.0001f < l2 && l2 < 1.0f) return rb_normalize(v);
     }
 }
+// closestHitCommon.h.glsl:211-213. The GLSL function takes `inout uint rngState` but draws from the GLOBAL pld.rngState,
+// and every caller passes pld.rngState itself: copy-out writes the value the state had BEFORE the call back over the
+// advanced one, so the draws of randomUnitVec are not consumed (the next random() repeats them). Confirmed by executing
+// the reference's compiled metal.rchit.spv / dielectric.rchit.spv (tests/test_spirv_golden.py).
 __device__ __forceinline__ rb_v3 fuzzy_reflection(rb_v3 in, rb_v3 n, float fuzz, uint32_t& rng) {
+    const uint32_t stateAtCall = rng;
     rb_v3 r = rb_reflect(rb_normalize(in), rb_normalize(n));
-    return r + random_unit_vec(rng) * fuzz;
+    const rb_v3 out = r + random_unit_vec(rng) * fuzz;
+    rng = stateAtCall;
+    return out;
 }
 __device__ __forceinline__ rb_v3 diffuse_reflection(rb_v3 n, uint32_t& rng) {
     const float theta = (2.0f * RB_PI) * rb_random(&rng);

@@ -200,6 +200,8 @@ class Interpreter:
                 val = builtins[dec[11][0]]
             elif storage == 9 and "push_constant" in bindings:
                 val = _copy(bindings["push_constant"])
+            elif ("storage", storage) in bindings:           # e.g. ray payload (5338 / 5342), hit attributes (5339)
+                val = bindings[("storage", storage)]
             elif name in bindings:
                 val = bindings[name]
             elif key in bindings:
@@ -323,6 +325,8 @@ class Interpreter:
             V(a[0]).write([_s32(x) for x in c], V(a[2]))
         elif op == 100:
             env[a[1]] = V(a[2])
+        elif op == 88:                                 # OpImageSampleExplicitLod (Lod 0): the sampler object decides
+            env[a[1]] = V(a[2]).sample(V(a[3]))
         elif op in (109, 110):                         # ConvertFToU / FToS: truncation toward zero
             env[a[1]] = mp(lambda x: int(np.trunc(np.float64(x))) & MASK if np.isfinite(x) else 0, V(a[2]))
         elif op == 111:

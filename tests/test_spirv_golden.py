@@ -71,3 +71,97 @@ def test_cuda_postprocessing_equals_the_reference_spirv(rb):
         got = r.read_ldr()
         assert (got[..., :3] == g["ldr_%d" % i][..., :3]).all(), i
     r.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the ray-tracing pipeline: raytrace.rgen.spv + the four *.rchit.spv + raytrace.rmiss.spv (tests/spirv_rt.py)
+# ---------------------------------------------------------------------------------------------------------------------
+RT_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spirv_rt.npz")
+RT_SHADERS = "/root/reference/shaders/raytrace"
+
+
+def _rt_cases(rb):
+    import golden.make_spirv_rt_golden as mk
+    g = np.load(RT_GOLD)
+    for name, case in mk.CASES.items():
+        yield name, case, mk.workload(rb, case), g
+
+
+def test_oracle_equals_the_reference_ray_tracing_shaders(ol, rb):
+    """SURVEY.md 8a rows a1-a4 (as shipped: NEE compiled out), a7-a13, a15, a16 and 8f row 4: camera, RNG, bounce loop,
+    the four materials, parallax mapping, sky and accumulation of the oracle against the images the reference's compiled
+    shaders produce for the same tables, seeds and push constants — every pixel of every batch, bit for bit, and the
+    same number of rays."""
+    n = 0
+    for name, case, wl, g in _rt_cases(rb):
+        sc = ol.OracleScene(wl.tables)
+        hdr = np.zeros((case["height"], case["width"], 4), np.float32)
+        for b in range(case["batches"]):
+            hdr, cnt = sc.render_batch(case["width"], case["height"], 0, wl.push_constants(b), hdr)
+            want = g["%s_hdr_%d" % (name, b)]
+            assert np.isfinite(want).all()
+            assert (hdr.view(np.uint32) == want.view(np.uint32)).all(), (name, b)
+            assert cnt["extendRays"] == int(g["%s_rays_%d" % (name, b)]) and cnt["shadowRays"] == 0, (name, b)
+            n += 1
+    assert n == 6
+
+
+@pytest.mark.skipif(not os.path.isdir(RT_SHADERS), reason="reference checkout not present")
+def test_reexecuting_the_reference_ray_tracing_shaders(ol, rb):
+    """Run the binaries again on a frame the fixture does not hold (another size, sample count and batch index)."""
+    import spirv_rt
+    wl = rb.configs.small_mixed(12, 9, nee=False, samples_per_pixel=3, max_bounces=5)
+    pipe = spirv_rt.Pipeline(RT_SHADERS, wl.tables, ol)
+    pc = wl.push_constants(7)                        # sampleBatch 7: folds into an existing image with weight 7 / 8
+    rng = np.random.RandomState(5)
+    start = np.zeros((9, 12, 4), np.float32)
+    start[..., :3] = rng.uniform(0, 1, (9, 12, 3)).astype(np.float32)
+    start[..., 3] = 1
+    ref = pipe.render_batch(pc, 12, 9, start.copy())
+    got, cnt = pipe.scene.render_batch(12, 9, 0, pc, start.copy())
+    assert (got.view(np.uint32) == ref.view(np.uint32)).all() and cnt["extendRays"] == pipe.rays
+
+
+@pytest.mark.skipif(not os.path.isdir(RT_SHADERS), reason="reference checkout not present")
+def test_compiled_metal_shader_does_not_consume_its_fuzz_draws(ol, rb):
+    """The quirk the compiled binaries revealed (and the oracle and the kernels now reproduce): fuzzyReflection(...,
+    inout uint rngState) draws from the GLOBAL pld.rngState while every caller passes pld.rngState as the inout
+    argument, so copy-out writes the old state back: metal.rchit.spv leaves the payload's RNG state exactly as it
+    found it, although randomUnitVec drew at least three numbers."""
+    import spirv_rt
+    F = np.float32
+    wl = rb.configs.small_mixed(32, 24, nee=False, samples_per_pixel=2, max_bounces=6)
+    pipe = spirv_rt.Pipeline(RT_SHADERS, wl.tables, ol)
+    m = pipe.rgen.m
+    ptype = [m.types[pt][2] for v, (st, pt, _) in m.globals.items() if st == spirv_rt.SC_RAY_PAYLOAD][0]
+    o, d = [-0.65, 2.0, 0.94], [0.13, -0.75, -0.65]                      # from the ceiling towards the metal sphere
+    hit = pipe.scene.trace_rays(np.array([o], np.float32), np.array([d], np.float32), 1e4, brute=True, threads=1)[0]
+    i = int(hit["instance"])
+    assert int(pipe.inst_material[i]) == 1
+    for state in (12345, 1, 0xDEADBEEF):
+        payload = m.zero(ptype)
+        payload[4] = state
+        M = pipe.inst_transform[i]
+        builtins = {spirv_rt.BUILTIN_WORLD_RAY_ORIGIN: [F(x) for x in o], spirv_rt.BUILTIN_WORLD_RAY_DIRECTION: [F(x) for x in d],
+                    spirv_rt.BUILTIN_OBJECT_TO_WORLD: [[F(M[4 * c + r]) for r in range(3)] for c in range(4)],
+                    spirv_rt.BUILTIN_INSTANCE_CUSTOM_INDEX: int(pipe.inst_props[i]), spirv_rt.BUILTIN_PRIMITIVE_ID: int(hit["primitive"])}
+        b = dict(pipe.hit_bindings[1])
+        b[("storage", spirv_rt.SC_INCOMING_RAY_PAYLOAD)] = payload
+        b[("storage", spirv_rt.SC_HIT_ATTRIBUTE)] = [F(hit["u"]), F(hit["v"])]
+        pipe.rchit[1].run(b, builtins=builtins)
+        assert payload[8] == 1 and payload[4] == state                   # materialID 1, rngState untouched
+        assert abs(float(np.sqrt(sum(float(c) ** 2 for c in payload[3]))) - 1.0) < 0.2      # reflect + 0.15 * unit vector
+
+
+@pytest.mark.gpu
+def test_cuda_path_equals_the_reference_ray_tracing_shaders(rb):
+    for name, case, wl, g in _rt_cases(rb):
+        r = rb.Renderer(case["width"], case["height"], wl.tables, flags=0)
+        for b in range(case["batches"]):
+            r.render_batch(wl.push_constants(b))
+            got = r.read_hdr()
+            want = g["%s_hdr_%d" % (name, b)]
+            assert (got.view(np.uint32) == want.view(np.uint32)).all(), (name, b)
+            last, _ = r.stats()
+            assert last["extendRays"] == int(g["%s_rays_%d" % (name, b)]) and last["shadowRays"] == 0, (name, b)
+        r.close()
