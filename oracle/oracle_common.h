@@ -9,7 +9,9 @@
  * built here (Vulkan RT + glslc + Assimp absent), and ray/triangle intersection lives in the Vulkan driver
  * (traversal: UNPINNED). What the reference does ship is the compiled SPIR-V of every shader; tests/spirv_interp.py
  * executes those binaries on the CPU and tests/golden/spirv_*.npz holds their outputs: the parts of this
- * restatement listed in tests/test_spirv_golden.py are pinned to the reference's compiled code bit for bit. The
+ * restatement listed in tests/test_spirv_golden.py (post-processing; camera, RNG, bounce loop, the four materials,
+ * parallax mapping, sky and accumulation of the as-shipped estimator) are pinned to the reference's compiled code bit
+ * for bit. The
  * rest is defended line-by-line against the GLSL (every function cites the lines it follows) and pinned by the
  * known-answer values in SURVEY.md Appendix A3 (tests/test_oracle_kat.py).
  *
