@@ -11,6 +11,8 @@ float kat_random(uint32_t* state);
 vec3 kat_offset(vec3 p, vec3 n);
 vec3 kat_sky(vec3 dir);
 float kat_power_heuristic(float a, float b);
+void kat_trace_main(const Scene& s, const float o[3], const float d[3], uint32_t* rngState, int insideDielectric,
+                    float accumulatedDistance, float out[21], uint32_t* flags);
 void kat_bump(const uint8_t* rgba, uint32_t w, uint32_t h, const float uv[2], const float rayIn[3], const float tbn[9],
               float out[2]);
 void starting_ray(const RB200RtPushConsts& pc, float px, float py, float resx, float resy, uint32_t& rng,
@@ -154,6 +156,10 @@ ORACLE_API void oracle_kat_sky(const float* d, float* out) {
 }
 ORACLE_API void oracle_kat_bump(const uint8_t* rgba, uint32_t w, uint32_t h, const float* uv, const float* rayIn,
                                 const float* tbn, float* out) { kat_bump(rgba, w, h, uv, rayIn, tbn, out); }
+ORACLE_API void oracle_kat_trace_main(void* scene, const float* o, const float* d, uint32_t* rngState, int insideDielectric,
+                                      float accumulatedDistance, float* out, uint32_t* flags) {
+    kat_trace_main(*(Scene*)scene, o, d, rngState, insideDielectric, accumulatedDistance, out, flags);
+}
 ORACLE_API float oracle_kat_power_heuristic(float a, float b) { return kat_power_heuristic(a, b); }
 ORACLE_API void oracle_kat_tonemap(const float* rgb, float exposure, uint8_t* out) { tonemap_pixel(rgb, exposure, out); }
 ORACLE_API void oracle_kat_starting_ray(const RB200RtPushConsts* pc, uint32_t x, uint32_t y, uint32_t W, uint32_t H,

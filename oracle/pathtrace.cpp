@@ -279,7 +279,7 @@ static void shade_lambertian(const Scene& s, Payload& pld, const HitInfo& h, con
     pld.rayDirection = diffuse_reflection(wn, pld.rngState);
     pld.rayHitSky = false; pld.skip = false; pld.insideDielectric = false;
     pld.materialID = 0; pld.surfaceNormal = wn;
-    pld.pdf = rb_max(rb_dot(pld.surfaceNormal, pld.rayDirection), 0.0f) / RB_PI;   // pdf.h.glsl:10-12
+    pld.pdf = rb_max(rb_dot(pld.surfaceNormal, pld.rayDirection), 0.0f) * RB_RCP_PI;   // pdf.h.glsl:10-12
     pld.tbn = h.tbn; pld.props = &props; pld.didRefract = false; pld.eta = 0.0f;
     track_distance(pld, h, rayOrigin);
 }
@@ -478,7 +478,7 @@ static vec4r direct_light(const Scene& s, const RB200RtPushConsts& pc, const Pay
 
     vec3 brdf = rb_splat3(0.0f);
     if (pldIn.materialID == 0) {
-        brdf = pldIn.albedo / RB_PI;
+        brdf = pldIn.albedo * RB_RCP_PI;
     } else if (pldIn.materialID == 3) {
         vec3 wi = -rayIn;
         vec3 hv = rb_normalize(direction + wi);
@@ -535,6 +535,25 @@ static vec3 trace_segments(const Scene& s, const RB200RtPushConsts& pc, bool nee
         firstBounce = false;
     }
     return radiance;
+}
+
+// known-answer hook: one traceRayEXT of the bounce loop (intersection + the closest-hit / miss shader) on a caller-
+// provided payload state. out[0..2] color, [3..5] albedo, [6..8] rayOrigin, [9..11] rayDirection, [12..14] emission,
+// [15..17] surfaceNormal, [18] pdf, [19] accumulatedDistance, [20] eta; flags: bit 0 rayHitSky, 1 skip, 2 insideDielectric,
+// 3 didRefract, bits 8.. materialID.
+void kat_trace_main(const Scene& s, const float o[3], const float d[3], uint32_t* rngState, int insideDielectric,
+                    float accumulatedDistance, float out[21], uint32_t* flags) {
+    Payload pld{};
+    pld.rngState = *rngState;
+    pld.insideDielectric = insideDielectric != 0;
+    pld.accumulatedDistance = accumulatedDistance;
+    Counters cnt;
+    trace_main(s, pld, rb_mk3(o[0], o[1], o[2]), rb_mk3(d[0], d[1], d[2]), &cnt);
+    const vec3 v[6] = {pld.color, pld.albedo, pld.rayOrigin, pld.rayDirection, pld.emission, pld.surfaceNormal};
+    for (int k = 0; k < 6; k++) { out[3 * k] = v[k].x; out[3 * k + 1] = v[k].y; out[3 * k + 2] = v[k].z; }
+    out[18] = pld.pdf; out[19] = pld.accumulatedDistance; out[20] = pld.eta;
+    *flags = (pld.rayHitSky ? 1u : 0u) | (pld.skip ? 2u : 0u) | (pld.insideDielectric ? 4u : 0u) | (pld.didRefract ? 8u : 0u) | (pld.materialID << 8);
+    *rngState = pld.rngState;
 }
 
 // raytrace.rgen.glsl:34-41

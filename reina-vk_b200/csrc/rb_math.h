@@ -26,6 +26,10 @@
 
 #define RB_PI      3.14159265f      /* k_pi      shaders/raytrace/shaderCommon.h.glsl:47 */
 #define RB_INV_PI  0.31830989f      /* k_inv_pi  shaders/raytrace/shaderCommon.h.glsl:48 */
+/* "x / k_pi" in the reference's shaders: its compiler (spirv-opt) turns a division by a constant into a multiplication
+ * by the constant's fp32 reciprocal, 1.0f / 3.14159265f = 0x3EA2F983 — one ulp below k_inv_pi. Seen in the compiled
+ * lambertian.rchit.spv (pdfLambertian) and disney.rchit.spv (fBaseDiffuse); tests/test_spirv_golden.py. */
+#define RB_RCP_PI  0.31830987334251404f
 
 RB_HD uint32_t rb_f2u(float f) {
 #if defined(__CUDA_ARCH__)

@@ -364,10 +364,12 @@ __device__ rb_v3 sample_gtr1(float alpha, uint32_t& rng) {
 __device__ rb_v3 eval_diffuse(const DisneyP& p, rb_v3 n, rb_v3 wi, rb_v3 wo, rb_v3 h) {
     const float hdwo = rb_dot(h, wo);
     const float ndwi = rb_max(rb_dot(n, wi), 0.0f), ndwo = rb_max(rb_dot(n, wo), 0.0f);
-    float fd90 = 0.5f + 2.0f * p.roughness * rb_max(hdwo, 0.0f) * rb_max(hdwo, 0.0f);
-    float fdIn = 1.0f + (fd90 - 1.0f) * rb_pow5(1.0f - ndwi);
-    float fdOut = 1.0f + (fd90 - 1.0f) * rb_pow5(1.0f - ndwo);
-    rb_v3 baseDiffuse = ((p.baseColor / RB_PI) * fdIn) * fdOut;
+    // FD90 = 0.5 + x, and FD uses (FD90 - 1): the reference's compiler (spirv-opt) merges the two constants into
+    // x + (-0.5), which skips the rounding of 0.5 + x (seen in the compiled disney.rchit.spv)
+    const float fd90m1 = 2.0f * p.roughness * rb_max(hdwo, 0.0f) * rb_max(hdwo, 0.0f) + -0.5f;
+    float fdIn = 1.0f + fd90m1 * rb_pow5(1.0f - ndwi);
+    float fdOut = 1.0f + fd90m1 * rb_pow5(1.0f - ndwo);
+    rb_v3 baseDiffuse = ((p.baseColor * RB_RCP_PI) * fdIn) * fdOut;     // "/ k_pi" is compiled as "* (1 / k_pi)"
     rb_v3 k = (p.baseColor * 1.25f) * RB_INV_PI;
     float fss90 = p.roughness * rb_max(hdwo, 0.0f) * rb_max(hdwo, 0.0f);
     float fssIn = 1.0f + (fss90 - 1.0f) * rb_pow5(1.0f - ndwi);

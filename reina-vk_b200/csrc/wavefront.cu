@@ -316,7 +316,7 @@ __device__ __forceinline__ uint32_t shade_slot(const WaveParams& P, const uint32
             o.newO = rb_offset_along_normal(s.worldPosition, s.worldNormalGeometry);
             o.newD = diffuse_reflection(wn, rng);
             o.inside = false; o.normal = wn;
-            o.pdf = rb_max(rb_dot(wn, o.newD), 0.0f) / RB_PI;
+            o.pdf = rb_max(rb_dot(wn, o.newD), 0.0f) * RB_RCP_PI;
             accDist = 0.0f;
         }
     } else if (MAT == 1) {    // metal.rchit.glsl:7-70
@@ -413,7 +413,7 @@ __device__ __forceinline__ uint32_t shade_slot(const WaveParams& P, const uint32
                 const float pdfNEE = target.pdf * dist * dist / rb_max(rb_dot(target.normal, -direction), 0.0001f);
                 rb_v3 brdf;
                 if (MAT == 0) {
-                    brdf = o.albedo / RB_PI;
+                    brdf = o.albedo * RB_RCP_PI;
                 } else {
                     const rb_v3 wi = -rayDir;
                     const rb_v3 hv = rb_normalize(direction + wi);

@@ -10,6 +10,8 @@ of rays traced. Cases (sizes chosen so that the interpreter needs about a minute
   mixed     configs.small_mixed: every material, albedo / normal / alpha textures, cull and alpha skips, instancing
   cornell   configs.cornell (BASELINE C1 at reduced size), textured walls
   parallax  configs.parallax: texutils.h.glsl bumpMapping compiled into all four closest-hit shaders
+  showroom  configs.showroom_mixed (BASELINE C5 at reduced size): open scene (sky misses after bounces), a Disney blob with
+            subsurface and sheen, one sphere per material id, Disney with specular transmission
 The workloads are rebuilt from the same configs by tests/test_spirv_golden.py; the oracle (CPU) and the CUDA path (GPU)
 must reproduce every image bit for bit."""
 import os
@@ -23,12 +25,14 @@ sys.path.insert(0, os.path.dirname(HERE))
 SHADERS = "/root/reference/shaders/raytrace"
 CASES = {"mixed": dict(config="small_mixed", width=32, height=24, samples_per_pixel=2, max_bounces=6, batches=2),
          "cornell": dict(config="cornell", width=24, height=18, samples_per_pixel=2, max_bounces=8, batches=2),
-         "parallax": dict(config="parallax", width=32, height=24, samples_per_pixel=2, max_bounces=6, batches=2)}
+         "parallax": dict(config="parallax", width=32, height=24, samples_per_pixel=2, max_bounces=6, batches=2),
+         "showroom": dict(config="showroom_mixed", width=32, height=18, samples_per_pixel=2, max_bounces=8, batches=2, levels=2)}
 
 
 def workload(rb, case):
+    extra = {"levels": case["levels"]} if "levels" in case else {}
     return getattr(rb.configs, case["config"])(case["width"], case["height"], nee=False, samples_per_pixel=case["samples_per_pixel"],
-                                               max_bounces=case["max_bounces"])
+                                               max_bounces=case["max_bounces"], **extra)
 
 
 def main():

@@ -103,7 +103,7 @@ def test_oracle_equals_the_reference_ray_tracing_shaders(ol, rb):
             assert (hdr.view(np.uint32) == want.view(np.uint32)).all(), (name, b)
             assert cnt["extendRays"] == int(g["%s_rays_%d" % (name, b)]) and cnt["shadowRays"] == 0, (name, b)
             n += 1
-    assert n == 6
+    assert n == 8
 
 
 @pytest.mark.skipif(not os.path.isdir(RT_SHADERS), reason="reference checkout not present")
