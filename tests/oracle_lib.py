@@ -56,6 +56,8 @@ def lib():
         _lib.oracle_kat_power_heuristic.restype = C.c_float
         _lib.oracle_kat_offset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.oracle_kat_bump.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oracle_kat_trace_main.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_int, C.c_float,
+                                               C.c_void_p, C.POINTER(C.c_uint32)]
         _lib.oracle_kat_sky.argtypes = [C.c_void_p, C.c_void_p]
         _lib.oracle_kat_tonemap.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
         _lib.oracle_kat_starting_ray.argtypes = [C.POINTER(abi.RtPushConsts), C.c_uint32, C.c_uint32, C.c_uint32,

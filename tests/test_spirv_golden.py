@@ -153,6 +153,79 @@ def test_compiled_metal_shader_does_not_consume_its_fuzz_draws(ol, rb):
         assert abs(float(np.sqrt(sum(float(c) ** 2 for c in payload[3]))) - 1.0) < 0.2      # reflect + 0.15 * unit vector
 
 
+@pytest.mark.skipif(not os.path.isdir(RT_SHADERS), reason="reference checkout not present")
+def test_random_hits_with_random_materials_match_the_compiled_shaders(ol, rb):
+    """Single closest-hit invocations with random material parameters (every Disney lobe weight, anisotropy, tints, ior,
+    absorption, roughness; albedo / normal / height maps on or off; culling on or off), random un-normalised rays that
+    start outside or inside the spheres, random RNG states and dielectric entry states: every payload field, the RNG
+    state and the flags of the oracle equal the compiled shader's. (4000 such hits were run when the fixture was made;
+    this keeps 160 in the suite.)"""
+    import ctypes as C
+    import spirv_rt
+    F = np.float32
+    Cf = rb.configs
+    R = np.random.RandomState(20)
+    u = lambda a=0.0, b=1.0: float(R.uniform(a, b))
+    s = rb.Scene()
+    tex, nmap = s.defineTexture(rb.meshes.cornell_texture(32, 48)), s.defineTexture(Cf._bumpy_normal_map(32))
+    leaf, hmap = s.defineTexture(Cf._leaf_texture(32)), s.defineTexture(Cf.brick_height_map(32))
+    pick = lambda t: t if R.rand() < 0.5 else -1
+    s.addObject(rb.meshes.cornell_box(), Cf.IDENT, rb.Material(**Cf.CORNELL_WALL))
+    s.addObject(rb.meshes.cornell_light(), Cf.IDENT, rb.Material(**Cf.LIGHT))
+    sph = s.defineObject(rb.meshes.uv_sphere(12, 6, radius=0.22))
+    mats = [rb.Material(materialIdx=0, albedo=(u(), u(), u()), interpNormals=True, textureID=pick(leaf), normalMapID=pick(nmap), bumpMapID=pick(hmap), cullBackface=True),
+            rb.Material(materialIdx=1, albedo=(u(), u(), u()), roughness=u(0, 0.6), interpNormals=True, textureID=pick(tex), normalMapID=pick(nmap), bumpMapID=pick(hmap)),
+            rb.Material(materialIdx=2, albedo=(u(), u(), u()), roughness=u(0, 0.4), ior=u(1.1, 2.0), absorption=u(0, 3), interpNormals=True, textureID=pick(tex), normalMapID=pick(nmap)),
+            rb.Material(materialIdx=3, albedo=(u(), u(), u()), roughness=u(0.05, 1), ior=u(1.1, 2), interpNormals=True, metallic=u(), clearcoat=u(), clearcoatGloss=u(),
+                        specularTransmission=u(), sheen=u(), subsurface=u(), anisotropic=u(), sheenTint=(u(), u(), u()), specularTint=(u(), u(), u()), textureID=pick(tex), normalMapID=pick(nmap))]
+    pos = [(-0.5, 0.5, -0.3), (0.0, 0.5, 0.3), (0.5, 0.5, -0.3), (0.0, 1.2, -0.2)]
+    for k in range(4):
+        s.addInstance(sph, Cf.compose(Cf.translate(pos[k]), Cf.scale((u(0.7, 1.3), u(0.7, 1.3), u(0.7, 1.3)))), mats[k])
+    pipe = spirv_rt.Pipeline(RT_SHADERS, s.build(), ol)
+    m = pipe.rgen.m
+    ptype = [m.types[pt][2] for v, (st, pt, _) in m.globals.items() if st == spirv_rt.SC_RAY_PAYLOAD][0]
+    same = lambda a, b: ((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all()
+    done, seen = 0, set()
+    while done < 160:
+        k = int(R.randint(0, 4))
+        c = np.array(pos[k], np.float32)
+        o = (c + R.normal(size=3) * 0.03).astype(np.float32) if R.rand() < 0.25 else np.array([u(-0.9, 0.9), u(0.1, 1.9), u(-0.9, 0.9)], np.float32)
+        d = (c + R.uniform(-0.2, 0.2, 3)).astype(np.float32) - o
+        if np.linalg.norm(d) < 1e-3:
+            continue
+        d = (d / np.linalg.norm(d) * u(0.5, 2.0)).astype(np.float32)
+        state, inside = int(R.randint(0, 2 ** 31)), int(R.rand() < 0.3)
+        acc = F(u(0, 2) if inside else 0)
+        hit = pipe.scene.trace_rays(o[None], d[None], 1e4, brute=True, threads=1)[0]
+        if hit["t"] < 0:
+            continue
+        i = int(hit["instance"])
+        kk = min(int(pipe.inst_material[i]), 3)
+        payload = m.zero(ptype)
+        payload[4], payload[12], payload[11] = state, bool(inside), acc
+        M = pipe.inst_transform[i]
+        builtins = {spirv_rt.BUILTIN_WORLD_RAY_ORIGIN: [F(x) for x in o], spirv_rt.BUILTIN_WORLD_RAY_DIRECTION: [F(x) for x in d],
+                    spirv_rt.BUILTIN_OBJECT_TO_WORLD: [[F(M[4 * cc + r]) for r in range(3)] for cc in range(4)],
+                    spirv_rt.BUILTIN_INSTANCE_CUSTOM_INDEX: int(pipe.inst_props[i]), spirv_rt.BUILTIN_PRIMITIVE_ID: int(hit["primitive"])}
+        b = dict(pipe.hit_bindings[kk])
+        b[("storage", spirv_rt.SC_INCOMING_RAY_PAYLOAD)] = payload
+        b[("storage", spirv_rt.SC_HIT_ATTRIBUTE)] = [F(hit["u"]), F(hit["v"])]
+        pipe.rchit[kk].run(b, builtins=builtins)
+        out, st, fl = np.zeros(21, np.float32), C.c_uint32(state), C.c_uint32()
+        ol.lib().oracle_kat_trace_main(pipe.scene._h, o.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), C.byref(st), inside,
+                                       C.c_float(acc), out.ctypes.data_as(C.c_void_p), C.byref(fl))
+        skipped = bool(payload[9])
+        ref = [payload[1], payload[0], payload[2], payload[3], payload[6], payload[7]]      # color, albedo, origin, direction, emission, normal
+        for f in ((2, 3) if skipped else range(6)):                                          # a skipped hit only defines the new ray
+            assert same(np.array(ref[f], np.float32), out[3 * f: 3 * f + 3]), (kk, f, ref[f], out[3 * f: 3 * f + 3])
+        assert payload[4] == st.value and skipped == bool(fl.value & 2), (kk, "rng / skip")
+        if not skipped:
+            assert same(np.array([payload[10], payload[11]], np.float32), out[18:20]) and bool(payload[12]) == bool(fl.value & 4), (kk, "pdf / distance / inside")
+        done += 1
+        seen.add(kk)
+    assert seen == {0, 1, 2, 3}
+
+
 @pytest.mark.gpu
 def test_cuda_path_equals_the_reference_ray_tracing_shaders(rb):
     for name, case, wl, g in _rt_cases(rb):
