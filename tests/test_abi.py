@@ -73,3 +73,23 @@ def test_no_device_is_an_error_not_a_fallback(rb):
     rc = lib.rb200_context_create(64, 64, 0, 0, C.byref(ctx))
     assert rc != 0
     assert b"no CUDA device" in lib.rb200_last_error() or b"CUDA" in lib.rb200_last_error()
+
+
+def test_header_compiles_as_plain_c99_and_cxx11(tmp_path):
+    """The boundary is a C ABI: include/reina_b200.h must be usable from C (a cgo / JNI / ctypes-style binding) and from
+    the C++ the reference is written in, with the POD sizes the reference's polyglot headers have."""
+    import shutil
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "reina_b200.h"\n'
+                   'int main(void) { RB200RtPushConsts pc; (void)pc;\n'
+                   '  return sizeof(RB200InstanceProperties) == 120 && sizeof(RB200RtPushConsts) == 160 && sizeof(RB200InstanceData) == 112\n'
+                   '         && sizeof(RB200Instance) == 80 ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    cc, cxx = shutil.which("gcc"), shutil.which("g++")
+    if not cc or not cxx:
+        pytest.skip("no host compiler")
+    exe = str(tmp_path / "hdr")
+    subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-o", exe, str(src)], check=True)
+    assert subprocess.run([exe]).returncode == 0
+    subprocess.run([cxx, "-std=c++11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-x", "c++", "-fsyntax-only", str(src)], check=True)
