@@ -112,7 +112,11 @@ def test_reexecuting_the_reference_ray_tracing_shaders(ol, rb):
     import spirv_rt
     wl = rb.configs.small_mixed(12, 9, nee=False, samples_per_pixel=3, max_bounces=5)
     pipe = spirv_rt.Pipeline(RT_SHADERS, wl.tables, ol)
-    pc = wl.push_constants(7)                        # sampleBatch 7: folds into an existing image with weight 7 / 8
+    # another camera (inside the box), lens and clamp settings, and a sampleBatch whose seed (sampleBatch * H + y) * W + x
+    # wraps around 2^32; the batch folds into an existing image with weight sampleBatch / (sampleBatch + 1)
+    pc = rb.camera.push_constants(12, 9, (0.0, 1.0, 0.9), (0.3, 0.4, -0.3), 70.0, total_emissive_weight=wl.tables.totalEmissiveWeight,
+                                  sample_batch=2 ** 31 + 5, samples_per_pixel=3, max_bounces=5, focus_dist=3.0,
+                                  defocus_multiplier=6.0, direct_clamp=2.0)
     rng = np.random.RandomState(5)
     start = np.zeros((9, 12, 4), np.float32)
     start[..., :3] = rng.uniform(0, 1, (9, 12, 3)).astype(np.float32)
