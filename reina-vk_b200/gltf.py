@@ -24,7 +24,7 @@ an accident of that call, not a specification. Rules of this importer where the 
   * TANGENT absent: per-vertex tangent frames from the UV derivatives, the importer's own rule (meshes._tangent_frames);
   * TRS node transforms are composed in float64 (T * R * S, quaternion -> matrix by the standard formula), products
     are accumulated in float64 in a fixed order and rounded to float32 once per instance;
-  * images: PNG and baseline JPEG (progressive / CMYK JPEG are refused loudly);
+  * images: PNG and baseline / progressive JPEG (CMYK JPEG is refused loudly);
   * primitive modes other than TRIANGLES and sparse accessors are refused loudly.
 The C++ host (host/gltf.cpp) implements the same rules; tests/test_gltf.py checks both yield identical tables.
 """
@@ -280,14 +280,14 @@ def addMeshesToScene(scene, meshIdToPrimitives):
 
 
 def _decode_image(data, flip, name):
-    """PNG or baseline JPEG, by signature (the C++ host decodes both itself: host/texture.cpp, host/jpeg.cpp; its JPEG
+    """PNG or JPEG (baseline or progressive), by signature (the C++ host decodes both itself: host/texture.cpp, host/jpeg.cpp; its JPEG
     path follows the IJG integer pipeline, i.e. it yields PIL's bytes)."""
     from PIL import Image
     if data[:8] != b"\x89PNG\r\n\x1a\n" and data[:3] != b"\xff\xd8\xff":
         raise RuntimeError("Could not load image at path: " + name + ": neither a PNG nor a JPEG file")
     im = Image.open(io.BytesIO(data))
-    if im.format == "JPEG" and (im.mode == "CMYK" or getattr(im, "info", {}).get("progressive")):
-        raise RuntimeError("Could not load image at path: " + name + ": unsupported JPEG (progressive or CMYK)")
+    if im.format == "JPEG" and im.mode == "CMYK":
+        raise RuntimeError("Could not load image at path: " + name + ": unsupported JPEG (CMYK)")
     img = np.asarray(im.convert("RGBA"), np.uint8)
     return np.ascontiguousarray(img[::-1] if flip else img)
 

@@ -4,9 +4,10 @@
 // published pipeline instead — the slow-but-accurate integer IDCT (13-bit constants, two passes), "fancy" triangle
 // chroma upsampling (h2v1 / h2v2 / h1v2) and the 16-bit fixed-point YCbCr -> RGB conversion — which is what PIL
 // (libjpeg-turbo, bit-exact with the IJG integer path) produces, so tests/test_cpp_host.py can compare byte for byte.
-// Supported: 8-bit baseline / extended sequential Huffman JPEG (SOF0 / SOF1), 1 or 3 components, luma sampling 1x1, 2x1,
-// 1x2, 2x2 with 1x1 chroma, interleaved or per-component scans, restart intervals, Adobe transform flag 0 (RGB).
-// Progressive, arithmetic-coded, lossless, 12-bit and CMYK files are refused loudly.
+// Supported: 8-bit baseline / extended sequential (SOF0 / SOF1) and progressive (SOF2: spectral selection + successive
+// approximation, ITU-T T.81 annex G, the coefficient rules of IJG jdphuff.c) Huffman JPEG, 1 or 3 components, luma
+// sampling 1x1, 2x1, 1x2, 2x2 with 1x1 chroma, interleaved or per-component scans, restart intervals, Adobe transform
+// flag 0 (RGB). Arithmetic-coded, lossless, hierarchical, 12-bit and CMYK files are refused loudly.
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
@@ -41,6 +42,8 @@ struct Component {
     int stride = 0, rows = 0;             // plane size, padded to whole MCUs
     int64_t pred = 0;
     std::vector<uint8_t> plane;
+    int blocksX = 0, blocksY = 0;         // progressive only: quantised coefficients of every block, zigzag order
+    std::vector<int> coef;
 };
 
 struct BitReader {
@@ -91,6 +94,9 @@ int decode_symbol(BitReader& br, const Huff& h, const std::string& name) {
 inline int extend(int v, int n) { return v < (1 << (n - 1)) ? v - (1 << n) + 1 : v; }
 
 inline uint8_t clamp8(int v) { return uint8_t(v < 0 ? 0 : v > 255 ? 255 : v); }
+
+// quantised coefficients are 16-bit in a valid file (JCOEF); corrupt data saturates instead of wrapping
+inline int clamp16(int64_t v) { return int(v < -32768 ? -32768 : v > 32767 ? 32767 : v); }
 
 // de-quantised coefficients of a valid 8-bit file stay within +-2^15; corrupt data may not
 inline int clamp_coef(int64_t v) { return int(v < -(1 << 24) ? -(1 << 24) : v > (1 << 24) ? (1 << 24) : v); }
@@ -197,7 +203,7 @@ Image8 decode_jpeg_rgba8(const uint8_t* data, size_t size, bool flip, const std:
     Huff dc[4], ac[4];
     std::vector<Component> comps;
     int width = 0, height = 0, hmax = 1, vmax = 1, restartInterval = 0;
-    bool sawFrame = false, adobe = false, decodedAny = false;
+    bool sawFrame = false, adobe = false, decodedAny = false, progressive = false;
     int adobeTransform = -1;
     size_t pos = 2;
     auto be16 = [&](size_t at) -> int { if (at + 2 > size) jfail(name, "truncated JPEG"); return (data[at] << 8) | data[at + 1]; };
@@ -249,14 +255,16 @@ Image8 decode_jpeg_rgba8(const uint8_t* data, size_t size, bool flip, const std:
                 }
                 h.present = true;
             }
-        } else if (marker == 0xC0 || marker == 0xC1) {           // SOF0 / SOF1
+        } else if (marker == 0xC0 || marker == 0xC1 || marker == 0xC2) {           // SOF0 / SOF1 / SOF2
             if (sawFrame) jfail(name, "more than one frame");
+            progressive = marker == 0xC2;
             if (n < 6) jfail(name, "truncated SOF");
             if (seg[0] != 8) jfail(name, "only 8-bit JPEG is supported");
             height = (seg[1] << 8) | seg[2];
             width = (seg[3] << 8) | seg[4];
             const int nc = seg[5];
             if (width == 0 || height == 0 || width > 65535 || height > 65535) jfail(name, "unsupported dimensions");
+            if (int64_t(width) * int64_t(height) > (int64_t(1) << 28)) jfail(name, "image too large");      // 268 Mpixel
             if (nc != 1 && nc != 3) jfail(name, "only grayscale and 3-component JPEG are supported");
             if (n < 6 + 3 * nc) jfail(name, "truncated SOF");
             comps.resize(size_t(nc));
@@ -278,10 +286,13 @@ Image8 decode_jpeg_rgba8(const uint8_t* data, size_t size, bool flip, const std:
                 k.stride = mcusX * k.h * 8;
                 k.rows = mcusY * k.v * 8;
                 k.plane.assign(size_t(k.stride) * size_t(k.rows), 128);
+                if (progressive) {
+                    k.blocksX = k.stride / 8; k.blocksY = k.rows / 8;
+                    k.coef.assign(size_t(k.blocksX) * size_t(k.blocksY) * 64, 0);
+                }
             }
             sawFrame = true;
-        } else if (marker == 0xC2) jfail(name, "progressive JPEG is not supported");
-        else if ((marker >= 0xC3 && marker <= 0xCF) && marker != 0xC4 && marker != 0xC8 && marker != 0xCC)
+        } else if ((marker >= 0xC3 && marker <= 0xCF) && marker != 0xC4 && marker != 0xC8 && marker != 0xCC)
             jfail(name, "unsupported JPEG coding process");
         else if (marker == 0xCC) jfail(name, "arithmetic-coded JPEG is not supported");
         else if (marker == 0xDD) { if (n < 2) jfail(name, "truncated DRI"); restartInterval = (seg[0] << 8) | seg[1]; }
@@ -291,6 +302,11 @@ Image8 decode_jpeg_rgba8(const uint8_t* data, size_t size, bool flip, const std:
             if (n < 1) jfail(name, "truncated SOS");
             const int ns = seg[0];
             if (ns < 1 || ns > int(comps.size()) || n < 1 + 2 * ns + 3) jfail(name, "bad SOS");
+            // progression parameters (T.81 G.1.1.1): band Ss..Se, previous / current point transform Ah / Al
+            const int Ss = seg[1 + 2 * ns], Se = seg[2 + 2 * ns], Ah = seg[3 + 2 * ns] >> 4, Al = seg[3 + 2 * ns] & 15;
+            if (progressive && (Ss > Se || Se > 63 || Al > 13 || (Ss == 0 && Se != 0) || (Ss > 0 && ns != 1) || (Ah != 0 && Al != Ah - 1)))
+                jfail(name, "bad progression parameters");
+            const bool needDc = !progressive || (Ss == 0 && Ah == 0), needAc = !progressive || Ss > 0;
             std::vector<Component*> scan;
             for (int s = 0; s < ns; s++) {
                 const int cid = seg[1 + 2 * s];
@@ -298,8 +314,10 @@ Image8 decode_jpeg_rgba8(const uint8_t* data, size_t size, bool flip, const std:
                 for (Component& k : comps) if (k.id == cid) found = &k;
                 if (!found) jfail(name, "scan refers to an unknown component");
                 found->td = seg[2 + 2 * s] >> 4; found->ta = seg[2 + 2 * s] & 15;
-                if (found->td > 3 || found->ta > 3 || !dc[found->td].present || !ac[found->ta].present) jfail(name, "missing Huffman table");
-                if (!haveQuant[found->tq]) jfail(name, "missing quantisation table");
+                if (found->td > 3 || found->ta > 3 || (needDc && !dc[found->td].present) || (needAc && !ac[found->ta].present))
+                    jfail(name, "missing Huffman table");
+                if (!progressive && !haveQuant[found->tq]) jfail(name, "missing quantisation table");
+                for (Component* seen : scan) if (seen == found) jfail(name, "component listed twice in a scan");
                 scan.push_back(found);
             }
             const uint8_t* sp = seg + n;
@@ -311,6 +329,71 @@ Image8 decode_jpeg_rgba8(const uint8_t* data, size_t size, bool flip, const std:
             else { unitsX = (scan[0]->width + 7) / 8; unitsY = (scan[0]->height + 7) / 8; }
             int untilRestart = restartInterval, expectRst = 0;
             int block[64];
+            int eobrun = 0;                                     // progressive AC scans: blocks left in the end-of-band run
+            // one block of a progressive scan (jdphuff.c decode_mcu_DC_first / DC_refine / AC_first / AC_refine)
+            auto progressive_block = [&](Component* k, int bx, int by) {
+                int scratch[64] = {0};
+                int* b = (bx < k->blocksX && by < k->blocksY) ? &k->coef[(size_t(by) * size_t(k->blocksX) + size_t(bx)) * 64] : scratch;
+                const int p1 = 1 << Al, m1 = -(1 << Al);
+                if (Ss == 0) {
+                    if (Ah == 0) {
+                        const int t = decode_symbol(br, dc[k->td], name);
+                        if (t > 11) jfail(name, "corrupt JPEG data: bad DC size");
+                        k->pred += t ? extend(br.get(t), t) : 0;
+                        b[0] = clamp16(k->pred * p1);
+                    } else if (br.get(1)) b[0] |= p1;
+                    return;
+                }
+                const Huff& h = ac[k->ta];
+                if (Ah == 0) {                                  // first pass over the band
+                    if (eobrun > 0) { eobrun--; return; }
+                    for (int i = Ss; i <= Se; i++) {
+                        const int rs = decode_symbol(br, h, name);
+                        const int r = rs >> 4, s = rs & 15;
+                        if (s) {
+                            i += r;
+                            if (i > 63) jfail(name, "corrupt JPEG data: coefficient index out of range");
+                            b[i] = clamp16(int64_t(extend(br.get(s), s)) * p1);
+                        } else if (r == 15) i += 15;
+                        else {                                  // EOBr: this block and eobrun more end here
+                            eobrun = (1 << r) - 1;
+                            if (r) eobrun += br.get(r);
+                            break;
+                        }
+                    }
+                    return;
+                }
+                // refinement: one more bit for the coefficients that are already non-zero, new +-1 coefficients between them
+                auto correct = [&](int& c) {
+                    if (br.get(1) && (c & p1) == 0) c += c >= 0 ? p1 : m1;
+                };
+                int i = Ss;
+                if (eobrun == 0) {
+                    for (; i <= Se; i++) {
+                        const int rs = decode_symbol(br, h, name);
+                        int r = rs >> 4, s = rs & 15;
+                        if (s) s = br.get(1) ? p1 : m1;         // the size must be 1: a newly non-zero coefficient
+                        else if (r != 15) {
+                            eobrun = 1 << r;
+                            if (r) eobrun += br.get(r);
+                            break;                              // the rest of the band is handled below
+                        }
+                        // skip r still-zero coefficients, refining the non-zero ones on the way
+                        for (; i <= Se; i++) {
+                            if (b[i] != 0) correct(b[i]);
+                            else if (--r < 0) break;
+                        }
+                        if (s) {
+                            if (i > 63) jfail(name, "corrupt JPEG data: coefficient index out of range");
+                            b[i] = s;
+                        }
+                    }
+                }
+                if (eobrun > 0) {
+                    for (; i <= Se; i++) if (b[i] != 0) correct(b[i]);
+                    eobrun--;
+                }
+            };
             for (int uy = 0; uy < unitsY; uy++)
                 for (int ux = 0; ux < unitsX; ux++) {
                     if (restartInterval && untilRestart == 0) {
@@ -323,12 +406,14 @@ Image8 decode_jpeg_rgba8(const uint8_t* data, size_t size, bool flip, const std:
                         br.p = q + 2;
                         br.reset();
                         for (Component& k : comps) k.pred = 0;
+                        eobrun = 0;
                         untilRestart = restartInterval;
                     }
                     for (Component* k : scan) {
                         const int bw = interleaved ? k->h : 1, bh = interleaved ? k->v : 1;
                         for (int by = 0; by < bh; by++)
                             for (int bx = 0; bx < bw; bx++) {
+                                if (progressive) { progressive_block(k, ux * bw + bx, uy * bh + by); continue; }
                                 std::memset(block, 0, sizeof block);
                                 const uint16_t* q = quant[k->tq];
                                 int t = decode_symbol(br, dc[k->td], name);
@@ -364,6 +449,19 @@ Image8 decode_jpeg_rgba8(const uint8_t* data, size_t size, bool flip, const std:
         pos += size_t(len);
     }
     if (!sawFrame || !decodedAny) jfail(name, "no image data");
+    if (progressive) {                                          // all scans are in: de-quantise and transform every block
+        int block[64];
+        for (Component& k : comps) {
+            if (!haveQuant[k.tq]) jfail(name, "missing quantisation table");
+            const uint16_t* q = quant[k.tq];
+            for (int by = 0; by < k.blocksY; by++)
+                for (int bx = 0; bx < k.blocksX; bx++) {
+                    const int* b = &k.coef[(size_t(by) * size_t(k.blocksX) + size_t(bx)) * 64];
+                    for (int i = 0; i < 64; i++) block[kZigzag[i]] = clamp_coef(int64_t(b[i]) * int64_t(q[kZigzag[i]]));
+                    idct_islow(block, &k.plane[size_t(by) * 8 * size_t(k.stride) + size_t(bx) * 8], k.stride);
+                }
+        }
+    }
 
     Image8 img;
     img.width = width; img.height = height;

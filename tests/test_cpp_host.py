@@ -436,9 +436,10 @@ def _image_load(host, path, flip=0):
 
 
 def test_jpeg_decoder_matches_pil_byte_for_byte(host, tmp_path):
-    """host/jpeg.cpp (baseline Huffman JPEG: IJG integer IDCT, fancy chroma upsampling, fixed-point YCbCr -> RGB) against
-    PIL / libjpeg-turbo: identical bytes for 4:4:4, 4:2:2 and 4:2:0, odd sizes down to 1x1, optimised Huffman tables,
-    restart intervals, grayscale, quality 1..100; file textures flipped vertically like the reference's."""
+    """host/jpeg.cpp (baseline and progressive Huffman JPEG: IJG integer IDCT, fancy chroma upsampling, fixed-point
+    YCbCr -> RGB) against PIL / libjpeg-turbo: identical bytes for 4:4:4, 4:2:2 and 4:2:0, odd sizes down to 1x1, optimised
+    Huffman tables, restart intervals, grayscale, quality 5..100, sequential and progressive (spectral selection +
+    successive approximation: DC / AC first and refinement scans); file textures flipped vertically like the reference's."""
     from PIL import Image
     rng = np.random.default_rng(5)
 
@@ -453,14 +454,18 @@ def test_jpeg_decoder_matches_pil_byte_for_byte(host, tmp_path):
     cases = 0
     for (w, h) in [(64, 48), (37, 29), (16, 16), (1, 1), (3, 5), (130, 67), (17, 33)]:
         for sub in (0, 1, 2):
-            for kw in (dict(quality=30), dict(quality=75, optimize=True), dict(quality=95, restart_marker_blocks=2), dict(quality=100)):
+            for kw in (dict(quality=30), dict(quality=75, optimize=True), dict(quality=95, restart_marker_blocks=2), dict(quality=100),
+                       dict(quality=5, progressive=True), dict(quality=40, progressive=True), dict(quality=85, progressive=True, restart_marker_blocks=2),
+                       dict(quality=98, progressive=True)):
                 Image.fromarray(picture(w, h)).save(p, subsampling=sub, **kw)
+                assert (b"\xff\xc2" in p.read_bytes()) == ("progressive" in kw)
                 want = np.asarray(Image.open(p).convert("RGBA"))
                 assert (_image_load(host, p) == want).all(), (w, h, sub, kw)
                 cases += 1
-        Image.fromarray(picture(w, h)[..., 0]).save(p, quality=80)                 # grayscale
-        assert (_image_load(host, p) == np.asarray(Image.open(p).convert("RGBA"))).all()
-    assert cases == 84
+        for prog in (False, True):                                                 # grayscale
+            Image.fromarray(picture(w, h)[..., 0]).save(p, quality=80, progressive=prog)
+            assert (_image_load(host, p) == np.asarray(Image.open(p).convert("RGBA"))).all()
+    assert cases == 168
     Image.fromarray(picture(40, 30)).save(p, quality=90)
     assert (_image_load(host, p, flip=1) == np.asarray(Image.open(p).convert("RGBA"))[::-1]).all()
     # the same entry point still decodes PNG
@@ -474,7 +479,12 @@ def test_jpeg_decoder_refuses_what_it_does_not_support(host, tmp_path):
     img = np.random.default_rng(1).integers(0, 256, (24, 24, 3), dtype=np.uint8)
     p = tmp_path / "bad.jpg"
     Image.fromarray(img).save(p, progressive=True)
-    with pytest.raises(RuntimeError, match="Could not load image at path: .*progressive JPEG is not supported"):
+    data = bytearray(p.read_bytes())
+    sos = data.index(b"\xff\xda")
+    ns = data[sos + 4]
+    data[sos + 5 + 2 * ns] = 9                      # Ss > Se in the first scan header
+    p.write_bytes(bytes(data))
+    with pytest.raises(RuntimeError, match="Could not load image at path: .*bad progression parameters"):
         _image_load(host, p)
     Image.fromarray(img).convert("CMYK").save(p)
     with pytest.raises(RuntimeError, match="only grayscale and 3-component JPEG"):

@@ -1,4 +1,4 @@
-"""Robustness of the C++ host's file parsers (PNG inflate / defilter, baseline JPEG, JSON + glTF / GLB, OBJ, the TOML configuration): mutated inputs
+"""Robustness of the C++ host's file parsers (PNG inflate / defilter, baseline and progressive JPEG, JSON + glTF / GLB, OBJ, the TOML configuration): mutated inputs
 must be either decoded or refused with an exception — never a crash, an out-of-bounds access or undefined behaviour.
 The harness (tools/fuzz_host.cpp) is built with AddressSanitizer + UndefinedBehaviorSanitizer and fed ~2000 mutations
 (byte flips, truncations, zeroed and inserted runs, 0xFFFFFFFF words) of valid files."""
@@ -60,6 +60,8 @@ def test_mutated_files_never_crash_the_parsers(harness, tmp_path):
     d = tmp_path
     Image.fromarray(pic).save(d / "a.jpg", quality=80, subsampling=2)
     Image.fromarray(pic).save(d / "b.jpg", quality=60, subsampling=1, restart_marker_blocks=2)
+    Image.fromarray(pic).save(d / "p.jpg", quality=70, subsampling=2, progressive=True)
+    Image.fromarray(pic).save(d / "q.jpg", quality=90, subsampling=0, progressive=True, restart_marker_blocks=3)
     Image.fromarray(pic).save(d / "a.png")
     Image.fromarray(pic[..., 0]).save(d / "c.png")
     Image.fromarray(pic).convert("P").save(d / "d.png")
@@ -69,7 +71,7 @@ def test_mutated_files_never_crash_the_parsers(harness, tmp_path):
     from test_cpp_host import OBJ_FULL, REFERENCE_SCHEMA
     (d / "a.obj").write_text(OBJ_FULL)
     (d / "a.toml").write_text(REFERENCE_SCHEMA + "\n[render]\nwidth = 80\nheight = 60\ncamera_pos = [0.4, 0.9, 2.6]\nscene = \"cornell\"\n")
-    seeds = [d / "a.jpg", d / "b.jpg", d / "a.png", d / "c.png", d / "d.png", pathlib.Path(glb), pathlib.Path(gltf), d / "a.obj", d / "a.toml"]
+    seeds = [d / "a.jpg", d / "b.jpg", d / "p.jpg", d / "q.jpg", d / "a.png", d / "c.png", d / "d.png", pathlib.Path(glb), pathlib.Path(gltf), d / "a.obj", d / "a.toml"]
     files = [str(s) for s in seeds]                       # the valid files themselves must decode
     for s in seeds:
         raw = s.read_bytes()
