@@ -56,7 +56,6 @@ Image8 decode_png_rgba8(const uint8_t* data, size_t size, bool flip, const std::
     }
     if (!sawHeader || idat.empty()) fail(name, "missing IHDR or IDAT");
     if (width == 0 || height == 0 || width > 65536 || height > 65536) fail(name, "unsupported dimensions");
-    if (interlace != 0) fail(name, "interlaced PNG is not supported");
     int channels;
     switch (ctype) {
         case 0: channels = 1; break;
@@ -73,33 +72,52 @@ Image8 decode_png_rgba8(const uint8_t* data, size_t size, bool flip, const std::
     if (ctype == 3 && palette.size() < 3) fail(name, "palette image without PLTE");
 
     const size_t bitsPerPixel = size_t(channels) * depth;
-    const size_t stride = (size_t(width) * bitsPerPixel + 7) / 8;
     const size_t bpp = bitsPerPixel < 8 ? 1 : bitsPerPixel / 8;       // filter distance in bytes
-    std::vector<uint8_t> raw((stride + 1) * height);
+    // one pass for a sequential image, the seven Adam7 passes for an interlaced one: {first column, first row, column
+    // step, row step}; every pass is a small image of its own (own scanline length, own filter history)
+    struct Pass { uint32_t x0, y0, dx, dy, w, h; size_t stride, offset; };
+    static const uint32_t kAdam7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+    if (interlace > 1) fail(name, "unknown interlace method");
+    std::vector<Pass> passes;
+    size_t rawSize = 0;
+    for (int k = 0; k < (interlace ? 7 : 1); k++) {
+        Pass ps;
+        ps.x0 = interlace ? kAdam7[k][0] : 0; ps.y0 = interlace ? kAdam7[k][1] : 0;
+        ps.dx = interlace ? kAdam7[k][2] : 1; ps.dy = interlace ? kAdam7[k][3] : 1;
+        ps.w = width > ps.x0 ? (width - ps.x0 + ps.dx - 1) / ps.dx : 0;
+        ps.h = height > ps.y0 ? (height - ps.y0 + ps.dy - 1) / ps.dy : 0;
+        if (ps.w == 0 || ps.h == 0) continue;                       // an empty pass has no scanlines at all
+        ps.stride = (size_t(ps.w) * bitsPerPixel + 7) / 8;
+        ps.offset = rawSize;
+        rawSize += (ps.stride + 1) * ps.h;
+        passes.push_back(ps);
+    }
+    std::vector<uint8_t> raw(rawSize);
     uLongf rawLen = uLongf(raw.size());
     const int zrc = uncompress(raw.data(), &rawLen, idat.data(), uLong(idat.size()));
     if (zrc != Z_OK || rawLen != raw.size()) fail(name, "corrupt image data");
 
     // defilter in place (scanlines keep their leading filter byte)
-    std::vector<uint8_t> zero(stride, 0);
-    for (uint32_t y = 0; y < height; y++) {
-        uint8_t* cur = &raw[(stride + 1) * y + 1];
-        const uint8_t* up = y ? &raw[(stride + 1) * (y - 1) + 1] : zero.data();
-        const int filter = raw[(stride + 1) * y];
-        for (size_t x = 0; x < stride; x++) {
-            const int a = x >= bpp ? cur[x - bpp] : 0, b = up[x], c = x >= bpp ? up[x - bpp] : 0;
-            int v = cur[x];
-            switch (filter) {
-                case 0: break;
-                case 1: v += a; break;
-                case 2: v += b; break;
-                case 3: v += (a + b) >> 1; break;
-                case 4: v += paeth(a, b, c); break;
-                default: fail(name, "unknown scanline filter");
+    std::vector<uint8_t> zero((size_t(width) * bitsPerPixel + 7) / 8, 0);
+    for (const Pass& ps : passes)
+        for (uint32_t y = 0; y < ps.h; y++) {
+            uint8_t* cur = &raw[ps.offset + (ps.stride + 1) * y + 1];
+            const uint8_t* up = y ? &raw[ps.offset + (ps.stride + 1) * (y - 1) + 1] : zero.data();
+            const int filter = cur[-1];
+            for (size_t x = 0; x < ps.stride; x++) {
+                const int a = x >= bpp ? cur[x - bpp] : 0, b = up[x], c = x >= bpp ? up[x - bpp] : 0;
+                int v = cur[x];
+                switch (filter) {
+                    case 0: break;
+                    case 1: v += a; break;
+                    case 2: v += b; break;
+                    case 3: v += (a + b) >> 1; break;
+                    case 4: v += paeth(a, b, c); break;
+                    default: fail(name, "unknown scanline filter");
+                }
+                cur[x] = uint8_t(v);
             }
-            cur[x] = uint8_t(v);
         }
-    }
 
     Image8 img;
     img.width = int(width);
@@ -117,44 +135,47 @@ Image8 decode_png_rgba8(const uint8_t* data, size_t size, bool flip, const std::
         if (depth == 8) return uint8_t(v);
         return uint8_t(v * 255u / uint32_t(maxv));      // 1 -> x255, 2 -> x85, 4 -> x17
     };
-    for (uint32_t y = 0; y < height; y++) {
-        const uint8_t* row = &raw[(stride + 1) * y + 1];
-        uint8_t* out = &img.rgba[size_t(flip ? height - 1 - y : y) * width * 4];
-        for (uint32_t x = 0; x < width; x++, out += 4) {
-            switch (ctype) {
-                case 0: {
-                    const uint32_t g = sample(row, x);
-                    out[0] = out[1] = out[2] = to8(g);
-                    out[3] = 255;
-                    if (trns.size() >= 2 && g == ((uint32_t(trns[0]) << 8) | trns[1])) out[3] = 0;
-                    break;
-                }
-                case 2: {
-                    const uint32_t r = sample(row, 3 * x), g = sample(row, 3 * x + 1), b = sample(row, 3 * x + 2);
-                    out[0] = to8(r); out[1] = to8(g); out[2] = to8(b); out[3] = 255;
-                    if (trns.size() >= 6 && r == ((uint32_t(trns[0]) << 8) | trns[1]) && g == ((uint32_t(trns[2]) << 8) | trns[3]) &&
-                        b == ((uint32_t(trns[4]) << 8) | trns[5])) out[3] = 0;
-                    break;
-                }
-                case 3: {
-                    const uint32_t i = sample(row, x);
-                    if (size_t(i) * 3 + 2 >= palette.size()) fail(name, "palette index out of range");
-                    out[0] = palette[3 * i]; out[1] = palette[3 * i + 1]; out[2] = palette[3 * i + 2];
-                    out[3] = i < trns.size() ? trns[i] : 255;
-                    break;
-                }
-                case 4: {
-                    out[0] = out[1] = out[2] = to8(sample(row, 2 * x));
-                    out[3] = to8(sample(row, 2 * x + 1));
-                    break;
-                }
-                default: {
-                    for (int k = 0; k < 4; k++) out[k] = to8(sample(row, 4 * x + k));
-                    break;
+    for (const Pass& ps : passes)
+        for (uint32_t py = 0; py < ps.h; py++) {
+            const uint8_t* row = &raw[ps.offset + (ps.stride + 1) * py + 1];
+            const uint32_t y = ps.y0 + py * ps.dy;
+            uint8_t* line = &img.rgba[size_t(flip ? height - 1 - y : y) * width * 4];
+            for (uint32_t x = 0; x < ps.w; x++) {
+                uint8_t* out = line + size_t(ps.x0 + x * ps.dx) * 4;
+                switch (ctype) {
+                    case 0: {
+                        const uint32_t g = sample(row, x);
+                        out[0] = out[1] = out[2] = to8(g);
+                        out[3] = 255;
+                        if (trns.size() >= 2 && g == ((uint32_t(trns[0]) << 8) | trns[1])) out[3] = 0;
+                        break;
+                    }
+                    case 2: {
+                        const uint32_t r = sample(row, 3 * x), g = sample(row, 3 * x + 1), b = sample(row, 3 * x + 2);
+                        out[0] = to8(r); out[1] = to8(g); out[2] = to8(b); out[3] = 255;
+                        if (trns.size() >= 6 && r == ((uint32_t(trns[0]) << 8) | trns[1]) && g == ((uint32_t(trns[2]) << 8) | trns[3]) &&
+                            b == ((uint32_t(trns[4]) << 8) | trns[5])) out[3] = 0;
+                        break;
+                    }
+                    case 3: {
+                        const uint32_t i = sample(row, x);
+                        if (size_t(i) * 3 + 2 >= palette.size()) fail(name, "palette index out of range");
+                        out[0] = palette[3 * i]; out[1] = palette[3 * i + 1]; out[2] = palette[3 * i + 2];
+                        out[3] = i < trns.size() ? trns[i] : 255;
+                        break;
+                    }
+                    case 4: {
+                        out[0] = out[1] = out[2] = to8(sample(row, 2 * x));
+                        out[3] = to8(sample(row, 2 * x + 1));
+                        break;
+                    }
+                    default: {
+                        for (int k = 0; k < 4; k++) out[k] = to8(sample(row, 4 * x + k));
+                        break;
+                    }
                 }
             }
         }
-    }
     return img;
 }
 

@@ -377,6 +377,104 @@ def test_png_decoder_matches_pil_on_every_colour_type(host, tmp_path):
     assert (png_load(host, tmp_path / "own.png", False) == rgba).all()
 
 
+def _write_png(path, samples, ctype, depth, interlace, rng, palette=None, trns=None):
+    """A PNG writer for the tests: `samples` is (h, w, channels) of full-depth sample values; scanlines get every filter
+    type in turn; interlace = 1 splits the image into the seven Adam7 passes (PNG specification, section 8.2)."""
+    import struct
+    import zlib
+    h, w, ch = samples.shape
+    bpp = max(1, ch * depth // 8)
+
+    def pack(rows):                                     # (n, pw, ch) sample rows -> list of packed byte rows
+        out = []
+        for r in rows:
+            flat = r.reshape(-1)
+            if depth == 16:
+                out.append(flat.astype(">u2").tobytes())
+            elif depth == 8:
+                out.append(flat.astype(np.uint8).tobytes())
+            else:
+                bits = np.zeros(((flat.size * depth + 7) // 8) * 8, np.uint8)
+                for k in range(depth):
+                    bits[k:flat.size * depth:depth] = (flat >> (depth - 1 - k)) & 1
+                out.append(np.packbits(bits).tobytes())
+        return out
+
+    def paeth(a, b, c):
+        pa, pb, pc = abs(b - c), abs(a - c), abs(a + b - 2 * c)
+        return a if pa <= pb and pa <= pc else (b if pb <= pc else c)
+
+    def filtered(lines, first):
+        out, prev = bytearray(), bytes(len(lines[0])) if lines else b""
+        for i, line in enumerate(lines):
+            f = (first + i) % 5
+            out.append(f)
+            for x, v in enumerate(line):
+                a = line[x - bpp] if x >= bpp else 0
+                b = prev[x]
+                c = prev[x - bpp] if x >= bpp else 0
+                out.append((v - (0, a, b, (a + b) >> 1, paeth(a, b, c))[f]) & 255)
+            prev = line
+        return bytes(out)
+    passes = [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)] if interlace else [(0, 0, 1, 1)]
+    raw = b""
+    for k, (x0, y0, dx, dy) in enumerate(passes):
+        sub = samples[y0::dy, x0::dx]
+        if sub.shape[0] and sub.shape[1]:
+            raw += filtered(pack(sub), int(rng.integers(0, 5)) + k)
+
+    def chunk(t, body):
+        return struct.pack(">I", len(body)) + t + body + struct.pack(">I", zlib.crc32(t + body))
+    data = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, interlace))
+    if palette is not None:
+        data += chunk(b"PLTE", bytes(palette))
+    if trns is not None:
+        data += chunk(b"tRNS", bytes(trns))
+    z = zlib.compress(raw, 6)
+    half = len(z) // 2
+    data += chunk(b"IDAT", z[:half]) + chunk(b"IDAT", z[half:]) + chunk(b"IEND", b"")
+    path.write_bytes(data)
+
+
+def test_png_decoder_adam7_interlace_matches_pil(host, tmp_path):
+    """Interlaced PNGs (stb_image, the reference's decoder, reads them): seven passes with their own scanline lengths and
+    filter histories, empty passes for images narrower / shorter than the 8 x 8 pattern, sub-byte depths packed per pass.
+    PIL cannot write Adam7, so the files come from the writer above; PIL reads them and must agree byte for byte."""
+    from PIL import Image
+    rng = np.random.default_rng(31)
+    p = tmp_path / "i.png"
+    kinds = [(0, 1, 1), (0, 2, 1), (0, 4, 1), (0, 8, 1), (0, 16, 1), (2, 8, 3), (2, 16, 3), (3, 1, 1), (3, 2, 1), (3, 4, 1), (3, 8, 1), (4, 8, 2),
+             (4, 16, 2), (6, 8, 4), (6, 16, 4)]
+    cases = 0
+    for (w, h) in [(1, 1), (2, 3), (3, 2), (4, 4), (5, 7), (8, 8), (9, 9), (33, 17), (16, 40)]:
+        for ctype, depth, ch in kinds:
+            top = (1 << depth) if ctype != 3 else min(1 << depth, 23)
+            samples = rng.integers(0, top, (h, w, ch)).astype(np.uint32)
+            palette = rng.integers(0, 256, 3 * top).astype(np.uint8) if ctype == 3 else None
+            trns = rng.integers(0, 256, 5).astype(np.uint8) if ctype == 3 and depth >= 4 else None
+            for interlace in (1, 0):
+                _write_png(p, samples, ctype, depth, interlace, rng, palette, trns)
+                got = png_load(host, p, False)
+                if depth == 16:                          # PIL keeps 16 bits for grey and rescales; the host keeps the high byte
+                    want = (samples >> 8).astype(np.uint8)
+                    want = {1: lambda a: np.concatenate([a, a, a, np.full_like(a, 255)], 2), 2: lambda a: np.concatenate([a[..., :1]] * 3 + [a[..., 1:]], 2),
+                            3: lambda a: np.concatenate([a, np.full_like(a[..., :1], 255)], 2), 4: lambda a: a}[ch](want)
+                else:
+                    want = np.asarray(Image.open(p).convert("RGBA"))
+                assert (got == want).all(), (w, h, ctype, depth, interlace)
+                assert (png_load(host, p, True) == want[::-1]).all()
+                cases += 1
+    assert cases == 9 * 15 * 2
+    data = bytearray(p.read_bytes())
+    data[28] = 2                                           # interlace method 2 does not exist (the checksum is checked first)
+    import struct
+    import zlib
+    data[29:33] = struct.pack(">I", zlib.crc32(bytes(data[12:29])))
+    p.write_bytes(bytes(data))
+    with pytest.raises(RuntimeError, match="unknown interlace method"):
+        png_load(host, p, False)
+
+
 def test_png_decoder_refuses_what_it_does_not_support(host, tmp_path):
     from PIL import Image
     (tmp_path / "not.png").write_bytes(b"JFIF" * 10)

@@ -68,10 +68,12 @@ def test_mutated_files_never_crash_the_parsers(harness, tmp_path):
     glb, _ = gf.build(d)
     (d / "ext").mkdir()
     gltf, _ = gf.build(d / "ext", external=True, jpeg=True)
-    from test_cpp_host import OBJ_FULL, REFERENCE_SCHEMA
+    from test_cpp_host import OBJ_FULL, REFERENCE_SCHEMA, _write_png
+    _write_png(d / "i.png", pic[:19, :21].astype(np.uint32), 2, 8, 1, rng)                        # Adam7
+    _write_png(d / "j.png", (pic[:9, :13, :1] >> 6).astype(np.uint32), 0, 2, 1, rng)             # Adam7, 2-bit grey
     (d / "a.obj").write_text(OBJ_FULL)
     (d / "a.toml").write_text(REFERENCE_SCHEMA + "\n[render]\nwidth = 80\nheight = 60\ncamera_pos = [0.4, 0.9, 2.6]\nscene = \"cornell\"\n")
-    seeds = [d / "a.jpg", d / "b.jpg", d / "p.jpg", d / "q.jpg", d / "a.png", d / "c.png", d / "d.png", pathlib.Path(glb), pathlib.Path(gltf), d / "a.obj", d / "a.toml"]
+    seeds = [d / "a.jpg", d / "b.jpg", d / "p.jpg", d / "q.jpg", d / "a.png", d / "c.png", d / "d.png", d / "i.png", d / "j.png", pathlib.Path(glb), pathlib.Path(gltf), d / "a.obj", d / "a.toml"]
     files = [str(s) for s in seeds]                       # the valid files themselves must decode
     for s in seeds:
         raw = s.read_bytes()
