@@ -25,7 +25,8 @@ an accident of that call, not a specification. Rules of this importer where the 
   * TRS node transforms are composed in float64 (T * R * S, quaternion -> matrix by the standard formula), products
     are accumulated in float64 in a fixed order and rounded to float32 once per instance;
   * images: PNG and baseline / progressive JPEG (CMYK JPEG is refused loudly);
-  * primitive modes other than TRIANGLES and sparse accessors are refused loudly.
+  * sparse accessors are resolved (base elements or zeros, then the substitutions);
+  * primitive modes other than TRIANGLES are refused loudly.
 The C++ host (host/gltf.cpp) implements the same rules; tests/test_gltf.py checks both yield identical tables.
 """
 import base64
@@ -117,8 +118,6 @@ def _read_accessor(asset, index, want_float=True):
     normalized -> c / max (signed: max(c / max, -1)), as the glTF specification and KHR_mesh_quantization define."""
     doc = asset.doc
     acc = doc["accessors"][index]
-    if "sparse" in acc:
-        raise RuntimeError("Failed to parse glTF: sparse accessors are not supported")
     dt, size = _COMPONENT[acc["componentType"]]
     ncomp = _NCOMP[acc["type"]]
     count = int(acc["count"])
@@ -135,6 +134,31 @@ def _read_accessor(asset, index, want_float=True):
         raw = np.frombuffer(buf, np.uint8)
         idx = start + np.arange(count, dtype=np.int64)[:, None] * stride + np.arange(size * ncomp, dtype=np.int64)[None, :]
         out = np.ascontiguousarray(raw[idx]).view(dt).reshape(count, ncomp)
+    if "sparse" in acc:
+        # glTF 2.0, 3.6.2.3: `count` elements replaced; strictly increasing element numbers, tightly packed values
+        sp = acc["sparse"]
+        n = int(sp["count"])
+        idt, isize = _COMPONENT[sp["indices"]["componentType"]]
+        if idt not in (np.uint8, np.uint16, np.uint32):
+            raise RuntimeError("Failed to parse glTF: bad sparse index type")
+
+        def view(ref, nbytes):
+            bv = doc["bufferViews"][ref["bufferView"]]
+            buf = asset.buffers[bv["buffer"]]
+            voff = int(bv.get("byteOffset", 0))
+            start = voff + int(ref.get("byteOffset", 0))
+            if start + nbytes > len(buf) or start + nbytes > voff + int(bv["byteLength"]):
+                raise RuntimeError("Failed to parse glTF: accessor %d reads past its buffer view" % index)
+            return bytes(buf[start:start + nbytes])
+        if n > count:
+            raise RuntimeError("Failed to parse glTF: bad sparse accessor")
+        out = out.copy()
+        if n:
+            at = np.frombuffer(view(sp["indices"], n * isize), idt).astype(np.int64)
+            vals = np.frombuffer(view(sp["values"], n * size * ncomp), dt).reshape(n, ncomp)
+            if at.max() >= count or (np.diff(at) <= 0).any():
+                raise RuntimeError("Failed to parse glTF: bad sparse accessor")
+            out[at] = vals
     if not want_float:
         return out
     if dt == np.float32:

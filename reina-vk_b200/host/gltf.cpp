@@ -313,11 +313,11 @@ struct AccessorView {
     int ncomp = 0, csize = 0;
     long ctype = 0;
     bool normalized = false;
+    std::shared_ptr<std::vector<uint8_t>> owned;   // sparse accessors: a packed copy with the substitutions applied
 };
 
 AccessorView open_accessor(const Asset& a, long index) {
     const Json& acc = a.doc.at("accessors").at(size_t(index));
-    if (acc.has("sparse")) throw std::runtime_error("Failed to parse glTF: sparse accessors are not supported");
     AccessorView v;
     v.ctype = acc.at("componentType").integer();
     v.csize = component_size(v.ctype);
@@ -338,6 +338,42 @@ AccessorView open_accessor(const Asset& a, long index) {
         if (need > buf.size() || need > viewOff + size_t(bv.at("byteLength").integer()))
             throw std::runtime_error("Failed to parse glTF: accessor " + std::to_string(index) + " reads past its buffer view");
         v.base = buf.data() + start;
+    }
+    if (const Json* sp = acc.find("sparse")) {
+        // glTF 2.0, 3.6.2.3: the accessor's elements (zeros without a buffer view) with `count` of them replaced;
+        // indices are strictly increasing element numbers, values are tightly packed elements of the accessor's type
+        const size_t elem = size_t(v.csize) * size_t(v.ncomp);
+        auto packed = std::make_shared<std::vector<uint8_t>>(v.count * elem, uint8_t(0));
+        if (v.base) for (size_t i = 0; i < v.count; i++) std::memcpy(packed->data() + i * elem, v.base + i * v.stride, elem);
+        const size_t n = size_t(sp->at("count").integer());
+        const Json& si = sp->at("indices");
+        const Json& sv = sp->at("values");
+        const long ict = si.at("componentType").integer();
+        if (ict != 5121 && ict != 5123 && ict != 5125) throw std::runtime_error("Failed to parse glTF: bad sparse index type");
+        const size_t isize = size_t(component_size(ict));
+        auto view = [&](const Json& ref, size_t bytes) -> const uint8_t* {
+            const Json& bv = a.doc.at("bufferViews").at(size_t(ref.at("bufferView").integer()));
+            const size_t bi = size_t(bv.at("buffer").integer());
+            if (bi >= a.buffers.size()) throw std::runtime_error("Failed to parse glTF: buffer index out of range");
+            const size_t viewOff = size_t(bv.integer_or("byteOffset", 0)), start = viewOff + size_t(ref.integer_or("byteOffset", 0));
+            if (start + bytes > a.buffers[bi].size() || start + bytes > viewOff + size_t(bv.at("byteLength").integer()))
+                throw std::runtime_error("Failed to parse glTF: accessor " + std::to_string(index) + " reads past its buffer view");
+            return a.buffers[bi].data() + start;
+        };
+        if (n > v.count) throw std::runtime_error("Failed to parse glTF: bad sparse accessor");
+        const uint8_t* ip = n ? view(si, n * isize) : nullptr;
+        const uint8_t* vp = n ? view(sv, n * elem) : nullptr;
+        size_t previous = 0;
+        for (size_t k = 0; k < n; k++) {
+            size_t at = 0;
+            for (size_t b = 0; b < isize; b++) at |= size_t(ip[k * isize + b]) << (8 * b);
+            if (at >= v.count || (k && at <= previous)) throw std::runtime_error("Failed to parse glTF: bad sparse accessor");
+            previous = at;
+            std::memcpy(packed->data() + at * elem, vp + k * elem, elem);
+        }
+        v.owned = packed;
+        v.base = packed->data();
+        v.stride = elem;
     }
     return v;
 }

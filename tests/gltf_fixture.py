@@ -90,8 +90,10 @@ def _jpeg_bytes(img, **kw):
     return b.getvalue()
 
 
-def build(tmp_path, external=False, jpeg=False):
-    """Writes scene.glb (external=False) or scene.gltf + scene.bin + tex0.png (external=True) and returns the path."""
+def build(tmp_path, external=False, jpeg=False, sparse=False):
+    """Writes scene.glb (external=False) or scene.gltf + scene.bin + tex0.png (external=True) and returns the path.
+    sparse=True stores the same scene through sparse accessors: the sphere's POSITION over a perturbed base array, the
+    lamp's NORMAL over no buffer view at all (zeros + substitutions)."""
     rng = np.random.RandomState(4)
     B = _Bin()
     # mesh 0: floor grid — interleaved POSITION/NORMAL (stride 24), TANGENT vec4, normalized ushort UVs, ubyte indices
@@ -109,7 +111,15 @@ def build(tmp_path, external=False, jpeg=False):
     sp, suv, sn, st = _sphere(16, 10, 0.3)
     upper = st[: st.shape[0] // 2]
     lower = st[st.shape[0] // 2:]
-    a_spos = B.accessor(B.view(sp.tobytes()), 5126, sp.shape[0], "VEC3", minmax=(sp.min(0), sp.max(0)))
+    if sparse:
+        k = np.array([1, 5, 17, 40, sp.shape[0] - 1], np.int64)
+        base = sp.copy()
+        base[k] += 7.0
+        a_spos = B.accessor(B.view(base.tobytes()), 5126, sp.shape[0], "VEC3", minmax=(sp.min(0), sp.max(0)))
+        B.accessors[a_spos]["sparse"] = {"count": len(k), "indices": {"bufferView": B.view(k.astype(np.uint16).tobytes()), "componentType": 5123},
+                                         "values": {"bufferView": B.view(sp[k].tobytes())}}
+    else:
+        a_spos = B.accessor(B.view(sp.tobytes()), 5126, sp.shape[0], "VEC3", minmax=(sp.min(0), sp.max(0)))
     a_snrm = B.accessor(B.view(sn.tobytes()), 5126, sp.shape[0], "VEC3")
     a_suv = B.accessor(B.view(suv.tobytes()), 5126, sp.shape[0], "VEC2")
     a_si0 = B.accessor(B.view(upper.astype(np.uint16).tobytes()), 5123, upper.size, "SCALAR")
@@ -118,7 +128,15 @@ def build(tmp_path, external=False, jpeg=False):
     q = np.array([[-0.4, 0, -0.4], [0.4, 0, 0.4], [0.4, 0, -0.4], [-0.4, 0, -0.4], [-0.4, 0, 0.4], [0.4, 0, 0.4]], np.float32)
     qn = np.tile(np.array([[0, -1, 0]], np.float32), (6, 1))
     a_qpos = B.accessor(B.view(q.tobytes()), 5126, 6, "VEC3", minmax=(q.min(0), q.max(0)))
-    a_qnrm = B.accessor(B.view(qn.tobytes()), 5126, 6, "VEC3")
+    if sparse:
+        pad = B.view(bytes(8))                                   # values start at a byteOffset inside their view
+        B.accessors.append({"componentType": 5126, "count": 6, "type": "VEC3",
+                            "sparse": {"count": 6, "indices": {"bufferView": B.view(np.arange(6, dtype=np.uint8).tobytes()), "componentType": 5121},
+                                       "values": {"bufferView": B.view(bytes(12) + qn.tobytes()), "byteOffset": 12}}})
+        a_qnrm = len(B.accessors) - 1
+        assert pad >= 0
+    else:
+        a_qnrm = B.accessor(B.view(qn.tobytes()), 5126, 6, "VEC3")
     # mesh 3: never referenced by the default scene
     a_upos = B.accessor(B.view(q.tobytes()), 5126, 6, "VEC3", minmax=(q.min(0), q.max(0)))
 
@@ -127,10 +145,10 @@ def build(tmp_path, external=False, jpeg=False):
     nmap = np.zeros((32, 32, 4), np.uint8)
     nmap[..., 0] = 128 + 60 * np.sin(x * 12); nmap[..., 1] = 128 + 60 * np.cos(y * 12); nmap[..., 2] = 230; nmap[..., 3] = 255
     images = []
-    if external and jpeg:       # a JPEG file (4:2:0, flipped on load) and a data-URI JPEG (4:4:4, not flipped)
+    if external and jpeg:       # a JPEG file (4:2:0, flipped on load) and a progressive data-URI JPEG (4:4:4, not flipped)
         (tmp_path / "tex0.jpg").write_bytes(_jpeg_bytes(tex0, quality=85, subsampling=2))
         images.append({"uri": "tex0.jpg"})
-        images.append({"uri": "data:image/jpeg;base64," + base64.b64encode(_jpeg_bytes(nmap, quality=95, subsampling=0)).decode()})
+        images.append({"uri": "data:image/jpeg;base64," + base64.b64encode(_jpeg_bytes(nmap, quality=95, subsampling=0, progressive=True)).decode()})
     elif external:
         (tmp_path / "tex0.png").write_bytes(_png_bytes(tex0))
         images.append({"uri": "tex0.png"})

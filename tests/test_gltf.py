@@ -87,6 +87,36 @@ def test_cpp_importer_tables_identical_to_python(host, rb, gl, tmp_path, externa
 
 
 @pytest.mark.filterwarnings("ignore:falling back to UV")
+def test_sparse_accessors_resolve_to_the_dense_scene(host, rb, gl, tmp_path):
+    """glTF 2.0 3.6.2.3 (fastgltf resolves sparse accessors for the reference): base elements — or zeros when the accessor
+    has no buffer view — with the listed elements replaced. The sparse file must give the tables of the dense one, in
+    both importers; malformed index lists are refused."""
+    (tmp_path / "d").mkdir()
+    (tmp_path / "s").mkdir()
+    dense, _ = gf.build(tmp_path / "d")
+    sparse, _ = gf.build(tmp_path / "s", sparse=True)
+    want = py_tables(gl.loadScene(dense).build(require_emitter=True))
+    assert_tables_identical(py_tables(gl.loadScene(sparse).build(require_emitter=True)), want)
+    host.rbhost_tables_gltf.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    h = C.c_void_p()
+    assert host.rbhost_tables_gltf(sparse.encode(), 1, C.byref(h)) == 0, err(host)
+    assert_tables_identical(cpp_tables(host, rb, h), want)
+    host.rbhost_tables_free(h)
+    # indices out of order
+    (tmp_path / "e").mkdir()
+    ext, _ = gf.build(tmp_path / "e", external=True, sparse=True)
+    doc = json.loads(open(ext).read())
+    acc = [a for a in doc["accessors"] if "sparse" in a and "bufferView" in a][0]
+    bv = doc["bufferViews"][acc["sparse"]["indices"]["bufferView"]]
+    raw = bytearray((tmp_path / "e" / "scene.bin").read_bytes())
+    raw[bv["byteOffset"]:bv["byteOffset"] + 4] = raw[bv["byteOffset"] + 2:bv["byteOffset"] + 4] + raw[bv["byteOffset"]:bv["byteOffset"] + 2]
+    (tmp_path / "e" / "scene.bin").write_bytes(bytes(raw))
+    with pytest.raises(RuntimeError, match="bad sparse accessor"):
+        gl.loadScene(ext)
+    assert host.rbhost_tables_gltf(ext.encode(), 1, C.byref(h)) != 0 and "bad sparse accessor" in err(host)
+
+
+@pytest.mark.filterwarnings("ignore:falling back to UV")
 def test_jpeg_textures_give_identical_tables_too(host, rb, gl, tmp_path):
     """Most real .glb files embed JPEG images: the C++ host decodes baseline JPEG itself (host/jpeg.cpp, the IJG integer
     pipeline) and must hand over the same texels PIL gives the Python host."""

@@ -65,7 +65,7 @@ def test_mutated_files_never_crash_the_parsers(harness, tmp_path):
     Image.fromarray(pic).save(d / "a.png")
     Image.fromarray(pic[..., 0]).save(d / "c.png")
     Image.fromarray(pic).convert("P").save(d / "d.png")
-    glb, _ = gf.build(d)
+    glb, _ = gf.build(d, sparse=True)
     (d / "ext").mkdir()
     gltf, _ = gf.build(d / "ext", external=True, jpeg=True)
     from test_cpp_host import OBJ_FULL, REFERENCE_SCHEMA, _write_png
