@@ -43,6 +43,8 @@ from .scene import Material, Scene
 
 _COMPONENT = {5120: (np.int8, 1), 5121: (np.uint8, 1), 5122: (np.int16, 2), 5123: (np.uint16, 2), 5125: (np.uint32, 4),
               5126: (np.float32, 4)}
+_ENABLED_EXTENSIONS = ("KHR_mesh_quantization", "KHR_texture_transform", "KHR_materials_variants", "KHR_materials_transmission",
+                       "KHR_materials_clearcoat", "KHR_materials_emissive_strength")
 _NCOMP = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4, "MAT2": 4, "MAT3": 9, "MAT4": 16}
 
 
@@ -92,6 +94,11 @@ def loadGltf(filepath):
             doc = json.loads(raw.decode("utf-8"))
         except ValueError as e:
             raise RuntimeError("Failed to parse glTF: " + str(e))
+    # the parser of the reference is created with exactly these extensions (gltfloader.cpp:87-93) and rejects a file that
+    # REQUIRES any other one (compressed geometry, basis textures, ...)
+    for e in doc.get("extensionsRequired", []):
+        if e not in _ENABLED_EXTENSIONS:
+            raise RuntimeError("Failed to parse glTF: required extension " + str(e) + " is not enabled")
     buffers = []
     for i, b in enumerate(doc.get("buffers", [])):
         uri = b.get("uri")

@@ -265,6 +265,18 @@ Asset load_gltf(const std::string& filepath) {
         a.doc = JsonParser(reinterpret_cast<const char*>(raw.data()), reinterpret_cast<const char*>(raw.data()) + raw.size()).parse();
     }
     if (a.doc.type != Json::Object) throw std::runtime_error("Failed to parse glTF: JSON: top level is not an object");
+    // the parser of the reference is created with exactly these extensions (gltfloader.cpp:87-93) and rejects a file
+    // that REQUIRES any other one (compressed geometry, basis textures, ...)
+    if (const Json* req = a.doc.find("extensionsRequired")) {
+        static const char* kEnabled[] = {"KHR_mesh_quantization", "KHR_texture_transform", "KHR_materials_variants",
+                                         "KHR_materials_transmission", "KHR_materials_clearcoat", "KHR_materials_emissive_strength"};
+        for (size_t i = 0; i < req->size(); i++) {
+            const std::string& e = req->at(i).string();
+            bool ok = false;
+            for (const char* k : kEnabled) ok = ok || e == k;
+            if (!ok) throw std::runtime_error("Failed to parse glTF: required extension " + e + " is not enabled");
+        }
+    }
     if (const Json* bufs = a.doc.find("buffers")) {
         for (size_t i = 0; i < bufs->size(); i++) {
             const Json& b = bufs->at(i);

@@ -146,6 +146,8 @@ def test_errors_match_the_reference_messages(host, rb, gl, tmp_path):
         assert host.rbhost_tables_gltf(path.encode(), 0, C.byref(h)) != 0 and needle in err(host), err(host)
     both(str(tmp_path / "absent.glb"), "Failed to find glTF file")
     both(_write_gltf(tmp_path, {"asset": {"version": "2.0"}}), "No scenes supplied in gLTF file")
+    both(_write_gltf(tmp_path, {"asset": {"version": "2.0"}, "extensionsRequired": ["KHR_mesh_quantization", "KHR_draco_mesh_compression"],
+                                "scenes": [{"nodes": []}]}, "draco.gltf"), "required extension KHR_draco_mesh_compression is not enabled")
     (tmp_path / "junk.gltf").write_text("{ not json")
     both(str(tmp_path / "junk.gltf"), "Failed to parse glTF")
     tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
