@@ -230,6 +230,21 @@ def test_random_hits_with_random_materials_match_the_compiled_shaders(ol, rb):
     assert seen == {0, 1, 2, 3}
 
 
+@pytest.mark.skipif(not os.path.isdir(RT_SHADERS), reason="reference checkout not present")
+def test_shadow_miss_shader_clears_the_occlusion_flag():
+    """shadow.rmiss.spv is the whole any-hit contract of the reference — the caller presets
+    occluded = true, traces with TerminateOnFirstHit | SkipClosestHit, and only a miss clears the flag (nee.h.glsl:126-144). The
+    binary ships although raytrace.rgen.spv never calls it (NEE compiled out); k_shadow / the oracle's occluded() return
+    exactly that flag."""
+    import spirv_interp as sp
+    m = sp.Module(os.path.join(RT_SHADERS, "shadow.rmiss.spv"))
+    it = sp.Interpreter(m, {}, max_steps=1000)
+    for preset in (True, False):
+        payload = [preset]
+        it.run({("storage", 5342): payload}, builtins={})
+        assert payload == [False]
+
+
 @pytest.mark.gpu
 def test_cuda_path_equals_the_reference_ray_tracing_shaders(rb):
     for name, case, wl, g in _rt_cases(rb):
