@@ -231,6 +231,46 @@ def test_random_hits_with_random_materials_match_the_compiled_shaders(ol, rb):
 
 
 @pytest.mark.skipif(not os.path.isdir(RT_SHADERS), reason="reference checkout not present")
+def test_the_accumulated_distance_deviation_is_exactly_the_missing_reset(ol, rb):
+    """DESIGN.md 2, documented deviation: upstream never clears pld.accumulatedDistance between the samples
+    of a pixel, so a path that enters glass inherits the distance of an earlier path of the same pixel that ended inside
+    glass, and its Beer-Lambert factor is too dark. This repository clears it per path. A glass sphere under the open sky
+    makes the effect frequent: the shipped binaries and the oracle differ in some pixels, and the SAME binaries with the
+    payload word cleared at every camera ray (recognised by its origin) agree with the oracle in every pixel — the
+    deviation is that reset and nothing else."""
+    import spirv_rt
+    cfg = rb.configs
+    sc = rb.Scene()
+    sc.addObject(rb.meshes.uv_sphere(24, 12, radius=0.3), cfg.translate((0.0, 0.3, 0.35)), rb.Material(**cfg.GLASS))
+    sc.addObject(rb.meshes.quad((-2, 0, -2), (-2, 0, 2), (2, 0, 2), (2, 0, -2)), cfg.IDENT, rb.Material(materialIdx=0, albedo=(0.7, 0.7, 0.7)))
+    tables = sc.build(require_emitter=False)
+    W, H = 14, 10
+    pc = rb.camera.push_constants(W, H, (0.0, 0.32, 1.25), (0.0, 0.3, 0.35), 32.0, sample_batch=0, samples_per_pixel=8, max_bounces=3,
+                                  defocus_multiplier=0.0)
+    cam = [np.float32(v) for v in pc.invView[12:15]]
+    ACCUMULATED_DISTANCE = 11                            # member index in HitPayload (shaderCommon.h.glsl:18-31)
+    cleared = [0]
+
+    class ResetPerPath(spirv_rt.Pipeline):
+        def _trace_ray(self, interp, env, a):
+            origin = interp.val(env, a[6])
+            if all(np.float32(o) == c for o, c in zip(origin, cam)):      # a camera ray: the first segment of a path
+                payload = interp.val(env, a[10]).load()
+                cleared[0] += int(payload[ACCUMULATED_DISTANCE] != 0)
+                payload[ACCUMULATED_DISTANCE] = np.float32(0)
+            return super()._trace_ray(interp, env, a)
+    blank = lambda: np.zeros((H, W, 4), np.float32)
+    shipped = spirv_rt.Pipeline(RT_SHADERS, tables, ol).render_batch(pc, W, H, blank())
+    reset = ResetPerPath(RT_SHADERS, tables, ol).render_batch(pc, W, H, blank())
+    got, _ = ol.OracleScene(tables).render_batch(W, H, 0, pc, blank())
+    differing = lambda a, b: int((a.view(np.uint32) != b.view(np.uint32)).any(axis=2).sum())
+    assert cleared[0] > 20 and 0 < differing(shipped, got) < W * H // 2
+    assert differing(reset, got) == 0
+    # the inherited distance only ever darkens a sample
+    assert (shipped[..., :3] <= got[..., :3]).all()
+
+
+@pytest.mark.skipif(not os.path.isdir(RT_SHADERS), reason="reference checkout not present")
 def test_shadow_miss_shader_clears_the_occlusion_flag():
     """shadow.rmiss.spv is the whole any-hit contract of the reference — the caller presets
     occluded = true, traces with TerminateOnFirstHit | SkipClosestHit, and only a miss clears the flag (nee.h.glsl:126-144). The
