@@ -237,7 +237,11 @@ RB200_API int rb200_context_set_stream(RB200Context* ctx, void* cuda_stream);
 RB200_API int rb200_context_set_tiles(RB200Context* ctx, uint32_t tileRank, uint32_t tileCount, uint32_t tileSize);
 
 /* Copy the scene tables to the device and build the acceleration structure (LBVH -> 8-wide compressed BVH).
- * The scene is immutable afterwards (the reference never updates an acceleration structure). */
+ * The scene is immutable afterwards (the reference never updates an acceleration structure).
+ * With RB200_FLAG_NEE: RB200_ERR_NO_EMITTER without an emissive instance (src/scene/Instances.cpp:125-127), and
+ * RB200_ERR_INVALID_ARGUMENT if light sampling would read past the index buffer — nee.h.glsl:97-105 addresses an
+ * emitter's triangles as indices[3 * cdfSlot + indexOffset] with cdfSlot counted over the CONCATENATED triangle CDF,
+ * which is only the emitter's own triangle for an emitter whose CDF starts at slot 0 (reproduced as is otherwise). */
 RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* desc, RB200Scene** out);
 RB200_API int rb200_scene_destroy(RB200Scene* scene);
 RB200_API int rb200_scene_bvh_info(const RB200Scene* scene, RB200BvhInfo* out);

@@ -11,6 +11,9 @@ float kat_random(uint32_t* state);
 vec3 kat_offset(vec3 p, vec3 n);
 vec3 kat_sky(vec3 dir);
 float kat_power_heuristic(float a, float b);
+void kat_light_sample(const Scene& s, const RB200RtPushConsts& pc, uint32_t* rng, float out[11]);
+void kat_direct_light_lambertian(const Scene& s, const RB200RtPushConsts& pc, const float o[3], const float n[3],
+                                 const float albedo[3], uint32_t* rng, float out[4]);
 void kat_trace_main(const Scene& s, const float o[3], const float d[3], uint32_t* rngState, int insideDielectric,
                     float accumulatedDistance, float out[21], uint32_t* flags);
 void kat_bump(const uint8_t* rgba, uint32_t w, uint32_t h, const float uv[2], const float rayIn[3], const float tbn[9],
@@ -75,6 +78,9 @@ ORACLE_API int oracle_render_batch_tiles(void* scene, uint32_t W, uint32_t H, ui
     if (tileCount == 0 || tileRank >= tileCount || tileSize == 0) return -1;
     TilePartition tiles; tiles.rank = tileRank; tiles.count = tileCount; tiles.size = tileSize;
     if ((flags & RB200_FLAG_NEE) && s->cdfTriangles.empty()) return RB200_ERR_NO_EMITTER;
+    if (flags & RB200_FLAG_NEE)                 // same refusal as rb200_scene_create: nee.h.glsl:97-105 would read past the indices
+        for (const RB200InstanceData& e : s->emissive)
+            if (3ull * e.cdfRangeEnd + e.indexOffset + 2ull >= (unsigned long long)s->indices.size()) return RB200_ERR_INVALID_ARGUMENT;
     if (threads < 1) threads = 1;
     std::vector<Counters> cnt((size_t)threads);
     std::vector<std::thread> pool;
@@ -161,6 +167,13 @@ ORACLE_API void oracle_kat_trace_main(void* scene, const float* o, const float* 
     kat_trace_main(*(Scene*)scene, o, d, rngState, insideDielectric, accumulatedDistance, out, flags);
 }
 ORACLE_API float oracle_kat_power_heuristic(float a, float b) { return kat_power_heuristic(a, b); }
+ORACLE_API void oracle_kat_light_sample(void* scene, const RB200RtPushConsts* pc, uint32_t* rngState, float* out) {
+    kat_light_sample(*(Scene*)scene, *pc, rngState, out);
+}
+ORACLE_API void oracle_kat_direct_light_lambertian(void* scene, const RB200RtPushConsts* pc, const float* o, const float* n,
+                                                   const float* albedo, uint32_t* rngState, float* out) {
+    kat_direct_light_lambertian(*(Scene*)scene, *pc, o, n, albedo, rngState, out);
+}
 ORACLE_API void oracle_kat_tonemap(const float* rgb, float exposure, uint8_t* out) { tonemap_pixel(rgb, exposure, out); }
 ORACLE_API void oracle_kat_starting_ray(const RB200RtPushConsts* pc, uint32_t x, uint32_t y, uint32_t W, uint32_t H,
                                         float* origin, float* dir, uint32_t* rng_after) {

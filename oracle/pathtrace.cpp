@@ -495,6 +495,28 @@ static vec4r direct_light(const Scene& s, const RB200RtPushConsts& pc, const Pay
     return out;
 }
 
+// known-answer hooks: tests/test_oracle_kat.py restates nee.h.glsl and directLight's Lambertian branch in numpy
+// out: point[3], normal[3], emission[3], pdf, cullBackface
+void kat_light_sample(const Scene& s, const RB200RtPushConsts& pc, uint32_t* rng, float out[11]) {
+    const LightSample t = random_emissive_point(s, pc, *rng);
+    out[0] = t.point.x; out[1] = t.point.y; out[2] = t.point.z;
+    out[3] = t.normal.x; out[4] = t.normal.y; out[5] = t.normal.z;
+    out[6] = t.emission.x; out[7] = t.emission.y; out[8] = t.emission.z;
+    out[9] = t.pdf; out[10] = t.cullBackface ? 1.0f : 0.0f;
+}
+// out: rgb[3], pdf (directLight's vec4) for a Lambertian surface point
+void kat_direct_light_lambertian(const Scene& s, const RB200RtPushConsts& pc, const float o[3], const float n[3],
+                                 const float albedo[3], uint32_t* rng, float out[4]) {
+    Payload pld{};
+    pld.rayOrigin = rb_mk3(o[0], o[1], o[2]);
+    pld.surfaceNormal = rb_mk3(n[0], n[1], n[2]);
+    pld.albedo = rb_mk3(albedo[0], albedo[1], albedo[2]);
+    pld.materialID = 0;
+    pld.props = nullptr;
+    const vec4r r = direct_light(s, pc, pld, rb_mk3(0.0f, 0.0f, -1.0f), *rng, nullptr);
+    out[0] = r.rgb.x; out[1] = r.rgb.y; out[2] = r.rgb.z; out[3] = r.w;
+}
+
 static inline float power_heuristic(float p1, float p2) { return p1 * p1 / (p1 * p1 + p2 * p2); }  // pdf.h.glsl:4-7
 float kat_power_heuristic(float a, float b) { return power_heuristic(a, b); }
 

@@ -179,6 +179,18 @@ RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB2
         set_error("Scene must have at least one emissive object");   // src/scene/Instances.cpp:125-127
         return RB200_ERR_NO_EMITTER;
     }
+    if (ctx->flags & RB200_FLAG_NEE)
+        for (uint32_t i = 0; i < d->numEmissive; i++) {
+            // nee.h.glsl:97-105 addresses an emitter's triangles by their position in the CONCATENATED triangle CDF
+            // (indices[3 * cdfIndex + indexOffset]). For an emitter whose CDF does not start at 0 that reaches past its own
+            // triangles (reproduced as is), and past the end of the index buffer it is an out-of-bounds read: refused.
+            const RB200InstanceData& e = d->emissiveMetadata[i];
+            if (3ull * e.cdfRangeEnd + e.indexOffset + 2ull >= (unsigned long long)d->numIndices) {
+                set_error("emissive %u: light sampling would read past the index buffer (triangle CDF slot %u + indexOffset %u)",
+                          i, e.cdfRangeEnd, e.indexOffset);
+                return RB200_ERR_INVALID_ARGUMENT;
+            }
+        }
     RB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     RB200Scene* sc = new RB200Scene();

@@ -221,3 +221,148 @@ def test_parallax_flat_height_map_is_identity_at_zero_height(ol):
     ol.lib().oracle_kat_bump(img.ctypes.data_as(C.c_void_p), 8, 8, uv.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
                              tbn.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     assert abs(out[0] - (0.25 - 0.2 * 0.2)) < 2e-3 and out[1] == np.float32(0.5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# next-event estimation: compiled OUT of the binaries upstream ships, so it cannot be pinned by
+# executing them; nee.h.glsl and directLight are restated here in numpy float32, independently of oracle/pathtrace.cpp
+# ---------------------------------------------------------------------------------------------------------------------
+F = np.float32
+
+
+def _np_random(state):
+    """shaderCommon.h.glsl random(): PCG step + output permutation, float(w) / 2^32 (rounds up to 1.0 for large w)."""
+    s = (state * 747796405 + 1) & 0xFFFFFFFF
+    w = (((s >> ((s >> 28) + 4)) ^ s) * 277803737) & 0xFFFFFFFF
+    w = ((w >> 22) ^ w) & 0xFFFFFFFF
+    return s, F(F(w) * F(2.3283064365386963e-10))
+
+
+def _np_dot(a, b):
+    return F(F(F(a[0] * b[0]) + F(a[1] * b[1])) + F(a[2] * b[2]))
+
+
+def _np_normalize(v):
+    inv = F(F(1) / F(np.sqrt(_np_dot(v, v))))
+    return np.array([F(c * inv) for c in v], F)
+
+
+def _np_random_emissive_point(t, rb, pc, state):
+    """nee.h.glsl:52-124: instance by CDF, triangle by CDF (lower bound, u <= cdf[mid]), point by the square-root
+    parametrisation, pdf = (weight / totalEmissiveWeight) * (1 / area)."""
+    def lower_bound(cdf, lo, hi, u):
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if u <= cdf[mid]:
+                hi = mid
+            else:
+                lo = mid + 1
+        return lo
+    md_all = np.frombuffer(t.emissive.tobytes()[: t.numEmissive * 112], np.uint8).reshape(-1, 112)
+    state, u = _np_random(state)
+    inst = lower_bound(t.cdfInstances, 0, t.numEmissive - 1, u)
+    md = rb.abi.InstanceData.from_buffer_copy(md_all[inst].tobytes())
+    state, u = _np_random(state)
+    tri = lower_bound(t.cdfTriangles, md.cdfRangeStart, md.cdfRangeEnd, u)
+    M = np.array(md.transform[:], F).reshape(4, 4)          # column-major: M[c][r]
+    vs = []
+    for k in range(3):
+        v = t.vertices.reshape(-1, 4)[t.indices[3 * tri + md.indexOffset + k]][:3]
+        # mat4 * vec4(v, 1): x*c0 + y*c1 + z*c2 + c3, summed left to right
+        vs.append(np.array([F(F(F(F(M[0][r] * v[0]) + F(M[1][r] * v[1])) + F(M[2][r] * v[2])) + M[3][r]) for r in range(3)], F))
+    state, r1 = _np_random(state)
+    beta = F(F(1) - F(np.sqrt(r1)))
+    state, r2 = _np_random(state)
+    gamma = F(F(F(1) - beta) * r2)
+    alpha = F(F(F(1) - beta) - gamma)
+    point = np.array([F(F(F(alpha * vs[0][c]) + F(beta * vs[1][c])) + F(gamma * vs[2][c])) for c in range(3)], F)
+    e1, e2 = (vs[1] - vs[0]).astype(F), (vs[2] - vs[0]).astype(F)
+    cross = np.array([F(F(e1[1] * e2[2]) - F(e1[2] * e2[1])), F(F(e1[2] * e2[0]) - F(e1[0] * e2[2])), F(F(e1[0] * e2[1]) - F(e1[1] * e2[0]))], F)
+    pdf = F(F(F(md.weight) / F(pc.totalEmissiveWeight)) * F(F(1) / F(md.area)))
+    return state, point, _np_normalize(cross), np.array(md.emission[:], F), pdf, bool(md.cullBackface)
+
+
+def _two_light_scene(rb, emitters_first=True):
+    """Two emitters. nee.h.glsl:97-105 addresses an emitter's triangles by their position in the CONCATENATED triangle CDF
+    (indices[3 * cdfIndex + indexOffset]), so the second emitter (CDF slots 2..49) reads 2 triangles past its own mesh —
+    with the emitters first those slots still lie inside the index buffer (the box's triangles, moved by the emitter's
+    transform: upstream's behaviour, restated literally); with the emitters last they lie past its end."""
+    cfg = rb.configs
+    s = rb.Scene()
+    if not emitters_first:
+        s.addObject(rb.meshes.cornell_box(), cfg.IDENT, rb.Material(**cfg.CORNELL_WALL))
+    s.addObject(rb.meshes.cornell_light(), cfg.IDENT, rb.Material(**cfg.LIGHT))
+    # a second, differently sized, double-sided and differently coloured emitter with a non-trivial transform
+    M = cfg.compose(cfg.translate((-0.5, 0.9, -0.2)), cfg.scale((0.5, 1.0, 0.7)))
+    s.addObject(rb.meshes.uv_sphere(8, 4, radius=0.2), M, rb.Material(materialIdx=0, albedo=(1, 1, 1), emission=(2.0, 7.0, 4.0), cullBackface=False))
+    if emitters_first:
+        s.addObject(rb.meshes.cornell_box(), cfg.IDENT, rb.Material(**cfg.CORNELL_WALL))
+    return s.build(require_emitter=True)
+
+
+def test_light_sampling_past_the_index_buffer_is_refused(ol, rb):
+    t = _two_light_scene(rb, emitters_first=False)
+    pc = rb.camera.push_constants(8, 8, (0, 1, 3.9), (0, 1, 0), 40.0, total_emissive_weight=t.totalEmissiveWeight)
+    sc = ol.OracleScene(t)
+    hdr = np.zeros((8, 8, 4), np.float32)
+    args = (sc._h, 8, 8, C.byref(pc), hdr.ctypes.data_as(C.c_void_p), 1, None, 0, 1, 32)
+    assert ol.lib().oracle_render_batch_tiles(args[0], 8, 8, rb.RB200_FLAG_NEE, *args[3:]) == -1       # RB200_ERR_INVALID_ARGUMENT
+    assert ol.lib().oracle_render_batch_tiles(args[0], 8, 8, 0, *args[3:]) == 0                          # without NEE nothing samples lights
+
+
+def test_light_sampling_matches_a_numpy_restatement(ol, rb):
+    t = _two_light_scene(rb)
+    assert t.numEmissive == 2
+    pc = rb.camera.push_constants(8, 8, (0, 1, 3.9), (0, 1, 0), 40.0, total_emissive_weight=t.totalEmissiveWeight)
+    sc = ol.OracleScene(t)
+    picked = set()
+    for state0 in [0, 1, 7, 12345, 0xFFFFFFFF, 0x80000000] + [int(x) for x in np.random.RandomState(2).randint(0, 2 ** 32, 300, dtype=np.uint64)]:
+        st = C.c_uint32(state0)
+        out = np.zeros(11, np.float32)
+        ol.lib().oracle_kat_light_sample(sc._h, C.byref(pc), C.byref(st), out.ctypes.data_as(C.c_void_p))
+        state, point, normal, emission, pdf, cull = _np_random_emissive_point(t, rb, pc, state0)
+        want = np.concatenate([point, normal, emission, [pdf, F(cull)]]).astype(np.float32)
+        assert st.value == state and (out.view(np.uint32) == want.view(np.uint32)).all(), hex(state0)
+        picked.add(tuple(emission))
+    assert len(picked) == 2                                  # both emitters are drawn
+
+
+def test_direct_light_lambertian_matches_a_numpy_restatement(ol, rb):
+    """raytrace.rgen.glsl:43-95 for materialID 0: solid-angle pdf, BRDF = albedo / k_pi (a reciprocal multiply in the
+    reference build), cosine and geometry terms with the emitter's cull rule, occlusion from the oracle's own
+    any-hit query (the traversal is tested on its own)."""
+    t = _two_light_scene(rb)
+    pc = rb.camera.push_constants(8, 8, (0, 1, 3.9), (0, 1, 0), 40.0, total_emissive_weight=t.totalEmissiveWeight)
+    sc = ol.OracleScene(t)
+    rng = np.random.RandomState(9)
+    lit = dark = 0
+    for _ in range(300):
+        o = np.array([rng.uniform(-0.9, 0.9), rng.uniform(0.05, 1.9), rng.uniform(-0.9, 0.9)], F)
+        n = _np_normalize(rng.normal(size=3).astype(F))
+        albedo = rng.uniform(0, 1, 3).astype(F)
+        state0 = int(rng.randint(0, 2 ** 32, dtype=np.uint64))
+        st = C.c_uint32(state0)
+        out = np.zeros(4, np.float32)
+        ol.lib().oracle_kat_direct_light_lambertian(sc._h, C.byref(pc), o.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p),
+                                                    albedo.ctypes.data_as(C.c_void_p), C.byref(st), out.ctypes.data_as(C.c_void_p))
+        state, point, ln, emission, lpdf, cull = _np_random_emissive_point(t, rb, pc, state0)
+        to = (point - o).astype(F)
+        d = _np_normalize(to)
+        dist = F(np.sqrt(_np_dot(to, to)))
+        pdf = F(F(F(lpdf * dist) * dist) / max(_np_dot(ln, -d), F(0.0001)))
+        occluded = sc.trace_rays(o[None], d[None], np.array([dist - F(0.001)], F), any_hit=True, threads=1)["t"][0] >= 0
+        if occluded:
+            want = np.array([0, 0, 0, pdf], F)
+            dark += 1
+        else:
+            brdf = (albedo * F(0.31830987334251404)).astype(F)
+            cos_i = _np_dot(n, d)
+            cos_i = max(cos_i, F(0)) if cull else abs(cos_i)
+            g = _np_dot(ln, -d)
+            g = max(g, F(0)) if cull else abs(g)
+            geom = F(g / F(dist * dist))
+            rgb = [F(F(F(F(emission[c] * brdf[c]) * cos_i) * geom) / lpdf) for c in range(3)]
+            want = np.array(rgb + [pdf], F)
+            lit += 1
+        assert st.value == state and (out.view(np.uint32) == want.view(np.uint32)).all(), (o, n, state0, out, want)
+    assert lit > 50 and dark > 20
