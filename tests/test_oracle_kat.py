@@ -366,3 +366,82 @@ def test_direct_light_lambertian_matches_a_numpy_restatement(ol, rb):
             lit += 1
         assert st.value == state and (out.view(np.uint32) == want.view(np.uint32)).all(), (o, n, state0, out, want)
     assert lit > 50 and dark > 20
+
+
+def test_bounce_loop_with_nee_matches_a_python_restatement(ol, rb):
+    """raytrace.rgen.glsl:97-184 with next-event estimation switched ON (upstream ships it compiled out, so the binaries
+    cannot pin this part): the skip / sky / inside-dielectric branches, skipNEE, the MIS weight cases (first bounce,
+    previous skip, left a dielectric, last bounce, general), the order of the radiance and throughput updates, the clamp
+    and the running average — restated here over three building blocks that are pinned elsewhere: one traceRayEXT (the
+    compiled closest-hit / miss shaders, test_spirv_golden.py), directLight (numpy restatement above) and the starting
+    ray. Whole images of the Lambertian Cornell box must agree bit for bit over three batches."""
+    W, H, BOUNCES = 12, 9, 5
+    wl = rb.configs.cornell(W, H, nee=True, samples_per_pixel=1, max_bounces=BOUNCES)
+    sc = ol.OracleScene(wl.tables)
+    L = ol.lib()
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def heuristic(a, b):
+        return F(F(a * a) / F(F(a * a) + F(b * b)))
+
+    def trace_segments(pc, org, d, state):
+        inside, acc = False, F(0)
+        T, rad = np.ones(3, F), np.zeros(3, F)
+        first, prev_skip = True, False
+        for seg in range(BOUNCES):
+            prev_inside = inside
+            st, out, flags = C.c_uint32(state), np.zeros(21, F), C.c_uint32()
+            L.oracle_kat_trace_main(sc._h, ptr(org), ptr(d), C.byref(st), int(inside), float(acc), ptr(out), C.byref(flags))
+            state = st.value
+            color, albedo, org, d, emission, normal = (out[3 * k:3 * k + 3].copy() for k in range(6))
+            pdf_brdf, acc = out[18], out[19]
+            hit_sky, skip, inside, material = bool(flags.value & 1), bool(flags.value & 2), bool(flags.value & 4), flags.value >> 8
+            left = (not inside) and prev_inside
+            if skip:
+                continue
+            if hit_sky:
+                rad = (rad + color * T).astype(F)
+                break
+            if not inside:
+                skip_nee = material not in (0, 3)
+                direct = np.zeros(4, F)
+                if not skip_nee:
+                    assert material == 0                     # this scene is Lambertian throughout
+                    st = C.c_uint32(state)
+                    L.oracle_kat_direct_light_lambertian(sc._h, C.byref(pc), ptr(org), ptr(normal), ptr(albedo), C.byref(st), ptr(direct))
+                    state = st.value
+                w_nee, w_brdf = F(0), F(1)
+                if not skip_nee:
+                    if first or prev_skip or left:
+                        w_nee, w_brdf = F(1), F(1)
+                    elif seg + 1 == BOUNCES:
+                        w_nee, w_brdf = F(0), heuristic(pdf_brdf, direct[3])
+                    else:
+                        w_nee, w_brdf = heuristic(direct[3], pdf_brdf), heuristic(pdf_brdf, direct[3])
+                prev_skip = skip_nee
+                combined = ((direct[:3] * w_nee).astype(F) + (emission * w_brdf).astype(F)).astype(F)
+                rad = (rad + (combined * T).astype(F)).astype(F)
+                T = (T * color).astype(F)
+            first = False
+        return rad
+
+    img = np.zeros((H, W, 4), F)
+    want = np.zeros((H, W, 4), F)
+    seen = {"clamped": 0, "lit": 0}
+    for batch in range(3):
+        pc = wl.push_constants(batch, direct_clamp=2.0)
+        sc.render_batch(W, H, rb.RB200_FLAG_NEE, pc, want, threads=1)
+        for y in range(H):
+            for x in range(W):
+                o, d, st = np.zeros(3, F), np.zeros(3, F), C.c_uint32()
+                L.oracle_kat_starting_ray(C.byref(pc), x, y, W, H, ptr(o), ptr(d), C.byref(st))
+                c = trace_segments(pc, o, d, st.value)
+                seen["clamped"] += int((c > 2.0).any())
+                seen["lit"] += int((c > 0).any())
+                c = np.minimum(np.maximum(c, F(0)), F(2.0)).astype(F)
+                assert not np.isnan(c).any()
+                if batch:
+                    c = (((img[y, x, :3] * F(batch)).astype(F) + c).astype(F) / F(batch + 1)).astype(F)
+                img[y, x] = (c[0], c[1], c[2], 1)
+        assert (img.view(np.uint32) == want.view(np.uint32)).all(), batch
+    assert seen["lit"] > 200 and seen["clamped"] > 0
