@@ -11,9 +11,10 @@
  * executes those binaries on the CPU and tests/golden/spirv_*.npz holds their outputs: the parts of this
  * restatement listed in tests/test_spirv_golden.py (post-processing; camera, RNG, bounce loop, the four materials,
  * parallax mapping, sky and accumulation of the as-shipped estimator) are pinned to the reference's compiled code bit
- * for bit. The
- * rest is defended line-by-line against the GLSL (every function cites the lines it follows) and pinned by the
- * known-answer values in SURVEY.md Appendix A3 (tests/test_oracle_kat.py).
+ * for bit. Next-event estimation is compiled out of those binaries: nee.h.glsl, directLight and the bounce loop with
+ * NEE on are pinned by independent numpy / Python restatements (tests/test_oracle_kat.py, bit-exact). The rest is
+ * defended line-by-line against the GLSL (every function cites the lines it follows) and pinned by the known-answer
+ * values in SURVEY.md Appendix A3 (tests/test_oracle_kat.py).
  *
  * Elementary layer: rb_math.h / rb_vec.h / rb_tri.h (sin, cos, log, exp, acos, vector built-ins, the
  * watertight triangle test) are shared with the kernels on purpose, so that both sides round identically and
