@@ -46,6 +46,11 @@ class Renderer:
         self._scene = C.c_void_p()
         self.tables = tables
         desc = tables.desc()
+        if (flags & RB200_FLAG_NEE) and tables.numEmissive > 1:
+            import warnings
+            warnings.warn("%d emissive instances: the reference's light sampling (nee.h.glsl:97-105) addresses the triangles of "
+                          "every emitter after the first through the concatenated triangle CDF, i.e. beyond the emitter's own "
+                          "triangles; reproduced as is (DESIGN.md 2)" % tables.numEmissive)
         try:
             abi.check(self.lib, self.lib.rb200_scene_create(self._ctx, C.byref(desc), C.byref(self._scene)))
         except Exception:

@@ -132,6 +132,11 @@ Renderer::~Renderer() {
 void Renderer::setScene(SceneTables& tables) {
     if (scene) { rb200_scene_destroy(scene); scene = nullptr; }
     RB200SceneDesc d = tables.desc();
+    if (d.numEmissive > 1)
+        std::fprintf(stderr, "warning: %u emissive instances: with next-event estimation the reference's light sampling "
+                             "(nee.h.glsl:97-105) addresses the triangles of every emitter after the first through the "
+                             "concatenated triangle CDF, i.e. beyond the emitter's own triangles; reproduced as is (DESIGN.md 2)\n",
+                     d.numEmissive);
     check(rb200_scene_create(ctx, &d, &scene), "rb200_scene_create");
 }
 
