@@ -16,6 +16,9 @@ void kat_direct_light_lambertian(const Scene& s, const RB200RtPushConsts& pc, co
                                  const float albedo[3], uint32_t* rng, float out[4]);
 void kat_trace_main(const Scene& s, const float o[3], const float d[3], uint32_t* rngState, int insideDielectric,
                     float accumulatedDistance, float out[21], uint32_t* flags);
+void kat_bounce(const Scene& s, const RB200RtPushConsts& pc, const float o[3], const float d[3], uint32_t* rngState,
+                int insideDielectric, float accumulatedDistance, float out[21], uint32_t* flags, float direct[4],
+                uint32_t* rngAfterDirect);
 void kat_bump(const uint8_t* rgba, uint32_t w, uint32_t h, const float uv[2], const float rayIn[3], const float tbn[9],
               float out[2]);
 void starting_ray(const RB200RtPushConsts& pc, float px, float py, float resx, float resy, uint32_t& rng,
@@ -165,6 +168,11 @@ ORACLE_API void oracle_kat_bump(const uint8_t* rgba, uint32_t w, uint32_t h, con
 ORACLE_API void oracle_kat_trace_main(void* scene, const float* o, const float* d, uint32_t* rngState, int insideDielectric,
                                       float accumulatedDistance, float* out, uint32_t* flags) {
     kat_trace_main(*(Scene*)scene, o, d, rngState, insideDielectric, accumulatedDistance, out, flags);
+}
+ORACLE_API void oracle_kat_bounce(void* scene, const RB200RtPushConsts* pc, const float* o, const float* d, uint32_t* rngState,
+                                  int insideDielectric, float accumulatedDistance, float* out, uint32_t* flags, float* direct,
+                                  uint32_t* rngAfterDirect) {
+    kat_bounce(*(Scene*)scene, *pc, o, d, rngState, insideDielectric, accumulatedDistance, out, flags, direct, rngAfterDirect);
 }
 ORACLE_API float oracle_kat_power_heuristic(float a, float b) { return kat_power_heuristic(a, b); }
 ORACLE_API void oracle_kat_light_sample(void* scene, const RB200RtPushConsts* pc, uint32_t* rngState, float* out) {

@@ -578,6 +578,34 @@ void kat_trace_main(const Scene& s, const float o[3], const float d[3], uint32_t
     *rngState = pld.rngState;
 }
 
+// known-answer hook: kat_trace_main plus, where the hit is a non-skipped Lambertian or Disney surface outside glass, the
+// directLight call that would follow it (on a COPY of the RNG state: the caller's restatement of the bounce loop decides
+// whether that call happens and which state it continues with). direct = rgb + pdf.
+void kat_bounce(const Scene& s, const RB200RtPushConsts& pc, const float o[3], const float d[3], uint32_t* rngState,
+                int insideDielectric, float accumulatedDistance, float out[21], uint32_t* flags, float direct[4],
+                uint32_t* rngAfterDirect) {
+    Payload pld{};
+    pld.rngState = *rngState;
+    pld.insideDielectric = insideDielectric != 0;
+    pld.accumulatedDistance = accumulatedDistance;
+    Counters cnt;
+    const vec3 dir = rb_mk3(d[0], d[1], d[2]);
+    trace_main(s, pld, rb_mk3(o[0], o[1], o[2]), dir, &cnt);
+    const vec3 v[6] = {pld.color, pld.albedo, pld.rayOrigin, pld.rayDirection, pld.emission, pld.surfaceNormal};
+    for (int k = 0; k < 6; k++) { out[3 * k] = v[k].x; out[3 * k + 1] = v[k].y; out[3 * k + 2] = v[k].z; }
+    out[18] = pld.pdf; out[19] = pld.accumulatedDistance; out[20] = pld.eta;
+    *flags = (pld.rayHitSky ? 1u : 0u) | (pld.skip ? 2u : 0u) | (pld.insideDielectric ? 4u : 0u) | (pld.didRefract ? 8u : 0u) | (pld.materialID << 8);
+    *rngState = pld.rngState;
+    direct[0] = direct[1] = direct[2] = direct[3] = 0.0f;
+    *rngAfterDirect = pld.rngState;
+    if (!pld.rayHitSky && !pld.skip && !pld.insideDielectric && (pld.materialID == 0 || pld.materialID == 3)) {
+        uint32_t r = pld.rngState;
+        const vec4r dl = direct_light(s, pc, pld, dir, r, nullptr);
+        direct[0] = dl.rgb.x; direct[1] = dl.rgb.y; direct[2] = dl.rgb.z; direct[3] = dl.w;
+        *rngAfterDirect = r;
+    }
+}
+
 // raytrace.rgen.glsl:34-41
 static vec2 random_gaussian(uint32_t& rng) {
     const float u1 = rb_max(1e-5f, rnd(rng));

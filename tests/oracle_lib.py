@@ -59,6 +59,8 @@ def lib():
         _lib.oracle_kat_trace_main.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_int, C.c_float,
                                                C.c_void_p, C.POINTER(C.c_uint32)]
         _lib.oracle_kat_sky.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.oracle_kat_bounce.argtypes = [C.c_void_p, C.POINTER(abi.RtPushConsts), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_int,
+                                           C.c_float, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(C.c_uint32)]
         _lib.oracle_kat_light_sample.argtypes = [C.c_void_p, C.POINTER(abi.RtPushConsts), C.POINTER(C.c_uint32), C.c_void_p]
         _lib.oracle_kat_direct_light_lambertian.argtypes = [C.c_void_p, C.POINTER(abi.RtPushConsts), C.c_void_p, C.c_void_p, C.c_void_p,
                                                             C.POINTER(C.c_uint32), C.c_void_p]

@@ -445,3 +445,87 @@ def test_bounce_loop_with_nee_matches_a_python_restatement(ol, rb):
                 img[y, x] = (c[0], c[1], c[2], 1)
         assert (img.view(np.uint32) == want.view(np.uint32)).all(), batch
     assert seen["lit"] > 200 and seen["clamped"] > 0
+
+
+def test_bounce_loop_with_nee_on_every_material(ol, rb):
+    """The same restatement of raytrace.rgen.glsl:97-184 on a scene with all four materials, textures and skips, so that
+    the branches the Lambertian box never takes are compared too: skipNEE for metal and glass (prevSkip makes the next
+    diffuse hit count its light sample fully), paths inside glass (no light sample, no throughput update), leftDielectric,
+    cull / alpha skips that do not consume a bounce's bookkeeping. One bounce = oracle_kat_bounce (the closest-hit shader
+    and, for Lambertian / Disney hits, the directLight that would follow, on a copy of the RNG state); WHETHER it follows,
+    its weight and everything after it are decided here."""
+    W, H, BOUNCES = 16, 12, 8
+    wl = rb.configs.small_mixed(W, H, nee=True, samples_per_pixel=1, max_bounces=BOUNCES)
+    sc = ol.OracleScene(wl.tables)
+    L = ol.lib()
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    heuristic = lambda a, b: F(F(a * a) / F(F(a * a) + F(b * b)))
+    taken = {"skip": 0, "prev_skip_full_weight": 0, "left_dielectric": 0, "inside": 0, "last_bounce": 0, "general": 0, "disney_nee": 0}
+
+    def trace_segments(pc, org, d, state):
+        inside, acc = False, F(0)
+        T, rad = np.ones(3, F), np.zeros(3, F)
+        first, prev_skip = True, False
+        for seg in range(BOUNCES):
+            prev_inside = inside
+            st, out, flags, direct, st_direct = C.c_uint32(state), np.zeros(21, F), C.c_uint32(), np.zeros(4, F), C.c_uint32()
+            L.oracle_kat_bounce(sc._h, C.byref(pc), ptr(org), ptr(d), C.byref(st), int(inside), float(acc), ptr(out), C.byref(flags),
+                                ptr(direct), C.byref(st_direct))
+            state = st.value
+            color, albedo, org, d, emission, normal = (out[3 * k:3 * k + 3].copy() for k in range(6))
+            pdf_brdf, acc = out[18], out[19]
+            hit_sky, skip, inside, material = bool(flags.value & 1), bool(flags.value & 2), bool(flags.value & 4), flags.value >> 8
+            left = (not inside) and prev_inside
+            if skip:
+                taken["skip"] += 1
+                continue
+            if hit_sky:
+                rad = (rad + color * T).astype(F)
+                break
+            if inside:
+                taken["inside"] += 1
+            else:
+                skip_nee = material not in (0, 3)
+                w_nee, w_brdf = F(0), F(1)
+                if skip_nee:
+                    direct = np.zeros(4, F)
+                else:
+                    state = st_direct.value                   # directLight ran: its four draws are consumed
+                    taken["disney_nee"] += int(material == 3)
+                    if first or prev_skip or left:
+                        w_nee, w_brdf = F(1), F(1)
+                        taken["prev_skip_full_weight"] += int(prev_skip and not first)
+                        taken["left_dielectric"] += int(left)
+                    elif seg + 1 == BOUNCES:
+                        w_nee, w_brdf = F(0), heuristic(pdf_brdf, direct[3])
+                        taken["last_bounce"] += 1
+                    else:
+                        w_nee, w_brdf = heuristic(direct[3], pdf_brdf), heuristic(pdf_brdf, direct[3])
+                        taken["general"] += 1
+                prev_skip = skip_nee
+                combined = ((direct[:3] * w_nee).astype(F) + (emission * w_brdf).astype(F)).astype(F)
+                rad = (rad + (combined * T).astype(F)).astype(F)
+                T = (T * color).astype(F)
+            first = False
+        return rad
+
+    img, want = np.zeros((H, W, 4), F), np.zeros((H, W, 4), F)
+    for batch in range(2):
+        pc = wl.push_constants(batch)
+        clamp = F(pc.directClamp)
+        sc.render_batch(W, H, rb.RB200_FLAG_NEE, pc, want, threads=1)
+        for y in range(H):
+            for x in range(W):
+                o, d, st = np.zeros(3, F), np.zeros(3, F), C.c_uint32()
+                L.oracle_kat_starting_ray(C.byref(pc), x, y, W, H, ptr(o), ptr(d), C.byref(st))
+                c = trace_segments(pc, o, d, st.value)
+                if np.isnan(c).any():                     # a NaN sample is dropped (rgen.glsl:268-272); with 1 spp the pixel keeps its value
+                    if batch == 0:
+                        img[y, x] = (0, 0, 0, 1)
+                    continue
+                c = np.minimum(np.maximum(c, F(0)), clamp).astype(F)
+                if batch:
+                    c = (((img[y, x, :3] * F(batch)).astype(F) + c).astype(F) / F(batch + 1)).astype(F)
+                img[y, x] = (c[0], c[1], c[2], 1)
+        assert (img.view(np.uint32) == want.view(np.uint32)).all(), batch
+    assert all(v > 0 for v in taken.values()), taken
