@@ -90,10 +90,11 @@ def _jpeg_bytes(img, **kw):
     return b.getvalue()
 
 
-def build(tmp_path, external=False, jpeg=False, sparse=False):
+def build(tmp_path, external=False, jpeg=False, sparse=False, glowing_glass=False):
     """Writes scene.glb (external=False) or scene.gltf + scene.bin + tex0.png (external=True) and returns the path.
     sparse=True stores the same scene through sparse accessors: the sphere's POSITION over a perturbed base array, the
-    lamp's NORMAL over no buffer view at all (zeros + substitutions)."""
+    lamp's NORMAL over no buffer view at all (zeros + substitutions). glowing_glass=True makes the glass material emissive
+    as well: three emitters, two of them instances of the same primitive."""
     rng = np.random.RandomState(4)
     B = _Bin()
     # mesh 0: floor grid — interleaved POSITION/NORMAL (stride 24), TANGENT vec4, normalized ushort UVs, ubyte indices
@@ -196,6 +197,8 @@ def build(tmp_path, external=False, jpeg=False, sparse=False):
         "accessors": B.accessors,
         "bufferViews": B.views,
     }
+    if glowing_glass:
+        doc["materials"][1]["emissiveFactor"] = [0.2, 0.1, 0.05]
     while len(B.data) % 4:
         B.data.append(0)
     if external:

@@ -87,6 +87,21 @@ def test_cpp_importer_tables_identical_to_python(host, rb, gl, tmp_path, externa
 
 
 @pytest.mark.filterwarnings("ignore:falling back to UV")
+def test_several_emitters_give_identical_light_tables_in_both_hosts(host, rb, gl, tmp_path):
+    """Instances.cpp:52-114 with more than one emitter: emissive metadata (transform, CDF range, index offset, weight, area,
+    cull flag), the concatenated triangle CDF, the instance CDF and totalEmissiveWeight of the C++ host equal the Python
+    host's; two of the three emitters are instances of the same primitive."""
+    path, _ = gf.build(tmp_path, glowing_glass=True)
+    py = gl.loadScene(path).build(require_emitter=True)
+    assert py.numEmissive == 3 and py.cdfInstances.size == 3 and py.cdfInstances[-1] == 1.0
+    host.rbhost_tables_gltf.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    h = C.c_void_p()
+    assert host.rbhost_tables_gltf(path.encode(), 1, C.byref(h)) == 0, err(host)
+    assert_tables_identical(cpp_tables(host, rb, h), py_tables(py))
+    host.rbhost_tables_free(h)
+
+
+@pytest.mark.filterwarnings("ignore:falling back to UV")
 def test_sparse_accessors_resolve_to_the_dense_scene(host, rb, gl, tmp_path):
     """glTF 2.0 3.6.2.3 (fastgltf resolves sparse accessors for the reference): base elements — or zeros when the accessor
     has no buffer view — with the listed elements replaced. The sparse file must give the tables of the dense one, in
