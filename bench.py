@@ -338,11 +338,14 @@ def roofline(rb, wl, device, stream):
     peak, peak_src = measured_peak_hbm()
     res = {"bound": "hbm", "kernel": "k_extend", "unit": "GB/s", "peak": peak, "peak_source": peak_src}
     pc = wl.push_constants(1000)
-    # timing pass (events around every kernel; no counters)
+    # timing pass (events around every kernel, launches serialised; no counters). Consecutive batches, so that the
+    # engine is in its steady state — every launch of the last call carries the rays of all batches in flight — and
+    # the launches timed are the launches the bench loop above issues
     rt = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE | rb.RB200_FLAG_TIME_KERNELS, device=device,
                      stream=stream.cuda_stream)
-    for _ in range(2):
-        rt.render_batch(pc)
+    engines, lanes, _ = rt.engine_config()
+    for b in range(2 + 2 * lanes):
+        rt.render_batch(wl.push_constants(1000 + b * engines))
     kt = rt.kernel_times()
     last_t, _ = rt.stats()
     rt.close()
@@ -357,11 +360,14 @@ def roofline(rb, wl, device, stream):
     table_bytes = int(info["nodeBytes"] + info["triangleBytes"])
     l2_gather = rc.measure_gather(table_bytes, 80)
     rc.close()
-    n_rays = last_c["extendRays"] + last_c["shadowRays"]
-    n_node = last_c["nodeVisits"] / n_rays
-    n_tri = last_c["triTests"] / n_rays
-    bytes_per_ray = 80.0 * n_node + 48.0 * n_tri + 32.0 + 16.0
-    ext_bytes = bytes_per_ray * last_t["extendRays"]
+    node_bytes = info["nodeBytes"] / max(1, info["numWideNodes"])
+    n_node = (last_c["nodeVisits"] - last_c["shadowNodeVisits"]) / max(1, last_c["extendRays"])
+    n_tri = (last_c["triTests"] - last_c["shadowTriTests"]) / max(1, last_c["extendRays"])
+    n_node_sh = last_c["shadowNodeVisits"] / max(1, last_c["shadowRays"])
+    n_tri_sh = last_c["shadowTriTests"] / max(1, last_c["shadowRays"])
+    bytes_per_ray = node_bytes * n_node + 48.0 * n_tri + 32.0 + 16.0
+    bytes_per_shadow_ray = node_bytes * n_node_sh + 48.0 * n_tri_sh + 32.0 + 48.0 + 32.0   # ray record, 3 result records, radiance r/w
+    ext_bytes = bytes_per_ray * kt["extendRays"]
     achieved = ext_bytes / (kt["extendMs"] * 1e-3) / 1e9
     total_ms = kt["generateMs"] + kt["extendMs"] + sum(kt["shadeMs"]) + kt["shadowMs"] + kt["finishMs"]
     traffic = None
@@ -370,11 +376,20 @@ def roofline(rb, wl, device, stream):
     except Exception:
         pass
     res.update({"achieved": achieved, "frac": achieved / peak, "traffic": traffic,
-                "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri,
-                "extend_rays_per_batch": last_t["extendRays"], "extend_launches": kt["extendLaunches"],
+                "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri, "node_bytes": node_bytes,
+                "shadow": {"bytes_per_ray": bytes_per_shadow_ray, "nodes_per_ray": n_node_sh, "tris_per_ray": n_tri_sh,
+                           "rays_per_step": kt["shadowRays"], "ms_per_step": kt["shadowMs"], "launches": kt["shadowLaunches"],
+                           "achieved": (bytes_per_shadow_ray * kt["shadowRays"] / (kt["shadowMs"] * 1e-3) / 1e9) if kt["shadowMs"] > 0 else None,
+                           "frac": (bytes_per_shadow_ray * kt["shadowRays"] / (kt["shadowMs"] * 1e-3) / 1e9 / peak) if kt["shadowMs"] > 0 else None},
+                "engine": {"engines": engines, "lanes": lanes},
+                "extend_rays_per_batch": last_t["extendRays"], "extend_rays_per_step": kt["extendRays"],
+                "extend_launches": kt["extendLaunches"],
                 "extend_ms_per_batch": kt["extendMs"], "avg_launch_ms": kt["extendMs"] / max(1, kt["extendLaunches"]),
-                "extend_mrays_s": last_t["extendRays"] / (kt["extendMs"] * 1e-3) / 1e6,
-                "shadow_mrays_s": (last_t["shadowRays"] / (kt["shadowMs"] * 1e-3) / 1e6) if kt["shadowMs"] > 0 else None,
+                "extend_mrays_s": kt["extendRays"] / (kt["extendMs"] * 1e-3) / 1e6,
+                "shadow_mrays_s": (kt["shadowRays"] / (kt["shadowMs"] * 1e-3) / 1e6) if kt["shadowMs"] > 0 else None,
+                "shade_items_per_step": {"lambertian": kt["shadeItems"][0], "metal": kt["shadeItems"][1],
+                                         "dielectric": kt["shadeItems"][2], "disney": kt["shadeItems"][3],
+                                         "miss": kt["shadeItems"][4], "finish": kt["finishItems"]},
                 "kernel_ms_per_batch": {"generate": kt["generateMs"], "extend": kt["extendMs"], "shade_lambertian": kt["shadeMs"][0],
                                         "shade_metal": kt["shadeMs"][1], "shade_dielectric": kt["shadeMs"][2],
                                         "shade_disney": kt["shadeMs"][3], "miss": kt["shadeMs"][4], "shadow": kt["shadowMs"],
@@ -387,7 +402,7 @@ def roofline(rb, wl, device, stream):
                                 "extend_mrays_s": kt["extendFullRays"] / (kt["extendFullMs"] * 1e-3) / 1e6,
                                 "achieved": bytes_per_ray * kt["extendFullRays"] / (kt["extendFullMs"] * 1e-3) / 1e9,
                                 "frac": bytes_per_ray * kt["extendFullRays"] / (kt["extendFullMs"] * 1e-3) / 1e9 / peak,
-                                "share_of_extend_rays": kt["extendFullRays"] / max(1, last_t["extendRays"]),
+                                "share_of_extend_rays": kt["extendFullRays"] / max(1, kt["extendRays"]),
                                 "shadow_mrays_s": (kt["shadowFullRays"] / (kt["shadowFullMs"] * 1e-3) / 1e6) if kt["shadowFullMs"] > 0 else None}
                                if kt["extendFullMs"] > 0 else None),
                 "l2_gather": {"peak": l2_gather, "unit": "GB/s", "frac": achieved / l2_gather, "table_bytes": table_bytes,

@@ -176,9 +176,13 @@ typedef struct RB200Stats {
     uint64_t triTests;       /* triangle tests     (only with RB200_FLAG_COUNT_BVH) */
     uint64_t waves;          /* wavefront iterations executed */
     uint64_t kernelLaunches; /* kernels launched by the library */
+    uint64_t shadowNodeVisits; /* the part of nodeVisits / triTests spent on any-hit (shadow) rays */
+    uint64_t shadowTriTests;
 } RB200Stats;
 
-/* Device time per kernel class of the last rb200_render_batch (needs RB200_FLAG_TIME_KERNELS). */
+/* Device time per kernel class of the launches issued by the last rb200_render_batch (needs RB200_FLAG_TIME_KERNELS).
+ * With several lanes a launch carries the rays of every batch in flight, so in steady state the launches of one call
+ * trace one batch's worth of rays in total. */
 typedef struct RB200KernelTimes {
     float    generateMs, extendMs, shadeMs[5] /* lambertian, metal, dielectric, disney, miss */, shadowMs, finishMs;
     uint32_t extendLaunches, shadeLaunches, shadowLaunches, finishLaunches;
@@ -187,6 +191,9 @@ typedef struct RB200KernelTimes {
     float    extendFullMs, shadowFullMs;
     uint32_t extendFullLaunches, shadowFullLaunches;
     uint64_t extendFullRays, shadowFullRays;
+    /* what the launches of the call processed: rays traced by k_extend / k_shadow, slots shaded per material kernel
+     * (lambertian, metal, dielectric, disney, miss) and paths ended by k_finish */
+    uint64_t extendRays, shadowRays, shadeItems[5], finishItems;
 } RB200KernelTimes;
 
 typedef struct RB200BvhInfo {
@@ -248,7 +255,14 @@ RB200_API int rb200_scene_bvh_info(const RB200Scene* scene, RB200BvhInfo* out);
 
 /* Trace + shade + accumulate one sample batch (pc->samplesPerPixel samples per pixel, <= pc->maxBounces
  * segments each). pc->sampleBatch == 0 overwrites the HDR image, > 0 folds into the running average
- * (raytrace.rgen.glsl:277-284). Asynchronous on the context stream. */
+ * (raytrace.rgen.glsl:277-284). Asynchronous on the context stream.
+ * Replaces Reina::traceRays (src/Reina.cpp:425-470: push RtPushConsts, sampleBatch++, vkCmdTraceRaysKHR(W,H,1)).
+ * When the stream-ordered work of this call has run, the image holds exactly the batches asked for so far, in call
+ * order. Inside the library the NEXT batches of a regular sequence (same push constants, sampleBatch advancing by a
+ * constant stride — the reference's frame loop) are traced speculatively alongside this one so that every kernel
+ * launch stays full; they are folded into the image only by the calls that ask for them and are discarded if the
+ * sequence changes (camera move, other scene, other sample counts). RB200_NO_SPECULATION=1 turns this off.
+ * samplesPerPixel * maxBounces must not exceed 2^22. */
 RB200_API int rb200_render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc);
 
 /* With RB200_FLAG_ACCUM_SUM: turn the accumulated sum of `numBatches` batch means into the mean image. */
@@ -275,8 +289,8 @@ RB200_API int rb200_read_hdr(RB200Context* ctx, float* rgba32f);
  * frame overlap the next batch (what a swap chain gives the reference's loop between endSubmit and present,
  * src/Reina.cpp:380-385). Several copies may be outstanding, each into its own host frame: rb200_wait_ldr_pending
  * blocks until at most `max_pending` of them (the most recent ones) are still in flight, rb200_wait_ldr until none is.
- * rb200_pipeline_depth: how many batches the context keeps in flight (its path-state lanes); a frame loop that keeps
- * that many frames outstanding never drains the device. */
+ * rb200_pipeline_depth: how many frames a display loop should keep outstanding so that the host never drains the
+ * device. */
 RB200_API int rb200_read_ldr_async(RB200Context* ctx, uint8_t* rgba8);
 RB200_API int rb200_wait_ldr(RB200Context* ctx);
 RB200_API int rb200_wait_ldr_pending(RB200Context* ctx, uint32_t max_pending);
@@ -299,6 +313,20 @@ RB200_API int rb200_trace_primary(RB200Context* ctx, const RB200Scene* scene, co
 RB200_API int rb200_trace_rays(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* origins,
                                const float* directions, const float* tmax, int any_hit, RB200PrimaryHit* out_hits);
 
+/* Measurement aid: the traversal kernel alone on the caller's rays (as rb200_trace_rays), one warm-up launch and `reps`
+ * timed ones (CUDA events on the launching stream); *out_ms_per_launch = mean device time of a launch, *out_checksum =
+ * a hash of all hit records of the last launch (equal results <=> equal checksums, whatever the kernel variant). */
+RB200_API int rb200_bench_trace(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* origins,
+                                const float* directions, const float* tmax, int any_hit, uint32_t reps,
+                                float* out_ms_per_launch, uint64_t* out_checksum);
+
+/* How the context schedules batches: `engines` wave loops on as many streams, each tracing `lanes` consecutive batches
+ * of the caller's sequence together (RB200_ENGINES / RB200_LANES at context creation); *discarded_batches = speculative
+ * batches thrown away because the caller's sequence changed. Any pointer may be NULL. */
+RB200_API int rb200_engine_config(RB200Context* ctx, uint32_t* engines, uint32_t* lanes, uint64_t* discarded_batches);
+
+/* last_batch = the batch folded into the image by the most recent rb200_render_batch (its rays are counted per path,
+ * whichever launches traced them); cumulative = all batches folded so far. */
 RB200_API int rb200_get_stats(RB200Context* ctx, RB200Stats* last_batch, RB200Stats* cumulative);
 RB200_API int rb200_get_kernel_times(RB200Context* ctx, RB200KernelTimes* out);
 RB200_API int rb200_synchronize(RB200Context* ctx);

@@ -112,7 +112,7 @@ class Renderer:
         abi.check(self.lib, self.lib.rb200_wait_ldr_pending(self._ctx, max_pending))
 
     def pipeline_depth(self):
-        """Batches the context keeps in flight (path-state lanes): the frame-loop depth that never drains the device."""
+        """Frames a display loop should keep outstanding so that the host never drains the device."""
         return int(self.lib.rb200_pipeline_depth())
 
     def write_hdr(self, img):
@@ -141,6 +141,23 @@ class Renderer:
                                                       d.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p),
                                                       1 if any_hit else 0, hits.ctypes.data_as(C.c_void_p)))
         return hits
+
+    def bench_trace(self, origins, directions, tmax, any_hit=False, reps=10):
+        """(ms per launch, checksum of the hits) of the traversal kernel alone on these rays (rb200_bench_trace)."""
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(tmax, np.float32), (o.shape[0],)), np.float32)
+        ms, ck = C.c_float(), C.c_uint64()
+        abi.check(self.lib, self.lib.rb200_bench_trace(self._ctx, self._scene, o.shape[0], o.ctypes.data_as(C.c_void_p),
+                                                       d.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p),
+                                                       1 if any_hit else 0, reps, C.byref(ms), C.byref(ck)))
+        return float(ms.value), int(ck.value)
+
+    def engine_config(self):
+        """(engines, lanes per engine, speculative batches discarded so far): see rb200_engine_config."""
+        e, l, w = C.c_uint32(), C.c_uint32(), C.c_uint64()
+        abi.check(self.lib, self.lib.rb200_engine_config(self._ctx, C.byref(e), C.byref(l), C.byref(w)))
+        return int(e.value), int(l.value), int(w.value)
 
     def bvh_info(self):
         info = abi.BvhInfo()

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librb200.so")
+# RB200_LIBRARY (developer aid, tools/sweep_variants.sh): another build of the same library, e.g. csrc/variants/<name>.so
+LIB_PATH = os.environ.get("RB200_LIBRARY") or os.path.join(_HERE, "csrc", "librb200.so")
 
 RB200_OK = 0
 RB200_FLAG_NEE = 1 << 0
@@ -87,7 +88,7 @@ class Stats(C.Structure):
     _fields_ = [
         ("extendRays", C.c_uint64), ("shadowRays", C.c_uint64), ("paths", C.c_uint64),
         ("nodeVisits", C.c_uint64), ("triTests", C.c_uint64), ("waves", C.c_uint64),
-        ("kernelLaunches", C.c_uint64),
+        ("kernelLaunches", C.c_uint64), ("shadowNodeVisits", C.c_uint64), ("shadowTriTests", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -114,7 +115,8 @@ class KernelTimes(C.Structure):
                 ("finishMs", C.c_float), ("extendLaunches", C.c_uint32), ("shadeLaunches", C.c_uint32),
                 ("shadowLaunches", C.c_uint32), ("finishLaunches", C.c_uint32),
                 ("extendFullMs", C.c_float), ("shadowFullMs", C.c_float), ("extendFullLaunches", C.c_uint32),
-                ("shadowFullLaunches", C.c_uint32), ("extendFullRays", C.c_uint64), ("shadowFullRays", C.c_uint64)]
+                ("shadowFullLaunches", C.c_uint32), ("extendFullRays", C.c_uint64), ("shadowFullRays", C.c_uint64),
+                ("extendRays", C.c_uint64), ("shadowRays", C.c_uint64), ("shadeItems", C.c_uint64 * 5), ("finishItems", C.c_uint64)]
 
     def as_dict(self):
         return {"generateMs": self.generateMs, "extendMs": self.extendMs, "shadeMs": list(self.shadeMs),
@@ -122,7 +124,9 @@ class KernelTimes(C.Structure):
                 "shadeLaunches": self.shadeLaunches, "shadowLaunches": self.shadowLaunches,
                 "finishLaunches": self.finishLaunches, "extendFullMs": self.extendFullMs, "shadowFullMs": self.shadowFullMs,
                 "extendFullLaunches": self.extendFullLaunches, "shadowFullLaunches": self.shadowFullLaunches,
-                "extendFullRays": self.extendFullRays, "shadowFullRays": self.shadowFullRays}
+                "extendFullRays": self.extendFullRays, "shadowFullRays": self.shadowFullRays,
+                "extendRays": self.extendRays, "shadowRays": self.shadowRays, "shadeItems": list(self.shadeItems),
+                "finishItems": self.finishItems}
 
 
 class PrimaryHit(C.Structure):
@@ -165,6 +169,9 @@ SYMBOLS = {
     "rb200_trace_primary": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RtPushConsts), C.c_void_p]),
     "rb200_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_void_p]),
+    "rb200_bench_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32,
+                                    C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
+    "rb200_engine_config": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "rb200_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats), C.POINTER(Stats)]),
     "rb200_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(KernelTimes)]),
     "rb200_synchronize": (C.c_int, [C.c_void_p]),

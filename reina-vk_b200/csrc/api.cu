@@ -82,59 +82,84 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device available (this library has no CPU path)"); return RB200_ERR_NO_DEVICE; }
     if (device < 0 || device >= ndev) { set_error("device %d out of range (%d devices)", device, ndev); return RB200_ERR_INVALID_ARGUMENT; }
     RB_CUDA(cudaSetDevice(device));
-    RB200Context* c = new RB200Context();
-    c->width = width; c->height = height; c->flags = flags; c->device = device;
     cudaDeviceProp prop;
     RB_CUDA(cudaGetDeviceProperties(&prop, device));
+    cudaStream_t front = nullptr;
+    RB_CUDA(cudaStreamCreateWithFlags(&front, cudaStreamNonBlocking));
+    RB200Context* c = new RB200Context();
+    c->width = width; c->height = height; c->flags = flags; c->device = device;
     c->numSMs = prop.multiProcessorCount;
-    RB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->stream = front;
     c->ownStream = true;
     const size_t N = (size_t)width * height;
-    WaveParams& P = c->wp;
+    // engines x lanes (context.cuh): RB200_ENGINES / RB200_LANES override the compiled defaults; the counting pass renders
+    // one batch at a time
+    c->numEngines = RB_ENGINES; c->numLanes = RB_LANES;
+    if (const char* e = getenv("RB200_ENGINES")) c->numEngines = atoi(e);
+    if (const char* e = getenv("RB200_LANES")) c->numLanes = atoi(e);
+    if (flags & RB200_FLAG_COUNT_BVH) { c->numEngines = 1; c->numLanes = 1; }
+    if (c->numEngines < 1 || c->numEngines > RB_MAX_ENGINES || c->numLanes < 1 || c->numLanes > RB_MAX_LANES ||
+        (uint64_t)N * (uint64_t)c->numLanes > 0x7FFFFFFFull) {
+        set_error("engines x lanes = %d x %d out of range (at most %d x %d, lanes * pixels < 2^31)", c->numEngines, c->numLanes,
+                  RB_MAX_ENGINES, RB_MAX_LANES);
+        rb200_context_destroy(c);
+        return RB200_ERR_INVALID_ARGUMENT;
+    }
     int rc;
-#define A(ptr, n) if ((rc = ctx_alloc(c, &(ptr), (n))) != RB200_OK) return rc
-    for (int lane = 0; lane < RB_LANES; lane++) {
-        WaveParams& L = c->lanes[lane];
+#define A(ptr, n) if ((rc = ctx_alloc(c, &(ptr), (n))) != RB200_OK) { rb200_context_destroy(c); return rc; }
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); rb200_context_destroy(c); return RB200_ERR_CUDA; } } while (0)
+    float4* image = nullptr;
+    A(image, N);
+    for (int en = 0; en < c->numEngines; en++) {
+        Engine& E = c->eng[en];
+        E.numLanes = c->numLanes;
+        WaveParams& L = E.P;
+        const size_t NT = N * (size_t)c->numLanes;
         L.W = width; L.H = height; L.N = (uint32_t)N; L.flags = flags;
+        L.numLanes = (uint32_t)c->numLanes; L.NT = (uint32_t)NT;
         L.tileRank = 0; L.tileCount = 1; L.tileSize = 32; L.tilesX = (width + 31u) / 32u;
+        L.image = image;
 #if RB_PAIR_STATE == 2
         // one 128-byte line per slot: float4 records 0..7 = rayO, rayD, thr, st, hit, rad, sum, (spare)
-        A(L.rayO.p, 8 * N); L.rayD.p = L.rayO.p + 1; L.thr.p = L.rayO.p + 2; L.st.p = reinterpret_cast<uint4*>(L.rayO.p + 3);
+        A(L.rayO.p, 8 * NT); L.rayD.p = L.rayO.p + 1; L.thr.p = L.rayO.p + 2; L.st.p = reinterpret_cast<uint4*>(L.rayO.p + 3);
         L.hit.p = reinterpret_cast<uint4*>(L.rayO.p + 4); L.rad.p = L.rayO.p + 5; L.sum.p = L.rayO.p + 6;
 #elif RB_PAIR_STATE
         // interleaved pairs (see context.cuh): record 2*slot is the first member, 2*slot+1 the second
-        A(L.rayO.p, 2 * N); L.rayD.p = L.rayO.p + 1;
-        A(L.thr.p, 2 * N);  L.st.p = reinterpret_cast<uint4*>(L.thr.p + 1);
-        A(L.hit.p, 2 * N);  L.rad.p = reinterpret_cast<float4*>(L.hit.p + 1);
-        A(L.sum.p, N);
+        A(L.rayO.p, 2 * NT); L.rayD.p = L.rayO.p + 1;
+        A(L.thr.p, 2 * NT);  L.st.p = reinterpret_cast<uint4*>(L.thr.p + 1);
+        A(L.hit.p, 2 * NT);  L.rad.p = reinterpret_cast<float4*>(L.hit.p + 1);
+        A(L.sum.p, NT);
 #else
-        A(L.rayO.p, N); A(L.rayD.p, N); A(L.hit.p, N); A(L.thr.p, N); A(L.rad.p, N); A(L.sum.p, N); A(L.st.p, N);
+        A(L.rayO.p, NT); A(L.rayD.p, NT); A(L.hit.p, NT); A(L.thr.p, NT); A(L.rad.p, NT); A(L.sum.p, NT); A(L.st.p, NT);
 #endif
-        A(L.shO.p, N); A(L.shD.p, N); A(L.shA.p, N); A(L.shB.p, N); A(L.shT.p, N);
-        A(L.rayQ[0], N); A(L.rayQ[1], N);
-        for (int m = 0; m < 5; m++) A(L.matQ[m], N);
-        A(L.endQ, N); A(L.counters, 2 * CNT_SET); A(L.mean.p, N); A(L.stats, ST_COUNT);
-        RB_CUDA(cudaMemsetAsync(L.stats, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
-        RB_CUDA(cudaStreamCreateWithFlags(&c->laneStream[lane], cudaStreamNonBlocking));
-        RB_CUDA(cudaEventCreateWithFlags(&c->accumDone[lane], cudaEventDisableTiming));
-        RB_CUDA(cudaEventCreateWithFlags(&c->staggerEv[lane], cudaEventDisableTiming));
+        A(L.shO.p, NT); A(L.shD.p, NT); A(L.shA.p, NT); A(L.shB.p, NT); A(L.shT.p, NT);
+        A(L.rayQ[0], NT); A(L.rayQ[1], NT);
+        for (int m = 0; m < 5; m++) A(L.matQ[m], NT);
+        A(L.endQ, NT); A(L.counters, 2 * CNT_SET); A(L.mean.p, NT); A(L.stats, (size_t)RB_MAX_LANES * ST_COUNT);
+        CK(cudaMemsetAsync(L.stats, 0, (size_t)RB_MAX_LANES * ST_COUNT * sizeof(unsigned long long), c->stream));
+        CK(cudaMemsetAsync(L.counters, 0, 2 * CNT_SET * sizeof(uint32_t), c->stream));
+        CK(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&E.accumDone, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&E.staggerEv, cudaEventDisableTiming));
     }
     c->staggerWave = RB_STAGGER_WAVE;
     if (const char* e = getenv("RB200_STAGGER_WAVE")) c->staggerWave = atoi(e);
-    preload_wave_kernels();
+    if ((rc = configure_wave_kernels(c)) != RB200_OK) { rb200_context_destroy(c); return rc; }
     preload_post_kernels();
-    RB_CUDA(cudaEventCreateWithFlags(&c->frontMark, cudaEventDisableTiming));
-    A(c->statsSnap, ST_COUNT);
-    A(P.image, N); A(c->ping, N); A(c->pong, N); A(c->ldr, N);
+    CK(cudaEventCreateWithFlags(&c->frontMark, cudaEventDisableTiming));
+    A(c->statsSnap, ST_COUNT); A(c->statsLast, ST_COUNT); A(c->queryCursor, 1);
+    A(c->ping, N); A(c->pong, N); A(c->ldr, N);
     // rb200_present_sum's staging image: allocated here in sum mode (cudaMalloc synchronises the device, which would
-    // drain the lanes if it happened on the first presented frame), on first use otherwise
+    // drain the engines if it happened on the first presented frame), on first use otherwise
     if (flags & RB200_FLAG_ACCUM_SUM) A(c->resolved, N);
-    for (int lane = 1; lane < RB_LANES; lane++) c->lanes[lane].image = P.image;
+    WaveParams& P = c->wp;
 #undef A
-    RB_CUDA(cudaMemsetAsync(c->statsSnap, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
-    RB_CUDA(cudaMemsetAsync(P.image, 0, N * sizeof(float4), c->stream));
-    RB_CUDA(cudaMemsetAsync(c->ldr, 0, N * sizeof(uchar4), c->stream));
-    RB_CUDA(cudaStreamSynchronize(c->stream));
+    CK(cudaMemsetAsync(c->statsSnap, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->statsLast, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(P.image, 0, N * sizeof(float4), c->stream));
+    CK(cudaMemsetAsync(c->ldr, 0, N * sizeof(uchar4), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+#undef CK
     *out = c;
     return RB200_OK;
 }
@@ -142,28 +167,31 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
 RB200_API int rb200_context_destroy(RB200Context* ctx) {
     if (!ctx) return RB200_OK;
     cudaSetDevice(ctx->device);
-    for (int lane = 0; lane < RB_LANES; lane++) if (ctx->laneStream[lane]) cudaStreamSynchronize(ctx->laneStream[lane]);
-    cudaStreamSynchronize(ctx->stream);
+    for (int e = 0; e < RB_MAX_ENGINES; e++) if (ctx->eng[e].stream) cudaStreamSynchronize(ctx->eng[e].stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void* p : ctx->allocations) cudaFree(p);
     for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
-    for (int lane = 0; lane < RB_LANES; lane++) {
-        if (ctx->waveGraph[lane]) cudaGraphExecDestroy(ctx->waveGraph[lane]);
-        if (ctx->staggerEv[lane]) cudaEventDestroy(ctx->staggerEv[lane]);
-        if (ctx->accumDone[lane]) cudaEventDestroy(ctx->accumDone[lane]);
-        if (ctx->laneStream[lane]) cudaStreamDestroy(ctx->laneStream[lane]);
+    for (int e = 0; e < RB_MAX_ENGINES; e++) {
+        Engine& E = ctx->eng[e];
+        for (WaveGraph& g : E.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (E.staggerEv) cudaEventDestroy(E.staggerEv);
+        if (E.accumDone) cudaEventDestroy(E.accumDone);
+        if (E.stream) cudaStreamDestroy(E.stream);
     }
     if (ctx->frontMark) cudaEventDestroy(ctx->frontMark);
     if (ctx->waveCountsDev) cudaFree(ctx->waveCountsDev);
     for (cudaEvent_t e : ctx->ldrPendingEvents) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ldrEventPool) cudaEventDestroy(e);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();
     delete ctx;
     return RB200_OK;
 }
 
 RB200_API int rb200_context_set_stream(RB200Context* ctx, void* cuda_stream) {
     if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
-    for (int lane = 0; lane < RB_LANES; lane++) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[lane]));
+    RB_CUDA(cudaSetDevice(ctx->device));
+    for (int e = 0; e < ctx->numEngines; e++) RB_CUDA(cudaStreamSynchronize(ctx->eng[e].stream));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream;
@@ -302,8 +330,8 @@ RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB2
                 attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
                 attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
                 bool ok = true;
-                for (int lane = 0; lane < RB_LANES; lane++)
-                    ok &= cudaStreamSetAttribute(ctx->laneStream[lane], cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+                for (int e = 0; e < ctx->numEngines; e++)
+                    ok &= cudaStreamSetAttribute(ctx->eng[e].stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
                 ok &= cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
                 if (ok) sc->l2PersistBytes = setAside;
             }
@@ -352,6 +380,7 @@ RB200_API int rb200_render_batch(RB200Context* ctx, const RB200Scene* scene, con
 
 RB200_API int rb200_resolve_sum(RB200Context* ctx, uint32_t numBatches) {
     if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
     return resolve_sum(ctx, numBatches);
 }
 
@@ -365,8 +394,10 @@ RB200_API int rb200_postprocess(RB200Context* ctx, const RB200BloomPushConsts* b
 RB200_API int rb200_context_set_tiles(RB200Context* ctx, uint32_t tileRank, uint32_t tileCount, uint32_t tileSize) {
     if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
     if (tileCount == 0 || tileRank >= tileCount || tileSize == 0) { set_error("invalid tile partition: need tileRank < tileCount and tileSize > 0"); return RB200_ERR_INVALID_ARGUMENT; }
-    for (int lane = 0; lane < RB_LANES; lane++) {
-        WaveParams& L = ctx->lanes[lane];
+    RB_CUDA(cudaSetDevice(ctx->device));
+    invalidate_speculation(ctx);      // batches in flight were generated with the old partition
+    for (int e = 0; e < ctx->numEngines; e++) {
+        WaveParams& L = ctx->eng[e].P;
         L.tileRank = tileRank; L.tileCount = tileCount; L.tileSize = tileSize; L.tilesX = (ctx->width + tileSize - 1u) / tileSize;
     }
     return RB200_OK;
@@ -383,6 +414,7 @@ RB200_API int rb200_present_sum(RB200Context* ctx, const void* device_sum_rgba32
 
 RB200_API int rb200_read_ldr(RB200Context* ctx, uint8_t* rgba8) {
     if (!ctx || !rgba8) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
     RB_CUDA(cudaMemcpyAsync(rgba8, ctx->ldr, (size_t)ctx->width * ctx->height * 4, cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     return RB200_OK;
@@ -390,6 +422,7 @@ RB200_API int rb200_read_ldr(RB200Context* ctx, uint8_t* rgba8) {
 
 RB200_API int rb200_read_ldr_async(RB200Context* ctx, uint8_t* rgba8) {
     if (!ctx || !rgba8) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
     RB_CUDA(cudaMemcpyAsync(rgba8, ctx->ldr, (size_t)ctx->width * ctx->height * 4, cudaMemcpyDeviceToHost, ctx->stream));
     cudaEvent_t e;
     if (!ctx->ldrEventPool.empty()) { e = ctx->ldrEventPool.back(); ctx->ldrEventPool.pop_back(); }
@@ -401,6 +434,7 @@ RB200_API int rb200_read_ldr_async(RB200Context* ctx, uint8_t* rgba8) {
 
 RB200_API int rb200_wait_ldr_pending(RB200Context* ctx, uint32_t max_pending) {
     if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
     while (ctx->ldrPendingEvents.size() > max_pending) {
         cudaEvent_t e = ctx->ldrPendingEvents.front();
         ctx->ldrPendingEvents.erase(ctx->ldrPendingEvents.begin());
@@ -412,7 +446,21 @@ RB200_API int rb200_wait_ldr_pending(RB200Context* ctx, uint32_t max_pending) {
 
 RB200_API int rb200_wait_ldr(RB200Context* ctx) { return rb200_wait_ldr_pending(ctx, 0); }
 
-RB200_API uint32_t rb200_pipeline_depth(void) { return RB_LANES; }
+// Frames a display loop should keep in flight so that the host never drains the device: the batches behind the one being
+// presented are traced speculatively inside the library, so this no longer depends on the lane count.
+RB200_API uint32_t rb200_pipeline_depth(void) { return 4u; }
+
+RB200_API int rb200_engine_config(RB200Context* ctx, uint32_t* engines, uint32_t* lanes, uint64_t* discarded_batches) {
+    if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
+    if (engines) *engines = (uint32_t)ctx->numEngines;
+    if (lanes) *lanes = (uint32_t)ctx->numLanes;
+    if (discarded_batches) {
+        uint64_t w = 0;
+        for (int e = 0; e < ctx->numEngines; e++) w += ctx->eng[e].wastedBatches;
+        *discarded_batches = w;
+    }
+    return RB200_OK;
+}
 
 RB200_API int rb200_host_alloc(size_t bytes, void** out) {
     if (!out || bytes == 0) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
@@ -430,6 +478,7 @@ RB200_API int rb200_host_free(void* p) {
 
 RB200_API int rb200_read_hdr(RB200Context* ctx, float* rgba32f) {
     if (!ctx || !rgba32f) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
     RB_CUDA(cudaMemcpyAsync(rgba32f, ctx->wp.image, (size_t)ctx->width * ctx->height * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     return RB200_OK;
@@ -437,6 +486,7 @@ RB200_API int rb200_read_hdr(RB200Context* ctx, float* rgba32f) {
 
 RB200_API int rb200_write_hdr(RB200Context* ctx, const float* rgba32f) {
     if (!ctx || !rgba32f) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
     RB_CUDA(cudaMemcpyAsync(ctx->wp.image, rgba32f, (size_t)ctx->width * ctx->height * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     return RB200_OK;
@@ -461,20 +511,30 @@ RB200_API int rb200_trace_rays(RB200Context* ctx, const RB200Scene* scene, uint3
     return trace_rays(ctx, scene, n, origins, directions, tmax, any_hit, out_hits);
 }
 
+RB200_API int rb200_bench_trace(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* origins, const float* directions,
+                                const float* tmax, int any_hit, uint32_t reps, float* out_ms_per_launch, uint64_t* out_checksum) {
+    if (!ctx || !scene || !origins || !directions || !tmax) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
+    return bench_trace(ctx, scene, n, origins, directions, tmax, any_hit, reps, out_ms_per_launch, out_checksum);
+}
+
 RB200_API int rb200_get_stats(RB200Context* ctx, RB200Stats* last_batch, RB200Stats* cumulative) {
     if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
-    // per-lane counters hold the lane's last batch; k_accumulate adds them to the cumulative array when the batch ends.
-    // The front-end stream waits for the last batch's accumulation, which is ordered after every earlier batch.
+    // a lane's counters hold its batch; k_accumulate copies them to statsLast and adds them to the cumulative array when
+    // the batch is folded. The front-end stream waits for the last fold, which is ordered after every earlier one.
     unsigned long long lastc[ST_COUNT] = {0}, cum[ST_COUNT];
-    const rb200::WaveParams& lastLane = ctx->lanes[ctx->batchCalls > 0 ? (ctx->batchCalls - 1) % RB_LANES : 0];
-    if (ctx->batchCalls > 0) RB_CUDA(cudaMemcpyAsync(lastc, lastLane.stats, sizeof(lastc), cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(cudaSetDevice(ctx->device));
+    RB_CUDA(cudaMemcpyAsync(lastc, ctx->statsLast, sizeof(lastc), cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(cudaMemcpyAsync(cum, ctx->statsSnap, sizeof(cum), cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     RB200Stats& L = ctx->last; RB200Stats& Cm = ctx->cumulative;
     L.extendRays = lastc[ST_EXTEND]; L.shadowRays = lastc[ST_SHADOW];
-    L.paths = lastc[ST_PATHS]; L.nodeVisits = lastc[ST_NODES]; L.triTests = lastc[ST_TRIS];
+    L.paths = lastc[ST_PATHS];
+    L.nodeVisits = lastc[ST_NODES] + lastc[ST_NODES_SHADOW]; L.triTests = lastc[ST_TRIS] + lastc[ST_TRIS_SHADOW];
+    L.shadowNodeVisits = lastc[ST_NODES_SHADOW]; L.shadowTriTests = lastc[ST_TRIS_SHADOW];
     Cm.extendRays = cum[ST_EXTEND]; Cm.shadowRays = cum[ST_SHADOW]; Cm.paths = cum[ST_PATHS];
-    Cm.nodeVisits = cum[ST_NODES]; Cm.triTests = cum[ST_TRIS]; Cm.kernelLaunches = ctx->launches;
+    Cm.nodeVisits = cum[ST_NODES] + cum[ST_NODES_SHADOW]; Cm.triTests = cum[ST_TRIS] + cum[ST_TRIS_SHADOW];
+    Cm.shadowNodeVisits = cum[ST_NODES_SHADOW]; Cm.shadowTriTests = cum[ST_TRIS_SHADOW]; Cm.kernelLaunches = ctx->launches;
     if (last_batch) *last_batch = L;
     if (cumulative) *cumulative = Cm;
     return RB200_OK;
@@ -483,11 +543,17 @@ RB200_API int rb200_get_stats(RB200Context* ctx, RB200Stats* last_batch, RB200St
 RB200_API int rb200_get_kernel_times(RB200Context* ctx, RB200KernelTimes* out) {
     if (!ctx || !out) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
     if (!(ctx->flags & RB200_FLAG_TIME_KERNELS)) { set_error("context was not created with RB200_FLAG_TIME_KERNELS"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     memset(out, 0, sizeof(*out));
-    std::vector<uint32_t> waveCounts((size_t)ctx->waveCountsWaves * 2, 0u);
+    std::vector<uint32_t> waveCounts((size_t)ctx->waveCountsWaves * CNT_SET, 0u);
     if (ctx->waveCountsDev && ctx->waveCountsWaves)
         RB_CUDA(cudaMemcpy(waveCounts.data(), ctx->waveCountsDev, waveCounts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint32_t w = 0; w < ctx->waveCountsWaves; w++) {
+        const uint32_t* c = &waveCounts[(size_t)w * CNT_SET];
+        out->extendRays += c[CNT_RAYS]; out->shadowRays += c[CNT_SHADOW]; out->finishItems += c[CNT_END];
+        for (int m = 0; m < 5; m++) out->shadeItems[m] += c[CNT_MAT0 + m];
+    }
     const uint32_t half = ctx->width * ctx->height / 2u;
     uint32_t extendWave = 0, shadowWave = 0;
     for (size_t i = 0; i < ctx->evClass.size(); i++) {
@@ -497,14 +563,14 @@ RB200_API int rb200_get_kernel_times(RB200Context* ctx, RB200KernelTimes* out) {
         if (c == 0) out->generateMs += ms;
         else if (c == 1) {
             out->extendMs += ms; out->extendLaunches++;
-            const uint32_t n = extendWave < ctx->waveCountsWaves ? waveCounts[2 * (size_t)extendWave] : 0u;
+            const uint32_t n = extendWave < ctx->waveCountsWaves ? waveCounts[(size_t)CNT_SET * extendWave + CNT_RAYS] : 0u;
             if (n >= half) { out->extendFullMs += ms; out->extendFullLaunches++; out->extendFullRays += n; }
             extendWave++;
         }
         else if (c >= 2 && c <= 6) { out->shadeMs[c - 2] += ms; out->shadeLaunches++; }
         else if (c == 7) {
             out->shadowMs += ms; out->shadowLaunches++;
-            const uint32_t n = shadowWave < ctx->waveCountsWaves ? waveCounts[2 * (size_t)shadowWave + 1] : 0u;
+            const uint32_t n = shadowWave < ctx->waveCountsWaves ? waveCounts[(size_t)CNT_SET * shadowWave + CNT_SHADOW] : 0u;
             if (n >= half) { out->shadowFullMs += ms; out->shadowFullLaunches++; out->shadowFullRays += n; }
             shadowWave++;
         }
@@ -578,6 +644,7 @@ RB200_API int rb200_measure_gather(RB200Context* ctx, size_t tableBytes, uint32_
 
 RB200_API int rb200_synchronize(RB200Context* ctx) {
     if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     return RB200_OK;
 }

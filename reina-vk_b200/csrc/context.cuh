@@ -21,7 +21,7 @@ namespace rb200 {
 // counters of one wave parity set
 enum { CNT_RAYS = 0, CNT_MAT0 = 1, CNT_MISS = 5, CNT_SHADOW = 6, CNT_END = 7, CNT_CURSOR_EXTEND = 8, CNT_CURSOR_SHADOW = 9, CNT_SET = 12 };
 // device statistics (unsigned long long each)
-enum { ST_EXTEND = 0, ST_SHADOW = 1, ST_PATHS = 2, ST_NODES = 3, ST_TRIS = 4, ST_COUNT = 8 };
+enum { ST_EXTEND = 0, ST_SHADOW = 1, ST_PATHS = 2, ST_NODES = 3, ST_TRIS = 4, ST_NODES_SHADOW = 5, ST_TRIS_SHADOW = 6, ST_COUNT = 8 };
 
 // path flags kept in PathState.st.y (low byte); the traced-segment counter lives in bits 8..31
 enum { F_INSIDE = 1u, F_FIRST = 2u, F_PREVSKIP = 4u };
@@ -71,38 +71,107 @@ static constexpr int SUM_STRIDE = RB_PAIR_STATE == 2 ? 8 : 1;
 struct WaveParams {
     DeviceScene S;
     RB200RtPushConsts pc;
-    uint32_t W, H, N, flags;
+    uint32_t W, H, N, flags;                  // N = W * H = pixels = slots of ONE lane
     uint32_t tileRank, tileCount, tileSize, tilesX;   // interleaved-tile partition (rb200_context_set_tiles); tileCount 1 = whole image
+    uint32_t numLanes, NT;                    // lanes of this engine; NT = numLanes * N = slots of the engine (slot = lane * N + pixel)
     StateArr<float4, STATE_STRIDE> rayO;      // xyz origin
     StateArr<float4, STATE_STRIDE> rayD;      // xyz direction (not necessarily unit)
     StateArr<uint4, STATE_STRIDE> hit;        // x = bits(b1), y = bits(b2), z = primitive, w = instance
     StateArr<float4, STATE_STRIDE> thr;       // xyz throughput, w = accumulatedDistance
     StateArr<float4, STATE_STRIDE> rad;       // xyz radiance of the current path
     StateArr<float4, SUM_STRIDE> sum;       // xyz summed sample colours of this batch, w = bits(actualSamples)
-    StateArr<uint4, STATE_STRIDE> st;         // x = rng state, y = flags | segments << 8, z = sample index
+    StateArr<uint4, STATE_STRIDE> st;         // x = rng state, y = flags | segments << 8, z = sample index, w = shadow rays of this path
     StateArr<float4> shO, shD, shA, shB, shT;   // shadow-ray records (compacted): origin/tmax, dir, D/wNEE, E*wBRDF/slot, throughput
     uint32_t* rayQ[2];
     uint32_t* matQ[5]; // 0..3 materials, 4 = miss
     uint32_t* endQ;
     uint32_t* counters;            // [2][CNT_SET]
-    unsigned long long* stats;     // [ST_COUNT]
-    StateArr<float4> mean;         // per pixel: mean of this batch's valid samples (xyz), w = 1 if any sample was valid
-    float4* image;                 // HDR accumulation image (shared by both lanes)
+    unsigned long long* stats;     // [RB_MAX_LANES][ST_COUNT]: counters of the batch each lane is rendering
+    StateArr<float4> mean;         // per slot: mean of this batch's valid samples (xyz), w = 1 if any sample was valid
+    float4* image;                 // HDR accumulation image (shared by all engines and lanes)
 };
 
 } // namespace rb200
 
-// Number of batches in flight. A batch's waves thin out (at 1080p, 8 spp x 16 bounces: wave 40 of 128 carries 8 % of
-// the paths, wave 64 0.2 %) but a thin wave still costs 50-170 us of dependent-fetch latency per kernel; with more
-// lanes more of those tails run beside another batch's full waves. 0.5 GB of path state per lane at 1080p.
-// Headline scene on B200, device-resident loop: 1 / 2 / 3 / 4 / 6 lanes = 1478 / 1798 / 1891 / 1955 / 1985 Mrays/s.
+// ---------------------------------------------------------------------------------------------------
+// Engines and lanes: how several batches share the kernels of a wave.
+//
+// A batch's waves thin out — at 1080p, 8 spp x 16 bounces, wave 40 of 128 carries 8 % of the paths, wave 64 0.2 % — but
+// a thin wave still costs the dependent-fetch latency of its longest ray in every traversal launch, and the samples of a
+// pixel are sequential by construction (one RNG stream per pixel and batch), so a batch cannot be made shorter.
+// Round 1 overlapped the thin tails by running RB_LANES independent wave loops on as many streams; every loop still
+// launched its own thin waves (102 of a batch's 128 extend launches took 38 % of the extend time for 15 % of the rays).
+//
+// Now an ENGINE owns L lanes (path-state sets) that SHARE one set of queues and one wave loop on one stream: the
+// kernels of a wave process the rays of every lane's batch together (slot = lane * N + pixel; a slot is still private
+// to its pixel and batch, so the image does not depend on how batches are mixed). The L batches in flight are L
+// consecutive batches of the caller's sequence, staggered by ceil(maxWaves / L) waves: while batch b runs waves
+// 96..127, b+1 runs 64..95, b+2 32..63 and b+3 0..31, so every launch of the engine carries about one batch's worth of
+// rays in total and no launch is thin. Batches b+1.. are started SPECULATIVELY: rb200_render_batch(b) predicts that the
+// next calls will differ from this one only by sampleBatch += stride (progressive rendering, the reference's frame loop
+// src/Reina.cpp:425-470; stride = number of ranks under a sample split). A batch is only ever folded into the image by
+// the call that asks for it, in call order, after all of its waves — the contract of rb200_render_batch is unchanged.
+// A call that does not match the prediction (camera moved, other scene, other sample counts) discards the speculative
+// lanes and starts over; speculation begins with the second call of a regular sequence, so isolated calls pay nothing.
+// A context owns E engines on E streams (calls rotate through them) so that kernels of different classes — traversal:
+// issue / latency-bound, shading: DRAM-bound — still overlap. E = 4, L = 1 is the round-1 organisation.
+// ---------------------------------------------------------------------------------------------------
+#ifndef RB_MAX_ENGINES
+#define RB_MAX_ENGINES 4
+#endif
+#ifndef RB_MAX_LANES
+#define RB_MAX_LANES 8
+#endif
+#ifndef RB_ENGINES
+#define RB_ENGINES 1           // default engines per context (RB200_ENGINES overrides at context creation)
+#endif
 #ifndef RB_LANES
-#define RB_LANES 4
+#define RB_LANES 4             // default lanes per engine (RB200_LANES overrides)
+#endif
+#ifndef RB_GRAPH_CHUNK
+#define RB_GRAPH_CHUNK 32      // waves per captured graph (even: a chunk preserves the queue parity)
 #endif
 
 #ifndef RB_STAGGER_WAVE
 #define RB_STAGGER_WAVE 0      // 0: 5/32 of the batch's waves (wave 20 of 128); see RB200Context::staggerWave
 #endif
+
+namespace rb200 {
+
+struct LaneState {
+    bool active = false;
+    uint32_t sampleBatch = 0;      // the batch this lane renders
+    uint32_t wavesDone = 0;
+};
+
+struct WaveGraph {
+    cudaGraphExec_t exec = nullptr;
+    uint32_t waves = 0, parity = 0, staggerAt = 0;
+};
+
+struct Engine {
+    WaveParams P{};                         // arrays sized numLanes * N
+    cudaStream_t stream = nullptr;
+    cudaEvent_t accumDone = nullptr, staggerEv = nullptr;
+    int numLanes = 1;
+    LaneState lane[RB_MAX_LANES];
+    int head = 0;                            // lane of the oldest batch in flight
+    int active = 0;                          // lanes in flight: head, head+1, ... (mod numLanes), in batch order
+    uint32_t globalWave = 0;                 // waves issued since the last reset: its parity selects the queue set
+    // prediction state
+    bool keyValid = false;
+    WaveParams key{};                        // P with pc.sampleBatch = 0 at the last call
+    const RB200Scene* scene = nullptr;
+    bool havePrev = false;
+    uint32_t prevBatch = 0;
+    uint32_t stride = 1;                     // predicted sampleBatch increment between this engine's calls
+    uint32_t streak = 0;                     // consecutive calls that continued the sequence
+    std::vector<WaveGraph> graphs;           // captured chunks of the wave loop for the current key
+    uint64_t calls = 0;
+    uint64_t wastedBatches = 0;              // speculative batches discarded by a mismatch
+};
+
+} // namespace rb200
 
 struct RB200Context {
     uint32_t width = 0, height = 0, flags = 0;
@@ -110,45 +179,38 @@ struct RB200Context {
     int numSMs = 148;
     cudaStream_t stream = nullptr;             // front-end stream: API calls are ordered on it (may be the caller's)
     bool ownStream = false;
-    // RB_LANES lanes (path-state sets + internal streams). Consecutive rb200_render_batch calls rotate through the
-    // lanes so the long, thinly populated tail of one batch overlaps the heads of the next ones; the per-pixel
-    // accumulation into the shared HDR image stays in batch order (k_accumulate of batch b waits for that of b-1).
-    rb200::WaveParams lanes[RB_LANES]{};       // lanes[0] is also the scratch of the query entry points
-    rb200::WaveParams& wp = lanes[0];
-    cudaStream_t laneStream[RB_LANES] = {};
-    cudaEvent_t accumDone[RB_LANES] = {};
-    // The wave loop of a lane (maxWaves x (counter reset + extend + 5 shade + shadow + finish)) as a CUDA graph: its
-    // kernel arguments depend on the lane, the scene and the push constants but not on sampleBatch (only k_generate
-    // and k_accumulate read it), so one capture serves every batch until the camera / scene / sample counts change.
-    cudaGraphExec_t waveGraph[RB_LANES] = {};
-    rb200::WaveParams waveGraphKey[RB_LANES]{};
-    uint32_t waveGraphWaves[RB_LANES] = {};
+    int numEngines = RB_ENGINES, numLanes = RB_LANES;
+    rb200::Engine eng[RB_MAX_ENGINES];
+    rb200::WaveParams& wp = eng[0].P;          // eng[0]'s arrays are also the scratch of the query entry points
+    // persistent-grid sizes of the wave kernels on THIS device (function attributes are per device)
+    int gExtend = 0, gExtendC = 0, gShadow = 0, gShadowC = 0, gShade[5] = {0, 0, 0, 0, 0}, gFinish = 0, gQuery[2] = {0, 0};
     uint64_t graphCaptures = 0;
-    // Lane stagger: a batch may start once the previous batch (on the previous lane) has finished wave staggerWave.
-    // Without it batches submitted faster than they render (graph launches cost the host ~0.3 ms) run in lockstep:
-    // all lanes are in their full waves together and in their thin tails together, which is what the lanes are there
-    // to avoid. Headline scene, 4 lanes, graph launches, end-to-end ms per step with the gate at wave 0 (off) / 6 / 12 /
-    // 20 / 32 of 128: 54.9 / 50.9 / 50.6 / 50.1 / 53.0. staggerWave: 0 = 5/32 of the batch's waves, -1 = off, else the wave.
-    cudaEvent_t staggerEv[RB_LANES] = {};
+    // Engine stagger (only with one lane per engine, i.e. without speculation): a batch may start once the previous
+    // batch (on the previous engine) has finished wave staggerWave. Without it batches submitted faster than they render
+    // run in lockstep: all engines are in their full waves together and in their thin tails together.
+    // staggerWave: 0 = 5/32 of the batch's waves, -1 = off, else the wave.
     int staggerWave = 0;
     cudaEvent_t frontMark = nullptr;
     std::vector<cudaEvent_t> ldrPendingEvents; // completion events of the outstanding rb200_read_ldr_async copies, oldest first
     std::vector<cudaEvent_t> ldrEventPool;
     uint64_t batchCalls = 0;
+    int lastEngine = -1;                       // engine of the most recent rb200_render_batch call
     std::vector<void*> allocations;
     float4 *ping = nullptr, *pong = nullptr;   // bloom work images
     float4* resolved = nullptr;                // rb200_present_sum: mean image of a SUM image (allocated on first use)
     uchar4* ldr = nullptr;
+    uint32_t* queryCursor = nullptr;           // cursor of the query kernels (rb200_trace_*)
     RB200Stats last{}, cumulative{};
-    unsigned long long* statsSnap = nullptr;   // cumulative device counters (each lane's per-batch counters are added
-                                               // by k_accumulate when its batch ends)
+    unsigned long long* statsSnap = nullptr;   // cumulative device counters (a lane's per-batch counters are added by
+                                               // k_accumulate when its batch is folded into the image)
+    unsigned long long* statsLast = nullptr;   // counters of the batch folded last
     uint64_t launches = 0;                     // kernels launched by this context (all entry points)
-    // RB200_FLAG_TIME_KERNELS: event pairs recorded around the kernels of the last batch, tagged by class
+    // RB200_FLAG_TIME_KERNELS: event pairs recorded around the kernels of the last call, tagged by class
     std::vector<cudaEvent_t> evPool;
     std::vector<int> evClass;                  // class of pair i (events 2i, 2i+1): 0 generate, 1 extend, 2..6 shade, 7 shadow, 8 finish
     size_t evUsed = 0;
-    uint32_t* waveCountsDev = nullptr;         // timing pass: per wave (rays extended, shadow rays), copied from the lane counters
-    uint32_t waveCountsWaves = 0;              // waves of the last timed batch
+    uint32_t* waveCountsDev = nullptr;         // timing pass: per wave (rays extended, shadow rays), copied from the queue counters
+    uint32_t waveCountsWaves = 0;              // waves of the last timed call
     uint32_t waveCountsCap = 0;
 };
 
@@ -159,12 +221,15 @@ int trace_primary(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushC
 int trace_rays(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* o, const float* d, const float* tmax,
                int any, RB200PrimaryHit* out);
 int resolve_sum(RB200Context* ctx, uint32_t numBatches);
+int bench_trace(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* o, const float* d, const float* tmax, int any,
+                uint32_t reps, float* outMs, uint64_t* outChecksum);
+int configure_wave_kernels(RB200Context* ctx);     // per device: shared-memory limits, persistent grids, code preload
+void invalidate_speculation(RB200Context* ctx);    // drains the engines and discards speculative batches
 // post.cu
 int postprocess(RB200Context* ctx, const RB200BloomPushConsts* bloom, const RB200TonemappingPushConsts* tm,
                 const float4* source = nullptr);      // source: HDR image to post-process (default: the context's)
 int build_shade_records(const DeviceScene& S, float4* base, float4* frame, cudaStream_t stream);
 void preload_post_kernels();
-void preload_wave_kernels();
 int present_sum(RB200Context* ctx, const float4* deviceSum, uint32_t numBatches, const RB200BloomPushConsts* bloom,
                 const RB200TonemappingPushConsts* tm);
 } // namespace rb200

@@ -22,6 +22,11 @@ static constexpr int BLOCK = 256;
 #ifndef RB_TRAV_BLOCK
 #define RB_TRAV_BLOCK 256        // threads per block of k_extend / k_shadow (with RB_TRAV_MINBLOCKS: 1024 threads per SM at 64 registers)
 #endif
+// RB_SHADOW_LDCS=1: the shadow-ray records are read once, by k_shadow, and are dead afterwards: ld.global.cs (evict
+// first) keeps their 5 x 33 MB per wave from displacing the hierarchy and the path state in L2.
+#ifndef RB_SHADOW_LDCS
+#define RB_SHADOW_LDCS 0
+#endif
 #ifndef RB_TRAV_MINBLOCKS
 #define RB_TRAV_MINBLOCKS (1024 / RB_TRAV_BLOCK)      // resident blocks per SM the traversal kernels are compiled for (register cap)
 #endif
@@ -93,9 +98,35 @@ __device__ void starting_ray(const RB200RtPushConsts& pc, float px, float py, fl
     dir = rb_normalize(focalPoint - origin);
 }
 
+// lane of an engine slot (slot = lane * N + pixel); an engine has at most RB_MAX_LANES lanes
+__device__ __forceinline__ uint32_t lane_of(const WaveParams& P, uint32_t slot) {
+    uint32_t l = 0;
+    for (uint32_t k = 1; k < P.numLanes; k++) l += slot >= k * P.N ? 1u : 0u;
+    return l;
+}
+
+// Per-block accumulators of the per-lane batch counters (shared memory; flushed to WaveParams::stats once per block).
+// word 0: extend rays (low 32 bits) | shadow rays (high 32 bits) of the paths that ended; word 1: paths started.
+struct LaneAcc { unsigned long long rays[RB_MAX_LANES]; unsigned int started[RB_MAX_LANES]; };
+__device__ __forceinline__ void lane_acc_init(LaneAcc& a) {
+    if (threadIdx.x < RB_MAX_LANES) { a.rays[threadIdx.x] = 0ull; a.started[threadIdx.x] = 0u; }
+    __syncthreads();
+}
+__device__ __forceinline__ void lane_acc_flush(const WaveParams& P, LaneAcc& a) {
+    __syncthreads();
+    if (threadIdx.x < P.numLanes) {
+        const unsigned long long r = a.rays[threadIdx.x];
+        const unsigned int st = a.started[threadIdx.x];
+        unsigned long long* dst = P.stats + (size_t)threadIdx.x * ST_COUNT;
+        if (r & 0xFFFFFFFFull) atomicAdd(&dst[ST_EXTEND], r & 0xFFFFFFFFull);
+        if (r >> 32) atomicAdd(&dst[ST_SHADOW], r >> 32);
+        if (st) atomicAdd(&dst[ST_PATHS], (unsigned long long)st);
+    }
+}
+
 // start (or restart) the path of a slot: traceSegments' locals (rgen.glsl:98-104)
-__device__ __forceinline__ void begin_path(const WaveParams& P, uint32_t slot, uint32_t& rng, uint32_t sampleIdx) {
-    const uint32_t x = slot % P.W, y = slot / P.W;
+__device__ __forceinline__ void begin_path(const WaveParams& P, uint32_t slot, uint32_t pixel, uint32_t& rng, uint32_t sampleIdx) {
+    const uint32_t x = pixel % P.W, y = pixel / P.W;
     rb_v3 o, d;
     starting_ray(P.pc, (float)x, (float)y, (float)P.W, (float)P.H, rng, o, d);
     P.rayO[slot] = make_float4(o.x, o.y, o.z, 0.f);
@@ -105,32 +136,39 @@ __device__ __forceinline__ void begin_path(const WaveParams& P, uint32_t slot, u
     P.st[slot] = make_uint4(rng, F_FIRST, sampleIdx, 0u);
 }
 
-__global__ void __launch_bounds__(BLOCK) k_generate(WaveParams P) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (P.tileCount <= 1u) {
-        if (slot == 0) atomicAdd(&P.stats[ST_PATHS], (unsigned long long)P.N);
-        if (slot >= P.N) return;
-        const uint32_t x = slot % P.W, y = slot / P.W;
-        uint32_t rng = (P.pc.sampleBatch * P.H + y) * P.W + x;       // rgen.glsl:259
-        P.sum[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
-        begin_path(P, slot, rng, 0u);
-        P.rayQ[0][slot] = slot;
-        if (slot == 0) P.counters[CNT_RAYS] = P.N;
-        return;
-    }
+// Starts batch `sampleBatch` in lane `lane` of the engine: one camera path per pixel, appended to the ray queue that the
+// next wave (queue set `parity`) reads. Runs between two waves on the engine's stream.
+__global__ void __launch_bounds__(BLOCK) k_generate(WaveParams P, uint32_t lane, uint32_t sampleBatch, int parity) {
+    const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t* cnt = P.counters + parity * CNT_SET;
+    unsigned long long* laneStats = P.stats + (size_t)lane * ST_COUNT;
+    bool mine = pixel < P.N;
+    const uint32_t x = pixel % P.W, y = pixel / P.W;
     // interleaved-tile partition (latency mode): this context traces the pixels of the tiles whose
     // row-major index is congruent to tileRank; the other pixels are not touched (mean.w < 0 makes k_accumulate
     // skip them), so the partial images of all ranks add up to the single-GPU image bit for bit
-    if (slot >= P.N) return;
-    const uint32_t x = slot % P.W, y = slot / P.W;
-    const bool mine = ((y / P.tileSize) * P.tilesX + x / P.tileSize) % P.tileCount == P.tileRank;
-    if (!mine) { P.mean[slot] = make_float4(0.f, 0.f, 0.f, -1.f); return; }     // w < 0: not this rank's pixel
-    uint32_t rng = (P.pc.sampleBatch * P.H + y) * P.W + x;
+    if (mine && P.tileCount > 1u) {
+        mine = ((y / P.tileSize) * P.tilesX + x / P.tileSize) % P.tileCount == P.tileRank;
+        if (!mine) P.mean[lane * P.N + pixel] = make_float4(0.f, 0.f, 0.f, -1.f);     // w < 0: not this rank's pixel
+    }
+    // one queue reservation per block
+    __shared__ uint32_t s_base, s_count;
+    if (threadIdx.x == 0) s_count = 0u;
+    __syncthreads();
+    uint32_t rank = 0;
+    if (mine) rank = atomicAdd(&s_count, 1u);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_count) {
+        s_base = atomicAdd(&cnt[CNT_RAYS], s_count);
+        atomicAdd(&laneStats[ST_PATHS], (unsigned long long)s_count);
+    }
+    __syncthreads();
+    if (!mine) return;
+    const uint32_t slot = lane * P.N + pixel;
+    uint32_t rng = (sampleBatch * P.H + y) * P.W + x;       // rgen.glsl:259
     P.sum[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
-    begin_path(P, slot, rng, 0u);
-    const uint32_t active = __activemask();
-    queue_push(P.rayQ[0], &P.counters[CNT_RAYS], slot);
-    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(active) - 1)) atomicAdd(&P.stats[ST_PATHS], (unsigned long long)__popc(active));
+    begin_path(P, slot, pixel, rng, 0u);
+    P.rayQ[parity][s_base + rank] = slot;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -141,7 +179,7 @@ __global__ void __launch_bounds__(RB_TRAV_BLOCK, RB_TRAV_MINBLOCKS) k_extend(Wav
     uint32_t* cnt = P.counters + parity * CNT_SET;
     const uint32_t n = cnt[CNT_RAYS];
     const uint32_t* __restrict__ q = P.rayQ[parity];
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_EXTEND], (unsigned long long)n);
+    // (rays are counted per batch when their path ends: finish_slot)
     uint32_t nodeVisits = 0, triTests = 0;
     extern __shared__ __align__(16) unsigned char rb_dyn_smem[];      // WarpShared<false>[RB_TRAV_BLOCK / 32]: may exceed the 48 KB static limit
     WarpShared<false>* ws = reinterpret_cast<WarpShared<false>*>(rb_dyn_smem);
@@ -224,13 +262,13 @@ __device__ __forceinline__ bool surface_prologue(const WaveParams& P, const RB20
 }
 
 // End of a path (rgen.glsl:264-284): clamp, drop NaN samples, add to the pixel's batch sum; then either restart the
-// slot with the pixel's next sample (returns 1) or store the batch mean of the pixel (returns 0). L is the path's
-// final radiance, st the slot's state record.
-#ifndef RB_FINISH_IN_MISS
-#define RB_FINISH_IN_MISS 1      // sky misses finish their path inside the miss shader instead of going through endQ + k_finish
-#endif
-__device__ __forceinline__ uint32_t finish_slot(const WaveParams& P, const uint32_t slot, const rb_v3 L, const uint4 st,
-                                                uint32_t* cntNext, int parity) {
+// slot with the pixel's next sample or store the batch mean of the pixel. L is the path's final radiance, st the slot's
+// state record, extendRays the rays this path traced. The batch counters of the slot's lane are updated through the
+// block's accumulators.
+__device__ __forceinline__ void finish_slot(const WaveParams& P, const uint32_t slot, const rb_v3 L, const uint4 st,
+                                            const uint32_t extendRays, uint32_t* cntNext, int parity, LaneAcc& acc) {
+    const uint32_t lane = lane_of(P, slot);
+    atomicAdd(&acc.rays[lane], (unsigned long long)extendRays | ((unsigned long long)st.w << 32));
     const rb_v3 c = rb_clamp3_keepnan(L, 0.0f, P.pc.directClamp);
     float4 s4 = P.sum[slot];
     uint32_t actual = __float_as_uint(s4.w);
@@ -239,9 +277,10 @@ __device__ __forceinline__ uint32_t finish_slot(const WaveParams& P, const uint3
     if (sampleIdx < P.pc.samplesPerPixel) {
         P.sum[slot] = make_float4(s4.x, s4.y, s4.z, __uint_as_float(actual));
         uint32_t rng = st.x;
-        begin_path(P, slot, rng, sampleIdx);
+        begin_path(P, slot, slot - lane * P.N, rng, sampleIdx);
         queue_push(P.rayQ[parity ^ 1], &cntNext[CNT_RAYS], slot);
-        return 1u;
+        atomicAdd(&acc.started[lane], 1u);
+        return;
     }
     // last sample of the pixel: this batch's mean over the valid samples (rgen.glsl:275); folded into the image by
     // k_accumulate once the whole batch is done
@@ -250,11 +289,10 @@ __device__ __forceinline__ uint32_t finish_slot(const WaveParams& P, const uint3
         const rb_v3 fin = rb_mk3(s4.x, s4.y, s4.z) / (float)actual;
         P.mean[slot] = make_float4(fin.x, fin.y, fin.z, 1.f);
     }
-    return 0u;
 }
 
 template <int MAT>
-__device__ __forceinline__ uint32_t shade_slot(const WaveParams& P, const uint32_t slot, uint32_t* cnt, uint32_t* cntNext, int parity) {
+__device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t slot, uint32_t* cnt, uint32_t* cntNext, int parity, LaneAcc& acc) {
     const float4 ro4 = P.rayO[slot], rd4 = P.rayD[slot];
     const rb_v3 rayOrigin = rb_mk3(ro4.x, ro4.y, ro4.z), rayDir = rb_mk3(rd4.x, rd4.y, rd4.z);
     uint4 st = P.st[slot];
@@ -270,15 +308,11 @@ __device__ __forceinline__ uint32_t shade_slot(const WaveParams& P, const uint32
         // miss shader + raygen's sky branch (rgen.glsl:138-141): radiance += sky * throughput, path ends
         const float4 L4 = P.rad[slot];
         const rb_v3 L = rb_mk3(L4.x, L4.y, L4.z) + sky_color(rayDir) * T;
-#if RB_FINISH_IN_MISS
         // nothing else can add to this path (a miss casts no shadow ray, and the previous hit's shadow ray was resolved
-        // in the previous wave), so the path ends here: about 60 % of all path ends skip endQ and k_finish
-        return finish_slot(P, slot, L, st, cntNext, parity);
-#else
-        P.rad[slot] = make_float4(L.x, L.y, L.z, 0.f);
-        queue_push(P.endQ, &cnt[CNT_END], slot);
-        return 0u;
-#endif
+        // in the previous wave), so the path ends here: about 60 % of all path ends skip endQ and k_finish.
+        // Rays traced by this path: one per shaded segment plus the one that missed.
+        finish_slot(P, slot, L, st, segments + 1u, cntNext, parity, acc);
+        return;
     }
 
     const uint4 h = P.hit[slot];
@@ -436,6 +470,7 @@ __device__ __forceinline__ uint32_t shade_slot(const WaveParams& P, const uint32
                     wBRDF = pdfBRDF * pdfBRDF / (pdfBRDF * pdfBRDF + pdfNEE * pdfNEE);
                 }
                 const rb_v3 Bv = indirect * wBRDF;
+                st.w += 1u;       // shadow rays of this path (counted into the batch when the path ends)
                 const uint32_t k = queue_reserve(&cnt[CNT_SHADOW]);
                 P.shO[k] = make_float4(o.newO.x, o.newO.y, o.newO.z, dist - 0.001f);
                 P.shD[k] = make_float4(direction.x, direction.y, direction.z, 0.f);
@@ -452,7 +487,6 @@ __device__ __forceinline__ uint32_t shade_slot(const WaveParams& P, const uint32
     P.st[slot] = make_uint4(rng, newFlags | (segments << 8), st.z, st.w);
     if (segments < P.pc.maxBounces) queue_push(P.rayQ[parity ^ 1], &cntNext[CNT_RAYS], slot);
     else queue_push(P.endQ, &cnt[CNT_END], slot);
-    return 0u;
 }
 
 #ifndef RB_SHADE_MINBLOCKS
@@ -470,13 +504,11 @@ __global__ void __launch_bounds__(RB_SHADE_BLOCK, MAT == 3 ? RB_DISNEY_MINBLOCKS
     uint32_t* cntNext = P.counters + (parity ^ 1) * CNT_SET;
     const uint32_t n = cnt[CNT_MAT0 + MAT];
     const uint32_t* __restrict__ q = P.matQ[MAT];
-    uint32_t started = 0;
+    __shared__ LaneAcc acc;           // only the miss shader ends paths
+    if (MAT == 4) lane_acc_init(acc);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        started += shade_slot<MAT>(P, q[i], cnt, cntNext, parity);
-    if (MAT == 4) {      // paths restarted by the miss shader (one counter update per warp)
-        const uint32_t warpStarted = __reduce_add_sync(0xffffffffu, started);
-        if ((threadIdx.x & 31u) == 0u && warpStarted) atomicAdd(&P.stats[ST_PATHS], (unsigned long long)warpStarted);
-    }
+        shade_slot<MAT>(P, q[i], cnt, cntNext, parity, acc);
+    if (MAT == 4) lane_acc_flush(P, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -486,19 +518,26 @@ template <bool COUNT>
 __global__ void __launch_bounds__(RB_TRAV_BLOCK, RB_TRAV_MINBLOCKS) k_shadow(WaveParams P, int parity) {
     uint32_t* cnt = P.counters + parity * CNT_SET;
     const uint32_t n = cnt[CNT_SHADOW];
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[ST_SHADOW], (unsigned long long)n);
     uint32_t nodeVisits = 0, triTests = 0;
     extern __shared__ __align__(16) unsigned char rb_dyn_smem[];      // WarpShared<true>[RB_TRAV_BLOCK / 32]
     WarpShared<true>* ws = reinterpret_cast<WarpShared<true>*>(rb_dyn_smem);
     trace_queue<true, COUNT>(
         P.S.nodes, P.S.tris, n, &cnt[CNT_CURSOR_SHADOW],
         [&](uint32_t i, rb_v3& o, rb_v3& d, float& tmax) {
+#if RB_SHADOW_LDCS
+            const float4 o4 = __ldcs(P.shO.p + i), d4 = __ldcs(P.shD.p + i);
+#else
             const float4 o4 = P.shO[i], d4 = P.shD[i];
+#endif
             o = rb_mk3(o4.x, o4.y, o4.z); d = rb_mk3(d4.x, d4.y, d4.z); tmax = o4.w;
         },
         [&](uint32_t i, const RayHit& h) {
             const bool occluded = h.tri != 0xFFFFFFFFu;
+#if RB_SHADOW_LDCS
+            const float4 A = __ldcs(P.shA.p + i), B = __ldcs(P.shB.p + i), T = __ldcs(P.shT.p + i);
+#else
             const float4 A = P.shA[i], B = P.shB[i], T = P.shT[i];
+#endif
             const uint32_t slot = __float_as_uint(B.w);
             const rb_v3 direct = occluded ? rb_splat3(0.0f) : rb_mk3(A.x, A.y, A.z);
             const rb_v3 combined = direct * A.w + rb_mk3(B.x, B.y, B.z);
@@ -507,9 +546,9 @@ __global__ void __launch_bounds__(RB_TRAV_BLOCK, RB_TRAV_MINBLOCKS) k_shadow(Wav
             P.rad[slot] = make_float4(L.x, L.y, L.z, 0.f);
         },
         nodeVisits, triTests, ws[threadIdx.x >> 5]);
-    if (COUNT) {
-        atomicAdd(&P.stats[ST_NODES], (unsigned long long)nodeVisits);
-        atomicAdd(&P.stats[ST_TRIS], (unsigned long long)triTests);
+    if (COUNT) {      // the counting pass runs one lane (context_create), so lane 0's counters are the batch's
+        atomicAdd(&P.stats[ST_NODES_SHADOW], (unsigned long long)nodeVisits);
+        atomicAdd(&P.stats[ST_TRIS_SHADOW], (unsigned long long)triTests);
     }
 }
 
@@ -520,15 +559,15 @@ __global__ void __launch_bounds__(BLOCK) k_finish(WaveParams P, int parity) {
     uint32_t* cnt = P.counters + parity * CNT_SET;
     uint32_t* cntNext = P.counters + (parity ^ 1) * CNT_SET;
     const uint32_t n = cnt[CNT_END];
-    uint32_t started = 0;
+    __shared__ LaneAcc acc;
+    lane_acc_init(acc);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t slot = P.endQ[i];
         const float4 L4 = P.rad[slot];
-        started += finish_slot(P, slot, rb_mk3(L4.x, L4.y, L4.z), P.st[slot], cntNext, parity);
+        const uint4 st = P.st[slot];
+        finish_slot(P, slot, rb_mk3(L4.x, L4.y, L4.z), st, st.y >> 8, cntNext, parity, acc);
     }
-    // one counter update per warp, not per thread: a same-address 64-bit atomic from every thread serialises in L2
-    const uint32_t warpStarted = __reduce_add_sync(0xffffffffu, started);
-    if ((threadIdx.x & 31u) == 0u && warpStarted) atomicAdd(&P.stats[ST_PATHS], (unsigned long long)warpStarted);
+    lane_acc_flush(P, acc);
 }
 
 // rgen.glsl:277-284: running average over batches (or the plain sum with RB200_FLAG_ACCUM_SUM). Runs once per batch,
@@ -536,9 +575,10 @@ __global__ void __launch_bounds__(BLOCK) k_finish(WaveParams P, int parity) {
 __global__ void __launch_bounds__(BLOCK) k_accumulate(float4* __restrict__ image, const float4* __restrict__ mean, uint32_t n,
                                                       uint32_t sampleBatch, uint32_t flags,
                                                       const unsigned long long* __restrict__ laneStats,
-                                                      unsigned long long* __restrict__ cumStats) {
+                                                      unsigned long long* __restrict__ cumStats,
+                                                      unsigned long long* __restrict__ lastStats) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ST_COUNT) cumStats[i] += laneStats[i];     // batches are folded one at a time, in order: no race
+    if (i < ST_COUNT) { const unsigned long long v = laneStats[i]; cumStats[i] += v; lastStats[i] = v; }     // batches are folded one at a time, in order: no race
     if (i >= n) return;
     const float4 m = mean[i];
     if (m.w < 0.f) return;       // tile partition: another rank's pixel
@@ -571,12 +611,6 @@ __global__ void k_resolve_sum(float4* image, uint32_t n, float inv) {
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-template <class K> static int persistent_grid(K kernel, int numSMs, int block = BLOCK, size_t dynSmem = 0) {
-    int perSM = 0;
-    if (dynSmem) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, block, dynSmem) != cudaSuccess || perSM < 1) perSM = 1;
-    return numSMs * perSM;
-}
 static constexpr size_t SMEM_EXTEND = sizeof(WarpShared<false>) * (RB_TRAV_BLOCK / 32);
 static constexpr size_t SMEM_SHADOW = sizeof(WarpShared<true>) * (RB_TRAV_BLOCK / 32);
 
@@ -623,197 +657,274 @@ int build_shade_records(const DeviceScene& S, float4* base, float4* frame, cudaS
     return RB200_OK;
 }
 
-// see preload_post_kernels (post.cu)
-void preload_wave_kernels() {
-    cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, k_generate);
-    cudaFuncGetAttributes(&a, k_extend<false>); cudaFuncGetAttributes(&a, k_extend<true>);
-    cudaFuncGetAttributes(&a, k_shadow<false>); cudaFuncGetAttributes(&a, k_shadow<true>);
-    cudaFuncGetAttributes(&a, k_shade<0>); cudaFuncGetAttributes(&a, k_shade<1>); cudaFuncGetAttributes(&a, k_shade<2>);
-    cudaFuncGetAttributes(&a, k_shade<3>); cudaFuncGetAttributes(&a, k_shade<4>);
-    cudaFuncGetAttributes(&a, k_finish);
-    cudaFuncGetAttributes(&a, k_accumulate);
-    cudaFuncGetAttributes(&a, k_resolve_sum);
-    cudaGetLastError();
+// ---------------------------------------------------------------------------------------------------
+// the wave loop of an engine (see context.cuh: engines, lanes and speculation)
+// ---------------------------------------------------------------------------------------------------
+struct CallTimer {          // RB200_FLAG_TIME_KERNELS: one event pair per kernel of the call
+    RB200Context* ctx; cudaStream_t s; bool on;
+    void tic(int cls) {
+        if (!on) return;
+        while (ctx->evPool.size() < ctx->evUsed + 2) { cudaEvent_t e; cudaEventCreate(&e); ctx->evPool.push_back(e); }
+        ctx->evClass.push_back(cls);
+        cudaEventRecord(ctx->evPool[ctx->evUsed], s);
+    }
+    void toc() {
+        if (!on) return;
+        cudaEventRecord(ctx->evPool[ctx->evUsed + 1], s);
+        ctx->evUsed += 2;
+    }
+};
+
+// Issues `count` waves of engine E on its stream, starting with queue set `parity`. staggerAt (1-based wave within this
+// span, 0 = none) records E.staggerEv behind that wave. `waveBase`: index of the first wave in the call (timing pass).
+static int issue_waves(RB200Context* ctx, Engine& E, uint32_t count, uint32_t parity, uint32_t staggerAt, bool capturing,
+                       CallTimer& tm, uint32_t waveBase, std::vector<uint32_t>* waveLog) {
+    WaveParams& P = E.P;
+    cudaStream_t s = E.stream;
+    const bool countBvh = (ctx->flags & RB200_FLAG_COUNT_BVH) != 0;
+    const bool nee = (ctx->flags & RB200_FLAG_NEE) != 0;
+    const uint32_t mats = P.S.materialMask & 15u;
+    for (uint32_t w = 0; w < count; w++) {
+        const int p = (int)((parity + w) & 1u);
+        RB_CUDA(cudaMemsetAsync(P.counters + (p ^ 1) * CNT_SET, 0, CNT_SET * sizeof(uint32_t), s));
+        tm.tic(1);
+        if (countBvh) k_extend<true><<<ctx->gExtendC, RB_TRAV_BLOCK, SMEM_EXTEND, s>>>(P, p);
+        else k_extend<false><<<ctx->gExtend, RB_TRAV_BLOCK, SMEM_EXTEND, s>>>(P, p);
+        tm.toc();
+        tm.tic(6); k_shade<4><<<ctx->gShade[4], RB_SHADE_BLOCK, 0, s>>>(P, p); tm.toc();
+        // a material no instance uses has an empty queue in every wave: its kernel is not launched
+        if (mats & 1u) { tm.tic(2); k_shade<0><<<ctx->gShade[0], RB_SHADE_BLOCK, 0, s>>>(P, p); tm.toc(); }
+        if (mats & 2u) { tm.tic(3); k_shade<1><<<ctx->gShade[1], RB_SHADE_BLOCK, 0, s>>>(P, p); tm.toc(); }
+        if (mats & 4u) { tm.tic(4); k_shade<2><<<ctx->gShade[2], RB_SHADE_BLOCK, 0, s>>>(P, p); tm.toc(); }
+        if (mats & 8u) { tm.tic(5); k_shade<3><<<ctx->gShade[3], RB_SHADE_BLOCK, 0, s>>>(P, p); tm.toc(); }
+        if (nee) {
+            tm.tic(7);
+            if (countBvh) k_shadow<true><<<ctx->gShadowC, RB_TRAV_BLOCK, SMEM_SHADOW, s>>>(P, p);
+            else k_shadow<false><<<ctx->gShadow, RB_TRAV_BLOCK, SMEM_SHADOW, s>>>(P, p);
+            tm.toc();
+        }
+        tm.tic(8); k_finish<<<ctx->gFinish, BLOCK, 0, s>>>(P, p); tm.toc();
+        if (tm.on && ctx->waveCountsDev && waveBase + w < ctx->waveCountsCap)      // the queue counters of this wave, device to device: no host wait
+            RB_CUDA(cudaMemcpyAsync(ctx->waveCountsDev + (size_t)CNT_SET * (waveBase + w), P.counters + p * CNT_SET, CNT_SET * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToDevice, s));
+        if (staggerAt && w + 1 == staggerAt)
+            RB_CUDA(cudaEventRecordWithFlags(E.staggerEv, s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+        if (waveLog) {
+            waveLog->resize((size_t)(waveBase + w + 1) * CNT_SET);
+            RB_CUDA(cudaMemcpyAsync(&(*waveLog)[(size_t)(waveBase + w) * CNT_SET], P.counters + p * CNT_SET, CNT_SET * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToHost, s));
+            RB_CUDA(cudaStreamSynchronize(s));
+        }
+    }
+    RB_CUDA(cudaGetLastError());
+    return RB200_OK;
+}
+
+static uint32_t kernels_per_wave(const RB200Context* ctx, const Engine& E) {
+    return ((ctx->flags & RB200_FLAG_NEE) ? 4u : 3u) + (uint32_t)__builtin_popcount(E.P.S.materialMask & 15u);
+}
+
+static void drop_graphs(Engine& E) {
+    for (WaveGraph& g : E.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    E.graphs.clear();
+}
+
+// `count` waves as graph launches: chunks of RB_GRAPH_CHUNK waves (a few hundred stream operations become one launch, and
+// the device-side gap between dependent kernels shrinks); a chunk is captured once per (length, parity, stagger position)
+// and reused until the engine's key (scene, camera, sample counts) changes.
+static int run_waves(RB200Context* ctx, Engine& E, uint32_t count, uint32_t staggerAt, CallTimer& tm, uint32_t waveBase,
+                     std::vector<uint32_t>* waveLog) {
+    static const bool graphsOff = getenv("RB200_NO_GRAPH") != nullptr;
+    const bool direct = tm.on || waveLog || graphsOff || (ctx->flags & RB200_FLAG_COUNT_BVH);
+    uint32_t done = 0;
+    while (done < count) {
+        const uint32_t c = std::min<uint32_t>(count - done, RB_GRAPH_CHUNK);
+        const uint32_t parity = E.globalWave & 1u;
+        const uint32_t st = (staggerAt > done && staggerAt <= done + c) ? staggerAt - done : 0u;
+        if (direct) {
+            const int rc = issue_waves(ctx, E, c, parity, st, false, tm, waveBase + done, waveLog);
+            if (rc != RB200_OK) return rc;
+        } else {
+            WaveGraph* g = nullptr;
+            for (WaveGraph& k : E.graphs) if (k.waves == c && k.parity == parity && k.staggerAt == st) { g = &k; break; }
+            if (!g) {
+                cudaGraph_t graph = nullptr;
+                RB_CUDA(cudaStreamBeginCapture(E.stream, cudaStreamCaptureModeThreadLocal));
+                const int rc = issue_waves(ctx, E, c, parity, st, true, tm, 0, nullptr);
+                const cudaError_t ce = cudaStreamEndCapture(E.stream, &graph);
+                if (rc != RB200_OK || ce != cudaSuccess || !graph) {
+                    cudaGetLastError();
+                    if (graph) cudaGraphDestroy(graph);
+                    set_error("CUDA graph capture of the wave loop failed: %s", cudaGetErrorString(ce));
+                    return RB200_ERR_CUDA;
+                }
+                WaveGraph ng; ng.waves = c; ng.parity = parity; ng.staggerAt = st;
+                const cudaError_t ie = cudaGraphInstantiate(&ng.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ie != cudaSuccess) { cudaGetLastError(); set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return RB200_ERR_CUDA; }
+                E.graphs.push_back(ng);
+                g = &E.graphs.back();
+                ctx->graphCaptures++;
+            }
+            RB_CUDA(cudaGraphLaunch(g->exec, E.stream));
+        }
+        E.globalWave += c;
+        done += c;
+    }
+    return RB200_OK;
+}
+
+// Discards every batch in flight on the engine (their rays are dropped with the queue counters).
+static int reset_engine(Engine& E) {
+    for (int l = 0; l < E.numLanes; l++) {
+        if (E.lane[l].active) E.wastedBatches++;
+        E.lane[l] = LaneState();
+    }
+    E.head = 0; E.active = 0; E.globalWave = 0;
+    RB_CUDA(cudaMemsetAsync(E.P.counters, 0, 2 * CNT_SET * sizeof(uint32_t), E.stream));
+    return RB200_OK;
+}
+
+void invalidate_speculation(RB200Context* ctx) {
+    for (int e = 0; e < ctx->numEngines; e++) {
+        Engine& E = ctx->eng[e];
+        cudaStreamSynchronize(E.stream);
+        reset_engine(E);
+        E.keyValid = false; E.havePrev = false; E.streak = 0; E.stride = 1;
+        drop_graphs(E);
+    }
+}
+
+// Starts batch `sampleBatch` in the next free lane of the engine (behind the batches already in flight).
+static int inject_batch(RB200Context* ctx, Engine& E, uint32_t sampleBatch, CallTimer& tm, uint64_t& nl) {
+    const int l = (E.head + E.active) % E.numLanes;
+    E.lane[l].active = true; E.lane[l].sampleBatch = sampleBatch; E.lane[l].wavesDone = 0;
+    E.active++;
+    WaveParams& P = E.P;
+    RB_CUDA(cudaMemsetAsync(P.stats + (size_t)l * ST_COUNT, 0, ST_COUNT * sizeof(unsigned long long), E.stream));
+    tm.tic(0);
+    k_generate<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, E.stream>>>(P, (uint32_t)l, sampleBatch, (int)(E.globalWave & 1u));
+    tm.toc();
+    nl++;
+    RB_CUDA(cudaGetLastError());
+    return RB200_OK;
 }
 
 int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc) {
     if (pc->samplesPerPixel == 0 || pc->maxBounces == 0) { set_error("samplesPerPixel and maxBounces must be > 0"); return RB200_ERR_INVALID_ARGUMENT; }
+    const uint64_t waves64 = (uint64_t)pc->samplesPerPixel * pc->maxBounces;
+    if (waves64 > (1ull << 22)) {
+        set_error("samplesPerPixel * maxBounces = %llu waves per batch: more than 2^22 (split the samples over several batches)",
+                  (unsigned long long)waves64);
+        return RB200_ERR_INVALID_ARGUMENT;
+    }
     if ((ctx->flags & RB200_FLAG_NEE) && scene->numEmissive == 0) {
         set_error("Scene must have at least one emissive object");   // src/scene/Instances.cpp:125-127
         return RB200_ERR_NO_EMITTER;
     }
-    // Lane selection: consecutive calls rotate through RB_LANES path-state sets on as many internal streams, so the
-    // thin tail of batch b (few live paths, latency-bound launches) overlaps the heads of the following batches.
-    const int lane = (int)(ctx->batchCalls % RB_LANES);
-    const int other = (lane + RB_LANES - 1) % RB_LANES;        // the lane of the previous batch
-    const bool hadPrevious = ctx->batchCalls > 0;
+    const uint32_t maxWaves = (uint32_t)waves64;
+    const int e = (int)(ctx->batchCalls % (uint64_t)ctx->numEngines);
+    const int prevEngine = ctx->lastEngine;
     ctx->batchCalls++;
-    WaveParams& P = ctx->lanes[lane];
+    ctx->lastEngine = e;
+    Engine& E = ctx->eng[e];
+    E.calls++;
+    WaveParams& P = E.P;
     P.S = scene->dev;
     P.pc = *pc;
-    cudaStream_t s = ctx->laneStream[lane];
+    cudaStream_t s = E.stream;
     // everything the caller enqueued on the front-end stream before this call (write_hdr, postprocess of the previous
     // frame, an external reduce of the image ...) must precede this batch's accumulation — not its tracing
     RB_CUDA(cudaEventRecord(ctx->frontMark, ctx->stream));
-    const bool count = (ctx->flags & RB200_FLAG_COUNT_BVH) != 0;
-    if (ctx->flags & RB200_FLAG_TIME_KERNELS)      // timing pass: no overlap
-        for (int l = 0; l < RB_LANES; l++) if (l != lane) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[l]));
-
-    static int gExtend = 0, gExtendC = 0, gShadow = 0, gShadowC = 0, gShade[5] = {0, 0, 0, 0, 0}, gFinish = 0;
-    if (!gExtend) {
-        gExtend = persistent_grid(k_extend<false>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_EXTEND);
-        gExtendC = persistent_grid(k_extend<true>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_EXTEND);
-        gShadow = persistent_grid(k_shadow<false>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_SHADOW);
-        gShadowC = persistent_grid(k_shadow<true>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_SHADOW);
-        gShade[0] = persistent_grid(k_shade<0>, ctx->numSMs, RB_SHADE_BLOCK);
-        gShade[1] = persistent_grid(k_shade<1>, ctx->numSMs, RB_SHADE_BLOCK);
-        gShade[2] = persistent_grid(k_shade<2>, ctx->numSMs, RB_SHADE_BLOCK);
-        gShade[3] = persistent_grid(k_shade<3>, ctx->numSMs, RB_SHADE_BLOCK);
-        gShade[4] = persistent_grid(k_shade<4>, ctx->numSMs, RB_SHADE_BLOCK);
-        gFinish = persistent_grid(k_finish, ctx->numSMs);
-    }
-
-    // lane stagger (see RB200Context::staggerWave): start behind wave `staggerWave` of the previous batch
-    if (ctx->staggerWave >= 0 && hadPrevious && other != lane && !(ctx->flags & RB200_FLAG_TIME_KERNELS))
-        RB_CUDA(cudaStreamWaitEvent(s, ctx->staggerEv[other], 0));
-    // snapshot of the cumulative device counters at batch start (device-to-device: no host synchronisation here;
-    // rb200_get_stats resolves "last batch" = cumulative - snapshot after synchronising)
-    RB_CUDA(cudaMemsetAsync(P.stats, 0, ST_COUNT * sizeof(unsigned long long), s));   // this lane's per-batch counters
-    RB_CUDA(cudaMemsetAsync(P.counters, 0, 2 * CNT_SET * sizeof(uint32_t), s));
-    uint64_t nl = 0;
     const bool timed = (ctx->flags & RB200_FLAG_TIME_KERNELS) != 0;
+    if (timed)      // timing pass: no overlap between engines
+        for (int o = 0; o < ctx->numEngines; o++) if (o != e) RB_CUDA(cudaStreamSynchronize(ctx->eng[o].stream));
+    CallTimer tm{ctx, s, timed};
     ctx->evUsed = 0; ctx->evClass.clear();
-    auto tic = [&](int cls) {
-        if (!timed) return;
-        while (ctx->evPool.size() < ctx->evUsed + 2) { cudaEvent_t e; cudaEventCreate(&e); ctx->evPool.push_back(e); }
-        ctx->evClass.push_back(cls);
-        cudaEventRecord(ctx->evPool[ctx->evUsed], s);
-    };
-    auto toc = [&]() {
-        if (!timed) return;
-        cudaEventRecord(ctx->evPool[ctx->evUsed + 1], s);
-        ctx->evUsed += 2;
-    };
-    tic(0); k_generate<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(P); toc(); nl++;
-    const uint32_t maxWaves = pc->samplesPerPixel * pc->maxBounces;
-    // developer aid: RB200_WAVE_LOG=<file> (with RB200_FLAG_TIME_KERNELS) writes one CSV row per wave — queue counters
-    // and the device time of every kernel — for the last batch rendered; it synchronises after every wave
+
+    // ---- does this call continue the sequence the engine predicted? ----
+    WaveParams key = P;
+    key.pc.sampleBatch = 0u;
+    const bool sameKey = E.keyValid && E.scene == scene && memcmp(&key, &E.key, sizeof(WaveParams)) == 0;
+    if (!sameKey) drop_graphs(E);
+    const uint32_t delta = pc->sampleBatch - E.prevBatch;        // modulo 2^32, like the seed
+    if (sameKey && E.havePrev && delta == E.stride) E.streak++;
+    else {
+        E.streak = 0;
+        E.stride = (sameKey && E.havePrev && delta != 0u && delta <= 65536u) ? delta : 1u;     // learn the stride (ranks of a sample split)
+    }
+    bool inFlightOk = sameKey && E.active > 0 && E.lane[E.head].sampleBatch == pc->sampleBatch;
+    for (int k = 1; inFlightOk && k < E.active; k++)
+        inFlightOk = E.lane[(E.head + k) % E.numLanes].sampleBatch == pc->sampleBatch + (uint32_t)k * E.stride;
+    uint64_t nl = 0;
+    if (!inFlightOk) {
+        int rc = reset_engine(E);
+        if (rc != RB200_OK) return rc;
+        if ((rc = inject_batch(ctx, E, pc->sampleBatch, tm, nl)) != RB200_OK) return rc;
+    }
+    memcpy(&E.key, &key, sizeof(WaveParams));
+    E.keyValid = true; E.scene = scene;
+
+    // Speculate from the second call of a regular sequence on; never in the counting pass (its counters are per call).
+    const bool speculate = E.numLanes > 1 && E.streak >= 1u && !(ctx->flags & RB200_FLAG_COUNT_BVH) && !getenv("RB200_NO_SPECULATION");
+    const uint32_t span = speculate ? (maxWaves + (uint32_t)E.numLanes - 1u) / (uint32_t)E.numLanes : maxWaves;
+
+    // engine stagger (one lane per engine only): start behind wave `staggerWave` of the previous batch
+    const bool stagger = ctx->numEngines > 1 && E.numLanes == 1 && ctx->staggerWave >= 0 && !timed;
+    if (stagger && prevEngine >= 0 && prevEngine != e) RB_CUDA(cudaStreamWaitEvent(s, ctx->eng[prevEngine].staggerEv, 0));
+    const uint32_t staggerWant = ctx->staggerWave > 0 ? (uint32_t)ctx->staggerWave : std::max(1u, maxWaves * 5u / 32u);
+    uint32_t staggerAt = stagger ? std::min(staggerWant, maxWaves) : 0u;
+
+    // developer aid: RB200_WAVE_LOG=<file> (with RB200_FLAG_TIME_KERNELS) writes one CSV row per wave of the last call —
+    // queue counters and the device time of every kernel; it synchronises after every wave
     const char* waveLogPath = timed ? getenv("RB200_WAVE_LOG") : nullptr;
     std::vector<uint32_t> waveCounters;
-    const bool nee = (ctx->flags & RB200_FLAG_NEE) != 0;
     if (timed) {
         if (ctx->waveCountsCap < maxWaves) {
             if (ctx->waveCountsDev) cudaFree(ctx->waveCountsDev);
             ctx->waveCountsDev = nullptr; ctx->waveCountsCap = 0;
-            RB_CUDA(cudaMalloc(&ctx->waveCountsDev, (size_t)maxWaves * 2 * sizeof(uint32_t)));
+            RB_CUDA(cudaMalloc(&ctx->waveCountsDev, (size_t)maxWaves * CNT_SET * sizeof(uint32_t)));
             ctx->waveCountsCap = maxWaves;
         }
-        ctx->waveCountsWaves = maxWaves;
     }
-    const uint32_t staggerWant = ctx->staggerWave < 0 ? 0u : ctx->staggerWave > 0 ? (uint32_t)ctx->staggerWave : std::max(1u, maxWaves * 5u / 32u);
-    const uint32_t staggerAt = timed ? 0u : std::min(staggerWant, maxWaves);
-    bool capturing = false;
-    const uint32_t mats = P.S.materialMask & 15u;
-    auto launch_waves_on = [&](WaveParams& P, cudaStream_t s, int lane) -> int {
-        for (uint32_t w = 0; w < maxWaves; w++) {
-            const int p = (int)(w & 1u);
-            RB_CUDA(cudaMemsetAsync(P.counters + (p ^ 1) * CNT_SET, 0, CNT_SET * sizeof(uint32_t), s));
-            tic(1);
-            if (count) k_extend<true><<<gExtendC, RB_TRAV_BLOCK, SMEM_EXTEND, s>>>(P, p); else k_extend<false><<<gExtend, RB_TRAV_BLOCK, SMEM_EXTEND, s>>>(P, p);
-            toc();
-            tic(6); k_shade<4><<<gShade[4], RB_SHADE_BLOCK, 0, s>>>(P, p); toc();
-            // a material no instance uses has an empty queue in every wave: its kernel is not launched
-            if (mats & 1u) { tic(2); k_shade<0><<<gShade[0], RB_SHADE_BLOCK, 0, s>>>(P, p); toc(); }
-            if (mats & 2u) { tic(3); k_shade<1><<<gShade[1], RB_SHADE_BLOCK, 0, s>>>(P, p); toc(); }
-            if (mats & 4u) { tic(4); k_shade<2><<<gShade[2], RB_SHADE_BLOCK, 0, s>>>(P, p); toc(); }
-            if (mats & 8u) { tic(5); k_shade<3><<<gShade[3], RB_SHADE_BLOCK, 0, s>>>(P, p); toc(); }
-            if (nee) {
-                tic(7);
-                if (count) k_shadow<true><<<gShadowC, RB_TRAV_BLOCK, SMEM_SHADOW, s>>>(P, p); else k_shadow<false><<<gShadow, RB_TRAV_BLOCK, SMEM_SHADOW, s>>>(P, p);
-                toc();
-            }
-            tic(8); k_finish<<<gFinish, BLOCK, 0, s>>>(P, p); toc();
-            if (timed && ctx->waveCountsDev) {      // CNT_RAYS / CNT_SHADOW of this wave, device to device: no host wait
-                RB_CUDA(cudaMemcpyAsync(ctx->waveCountsDev + 2 * w, P.counters + p * CNT_SET + CNT_RAYS, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-                RB_CUDA(cudaMemcpyAsync(ctx->waveCountsDev + 2 * w + 1, P.counters + p * CNT_SET + CNT_SHADOW, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-            }
-            if (staggerAt && w + 1 == staggerAt)
-                RB_CUDA(cudaEventRecordWithFlags(ctx->staggerEv[lane], s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
-            if (waveLogPath) {
-                waveCounters.resize((size_t)(w + 1) * CNT_SET);
-                RB_CUDA(cudaMemcpyAsync(&waveCounters[(size_t)w * CNT_SET], P.counters + p * CNT_SET, CNT_SET * sizeof(uint32_t),
-                                        cudaMemcpyDeviceToHost, s));
-                RB_CUDA(cudaStreamSynchronize(s));
+
+    uint32_t issued = 0;
+    while (E.lane[E.head].wavesDone < maxWaves) {
+        if (speculate && E.active < E.numLanes) {
+            const LaneState& newest = E.lane[(E.head + E.active - 1) % E.numLanes];
+            if (newest.wavesDone >= span) {
+                const int rc = inject_batch(ctx, E, newest.sampleBatch + E.stride, tm, nl);
+                if (rc != RB200_OK) return rc;
             }
         }
-        return RB200_OK;
-    };
-    auto launch_waves = [&]() -> int { return launch_waves_on(P, s, lane); };
-    nl += (uint64_t)maxWaves * ((nee ? 4u : 3u) + (uint32_t)__builtin_popcount(mats));
-    static const bool graphsOff = getenv("RB200_NO_GRAPH") != nullptr;
-    if (timed || count || graphsOff) {
-        const int rc = launch_waves();
+        const uint32_t n = std::min(span, maxWaves - E.lane[E.head].wavesDone);
+        const uint32_t st = (staggerAt > issued && staggerAt <= issued + n) ? staggerAt - issued : 0u;
+        const int rc = run_waves(ctx, E, n, st, tm, issued, waveLogPath ? &waveCounters : nullptr);
         if (rc != RB200_OK) return rc;
-    } else {
-        // the wave loop as one graph launch: ~1150 stream operations per batch become one, and the device-side gap
-        // between the dependent kernels of a thin wave shrinks
-        // (Re)capture when the arguments changed. Every lane is captured at once — the other lanes' graphs differ only in
-        // their buffers — so the cost (a few ms per lane) falls on one call instead of on the first call of each lane.
-        const uint32_t wavesKey = maxWaves | (staggerAt << 16);
-        {
-            WaveParams key = P;
-            key.pc.sampleBatch = 0u;
-            if (!ctx->waveGraph[lane] || ctx->waveGraphWaves[lane] != wavesKey || memcmp(&key, &ctx->waveGraphKey[lane], sizeof(WaveParams)) != 0) {
-                const int laneNow = lane;
-                for (int l = 0; l < RB_LANES; l++) {
-                    WaveParams& PL = ctx->lanes[l];
-                    PL.S = P.S; PL.pc = P.pc;
-                    WaveParams k2 = PL;
-                    k2.pc.sampleBatch = 0u;
-                    if (ctx->waveGraph[l] && ctx->waveGraphWaves[l] == wavesKey && memcmp(&k2, &ctx->waveGraphKey[l], sizeof(WaveParams)) == 0) continue;
-                    if (ctx->waveGraph[l]) { cudaGraphExecDestroy(ctx->waveGraph[l]); ctx->waveGraph[l] = nullptr; }
-                    cudaGraph_t g = nullptr;
-                    cudaStream_t sl = ctx->laneStream[l];
-                    RB_CUDA(cudaStreamBeginCapture(sl, cudaStreamCaptureModeThreadLocal));
-                    capturing = true;
-                    const int rc = launch_waves_on(PL, sl, l);
-                    capturing = false;
-                    const cudaError_t ce = cudaStreamEndCapture(sl, &g);
-                    if (rc != RB200_OK || ce != cudaSuccess || !g) {
-                        cudaGetLastError();
-                        if (g) cudaGraphDestroy(g);
-                        set_error("CUDA graph capture of the wave loop failed: %s", cudaGetErrorString(ce));
-                        return RB200_ERR_CUDA;
-                    }
-                    const cudaError_t ie = cudaGraphInstantiate(&ctx->waveGraph[l], g, 0);
-                    cudaGraphDestroy(g);
-                    if (ie != cudaSuccess) { cudaGetLastError(); ctx->waveGraph[l] = nullptr; set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ie)); return RB200_ERR_CUDA; }
-                    memcpy(&ctx->waveGraphKey[l], &k2, sizeof(WaveParams));
-                    ctx->waveGraphWaves[l] = wavesKey;
-                    ctx->graphCaptures++;
-                }
-                (void)laneNow;
-            }
-        }
-        RB_CUDA(cudaGraphLaunch(ctx->waveGraph[lane], s));
+        issued += n;
+        for (int k = 0; k < E.active; k++) E.lane[(E.head + k) % E.numLanes].wavesDone += n;
     }
+    nl += (uint64_t)issued * kernels_per_wave(ctx, E);
+    if (timed) ctx->waveCountsWaves = std::min(issued, ctx->waveCountsCap);
+
     if (waveLogPath) {
         if (FILE* f = fopen(waveLogPath, "w")) {
             fprintf(f, "wave,rays,lambertian,metal,dielectric,disney,miss,shadow,end,extend_us,miss_us,lambertian_us,metal_us,dielectric_us,disney_us,shadow_us,finish_us\n");
-            size_t e = 2;      // event pair 0 is k_generate
-            for (uint32_t w = 0; w < maxWaves; w++) {
+            size_t ev = 0;
+            while (ev < ctx->evClass.size() && ctx->evClass[ev] == 0) ev++;      // k_generate pairs come first
+            for (uint32_t w = 0; w < issued && (size_t)(w + 1) * CNT_SET <= waveCounters.size(); w++) {
                 const uint32_t* c = &waveCounters[(size_t)w * CNT_SET];
                 fprintf(f, "%u,%u,%u,%u,%u,%u,%u,%u,%u", w, c[CNT_RAYS], c[CNT_MAT0], c[CNT_MAT0 + 1], c[CNT_MAT0 + 2], c[CNT_MAT0 + 3],
                         c[CNT_MISS], c[CNT_SHADOW], c[CNT_END]);
                 // event classes: 1 extend, 6 miss, 2..5 materials, 7 shadow, 8 finish; columns in that order
                 float us[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-                for (;;) {
-                    const int cls = ctx->evClass[e / 2];
+                while (ev < ctx->evClass.size()) {
+                    const int cls = ctx->evClass[ev];
                     float ms = 0.f;
-                    cudaEventElapsedTime(&ms, ctx->evPool[e], ctx->evPool[e + 1]);
+                    cudaEventElapsedTime(&ms, ctx->evPool[2 * ev], ctx->evPool[2 * ev + 1]);
+                    ev++;
+                    if (cls == 0) continue;       // a speculative batch was started between two waves
                     us[cls] = ms * 1000.f;
-                    e += 2;
                     if (cls == 8) break;
                 }
                 fprintf(f, ",%.1f,%.1f,%.1f,%.1f,%.1f,%.1f,%.1f,%.1f\n", us[1], us[6], us[2], us[3], us[4], us[5], us[7], us[8]);
@@ -821,18 +932,24 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
             fclose(f);
         }
     }
-    // fold this batch's pixel means into the shared image: after the previous batch's fold and after whatever the
-    // caller had queued on the front-end stream; then let the front-end stream see the result
-    if (hadPrevious && other != lane) RB_CUDA(cudaStreamWaitEvent(s, ctx->accumDone[other], 0));
+
+    // fold the head batch's pixel means into the shared image: after the previous call's fold (another engine's stream)
+    // and after whatever the caller had queued on the front-end stream; then let the front-end stream see the result
+    const int hl = E.head;
+    if (prevEngine >= 0 && prevEngine != e) RB_CUDA(cudaStreamWaitEvent(s, ctx->eng[prevEngine].accumDone, 0));
     RB_CUDA(cudaStreamWaitEvent(s, ctx->frontMark, 0));
-    k_accumulate<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(P.image, P.mean.p, P.N, pc->sampleBatch, ctx->flags, P.stats,
-                                                             ctx->statsSnap); nl++;
-    RB_CUDA(cudaEventRecord(ctx->accumDone[lane], s));
-    RB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->accumDone[lane], 0));
+    k_accumulate<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(P.image, P.mean.p + (size_t)hl * P.N, P.N, pc->sampleBatch, ctx->flags,
+                                                             P.stats + (size_t)hl * ST_COUNT, ctx->statsSnap, ctx->statsLast); nl++;
+    RB_CUDA(cudaEventRecord(E.accumDone, s));
+    RB_CUDA(cudaStreamWaitEvent(ctx->stream, E.accumDone, 0));
     RB_CUDA(cudaGetLastError());
-    ctx->last.waves = maxWaves;
+    E.lane[hl] = LaneState();
+    E.head = (E.head + 1) % E.numLanes;
+    E.active--;
+    E.havePrev = true; E.prevBatch = pc->sampleBatch;
+    ctx->last.waves = issued;
     ctx->last.kernelLaunches = nl;
-    ctx->cumulative.waves += maxWaves;
+    ctx->cumulative.waves += issued;
     ctx->launches += nl;
     return RB200_OK;
 }
@@ -887,53 +1004,159 @@ __global__ void __launch_bounds__(BLOCK) k_trace_query(const WideNode* nodes, co
         nv, tt, ws[threadIdx.x >> 5]);
 }
 
-static int run_query(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float4* dO, const float4* dD, int any,
-                     RB200PrimaryHit* out) {
-    RB200PrimaryHit* dOut;
-    for (int lane = 0; lane < RB_LANES; lane++) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[lane]));   // lane 0's arrays are the scratch
-    uint32_t* dCursor;
-    RB_CUDA(cudaMalloc(&dOut, (size_t)n * sizeof(RB200PrimaryHit)));
-    RB_CUDA(cudaMalloc(&dCursor, sizeof(uint32_t)));
-    RB_CUDA(cudaMemsetAsync(dCursor, 0, sizeof(uint32_t), ctx->stream));
-    const int grid = (int)std::min<uint64_t>((n + BLOCK - 1) / BLOCK, (uint64_t)ctx->numSMs * 8);
+static int sync_engines(RB200Context* ctx) {
+    for (int e = 0; e < ctx->numEngines; e++) RB_CUDA(cudaStreamSynchronize(ctx->eng[e].stream));
+    return RB200_OK;
+}
+
+struct DeviceBuf {          // frees on every return path
+    void* p = nullptr;
+    ~DeviceBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+
+static int launch_query(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float4* dO, const float4* dD, int any,
+                        RB200PrimaryHit* dOut) {
+    RB_CUDA(cudaMemsetAsync(ctx->queryCursor, 0, sizeof(uint32_t), ctx->stream));
+    const int grid = (int)std::min<uint64_t>((n + BLOCK - 1) / BLOCK, (uint64_t)ctx->gQuery[any ? 1 : 0]);
     constexpr size_t smAny = sizeof(WarpShared<true>) * (BLOCK / 32), smClosest = sizeof(WarpShared<false>) * (BLOCK / 32);
-    RB_CUDA(cudaFuncSetAttribute(k_trace_query<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smAny));
-    RB_CUDA(cudaFuncSetAttribute(k_trace_query<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smClosest));
-    if (any) k_trace_query<true><<<grid, BLOCK, smAny, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut, dCursor);
-    else k_trace_query<false><<<grid, BLOCK, smClosest, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut, dCursor);
+    if (any) k_trace_query<true><<<grid, BLOCK, smAny, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut, ctx->queryCursor);
+    else k_trace_query<false><<<grid, BLOCK, smClosest, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut, ctx->queryCursor);
     ctx->launches++;
     RB_CUDA(cudaGetLastError());
-    RB_CUDA(cudaMemcpyAsync(out, dOut, (size_t)n * sizeof(RB200PrimaryHit), cudaMemcpyDeviceToHost, ctx->stream));
+    return RB200_OK;
+}
+
+static int run_query(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float4* dO, const float4* dD, int any,
+                     RB200PrimaryHit* out) {
+    DeviceBuf dOut;
+    RB_CUDA(dOut.alloc((size_t)n * sizeof(RB200PrimaryHit)));
+    const int rc = launch_query(ctx, scene, n, dO, dD, any, static_cast<RB200PrimaryHit*>(dOut.p));
+    if (rc != RB200_OK) return rc;
+    RB_CUDA(cudaMemcpyAsync(out, dOut.p, (size_t)n * sizeof(RB200PrimaryHit), cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(dOut); cudaFree(dCursor);
     return RB200_OK;
 }
 
 int trace_primary(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc, RB200PrimaryHit* out) {
-    WaveParams& P = ctx->wp;
-    for (int lane = 0; lane < RB_LANES; lane++) RB_CUDA(cudaStreamSynchronize(ctx->laneStream[lane]));
+    const int src = sync_engines(ctx);
+    if (src != RB200_OK) return src;
+    // engine 0's shadow-record arrays are the scratch for the camera rays: between two calls no wave is running and the
+    // records of a wave do not outlive it
+    WaveParams P = ctx->wp;
     P.S = scene->dev; P.pc = *pc;
     k_primary_rays<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, ctx->stream>>>(P, P.shO.p, P.shD.p);
     ctx->launches++;
     return run_query(ctx, scene, P.N, P.shO.p, P.shD.p, 0, out);
 }
 
-int trace_rays(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* o, const float* d, const float* tmax,
-               int any, RB200PrimaryHit* out) {
-    if (n == 0) return RB200_OK;
+static int upload_rays(RB200Context* ctx, uint32_t n, const float* o, const float* d, const float* tmax, DeviceBuf& dO, DeviceBuf& dD) {
     std::vector<float4> ho(n), hd(n);
     for (uint32_t i = 0; i < n; i++) {
         ho[i] = make_float4(o[3 * i], o[3 * i + 1], o[3 * i + 2], tmax[i]);
         hd[i] = make_float4(d[3 * i], d[3 * i + 1], d[3 * i + 2], 0.f);
     }
-    float4 *dO, *dD;
-    RB_CUDA(cudaMalloc(&dO, (size_t)n * sizeof(float4)));
-    RB_CUDA(cudaMalloc(&dD, (size_t)n * sizeof(float4)));
-    RB_CUDA(cudaMemcpyAsync(dO, ho.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    RB_CUDA(cudaMemcpyAsync(dD, hd.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = run_query(ctx, scene, n, dO, dD, any, out);
-    cudaFree(dO); cudaFree(dD);
-    return rc;
+    RB_CUDA(dO.alloc((size_t)n * sizeof(float4)));
+    RB_CUDA(dD.alloc((size_t)n * sizeof(float4)));
+    RB_CUDA(cudaMemcpyAsync(dO.p, ho.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(cudaMemcpyAsync(dD.p, hd.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(cudaStreamSynchronize(ctx->stream));       // the staging vectors go out of scope
+    return RB200_OK;
+}
+
+int trace_rays(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* o, const float* d, const float* tmax,
+               int any, RB200PrimaryHit* out) {
+    if (n == 0) return RB200_OK;
+    DeviceBuf dO, dD;
+    const int rc = upload_rays(ctx, n, o, d, tmax, dO, dD);
+    if (rc != RB200_OK) return rc;
+    return run_query(ctx, scene, n, static_cast<float4*>(dO.p), static_cast<float4*>(dD.p), any, out);
+}
+
+// Measurement entry point (tools/trav_bench.py): the traversal kernel alone on a caller-supplied ray set, `reps` timed
+// launches (CUDA events on the launching stream) after one warm-up; the hits of the last launch are reduced to a checksum
+// so that kernel variants can be compared for equal results.
+__global__ void k_hit_checksum(const RB200PrimaryHit* __restrict__ hits, uint32_t n, unsigned long long* out) {
+    unsigned long long h = 0ull;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const RB200PrimaryHit r = hits[i];
+        unsigned long long v = ((unsigned long long)__float_as_uint(r.t) << 32) ^ ((unsigned long long)r.primitive * 0x9E3779B97F4A7C15ull)
+                               ^ ((unsigned long long)r.instance << 17) ^ __float_as_uint(r.u) ^ ((unsigned long long)__float_as_uint(r.v) << 13);
+        v ^= (unsigned long long)i * 0xD6E8FEB86659FD93ull;
+        v ^= v >> 29; v *= 0xBF58476D1CE4E5B9ull; v ^= v >> 32;
+        h += v;
+    }
+    atomicAdd(out, h);
+}
+
+int bench_trace(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* o, const float* d, const float* tmax, int any,
+                uint32_t reps, float* outMs, uint64_t* outChecksum) {
+    if (n == 0 || reps == 0) { set_error("bench_trace: n and reps must be > 0"); return RB200_ERR_INVALID_ARGUMENT; }
+    int rc = sync_engines(ctx);
+    if (rc != RB200_OK) return rc;
+    DeviceBuf dO, dD, dOut, dSum;
+    if ((rc = upload_rays(ctx, n, o, d, tmax, dO, dD)) != RB200_OK) return rc;
+    RB_CUDA(dOut.alloc((size_t)n * sizeof(RB200PrimaryHit)));
+    RB_CUDA(dSum.alloc(sizeof(unsigned long long)));
+    RB_CUDA(cudaMemsetAsync(dSum.p, 0, sizeof(unsigned long long), ctx->stream));
+    cudaEvent_t e0, e1;
+    RB_CUDA(cudaEventCreate(&e0)); RB_CUDA(cudaEventCreate(&e1));
+    rc = launch_query(ctx, scene, n, static_cast<float4*>(dO.p), static_cast<float4*>(dD.p), any, static_cast<RB200PrimaryHit*>(dOut.p));
+    cudaEventRecord(e0, ctx->stream);
+    for (uint32_t r = 0; r < reps && rc == RB200_OK; r++)
+        rc = launch_query(ctx, scene, n, static_cast<float4*>(dO.p), static_cast<float4*>(dD.p), any, static_cast<RB200PrimaryHit*>(dOut.p));
+    cudaEventRecord(e1, ctx->stream);
+    if (rc == RB200_OK) {
+        k_hit_checksum<<<256, 256, 0, ctx->stream>>>(static_cast<const RB200PrimaryHit*>(dOut.p), n, static_cast<unsigned long long*>(dSum.p));
+        ctx->launches++;
+    }
+    unsigned long long sum = 0ull;
+    cudaError_t ce = cudaMemcpyAsync(&sum, dSum.p, sizeof(sum), cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    float ms = 0.f;
+    if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc != RB200_OK) return rc;
+    if (ce != cudaSuccess) { set_error("bench_trace: %s", cudaGetErrorString(ce)); return RB200_ERR_CUDA; }
+    if (outMs) *outMs = ms / (float)reps;
+    if (outChecksum) *outChecksum = sum;
+    return RB200_OK;
+}
+
+// Per context, i.e. per DEVICE (function attributes and occupancy are per device): shared-memory limits of the traversal
+// kernels, persistent-grid sizes, and the kernels' code loaded before the first frame (a first launch loads its code only
+// once the device is idle, which with several batches in flight stalled the first presented frame by 170 ms).
+template <class K> static int persistent_grid(K kernel, int numSMs, int block = BLOCK, size_t dynSmem = 0) {
+    int perSM = 0;
+    if (dynSmem) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem);
+#ifdef RB_SMEM_CARVEOUT
+    if (dynSmem) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, RB_SMEM_CARVEOUT);
+#endif
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, block, dynSmem) != cudaSuccess || perSM < 1) perSM = 1;
+    return numSMs * perSM;
+}
+
+int configure_wave_kernels(RB200Context* ctx) {
+    constexpr size_t smAny = sizeof(WarpShared<true>) * (BLOCK / 32), smClosest = sizeof(WarpShared<false>) * (BLOCK / 32);
+    ctx->gExtend = persistent_grid(k_extend<false>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_EXTEND);
+    ctx->gExtendC = persistent_grid(k_extend<true>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_EXTEND);
+    ctx->gShadow = persistent_grid(k_shadow<false>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_SHADOW);
+    ctx->gShadowC = persistent_grid(k_shadow<true>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_SHADOW);
+    ctx->gShade[0] = persistent_grid(k_shade<0>, ctx->numSMs, RB_SHADE_BLOCK);
+    ctx->gShade[1] = persistent_grid(k_shade<1>, ctx->numSMs, RB_SHADE_BLOCK);
+    ctx->gShade[2] = persistent_grid(k_shade<2>, ctx->numSMs, RB_SHADE_BLOCK);
+    ctx->gShade[3] = persistent_grid(k_shade<3>, ctx->numSMs, RB_SHADE_BLOCK);
+    ctx->gShade[4] = persistent_grid(k_shade<4>, ctx->numSMs, RB_SHADE_BLOCK);
+    ctx->gFinish = persistent_grid(k_finish, ctx->numSMs);
+    ctx->gQuery[0] = persistent_grid(k_trace_query<false>, ctx->numSMs, BLOCK, smClosest);
+    ctx->gQuery[1] = persistent_grid(k_trace_query<true>, ctx->numSMs, BLOCK, smAny);
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_generate);
+    cudaFuncGetAttributes(&a, k_accumulate);
+    cudaFuncGetAttributes(&a, k_resolve_sum);
+    cudaFuncGetAttributes(&a, k_primary_rays);
+    RB_CUDA(cudaGetLastError());
+    return RB200_OK;
 }
 
 } // namespace rb200

@@ -484,6 +484,36 @@ def test_camera_and_sampling_changes_between_batches(ol, rb):
     r.close()
 
 
+@pytest.mark.parametrize("engines,lanes", [(1, 1), (1, 4), (2, 3), (4, 1), (1, 8)])
+def test_engines_lanes_and_speculation_do_not_change_the_result(ol, rb, monkeypatch, engines, lanes):
+    """The context traces the next batches of a regular sequence speculatively, mixed into the launches of the batch
+    asked for (context.cuh). Whatever the organisation — one wave loop per batch as in round 1 (4 x 1), one engine with
+    4 or 8 lanes, two engines with 3 — after every call the image is bit-identical to the oracle's and the counters of
+    the batch folded last are the oracle's, over a regular sequence (speculation starts), a jump (speculative batches
+    discarded), a strided sequence as a sample split over 3 ranks issues it (stride learned), a repeated batch, and a
+    sequence that wraps the 32-bit batch index."""
+    monkeypatch.setenv("RB200_ENGINES", str(engines))
+    monkeypatch.setenv("RB200_LANES", str(lanes))
+    wl = rb.configs.small_mixed(96, 72, nee=True, samples_per_pixel=2, max_bounces=6)
+    r = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE)
+    assert r.engine_config()[:2] == (engines, lanes)
+    sc = ol.OracleScene(wl.tables)
+    seq = list(range(0, 7)) + [20] + [23, 26, 29, 32, 35] + [35] + [2 ** 32 - 2, 2 ** 32 - 1, 0, 1, 2]
+    hdr_o = np.zeros((wl.height, wl.width, 4), np.float32)
+    for i, b in enumerate(seq):
+        pc = wl.push_constants(b)
+        r.render_batch(pc)
+        hdr_o, cnt = sc.render_batch(wl.width, wl.height, rb.RB200_FLAG_NEE, pc, hdr_o)
+        if i % 3 == 2 or i == len(seq) - 1:       # reading drains the device: not after every call
+            last, _ = r.stats()
+            assert (last["extendRays"], last["shadowRays"], last["paths"]) == (cnt["extendRays"], cnt["shadowRays"], cnt["paths"]), (i, b)
+            assert (bits(r.read_hdr()) == bits(hdr_o)).all(), (i, b)
+    _, _, discarded = r.engine_config()
+    assert (discarded > 0) == (lanes > 1)
+    r.close()
+    sc.close()
+
+
 @pytest.mark.parametrize("count,tile", [(2, 32), (3, 16), (8, 32)])
 def test_interleaved_tiles_add_up_to_the_single_gpu_image_bit_for_bit(ol, rb, count, tile):
     """SURVEY 8e, latency mode: rank r of N traces the tiles whose row-major index is congruent to r (every batch of
