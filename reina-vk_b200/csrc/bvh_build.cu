@@ -61,7 +61,7 @@ __global__ void k_flatten(const float4* __restrict__ verts, const uint32_t* __re
         }
         TriRecord t;
         t.v0 = make_float4(w[0].x, w[0].y, w[0].z, __uint_as_float(p));
-        t.v1 = make_float4(w[1].x, w[1].y, w[1].z, __uint_as_float(a));
+        t.v1 = make_float4(w[1].x, w[1].y, w[1].z, __uint_as_float(a | ((in.materialIdx > 3u ? 3u : in.materialIdx) << 30)));
         t.v2 = make_float4(w[2].x, w[2].y, w[2].z, __uint_as_float(g));
         out[g] = t;
     }
@@ -746,6 +746,7 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
     const uint32_t N = prefix.back();
     if (N == 0) { set_error("scene has no triangles"); return RB200_ERR_INVALID_ARGUMENT; }
     if (N >= 0x08000000u) { set_error("too many triangles (limit 2^27: the traversal packs triangle index and lane into 32 bits)"); return RB200_ERR_INVALID_ARGUMENT; }
+    if (hi.size() > (size_t)TRI_INST_MASK) { set_error("too many instances (limit 2^30)"); return RB200_ERR_INVALID_ARGUMENT; }
 
     Arena arena;
     arena.cap = (size_t)N * 704 + prefix.size() * 4 + (1u << 20);

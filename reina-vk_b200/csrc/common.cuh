@@ -40,7 +40,9 @@ struct alignas(16) WideNode {
 static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
 
 // triangle record in leaf order: three float4, w lanes carry ids
-//   v0.w = primitive id within the model, v1.w = instance index, v2.w = global primitive id (tie-break key)
+//   v0.w = primitive id within the model, v1.w = instance index | material kernel (0..3) << 30, v2.w = global primitive
+//   id (tie-break key). The material bits let k_extend bin a finished ray without touching the instance table.
+static constexpr uint32_t TRI_INST_MASK = 0x3FFFFFFFu;
 struct alignas(16) TriRecord { float4 v0, v1, v2; };
 static_assert(sizeof(TriRecord) == 48, "TriRecord must be 48 bytes");
 

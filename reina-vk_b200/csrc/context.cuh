@@ -115,18 +115,22 @@ struct WaveParams {
 // lanes and starts over; speculation begins with the second call of a regular sequence, so isolated calls pay nothing.
 // A context owns E engines on E streams (calls rotate through them) so that kernels of different classes — traversal:
 // issue / latency-bound, shading: DRAM-bound — still overlap. E = 4, L = 1 is the round-1 organisation.
+// Headline scene on B200 (Mrays/s of the device loop / end to end / fraction of the HBM roofline reached by k_extend over
+// ALL launches of a step), E x L: 4 x 1 2277 / 2253 / 0.385; 1 x 4 2286 / 2272 / 0.507; 1 x 8 2438 / 2420 / 0.555;
+// 2 x 4 2519 / 2496 / 0.515; 2 x 6 2571 / 2552 / 0.545; 2 x 8 2643 / 2605 / 0.563 (default); 3 x 4 2583 / 2540; 3 x 6
+// 2690 / 2462; 4 x 4 2593 / 2452 (profiles/r02_summary.md). Path state: 0.53 GB per lane at 1080p.
 // ---------------------------------------------------------------------------------------------------
 #ifndef RB_MAX_ENGINES
 #define RB_MAX_ENGINES 4
 #endif
 #ifndef RB_MAX_LANES
-#define RB_MAX_LANES 8
+#define RB_MAX_LANES 16
 #endif
 #ifndef RB_ENGINES
-#define RB_ENGINES 1           // default engines per context (RB200_ENGINES overrides at context creation)
+#define RB_ENGINES 2           // default engines per context (RB200_ENGINES overrides at context creation)
 #endif
 #ifndef RB_LANES
-#define RB_LANES 4             // default lanes per engine (RB200_LANES overrides)
+#define RB_LANES 8             // default lanes per engine (RB200_LANES overrides)
 #endif
 #ifndef RB_GRAPH_CHUNK
 #define RB_GRAPH_CHUNK 32      // waves per captured graph (even: a chunk preserves the queue parity)

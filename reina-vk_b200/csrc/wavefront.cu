@@ -27,6 +27,11 @@ static constexpr int BLOCK = 256;
 #ifndef RB_SHADOW_LDCS
 #define RB_SHADOW_LDCS 0
 #endif
+// RB_BIN_MATCH=1: k_extend bins the finished rays of a warp by material with one __match_any_sync instead of five
+// predicated passes.
+#ifndef RB_BIN_MATCH
+#define RB_BIN_MATCH 1
+#endif
 #ifndef RB_TRAV_MINBLOCKS
 #define RB_TRAV_MINBLOCKS (1024 / RB_TRAV_BLOCK)      // resident blocks per SM the traversal kernels are compiled for (register cap)
 #endif
@@ -200,15 +205,26 @@ __global__ void __launch_bounds__(RB_TRAV_BLOCK, RB_TRAV_MINBLOCKS) k_extend(Wav
 #else
                 const uint32_t prim = __float_as_uint(__ldg(tp).w);
 #endif
-                const uint32_t inst = __float_as_uint(__ldg(tp + 1).w);
-                P.hit[slot] = make_uint4(__float_as_uint(h.b1), __float_as_uint(h.b2), prim, inst);
-                const uint32_t m = __ldg(&P.S.instances[inst].materialIdx);
-                bin = m > 3u ? 3u : m;
+                const uint32_t iw = __float_as_uint(__ldg(tp + 1).w);      // instance | material kernel << 30: no instance-table gather
+                P.hit[slot] = make_uint4(__float_as_uint(h.b1), __float_as_uint(h.b2), prim, iw & TRI_INST_MASK);
+                bin = iw >> 30;
             }
             // bin the slot by material (warp-aggregated per bin)
+#if RB_BIN_MATCH
+            const uint32_t active = __activemask();
+            const uint32_t peers = __match_any_sync(active, bin);
+            const uint32_t lane = threadIdx.x & 31u;
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(&cnt[CNT_MAT0 + bin], (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            uint32_t* mq = bin == 0u ? P.matQ[0] : bin == 1u ? P.matQ[1] : bin == 2u ? P.matQ[2] : bin == 3u ? P.matQ[3] : P.matQ[4];
+            mq[base + __popc(peers & ((1u << lane) - 1u))] = slot;
+#else
 #pragma unroll
             for (uint32_t b = 0; b < 5; b++)
                 if (bin == b) queue_push(P.matQ[b], &cnt[CNT_MAT0 + b], slot);
+#endif
         },
         nodeVisits, triTests, ws[threadIdx.x >> 5]);
     if (COUNT) {
@@ -620,7 +636,7 @@ __global__ void k_build_shade_records(DeviceScene S, float4* __restrict__ base, 
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= S.numTris) return;
     const float4* tp = reinterpret_cast<const float4*>(S.tris + t);
-    const uint32_t prim = __float_as_uint(tp[0].w), inst = __float_as_uint(tp[1].w);
+    const uint32_t prim = __float_as_uint(tp[0].w), inst = __float_as_uint(tp[1].w) & TRI_INST_MASK;
     const RB200InstanceProperties* props = &S.props[S.instances[inst].instancePropertiesID];
     const uint32_t ib = 3u * prim + props->indicesOffset;
     const float4 v0 = S.vertices[S.indices[ib]], v1 = S.vertices[S.indices[ib + 1]], v2 = S.vertices[S.indices[ib + 2]];
@@ -997,7 +1013,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace_query(const WideNode* nodes, co
                 const float4* tp = reinterpret_cast<const float4*>(tris + h.tri);
                 r.t = h.t;
                 r.primitive = __float_as_uint(__ldg(tp).w);
-                r.instance = __float_as_uint(__ldg(tp + 1).w);
+                r.instance = __float_as_uint(__ldg(tp + 1).w) & TRI_INST_MASK;
             } else { r.t = -1.0f; r.u = r.v = 0.f; r.primitive = r.instance = 0xFFFFFFFFu; }
             out[i] = r;
         },
@@ -1129,9 +1145,10 @@ int bench_trace(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const fl
 template <class K> static int persistent_grid(K kernel, int numSMs, int block = BLOCK, size_t dynSmem = 0) {
     int perSM = 0;
     if (dynSmem) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem);
-#ifdef RB_SMEM_CARVEOUT
-    if (dynSmem) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, RB_SMEM_CARVEOUT);
-#endif
+    // RB200_SMEM_CARVEOUT=<percent>: preferred shared-memory carve-out of the traversal kernels (developer aid; the
+    // driver's default picks the smallest configuration that holds the resident blocks)
+    static const char* carve = getenv("RB200_SMEM_CARVEOUT");
+    if (dynSmem && carve) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(carve));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, block, dynSmem) != cudaSuccess || perSM < 1) perSM = 1;
     return numSMs * perSM;
 }
