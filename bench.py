@@ -198,10 +198,51 @@ def main():
     r.synchronize()
     scene_create_s = time.time() - t0
     bvh = r.bvh_info()
-    hdr_t = torch.as_tensor(r.hdr_device_array(), device=f"cuda:{local_rank}") if world > 1 else None
+    parity_check = None
+    total_batches = 0       # batches folded into the ranks' SUM images so far, over all ranks
+    if world > 1:
+        # the library's own NCCL communicator (rb200_context_comm_init -> ncclCommInitRank); torch.distributed only
+        # carries the 128-byte unique id to the other ranks and the timing / counter reductions below
+        uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(rb.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        r.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+        # every replica of the BVH must be the same structure (deterministic build)
+        hashes = [None] * world
+        dist.all_gather_object(hashes, int(bvh["hash"]))
+        assert len(set(hashes)) == 1, f"BVH hashes differ across ranks: {hashes}"
+        # parity of the multi-GPU path: 2 batches per rank, reduced by the library, against the same 2 * world batches
+        # rendered by ONE GPU (rank 0, a second context); only the fp32 summation order differs
+        with torch.cuda.stream(stream):
+            for i in range(2):
+                r.render_batch(wl.push_constants(rank + i * world))
+            total_batches += 2 * world
+            r.reduce_present(total_batches)
+            r.synchronize()
+        if rank == 0:
+            multi = torch.as_tensor(r.reduced_device_array(), device=f"cuda:{local_rank}").cpu().numpy() / float(total_batches)
+            os.environ["RB200_LANES"], os.environ["RB200_ENGINES"] = "2", "1"
+            r1 = rb.Renderer(wl.width, wl.height, wl.tables, flags=flags, device=local_rank, stream=stream.cuda_stream)
+            del os.environ["RB200_LANES"], os.environ["RB200_ENGINES"]
+            with torch.cuda.stream(stream):
+                for b in range(2 * world):
+                    r1.render_batch(wl.push_constants(b))
+                single = r1.read_hdr() / float(total_batches)
+            r1.close()
+            num = np.abs(multi[..., :3] - single[..., :3]).max()
+            den = max(1e-30, float(np.abs(single[..., :3]).max()))
+            rel = np.abs(multi[..., :3] - single[..., :3]) / np.maximum(np.abs(single[..., :3]), 1e-3)
+            parity_check = {"batches": 2 * world, "max_abs_diff": float(num), "max_abs_diff_over_max": float(num / den),
+                            "max_rel_diff": float(rel.max()), "tolerance_rel": 1e-4, "bvh_hashes_equal": True,
+                            "ok": bool(rel.max() <= 1e-4),
+                            "what": "mean image of 2 batches per rank reduced by rb200_context_reduce_present vs the same batches "
+                                    "rendered by one GPU (sum mode): identical samples, fp32 summation order differs"}
+            assert parity_check["ok"], parity_check
+        dist.barrier()
 
-    def batch_index(i):       # rank r renders batches r, r + N, r + 2N, ...
-        return rank + i * world
+    def batch_index(i):       # rank r renders batches r, r + N, r + 2N, ... (behind the two of the parity check)
+        return rank + (i + (2 if world > 1 else 0)) * world
 
     K, Wm = args.steps, args.warmup
     # The library traces the batches behind the one asked for speculatively (engines x lanes, context.cuh); its pipeline
@@ -218,12 +259,10 @@ def main():
             r.render_batch(wl.push_constants(batch_index(i)))
         for i in range(Wm):
             r.render_batch(wl.push_constants(batch_index(i)))
+        total_batches += (fill + Wm) * world
         # the warm-up also presents one frame (NCCL reduce, resolve, bloom + tonemap, read-back), result discarded
         if world > 1:
-            warm = hdr_t.clone()
-            dist.reduce(warm, dst=0, op=dist.ReduceOp.SUM)
-            if rank == 0:
-                r.present_sum(max(1, Wm) * world, warm.data_ptr())
+            r.reduce_present(total_batches)
         else:
             r.postprocess()
         if rank == 0:
@@ -240,11 +279,12 @@ def main():
         ev0.record(stream)
         for i in range(K):
             r.render_batch(wl.push_constants(batch_index(Wm + i)))
+        total_batches += K * world
         if world > 1:
-            # the one collective of the path: every rank's SUM image (a stream-ordered snapshot, so the accumulation
-            # images stay per-rank sums and later frames can be presented from them) reduced to rank 0
-            reduced = hdr_t.clone()
-            dist.reduce(reduced, dst=0, op=dist.ReduceOp.SUM)
+            # the one collective of the path, issued by the library (ncclReduce from C++): every rank's SUM image (a
+            # stream-ordered snapshot, so the accumulation images stay per-rank sums) reduced to rank 0, which resolves
+            # and post-processes the reduced copy
+            r.reduce_present(total_batches)
         ev1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -271,7 +311,6 @@ def main():
     # are drained inside the timed region.
     depth = r.pipeline_depth()
     frames = [r.pinned_frame() for _ in range(depth)]
-    snaps = [torch.empty_like(hdr_t) for _ in range(depth)] if world > 1 else None      # allocated outside the timed region
     ldr_host = frames[0]
     with torch.cuda.stream(stream):
         r.synchronize()
@@ -284,15 +323,13 @@ def main():
         for i in range(K):
             r.render_batch(wl.push_constants(batch_index(Wm + K + i)))
             if world > 1:
-                # one presented frame per step: snapshot this rank's SUM image behind batch i (stream-ordered, no host
-                # wait), reduce the snapshots to rank 0 (the one collective of the path), and let rank 0 resolve +
-                # bloom + tonemap the reduced copy (rb200_present_sum) and read the frame back asynchronously. The
-                # accumulation images are never touched, so the lanes keep running under the reduce.
-                snap = snaps[i % depth]
-                snap.copy_(hdr_t)
-                dist.reduce(snap, dst=0, op=dist.ReduceOp.SUM)
+                # one presented frame per step, all inside the library: snapshot of this rank's SUM image behind batch i
+                # (stream-ordered, no host wait), ONE ncclReduce to rank 0, which resolves + blooms + tonemaps the reduced
+                # copy and reads the frame back asynchronously. The accumulation images are never touched, so the
+                # engines keep tracing underneath.
+                total_batches += world
+                r.reduce_present(total_batches)
                 if rank == 0:
-                    r.present_sum((Wm + 2 * K + i + 1) * world, snap.data_ptr())
                     r.wait_ldr(depth - 1)
                     r.read_ldr_async(frames[i % depth])
             else:
@@ -315,8 +352,9 @@ def main():
     e2e = {"value": rays_e2e / (ms_e2e * 1e-3) / 1e6, "unit": "Mrays/s",
            "h2d_bytes_per_step": C.sizeof(rb.abi.RtPushConsts) + C.sizeof(rb.abi.BloomPushConsts) + C.sizeof(rb.abi.TonemappingPushConsts),
            "d2h_bytes_per_step": int(ldr_host.nbytes), "ms_per_step": ms_e2e / K,
-           "note": ("per step and rank: rb200_render_batch(host push constants), snapshot of the SUM image, NCCL reduce to rank 0; "
-                    "rank 0: rb200_present_sum (resolve + bloom + tonemap of the reduced copy) + RGBA8 frame to pinned host memory "
+           "note": ("per step and rank: rb200_render_batch(host push constants) + rb200_context_reduce_present (snapshot of the SUM "
+                    "image, one ncclReduce to rank 0 issued by the library; rank 0: resolve + bloom + tonemap of the reduced copy) "
+                    "+ RGBA8 frame to pinned host memory "
                     if world > 1 else
                     "per step: rb200_render_batch(host push constants) + rb200_postprocess + RGBA8 frame to pinned host memory ") +
                    "(rb200_read_ldr_async, %d frames in flight = rb200_pipeline_depth, drained inside the timed region); " % depth +
@@ -333,6 +371,8 @@ def main():
            "bvh": {k: bvh[k] for k in ("numTriangles", "numWideNodes", "maxDepth", "nodeBytes", "triangleBytes", "buildMs")},
            "scene_create_s": scene_create_s}
 
+    if parity_check is not None:
+        out["parity_check"] = parity_check
     if rank == 0 and world == 1 and not args.no_roofline:
         out["roofline"] = roofline(rb, wl, local_rank, stream)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -63,6 +63,8 @@ enum {
                                         raytrace.rgen.glsl:277-284; used when the sample batches are split over
                                         several GPUs and reduced once (see rb200_resolve_sum). */
     RB200_FLAG_COUNT_BVH = 1u << 2,  /* counting build: also count wide-node visits and triangle tests per ray */
+    RB200_FLAG_GROUP_TILES = 1u << 4, /* rb200_group_create only: latency mode — every device traces its interleaved 32 x 32
+                                       * tiles of every batch instead of every n-th batch of all pixels */
     RB200_FLAG_TIME_KERNELS = 1u << 3 /* bracket every kernel of rb200_render_batch with CUDA events (per-class device
                                         times for the roofline report; serialises nothing but adds event overhead) */
 };
@@ -265,6 +267,10 @@ RB200_API int rb200_scene_bvh_info(const RB200Scene* scene, RB200BvhInfo* out);
  * samplesPerPixel * maxBounces must not exceed 2^22. */
 RB200_API int rb200_render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushConsts* pc);
 
+/* Back-pressure for a frame loop (the reference waits for its command buffer every frame, src/Reina.cpp:327-328): block
+ * until at most `max_pending` of the rb200_render_batch calls issued so far are still unfinished. */
+RB200_API int rb200_wait_batches_pending(RB200Context* ctx, uint32_t max_pending);
+
 /* With RB200_FLAG_ACCUM_SUM: turn the accumulated sum of `numBatches` batch means into the mean image. */
 RB200_API int rb200_resolve_sum(RB200Context* ctx, uint32_t numBatches);
 
@@ -335,6 +341,52 @@ RB200_API int rb200_synchronize(RB200Context* ctx);
  * hold): GB/s of independent random reads of whole `recordBytes`-sized records (80 = wide node, 48 = triangle, 16)
  * from a table of `tableBytes` (make it the size of the BVH so that it is L2-resident the way the BVH is). */
 RB200_API int rb200_measure_gather(RB200Context* ctx, size_t tableBytes, uint32_t recordBytes, float* out_gbps);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* several GPUs (SURVEY.md 8b "Context", 8e): BVH replicated per device, one ncclReduce of the float4   */
+/* accumulation images per presented frame. NCCL is loaded at run time (libnccl.so.2).                 */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct RB200Group      RB200Group;
+typedef struct RB200GroupScene RB200GroupScene;
+
+/* One process, n devices (what `Reina` with n GPUs would create once, src/Reina.cpp:54-80): a context per device, each
+ * driven by its own host thread, ncclCommInitAll over `devices`. Sample split by default (device i renders batches
+ * i, i + n, ... into a local SUM image; RB200_FLAG_ACCUM_SUM is implied); RB200_FLAG_GROUP_TILES selects latency mode. */
+RB200_API int rb200_group_create(uint32_t width, uint32_t height, const int* devices, int numDevices, uint32_t flags,
+                                 RB200Group** out);
+RB200_API int rb200_group_destroy(RB200Group* group);
+RB200_API int rb200_group_size(const RB200Group* group);
+RB200_API int rb200_group_context(RB200Group* group, int index, RB200Context** out);       /* member context (not owned by the caller) */
+RB200_API int rb200_group_set_tile_size(RB200Group* group, uint32_t tileSize);             /* latency mode, before the first batch */
+/* Upload the tables and build the hierarchy on every device concurrently; fails if the replicas' hashes differ (the
+ * build is deterministic). */
+RB200_API int rb200_group_scene_create(RB200Group* group, const RB200SceneDesc* desc, RB200GroupScene** out);
+RB200_API int rb200_group_scene_destroy(RB200GroupScene* scene);
+RB200_API int rb200_group_scene_bvh_info(const RB200GroupScene* scene, int index, RB200BvhInfo* out);
+/* Sample split: device i renders batches firstBatch + i + k * n, k < batchesPerDevice, with *pc (sampleBatch replaced).
+ * Latency mode: every device renders its tiles of batches firstBatch .. firstBatch + batchesPerDevice - 1. Asynchronous. */
+RB200_API int rb200_group_render_batches(RB200Group* group, const RB200GroupScene* scene, const RB200RtPushConsts* pc,
+                                         uint32_t firstBatch, uint32_t batchesPerDevice);
+/* One frame: snapshot of every device's image -> ONE ncclReduce(float, 4 * W * H) to device 0 -> resolve (sum / batches
+ * rendered so far; nothing to resolve in latency mode) + bloom + tonemap on device 0. Asynchronous on the devices' streams;
+ * rendering continues underneath. Replaces applyBloom + applyTonemapping of src/Reina.cpp:472-577 for n devices. */
+RB200_API int rb200_group_present(RB200Group* group, const RB200BloomPushConsts* bloom, const RB200TonemappingPushConsts* tonemap);
+RB200_API int rb200_group_read_ldr(RB200Group* group, uint8_t* rgba8);       /* the frame of the last rb200_group_present (blocking) */
+RB200_API int rb200_group_read_hdr(RB200Group* group, float* rgba32f);       /* reduce + resolve, blocking: the mean image so far */
+RB200_API int rb200_group_synchronize(RB200Group* group);
+RB200_API int rb200_group_get_stats(RB200Group* group, RB200Stats* cumulative);   /* summed over the devices */
+
+/* One process per GPU (torchrun, MPI): rank 0 calls rb200_comm_unique_id and hands the 128 bytes to the other ranks by
+ * its own means; every rank then calls rb200_context_comm_init (ncclCommInitRank on the context's device) and, per
+ * frame, rb200_context_reduce_present: snapshot of the rank's image, ONE ncclReduce to rank 0, and on rank 0 resolve
+ * (with RB200_FLAG_ACCUM_SUM: sum / totalBatches) + bloom + tonemap of the reduced copy. bloom / tonemap are only read
+ * on rank 0. rb200_context_reduced_device_ptr: rank 0's reduced image (device memory, W*H*4 floats). */
+RB200_API int rb200_comm_unique_id(void* out_128_bytes);
+RB200_API int rb200_context_comm_init(RB200Context* ctx, const void* unique_id_128_bytes, int rank, int nranks);
+RB200_API int rb200_context_comm_destroy(RB200Context* ctx);
+RB200_API int rb200_context_reduce_present(RB200Context* ctx, uint32_t totalBatches, const RB200BloomPushConsts* bloom,
+                                           const RB200TonemappingPushConsts* tonemap);
+RB200_API int rb200_context_reduced_device_ptr(RB200Context* ctx, void** out_device_ptr);
 
 #ifdef __cplusplus
 }

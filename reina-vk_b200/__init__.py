@@ -13,11 +13,11 @@ import ctypes as C
 import numpy as np
 
 from . import abi, camera, configs, gltf, meshes, scene
-from .abi import (RB200_FLAG_ACCUM_SUM, RB200_FLAG_COUNT_BVH, RB200_FLAG_NEE, RB200_FLAG_TIME_KERNELS, BloomPushConsts, RB200Error,
-                  RtPushConsts, TonemappingPushConsts, load_library)
+from .abi import (RB200_FLAG_ACCUM_SUM, RB200_FLAG_COUNT_BVH, RB200_FLAG_GROUP_TILES, RB200_FLAG_NEE, RB200_FLAG_TIME_KERNELS,
+                  BloomPushConsts, RB200Error, RtPushConsts, TonemappingPushConsts, load_library)
 from .scene import Material, ModelData, Scene, SceneTables
 
-__all__ = ["Renderer", "Material", "ModelData", "Scene", "SceneTables", "RtPushConsts", "BloomPushConsts",
+__all__ = ["Renderer", "Group", "comm_unique_id", "RB200_FLAG_GROUP_TILES", "Material", "ModelData", "Scene", "SceneTables", "RtPushConsts", "BloomPushConsts",
            "TonemappingPushConsts", "RB200_FLAG_NEE", "RB200_FLAG_ACCUM_SUM", "RB200_FLAG_COUNT_BVH", "RB200_FLAG_TIME_KERNELS",
            "RB200Error",
            "abi", "camera", "configs", "gltf", "meshes", "scene", "load_library"]
@@ -183,7 +183,29 @@ class Renderer:
     def synchronize(self):
         abi.check(self.lib, self.lib.rb200_synchronize(self._ctx))
 
+    # -- one process per GPU: the library's own NCCL communicator (rb200_context_comm_*) -------------------
+    def comm_init(self, unique_id, rank, nranks):
+        """ncclCommInitRank on this context's device; `unique_id` = the 128 bytes of comm_unique_id() from rank 0."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        abi.check(self.lib, self.lib.rb200_context_comm_init(self._ctx, C.cast(buf, C.c_void_p), rank, nranks))
+        self._has_comm = True
+
+    def reduce_present(self, total_batches, bloom=None, tonemap=None):
+        """Snapshot of this rank's image -> one ncclReduce to rank 0 -> (rank 0) resolve + bloom + tonemap."""
+        d = camera.DEFAULTS
+        bloom = bloom or BloomPushConsts(d["bloom_radius"], d["bloom_threshold"], d["bloom_intensity"])
+        tonemap = tonemap or TonemappingPushConsts(d["exposure"])
+        abi.check(self.lib, self.lib.rb200_context_reduce_present(self._ctx, total_batches, C.byref(bloom), C.byref(tonemap)))
+
+    def reduced_device_array(self):
+        p = C.c_void_p()
+        abi.check(self.lib, self.lib.rb200_context_reduced_device_ptr(self._ctx, C.byref(p)))
+        return _DevicePtr(p.value, (self.height, self.width, 4))
+
     def close(self):
+        if getattr(self, "_has_comm", False) and getattr(self, "_ctx", None):
+            self.lib.rb200_context_comm_destroy(self._ctx)
+            self._has_comm = False
         if getattr(self, "_scene", None):
             self.lib.rb200_scene_destroy(self._scene)
             self._scene = None
@@ -193,6 +215,86 @@ class Renderer:
         for p in getattr(self, "_pinned", []):
             self.lib.rb200_host_free(p)
         self._pinned = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def comm_unique_id():
+    """128 bytes from ncclGetUniqueId (rank 0 creates them and hands them to the other ranks)."""
+    lib = load_library()
+    buf = (C.c_char * 128)()
+    abi.check(lib, lib.rb200_comm_unique_id(C.cast(buf, C.c_void_p)))
+    return bytes(buf)
+
+
+class Group:
+    """Several GPUs in one process (rb200_group_*): a context and a host thread per device, the BVH replicated, one
+    ncclReduce of the accumulation images per presented frame. Sample split by default, interleaved tiles with
+    tiles=True."""
+
+    def __init__(self, width, height, tables, devices, flags=0, tiles=False):
+        self.lib = load_library()
+        self.width, self.height = width, height
+        devs = (C.c_int * len(devices))(*devices)
+        self._g = C.c_void_p()
+        abi.check(self.lib, self.lib.rb200_group_create(width, height, devs, len(devices),
+                                                        flags | (RB200_FLAG_GROUP_TILES if tiles else 0), C.byref(self._g)))
+        self._scene = C.c_void_p()
+        self.tables = tables
+        desc = tables.desc()
+        try:
+            abi.check(self.lib, self.lib.rb200_group_scene_create(self._g, C.byref(desc), C.byref(self._scene)))
+        except Exception:
+            self.lib.rb200_group_destroy(self._g)
+            self._g = None
+            raise
+
+    def size(self):
+        return int(self.lib.rb200_group_size(self._g))
+
+    def render_batches(self, pc, first_batch, batches_per_device):
+        abi.check(self.lib, self.lib.rb200_group_render_batches(self._g, self._scene, C.byref(pc), first_batch, batches_per_device))
+
+    def present(self, bloom=None, tonemap=None):
+        d = camera.DEFAULTS
+        bloom = bloom or BloomPushConsts(d["bloom_radius"], d["bloom_threshold"], d["bloom_intensity"])
+        tonemap = tonemap or TonemappingPushConsts(d["exposure"])
+        abi.check(self.lib, self.lib.rb200_group_present(self._g, C.byref(bloom), C.byref(tonemap)))
+
+    def read_ldr(self):
+        out = np.empty((self.height, self.width, 4), np.uint8)
+        abi.check(self.lib, self.lib.rb200_group_read_ldr(self._g, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def read_hdr(self):
+        out = np.empty((self.height, self.width, 4), np.float32)
+        abi.check(self.lib, self.lib.rb200_group_read_hdr(self._g, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def bvh_info(self, index=0):
+        info = abi.BvhInfo()
+        abi.check(self.lib, self.lib.rb200_group_scene_bvh_info(self._scene, index, C.byref(info)))
+        return info.as_dict()
+
+    def stats(self):
+        cum = abi.Stats()
+        abi.check(self.lib, self.lib.rb200_group_get_stats(self._g, C.byref(cum)))
+        return cum.as_dict()
+
+    def synchronize(self):
+        abi.check(self.lib, self.lib.rb200_group_synchronize(self._g))
+
+    def close(self):
+        if getattr(self, "_scene", None):
+            self.lib.rb200_group_scene_destroy(self._scene)
+            self._scene = None
+        if getattr(self, "_g", None):
+            self.lib.rb200_group_destroy(self._g)
+            self._g = None
 
     def __del__(self):
         try:

@@ -16,6 +16,7 @@ RB200_FLAG_NEE = 1 << 0
 RB200_FLAG_ACCUM_SUM = 1 << 1
 RB200_FLAG_COUNT_BVH = 1 << 2
 RB200_FLAG_TIME_KERNELS = 1 << 3
+RB200_FLAG_GROUP_TILES = 1 << 4
 
 
 class InstanceProperties(C.Structure):
@@ -152,6 +153,7 @@ SYMBOLS = {
     "rb200_scene_bvh_info": (C.c_int, [C.c_void_p, C.POINTER(BvhInfo)]),
     "rb200_render_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RtPushConsts)]),
     "rb200_resolve_sum": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "rb200_wait_batches_pending": (C.c_int, [C.c_void_p, C.c_uint32]),
     "rb200_postprocess": (C.c_int, [C.c_void_p, C.POINTER(BloomPushConsts), C.POINTER(TonemappingPushConsts)]),
     "rb200_read_ldr": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rb200_read_hdr": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -175,6 +177,26 @@ SYMBOLS = {
     "rb200_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats), C.POINTER(Stats)]),
     "rb200_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(KernelTimes)]),
     "rb200_synchronize": (C.c_int, [C.c_void_p]),
+    # several GPUs
+    "rb200_group_create": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_int), C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "rb200_group_destroy": (C.c_int, [C.c_void_p]),
+    "rb200_group_size": (C.c_int, [C.c_void_p]),
+    "rb200_group_context": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "rb200_group_set_tile_size": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "rb200_group_scene_create": (C.c_int, [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]),
+    "rb200_group_scene_destroy": (C.c_int, [C.c_void_p]),
+    "rb200_group_scene_bvh_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(BvhInfo)]),
+    "rb200_group_render_batches": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RtPushConsts), C.c_uint32, C.c_uint32]),
+    "rb200_group_present": (C.c_int, [C.c_void_p, C.POINTER(BloomPushConsts), C.POINTER(TonemappingPushConsts)]),
+    "rb200_group_read_ldr": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rb200_group_read_hdr": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rb200_group_synchronize": (C.c_int, [C.c_void_p]),
+    "rb200_group_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "rb200_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "rb200_context_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "rb200_context_comm_destroy": (C.c_int, [C.c_void_p]),
+    "rb200_context_reduce_present": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(BloomPushConsts), C.POINTER(TonemappingPushConsts)]),
+    "rb200_context_reduced_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
 }
 
 _lib = None

@@ -182,6 +182,8 @@ RB200_API int rb200_context_destroy(RB200Context* ctx) {
     if (ctx->waveCountsDev) cudaFree(ctx->waveCountsDev);
     for (cudaEvent_t e : ctx->ldrPendingEvents) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ldrEventPool) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->batchEvents) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->batchEventPool) cudaEventDestroy(e);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     cudaGetLastError();
     delete ctx;
@@ -375,7 +377,32 @@ RB200_API int rb200_render_batch(RB200Context* ctx, const RB200Scene* scene, con
     if (!ctx || !scene || !pc) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
     if (scene->ctx != ctx) { set_error("scene belongs to another context"); return RB200_ERR_INVALID_ARGUMENT; }
     RB_CUDA(cudaSetDevice(ctx->device));
-    return render_batch(ctx, scene, pc);
+    const int rc = render_batch(ctx, scene, pc);
+    if (rc != RB200_OK) return rc;
+    // completion marker of this batch on the front-end stream (which waits for the batch's fold)
+    cudaEvent_t e;
+    if (!ctx->batchEventPool.empty()) { e = ctx->batchEventPool.back(); ctx->batchEventPool.pop_back(); }
+    else RB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+    RB_CUDA(cudaEventRecord(e, ctx->stream));
+    ctx->batchEvents.push_back(e);
+    while (ctx->batchEvents.size() > 64) {      // bound the list for callers that never wait
+        if (cudaEventQuery(ctx->batchEvents.front()) != cudaSuccess) break;
+        ctx->batchEventPool.push_back(ctx->batchEvents.front()); ctx->batchEvents.pop_front();
+    }
+    cudaGetLastError();
+    return RB200_OK;
+}
+
+RB200_API int rb200_wait_batches_pending(RB200Context* ctx, uint32_t max_pending) {
+    if (!ctx) { set_error("null context"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
+    while (ctx->batchEvents.size() > max_pending) {
+        cudaEvent_t e = ctx->batchEvents.front();
+        ctx->batchEvents.pop_front();
+        ctx->batchEventPool.push_back(e);
+        RB_CUDA(cudaEventSynchronize(e));
+    }
+    return RB200_OK;
 }
 
 RB200_API int rb200_resolve_sum(RB200Context* ctx, uint32_t numBatches) {

@@ -1,6 +1,7 @@
 // context.cuh — host-side objects behind the opaque RB200Context / RB200Scene handles.
 #pragma once
 #include "common.cuh"
+#include <deque>
 
 struct RB200Scene {
     RB200Context* ctx = nullptr;
@@ -197,6 +198,8 @@ struct RB200Context {
     cudaEvent_t frontMark = nullptr;
     std::vector<cudaEvent_t> ldrPendingEvents; // completion events of the outstanding rb200_read_ldr_async copies, oldest first
     std::vector<cudaEvent_t> ldrEventPool;
+    std::deque<cudaEvent_t> batchEvents;       // one per rb200_render_batch still in flight (rb200_wait_batches_pending)
+    std::vector<cudaEvent_t> batchEventPool;
     uint64_t batchCalls = 0;
     int lastEngine = -1;                       // engine of the most recent rb200_render_batch call
     std::vector<void*> allocations;

@@ -4,7 +4,7 @@
 // formula into a local SUM image (RB200_FLAG_ACCUM_SUM), the scene and its BVH are replicated (the build is
 // deterministic, so the hashes must agree — checked at scene creation), and ONE ncclReduce(float, 4 * W * H) of
 // stream-ordered snapshots of the images to the root closes a frame; the root resolves (sum / batches), blooms,
-// tonemaps and reads back. In latency mode (rb200_group_set_tiles) every device traces its interleaved tiles of every
+// tonemaps and reads back. In latency mode (RB200_FLAG_GROUP_TILES) every device traces its interleaved tiles of every
 // batch with the reference's running average instead, and the same reduce yields the single-GPU image bit for bit.
 //
 // Two ways in:
@@ -263,13 +263,18 @@ RB200_API int rb200_group_create(uint32_t width, uint32_t height, const int* dev
     RB200Group* g = new RB200Group();
     g->devices.assign(devices, devices + numDevices);
     g->width = width; g->height = height;
-    g->flags = flags | RB200_FLAG_ACCUM_SUM;          // sample split: local sums, one reduce, resolve on the root
+    g->tiles = (flags & RB200_FLAG_GROUP_TILES) != 0;
+    // sample split: local sums, one reduce, resolve on the root; latency mode: running averages of disjoint tiles
+    g->flags = g->tiles ? (flags & ~(uint32_t)(RB200_FLAG_GROUP_TILES | RB200_FLAG_ACCUM_SUM)) : (flags | RB200_FLAG_ACCUM_SUM);
     g->ctx.assign(numDevices, nullptr);
     for (int i = 0; i < numDevices; i++) { Worker* w = new Worker(); w->start(); g->workers.push_back(w); }
     for (int i = 0; i < numDevices; i++)
         g->workers[i]->post([g, i] { return rb200_context_create(g->width, g->height, g->devices[i], g->flags, &g->ctx[i]); });
     int rc = g->wait_all();
     if (rc != RB200_OK) { rb200_group_destroy(g); return rc; }
+    if (g->tiles)
+        for (int i = 0; i < numDevices; i++)
+            if ((rc = rb200_context_set_tiles(g->ctx[i], (uint32_t)i, (uint32_t)numDevices, 32u)) != RB200_OK) { rb200_group_destroy(g); return rc; }
     if (numDevices > 1) {
         std::vector<NcclComm> comms(numDevices, nullptr);
         const int r = api->CommInitAll(comms.data(), numDevices, devices);
@@ -289,14 +294,14 @@ RB200_API int rb200_group_context(RB200Group* g, int index, RB200Context** out) 
     return RB200_OK;
 }
 
-RB200_API int rb200_group_set_tiles(RB200Group* g, uint32_t tileSize) {
+RB200_API int rb200_group_set_tile_size(RB200Group* g, uint32_t tileSize) {
     if (!g) { set_error("null group"); return RB200_ERR_INVALID_ARGUMENT; }
+    if (!g->tiles) { set_error("the group was not created with RB200_FLAG_GROUP_TILES"); return RB200_ERR_INVALID_ARGUMENT; }
     if (tileSize == 0) { set_error("tileSize must be > 0"); return RB200_ERR_INVALID_ARGUMENT; }
-    if (g->batchesRendered) { set_error("rb200_group_set_tiles must precede the first batch"); return RB200_ERR_INVALID_ARGUMENT; }
-    // latency mode needs the running average in every member image: contexts are re-created without the sum flag
-    set_error("latency mode is selected at creation: pass RB200_FLAG_GROUP_TILES to rb200_group_create");
-    (void)tileSize;
-    return RB200_ERR_INVALID_ARGUMENT;
+    if (g->batchesRendered) { set_error("the tile size must be chosen before the first batch"); return RB200_ERR_INVALID_ARGUMENT; }
+    int rc = g->wait_all();
+    for (int i = 0; i < g->n() && rc == RB200_OK; i++) rc = rb200_context_set_tiles(g->ctx[i], (uint32_t)i, (uint32_t)g->n(), tileSize);
+    return rc;
 }
 
 RB200_API int rb200_group_scene_destroy(RB200GroupScene* s) {
@@ -343,8 +348,10 @@ RB200_API int rb200_group_scene_bvh_info(const RB200GroupScene* s, int index, RB
     return g->workers[index]->wait();
 }
 
-// Device i renders batches firstBatch + i + k * n, k = 0 .. batchesPerDevice - 1, of the sequence whose push constants are
-// *pc with sampleBatch replaced. Asynchronous: returns when every device's thread has taken the job.
+// Sample split: device i renders batches firstBatch + i + k * n, k = 0 .. batchesPerDevice - 1, of the sequence whose push
+// constants are *pc with sampleBatch replaced (n * batchesPerDevice batches in all). Latency mode (RB200_FLAG_GROUP_TILES):
+// every device renders its tiles of batches firstBatch .. firstBatch + batchesPerDevice - 1. Asynchronous: returns when
+// the jobs are queued on the devices' threads.
 RB200_API int rb200_group_render_batches(RB200Group* g, const RB200GroupScene* s, const RB200RtPushConsts* pc, uint32_t firstBatch,
                                          uint32_t batchesPerDevice) {
     if (!g || !s || !pc || s->group != g) { set_error("invalid argument"); return RB200_ERR_INVALID_ARGUMENT; }
@@ -354,13 +361,13 @@ RB200_API int rb200_group_render_batches(RB200Group* g, const RB200GroupScene* s
         g->workers[i]->post([g, s, base, firstBatch, batchesPerDevice, i, n] {
             RB200RtPushConsts p = base;
             for (uint32_t k = 0; k < batchesPerDevice; k++) {
-                p.sampleBatch = firstBatch + (uint32_t)i + k * (uint32_t)n;
+                p.sampleBatch = g->tiles ? firstBatch + k : firstBatch + (uint32_t)i + k * (uint32_t)n;
                 const int rc = rb200_render_batch(g->ctx[i], s->scenes[i], &p);
                 if (rc != RB200_OK) return rc;
             }
             return (int)RB200_OK;
         });
-    g->batchesRendered += (uint64_t)batchesPerDevice * (uint64_t)n;
+    g->batchesRendered += g->tiles ? (uint64_t)batchesPerDevice : (uint64_t)batchesPerDevice * (uint64_t)n;
     return RB200_OK;
 }
 
@@ -374,7 +381,8 @@ RB200_API int rb200_group_present(RB200Group* g, const RB200BloomPushConsts* blo
     const RB200BloomPushConsts b = *bloom;
     const RB200TonemappingPushConsts t = *tm;
     if (g->n() == 1) {
-        g->workers[0]->post([g, total, b, t] { return rb200_present_sum(g->ctx[0], nullptr, total, &b, &t); });
+        if (g->tiles) g->workers[0]->post([g, b, t] { return rb200_postprocess(g->ctx[0], &b, &t); });
+        else g->workers[0]->post([g, total, b, t] { return rb200_present_sum(g->ctx[0], nullptr, total, &b, &t); });
         return RB200_OK;
     }
     for (int i = 0; i < g->n(); i++)
@@ -419,6 +427,7 @@ RB200_API int rb200_group_read_hdr(RB200Group* g, float* rgba32f) {
             RB_CUDA(cudaSetDevice(c->device));
             RB_CUDA(cudaMemcpyAsync(rgba32f, src, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
             RB_CUDA(cudaStreamSynchronize(c->stream));
+            if (g->tiles) return RB200_OK;                  // running averages of disjoint tiles: nothing to resolve
             const float inv = 1.0f / (float)total;          // the arithmetic of rb200_resolve_sum
             for (size_t k = 0; k < n; k++) { rgba32f[4 * k] *= inv; rgba32f[4 * k + 1] *= inv; rgba32f[4 * k + 2] *= inv; rgba32f[4 * k + 3] = 1.0f; }
             return RB200_OK;

@@ -143,6 +143,9 @@ void Renderer::setScene(SceneTables& tables) {
 void Renderer::renderBatch(const RB200RtPushConsts& pc) {
     if (!scene) throw std::runtime_error("renderBatch: no scene set");
     check(rb200_render_batch(ctx, scene, &pc), "rb200_render_batch");
+    // calls are asynchronous: without back-pressure the host clock (--seconds, the save_on_times thresholds) would run
+    // ahead of the device by the whole driver queue. Keep at most rb200_pipeline_depth() batches in flight.
+    check(rb200_wait_batches_pending(ctx, rb200_pipeline_depth()), "rb200_wait_batches_pending");
 }
 
 void Renderer::postprocess(const RB200BloomPushConsts& bloom, const RB200TonemappingPushConsts& tonemap) {
@@ -211,6 +214,95 @@ LoopResult render_loop(Renderer& r, const Config& cfg, RB200RtPushConsts pc, con
     }
     if (!opt.finalOutput.empty()) {
         r.postprocess(cfg.bloom, cfg.tonemap);
+        std::vector<uint8_t> px = r.readLdr();
+        write_png_rgba8(opt.finalOutput, px.data(), r.width(), r.height());
+        res.filesWritten.push_back(opt.finalOutput);
+    }
+    res.stats = r.cumulativeStats();   // synchronises
+    res.seconds = now();
+    return res;
+}
+
+GroupRenderer::GroupRenderer(uint32_t width, uint32_t height, int numDevices, uint32_t flags, bool tiles_)
+    : w(width), h(height), n(numDevices), tiles(tiles_) {
+    std::vector<int> devs(size_t(numDevices > 0 ? numDevices : 0));
+    for (int i = 0; i < numDevices; i++) devs[size_t(i)] = i;
+    check(rb200_group_create(width, height, devs.data(), numDevices, flags | (tiles ? uint32_t(RB200_FLAG_GROUP_TILES) : 0u), &group),
+          "rb200_group_create");
+}
+
+GroupRenderer::~GroupRenderer() {
+    if (scene) rb200_group_scene_destroy(scene);
+    if (group) rb200_group_destroy(group);
+}
+
+void GroupRenderer::setScene(SceneTables& tables) {
+    if (scene) { rb200_group_scene_destroy(scene); scene = nullptr; }
+    RB200SceneDesc d = tables.desc();
+    check(rb200_group_scene_create(group, &d, &scene), "rb200_group_scene_create");
+}
+
+void GroupRenderer::renderFrame(const RB200RtPushConsts& pc, uint32_t firstBatch) {
+    if (!scene) throw std::runtime_error("renderFrame: no scene set");
+    check(rb200_group_render_batches(group, scene, &pc, firstBatch, 1), "rb200_group_render_batches");
+}
+
+void GroupRenderer::present(const RB200BloomPushConsts& bloom, const RB200TonemappingPushConsts& tonemap) {
+    check(rb200_group_present(group, &bloom, &tonemap), "rb200_group_present");
+}
+
+std::vector<uint8_t> GroupRenderer::readLdr() {
+    std::vector<uint8_t> px(size_t(w) * h * 4);
+    check(rb200_group_read_ldr(group, px.data()), "rb200_group_read_ldr");
+    return px;
+}
+
+RB200BvhInfo GroupRenderer::bvhInfo() const {
+    RB200BvhInfo info{};
+    if (!scene) throw std::runtime_error("bvhInfo: no scene set");
+    check(rb200_group_scene_bvh_info(scene, 0, &info), "rb200_group_scene_bvh_info");
+    return info;
+}
+
+RB200Stats GroupRenderer::cumulativeStats() {
+    RB200Stats cum{};
+    check(rb200_group_get_stats(group, &cum), "rb200_group_get_stats");
+    return cum;
+}
+
+LoopResult render_loop_group(GroupRenderer& r, const Config& cfg, RB200RtPushConsts pc, const LoopOptions& opt) {
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
+    auto now = [t0] { return std::chrono::duration<double>(clk::now() - t0).count(); };
+    FrameClock clock(now);
+    SaveManager saves(cfg.saveOnSamples, cfg.saveOnTimes);
+    LoopResult res;
+    const std::string dir = opt.outputDir.empty() ? std::string(".") : opt.outputDir;
+    if (pc.samplesPerPixel == 0) throw std::runtime_error("sampling.samples_per_pixel must be at least 1");
+    const uint32_t batchesPerFrame = r.tileMode() ? 1u : uint32_t(r.devices());
+    const uint32_t samplesPerFrame = pc.samplesPerPixel * batchesPerFrame;
+    uint32_t nextBatch = 0;
+    for (;;) {
+        r.renderFrame(pc, nextBatch);
+        nextBatch += batchesPerFrame;
+        res.frames++;
+        res.samples += samplesPerFrame;
+        SaveInfo info = saves.shouldSave(clock.getSampleCount(), clock.getAge());
+        if (info.shouldSave) {
+            r.present(cfg.bloom, cfg.tonemap);
+            std::vector<uint8_t> px = r.readLdr();
+            const std::string file = dir + "/" + info.filename;
+            write_png_rgba8(file, px.data(), r.width(), r.height());
+            res.filesWritten.push_back(file);
+            if (!opt.quiet) std::printf("saved %s (%u samples per pixel in the image)\n", file.c_str(), res.samples);
+        }
+        clock.markFrame(samplesPerFrame);
+        if (opt.totalSamples && res.samples >= opt.totalSamples) break;
+        if (opt.maxSeconds > 0.0 && now() >= opt.maxSeconds) break;
+        if (!opt.totalSamples && opt.maxSeconds <= 0.0 && !saves.pending()) break;
+    }
+    if (!opt.finalOutput.empty()) {
+        r.present(cfg.bloom, cfg.tonemap);
         std::vector<uint8_t> px = r.readLdr();
         write_png_rgba8(opt.finalOutput, px.data(), r.width(), r.height());
         res.filesWritten.push_back(opt.finalOutput);

@@ -97,4 +97,35 @@ struct LoopResult {
 
 LoopResult render_loop(Renderer& r, const Config& cfg, RB200RtPushConsts pc, const LoopOptions& opt);
 
+// The same loop on several GPUs of this machine (rb200_group_*: a context and a host thread per device, the BVH
+// replicated, one ncclReduce of the accumulation images per saved frame). Sample split: a frame is one batch per device
+// (device g renders batch frame * n + g), so a frame adds n * samples_per_pixel samples; with `tiles` every device renders
+// its interleaved tiles of one batch per frame instead (latency mode).
+class GroupRenderer {
+public:
+    GroupRenderer(uint32_t width, uint32_t height, int numDevices, uint32_t flags, bool tiles);
+    ~GroupRenderer();
+    GroupRenderer(const GroupRenderer&) = delete;
+    GroupRenderer& operator=(const GroupRenderer&) = delete;
+    void setScene(SceneTables& tables);
+    void renderFrame(const RB200RtPushConsts& pc, uint32_t firstBatch);
+    void present(const RB200BloomPushConsts& bloom, const RB200TonemappingPushConsts& tonemap);
+    std::vector<uint8_t> readLdr();
+    RB200BvhInfo bvhInfo() const;
+    RB200Stats cumulativeStats();
+    int devices() const { return n; }
+    bool tileMode() const { return tiles; }
+    uint32_t width() const { return w; }
+    uint32_t height() const { return h; }
+
+private:
+    uint32_t w, h;
+    int n;
+    bool tiles;
+    RB200Group* group = nullptr;
+    RB200GroupScene* scene = nullptr;
+};
+
+LoopResult render_loop_group(GroupRenderer& r, const Config& cfg, RB200RtPushConsts pc, const LoopOptions& opt);
+
 }  // namespace rbhost

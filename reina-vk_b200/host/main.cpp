@@ -37,6 +37,9 @@ static void usage() {
         "  --outdir DIR         directory for the output_<N>spp.png / output_<T>sec.png files of [saving] (default .)\n"
         "  --nee | --no-nee     next-event estimation on / off (overrides [render].nee)\n"
         "  --device N           CUDA device (default 0)\n"
+        "  --gpus N             render on devices 0 .. N-1 of this machine: the BVH is replicated, device g renders sample batches\n"
+        "                       g, g + N, ... and one NCCL reduce of the accumulation images closes every saved frame\n"
+        "  --tiles              with --gpus: latency mode, every device renders its interleaved 32 x 32 tiles of every batch\n"
         "  --dump-pc FILE       write the 160-byte push-constant block of batch 0 to FILE\n"
         "  --quiet              no progress output\n");
 }
@@ -55,7 +58,8 @@ int main(int argc, char** argv) {
     Material nextMat;
     nextMat.albedo = {0.8f, 0.8f, 0.8f};
     nextMat.interpNormals = true;
-    long width = -1, height = -1, spp = 0, device = 0;
+    long width = -1, height = -1, spp = 0, device = 0, gpus = 1;
+    bool tiles = false;
     double seconds = 0.0;
     int nee = -1;
     bool quiet = false;
@@ -99,6 +103,8 @@ int main(int argc, char** argv) {
             else if (a == "--nee") nee = 1;
             else if (a == "--no-nee") nee = 0;
             else if (a == "--device") device = std::strtol(value(), nullptr, 10);
+            else if (a == "--gpus") gpus = std::strtol(value(), nullptr, 10);
+            else if (a == "--tiles") tiles = true;
             else if (a == "--dump-pc") dumpPc = value();
             else if (a == "--quiet") quiet = true;
             else throw std::runtime_error("unknown option " + a + " (see --help)");
@@ -123,6 +129,30 @@ int main(int argc, char** argv) {
             if (!f) throw std::runtime_error("cannot write " + dumpPc);
         }
 
+        LoopOptions opt;
+        opt.totalSamples = uint32_t(spp);
+        opt.maxSeconds = seconds;
+        opt.outputDir = outDir;
+        opt.finalOutput = finalOut;
+        opt.quiet = quiet;
+        if (gpus < 1) throw std::runtime_error("--gpus must be at least 1");
+        if (gpus > 1 || tiles) {
+            GroupRenderer group(cfg.width, cfg.height, int(gpus), cfg.nee ? uint32_t(RB200_FLAG_NEE) : 0u, tiles);
+            group.setScene(tables);
+            if (!quiet) {
+                const RB200BvhInfo bvh = group.bvhInfo();
+                std::printf("scene: %llu triangles, %u wide nodes, depth %u, built in %.2f ms on each of %ld devices (equal hashes)\n",
+                            static_cast<unsigned long long>(tables.numTriangles()), bvh.numWideNodes, bvh.maxDepth, bvh.buildMs, gpus);
+            }
+            const LoopResult res = render_loop_group(group, cfg, pc, opt);
+            if (!quiet) {
+                const double rays = double(res.stats.extendRays + res.stats.shadowRays);
+                std::printf("%u frames, %u samples per pixel, %.3f s, %.1f Mrays/s on %ld devices, %zu file(s) written\n", res.frames,
+                            res.samples, res.seconds, res.seconds > 0 ? rays / res.seconds * 1e-6 : 0.0, gpus, res.filesWritten.size());
+            }
+            return 0;
+        }
+
         Renderer renderer(cfg.width, cfg.height, int(device), cfg.nee ? uint32_t(RB200_FLAG_NEE) : 0u);
         renderer.setScene(tables);
         if (!quiet) {
@@ -131,12 +161,6 @@ int main(int argc, char** argv) {
                         static_cast<unsigned long long>(tables.numTriangles()), bvh.numWideNodes, bvh.maxDepth, bvh.buildMs);
         }
 
-        LoopOptions opt;
-        opt.totalSamples = uint32_t(spp);
-        opt.maxSeconds = seconds;
-        opt.outputDir = outDir;
-        opt.finalOutput = finalOut;
-        opt.quiet = quiet;
         const LoopResult res = render_loop(renderer, cfg, pc, opt);
         if (!quiet) {
             const double rays = double(res.stats.extendRays + res.stats.shadowRays);
