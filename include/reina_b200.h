@@ -219,6 +219,18 @@ typedef struct RB200PrimaryHit {
     uint32_t primitive;      /* triangle index within the model (gl_PrimitiveID) */
 } RB200PrimaryHit;
 
+/* What one closest-hit shader invocation leaves in the ray payload (shaders/raytrace/shaderCommon.h.glsl:17-35), for
+ * rb200_shade_hits. */
+typedef struct RB200ShadeResult {
+    float    color[3], albedo[3], origin[3], direction[3], emission[3], normal[3];   /* pld.color .. pld.surfaceNormal */
+    float    pdf;                    /* pld.pdf */
+    float    accumulatedDistance;    /* pld.accumulatedDistance after the shader */
+    uint32_t rngState;               /* pld.rngState after the shader */
+    uint32_t flags;                  /* bit 0: the ray hit something; bit 1: pld.skip; bit 2: pld.insideDielectric */
+    uint32_t material;               /* hit group that ran: 0 lambertian, 1 metal, 2 dielectric, 3 disney; 4 = miss */
+    uint32_t reserved;
+} RB200ShadeResult;
+
 /* ------------------------------------------------------------------------------------------------ */
 /* entry points                                                                                      */
 /* ------------------------------------------------------------------------------------------------ */
@@ -318,6 +330,14 @@ RB200_API int rb200_trace_primary(RB200Context* ctx, const RB200Scene* scene, co
  * and the traversal micro-benchmark. Host pointers. */
 RB200_API int rb200_trace_rays(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* origins,
                                const float* directions, const float* tmax, int any_hit, RB200PrimaryHit* out_hits);
+
+/* Parity aid: for each of n caller-supplied rays (xyz triples, not necessarily unit length) ONE closest-hit traversal and
+ * ONE invocation of the hit instance's material shader — the device code the wave loop runs — with the payload's incoming
+ * state set from rngStates / insideDielectric (0 or 1) / accumulatedDistance; *out = the payload afterwards. This is
+ * traceRayEXT + <material>.rchit of the reference for one ray (raytrace.rgen.glsl:110-122). Host pointers, blocking. */
+RB200_API int rb200_shade_hits(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* origins,
+                               const float* directions, const uint32_t* rngStates, const uint32_t* insideDielectric,
+                               const float* accumulatedDistance, RB200ShadeResult* out);
 
 /* Measurement aid: the traversal kernel alone on the caller's rays (as rb200_trace_rays), one warm-up launch and `reps`
  * timed ones (CUDA events on the launching stream); *out_ms_per_launch = mean device time of a launch, *out_checksum =

@@ -143,7 +143,12 @@ void build_bvh(Scene& s) {
 // fp32 ulps of |vertex - origin|, so boxes are padded by a slack proportional to the coordinates involved.
 static inline bool box_hit(const BvhNode& n, const double o[3], const double inv[3], double tmax, double slackScale,
                            double* tnear) {
-    double t0 = 0.0, t1 = tmax;
+    // Every box is dilated by a margin in ray parameters, and so is the best-t limit: the watertight test computes t as the
+    // barycentric mean of the vertices' ray parameters, with an fp32 error proportional to the triangle's extent in ray
+    // parameters (not to t). A triangle whose computed t beats the best so far can sit in a box that starts a few 1e-8 beyond
+    // it (a ray leaving a large floor triangle), and a ray that starts 1e-7 behind a two-metre triangle and moves away from
+    // it is reported at t = +4e-8. 2^-14 of the box's extent in ray parameters, as in csrc/traverse.cuh.
+    double t0 = -1e300, t1 = 1e300, ext = 0.0;
     for (int a = 0; a < 3; a++) {
         double m = std::max(std::max(std::fabs((double)n.lo[a]), std::fabs((double)n.hi[a])), std::fabs(o[a]));
         double slack = slackScale * m + 1e-30;
@@ -151,10 +156,14 @@ static inline bool box_hit(const BvhNode& n, const double o[3], const double inv
         double tb = ((double)n.hi[a] + slack - o[a]) * inv[a];
         if (ta != ta || tb != tb) continue;            // 0 * inf: origin on the slab plane, direction parallel -> inside
         if (ta > tb) std::swap(ta, tb);
+        if (std::fabs(ta) < 1e300) ext = std::max(ext, std::fabs(ta));
+        if (std::fabs(tb) < 1e300) ext = std::max(ext, std::fabs(tb));
         t0 = std::max(t0, ta); t1 = std::min(t1, tb);
     }
-    *tnear = t0;
-    return t0 <= t1 * (1.0 + 1e-9) + 1e-30;
+    const double margin = 6.103515625e-05 * ext;        // 2^-14
+    t0 -= margin; t1 += margin;
+    *tnear = std::max(t0, 0.0);
+    return t0 <= t1 * (1.0 + 1e-9) + 1e-30 && t1 >= 0.0 && t0 <= (tmax + margin) * (1.0 + 1e-9) + 1e-30;
 }
 
 static inline void test_tri(const Scene& s, uint32_t gid, vec3 org, const rb_ray_shear& sh, float tmax, Hit& best) {

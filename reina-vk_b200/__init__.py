@@ -142,6 +142,21 @@ class Renderer:
                                                       1 if any_hit else 0, hits.ctypes.data_as(C.c_void_p)))
         return hits
 
+    def shade_hits(self, origins, directions, rng_states, inside, acc_dist):
+        """One closest-hit traversal + one material-shader invocation per ray (rb200_shade_hits): structured array with the
+        payload the shader leaves (color, albedo, origin, direction, emission, normal, pdf, accumulatedDistance, rngState,
+        flags: 1 hit | 2 skip | 4 insideDielectric, material)."""
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        r = np.ascontiguousarray(rng_states, np.uint32).reshape(n)
+        i = np.ascontiguousarray(inside, np.uint32).reshape(n)
+        a = np.ascontiguousarray(acc_dist, np.float32).reshape(n)
+        out = np.empty(n, dtype=np.dtype(abi.ShadeResult))
+        p = lambda x: x.ctypes.data_as(C.c_void_p)
+        abi.check(self.lib, self.lib.rb200_shade_hits(self._ctx, self._scene, n, p(o), p(d), p(r), p(i), p(a), p(out)))
+        return out
+
     def bench_trace(self, origins, directions, tmax, any_hit=False, reps=10):
         """(ms per launch, checksum of the hits) of the traversal kernel alone on these rays (rb200_bench_trace)."""
         o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)

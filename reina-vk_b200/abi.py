@@ -130,6 +130,12 @@ class KernelTimes(C.Structure):
                 "finishItems": self.finishItems}
 
 
+class ShadeResult(C.Structure):
+    _fields_ = [("color", C.c_float * 3), ("albedo", C.c_float * 3), ("origin", C.c_float * 3), ("direction", C.c_float * 3),
+                ("emission", C.c_float * 3), ("normal", C.c_float * 3), ("pdf", C.c_float), ("accumulatedDistance", C.c_float),
+                ("rngState", C.c_uint32), ("flags", C.c_uint32), ("material", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class PrimaryHit(C.Structure):
     _fields_ = [("t", C.c_float), ("u", C.c_float), ("v", C.c_float), ("instance", C.c_uint32),
                 ("primitive", C.c_uint32)]
@@ -171,6 +177,8 @@ SYMBOLS = {
     "rb200_trace_primary": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RtPushConsts), C.c_void_p]),
     "rb200_trace_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_void_p]),
+    "rb200_shade_hits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
     "rb200_bench_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32,
                                     C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "rb200_engine_config": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),

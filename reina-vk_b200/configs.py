@@ -220,6 +220,27 @@ def showroom_mixed(width=3840, height=2160, levels=6, nee=True, samples_per_pixe
     return Workload("showroom_mixed", tables, width, height, pc, nee, 4096, "stand-in geometry")
 
 
+def two_lights(width=96, height=72, emitters_first=True, nee=True, samples_per_pixel=2, max_bounces=6):
+    """Two emitters (NEE with more than one light, nee.h.glsl:52-124). nee.h.glsl:97-105 addresses an emitter's triangles
+    by their position in the CONCATENATED triangle CDF (indices[3 * cdfIndex + indexOffset]), so the second emitter (CDF
+    slots 2..49) reads 2 triangles past its own mesh — with the emitters first those slots still lie inside the index
+    buffer (the box's triangles, moved by the emitter's transform: upstream's behaviour, restated literally); with the
+    emitters last they lie past its end and the scene is refused with NEE on."""
+    s = Scene()
+    if not emitters_first:
+        s.addObject(meshes.cornell_box(), IDENT, Material(**CORNELL_WALL))
+    s.addObject(meshes.cornell_light(), IDENT, Material(**LIGHT))
+    # a second, differently sized, double-sided and differently coloured emitter with a non-trivial transform
+    M = compose(translate((-0.5, 0.9, -0.2)), scale((0.5, 1.0, 0.7)))
+    s.addObject(meshes.uv_sphere(8, 4, radius=0.2), M, Material(materialIdx=0, albedo=(1, 1, 1), emission=(2.0, 7.0, 4.0), cullBackface=False))
+    if emitters_first:
+        s.addObject(meshes.cornell_box(), IDENT, Material(**CORNELL_WALL))
+    tables = s.build(require_emitter=True)
+    pc = dict(pos=(0.0, 1.0, 3.9), look=(0.0, 1.0, 0.0), fovy_deg=40.0, samples_per_pixel=samples_per_pixel,
+              max_bounces=max_bounces)
+    return Workload("two_lights", tables, width, height, pc, nee, 2)
+
+
 def small_mixed(width=160, height=120, nee=True, samples_per_pixel=2, max_bounces=8, textured=True):
     """A small closed scene touching every material, texture and skip path; sized so the CPU oracle renders it in
     seconds. Used by the parity tests and by __graft_entry__.smoke()."""

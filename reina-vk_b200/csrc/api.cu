@@ -41,6 +41,12 @@ static int validate_desc(const RB200SceneDesc* d) {
         return RB200_ERR_INVALID_ARGUMENT;
     }
     if (!d->tbns || !d->tbnIndices) { set_error("scene description lacks the TBN tables (bindings 5, 6)"); return RB200_ERR_INVALID_ARGUMENT; }
+    // every table whose count is non-zero must be there
+    if ((d->numEmissive && !d->emissiveMetadata) || (d->numCdfTriangles && !d->cdfTriangles) || (d->numCdfInstances && !d->cdfInstances) ||
+        (d->numTexCoords && !d->texCoords) || (d->numTexIndices && !d->texIndices) || (d->numTextures && !d->textures)) {
+        set_error("scene description: a table with a non-zero count is NULL"); return RB200_ERR_INVALID_ARGUMENT;
+    }
+    bool usesTexCoords = false;
     for (uint32_t i = 0; i < d->numInstances; i++) {
         const RB200Instance& in = d->instances[i];
         if (in.instancePropertiesID >= d->numInstanceProperties) { set_error("instance %u: instancePropertiesID out of range", i); return RB200_ERR_INVALID_ARGUMENT; }
@@ -49,6 +55,9 @@ static int validate_desc(const RB200SceneDesc* d) {
         if (p.textureID >= (int)d->numTextures || p.normalMapTexID >= (int)d->numTextures || p.bumpMapTexID >= (int)d->numTextures) {
             set_error("instance %u: texture id out of range", i); return RB200_ERR_INVALID_ARGUMENT;
         }
+        // the shading kernels address the index buffer through the PROPERTIES' offset (closestHitCommon.h.glsl:61-66)
+        if ((uint64_t)p.indicesOffset + 3ull * in.triangleCount > d->numIndices) { set_error("instance %u: InstanceProperties.indicesOffset range out of bounds", i); return RB200_ERR_INVALID_ARGUMENT; }
+        if (p.texIndicesOffset != 0xFFFFFFFFu) usesTexCoords = true;
         if ((uint64_t)p.tbnsIndicesOffset + 3ull * in.triangleCount > d->numTbnIndices) { set_error("instance %u: TBN index range out of bounds", i); return RB200_ERR_INVALID_ARGUMENT; }
         if (p.texIndicesOffset != 0xFFFFFFFFu && (uint64_t)p.texIndicesOffset + 3ull * in.triangleCount > d->numTexIndices) {
             set_error("instance %u: texcoord index range out of bounds", i); return RB200_ERR_INVALID_ARGUMENT;
@@ -56,7 +65,8 @@ static int validate_desc(const RB200SceneDesc* d) {
     }
     for (uint32_t i = 0; i < d->numIndices; i++) if (d->indices[i] >= d->numVertices) { set_error("vertex index %u out of range", i); return RB200_ERR_INVALID_ARGUMENT; }
     for (uint32_t i = 0; i < d->numTbnIndices; i++) if (d->tbnIndices[i] >= d->numTbns) { set_error("TBN index %u out of range", i); return RB200_ERR_INVALID_ARGUMENT; }
-    if (d->numTexCoords) for (uint32_t i = 0; i < d->numTexIndices; i++)
+    if (usesTexCoords && d->numTexCoords == 0) { set_error("an instance refers to texture coordinates but the texcoord table is empty"); return RB200_ERR_INVALID_ARGUMENT; }
+    if (d->numTexCoords || usesTexCoords) for (uint32_t i = 0; i < d->numTexIndices; i++)
         if (d->texIndices[i] != 0xFFFFFFFFu && d->texIndices[i] >= d->numTexCoords) { set_error("texcoord index %u out of range", i); return RB200_ERR_INVALID_ARGUMENT; }
     for (uint32_t i = 0; i < d->numEmissive; i++) {
         const RB200InstanceData& e = d->emissiveMetadata[i];
@@ -536,6 +546,17 @@ RB200_API int rb200_trace_rays(RB200Context* ctx, const RB200Scene* scene, uint3
     if (!ctx || !scene || (n && (!origins || !directions || !tmax || !out_hits))) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
     RB_CUDA(cudaSetDevice(ctx->device));
     return trace_rays(ctx, scene, n, origins, directions, tmax, any_hit, out_hits);
+}
+
+RB200_API int rb200_shade_hits(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* origins, const float* directions,
+                               const uint32_t* rngStates, const uint32_t* insideDielectric, const float* accumulatedDistance,
+                               RB200ShadeResult* out) {
+    if (!ctx || !scene || (n && (!origins || !directions || !rngStates || !insideDielectric || !accumulatedDistance || !out))) {
+        set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT;
+    }
+    if (scene->ctx != ctx) { set_error("scene belongs to another context"); return RB200_ERR_INVALID_ARGUMENT; }
+    RB_CUDA(cudaSetDevice(ctx->device));
+    return shade_hits(ctx, scene, n, origins, directions, rngStates, insideDielectric, accumulatedDistance, out);
 }
 
 RB200_API int rb200_bench_trace(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* origins, const float* directions,

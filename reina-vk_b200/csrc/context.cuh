@@ -230,6 +230,8 @@ int trace_rays(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const flo
 int resolve_sum(RB200Context* ctx, uint32_t numBatches);
 int bench_trace(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* o, const float* d, const float* tmax, int any,
                 uint32_t reps, float* outMs, uint64_t* outChecksum);
+int shade_hits(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* o, const float* d, const uint32_t* rng,
+               const uint32_t* inside, const float* acc, RB200ShadeResult* out);
 int configure_wave_kernels(RB200Context* ctx);     // per device: shared-memory limits, persistent grids, code preload
 void invalidate_speculation(RB200Context* ctx);    // drains the engines and discards speculative batches
 // post.cu

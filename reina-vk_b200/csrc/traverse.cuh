@@ -241,9 +241,19 @@ struct Traversal {
         const float eps = 9.5367431640625e-07f;   // 2^-20
         // slack: 2^-20 * (255 |s| + |c|) bounds the rounding of q*s + c and the acceptance band of the triangle test;
         // + 2^-9 |s| (= 2^-20 * 2048, here 2305 with margin) bounds the rounding of the biased offsets c - 2^15 s
-        const float kx = eps * fmaf(2560.0f, fabsf(sx), fabsf(cx));
-        const float ky = eps * fmaf(2560.0f, fabsf(sy), fabsf(cy));
-        const float kz = eps * fmaf(2560.0f, fabsf(sz), fabsf(cz));
+        const float jx = eps * fmaf(2560.0f, fabsf(sx), fabsf(cx));
+        const float jy = eps * fmaf(2560.0f, fabsf(sy), fabsf(cy));
+        const float jz = eps * fmaf(2560.0f, fabsf(sz), fabsf(cz));
+        // + a margin in ray parameters, the same on every plane and on the best-t limit: the watertight test computes t as
+        // the barycentric mean of the vertices' ray parameters, whose fp32 error is proportional to the EXTENT of the triangle
+        // in ray parameters, not to t. A ray leaving a large floor triangle finds the neighbouring triangle at
+        // t = 2.65e-4 +- 3e-8, or — starting 1e-7 BEHIND a two-metre triangle and moving away from it — at t = +4e-8.
+        // What the triangle test accepts must never be culled, or the closest hit depends on the visiting order (found by
+        // the full-size C2 parity test: 4 of 518,400 pixels; tests/test_gpu_parity2.py has the ray set). 2^-14 of the node's
+        // extent in ray parameters bounds that error for triangles with an aspect ratio up to ~64 and weakens the cull by
+        // less than 1e-4 of a node's size.
+        const float margin = 64.0f * ((jx + jy) + jz);
+        const float kx = jx + margin, ky = jy + margin, kz = jz + margin;
         const float cnx = fmaf(-BYTE_BIAS, sx, cx - kx), cfx = fmaf(-BYTE_BIAS, sx, cx + kx);
         const float cny = fmaf(-BYTE_BIAS, sy, cy - ky), cfy = fmaf(-BYTE_BIAS, sy, cy + ky);
         const float cnz = fmaf(-BYTE_BIAS, sz, cz - kz), cfz = fmaf(-BYTE_BIAS, sz, cz + kz);
@@ -252,7 +262,7 @@ struct Traversal {
 
         ngroup.x = __float_as_uint(n1.x);
         uint32_t hitmask = 0u;
-        const float tcur = best.t;
+        const float tcur = best.t + margin;
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             const uint32_t meta4 = __float_as_uint(half == 0 ? n1.z : n1.w);

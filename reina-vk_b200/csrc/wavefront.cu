@@ -307,31 +307,13 @@ __device__ __forceinline__ void finish_slot(const WaveParams& P, const uint32_t 
     }
 }
 
+// The closest-hit shader of material MAT on one hit (lambertian / metal / dielectric / disney .rchit.glsl): everything
+// the shader writes into the payload — new ray, colour, albedo, emission, normal, pdf, the skip and insideDielectric
+// flags, the RNG state and the accumulated distance. Used by the wave loop (shade_slot) and by rb200_shade_hits.
 template <int MAT>
-__device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t slot, uint32_t* cnt, uint32_t* cntNext, int parity, LaneAcc& acc) {
-    const float4 ro4 = P.rayO[slot], rd4 = P.rayD[slot];
-    const rb_v3 rayOrigin = rb_mk3(ro4.x, ro4.y, ro4.z), rayDir = rb_mk3(rd4.x, rd4.y, rd4.z);
-    uint4 st = P.st[slot];
-    float4 T4 = P.thr[slot];
-    rb_v3 T = rb_mk3(T4.x, T4.y, T4.z);
-    float accDist = T4.w;
-    uint32_t rng = st.x;
-    uint32_t flags = st.y & 0xFFu;
-    uint32_t segments = st.y >> 8;
-    const bool nee = (P.flags & RB200_FLAG_NEE) != 0u;
-
-    if (MAT == 4) {
-        // miss shader + raygen's sky branch (rgen.glsl:138-141): radiance += sky * throughput, path ends
-        const float4 L4 = P.rad[slot];
-        const rb_v3 L = rb_mk3(L4.x, L4.y, L4.z) + sky_color(rayDir) * T;
-        // nothing else can add to this path (a miss casts no shadow ray, and the previous hit's shadow ray was resolved
-        // in the previous wave), so the path ends here: about 60 % of all path ends skip endQ and k_finish.
-        // Rays traced by this path: one per shaded segment plus the one that missed.
-        finish_slot(P, slot, L, st, segments + 1u, cntNext, parity, acc);
-        return;
-    }
-
-    const uint4 h = P.hit[slot];
+__device__ __forceinline__ void eval_hit(const WaveParams& P, const uint4 h, const rb_v3 rayOrigin, const rb_v3 rayDir, const bool prevInside,
+                                         uint32_t& rng, float& accDist, ShadeOut& o, Surf& s, const RB200InstanceProperties*& propsOut,
+                                         bool& didRefract) {
     const float a1 = __uint_as_float(h.x), a2 = __uint_as_float(h.y);
     const RB200Instance* inst = &P.S.instances[h.w];
 #if RB_INST_RECORDS
@@ -339,9 +321,7 @@ __device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t s
 #else
     const RB200InstanceProperties* props = &P.S.props[__ldg(&inst->instancePropertiesID)];
 #endif
-    const bool prevInside = (flags & F_INSIDE) != 0u;
 
-    Surf s;
     const bool hasNormalMap = __ldg(&props->normalMapTexID) >= 0;
     const bool needTbn = hasNormalMap || __ldg(&props->bumpMapTexID) >= 0;     // the parallax search runs in tangent space
 #if RB_SHADE_RECORDS
@@ -354,10 +334,9 @@ __device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t s
     else hit_info<false>(P.S, inst, props, h.z, a1, a2, rayDir, s);
 #endif
 
-    ShadeOut o;
     o.skip = false; o.pdf = 0.0f; o.inside = prevInside;
     o.color = o.albedo = o.emission = o.normal = rb_splat3(0.0f);
-    bool didRefract = false;   // always false when NEE sees it (disney.rchit.glsl:187)
+    didRefract = false;        // always false when NEE sees it (disney.rchit.glsl:187)
     rb_v3 wn, col;
 
     if (MAT == 0) {           // lambertian.rchit.glsl:11-78
@@ -438,6 +417,41 @@ __device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t s
             else accDist = 0.0f;
         }
     }
+
+    propsOut = props;
+}
+
+template <int MAT>
+__device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t slot, uint32_t* cnt, uint32_t* cntNext, int parity, LaneAcc& acc) {
+    const float4 ro4 = P.rayO[slot], rd4 = P.rayD[slot];
+    const rb_v3 rayOrigin = rb_mk3(ro4.x, ro4.y, ro4.z), rayDir = rb_mk3(rd4.x, rd4.y, rd4.z);
+    uint4 st = P.st[slot];
+    float4 T4 = P.thr[slot];
+    rb_v3 T = rb_mk3(T4.x, T4.y, T4.z);
+    float accDist = T4.w;
+    uint32_t rng = st.x;
+    uint32_t flags = st.y & 0xFFu;
+    uint32_t segments = st.y >> 8;
+    const bool nee = (P.flags & RB200_FLAG_NEE) != 0u;
+
+    if (MAT == 4) {
+        // miss shader + raygen's sky branch (rgen.glsl:138-141): radiance += sky * throughput, path ends
+        const float4 L4 = P.rad[slot];
+        const rb_v3 L = rb_mk3(L4.x, L4.y, L4.z) + sky_color(rayDir) * T;
+        // nothing else can add to this path (a miss casts no shadow ray, and the previous hit's shadow ray was resolved
+        // in the previous wave), so the path ends here: about 60 % of all path ends skip endQ and k_finish.
+        // Rays traced by this path: one per shaded segment plus the one that missed.
+        finish_slot(P, slot, L, st, segments + 1u, cntNext, parity, acc);
+        return;
+    }
+
+    const uint4 h = P.hit[slot];
+    const bool prevInside = (flags & F_INSIDE) != 0u;
+    ShadeOut o;
+    Surf s;
+    const RB200InstanceProperties* props;
+    bool didRefract;
+    eval_hit<MAT>(P, h, rayOrigin, rayDir, prevInside, rng, accDist, o, s, props, didRefract);
 
     // ---- what raygen does after traceRayEXT returns (rgen.glsl:124-181) ----
     P.rayO[slot] = make_float4(o.newO.x, o.newO.y, o.newO.z, 0.f);
@@ -1136,6 +1150,110 @@ int bench_trace(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const fl
     if (ce != cudaSuccess) { set_error("bench_trace: %s", cudaGetErrorString(ce)); return RB200_ERR_CUDA; }
     if (outMs) *outMs = ms / (float)reps;
     if (outChecksum) *outChecksum = sum;
+    return RB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rb200_shade_hits: ONE traceRayEXT + closest-hit shader invocation per caller-supplied ray — the payload the shader
+// leaves behind (shaderCommon.h.glsl payload struct), for parity against the reference's compiled *.rchit.spv
+// (tests/golden/spirv_hits.npz). The traversal kernel finds the hits, k_shade_hits runs the very eval_hit<MAT> the
+// wave loop runs.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_hits_for_shading(const WideNode* nodes, const TriRecord* tris, uint32_t n,
+                                                            const float4* __restrict__ o, const float4* __restrict__ d,
+                                                            uint4* __restrict__ hits, uint32_t* __restrict__ material, uint32_t* cursor) {
+    uint32_t nv = 0, tt = 0;
+    extern __shared__ __align__(16) unsigned char rb_dyn_smem[];
+    WarpShared<false>* ws = reinterpret_cast<WarpShared<false>*>(rb_dyn_smem);
+    trace_queue<false, false>(
+        nodes, tris, n, cursor,
+        [&](uint32_t i, rb_v3& ro, rb_v3& rd, float& tmax) {
+            const float4 o4 = o[i], d4 = d[i];
+            ro = rb_mk3(o4.x, o4.y, o4.z); rd = rb_mk3(d4.x, d4.y, d4.z); tmax = 10000.0f;
+        },
+        [&](uint32_t i, const RayHit& h) {
+            if (h.tri == 0xFFFFFFFFu) { material[i] = 4u; hits[i] = make_uint4(0u, 0u, 0u, 0u); return; }
+            const float4* tp = reinterpret_cast<const float4*>(tris + h.tri);
+            const uint32_t iw = __float_as_uint(__ldg(tp + 1).w);
+#if RB_SHADE_RECORDS
+            const uint32_t prim = h.tri;
+#else
+            const uint32_t prim = __float_as_uint(__ldg(tp).w);
+#endif
+            hits[i] = make_uint4(__float_as_uint(h.b1), __float_as_uint(h.b2), prim, iw & TRI_INST_MASK);
+            material[i] = iw >> 30;
+        },
+        nv, tt, ws[threadIdx.x >> 5]);
+}
+
+__global__ void __launch_bounds__(RB_SHADE_BLOCK) k_shade_hits(WaveParams P, uint32_t n, const float4* __restrict__ o4, const float4* __restrict__ d4,
+                                                              const uint4* __restrict__ hits, const uint32_t* __restrict__ material,
+                                                              const uint32_t* __restrict__ rngIn, const uint32_t* __restrict__ insideIn,
+                                                              const float* __restrict__ accIn, RB200ShadeResult* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RB200ShadeResult r;
+    memset(&r, 0, sizeof(r));
+    const uint32_t m = material[i];
+    r.material = m;
+    r.rngState = rngIn[i];
+    r.accumulatedDistance = accIn[i];
+    if (m > 3u) { out[i] = r; return; }          // miss: the payload is the miss shader's business
+    const rb_v3 ro = rb_mk3(o4[i].x, o4[i].y, o4[i].z), rd = rb_mk3(d4[i].x, d4[i].y, d4[i].z);
+    const bool prevInside = insideIn[i] != 0u;
+    uint32_t rng = rngIn[i];
+    float acc = accIn[i];
+    ShadeOut so;
+    Surf s;
+    const RB200InstanceProperties* props;
+    bool didRefract;
+    const uint4 h = hits[i];
+    if (m == 0u) eval_hit<0>(P, h, ro, rd, prevInside, rng, acc, so, s, props, didRefract);
+    else if (m == 1u) eval_hit<1>(P, h, ro, rd, prevInside, rng, acc, so, s, props, didRefract);
+    else if (m == 2u) eval_hit<2>(P, h, ro, rd, prevInside, rng, acc, so, s, props, didRefract);
+    else eval_hit<3>(P, h, ro, rd, prevInside, rng, acc, so, s, props, didRefract);
+    r.color[0] = so.color.x; r.color[1] = so.color.y; r.color[2] = so.color.z;
+    r.albedo[0] = so.albedo.x; r.albedo[1] = so.albedo.y; r.albedo[2] = so.albedo.z;
+    r.origin[0] = so.newO.x; r.origin[1] = so.newO.y; r.origin[2] = so.newO.z;
+    r.direction[0] = so.newD.x; r.direction[1] = so.newD.y; r.direction[2] = so.newD.z;
+    r.emission[0] = so.emission.x; r.emission[1] = so.emission.y; r.emission[2] = so.emission.z;
+    r.normal[0] = so.normal.x; r.normal[1] = so.normal.y; r.normal[2] = so.normal.z;
+    r.pdf = so.pdf;
+    r.accumulatedDistance = acc;
+    r.rngState = rng;
+    r.flags = 1u | (so.skip ? 2u : 0u) | (so.inside ? 4u : 0u);
+    out[i] = r;
+}
+
+int shade_hits(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* o, const float* d, const uint32_t* rng,
+               const uint32_t* inside, const float* acc, RB200ShadeResult* out) {
+    if (n == 0) return RB200_OK;
+    int rc = sync_engines(ctx);
+    if (rc != RB200_OK) return rc;
+    std::vector<float> tmax(n, 10000.0f);
+    DeviceBuf dO, dD, dHits, dMat, dRng, dIn, dAcc, dOut;
+    if ((rc = upload_rays(ctx, n, o, d, tmax.data(), dO, dD)) != RB200_OK) return rc;
+    RB_CUDA(dHits.alloc((size_t)n * sizeof(uint4))); RB_CUDA(dMat.alloc((size_t)n * 4)); RB_CUDA(dRng.alloc((size_t)n * 4));
+    RB_CUDA(dIn.alloc((size_t)n * 4)); RB_CUDA(dAcc.alloc((size_t)n * 4)); RB_CUDA(dOut.alloc((size_t)n * sizeof(RB200ShadeResult)));
+    cudaStream_t s = ctx->stream;
+    RB_CUDA(cudaMemcpyAsync(dRng.p, rng, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    RB_CUDA(cudaMemcpyAsync(dIn.p, inside, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    RB_CUDA(cudaMemcpyAsync(dAcc.p, acc, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    RB_CUDA(cudaMemsetAsync(ctx->queryCursor, 0, sizeof(uint32_t), s));
+    constexpr size_t smClosest = sizeof(WarpShared<false>) * (BLOCK / 32);
+    RB_CUDA(cudaFuncSetAttribute(k_hits_for_shading, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smClosest));
+    const int grid = (int)std::min<uint64_t>((n + BLOCK - 1) / BLOCK, (uint64_t)ctx->gQuery[0]);
+    k_hits_for_shading<<<grid, BLOCK, smClosest, s>>>(scene->dev.nodes, scene->dev.tris, n, static_cast<float4*>(dO.p), static_cast<float4*>(dD.p),
+                                                      static_cast<uint4*>(dHits.p), static_cast<uint32_t*>(dMat.p), ctx->queryCursor);
+    WaveParams P = ctx->wp;
+    P.S = scene->dev;
+    k_shade_hits<<<(n + RB_SHADE_BLOCK - 1) / RB_SHADE_BLOCK, RB_SHADE_BLOCK, 0, s>>>(
+        P, n, static_cast<float4*>(dO.p), static_cast<float4*>(dD.p), static_cast<uint4*>(dHits.p), static_cast<uint32_t*>(dMat.p),
+        static_cast<uint32_t*>(dRng.p), static_cast<uint32_t*>(dIn.p), static_cast<float*>(dAcc.p), static_cast<RB200ShadeResult*>(dOut.p));
+    ctx->launches += 2;
+    RB_CUDA(cudaGetLastError());
+    RB_CUDA(cudaMemcpyAsync(out, dOut.p, (size_t)n * sizeof(RB200ShadeResult), cudaMemcpyDeviceToHost, s));
+    RB_CUDA(cudaStreamSynchronize(s));
     return RB200_OK;
 }
 

@@ -120,23 +120,32 @@ def loadGltf(filepath):
     return Asset(doc, buffers, base_dir)
 
 
+def _checked(v, what, index):
+    """Untrusted JSON number -> int in [0, 2^31): negative or huge counts / offsets / strides are refused (host/gltf.cpp
+    applies the same rule)."""
+    if isinstance(v, bool) or not isinstance(v, int) or v < 0 or v > 0x7FFFFFFF:
+        raise RuntimeError("Failed to parse glTF: %s of accessor %d out of range" % (what, index))
+    return v
+
+
 def _read_accessor(asset, index, want_float=True):
     """Accessor -> (count, ncomp) array. Floats as stored; integers either raw (indices) or de-quantised to fp32:
     normalized -> c / max (signed: max(c / max, -1)), as the glTF specification and KHR_mesh_quantization define."""
     doc = asset.doc
-    acc = doc["accessors"][index]
+    acc = doc["accessors"][_checked(index, "index", index)]
     dt, size = _COMPONENT[acc["componentType"]]
     ncomp = _NCOMP[acc["type"]]
-    count = int(acc["count"])
+    count = _checked(acc["count"], "count", index)
     if "bufferView" not in acc:
         out = np.zeros((count, ncomp), dt)
     else:
-        bv = doc["bufferViews"][acc["bufferView"]]
-        buf = asset.buffers[bv["buffer"]]
-        start = int(bv.get("byteOffset", 0)) + int(acc.get("byteOffset", 0))
-        stride = int(bv.get("byteStride", 0)) or size * ncomp
+        bv = doc["bufferViews"][_checked(acc["bufferView"], "bufferView", index)]
+        buf = asset.buffers[_checked(bv["buffer"], "buffer", index)]
+        voff = _checked(bv.get("byteOffset", 0), "bufferView.byteOffset", index)
+        start = voff + _checked(acc.get("byteOffset", 0), "byteOffset", index)
+        stride = _checked(bv.get("byteStride", 0), "byteStride", index) or size * ncomp
         need = start + (count - 1) * stride + size * ncomp if count else start
-        if need > len(buf) or need > int(bv.get("byteOffset", 0)) + int(bv["byteLength"]) + 0:
+        if need > len(buf) or need > voff + _checked(bv["byteLength"], "bufferView.byteLength", index):
             raise RuntimeError("Failed to parse glTF: accessor %d reads past its buffer view" % index)
         raw = np.frombuffer(buf, np.uint8)
         idx = start + np.arange(count, dtype=np.int64)[:, None] * stride + np.arange(size * ncomp, dtype=np.int64)[None, :]

@@ -319,6 +319,22 @@ int type_components(const std::string& t) {
     throw std::runtime_error("Failed to parse glTF: unknown accessor type " + t);
 }
 
+// Counts, offsets and strides come from untrusted JSON: every one is range-checked before it is used in address
+// arithmetic (a negative or huge value would wrap the size_t expressions below), and the bounds tests are written so
+// that they cannot overflow. 2^31 elements / bytes is far beyond anything a scene for this renderer holds.
+size_t checked_size(long v, const char* what, long index) {
+    if (v < 0 || v > 0x7FFFFFFFL)
+        throw std::runtime_error(std::string("Failed to parse glTF: ") + what + " of accessor " + std::to_string(index) + " out of range");
+    return size_t(v);
+}
+// true iff `count` elements of `elem` bytes, `stride` apart, starting at `start`, lie inside [0, limit)
+bool range_fits(size_t start, size_t count, size_t stride, size_t elem, size_t limit) {
+    if (count == 0) return start <= limit;
+    if (start > limit || elem > limit - start) return false;
+    if (stride == 0) return count == 1;
+    return (count - 1) <= (limit - start - elem) / stride;
+}
+
 struct AccessorView {
     const uint8_t* base = nullptr;   // nullptr: accessor without a buffer view (all zeros)
     size_t stride = 0, count = 0;
@@ -329,25 +345,27 @@ struct AccessorView {
 };
 
 AccessorView open_accessor(const Asset& a, long index) {
+    if (index < 0) throw std::runtime_error("Failed to parse glTF: negative accessor index");
     const Json& acc = a.doc.at("accessors").at(size_t(index));
     AccessorView v;
     v.ctype = acc.at("componentType").integer();
     v.csize = component_size(v.ctype);
     v.ncomp = type_components(acc.at("type").string());
-    v.count = size_t(acc.at("count").integer());
+    v.count = checked_size(acc.at("count").integer(), "count", index);
     v.normalized = acc.bool_or("normalized", false);
     if (const Json* bvi = acc.find("bufferView")) {
-        const Json& bv = a.doc.at("bufferViews").at(size_t(bvi->integer()));
-        const size_t bi = size_t(bv.at("buffer").integer());
+        const Json& bv = a.doc.at("bufferViews").at(checked_size(bvi->integer(), "bufferView", index));
+        const size_t bi = checked_size(bv.at("buffer").integer(), "buffer", index);
         if (bi >= a.buffers.size()) throw std::runtime_error("Failed to parse glTF: buffer index out of range");
         const std::vector<uint8_t>& buf = a.buffers[bi];
-        const size_t viewOff = size_t(bv.integer_or("byteOffset", 0));
-        const size_t start = viewOff + size_t(acc.integer_or("byteOffset", 0));
+        const size_t viewOff = checked_size(bv.integer_or("byteOffset", 0), "bufferView.byteOffset", index);
+        const size_t viewLen = checked_size(bv.at("byteLength").integer(), "bufferView.byteLength", index);
+        const size_t start = viewOff + checked_size(acc.integer_or("byteOffset", 0), "byteOffset", index);
         const size_t elem = size_t(v.csize) * size_t(v.ncomp);
-        const long st = bv.integer_or("byteStride", 0);
-        v.stride = st ? size_t(st) : elem;
-        const size_t need = v.count ? start + (v.count - 1) * v.stride + elem : start;
-        if (need > buf.size() || need > viewOff + size_t(bv.at("byteLength").integer()))
+        const size_t st = checked_size(bv.integer_or("byteStride", 0), "byteStride", index);
+        v.stride = st ? st : elem;
+        const size_t limit = std::min(buf.size(), viewOff + viewLen);       // both terms < 2^32: no overflow
+        if (!range_fits(start, v.count, v.stride, elem, limit))
             throw std::runtime_error("Failed to parse glTF: accessor " + std::to_string(index) + " reads past its buffer view");
         v.base = buf.data() + start;
     }
@@ -357,18 +375,20 @@ AccessorView open_accessor(const Asset& a, long index) {
         const size_t elem = size_t(v.csize) * size_t(v.ncomp);
         auto packed = std::make_shared<std::vector<uint8_t>>(v.count * elem, uint8_t(0));
         if (v.base) for (size_t i = 0; i < v.count; i++) std::memcpy(packed->data() + i * elem, v.base + i * v.stride, elem);
-        const size_t n = size_t(sp->at("count").integer());
+        const size_t n = checked_size(sp->at("count").integer(), "sparse.count", index);
         const Json& si = sp->at("indices");
         const Json& sv = sp->at("values");
         const long ict = si.at("componentType").integer();
         if (ict != 5121 && ict != 5123 && ict != 5125) throw std::runtime_error("Failed to parse glTF: bad sparse index type");
         const size_t isize = size_t(component_size(ict));
         auto view = [&](const Json& ref, size_t bytes) -> const uint8_t* {
-            const Json& bv = a.doc.at("bufferViews").at(size_t(ref.at("bufferView").integer()));
-            const size_t bi = size_t(bv.at("buffer").integer());
+            const Json& bv = a.doc.at("bufferViews").at(checked_size(ref.at("bufferView").integer(), "sparse bufferView", index));
+            const size_t bi = checked_size(bv.at("buffer").integer(), "buffer", index);
             if (bi >= a.buffers.size()) throw std::runtime_error("Failed to parse glTF: buffer index out of range");
-            const size_t viewOff = size_t(bv.integer_or("byteOffset", 0)), start = viewOff + size_t(ref.integer_or("byteOffset", 0));
-            if (start + bytes > a.buffers[bi].size() || start + bytes > viewOff + size_t(bv.at("byteLength").integer()))
+            const size_t viewOff = checked_size(bv.integer_or("byteOffset", 0), "bufferView.byteOffset", index);
+            const size_t start = viewOff + checked_size(ref.integer_or("byteOffset", 0), "sparse byteOffset", index);
+            const size_t limit = std::min(a.buffers[bi].size(), viewOff + checked_size(bv.at("byteLength").integer(), "bufferView.byteLength", index));
+            if (!range_fits(start, 1, 0, bytes, limit))
                 throw std::runtime_error("Failed to parse glTF: accessor " + std::to_string(index) + " reads past its buffer view");
             return a.buffers[bi].data() + start;
         };

@@ -191,6 +191,47 @@ def test_errors_match_the_reference_messages(host, rb, gl, tmp_path):
     both(str(tmp_path / "v1.glb"), "unsupported GLB version")
 
 
+def test_hostile_numeric_fields_are_refused_not_trusted(host, rb, gl, tmp_path):
+    """Counts, offsets, strides and lengths are untrusted JSON numbers: negative or huge values (which would wrap the
+    importer's size_t address arithmetic — count = -2^63 once passed the bounds test and wrote out of bounds) must be
+    refused with an error by the C++ importer, whatever field carries them; the Python importer must raise as well."""
+    import base64
+    host.rbhost_tables_gltf.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    uv = np.zeros((3, 2), np.float32)
+    blob = tri.tobytes() + uv.tobytes()
+    uri = "data:application/octet-stream;base64," + base64.b64encode(blob).decode()
+
+    def doc():
+        return {"asset": {"version": "2.0"}, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+                "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "NORMAL": 0, "TEXCOORD_0": 1}}]}],
+                "buffers": [{"byteLength": len(blob), "uri": uri}],
+                "bufferViews": [{"buffer": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 24}],
+                "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"},
+                              {"bufferView": 1, "componentType": 5126, "count": 3, "type": "VEC2"}]}
+    h = C.c_void_p()
+    good = _write_gltf(tmp_path, doc(), "good.gltf")
+    assert host.rbhost_tables_gltf(good.encode(), 0, C.byref(h)) == 0, err(host)
+    host.rbhost_tables_free(h)
+    hostile = [-1, -2 ** 63, 2 ** 63 + 1024, 2 ** 32, 2 ** 31, 2 ** 62, -2 ** 31]
+    cases = 0
+    for where, field in (("accessors", "count"), ("accessors", "byteOffset"), ("bufferViews", "byteOffset"),
+                         ("bufferViews", "byteStride"), ("bufferViews", "byteLength"), ("accessors", "bufferView")):
+        for idx in (0, 1):
+            for v in hostile:
+                d = doc()
+                d[where][idx][field] = v
+                path = _write_gltf(tmp_path, d, "hostile.gltf")
+                rc = host.rbhost_tables_gltf(path.encode(), 0, C.byref(h))
+                if rc == 0:      # only harmless values may load (none of these are)
+                    host.rbhost_tables_free(h)
+                assert rc != 0 and "Failed to parse glTF" in err(host), (where, field, idx, v, err(host))
+                with pytest.raises(Exception):
+                    gl.loadScene(path).build()
+                cases += 1
+    assert cases == 84
+
+
 @pytest.mark.filterwarnings("ignore:falling back to UV")
 def test_oracle_renders_the_imported_scene(ol, rb, gl, tmp_path):
     """The imported tables are a valid scene for the path tracer: finite image, light reaches the floor."""

@@ -283,21 +283,8 @@ def _np_random_emissive_point(t, rb, pc, state):
 
 
 def _two_light_scene(rb, emitters_first=True):
-    """Two emitters. nee.h.glsl:97-105 addresses an emitter's triangles by their position in the CONCATENATED triangle CDF
-    (indices[3 * cdfIndex + indexOffset]), so the second emitter (CDF slots 2..49) reads 2 triangles past its own mesh —
-    with the emitters first those slots still lie inside the index buffer (the box's triangles, moved by the emitter's
-    transform: upstream's behaviour, restated literally); with the emitters last they lie past its end."""
-    cfg = rb.configs
-    s = rb.Scene()
-    if not emitters_first:
-        s.addObject(rb.meshes.cornell_box(), cfg.IDENT, rb.Material(**cfg.CORNELL_WALL))
-    s.addObject(rb.meshes.cornell_light(), cfg.IDENT, rb.Material(**cfg.LIGHT))
-    # a second, differently sized, double-sided and differently coloured emitter with a non-trivial transform
-    M = cfg.compose(cfg.translate((-0.5, 0.9, -0.2)), cfg.scale((0.5, 1.0, 0.7)))
-    s.addObject(rb.meshes.uv_sphere(8, 4, radius=0.2), M, rb.Material(materialIdx=0, albedo=(1, 1, 1), emission=(2.0, 7.0, 4.0), cullBackface=False))
-    if emitters_first:
-        s.addObject(rb.meshes.cornell_box(), cfg.IDENT, rb.Material(**cfg.CORNELL_WALL))
-    return s.build(require_emitter=True)
+    """Two emitters (rb.configs.two_lights): see there for how nee.h.glsl:97-105 addresses their triangles."""
+    return rb.configs.two_lights(8, 8, emitters_first=emitters_first).tables
 
 
 def test_light_sampling_past_the_index_buffer_is_refused(ol, rb):
