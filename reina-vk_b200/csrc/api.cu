@@ -4,6 +4,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <cmath>
 
 namespace rb200 {
 
@@ -389,6 +390,9 @@ RB200_API int rb200_render_batch(RB200Context* ctx, const RB200Scene* scene, con
     RB_CUDA(cudaSetDevice(ctx->device));
     const int rc = render_batch(ctx, scene, pc);
     if (rc != RB200_OK) return rc;
+    // samples are clamped to [0, directClamp] and NaN samples are dropped: the image stays finite unless the clamp is not
+    if (!std::isfinite(pc->directClamp)) ctx->hdrMayBeNonFinite = true;
+    else if (pc->sampleBatch == 0u && !(ctx->flags & RB200_FLAG_ACCUM_SUM)) ctx->hdrMayBeNonFinite = false;    // batch 0 overwrites the image
     // completion marker of this batch on the front-end stream (which waits for the batch's fold)
     cudaEvent_t e;
     if (!ctx->batchEventPool.empty()) { e = ctx->batchEventPool.back(); ctx->batchEventPool.pop_back(); }
@@ -525,6 +529,12 @@ RB200_API int rb200_write_hdr(RB200Context* ctx, const float* rgba32f) {
     if (!ctx || !rgba32f) { set_error("null argument"); return RB200_ERR_INVALID_ARGUMENT; }
     RB_CUDA(cudaSetDevice(ctx->device));
     RB_CUDA(cudaMemcpyAsync(ctx->wp.image, rgba32f, (size_t)ctx->width * ctx->height * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    // NaN / infinite pixels change how far a pixel reaches in the bloom passes (post.cu, k_blur_exact): note whether there are any
+    bool nonFinite = false;
+    const size_t n = (size_t)ctx->width * ctx->height;
+    for (size_t i = 0; i < n && !nonFinite; i++)
+        nonFinite = !std::isfinite(rgba32f[4 * i]) || !std::isfinite(rgba32f[4 * i + 1]) || !std::isfinite(rgba32f[4 * i + 2]);
+    ctx->hdrMayBeNonFinite = nonFinite;
     RB_CUDA(cudaStreamSynchronize(ctx->stream));
     return RB200_OK;
 }

@@ -206,6 +206,8 @@ struct RB200Context {
     float4 *ping = nullptr, *pong = nullptr;   // bloom work images
     float4* resolved = nullptr;                // rb200_present_sum: mean image of a SUM image (allocated on first use)
     uchar4* ldr = nullptr;
+    bool hdrMayBeNonFinite = false;            // the HDR image may hold NaN / infinities (rb200_write_hdr of such an image, or a
+                                               // non-finite directClamp): post-processing then runs the shader's loops as written
     uint32_t* queryCursor = nullptr;           // cursor of the query kernels (rb200_trace_*)
     RB200Stats last{}, cumulative{};
     unsigned long long* statsSnap = nullptr;   // cumulative device counters (a lane's per-batch counters are added by

@@ -10,6 +10,10 @@
 // the colour sum nor weightSum, so only the +-R taps with non-zero weight are visited — in the same ascending
 // order as the shader's loop, which keeps the fp32 sums bit-identical to the oracle.
 // Tiles are staged in shared memory with 128-bit loads; thresholded / out-of-image taps are staged as zeros.
+// Every thread visits only the span of NON-ZERO pixels of its tap window (an occupancy bit mask of the staged tile is built
+// while staging): most of a frame is zero after the threshold, a zero pixel contributes +-0 to sums that start at +0, so
+// the result is what the full loops would produce, bit for bit (NaN and infinities count as non-zero). With it the two
+// blur passes read and write each image once and approach the HBM bound like combine + tonemap.
 #include "context.cuh"
 
 namespace rb200 {
@@ -29,20 +33,23 @@ __device__ __forceinline__ float gauss(float x, float sigma) { return rb_exp(-x 
 // Each thread produces BLUR_OUT adjacent outputs along the blur axis: a staged pixel is loaded from shared memory once
 // and used by up to BLUR_OUT outputs (tap i of output o is pixel t = i + o), with the weights sliding through
 // registers. Every output still adds its taps in ascending order, one product and one add per channel, so the sums
-// are the ones the shader's loop produces; weightSum is the same sequence for every output and is formed once.
+// are the ones the shader's loop produces. Only the pixels t0 .. t1 of the thread's window are visited — the span of its
+// non-zero pixels: a zero pixel contributes +-0 to sums that start at +0, which never changes them (x + 0 = x, and
+// +0 + -0 = +0), so skipping it is exact. weightSum does not depend on the pixel and comes from the host.
 // `tile` points at tap 0 of output 0, consecutive pixels along the axis are `stride` entries apart.
-__device__ __forceinline__ void blur_outputs(const float* __restrict__ wts, const float4* __restrict__ tile, int stride, int R,
-                                             float (&cr)[BLUR_OUT], float (&cg)[BLUR_OUT], float (&cb)[BLUR_OUT], float& ws) {
+__device__ __forceinline__ void blur_outputs(const float* __restrict__ wts, const float4* __restrict__ tile, int stride, int R, int t0, int t1,
+                                             float (&cr)[BLUR_OUT], float (&cg)[BLUR_OUT], float (&cb)[BLUR_OUT]) {
     const int n = 2 * R + 1;
     float w[BLUR_OUT];
 #pragma unroll
-    for (int o = 0; o < BLUR_OUT; o++) { w[o] = 0.f; cr[o] = 0.f; cg[o] = 0.f; cb[o] = 0.f; }
-    ws = 0.f;
-    for (int t = 0; t < n + BLUR_OUT - 1; t++) {
+    for (int o = 0; o < BLUR_OUT; o++) { cr[o] = 0.f; cg[o] = 0.f; cb[o] = 0.f; }
+    // state of the sliding window as if tap t0 - 1 had just been processed: w[o] = wts[t0 - 1 - o]
+#pragma unroll
+    for (int o = 0; o < BLUR_OUT; o++) { const int i = t0 - 1 - o; w[o] = (i >= 0 && i < n) ? wts[i] : 0.f; }
+    for (int t = t0; t <= t1; t++) {
 #pragma unroll
         for (int o = BLUR_OUT - 1; o > 0; o--) w[o] = w[o - 1];
         w[0] = t < n ? wts[t] : 0.f;
-        if (t < n) ws += w[0];
         const float4 p = tile[t * stride];
         if (t >= BLUR_OUT - 1 && t < n) {          // the tap is valid for every output of this thread
 #pragma unroll
@@ -57,62 +64,123 @@ __device__ __forceinline__ void blur_outputs(const float* __restrict__ wts, cons
     }
 }
 
+// first and last set bit of mask[] within [lo, hi) (bit i of word i >> 5); first > last when none is set
+__device__ __forceinline__ void nonzero_span(const uint32_t* __restrict__ mask, int lo, int hi, int& first, int& last) {
+    first = hi; last = lo - 1;
+    for (int w = lo >> 5; w <= (hi - 1) >> 5; w++) {
+        uint32_t m = mask[w];
+        if (w == (lo >> 5)) m &= 0xFFFFFFFFu << (lo & 31);
+        if (w == ((hi - 1) >> 5) && (hi & 31)) m &= 0xFFFFFFFFu >> (32 - (hi & 31));
+        if (m) {
+            first = min(first, w * 32 + (__ffs(m) - 1));
+            last = max(last, w * 32 + 31 - __clz(m));
+        }
+    }
+}
+
 __device__ __forceinline__ float4 blur_resolve(float cr, float cg, float cb, float ws) {
     if (ws < 0.0001f) { cr = cg = cb = 0.f; } else { cr /= ws; cg /= ws; cb /= ws; }
     return make_float4(cr, cg, cb, 1.f);
 }
 
+// Blur along x with the threshold. Shared memory: weights | occupancy mask of the staged row segment | the segment.
 __global__ void __launch_bounds__(BX_THREADS) k_blur_x(const float4* __restrict__ in, float4* __restrict__ out, int W, int H,
-                                                       int R, float sigma, float threshold) {
+                                                       int R, float sigma, float threshold, float ws) {
     extern __shared__ float4 smem[];
+    const int TW = BX_TILE + 2 * R, MW = (TW + 31) / 32;
     float* wts = reinterpret_cast<float*>(smem);              // 2R+1 weights (padded to a multiple of 4 floats)
-    float4* tile = smem + ((2 * R + 1 + 3) / 4);              // BX_TILE + 2R pixels
+    uint32_t* mask = reinterpret_cast<uint32_t*>(smem + ((2 * R + 1 + 3) / 4));     // bit i: staged pixel i is non-zero
+    float4* tile = smem + ((2 * R + 1 + 3) / 4) + ((MW + 3) / 4);                   // BX_TILE + 2R pixels
     const int y = blockIdx.y;
     const int x0 = blockIdx.x * BX_TILE;
     for (int i = threadIdx.x; i <= 2 * R; i += BX_THREADS) wts[i] = gauss((float)(i - R), sigma);
-    for (int i = threadIdx.x; i < BX_TILE + 2 * R; i += BX_THREADS) {
-        const int x = x0 - R + i;
+    const int lane = threadIdx.x & 31;
+    for (int base = (int)(threadIdx.x & ~31u); base < TW; base += BX_THREADS) {      // a warp stages 32 consecutive pixels
+        const int i = base + lane, x = x0 - R + i;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (x >= 0 && x < W) {
+        if (i < TW && x >= 0 && x < W) {
             p = in[(size_t)y * W + x];
             const float lum = p.x * 0.299f + p.y * 0.587f + p.z * 0.114f;
             if (lum < threshold) p = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        tile[i] = p;
+        if (i < TW) tile[i] = p;
+        const uint32_t b = __ballot_sync(0xffffffffu, (p.x != 0.f) | (p.y != 0.f) | (p.z != 0.f));
+        if (lane == 0) mask[base >> 5] = b;
     }
     __syncthreads();
     const int xo = x0 + (int)threadIdx.x * BLUR_OUT;
     if (xo >= W) return;
-    float cr[BLUR_OUT], cg[BLUR_OUT], cb[BLUR_OUT], ws;
-    blur_outputs(wts, tile + threadIdx.x * BLUR_OUT, 1, R, cr, cg, cb, ws);
+    const int off = (int)threadIdx.x * BLUR_OUT, n = 2 * R + 1;
+    int first, last;
+    nonzero_span(mask, off, off + n + BLUR_OUT - 1, first, last);
+    float cr[BLUR_OUT], cg[BLUR_OUT], cb[BLUR_OUT];
+    if (first > last) {
+#pragma unroll
+        for (int o = 0; o < BLUR_OUT; o++) { cr[o] = 0.f; cg[o] = 0.f; cb[o] = 0.f; }
+    } else blur_outputs(wts, tile + off, 1, R, first - off, last - off, cr, cg, cb);
 #pragma unroll
     for (int o = 0; o < BLUR_OUT; o++)
         if (xo + o < W) out[(size_t)y * W + xo + o] = blur_resolve(cr[o], cg[o], cb[o], ws);
 }
 
+// Blur along y. Shared memory: weights | per-column occupancy masks of the staged rows | (BY_H + 2R) rows x BY_W.
 __global__ void __launch_bounds__(BY_THREADS) k_blur_y(const float4* __restrict__ in, float4* __restrict__ out, int W, int H,
-                                                       int R, float sigma) {
+                                                       int R, float sigma, float ws) {
     extern __shared__ float4 smem[];
+    const int rows = BY_H + 2 * R, MW = (rows + 31) / 32;
     float* wts = reinterpret_cast<float*>(smem);
-    float4* tile = smem + ((2 * R + 1 + 3) / 4);              // (BY_H + 2R) rows x BY_W
+    uint32_t* mask = reinterpret_cast<uint32_t*>(smem + ((2 * R + 1 + 3) / 4));     // [BY_W][MW]: bit r of column c
+    float4* tile = smem + ((2 * R + 1 + 3) / 4) + ((BY_W * MW + 3) / 4);
     const int x0 = blockIdx.x * BY_W, y0 = blockIdx.y * BY_H;
     const int tx = threadIdx.x % BY_W, tg = threadIdx.x / BY_W;     // column, group of BLUR_OUT rows
     for (int i = threadIdx.x; i <= 2 * R; i += BY_THREADS) wts[i] = gauss((float)(i - R), sigma);
-    const int rows = BY_H + 2 * R;
+    for (int i = threadIdx.x; i < BY_W * MW; i += BY_THREADS) mask[i] = 0u;
+    __syncthreads();
     for (int r = tg; r < rows; r += BY_THREADS / BY_W) {
         const int y = y0 - R + r, x = x0 + tx;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         if (y >= 0 && y < H && x < W) p = in[(size_t)y * W + x];
+        if ((p.x != 0.f) | (p.y != 0.f) | (p.z != 0.f)) atomicOr(&mask[tx * MW + (r >> 5)], 1u << (r & 31));
         tile[r * BY_W + tx] = p;
     }
     __syncthreads();
     const int x = x0 + tx, yo = y0 + tg * BLUR_OUT;
     if (x >= W || yo >= H) return;
-    float cr[BLUR_OUT], cg[BLUR_OUT], cb[BLUR_OUT], ws;
-    blur_outputs(wts, tile + (tg * BLUR_OUT) * BY_W + tx, BY_W, R, cr, cg, cb, ws);
+    const int off = tg * BLUR_OUT, n = 2 * R + 1;
+    int first, last;
+    nonzero_span(mask + tx * MW, off, off + n + BLUR_OUT - 1, first, last);
+    float cr[BLUR_OUT], cg[BLUR_OUT], cb[BLUR_OUT];
+    if (first > last) {
+#pragma unroll
+        for (int o = 0; o < BLUR_OUT; o++) { cr[o] = 0.f; cg[o] = 0.f; cb[o] = 0.f; }
+    } else blur_outputs(wts, tile + off * BY_W + tx, BY_W, R, first - off, last - off, cr, cg, cb);
 #pragma unroll
     for (int o = 0; o < BLUR_OUT; o++)
         if (yo + o < H) out[(size_t)(yo + o) * W + x] = blur_resolve(cr[o], cg[o], cb[o], ws);
+}
+
+// blurCommon.h.glsl:15-56 as written: one thread per pixel, every one of the 2k+1 taps, straight from global memory. Only
+// used when the image may hold NaN or infinite values (RB200Context::hdrMayBeNonFinite): a tap whose weight underflowed
+// to 0 still turns a NaN or an infinity into NaN in the shader's loop, so the window of non-zero weights the tiled kernels
+// visit is not enough there. ax = 1: blur along x with the threshold; ax = 0: along y without.
+__global__ void __launch_bounds__(256) k_blur_exact(const float4* __restrict__ in, float4* __restrict__ out, int W, int H, int k, float sigma,
+                                                    float threshold, int ax) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    float cr = 0.f, cg = 0.f, cb = 0.f, ws = 0.f;
+    for (int i = -k; i <= k; i++) {
+        const float w = gauss((float)i, sigma);
+        ws += w;
+        const int cx = ax ? x + i : x, cy = ax ? y : y + i;
+        if (cx < 0 || cx >= W || cy < 0 || cy >= H) continue;
+        const float4 p = in[(size_t)cy * W + cx];
+        if (ax) {
+            const float lum = p.x * 0.299f + p.y * 0.587f + p.z * 0.114f;
+            if (lum < threshold) continue;
+        }
+        cr += p.x * w; cg += p.y * w; cb += p.z * w;
+    }
+    out[(size_t)y * W + x] = blur_resolve(cr, cg, cb, ws);
 }
 
 // tonemapping.comp.glsl:34-39
@@ -209,14 +277,26 @@ int postprocess(RB200Context* ctx, const RB200BloomPushConsts* bloom, const RB20
     const int kX = (int)(radiusPxX * 3.0f + 0.5f), kY = (int)(radiusPxY * 3.0f + 0.5f);
     const int RX = effective_radius(kX, bloom->radius), RY = effective_radius(kY, bloom->radius);
 
-    const size_t smX = (size_t)(((2 * RX + 1 + 3) / 4) + BX_TILE + 2 * RX) * sizeof(float4);
-    const size_t smY = (size_t)(((2 * RY + 1 + 3) / 4) + (BY_H + 2 * RY) * BY_W) * sizeof(float4);
+    const size_t smX = (size_t)(((2 * RX + 1 + 3) / 4) + (((BX_TILE + 2 * RX + 31) / 32 + 3) / 4) + BX_TILE + 2 * RX) * sizeof(float4);
+    const size_t smY = (size_t)(((2 * RY + 1 + 3) / 4) + ((BY_W * ((BY_H + 2 * RY + 31) / 32) + 3) / 4) + (BY_H + 2 * RY) * BY_W) * sizeof(float4);
+    // weightSum of blurCommon.h.glsl:49-53: every tap's weight added in ascending order (the zero-weight taps beyond +-R do
+    // not change it); the same fp32 sequence the kernels used to form per thread, from the shared elementary layer
+    float wsX = 0.f, wsY = 0.f;
+    for (int i = 0; i <= 2 * RX; i++) { const float x = (float)(i - RX); wsX += rb_exp(-x * x / (2.0f * bloom->radius * bloom->radius)); }
+    for (int i = 0; i <= 2 * RY; i++) { const float x = (float)(i - RY); wsY += rb_exp(-x * x / (2.0f * bloom->radius * bloom->radius)); }
     if (smX > 200 * 1024 || smY > 200 * 1024) { set_error("bloom radius too large for the shared-memory tiles"); return RB200_ERR_INVALID_ARGUMENT; }
     RB_CUDA(cudaFuncSetAttribute(k_blur_x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smX));
     RB_CUDA(cudaFuncSetAttribute(k_blur_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smY));
     dim3 gx((W + BX_TILE - 1) / BX_TILE, H), gy((W + BY_W - 1) / BY_W, (H + BY_H - 1) / BY_H);
-    k_blur_x<<<gx, BX_THREADS, smX, s>>>(rt, ctx->ping, W, H, RX, bloom->radius, bloom->threshold);
-    k_blur_y<<<gy, BY_THREADS, smY, s>>>(ctx->ping, ctx->pong, W, H, RY, bloom->radius);
+    if (ctx->hdrMayBeNonFinite && !source) {
+        // NaN / infinite pixels (only rb200_write_hdr or a non-finite directClamp can bring them in): the shader's loop as written
+        dim3 ge((W + 255) / 256, H);
+        k_blur_exact<<<ge, 256, 0, s>>>(rt, ctx->ping, W, H, kX, bloom->radius, bloom->threshold, 1);
+        k_blur_exact<<<ge, 256, 0, s>>>(ctx->ping, ctx->pong, W, H, kY, bloom->radius, 0.f, 0);
+    } else {
+        k_blur_x<<<gx, BX_THREADS, smX, s>>>(rt, ctx->ping, W, H, RX, bloom->radius, bloom->threshold, wsX);
+        k_blur_y<<<gy, BY_THREADS, smY, s>>>(ctx->ping, ctx->pong, W, H, RY, bloom->radius, wsY);
+    }
     const uint32_t n = (uint32_t)W * (uint32_t)H;
     k_combine_tonemap<<<(n / 4 + 256) / 256, 256, 0, s>>>(rt, ctx->pong, reinterpret_cast<uint32_t*>(ctx->ldr), n,
                                                           bloom->intensity, tm->exposure);

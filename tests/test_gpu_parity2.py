@@ -198,3 +198,33 @@ def test_rays_leaving_a_surface_cuda_hierarchy_and_brute_force_agree(ol, rb):
     assert ((sc.trace_rays(o, d, tm, any_hit=True)["t"] >= 0) == ba).all()
     r.close()
     sc.close()
+
+
+def test_bloom_skips_dark_tiles_without_changing_a_bit(ol, rb):
+    """post.cu skips the tap loops of tiles that hold no non-zero value. A 1080p frame that is dark except for a few
+    bright spots, a NaN, an infinity, a negative zero and a pixel exactly at the threshold (blurCommon.h.glsl:37-44: lum <
+    threshold is dropped) — combined HDR through the LDR bytes identical to the oracle, for two thresholds."""
+    W, H = 1920, 1080
+    rng = np.random.RandomState(4)
+    img = np.zeros((H, W, 4), np.float32)
+    img[..., :3] = rng.uniform(0.0, 0.3, (H, W, 3)).astype(np.float32)          # below any threshold used here
+    img[..., 3] = 1.0
+    for _ in range(40):
+        y, x = rng.randint(0, H), rng.randint(0, W)
+        img[y:y + rng.randint(1, 6), x:x + rng.randint(1, 6), :3] = rng.uniform(1.0, 30.0, 3).astype(np.float32)
+    img[5, 7, :3] = np.nan
+    img[700, 1500, :3] = np.inf
+    img[300, 300, :3] = -0.0
+    img[0, 0, :3] = 50.0
+    img[H - 1, W - 1, :3] = 50.0
+    img[540, 960, :3] = 1.0                                                      # exactly at the threshold 1.0
+    wl = rb.configs.small_mixed(32, 24)
+    r = rb.Renderer(W, H, wl.tables, flags=0)
+    for thr in (1.0, 0.5):
+        bloom = rb.BloomPushConsts(5.0, thr, 0.3)
+        r.write_hdr(img)
+        r.postprocess(bloom=bloom)
+        got = r.read_ldr()
+        want = ol.postprocess(img, bloom=bloom)
+        assert (got == want).all(), thr
+    r.close()
