@@ -29,22 +29,36 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WIDTH, HEIGHT, SPP, BOUNCES = 1920, 1080, 8, 16
+SPP, BOUNCES = 8, 16       # config/config.toml defaults: one step = one batch of 8 samples per pixel, <= 16 segments each
 METRIC = "Mrays/s (primary+bounce+shadow), Stanford Dragon stand-in 1080p"
 
+# BASELINE.json `configs`; c3 is the headline the metric is quoted on, the others are reported by --config for context
+CONFIGS = {
+    "c1": dict(name="C1 Cornell box + light, Lambertian, 800x600, 8 bounces, NEE+MIS (64 spp = 8 steps)",
+               build=lambda rb: rb.configs.cornell(800, 600, samples_per_pixel=SPP, max_bounces=8), bounces=8),
+    "c2": dict(name="C2 bunny stand-in (2 x 81,920 triangles) metal + glass with Beer's-law absorption, 1920x1080, showroom",
+               build=lambda rb: rb.configs.bunny(1920, 1080, levels=6, samples_per_pixel=SPP, max_bounces=BOUNCES), bounces=BOUNCES),
+    "c3": dict(name="C3 dragon stand-in (torus-knot tube + value-noise displacement), Disney BSDF, NEE+MIS, showroom + light panel",
+               build=lambda rb: rb.configs.dragon(1920, 1080, samples_per_pixel=SPP, max_bounces=BOUNCES), bounces=BOUNCES),
+    "c4": dict(name="C4 plant-class scene: 34,000 alpha-tested leaf cards, soil, normal-mapped Disney pot, 1920x1080, showroom",
+               build=lambda rb: rb.configs.plant(1920, 1080, n_leaves=34000, samples_per_pixel=SPP, max_bounces=BOUNCES), bounces=BOUNCES),
+    "c5": dict(name="C5 showroom + Max-Planck stand-in + one sphere per material, bloom + tonemap, 3840x2160",
+               build=lambda rb: rb.configs.showroom_mixed(3840, 2160, levels=6, samples_per_pixel=SPP, max_bounces=BOUNCES), bounces=BOUNCES),
+}
 
-def build_workload(rb, small=False):
+
+def build_workload(rb, small=False, config="c3"):
     if small:   # debugging aid only (RB200_BENCH_SMALL=1); never used for reported numbers
         return rb.configs.dragon(480, 270, n_along=1500, n_ring=16, samples_per_pixel=SPP, max_bounces=BOUNCES)
-    return rb.configs.dragon(WIDTH, HEIGHT, samples_per_pixel=SPP, max_bounces=BOUNCES)
+    return CONFIGS[config]["build"](rb)
 
 
-def config_dict(wl, extra=None):
-    d = {"workload": "C3 dragon stand-in (torus-knot tube + value-noise displacement), Disney BSDF, NEE+MIS, showroom + light panel",
+def config_dict(wl, extra=None, config="c3"):
+    d = {"workload": CONFIGS[config]["name"], "config": config,
          "triangles": wl.tables.num_triangles(), "width": wl.width, "height": wl.height,
-         "samples_per_pixel_per_step": SPP, "max_bounces": BOUNCES,
-         "l2_policy": "inputs larger than L2: every wave sweeps the 2.07M-slot path state (~0.6 GB); the ~55 MB BVH is "
-                      "meant to stay L2-resident"}
+         "samples_per_pixel_per_step": SPP, "max_bounces": CONFIGS[config]["bounces"],
+         "l2_policy": "inputs larger than L2: every wave sweeps the path state of the batches in flight (0.5 GB per 2.07 M "
+                      "slots); the BVH (48 MB for the headline scene) is meant to stay L2-resident"}
     if extra:
         d.update(extra)
     return d
@@ -171,6 +185,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="BASELINE.json config (default: c3, the headline)")
+    ap.add_argument("--no-nee", action="store_true", help="the estimator as shipped upstream (next-event estimation compiled out)")
+    ap.add_argument("--no-as-shipped", action="store_true", help="skip the extra as-shipped (NEE off) measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -190,9 +207,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     rb = importlib.import_module("reina-vk_b200")
-    wl = build_workload(rb, small=bool(os.environ.get("RB200_BENCH_SMALL")))
+    wl = build_workload(rb, small=bool(os.environ.get("RB200_BENCH_SMALL")), config=args.config)
     stream = torch.cuda.Stream()
-    flags = rb.RB200_FLAG_NEE | (rb.RB200_FLAG_ACCUM_SUM if world > 1 else 0)
+    nee_flag = 0 if args.no_nee else rb.RB200_FLAG_NEE
+    flags = nee_flag | (rb.RB200_FLAG_ACCUM_SUM if world > 1 else 0)
     t0 = time.time()
     r = rb.Renderer(wl.width, wl.height, wl.tables, flags=flags, device=local_rank, stream=stream.cuda_stream)
     r.synchronize()
@@ -361,9 +379,10 @@ def main():
                    "scene upload + BVH build happen once (scene_create_s)"}
     r.close()
 
-    out = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
+    metric = METRIC if args.config == "c3" else "Mrays/s (primary+bounce+shadow), " + args.config.upper()
+    out = {"metric": metric, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": Wm,
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic", "config": config_dict(wl, {"parallelism": f"sample-split x{world}", "nee": True,
+           "data": "synthetic", "config": config_dict(wl, config=args.config, extra={"parallelism": f"sample-split x{world}", "nee": not args.no_nee,
                                                            "engines": engines, "lanes_per_engine": lanes,
                                                            "pipeline_fill_steps_before_warmup": fill}),
            "spp_per_s": SPP * K * world / (ms * 1e-3), "rays_per_step": rays / K / world,
@@ -374,7 +393,9 @@ def main():
     if parity_check is not None:
         out["parity_check"] = parity_check
     if rank == 0 and world == 1 and not args.no_roofline:
-        out["roofline"] = roofline(rb, wl, local_rank, stream)
+        out["roofline"] = roofline(rb, wl, local_rank, stream, nee_flag)
+    if rank == 0 and world == 1 and not args.no_nee and not args.no_as_shipped:
+        out["as_shipped"] = as_shipped(rb, wl, local_rank, stream, K)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(rb, wl)
     if rank == 0:
@@ -384,7 +405,34 @@ def main():
     return 0
 
 
-def roofline(rb, wl, device, stream):
+def as_shipped(rb, wl, device, stream, steps):
+    """The same workload with next-event estimation off — the estimator the reference's shipped binaries run
+    (raytrace.rgen.glsl:145-146, skipNEE hard-coded) and the one pinned to its compiled SPIR-V: device-timed Mrays/s."""
+    import torch
+    r = rb.Renderer(wl.width, wl.height, wl.tables, flags=0, device=device, stream=stream.cuda_stream)
+    engines, lanes, _ = r.engine_config()
+    fill = 3 * engines if lanes > 1 else engines
+    with torch.cuda.stream(stream):
+        for i in range(fill + 3):
+            r.render_batch(wl.push_constants(i))
+        r.synchronize()
+        _, c0 = r.stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            r.render_batch(wl.push_constants(fill + 3 + i))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        _, c1 = r.stats()
+    ms = e0.elapsed_time(e1)
+    r.close()
+    rays = c1["extendRays"] - c0["extendRays"]
+    return {"value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms / steps, "rays_per_step": rays / steps,
+            "spp_per_s": SPP * steps / (ms * 1e-3), "nee": False,
+            "note": "flags = 0: no shadow rays, emission picked up by BRDF sampling only; same scene, camera, sample counts"}
+
+
+def roofline(rb, wl, device, stream, nee_flag):
     """Dominant kernel = k_extend (closest-hit traversal). Algorithmic bytes per ray:
     80 * N_node + 48 * N_tri + 32 (ray in) + 16 (hit out), N_node / N_tri measured by a counting build of the same kernel
     on the same batch; time = sum of the kernel's launch durations (CUDA events on the launching stream)."""
@@ -394,23 +442,35 @@ def roofline(rb, wl, device, stream):
     # timing pass (events around every kernel, launches serialised; no counters). Consecutive batches, so that the
     # engine is in its steady state — every launch of the last call carries the rays of all batches in flight — and
     # the launches timed are the launches the bench loop above issues
-    rt = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE | rb.RB200_FLAG_TIME_KERNELS, device=device,
+    rt = rb.Renderer(wl.width, wl.height, wl.tables, flags=nee_flag | rb.RB200_FLAG_TIME_KERNELS, device=device,
                      stream=stream.cuda_stream)
     engines, lanes, _ = rt.engine_config()
     for b in range(3 * engines + 1):
         rt.render_batch(wl.push_constants(1000 + b))
     kt = rt.kernel_times()
     last_t, _ = rt.stats()
+    # post-processing of the frame just rendered: blur X + blur Y + fused combine / tonemap, CUDA events on the stream
+    import torch
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            rt.postprocess()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for _ in range(20):
+            rt.postprocess()
+        p1.record(stream)
+        torch.cuda.synchronize()
+    post_ms = p0.elapsed_time(p1) / 20
     rt.close()
     # counting pass
-    rc = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE | rb.RB200_FLAG_COUNT_BVH, device=device,
+    rc = rb.Renderer(wl.width, wl.height, wl.tables, flags=nee_flag | rb.RB200_FLAG_COUNT_BVH, device=device,
                      stream=stream.cuda_stream)
     rc.render_batch(pc)
     last_c, _ = rc.stats()
     # the bandwidth that bounds an L2-resident traversal is the L2 gather bandwidth; measure it on a
     # table the size of this BVH (independent random reads of whole 80-byte records, warm L2)
     info = rc.bvh_info()
-    table_bytes = int(info["nodeBytes"] + info["triangleBytes"])
+    table_bytes = max(int(info["nodeBytes"] + info["triangleBytes"]), 1 << 20)     # (tiny scenes: the micro-benchmark needs >= 1024 records)
     l2_gather = rc.measure_gather(table_bytes, 80)
     rc.close()
     node_bytes = info["nodeBytes"] / max(1, info["numWideNodes"])
@@ -423,12 +483,32 @@ def roofline(rb, wl, device, stream):
     ext_bytes = bytes_per_ray * kt["extendRays"]
     achieved = ext_bytes / (kt["extendMs"] * 1e-3) / 1e9
     total_ms = kt["generateMs"] + kt["extendMs"] + sum(kt["shadeMs"]) + kt["shadowMs"] + kt["finishMs"]
-    traffic = None
-    try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if present
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["k_extend_dram_bytes_per_launch"]
+    traffic, traffic_source = None, None
+    try:   # per-launch DRAM bytes of the dominant kernel: a STATIC figure from the committed ncu capture, not measured in this run
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        traffic, traffic_source = tj["k_extend_dram_bytes_per_launch"], "static ncu capture " + tj.get("source", "profiles/roofline_traffic.json")
     except Exception:
         pass
-    res.update({"achieved": achieved, "frac": achieved / peak, "traffic": traffic,
+
+    def kernel_entry(items, unit_bytes, ms, what):
+        if not ms or ms <= 0 or not items:
+            return None
+        ach = unit_bytes * items / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "units_per_step": items, "bytes_per_unit": unit_bytes, "ms_per_step": ms, "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "what": what}
+    px = wl.width * wl.height
+    kernels = {
+        "extend": kernel_entry(kt["extendRays"], bytes_per_ray, kt["extendMs"], "node_bytes * nodes/ray + 48 * tris/ray + 32 (ray in) + 16 (hit out), extend rays only"),
+        "shadow": kernel_entry(kt["shadowRays"], bytes_per_shadow_ray, kt["shadowMs"], "same for any-hit rays: + 32 (ray record) + 48 (result records) + 32 (radiance read + write)"),
+        "shade_disney": kernel_entry(kt["shadeItems"][3], 620.0, kt["shadeMs"][3], "SURVEY 8d: 0.62 KB gathered / written per shaded hit (with the shadow record)"),
+        "shade_lambertian": kernel_entry(kt["shadeItems"][0], 620.0, kt["shadeMs"][0], "SURVEY 8d: 0.62 KB per shaded hit"),
+        "shade_metal": kernel_entry(kt["shadeItems"][1], 580.0, kt["shadeMs"][1], "SURVEY 8d: 0.58 KB per shaded hit (no shadow record)"),
+        "shade_dielectric": kernel_entry(kt["shadeItems"][2], 580.0, kt["shadeMs"][2], "SURVEY 8d: 0.58 KB per shaded hit (no shadow record)"),
+        "miss": kernel_entry(kt["shadeItems"][4], 224.0, kt["shadeMs"][4], "96 B of path state in, 128 B out (the slot's next camera path)"),
+        "post": kernel_entry(px, 132.0, post_ms, "SURVEY 8d: 132 B per pixel with combine + tonemap fused; units = pixels, per call"),
+    }
+    res.update({"achieved": achieved, "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
+                "kernels": {k: v for k, v in kernels.items() if v}, "post_ms_per_call": post_ms,
                 "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri, "node_bytes": node_bytes,
                 "shadow": {"bytes_per_ray": bytes_per_shadow_ray, "nodes_per_ray": n_node_sh, "tris_per_ray": n_tri_sh,
                            "rays_per_step": kt["shadowRays"], "ms_per_step": kt["shadowMs"], "launches": kt["shadowLaunches"],

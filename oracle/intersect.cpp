@@ -156,8 +156,9 @@ static inline bool box_hit(const BvhNode& n, const double o[3], const double inv
         double tb = ((double)n.hi[a] + slack - o[a]) * inv[a];
         if (ta != ta || tb != tb) continue;            // 0 * inf: origin on the slab plane, direction parallel -> inside
         if (ta > tb) std::swap(ta, tb);
-        if (std::fabs(ta) < 1e300) ext = std::max(ext, std::fabs(ta));
-        if (std::fabs(tb) < 1e300) ext = std::max(ext, std::fabs(tb));
+        // the vertices' ray parameters are measured along the dominant axis of the ray (smallest |1 / d|): its slab bounds them
+        if (std::fabs(inv[a]) <= std::fabs(inv[(a + 1) % 3]) && std::fabs(inv[a]) <= std::fabs(inv[(a + 2) % 3]))
+            ext = std::max(ext, std::max(std::fabs(ta), std::fabs(tb)));
         t0 = std::max(t0, ta); t1 = std::min(t1, tb);
     }
     const double margin = 6.103515625e-05 * ext;        // 2^-14

@@ -235,6 +235,17 @@ RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB2
     RB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     RB200Scene* sc = new RB200Scene();
+    // from here on every failure path releases the half-built scene
+#define SC_CUDA(call)                                                                                  \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            rb200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+            cudaGetLastError();                                                                        \
+            rb200_scene_destroy(sc);                                                                   \
+            return RB200_ERR_CUDA;                                                                     \
+        }                                                                                              \
+    } while (0)
     sc->ctx = ctx;
     DeviceScene& D = sc->dev;
 #define U(field, host, count) if ((rc = upload(sc, host, (size_t)(count), &D.field, s)) != RB200_OK) { rb200_scene_destroy(sc); return rc; }
@@ -247,7 +258,7 @@ RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB2
         std::vector<RB200InstanceProperties> perInstance(d->numInstances);
         for (uint32_t i = 0; i < d->numInstances; i++) perInstance[i] = d->instanceProperties[d->instances[i].instancePropertiesID];
         U(instProps, perInstance.data(), perInstance.size());
-        RB_CUDA(cudaStreamSynchronize(s));      // perInstance goes out of scope
+        SC_CUDA(cudaStreamSynchronize(s));      // perInstance goes out of scope
     }
 #endif
     U(tbns, d->tbns, 9 * (size_t)d->numTbns);
@@ -274,22 +285,22 @@ RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB2
         if (!t.rgba8 || t.width == 0 || t.height == 0) { set_error("texture %u is empty", i); rb200_scene_destroy(sc); return RB200_ERR_INVALID_ARGUMENT; }
         cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
         cudaArray_t arr;
-        RB_CUDA(cudaMallocArray(&arr, &fmt, t.width, t.height));
+        SC_CUDA(cudaMallocArray(&arr, &fmt, t.width, t.height));
         sc->texArrays.push_back(arr);
-        RB_CUDA(cudaMemcpy2DToArrayAsync(arr, 0, 0, t.rgba8, (size_t)t.width * 4, (size_t)t.width * 4, t.height, cudaMemcpyHostToDevice, s));
+        SC_CUDA(cudaMemcpy2DToArrayAsync(arr, 0, 0, t.rgba8, (size_t)t.width * 4, (size_t)t.width * 4, t.height, cudaMemcpyHostToDevice, s));
         cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
         rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
         cudaTextureDesc td; memset(&td, 0, sizeof(td));
         td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
         td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
         cudaTextureObject_t obj;
-        RB_CUDA(cudaCreateTextureObject(&obj, &rd, &td, nullptr));
+        SC_CUDA(cudaCreateTextureObject(&obj, &rd, &td, nullptr));
         sc->texObjects.push_back(obj);
         sizes.push_back(make_uint2(t.width, t.height));
     }
     if ((rc = upload(sc, sc->texObjects.data(), sc->texObjects.size(), &D.textures, s)) != RB200_OK) { rb200_scene_destroy(sc); return rc; }
     if ((rc = upload(sc, sizes.data(), sizes.size(), &D.texSizes, s)) != RB200_OK) { rb200_scene_destroy(sc); return rc; }
-    RB_CUDA(cudaStreamSynchronize(s));   // host staging vectors go out of scope below
+    SC_CUDA(cudaStreamSynchronize(s));   // host staging vectors go out of scope below
 
     // RB200_BVH_BUILDER=lbvh | ploc selects the binary hierarchy under the collapse (see common.cuh); default ploc
     int builder = BUILDER_PLOC;
@@ -320,7 +331,7 @@ RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB2
         if ((rc = build_shade_records(D, base, frame, s)) != RB200_OK) { rb200_scene_destroy(sc); return rc; }
         ctx->launches++;
         D.shadeBase = base; D.shadeFrame = frame;
-        RB_CUDA(cudaStreamSynchronize(s));
+        SC_CUDA(cudaStreamSynchronize(s));
     }
 #endif
 
@@ -353,6 +364,7 @@ RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB2
     }
     *out = sc;
     return RB200_OK;
+#undef SC_CUDA
 }
 
 RB200_API int rb200_scene_destroy(RB200Scene* sc) {

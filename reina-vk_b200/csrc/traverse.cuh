@@ -252,7 +252,11 @@ struct Traversal {
         // the full-size C2 parity test: 4 of 518,400 pixels; tests/test_gpu_parity2.py has the ray set). 2^-14 of the node's
         // extent in ray parameters bounds that error for triangles with an aspect ratio up to ~64 and weakens the cull by
         // less than 1e-4 of a node's size.
-        const float margin = 64.0f * ((jx + jy) + jz);
+        // (the vertices' ray parameters are measured along the ray's dominant axis — the one with the smallest |1/d| —, so the
+        // node's slab along THAT axis bounds them; the other axes' slabs can be arbitrarily wide for a nearly parallel ray)
+        const float ax = fabsf(idx), ay = fabsf(idy), az = fabsf(idz);
+        const float ex = fmaf(256.0f, fabsf(sx), fabsf(cx)), ey = fmaf(256.0f, fabsf(sy), fabsf(cy)), ez = fmaf(256.0f, fabsf(sz), fabsf(cz));
+        const float margin = 6.103515625e-05f * ((ax <= ay && ax <= az) ? ex : (ay <= az ? ey : ez));   // 2^-14
         const float kx = jx + margin, ky = jy + margin, kz = jz + margin;
         const float cnx = fmaf(-BYTE_BIAS, sx, cx - kx), cfx = fmaf(-BYTE_BIAS, sx, cx + kx);
         const float cny = fmaf(-BYTE_BIAS, sy, cy - ky), cfy = fmaf(-BYTE_BIAS, sy, cy + ky);
