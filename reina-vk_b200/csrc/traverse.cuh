@@ -148,10 +148,24 @@ __device__ __forceinline__ float byte_f(uint32_t w, int j, uint32_t biasWord) {
     return __uint_as_float(__byte_perm(w, biasWord, 0x7404u + ((uint32_t)j << 4)));
 }
 
+// Culling margin as a fraction of the node's extent along the ray's dominant axis (see node_step): 2^-14.
+#ifndef RB_CULL_MARGIN
+#define RB_CULL_MARGIN 6.103515625e-05f
+#endif
+
+// RB_ORIGIN_FROM_STAGE=1: the node step reads the ray origin from the warp's shared-memory ray stage (one LDS.128, the
+// stage holds it for the triangle phase anyway) instead of keeping it in three registers: under the 64-register cap ptxas
+// spilled exactly those three and re-loaded them from local memory in every node step (3 LDL per step, r02a).
+#ifndef RB_ORIGIN_FROM_STAGE
+#define RB_ORIGIN_FROM_STAGE 1
+#endif
+
 template <bool ANY, bool COUNT>
 struct Traversal {
+#if !RB_ORIGIN_FROM_STAGE
     rb_v3 o;
-    float idx, idy, idz, tmax;
+#endif
+    float idx, idy, idz;
     uint32_t oct_inv;
     uint2 ngroup, tgroup;
     int sp, tsp;
@@ -180,7 +194,9 @@ struct Traversal {
     }
 
     __device__ __forceinline__ void init(const rb_v3 org, const rb_v3 d, const float tmax_, float4* rayStage) {
-        o = org; tmax = tmax_;
+#if !RB_ORIGIN_FROM_STAGE
+        o = org;
+#endif
         best.t = tmax_; best.b1 = 0.f; best.b2 = 0.f; best.tri = 0xFFFFFFFFu; best.gid = 0xFFFFFFFFu;
         const float ooeps = 8.2718061e-25f;   // 2^-80: keeps 1/d finite for axis-parallel rays (box tests only)
         idx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
@@ -237,6 +253,9 @@ struct Traversal {
         const float sx = __uint_as_float((eim & 0xFFu) << 23) * idx;
         const float sy = __uint_as_float(((eim >> 8) & 0xFFu) << 23) * idy;
         const float sz = __uint_as_float(((eim >> 16) & 0xFFu) << 23) * idz;
+#if RB_ORIGIN_FROM_STAGE
+        const float4 o = ws.ray[threadIdx.x & 31u][0];
+#endif
         const float cx = (n0.x - o.x) * idx, cy = (n0.y - o.y) * idy, cz = (n0.z - o.z) * idz;
         const float eps = 9.5367431640625e-07f;   // 2^-20
         // slack: 2^-20 * (255 |s| + |c|) bounds the rounding of q*s + c and the acceptance band of the triangle test;
@@ -256,7 +275,7 @@ struct Traversal {
         // node's slab along THAT axis bounds them; the other axes' slabs can be arbitrarily wide for a nearly parallel ray)
         const float ax = fabsf(idx), ay = fabsf(idy), az = fabsf(idz);
         const float ex = fmaf(256.0f, fabsf(sx), fabsf(cx)), ey = fmaf(256.0f, fabsf(sy), fabsf(cy)), ez = fmaf(256.0f, fabsf(sz), fabsf(cz));
-        const float margin = 6.103515625e-05f * ((ax <= ay && ax <= az) ? ex : (ay <= az ? ey : ez));   // 2^-14
+        const float margin = RB_CULL_MARGIN * ((ax <= ay && ax <= az) ? ex : (ay <= az ? ey : ez));
         const float kx = jx + margin, ky = jy + margin, kz = jz + margin;
         const float cnx = fmaf(-BYTE_BIAS, sx, cx - kx), cfx = fmaf(-BYTE_BIAS, sx, cx + kx);
         const float cny = fmaf(-BYTE_BIAS, sy, cy - ky), cfy = fmaf(-BYTE_BIAS, sy, cy + ky);

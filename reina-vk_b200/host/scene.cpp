@@ -3,7 +3,9 @@
 
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <stdexcept>
+#include <unordered_map>
 
 namespace rbhost {
 
@@ -180,28 +182,54 @@ SceneTables Scene::build(bool requireEmitter) {
         }
     }
 
-    // Instances::computeSamplingDataEmissives (src/scene/Instances.cpp:52-114); every emitter stores its own CDF
-    // (the reference's duplicate-CDF sharing mixes index spaces and is a no-op with one emitter)
+    // Instances::computeEmissiveDuplicates (src/scene/Instances.cpp:27-50): instance index of a later emitter -> instance
+    // index of the first earlier emitter whose CDF has the same length and agrees within FLT_EPSILON (:12-25)
+    std::unordered_map<size_t, size_t> duplicates;
+    for (size_t a = 0; a < emissiveIds.size(); a++) {
+        for (size_t b = a + 1; b < emissiveIds.size(); b++) {
+            const std::vector<float>&ca = cdfs[a].cdf, &cb = cdfs[b].cdf;
+            if (ca.size() != cb.size()) continue;
+            bool same = true;
+            for (size_t i = 0; i < ca.size() && same; i++) same = !(std::fabs(ca[i] - cb[i]) > std::numeric_limits<float>::epsilon());
+            if (same) duplicates.emplace(emissiveIds[b], emissiveIds[a]);      // emplace keeps the first assignment
+        }
+    }
+
+    // Instances::computeSamplingDataEmissives (src/scene/Instances.cpp:52-114), duplicate sharing reproduced AS WRITTEN:
+    // the map is keyed by instance index, but the loop asks `contains(position in the emissive list)` (:72), reads
+    // `.at(instance index)` (:86) and indexes the emissive records with the mapped INSTANCE index. The index spaces
+    // coincide only while every instance in front of the duplicate is emissive; otherwise upstream shares nothing,
+    // shares another emitter's range, throws std::out_of_range or reads past the vector (refused here).
     uint32_t offset = 0;
     float cum = 0.0f;
+    t.emissive.assign(emissiveIds.size(), RB200InstanceData{});
     for (size_t i = 0; i < emissiveIds.size(); i++) {
         const PendingInstance& pi = instancesToCreate[emissiveIds[i]];
         const Material& m = materials[pi.propertiesID];
-        RB200InstanceData d{};
+        RB200InstanceData& d = t.emissive[i];
         std::memcpy(d.transform, pi.transform.data(), sizeof d.transform);
         d.materialOffset = pi.materialIdx;
-        d.cdfRangeStart = offset;
-        d.cdfRangeEnd = offset + uint32_t(cdfs[i].cdf.size()) - 1;
         d.indexOffset = modelRanges[pi.objectID].indexOffset;
         for (int k = 0; k < 3; k++) d.emission[k] = m.emission[k];
         d.weight = cdfs[i].weight;
         d.area = cdfs[i].area;
         d.cullBackface = m.cullBackface ? 1u : 0u;
-        t.emissive.push_back(d);
-        t.cdfTriangles.insert(t.cdfTriangles.end(), cdfs[i].cdf.begin(), cdfs[i].cdf.end());
-        offset += uint32_t(cdfs[i].cdf.size());
         cum = cum + cdfs[i].weight;
         t.cdfInstances.push_back(cum);
+        if (duplicates.count(i)) {
+            const auto it = duplicates.find(emissiveIds[i]);
+            if (it == duplicates.end()) throw std::out_of_range("unordered_map::at");
+            if (it->second >= t.emissive.size())
+                throw std::runtime_error("emissive duplicate mapping points outside the emissive list "
+                                         "(undefined behaviour in the reference, src/scene/Instances.cpp:86)");
+            d.cdfRangeStart = t.emissive[it->second].cdfRangeStart;
+            d.cdfRangeEnd = t.emissive[it->second].cdfRangeEnd;
+            continue;
+        }
+        d.cdfRangeStart = offset;
+        d.cdfRangeEnd = offset + uint32_t(cdfs[i].cdf.size()) - 1;
+        t.cdfTriangles.insert(t.cdfTriangles.end(), cdfs[i].cdf.begin(), cdfs[i].cdf.end());
+        offset += uint32_t(cdfs[i].cdf.size());
     }
     if (!emissiveIds.empty()) {
         for (float& x : t.cdfInstances) x = x / cum;

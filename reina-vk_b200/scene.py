@@ -124,6 +124,21 @@ class SceneTables:
         return int(inst[:, 19].sum())
 
 
+def _emissive_duplicates(emissive_ids, inst_cdf):
+    """Instances::computeEmissiveDuplicates (src/scene/Instances.cpp:27-50): instance index of a later emitter -> instance
+    index of the first earlier emitter whose triangle CDF has the same length and agrees within FLT_EPSILON (:12-25)."""
+    eps = np.float32(np.finfo(np.float32).eps)
+    dup = {}
+    for a, i in enumerate(emissive_ids):
+        ci = inst_cdf[i][0]
+        for j in emissive_ids[a + 1:]:
+            cj = inst_cdf[j][0]
+            if ci.size != cj.size or bool(np.any(np.abs(ci - cj) > eps)):
+                continue
+            dup.setdefault(j, i)
+    return dup
+
+
 def _is_emissive(e):
     # Instance::isEmissive, src/scene/Instance.cpp:75-77
     e = np.asarray(e, dtype=np.float32)
@@ -297,27 +312,40 @@ class Scene:
                 emissive_ids.append(k)
         instances = np.frombuffer(b"".join(inst_bytes), dtype=np.uint8).copy() if inst_bytes else np.zeros(80, np.uint8)
 
-        # Instances::computeSamplingDataEmissives (src/scene/Instances.cpp:52-114). The reference's duplicate-CDF
-        # de-duplication mixes instance indices with emissive-list indices (:44,72,86); it has no effect with one
-        # emitter and is not reproduced for several (documented deviation: every emitter stores its own CDF).
+        # Instances::computeSamplingDataEmissives (src/scene/Instances.cpp:52-114), duplicate-CDF sharing included and
+        # reproduced AS WRITTEN: computeEmissiveDuplicates (:27-50) keys its map by INSTANCE index, the loop asks it
+        # `contains(position in the emissive list)` (:72) and then reads `.at(instance index)` (:86) and indexes the
+        # emissive records with the mapped INSTANCE index. The two index spaces coincide only while every instance in
+        # front of the duplicate is emissive; otherwise upstream shares nothing, shares another emitter's range, throws
+        # std::out_of_range or reads past the vector (refused here) — each outcome is kept.
+        dup = _emissive_duplicates(emissive_ids, inst_cdf)
         cdfTriangles = []
-        em_recs = []
+        recs = [abi.InstanceData() for _ in emissive_ids]        # value-initialised like std::vector<InstanceData>(n)
         offset = 0
-        for k in emissive_ids:
+        for pos, k in enumerate(emissive_ids):
             pid, matIdx, oid, T = self.instancesToCreate[k]
             cdf, area, weight = inst_cdf[k]
-            d = abi.InstanceData()
+            d = recs[pos]
             d.transform[:] = [float(x) for x in T.reshape(-1)]
             d.materialOffset = matIdx
-            d.cdfRangeStart = offset
-            d.cdfRangeEnd = offset + cdf.size - 1
             d.indexOffset = self.modelRanges[oid].indexOffset
             d.emission[:] = [float(x) for x in self.materials[pid].emission]
             d.weight, d.area = weight, area
             d.cullBackface = 1 if self.materials[pid].cullBackface else 0
-            em_recs.append(bytes(d))
+            if pos in dup:
+                if k not in dup:
+                    raise IndexError("unordered_map::at")        # what std::unordered_map::at throws upstream (:86)
+                src = dup[k]
+                if src >= len(recs):
+                    raise RuntimeError("emissive duplicate mapping points outside the emissive list "
+                                       "(undefined behaviour in the reference, src/scene/Instances.cpp:86)")
+                d.cdfRangeStart, d.cdfRangeEnd = recs[src].cdfRangeStart, recs[src].cdfRangeEnd
+                continue
+            d.cdfRangeStart = offset
+            d.cdfRangeEnd = offset + cdf.size - 1
             cdfTriangles.append(cdf)
             offset += cdf.size
+        em_recs = [bytes(d) for d in recs]
         cum = np.float32(0)
         cdfInstances = np.zeros(len(emissive_ids), np.float32)
         for i, k in enumerate(emissive_ids):

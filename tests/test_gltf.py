@@ -272,3 +272,72 @@ def test_cli_renders_glb_like_the_python_host(host, ol, rb, gl, tmp_path):
     r.close()
     got = decode_png(out.read_bytes())
     assert (got == want).all() and got[..., :3].max() > 0
+
+
+def _emitters_gltf(tmp_path, order):
+    """A flat scene of quads, one node per letter: A = lamp (instances of ONE mesh, translated: equal CDFs), D = lamp of
+    another shape (unequal triangles: a different CDF), F = non-emissive floor."""
+    B = gf._Bin()
+    quad = np.array([[-0.4, 0, -0.4], [0.4, 0, 0.4], [0.4, 0, -0.4], [-0.4, 0, -0.4], [-0.4, 0, 0.4], [0.4, 0, 0.4]], np.float32)
+    odd = np.array([[-0.4, 0, -0.4], [0.0, 0, 0.4], [0.4, 0, -0.4], [-0.4, 0, -0.4], [-0.4, 0, 0.4], [0.0, 0, 0.4]], np.float32)
+    nrm = np.tile(np.array([[0, -1, 0]], np.float32), (6, 1))
+    a_n = B.accessor(B.view(nrm.tobytes()), 5126, 6, "VEC3")
+    a_quad = B.accessor(B.view(quad.tobytes()), 5126, 6, "VEC3", minmax=(quad.min(0), quad.max(0)))
+    a_odd = B.accessor(B.view(odd.tobytes()), 5126, 6, "VEC3", minmax=(odd.min(0), odd.max(0)))
+    lamp = {"emissiveFactor": [1.0, 0.9, 0.8], "doubleSided": True}
+    doc = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": list(range(len(order)))}],
+           "nodes": [{"mesh": "AFD".index(c), "translation": [1.0 * i, 1.5 if c != "F" else 0.0, 0.0]} for i, c in enumerate(order)],
+           "meshes": [{"primitives": [{"attributes": {"POSITION": a_quad, "NORMAL": a_n}, "material": 0}]},
+                      {"primitives": [{"attributes": {"POSITION": a_quad, "NORMAL": a_n}, "material": 1}]},
+                      {"primitives": [{"attributes": {"POSITION": a_odd, "NORMAL": a_n}, "material": 0}]}],
+           "materials": [lamp, {"pbrMetallicRoughness": {"baseColorFactor": [0.8, 0.8, 0.8, 1.0]}}],
+           "accessors": B.accessors, "bufferViews": B.views}
+    while len(B.data) % 4:
+        B.data.append(0)
+    doc["buffers"] = [{"byteLength": len(B.data)}]
+    js = json.dumps(doc, separators=(",", ":")).encode()
+    js += b" " * (-len(js) % 4)
+    path = tmp_path / ("emitters_%s.glb" % order)
+    path.write_bytes(struct.pack("<III", 0x46546C67, 2, 12 + 8 + len(js) + 8 + len(B.data)) + struct.pack("<II", len(js), 0x4E4F534A) + js +
+                     struct.pack("<II", len(B.data), 0x004E4942) + bytes(B.data))
+    return str(path)
+
+
+@pytest.mark.filterwarnings("ignore:falling back to UV")
+@pytest.mark.filterwarnings("ignore:.*several emitters")
+def test_emissive_cdf_sharing_is_reproduced_as_written(host, rb, gl, tmp_path):
+    """Instances::computeEmissiveDuplicates / computeSamplingDataEmissives (src/scene/Instances.cpp:27-50, 52-114): emitters
+    with equal triangle CDFs share one range of cdfTriangles — but the map is keyed by instance index and consulted with
+    the position in the emissive list (:72 vs :86), so what happens depends on where the emitters sit among the instances.
+    Both hosts reproduce every outcome: sharing (AAF, AAAF), no sharing (FAA), another emitter's range (FAAA), and the
+    std::out_of_range upstream dies with (FAAD)."""
+    abi = importlib.import_module("reina-vk_b200.abi")
+    host.rbhost_tables_gltf.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+
+    def ranges(order):
+        path = _emitters_gltf(tmp_path, order)
+        py = gl.loadScene(path).build(require_emitter=True)
+        h = C.c_void_p()
+        assert host.rbhost_tables_gltf(path.encode(), 1, C.byref(h)) == 0, err(host)
+        assert_tables_identical(cpp_tables(host, rb, h), py_tables(py))
+        host.rbhost_tables_free(h)
+        recs = (abi.InstanceData * py.numEmissive).from_buffer_copy(py.emissive.tobytes())
+        return [(r.cdfRangeStart, r.cdfRangeEnd) for r in recs], py
+
+    r, py = ranges("AAF")          # instance index == emissive position: the second lamp shares the first one's CDF
+    assert r == [(0, 1), (0, 1)] and py.cdfTriangles.size == 2
+    assert np.array_equal(py.cdfInstances, np.array([0.5, 1.0], np.float32))
+    r, py = ranges("AAAF")
+    assert r == [(0, 1)] * 3 and py.cdfTriangles.size == 2
+    r, py = ranges("FAA")          # keys {2}, asked for positions 0 and 1: nothing is shared
+    assert r == [(0, 1), (2, 3)] and py.cdfTriangles.size == 4
+    r, py = ranges("FAAA")         # keys {2, 3}: position 2 (instance 3) is a key, at(3) = 1 -> emissive record 1 (instance 2)
+    assert r == [(0, 1), (2, 3), (2, 3)] and py.cdfTriangles.size == 4
+    r, py = ranges("AFA")          # keys {2}: position 1 (instance 2) is not asked about with its own index
+    assert r == [(0, 1), (2, 3)]
+    # FAAD: keys {2}; position 2 is instance 3 (the odd lamp): contains(2) is true, at(3) throws
+    path = _emitters_gltf(tmp_path, "FAAD")
+    with pytest.raises(IndexError, match="unordered_map::at"):
+        gl.loadScene(path).build(require_emitter=True)
+    h = C.c_void_p()
+    assert host.rbhost_tables_gltf(path.encode(), 1, C.byref(h)) != 0 and "unordered_map::at" in err(host)

@@ -7,10 +7,10 @@ FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=fa
 build_one() {
   name="${1%%=*}"; extra="${1#*=}"
   d=$(mktemp -d)
-  for f in api bvh_build wavefront post; do
+  for f in api bvh_build wavefront post group; do
     nvcc $FLAGS $extra -c $f.cu -o $d/$f.o 2> variants/$name.$f.log || { echo "BUILD FAILED: $name ($f)"; tail -5 variants/$name.$f.log; rm -rf $d; return 1; }
   done
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/$name.so $d/api.o $d/bvh_build.o $d/wavefront.o $d/post.o && echo "built variants/$name.so [$extra]"
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/$name.so $d/api.o $d/bvh_build.o $d/wavefront.o $d/post.o $d/group.o -ldl && echo "built variants/$name.so [$extra]"
   grep -A2 "k_extendILb0\|k_shadowILb0" variants/$name.wavefront.log | grep -E "spill|Used" | tr '\n' ' '; echo
   rm -rf $d
 }
