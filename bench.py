@@ -473,7 +473,11 @@ def roofline(rb, wl, device, stream, nee_flag):
     table_bytes = max(int(info["nodeBytes"] + info["triangleBytes"]), 1 << 20)     # (tiny scenes: the micro-benchmark needs >= 1024 records)
     l2_gather = rc.measure_gather(table_bytes, 80)
     rc.close()
-    node_bytes = info["nodeBytes"] / max(1, info["numWideNodes"])
+    # algorithmic bytes of a record = what it carries (80-byte wide node, 48-byte triangle), not its stride in memory:
+    # with RB_WIDE_LOADS the library pads records to 96 / 64 bytes for 256-bit loads, and padding is not information
+    node_bytes = 80.0
+    node_stride = info["nodeBytes"] / max(1, info["numWideNodes"])
+    tri_stride = info["triangleBytes"] / max(1, info["numTriangles"])
     n_node = (last_c["nodeVisits"] - last_c["shadowNodeVisits"]) / max(1, last_c["extendRays"])
     n_tri = (last_c["triTests"] - last_c["shadowTriTests"]) / max(1, last_c["extendRays"])
     n_node_sh = last_c["shadowNodeVisits"] / max(1, last_c["shadowRays"])
@@ -510,6 +514,7 @@ def roofline(rb, wl, device, stream, nee_flag):
     res.update({"achieved": achieved, "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
                 "kernels": {k: v for k, v in kernels.items() if v}, "post_ms_per_call": post_ms,
                 "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri, "node_bytes": node_bytes,
+                "node_stride_bytes": node_stride, "triangle_stride_bytes": tri_stride,
                 "shadow": {"bytes_per_ray": bytes_per_shadow_ray, "nodes_per_ray": n_node_sh, "tris_per_ray": n_tri_sh,
                            "rays_per_step": kt["shadowRays"], "ms_per_step": kt["shadowMs"], "launches": kt["shadowLaunches"],
                            "achieved": (bytes_per_shadow_ray * kt["shadowRays"] / (kt["shadowMs"] * 1e-3) / 1e9) if kt["shadowMs"] > 0 else None,

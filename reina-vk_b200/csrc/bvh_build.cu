@@ -63,6 +63,9 @@ __global__ void k_flatten(const float4* __restrict__ verts, const uint32_t* __re
         t.v0 = make_float4(w[0].x, w[0].y, w[0].z, __uint_as_float(p));
         t.v1 = make_float4(w[1].x, w[1].y, w[1].z, __uint_as_float(a | ((in.materialIdx > 3u ? 3u : in.materialIdx) << 30)));
         t.v2 = make_float4(w[2].x, w[2].y, w[2].z, __uint_as_float(g));
+#if RB_WIDE_LOADS
+        t.pad = make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
         out[g] = t;
     }
 #pragma unroll

@@ -25,8 +25,30 @@ void set_error(const char* fmt, ...);
 
 // ---------------------------------------------------------------------------------------------------
 // 8-wide compressed BVH (Ylitie, Karras, Laine 2017 layout): 80-byte nodes, 48-byte triangles
+//
+// RB_WIDE_LOADS=1: records padded to a multiple of 32 bytes (node 96 B, triangle 64 B, 32-byte aligned) and read with
+// 256-bit loads (LDG.E.256, sm_100): a wide node is 3 load instructions instead of 5, a triangle 2 instead of 3. Every
+// lane reads its own node, so each load instruction of a warp is up to 32 separate L1 requests, and the L1 data pipe was
+// the traversal kernels' busiest unit next to the issue slots (76 % of its peak, profiles/r02b). MEASURED ON B200: no
+// gain — k_extend 19.63 against 19.65 ms per step, k_shadow 10.50 against 10.37 (profiles/r02e_variant_sweep.txt): the
+// five 128-bit loads of a node already hit the one or two lines the first of them brought in. Off: the records keep
+// their 80 / 48 bytes (the padding would also cost 15.5 MB of L2 on the headline scene).
+// (RB_WIDE_RECORDS below — the same idea for the shading kernels, which ARE bound by the request rate — pays.)
 // ---------------------------------------------------------------------------------------------------
-struct alignas(16) WideNode {
+#ifndef RB_WIDE_LOADS
+#define RB_WIDE_LOADS 0
+#endif
+// RB_WIDE_RECORDS=1: the per-triangle shading records (64 and 128 bytes, 64-byte aligned) are read with 256-bit loads.
+#ifndef RB_WIDE_RECORDS
+#define RB_WIDE_RECORDS 1
+#endif
+#if RB_WIDE_LOADS
+#define RB_BVH_ALIGN 32
+#else
+#define RB_BVH_ALIGN 16
+#endif
+static constexpr uint32_t WIDE_NODE_INFO_BYTES = 80, TRI_RECORD_INFO_BYTES = 48;     // what a record carries, without padding
+struct alignas(RB_BVH_ALIGN) WideNode {
     float px, py, pz;        // origin of the quantisation grid = node AABB min
     uint8_t ex, ey, ez;      // biased fp32 exponents of the per-axis grid step
     uint8_t imask;           // bit s set: slot s holds an internal child
@@ -36,15 +58,23 @@ struct alignas(16) WideNode {
     uint8_t qlox[8], qloy[8];
     uint8_t qloz[8], qhix[8];
     uint8_t qhiy[8], qhiz[8];
+#if RB_WIDE_LOADS
+    uint32_t pad[4];         // zero
+#endif
 };
-static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
+static_assert(sizeof(WideNode) == (RB_WIDE_LOADS ? 96 : 80), "WideNode must be 80 bytes (+ 16 of padding with RB_WIDE_LOADS)");
 
 // triangle record in leaf order: three float4, w lanes carry ids
 //   v0.w = primitive id within the model, v1.w = instance index | material kernel (0..3) << 30, v2.w = global primitive
 //   id (tie-break key). The material bits let k_extend bin a finished ray without touching the instance table.
 static constexpr uint32_t TRI_INST_MASK = 0x3FFFFFFFu;
-struct alignas(16) TriRecord { float4 v0, v1, v2; };
-static_assert(sizeof(TriRecord) == 48, "TriRecord must be 48 bytes");
+struct alignas(RB_BVH_ALIGN) TriRecord {
+    float4 v0, v1, v2;
+#if RB_WIDE_LOADS
+    float4 pad;              // zero
+#endif
+};
+static_assert(sizeof(TriRecord) == (RB_WIDE_LOADS ? 64 : 48), "TriRecord must be 48 bytes (+ 16 of padding with RB_WIDE_LOADS)");
 
 struct Bvh {
     void* blob = nullptr;            // one allocation: nodes, then (256-byte aligned) triangles

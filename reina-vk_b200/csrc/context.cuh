@@ -66,8 +66,47 @@ template <class T, int STRIDE = 1> struct StateArr {
 #ifndef RB_PAIR_STATE
 #define RB_PAIR_STATE 2
 #endif
+// RB_WIDE_STATE=1 (needs the one-line-per-slot layout): the two records of a 32-byte sector — (rayO, rayD), (thr, st),
+// (hit, rad) — move with ONE 256-bit access (LDG / STG.E.256, sm_100) instead of two 128-bit ones. The shading kernels
+// run into the rate at which an SM can send scattered requests to L2, not into latency or DRAM bandwidth (the software
+// prefetch experiment in wavefront.cu made them slower by adding requests), so fewer, wider requests for the same
+// sectors are what helps: a shaded hit reads its state with 3 requests instead of 6 and writes it back with 3 or 4
+// instead of 5.
+#ifndef RB_WIDE_STATE
+#define RB_WIDE_STATE (RB_PAIR_STATE == 2)
+#endif
+#if RB_WIDE_STATE && RB_PAIR_STATE != 2
+#error "RB_WIDE_STATE needs RB_PAIR_STATE == 2"
+#endif
 static constexpr int STATE_STRIDE = RB_PAIR_STATE == 2 ? 8 : (RB_PAIR_STATE ? 2 : 1);
 static constexpr int SUM_STRIDE = RB_PAIR_STATE == 2 ? 8 : 1;
+
+// first[slot] and second[slot], which with RB_WIDE_STATE are the two halves of one 32-byte sector
+template <class TA, class TB, int S>
+__device__ __forceinline__ void load_pair(const StateArr<TA, S>& first, const StateArr<TB, S>& second, uint32_t slot, TA& a, TB& b) {
+    static_assert(sizeof(TA) == 16 && sizeof(TB) == 16, "16-byte records");
+#if RB_WIDE_STATE
+    uint32_t r[8];
+    asm volatile("ld.global.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(first.p + (size_t)slot * S) : "memory");
+    const uint4 ua = make_uint4(r[0], r[1], r[2], r[3]), ub = make_uint4(r[4], r[5], r[6], r[7]);
+    a = *reinterpret_cast<const TA*>(&ua); b = *reinterpret_cast<const TB*>(&ub);
+#else
+    a = first[slot]; b = second[slot];
+#endif
+}
+template <class TA, class TB, int S>
+__device__ __forceinline__ void store_pair(const StateArr<TA, S>& first, const StateArr<TB, S>& second, uint32_t slot, const TA& a, const TB& b) {
+    static_assert(sizeof(TA) == 16 && sizeof(TB) == 16, "16-byte records");
+#if RB_WIDE_STATE
+    const uint4 ua = *reinterpret_cast<const uint4*>(&a), ub = *reinterpret_cast<const uint4*>(&b);
+    asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(first.p + (size_t)slot * S), "r"(ua.x), "r"(ua.y), "r"(ua.z), "r"(ua.w), "r"(ub.x), "r"(ub.y), "r"(ub.z), "r"(ub.w) : "memory");
+#else
+    first[slot] = a; second[slot] = b;
+#endif
+}
 
 struct WaveParams {
     DeviceScene S;

@@ -32,6 +32,15 @@ __device__ __forceinline__ rb_v3 ld_tbn_col(const DeviceScene& S, uint32_t i, in
     return rb_mk3(__ldg(m), __ldg(m + 1), __ldg(m + 2));
 }
 __device__ __forceinline__ rb_v3 ld3(const float* p) { return rb_mk3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
+// two consecutive float4 of a 32-byte aligned read-only record: one 256-bit load on the device (RB_WIDE_RECORDS, common.cuh)
+__device__ __forceinline__ void ld_ro2(const float4* p, float4& a, float4& b) {
+#if defined(__CUDA_ARCH__) && RB_WIDE_RECORDS
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+    a = __ldg(p); b = __ldg(p + 1);
+#endif
+}
 
 // RGBA8 UNORM texel fetch through the texture unit (point sampled); the bilinear REPEAT filter of the reference's
 // sampler (src/tools/vktools.cpp:765-788) is applied in fp32 so that it is reproducible bit for bit.
@@ -182,7 +191,12 @@ template <bool NEED_TBN>
 __device__ __forceinline__ void hit_info_rec(const DeviceScene& S, const RB200Instance* inst, const RB200InstanceProperties* props,
                                              uint32_t tri, float a1, float a2, rb_v3 rayDir, Surf& r) {
     const float4* sb = S.shadeBase + 4 * (size_t)tri;
+#if RB_WIDE_RECORDS
+    float4 r0, r1, r2, r3;
+    ld_ro2(sb, r0, r1); ld_ro2(sb + 2, r2, r3);
+#else
     const float4 r0 = __ldg(sb), r1 = __ldg(sb + 1), r2 = __ldg(sb + 2), r3 = __ldg(sb + 3);
+#endif
     const rb_v3 v0 = rb_mk3(r0.x, r0.y, r0.z), v1 = rb_mk3(r1.x, r1.y, r1.z), v2 = rb_mk3(r2.x, r2.y, r2.z);
     const float bx = 1.0f - a1 - a2, by = a1, bz = a2;
     float M16[16];
@@ -197,8 +211,13 @@ __device__ __forceinline__ void hit_info_rec(const DeviceScene& S, const RB200In
     rb_v3 c2_0, c2_1, c2_2;
     if (interp || NEED_TBN) {
         const float4* sf = S.shadeFrame + 8 * (size_t)tri;
+#if RB_WIDE_RECORDS
+        if (NEED_TBN) { float4 f7; ld_ro2(sf, f0, f1); ld_ro2(sf + 2, f2, f3); ld_ro2(sf + 4, f4, f5); ld_ro2(sf + 6, f6, f7); }
+        else { ld_ro2(sf, f0, f1); f2 = __ldg(sf + 2); }
+#else
         f0 = __ldg(sf); f1 = __ldg(sf + 1); f2 = __ldg(sf + 2);
         if (NEED_TBN) { f3 = __ldg(sf + 3); f4 = __ldg(sf + 4); f5 = __ldg(sf + 5); f6 = __ldg(sf + 6); }
+#endif
         c2_0 = rb_mk3(f0.x, f0.y, f0.z); c2_1 = rb_mk3(f1.x, f1.y, f1.z); c2_2 = rb_mk3(f2.x, f2.y, f2.z);
     }
     rb_v3 nObj;

@@ -108,6 +108,13 @@ __device__ __forceinline__ float4 ld_bvh(const float4* p, unsigned long long pol
 __device__ __forceinline__ unsigned long long bvh_policy() { return 0ull; }
 __device__ __forceinline__ float4 ld_bvh(const float4* p, unsigned long long) { return __ldg(p); }
 #endif
+#if RB_WIDE_LOADS
+// two consecutive float4 of a 32-byte aligned record with one 256-bit read-only load (LDG.E.256.CONSTANT)
+__device__ __forceinline__ void ld_bvh2(const float4* p, float4& a, float4& b, unsigned long long) {
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+#endif
 
 // The first RB_TSTACK_N triangle groups a lane queues during a chunk live in shared memory, the rest (a lane queues
 // more than 4 groups in 2 % of its chunks) in local memory: with RB_WORK_CAP 128 a block then needs 38 KB instead of
@@ -115,6 +122,13 @@ __device__ __forceinline__ float4 ld_bvh(const float4* p, unsigned long long) { 
 #ifndef RB_TSTACK_N
 #define RB_TSTACK_N RB_CHUNK
 #endif
+// Chunk length of the any-hit kernels (<= RB_CHUNK, which sizes the triangle-group lists): a shadow ray ends with its
+// first hit, so testing the queued triangles sooner saves node steps that a found hit makes useless. B200, headline
+// step, k_shadow ms: 3 / 4 / 5 / 6 steps 10.55 / 10.35 / 10.36 / 10.55.
+#ifndef RB_CHUNK_ANY
+#define RB_CHUNK_ANY 4
+#endif
+static_assert(RB_CHUNK_ANY <= RB_CHUNK, "the triangle-group lists hold RB_CHUNK entries");
 
 // per-warp staging area of the pooled triangle phase
 template <bool TSTACK> struct WarpTStack { };
@@ -246,7 +260,12 @@ struct Traversal {
         const uint32_t slot = (bitIndex - 24u) ^ oct_inv;
         const uint32_t rel = __popc(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
         const float4* np = reinterpret_cast<const float4*>(nodes + (base + rel));
+#if RB_WIDE_LOADS
+        float4 n0, n1, n2, n3, n4, npad;
+        ld_bvh2(np + 0, n0, n1, pol); ld_bvh2(np + 2, n2, n3, pol); ld_bvh2(np + 4, n4, npad, pol);
+#else
         const float4 n0 = ld_bvh(np + 0, pol), n1 = ld_bvh(np + 1, pol), n2 = ld_bvh(np + 2, pol), n3 = ld_bvh(np + 3, pol), n4 = ld_bvh(np + 4, pol);
+#endif
         if (COUNT) nodeVisits++;
 
         const uint32_t eim = __float_as_uint(n0.w);
@@ -385,7 +404,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
         // ballot per step — was measured at -12 / -14 / -18 % closest-hit rays/s: the fixed chunk stays)
         if (has) {
 #pragma unroll 1
-            for (int it = 0; it < RB_CHUNK; it++) {
+            for (int it = 0; it < (ANY ? RB_CHUNK_ANY : RB_CHUNK); it++) {
                 if (!tr.want_node() && !tr.pop(ws)) break;
                 tr.node_step(nodes, tris, nodeVisits, ws, pol);
             }
@@ -419,7 +438,10 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                     triIdx = item >> 5; owner = item & 31u;
                     const float4 r0 = ws.ray[owner][0], r1 = ws.ray[owner][1], r2 = ws.ray[owner][2];
                     const float4* tp = reinterpret_cast<const float4*>(tris + triIdx);
-#if RB_TRI_LDCG
+#if RB_WIDE_LOADS
+                    float4 va, vb, vc, vpad;
+                    ld_bvh2(tp + 0, va, vb, pol); ld_bvh2(tp + 2, vc, vpad, pol);
+#elif RB_TRI_LDCG
                     // triangles are read about once per ray: keep them out of L1 so that it holds wide nodes
                     const float4 va = __ldcg(tp + 0), vb = __ldcg(tp + 1), vc = __ldcg(tp + 2);
 #else

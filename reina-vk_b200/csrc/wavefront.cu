@@ -134,11 +134,10 @@ __device__ __forceinline__ void begin_path(const WaveParams& P, uint32_t slot, u
     const uint32_t x = pixel % P.W, y = pixel / P.W;
     rb_v3 o, d;
     starting_ray(P.pc, (float)x, (float)y, (float)P.W, (float)P.H, rng, o, d);
-    P.rayO[slot] = make_float4(o.x, o.y, o.z, 0.f);
-    P.rayD[slot] = make_float4(d.x, d.y, d.z, 0.f);
-    P.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);     // throughput 1, accumulatedDistance 0 (documented deviation)
+    store_pair(P.rayO, P.rayD, slot, make_float4(o.x, o.y, o.z, 0.f), make_float4(d.x, d.y, d.z, 0.f));
+    // throughput 1, accumulatedDistance 0 (documented deviation)
+    store_pair(P.thr, P.st, slot, make_float4(1.f, 1.f, 1.f, 0.f), make_uint4(rng, F_FIRST, sampleIdx, 0u));
     P.rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-    P.st[slot] = make_uint4(rng, F_FIRST, sampleIdx, 0u);
 }
 
 // Starts batch `sampleBatch` in lane `lane` of the engine: one camera path per pixel, appended to the ray queue that the
@@ -192,7 +191,8 @@ __global__ void __launch_bounds__(RB_TRAV_BLOCK, RB_TRAV_MINBLOCKS) k_extend(Wav
         P.S.nodes, P.S.tris, n, &cnt[CNT_CURSOR_EXTEND],
         [&](uint32_t i, rb_v3& o, rb_v3& d, float& tmax) {
             const uint32_t slot = q[i];
-            const float4 o4 = P.rayO[slot], d4 = P.rayD[slot];
+            float4 o4, d4;
+            load_pair(P.rayO, P.rayD, slot, o4, d4);
             o = rb_mk3(o4.x, o4.y, o4.z); d = rb_mk3(d4.x, d4.y, d4.z); tmax = 10000.0f;
         },
         [&](uint32_t i, const RayHit& h) {
@@ -284,18 +284,30 @@ __device__ __forceinline__ bool surface_prologue(const WaveParams& P, const RB20
 __device__ __forceinline__ void finish_slot(const WaveParams& P, const uint32_t slot, const rb_v3 L, const uint4 st,
                                             const uint32_t extendRays, uint32_t* cntNext, int parity, LaneAcc& acc) {
     const uint32_t lane = lane_of(P, slot);
-    atomicAdd(&acc.rays[lane], (unsigned long long)extendRays | ((unsigned long long)st.w << 32));
+    const uint32_t sampleIdx = st.z + 1u;
+    const bool restart = sampleIdx < P.pc.samplesPerPixel;
+    {
+        // One shared-memory atomic per engine lane and warp instead of one per thread: a 64-bit shared atomicAdd is a
+        // compare-and-swap loop, and the threads of a warp mostly end paths of the same lane (same address): the miss
+        // shader spent 24 of its 45 stall cycles per issue there (short scoreboard, profiles/r02b).
+        const uint32_t peers = __match_any_sync(__activemask(), lane);
+        const uint32_t ext = __reduce_add_sync(peers, extendRays);
+        const uint32_t shd = __reduce_add_sync(peers, st.w);
+        const uint32_t started = __reduce_add_sync(peers, restart ? 1u : 0u);
+        if ((int)(threadIdx.x & 31u) == __ffs(peers) - 1) {
+            atomicAdd(&acc.rays[lane], (unsigned long long)ext | ((unsigned long long)shd << 32));
+            if (started) atomicAdd(&acc.started[lane], started);
+        }
+    }
     const rb_v3 c = rb_clamp3_keepnan(L, 0.0f, P.pc.directClamp);
     float4 s4 = P.sum[slot];
     uint32_t actual = __float_as_uint(s4.w);
     if (!rb_anynan3(c)) { actual += 1u; s4.x += c.x; s4.y += c.y; s4.z += c.z; }
-    const uint32_t sampleIdx = st.z + 1u;
-    if (sampleIdx < P.pc.samplesPerPixel) {
+    if (restart) {
         P.sum[slot] = make_float4(s4.x, s4.y, s4.z, __uint_as_float(actual));
         uint32_t rng = st.x;
         begin_path(P, slot, slot - lane * P.N, rng, sampleIdx);
         queue_push(P.rayQ[parity ^ 1], &cntNext[CNT_RAYS], slot);
-        atomicAdd(&acc.started[lane], 1u);
         return;
     }
     // last sample of the pixel: this batch's mean over the valid samples (rgen.glsl:275); folded into the image by
@@ -423,10 +435,11 @@ __device__ __forceinline__ void eval_hit(const WaveParams& P, const uint4 h, con
 
 template <int MAT>
 __device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t slot, uint32_t* cnt, uint32_t* cntNext, int parity, LaneAcc& acc) {
-    const float4 ro4 = P.rayO[slot], rd4 = P.rayD[slot];
+    float4 ro4, rd4, T4;
+    uint4 st;
+    load_pair(P.rayO, P.rayD, slot, ro4, rd4);
+    load_pair(P.thr, P.st, slot, T4, st);
     const rb_v3 rayOrigin = rb_mk3(ro4.x, ro4.y, ro4.z), rayDir = rb_mk3(rd4.x, rd4.y, rd4.z);
-    uint4 st = P.st[slot];
-    float4 T4 = P.thr[slot];
     rb_v3 T = rb_mk3(T4.x, T4.y, T4.z);
     float accDist = T4.w;
     uint32_t rng = st.x;
@@ -445,7 +458,9 @@ __device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t s
         return;
     }
 
-    const uint4 h = P.hit[slot];
+    uint4 h;
+    float4 radIn;          // the path's radiance so far: the other half of the hit record's sector
+    load_pair(P.hit, P.rad, slot, h, radIn);
     const bool prevInside = (flags & F_INSIDE) != 0u;
     ShadeOut o;
     Surf s;
@@ -454,8 +469,7 @@ __device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t s
     eval_hit<MAT>(P, h, rayOrigin, rayDir, prevInside, rng, accDist, o, s, props, didRefract);
 
     // ---- what raygen does after traceRayEXT returns (rgen.glsl:124-181) ----
-    P.rayO[slot] = make_float4(o.newO.x, o.newO.y, o.newO.z, 0.f);
-    P.rayD[slot] = make_float4(o.newD.x, o.newD.y, o.newD.z, 0.f);
+    store_pair(P.rayO, P.rayD, slot, make_float4(o.newO.x, o.newO.y, o.newO.z, 0.f), make_float4(o.newD.x, o.newD.y, o.newD.z, 0.f));
     const bool leftDielectric = !o.inside && prevInside;
     segments += 1u;
     uint32_t newFlags = (flags & (F_FIRST | F_PREVSKIP)) | (o.inside ? F_INSIDE : 0u);
@@ -464,7 +478,7 @@ __device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t s
             const rb_v3 indirect = o.emission;
             const bool skipNEE = !nee || (MAT != 0 && MAT != 3);
             if (skipNEE) {
-                const float4 L4 = P.rad[slot];
+                const float4 L4 = radIn;
                 const rb_v3 combined = rb_splat3(0.0f) * 0.0f + indirect * 1.0f;
                 const rb_v3 L = rb_mk3(L4.x, L4.y, L4.z) + combined * T;
                 P.rad[slot] = make_float4(L.x, L.y, L.z, 0.f);
@@ -513,14 +527,15 @@ __device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t s
         }
         newFlags &= ~F_FIRST;
     }
-    P.thr[slot] = make_float4(T.x, T.y, T.z, accDist);
-    P.st[slot] = make_uint4(rng, newFlags | (segments << 8), st.z, st.w);
+    store_pair(P.thr, P.st, slot, make_float4(T.x, T.y, T.z, accDist), make_uint4(rng, newFlags | (segments << 8), st.z, st.w));
     if (segments < P.pc.maxBounces) queue_push(P.rayQ[parity ^ 1], &cntNext[CNT_RAYS], slot);
     else queue_push(P.endQ, &cnt[CNT_END], slot);
 }
 
+// 5 resident blocks of 128 threads = 96 registers: with the 256-bit state accesses ptxas otherwise takes 102-108 and the
+// fifth block is lost (Lambertian 3.48 -> 3.28 ms per step with the cap, no spill).
 #ifndef RB_SHADE_MINBLOCKS
-#define RB_SHADE_MINBLOCKS 1
+#define RB_SHADE_MINBLOCKS 5
 #endif
 #ifndef RB_SHADE_BLOCK
 #define RB_SHADE_BLOCK 128       // threads per block of the shading kernels (85-119 registers: smaller blocks pack an SM's register file better)
@@ -528,6 +543,41 @@ __device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t s
 #ifndef RB_DISNEY_MINBLOCKS
 #define RB_DISNEY_MINBLOCKS 1
 #endif
+// RB_SHADE_PREFETCH=1: software pipeline of the shading kernels' gathers — while item k is shaded, the path-state line
+// of item k+2 and the shading records of item k+1 (whose hit record arrived with the line requested one iteration
+// earlier) are requested into L2 with prefetch.global.L2. The idea: a queue item costs a chain of dependent fetches
+// (queue entry -> 128-byte state line -> shading records) and the kernels wait on it (12 warps per scheduler on a long
+// scoreboard per issue, 26 % of the issue slots used, DRAM at 1.7 of 6.5 TB/s, profiles/r02b). MEASURED ON B200: WORSE —
+// Lambertian 3.84 -> 5.48 ms, Disney 4.05 -> 4.82 ms, miss 2.30 -> 3.22 ms per step, with or without a register cap
+// that keeps the fifth resident block (profiles/r02d_variant_sweep.txt). Every prefetch of a scattered address is one
+// more L1 -> L2 request per lane, and the request rate of that path, not the latency behind it, is what these kernels
+// run into; the pipeline doubles the requests. Kept as a switch, off.
+#ifndef RB_SHADE_PREFETCH
+#define RB_SHADE_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_state_line(const WaveParams& P, uint32_t slot, bool withSum) {
+    const char* line = reinterpret_cast<const char*>(P.rayO.p + (size_t)slot * STATE_STRIDE);
+    if (RB_PAIR_STATE == 2) {
+        prefetch_l2(line); prefetch_l2(line + 32); prefetch_l2(line + 64);
+        if (withSum) prefetch_l2(line + 96);
+    }
+}
+template <int MAT>
+__device__ __forceinline__ void prefetch_hit_records(const DeviceScene& S, uint32_t tri, uint32_t instance) {
+#if RB_SHADE_RECORDS && RB_INST_RECORDS
+    const char* sb = reinterpret_cast<const char*>(S.shadeBase + 4 * (size_t)tri);
+    prefetch_l2(sb); prefetch_l2(sb + 32);
+    const RB200InstanceProperties* props = &S.instProps[instance];
+    const bool tbn = MAT == 3 || __ldg(&props->normalMapTexID) >= 0 || __ldg(&props->bumpMapTexID) >= 0;
+    if (tbn || __ldg(&props->interpNormals) != 0u) {
+        const char* sf = reinterpret_cast<const char*>(S.shadeFrame + 8 * (size_t)tri);
+        prefetch_l2(sf); prefetch_l2(sf + 32);
+        if (tbn) { prefetch_l2(sf + 64); prefetch_l2(sf + 96); }
+    }
+#endif
+}
+
 template <int MAT>
 __global__ void __launch_bounds__(RB_SHADE_BLOCK, MAT == 3 ? RB_DISNEY_MINBLOCKS : RB_SHADE_MINBLOCKS) k_shade(WaveParams P, int parity) {
     uint32_t* cnt = P.counters + parity * CNT_SET;
@@ -536,8 +586,27 @@ __global__ void __launch_bounds__(RB_SHADE_BLOCK, MAT == 3 ? RB_DISNEY_MINBLOCKS
     const uint32_t* __restrict__ q = P.matQ[MAT];
     __shared__ LaneAcc acc;           // only the miss shader ends paths
     if (MAT == 4) lane_acc_init(acc);
+#if RB_SHADE_PREFETCH
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t NONE = 0xFFFFFFFFu;
+    uint32_t slot = i < n ? q[i] : NONE;
+    uint32_t slotNext = i + stride < n && i + stride >= i ? q[i + stride] : NONE;
+    if (slotNext != NONE) prefetch_state_line(P, slotNext, MAT == 4);
+    for (; slot != NONE; i += stride) {
+        const uint32_t i2 = i + 2u * stride;
+        uint32_t slotNext2 = NONE;
+        if (i2 < n && i2 >= i) { slotNext2 = q[i2]; prefetch_state_line(P, slotNext2, MAT == 4); }
+        uint4 hitNext = make_uint4(0u, 0u, 0u, 0u);
+        if (MAT != 4 && slotNext != NONE) hitNext = P.hit[slotNext];      // requested now, needed after this item is shaded
+        shade_slot<MAT>(P, slot, cnt, cntNext, parity, acc);
+        if (MAT != 4 && slotNext != NONE) prefetch_hit_records<MAT>(P.S, hitNext.z, hitNext.w);
+        slot = slotNext; slotNext = slotNext2;
+    }
+#else
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         shade_slot<MAT>(P, q[i], cnt, cntNext, parity, acc);
+#endif
     if (MAT == 4) lane_acc_flush(P, acc);
 }
 
@@ -1268,6 +1337,13 @@ template <class K> static int persistent_grid(K kernel, int numSMs, int block = 
     static const char* carve = getenv("RB200_SMEM_CARVEOUT");
     if (dynSmem && carve) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(carve));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, block, dynSmem) != cudaSuccess || perSM < 1) perSM = 1;
+    // RB200_TRAV_BLOCKS_PER_SM / RB200_SHADE_BLOCKS_PER_SM=<n>: cap the resident blocks of the traversal (dynamic shared
+    // memory) / the other persistent kernels below what fits, leaving room for the other engine's kernels to co-reside
+    // (developer aid for the co-scheduling experiment of profiles/r02_summary.md)
+    static const char* capTrav = getenv("RB200_TRAV_BLOCKS_PER_SM");
+    static const char* capShade = getenv("RB200_SHADE_BLOCKS_PER_SM");
+    const char* cap = dynSmem ? capTrav : capShade;
+    if (cap && atoi(cap) >= 1) perSM = std::min(perSM, atoi(cap));
     return numSMs * perSM;
 }
 

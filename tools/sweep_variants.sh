@@ -12,7 +12,7 @@ if [ ${#names[@]} -eq 0 ]; then names=(default $(ls reina-vk_b200/csrc/variants/
 for n in "${names[@]}"; do
   lib=""; [ "$n" != default ] && lib="$PWD/reina-vk_b200/csrc/variants/$n.so"
   echo "== $n $SWEEP_ENV" | tee -a $out
-  env $SWEEP_ENV RB200_LIBRARY=$lib timeout 300 python tools/trav_bench.py 2>&1 | tail -1 | tee -a $out
+  if [ "${SWEEP_TRAV:-1}" != 0 ]; then env $SWEEP_ENV RB200_LIBRARY=$lib timeout 300 python tools/trav_bench.py 2>&1 | tail -1 | tee -a $out; fi
   if [ "${SWEEP_BENCH:-1}" != 0 ]; then
     env $SWEEP_ENV RB200_LIBRARY=$lib timeout 600 python bench.py --steps ${SWEEP_STEPS:-8} --warmup 4 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import json,sys
