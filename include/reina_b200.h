@@ -65,8 +65,15 @@ enum {
     RB200_FLAG_COUNT_BVH = 1u << 2,  /* counting build: also count wide-node visits and triangle tests per ray */
     RB200_FLAG_GROUP_TILES = 1u << 4, /* rb200_group_create only: latency mode — every device traces its interleaved 32 x 32
                                        * tiles of every batch instead of every n-th batch of all pixels */
-    RB200_FLAG_TIME_KERNELS = 1u << 3 /* bracket every kernel of rb200_render_batch with CUDA events (per-class device
+    RB200_FLAG_TIME_KERNELS = 1u << 3, /* bracket every kernel of rb200_render_batch with CUDA events (per-class device
                                         times for the roofline report; serialises nothing but adds event overhead) */
+    RB200_FLAG_TWO_LEVEL = 1u << 5   /* scenes of this context keep the reference's two-level structure (src/scene/Scene.cpp:
+                                        93-111: ONE hierarchy per distinct object, a top-level hierarchy over the instances;
+                                        rays are moved into object space with the inverse instance transform, as the Vulkan
+                                        driver does) instead of flattening every instance into world-space triangles. Triangle
+                                        and shading records are then stored once per object, not once per instance. Slower per
+                                        ray (a ray set-up per visited instance); results differ from the flattened path in the
+                                        last bits of t (object-space arithmetic). Singular instance transforms are refused. */
 };
 
 /* ------------------------------------------------------------------------------------------------ */

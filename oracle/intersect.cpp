@@ -35,6 +35,44 @@ void flatten_scene(Scene& s) {
     }
 }
 
+// Two-level mode: the distinct model ranges in object space (flattened with the identity, so the vertex values go through
+// the same rb_m4_point as the kernels' BLAS build) and the inverse transform of every instance.
+bool build_two_level(Scene& s, bool withBvh) {
+    static const float identity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    s.blas.clear(); s.tl.clear();
+    std::vector<std::pair<uint32_t, uint32_t>> ranges;
+    uint32_t gidBase = 0;
+    for (uint32_t i = 0; i < s.instances.size(); i++) {
+        const RB200Instance& in = s.instances[i];
+        const std::pair<uint32_t, uint32_t> key(in.indexOffset, in.triangleCount);
+        uint32_t b = 0;
+        while (b < ranges.size() && ranges[b] != key) b++;
+        if (b == ranges.size()) {
+            ranges.push_back(key);
+            s.blas.emplace_back();
+            Scene& sub = s.blas.back();
+            for (uint32_t p = 0; p < in.triangleCount; p++) {
+                WorldTri t;
+                vec3 v[3];
+                for (int k = 0; k < 3; k++) {
+                    uint32_t vi = s.indices[3 * p + in.indexOffset + k];
+                    v[k] = rb_m4_point(identity, rb_mk3(s.vertices[4 * vi + 0], s.vertices[4 * vi + 1], s.vertices[4 * vi + 2]));
+                }
+                t.v0 = v[0]; t.v1 = v[1]; t.v2 = v[2]; t.instance = i; t.primitive = p;
+                sub.tris.push_back(t);
+            }
+            if (withBvh) build_bvh(sub);
+        }
+        Scene::TwoLevelInstance ti;
+        if (!rb_affine_inverse(in.transform, ti.inv)) return false;
+        ti.blas = b; ti.gidBase = gidBase;
+        s.tl.push_back(ti);
+        gidBase += in.triangleCount;
+    }
+    s.twoLevel = true;
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // binned-SAH binary BVH (16 bins), leaves of <= 4 triangles
 // ---------------------------------------------------------------------------------------------------
@@ -177,7 +215,21 @@ static inline void test_tri(const Scene& s, uint32_t gid, vec3 org, const rb_ray
     }
 }
 
+// Two-level closest hit: every instance in order, the ray in that instance's object space, t < best so far (a later
+// instance has larger global ids, so it loses a tie: strict is the closest-hit rule). No culling of instances: the answer
+// must not depend on a TLAS.
+static Hit closest_hit_two_level(const Scene& s, vec3 org, vec3 dir, float tmax, bool brute, uint64_t* tri_tests) {
+    Hit best; best.valid = false; best.t = tmax; best.b1 = best.b2 = 0; best.gid = 0xFFFFFFFFu;
+    for (size_t i = 0; i < s.tl.size(); i++) {
+        const Scene::TwoLevelInstance& ti = s.tl[i];
+        const Hit h = closest_hit(s.blas[ti.blas], rb_inv_point(ti.inv, org), rb_inv_vector(ti.inv, dir), best.t, brute, tri_tests);
+        if (h.valid) { best = h; best.gid = ti.gidBase + h.gid; }
+    }
+    return best;
+}
+
 Hit closest_hit(const Scene& s, vec3 org, vec3 dir, float tmax, bool brute, uint64_t* tri_tests) {
+    if (s.twoLevel) return closest_hit_two_level(s, org, dir, tmax, brute, tri_tests);
     Hit best; best.valid = false; best.t = tmax; best.b1 = best.b2 = 0; best.gid = 0xFFFFFFFFu;
     rb_ray_shear sh = rb_ray_prepare(dir);
     if (brute || !s.useBvh) {
@@ -212,6 +264,13 @@ Hit closest_hit(const Scene& s, vec3 org, vec3 dir, float tmax, bool brute, uint
 }
 
 bool any_hit(const Scene& s, vec3 org, vec3 dir, float tmax, bool brute) {
+    if (s.twoLevel) {
+        for (size_t i = 0; i < s.tl.size(); i++) {
+            const Scene::TwoLevelInstance& ti = s.tl[i];
+            if (any_hit(s.blas[ti.blas], rb_inv_point(ti.inv, org), rb_inv_vector(ti.inv, dir), tmax, brute)) return true;
+        }
+        return false;
+    }
     rb_ray_shear sh = rb_ray_prepare(dir);
     if (brute || !s.useBvh) {
         for (uint32_t g = 0; g < s.tris.size(); g++) {

@@ -2,6 +2,7 @@
 // cpu_baseline / --impl reference legs through ctypes. Mirrors the shape of include/reina_b200.h so that the same
 // RB200SceneDesc / RB200RtPushConsts blocks feed both sides.
 #include "oracle_common.h"
+#include <algorithm>
 #include <thread>
 #include <cstring>
 #include <string>
@@ -59,6 +60,15 @@ ORACLE_API int oracle_scene_create(const RB200SceneDesc* d, int bvh_threshold, v
     if ((int)s->tris.size() > bvh_threshold) build_bvh(*s);
     *out = s;
     return 0;
+}
+
+// Switch the scene to two-level intersection (object-space BLAS per distinct model range + inverse instance transforms,
+// src/scene/Scene.cpp:93-111). Returns -2 if an instance transform is singular.
+ORACLE_API int oracle_scene_set_two_level(void* scene, int bvh_threshold) {
+    Scene* s = (Scene*)scene;
+    size_t largest = 0;
+    for (const RB200Instance& in : s->instances) largest = std::max<size_t>(largest, in.triangleCount);
+    return build_two_level(*s, (int)largest > bvh_threshold) ? 0 : -2;
 }
 
 ORACLE_API int oracle_scene_destroy(void* scene) { delete (Scene*)scene; return 0; }

@@ -75,11 +75,21 @@ struct Scene {
     std::vector<BvhNode> nodes;
     std::vector<uint32_t> bvhTriOrder;      // leaf slots -> gid
     bool useBvh = false;
+
+    // Two-level instancing (src/scene/Scene.cpp:93-111: one BLAS per object, a transform per instance): rays are moved into
+    // object space with the inverse instance transform and intersected with the object's triangles there, as the Vulkan
+    // driver does with its TLAS / BLAS. `blas[b]` holds the object-space triangles (and hierarchy) of one distinct model
+    // range, `tl[i]` what instance i needs. `tris` above stays filled (gid -> instance, primitive).
+    struct TwoLevelInstance { float inv[12]; uint32_t blas; uint32_t gidBase; };
+    bool twoLevel = false;
+    std::vector<Scene> blas;
+    std::vector<TwoLevelInstance> tl;
 };
 
 // intersect.cpp
 void flatten_scene(Scene& s);
 void build_bvh(Scene& s);
+bool build_two_level(Scene& s, bool withBvh);      // false: an instance transform is singular
 Hit closest_hit(const Scene& s, vec3 org, vec3 dir, float tmax, bool brute, uint64_t* tri_tests = nullptr);
 bool any_hit(const Scene& s, vec3 org, vec3 dir, float tmax, bool brute);
 

@@ -17,6 +17,7 @@ RB200_FLAG_ACCUM_SUM = 1 << 1
 RB200_FLAG_COUNT_BVH = 1 << 2
 RB200_FLAG_TIME_KERNELS = 1 << 3
 RB200_FLAG_GROUP_TILES = 1 << 4
+RB200_FLAG_TWO_LEVEL = 1 << 5
 
 
 class InstanceProperties(C.Structure):

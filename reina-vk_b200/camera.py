@@ -57,6 +57,18 @@ def scale(s):
     return m
 
 
+def rotate(axis, angle):
+    """Rotation by `angle` radians about `axis`, glm layout (m[c][r])."""
+    a = np.asarray(axis, np.float64)
+    a = a / np.linalg.norm(a)
+    c, s_ = np.cos(angle), np.sin(angle)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    R = np.eye(3) * c + s_ * K + (1 - c) * np.outer(a, a)
+    m = np.eye(4, dtype=np.float64)
+    m[:3, :3] = R
+    return m.T.astype(np.float32)
+
+
 def compose(*ms):
     """Mathematical product M0 * M1 * ... for matrices in glm layout (m[c][r])."""
     out = np.eye(4, dtype=np.float64)

@@ -9,7 +9,7 @@ the stand-ins are labelled as such in bench output (`data`: "synthetic").
 import numpy as np
 
 from . import meshes
-from .camera import compose, push_constants, scale, translate
+from .camera import compose, push_constants, rotate, scale, translate
 from .scene import Material, Scene
 
 IDENT = np.eye(4, dtype=np.float32)
@@ -264,3 +264,35 @@ def small_mixed(width=160, height=120, nee=True, samples_per_pixel=2, max_bounce
     pc = dict(pos=(0.0, 1.0, 3.9), look=(0.0, 1.0, 0.0), fovy_deg=40.0, samples_per_pixel=samples_per_pixel,
               max_bounces=max_bounces)
     return Workload("small_mixed", tables, width, height, pc, nee, 2)
+
+
+def instanced(width=160, height=120, grid=4, segments=24, rings=12, nee=True, samples_per_pixel=2, max_bounces=8, seed=11):
+    """grid x grid instances of ONE sphere model and as many of ONE box-ish blob, each with its own rotation, non-uniform
+    scale, translation and material, over the Cornell box and its light: what the reference's Scene keeps as one BLAS per
+    object and a TLAS entry per instance (src/scene/Scene.cpp:93-111). Workload of the two-level tests."""
+    rng = np.random.RandomState(seed)
+    s = Scene()
+    s.addObject(meshes.cornell_box(), IDENT, Material(**CORNELL_WALL))
+    s.addObject(meshes.cornell_light(), IDENT, Material(**LIGHT))
+    sph = s.defineObject(meshes.uv_sphere(segments, rings, radius=1.0))
+    blob = s.defineObject(meshes.subdivided_blob(levels=2, seed=0x51, displacement=0.3, radius=1.0))
+    mats = [dict(materialIdx=0, albedo=(0.8, 0.5, 0.3)),
+            dict(materialIdx=1, albedo=(0.9, 0.8, 0.5), roughness=0.2, interpNormals=True),
+            dict(GLASS),
+            dict(materialIdx=3, albedo=(0.5, 0.4, 0.8), roughness=0.35, ior=1.5, interpNormals=True, metallic=0.4,
+                 clearcoat=0.5, clearcoatGloss=0.6, sheenTint=(1, 1, 1), specularTint=(1, 1, 1))]
+    k = 0
+    for iy in range(grid):
+        for ix in range(grid):
+            for obj, lift in ((sph, 0.0), (blob, 0.45)):
+                r = 0.32 / grid * (1.0 + 0.5 * rng.rand())
+                pos = (-0.75 + 1.5 * (ix + 0.5) / grid + 0.02 * rng.randn(), 0.18 + lift + 0.9 * rng.rand() * (lift + 0.2),
+                       -0.75 + 1.5 * (iy + 0.5) / grid + 0.02 * rng.randn())
+                M = compose(translate(pos), rotate(rng.randn(3), rng.rand() * 6.28),
+                            scale((r, r * (0.6 + 0.8 * rng.rand()), r * (0.6 + 0.8 * rng.rand()))))
+                s.addInstance(obj, M, Material(**mats[k % 4]))
+                k += 1
+    tables = s.build(require_emitter=nee)
+    pc = dict(pos=(0.0, 1.0, 3.9), look=(0.0, 0.8, 0.0), fovy_deg=40.0, samples_per_pixel=samples_per_pixel,
+              max_bounces=max_bounces)
+    return Workload("instanced", tables, width, height, pc, nee, 2)

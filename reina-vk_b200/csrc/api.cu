@@ -310,8 +310,24 @@ RB200_API int rb200_scene_create(RB200Context* ctx, const RB200SceneDesc* d, RB2
         else { set_error("RB200_BVH_BUILDER must be lbvh or ploc"); rb200_scene_destroy(sc); return RB200_ERR_INVALID_ARGUMENT; }
     }
     BuildInput bi{D.vertices, D.indices, D.instances, &sc->hostInstances, d->numInstances, builder};
-    rc = build_bvh(bi, s, &sc->bvh, &ctx->launches);
-    if (rc != RB200_OK) { rb200_scene_destroy(sc); return rc; }
+    D.tlasNodes = nullptr; D.tlasLeaves = nullptr; D.tlInstances = nullptr;
+    if (ctx->flags & RB200_FLAG_TWO_LEVEL) {
+        // the reference's structure (src/scene/Scene.cpp:93-111): a hierarchy per distinct object in object space + one over
+        // the instances; sc->bvh holds the former (its slots index the shading records), sc->tlas the latter
+        std::vector<TwoLevelInstance> entries;
+        rc = build_two_level(bi, s, &sc->bvh, &sc->tlas, &entries, &sc->numModels, &ctx->launches);
+        if (rc != RB200_OK) { rb200_scene_destroy(sc); return rc; }
+        if (2u * sc->tlas.maxDepth + sc->bvh.maxDepth + 2u > (uint32_t)TL_STACK) {
+            set_error("two-level hierarchy too deep for the traversal stack (top level %u, objects %u)", sc->tlas.maxDepth, sc->bvh.maxDepth);
+            rb200_scene_destroy(sc); return RB200_ERR_INVALID_ARGUMENT;
+        }
+        if ((rc = upload(sc, entries.data(), entries.size(), &D.tlInstances, s)) != RB200_OK) { rb200_scene_destroy(sc); return rc; }
+        SC_CUDA(cudaStreamSynchronize(s));
+        D.tlasNodes = sc->tlas.nodes; D.tlasLeaves = sc->tlas.tris;
+    } else {
+        rc = build_bvh(bi, s, &sc->bvh, &ctx->launches);
+        if (rc != RB200_OK) { rb200_scene_destroy(sc); return rc; }
+    }
     /* TRAV_MAX_DEPTH = 22: the per-lane traversal stack holds at most 2 groups per tree level */
     if (sc->bvh.maxDepth > (uint32_t)22) { set_error("BVH depth %u exceeds the traversal stack", sc->bvh.maxDepth); rb200_scene_destroy(sc); return RB200_ERR_INVALID_ARGUMENT; }
     D.nodes = sc->bvh.nodes; D.tris = sc->bvh.tris; D.numTris = sc->bvh.numTris;
@@ -374,6 +390,7 @@ RB200_API int rb200_scene_destroy(RB200Scene* sc) {
     for (cudaArray_t a : sc->texArrays) cudaFreeArray(a);
     for (void* p : sc->allocations) cudaFree(p);
     free_bvh(&sc->bvh);
+    free_bvh(&sc->tlas);
     delete sc;
     return RB200_OK;
 }
@@ -384,6 +401,11 @@ RB200_API int rb200_scene_bvh_info(const RB200Scene* scene, RB200BvhInfo* out) {
     if (!sc->hashValid) {
         int rc = hash_bvh(sc->bvh, sc->ctx->stream, &sc->hash);
         if (rc != RB200_OK) return rc;
+        if (sc->tlas.nodes) {
+            uint64_t top = 0;
+            if ((rc = hash_bvh(sc->tlas, sc->ctx->stream, &top)) != RB200_OK) return rc;
+            sc->hash = (sc->hash ^ top) * 1099511628211ull;
+        }
         sc->hashValid = true;
     }
     memset(out, 0, sizeof(*out));
@@ -393,6 +415,14 @@ RB200_API int rb200_scene_bvh_info(const RB200Scene* scene, RB200BvhInfo* out) {
     out->hash = sc->hash; out->buildMs = sc->bvh.buildMs;
     out->reserved = (uint32_t)(sc->l2PersistBytes >> 10);
     for (int a = 0; a < 3; a++) { out->sceneMin[a] = sc->bvh.sceneMin[a]; out->sceneMax[a] = sc->bvh.sceneMax[a]; }
+    if (sc->tlas.nodes) {
+        // two-level scene: the objects' hierarchies (triangles counted once per object) + the one over the instances
+        out->numWideNodes += sc->tlas.numNodes; out->maxDepth += sc->tlas.maxDepth;
+        out->nodeBytes += (uint64_t)sc->tlas.numNodes * sizeof(WideNode);
+        out->triangleBytes += (uint64_t)sc->tlas.numTris * (sizeof(TriRecord) + sizeof(TwoLevelInstance));
+        out->buildMs += sc->tlas.buildMs;
+        for (int a = 0; a < 3; a++) { out->sceneMin[a] = sc->tlas.sceneMin[a]; out->sceneMax[a] = sc->tlas.sceneMax[a]; }
+    }
     return RB200_OK;
 }
 

@@ -82,6 +82,38 @@ __global__ void k_flatten(const float4* __restrict__ verts, const uint32_t* __re
     }
 }
 
+// Premade records (BuildInput::premade: the instance boxes of the two-level mode's top level) instead of flattening:
+// copy, zero the padding, scene bounds as above.
+__global__ void k_premade(const TriRecord* __restrict__ in, uint32_t N, TriRecord* __restrict__ out, uint32_t* __restrict__ bounds) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    if (g < N) {
+        TriRecord t = in[g];
+#if RB_WIDE_LOADS
+        t.pad = make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
+        const float4 v[3] = {t.v0, t.v1, t.v2};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lo[0] = fminf(lo[0], v[k].x); lo[1] = fminf(lo[1], v[k].y); lo[2] = fminf(lo[2], v[k].z);
+            hi[0] = fmaxf(hi[0], v[k].x); hi[1] = fmaxf(hi[1], v[k].y); hi[2] = fmaxf(hi[2], v[k].z);
+        }
+        out[g] = t;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        float l = lo[a], h = hi[a];
+        for (int o = 16; o > 0; o >>= 1) {
+            l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
+            h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
+        }
+        if ((threadIdx.x & 31) == 0 && l <= h) {
+            atomicMin(&bounds[a], float_to_ordered(l));
+            atomicMax(&bounds[3 + a], float_to_ordered(h));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // 2. Morton codes (21 bits per axis of the triangle-AABB centre, normalised to the scene bounds)
 // ---------------------------------------------------------------------------------------------------
@@ -746,7 +778,7 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
     const std::vector<RB200Instance>& hi = *in.h_instances;
     std::vector<uint32_t> prefix(hi.size() + 1, 0);
     for (size_t i = 0; i < hi.size(); i++) prefix[i + 1] = prefix[i] + hi[i].triangleCount;
-    const uint32_t N = prefix.back();
+    const uint32_t N = in.premade ? in.numPremade : prefix.back();
     if (N == 0) { set_error("scene has no triangles"); return RB200_ERR_INVALID_ARGUMENT; }
     if (N >= 0x08000000u) { set_error("too many triangles (limit 2^27: the traversal packs triangle index and lane into 32 bits)"); return RB200_ERR_INVALID_ARGUMENT; }
     if (hi.size() > (size_t)TRI_INST_MASK) { set_error("too many instances (limit 2^30)"); return RB200_ERR_INVALID_ARGUMENT; }
@@ -786,7 +818,9 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
     RB_CUDA(cudaMemsetAsync(parentLeaf, 0xFF, (size_t)N * 4, stream));
 
     const uint32_t B = 256, G = (N + B - 1) / B;
-    k_flatten<<<G, B, 0, stream>>>(in.vertices, in.indices, in.d_instances, dPrefix, in.numInstances, N, unsorted, dBounds); nl++;
+    if (in.premade) k_premade<<<G, B, 0, stream>>>(in.premade, N, unsorted, dBounds);
+    else k_flatten<<<G, B, 0, stream>>>(in.vertices, in.indices, in.d_instances, dPrefix, in.numInstances, N, unsorted, dBounds);
+    nl++;
     k_morton<<<G, B, 0, stream>>>(unsorted, N, dBounds, keys[0], vals[0]); nl++;
     int cur = 0;
     for (int pass = 0; pass < 8; pass++) {
@@ -914,6 +948,138 @@ int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* lau
 
     g_arena = nullptr;      // the arena itself is released when `arena` goes out of scope
     if (launches) *launches += nl;
+    return RB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Two-level mode (RB200_FLAG_TWO_LEVEL; src/scene/Scene.cpp:93-111: a BLAS per object, a TLAS entry per instance)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_merge_nodes(const WideNode* __restrict__ in, uint32_t n, uint32_t nodeOff, uint32_t triOff, WideNode* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    WideNode w = in[i];
+    w.childBase += nodeOff; w.triBase += triOff;
+    out[i] = w;
+}
+__global__ void k_merge_tris(const TriRecord* __restrict__ in, uint32_t n, uint32_t representative, TriRecord* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TriRecord t = in[i];
+    t.v1.w = __uint_as_float(representative);      // an instance of this model: the shading records are built through it
+    out[i] = t;
+}
+
+// One hierarchy per distinct model range in OBJECT space (the existing builder on a single identity-transform instance, so
+// the vertex values are exactly the flattening path's rb_m4_point(identity, v)), merged into one node and one triangle
+// array with absolute indices; a hierarchy over the instances' padded world-space boxes; the instances' entry records.
+int build_two_level(const BuildInput& in, cudaStream_t stream, Bvh* blas, Bvh* tlas, std::vector<TwoLevelInstance>* entries,
+                    uint32_t* numModels, uint64_t* launches) {
+    const std::vector<RB200Instance>& hi = *in.h_instances;
+    struct Model { uint32_t indexOffset, triangleCount, representative; Bvh bvh; uint32_t nodeOff, triOff; };
+    std::vector<Model> models;
+    std::vector<uint32_t> modelOf(hi.size());
+    for (size_t i = 0; i < hi.size(); i++) {
+        size_t m = 0;
+        while (m < models.size() && !(models[m].indexOffset == hi[i].indexOffset && models[m].triangleCount == hi[i].triangleCount)) m++;
+        if (m == models.size()) { Model mm{}; mm.indexOffset = hi[i].indexOffset; mm.triangleCount = hi[i].triangleCount; mm.representative = (uint32_t)i; models.push_back(mm); }
+        modelOf[i] = (uint32_t)m;
+    }
+    auto release = [&]() { for (Model& m : models) free_bvh(&m.bvh); };
+    RB200Instance* dOne = nullptr;
+    if (cudaMalloc(&dOne, sizeof(RB200Instance)) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory"); return RB200_ERR_OUT_OF_MEMORY; }
+    uint32_t totalNodes = 0, totalTris = 0, maxDepth = 0;
+    float buildMs = 0.f;
+    for (Model& m : models) {
+        RB200Instance one = hi[m.representative];
+        static const float identity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        memcpy(one.transform, identity, sizeof identity);
+        std::vector<RB200Instance> hone(1, one);
+        cudaError_t e = cudaMemcpyAsync(dOne, &one, sizeof one, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { set_error("two-level build: %s", cudaGetErrorString(e)); cudaFree(dOne); release(); return RB200_ERR_CUDA; }
+        BuildInput bi{in.vertices, in.indices, dOne, &hone, 1u, in.builder};
+        const int rc = build_bvh(bi, stream, &m.bvh, launches);
+        if (rc != RB200_OK) { cudaFree(dOne); release(); return rc; }
+        m.nodeOff = totalNodes; m.triOff = totalTris;
+        totalNodes += m.bvh.numNodes; totalTris += m.bvh.numTris;
+        maxDepth = std::max(maxDepth, m.bvh.maxDepth);
+        buildMs += m.bvh.buildMs;
+    }
+    cudaFree(dOne);
+    if (totalTris >= 0x08000000u) { set_error("too many triangles (limit 2^27)"); release(); return RB200_ERR_INVALID_ARGUMENT; }
+
+    const size_t nodeBytes = ((size_t)totalNodes * sizeof(WideNode) + 255) & ~(size_t)255;
+    blas->blobBytes = nodeBytes + (size_t)totalTris * sizeof(TriRecord);
+    if (cudaMalloc(&blas->blob, blas->blobBytes) != cudaSuccess) { cudaGetLastError(); blas->blob = nullptr; set_error("out of device memory (two-level hierarchy)"); release(); return RB200_ERR_OUT_OF_MEMORY; }
+    blas->nodes = reinterpret_cast<WideNode*>(blas->blob);
+    blas->tris = reinterpret_cast<TriRecord*>(reinterpret_cast<char*>(blas->blob) + nodeBytes);
+    for (Model& m : models) {
+        k_merge_nodes<<<(m.bvh.numNodes + 127) / 128, 128, 0, stream>>>(m.bvh.nodes, m.bvh.numNodes, m.nodeOff, m.triOff, blas->nodes + m.nodeOff);
+        k_merge_tris<<<(m.bvh.numTris + 127) / 128, 128, 0, stream>>>(m.bvh.tris, m.bvh.numTris, m.representative, blas->tris + m.triOff);
+        if (launches) *launches += 2;
+    }
+    {
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error("two-level build: %s", cudaGetErrorString(e)); release(); free_bvh(blas); return RB200_ERR_CUDA; }
+    }
+    blas->numNodes = totalNodes; blas->numTris = totalTris; blas->maxDepth = maxDepth; blas->buildMs = buildMs;
+
+    // entry records and world-space boxes of the instances
+    entries->assign(hi.size(), TwoLevelInstance{});
+    std::vector<TriRecord> boxes(hi.size());
+    uint32_t gid = 0;
+    for (size_t i = 0; i < hi.size(); i++) {
+        const Model& m = models[modelOf[i]];
+        TwoLevelInstance& e = (*entries)[i];
+        if (!rb_affine_inverse(hi[i].transform, e.inv)) {
+            set_error("instance %zu: the transform is singular (or not finite); two-level mode needs its inverse", i);
+            release(); free_bvh(blas); return RB200_ERR_INVALID_ARGUMENT;
+        }
+        e.rootNode = m.nodeOff; e.gidBase = gid; e.material = hi[i].materialIdx > 3u ? 3u : hi[i].materialIdx; e.pad = 0u;
+        gid += hi[i].triangleCount;
+        // world box = box of the 8 transformed corners of the model's bounds (fp64), padded: the ray is intersected with the
+        // triangles in object space after an fp32 inverse transform, so "the world ray meets the world box" and "the object ray
+        // meets a triangle" can disagree by a few 1e-7 of the coordinates involved; 2^-15 of them (and of the extent) is ample
+        const float* M = hi[i].transform;
+        double lo[3] = {1e300, 1e300, 1e300}, hb[3] = {-1e300, -1e300, -1e300}, mag = 0.0;
+        for (int c = 0; c < 8; c++) {
+            const double x = (c & 1) ? m.bvh.sceneMax[0] : m.bvh.sceneMin[0], y = (c & 2) ? m.bvh.sceneMax[1] : m.bvh.sceneMin[1],
+                         z = (c & 4) ? m.bvh.sceneMax[2] : m.bvh.sceneMin[2];
+            for (int a = 0; a < 3; a++) {
+                const double w = (double)M[a] * x + (double)M[4 + a] * y + (double)M[8 + a] * z + (double)M[12 + a];
+                lo[a] = std::min(lo[a], w); hb[a] = std::max(hb[a], w); mag = std::max(mag, std::fabs(w));
+            }
+        }
+        const double ext = std::max(std::max(hb[0] - lo[0], hb[1] - lo[1]), hb[2] - lo[2]);
+        // ... times the condition of the transform (1 for a rotation with uniform scale): the rounding of the inverse
+        // transform, mapped back to world space, grows with it
+        double fm = 0.0, fi = 0.0;
+        for (int c = 0; c < 3; c++)
+            for (int a = 0; a < 3; a++) { fm += (double)M[4 * c + a] * M[4 * c + a]; fi += (double)e.inv[4 * a + c] * e.inv[4 * a + c]; }
+        const double cond = std::max(1.0, std::sqrt(fm * fi) / 3.0);
+        const double pad = 3.0517578125e-05 * cond * (mag + ext) + 1e-30;
+        TriRecord& b = boxes[i];
+        memset(&b, 0, sizeof b);
+        float idAsFloat;
+        const uint32_t id = (uint32_t)i;
+        memcpy(&idAsFloat, &id, 4);
+        b.v0 = make_float4((float)(lo[0] - pad), (float)(lo[1] - pad), (float)(lo[2] - pad), idAsFloat);
+        b.v1 = make_float4((float)(hb[0] + pad), (float)(hb[1] + pad), (float)(hb[2] + pad), 0.f);
+        b.v2 = b.v0;
+    }
+    release();
+    TriRecord* dBoxes = nullptr;
+    if (cudaMalloc(&dBoxes, boxes.size() * sizeof(TriRecord)) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory"); free_bvh(blas); return RB200_ERR_OUT_OF_MEMORY; }
+    cudaError_t e = cudaMemcpyAsync(dBoxes, boxes.data(), boxes.size() * sizeof(TriRecord), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { set_error("two-level build: %s", cudaGetErrorString(e)); cudaFree(dBoxes); free_bvh(blas); return RB200_ERR_CUDA; }
+    BuildInput bt = in;
+    bt.premade = dBoxes; bt.numPremade = (uint32_t)boxes.size();
+    const int rc = build_bvh(bt, stream, tlas, launches);
+    cudaFree(dBoxes);
+    if (rc != RB200_OK) { free_bvh(blas); return rc; }
+    *numModels = (uint32_t)models.size();
     return RB200_OK;
 }
 

@@ -119,7 +119,28 @@ struct DeviceScene {
     // fetch the instance record and its properties side by side instead of one after the other. Null when
     // RB_INST_RECORDS is 0.
     const RB200InstanceProperties* instProps;
+    // Two-level mode (RB200_FLAG_TWO_LEVEL; null / 0 otherwise). `nodes` / `tris` then hold the object-space hierarchies of
+    // the distinct model ranges, one after the other (child and triangle indices already absolute), so a triangle slot
+    // still indexes shadeBase / shadeFrame; tlasNodes / tlasLeaves are a hierarchy over the instances' world-space boxes
+    // whose "triangles" are box records (v0 = min, v1 = max, v0.w = instance index); tlInstances[i] is what a ray needs
+    // to enter instance i.
+    const WideNode* tlasNodes;
+    const TriRecord* tlasLeaves;
+    const struct TwoLevelInstance* tlInstances;
 };
+
+// Entry record of an instance in two-level mode (64 bytes)
+struct alignas(16) TwoLevelInstance {
+    float inv[12];           // inverse of the instance transform, three rows of four (rb_inv_point / rb_inv_vector)
+    uint32_t rootNode;       // index of the root wide node of the instance's model in DeviceScene::nodes
+    uint32_t gidBase;        // global primitive id of the instance's first triangle (instance-major order, as flattening numbers them)
+    uint32_t material;       // material kernel 0..3 (as k_extend bins)
+    uint32_t pad;
+};
+static_assert(sizeof(TwoLevelInstance) == 64, "TwoLevelInstance must be 64 bytes");
+// per-lane stack of the two-level traversal (two_level.cuh): node groups and instance groups of both levels + one sentinel;
+// rb200_scene_create refuses hierarchies with 2 * depth(top level) + depth(objects) + 2 beyond it
+static constexpr int TL_STACK = 64;
 
 #ifndef RB_SHADE_RECORDS
 #define RB_SHADE_RECORDS 1
@@ -135,6 +156,10 @@ struct BuildInput {
     const std::vector<RB200Instance>* h_instances;
     uint32_t numInstances;
     int builder;       // BUILDER_*
+    // non-null: build over these `numPremade` records (device memory) instead of flattening the instances — the top level of
+    // the two-level mode, whose leaves are instance boxes
+    const TriRecord* premade = nullptr;
+    uint32_t numPremade = 0;
 };
 // Binary hierarchy under the wide-node collapse: Karras 2012 over the sorted Morton keys (the north-star pipeline) or
 // PLOC clustering of the same sorted leaves (better surface-area cost, a few more milliseconds of build).
@@ -142,6 +167,8 @@ enum { BUILDER_LBVH = 0, BUILDER_PLOC = 1 };
 
 // bvh_build.cu
 int build_bvh(const BuildInput& in, cudaStream_t stream, Bvh* out, uint64_t* launches);
+int build_two_level(const BuildInput& in, cudaStream_t stream, Bvh* blas, Bvh* tlas, std::vector<TwoLevelInstance>* entries,
+                    uint32_t* numModels, uint64_t* launches);
 int hash_bvh(const Bvh& bvh, cudaStream_t stream, uint64_t* hash);
 void free_bvh(Bvh* b);
 

@@ -7,6 +7,8 @@ struct RB200Scene {
     RB200Context* ctx = nullptr;
     rb200::DeviceScene dev{};
     rb200::Bvh bvh{};
+    rb200::Bvh tlas{};                        // RB200_FLAG_TWO_LEVEL: the hierarchy over the instances (bvh = the objects')
+    uint32_t numModels = 0;                   // distinct objects of a two-level scene
     std::vector<void*> allocations;           // device buffers owned by the scene
     std::vector<cudaArray_t> texArrays;
     std::vector<cudaTextureObject_t> texObjects;
@@ -227,7 +229,7 @@ struct RB200Context {
     rb200::Engine eng[RB_MAX_ENGINES];
     rb200::WaveParams& wp = eng[0].P;          // eng[0]'s arrays are also the scratch of the query entry points
     // persistent-grid sizes of the wave kernels on THIS device (function attributes are per device)
-    int gExtend = 0, gExtendC = 0, gShadow = 0, gShadowC = 0, gShade[5] = {0, 0, 0, 0, 0}, gFinish = 0, gQuery[2] = {0, 0};
+    int gExtend = 0, gExtendC = 0, gShadow = 0, gShadowC = 0, gShade[5] = {0, 0, 0, 0, 0}, gFinish = 0, gQuery[2] = {0, 0}, gTwoLevel[2] = {0, 0};
     uint64_t graphCaptures = 0;
     // Engine stagger (only with one lane per engine, i.e. without speculation): a batch may start once the previous
     // batch (on the previous engine) has finished wave staggerWave. Without it batches submitted faster than they render

@@ -94,6 +94,39 @@ RB_HD rb_m3 rb_m4_upper3(const float* m) {
     return r;
 }
 
+/* Two-level instancing (src/scene/Scene.cpp:93-111: one BLAS per object, a transform per instance; the Vulkan driver
+ * moves the RAY into object space, src/tools/vktools.cpp:466-468 hands it the 3x4 instance matrix). The object-space ray
+ * is inv * (o, 1), inv * (d, 0) with inv = the inverse of the instance's affine transform, three rows of four floats;
+ * t is the same parameter in both spaces because d is not re-normalised. One definition for the kernels and the oracle.
+ * rb_affine_inverse runs on the host only (fp64 cofactors, rounded once): both sides get the same twelve floats. */
+RB_HD rb_v3 rb_inv_point(const float* inv, rb_v3 p) {
+    return rb_mk3(inv[0] * p.x + inv[1] * p.y + inv[2] * p.z + inv[3],
+                  inv[4] * p.x + inv[5] * p.y + inv[6] * p.z + inv[7],
+                  inv[8] * p.x + inv[9] * p.y + inv[10] * p.z + inv[11]);
+}
+RB_HD rb_v3 rb_inv_vector(const float* inv, rb_v3 d) {
+    return rb_mk3(inv[0] * d.x + inv[1] * d.y + inv[2] * d.z,
+                  inv[4] * d.x + inv[5] * d.y + inv[6] * d.z,
+                  inv[8] * d.x + inv[9] * d.y + inv[10] * d.z);
+}
+/* m: column-major 4x4 whose last row is (0, 0, 0, 1). Returns false for a singular (or non-finite) linear part. */
+static inline bool rb_affine_inverse(const float* m, float* inv) {
+    const double a00 = m[0], a01 = m[4], a02 = m[8], a10 = m[1], a11 = m[5], a12 = m[9], a20 = m[2], a21 = m[6], a22 = m[10];
+    const double c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+    const double det = a00 * c00 + a01 * c01 + a02 * c02;
+    if (!(det != 0.0) || !(det - det == 0.0)) return false;
+    const double r[3][3] = {{c00 / det, (a02 * a21 - a01 * a22) / det, (a01 * a12 - a02 * a11) / det},
+                            {c01 / det, (a00 * a22 - a02 * a20) / det, (a02 * a10 - a00 * a12) / det},
+                            {c02 / det, (a01 * a20 - a00 * a21) / det, (a00 * a11 - a01 * a10) / det}};
+    const double tx = m[12], ty = m[13], tz = m[14];
+    for (int i = 0; i < 3; i++) {
+        inv[4 * i + 0] = (float)r[i][0]; inv[4 * i + 1] = (float)r[i][1]; inv[4 * i + 2] = (float)r[i][2];
+        inv[4 * i + 3] = (float)(-(r[i][0] * tx + r[i][1] * ty + r[i][2] * tz));
+    }
+    for (int i = 0; i < 12; i++) if (!(inv[i] - inv[i] == 0.0f)) return false;
+    return true;
+}
+
 /* Wächter & Binder self-intersection offset, shaders/raytrace/closestHitCommon.h.glsl:156-177.
  * Integer arithmetic on the fp32 bit patterns: must be (and is) bit-exact everywhere. */
 RB_HD float rb_offset_component(float p, float n) {

@@ -14,6 +14,7 @@
 // private to its pixel. Draw order of the RNG follows SURVEY.md Appendix A exactly.
 #include "context.cuh"
 #include "traverse.cuh"
+#include "two_level.cuh"
 #include "shade.cuh"
 
 namespace rb200 {
@@ -540,8 +541,11 @@ __device__ __forceinline__ void shade_slot(const WaveParams& P, const uint32_t s
 #ifndef RB_SHADE_BLOCK
 #define RB_SHADE_BLOCK 128       // threads per block of the shading kernels (85-119 registers: smaller blocks pack an SM's register file better)
 #endif
+// Disney: 128 registers without a cap (4 resident blocks). B200, headline step, ms per step with __launch_bounds__(128, n):
+// n = 3 / 4 (no cap) 3.94, 5 (96 registers, 76 B spilled) 3.84, 6 (80 registers, 180 B spilled) 3.77: the kernel issues on
+// 45 % of the cycles with 4 warps per scheduler, so two more resident blocks are worth more than the spills cost.
 #ifndef RB_DISNEY_MINBLOCKS
-#define RB_DISNEY_MINBLOCKS 1
+#define RB_DISNEY_MINBLOCKS 6
 #endif
 // RB_SHADE_PREFETCH=1: software pipeline of the shading kernels' gathers — while item k is shaded, the path-state line
 // of item k+2 and the shading records of item k+1 (whose hit record arrived with the line requested one iteration
@@ -648,6 +652,51 @@ __global__ void __launch_bounds__(RB_TRAV_BLOCK, RB_TRAV_MINBLOCKS) k_shadow(Wav
     if (COUNT) {      // the counting pass runs one lane (context_create), so lane 0's counters are the batch's
         atomicAdd(&P.stats[ST_NODES_SHADOW], (unsigned long long)nodeVisits);
         atomicAdd(&P.stats[ST_TRIS_SHADOW], (unsigned long long)triTests);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// two-level mode (RB200_FLAG_TWO_LEVEL, two_level.cuh): the same two stages, one ray per thread over the same queues
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_extend_two_level(WaveParams P, int parity) {
+    uint32_t* cnt = P.counters + parity * CNT_SET;
+    const uint32_t n = cnt[CNT_RAYS];
+    const uint32_t* __restrict__ q = P.rayQ[parity];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = q[i];
+        float4 o4, d4;
+        load_pair(P.rayO, P.rayD, slot, o4, d4);
+        const TLHit h = trace_two_level<false>(P.S, rb_mk3(o4.x, o4.y, o4.z), rb_mk3(d4.x, d4.y, d4.z), 10000.0f);
+        uint32_t bin = 4;
+        if (h.tri != 0xFFFFFFFFu) {
+            P.hit[slot] = make_uint4(__float_as_uint(h.b1), __float_as_uint(h.b2), h.tri, h.inst);
+            bin = __ldg(&P.S.tlInstances[h.inst].material);
+        }
+        const uint32_t peers = __match_any_sync(__activemask(), bin);
+        const uint32_t lane = threadIdx.x & 31u;
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(&cnt[CNT_MAT0 + bin], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        uint32_t* mq = bin == 0u ? P.matQ[0] : bin == 1u ? P.matQ[1] : bin == 2u ? P.matQ[2] : bin == 3u ? P.matQ[3] : P.matQ[4];
+        mq[base + __popc(peers & ((1u << lane) - 1u))] = slot;
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK) k_shadow_two_level(WaveParams P, int parity) {
+    uint32_t* cnt = P.counters + parity * CNT_SET;
+    const uint32_t n = cnt[CNT_SHADOW];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o4 = P.shO[i], d4 = P.shD[i];
+        const TLHit h = trace_two_level<true>(P.S, rb_mk3(o4.x, o4.y, o4.z), rb_mk3(d4.x, d4.y, d4.z), o4.w);
+        const bool occluded = h.tri != 0xFFFFFFFFu;
+        const float4 A = P.shA[i], B = P.shB[i], T = P.shT[i];
+        const uint32_t slot = __float_as_uint(B.w);
+        const rb_v3 direct = occluded ? rb_splat3(0.0f) : rb_mk3(A.x, A.y, A.z);
+        const rb_v3 combined = direct * A.w + rb_mk3(B.x, B.y, B.z);
+        const float4 L4 = P.rad[slot];
+        const rb_v3 L = rb_mk3(L4.x, L4.y, L4.z) + combined * rb_mk3(T.x, T.y, T.z);
+        P.rad[slot] = make_float4(L.x, L.y, L.z, 0.f);
     }
 }
 
@@ -783,11 +832,13 @@ static int issue_waves(RB200Context* ctx, Engine& E, uint32_t count, uint32_t pa
     const bool countBvh = (ctx->flags & RB200_FLAG_COUNT_BVH) != 0;
     const bool nee = (ctx->flags & RB200_FLAG_NEE) != 0;
     const uint32_t mats = P.S.materialMask & 15u;
+    const bool twoLevel = P.S.tlasNodes != nullptr;
     for (uint32_t w = 0; w < count; w++) {
         const int p = (int)((parity + w) & 1u);
         RB_CUDA(cudaMemsetAsync(P.counters + (p ^ 1) * CNT_SET, 0, CNT_SET * sizeof(uint32_t), s));
         tm.tic(1);
-        if (countBvh) k_extend<true><<<ctx->gExtendC, RB_TRAV_BLOCK, SMEM_EXTEND, s>>>(P, p);
+        if (twoLevel) k_extend_two_level<<<ctx->gTwoLevel[0], BLOCK, 0, s>>>(P, p);
+        else if (countBvh) k_extend<true><<<ctx->gExtendC, RB_TRAV_BLOCK, SMEM_EXTEND, s>>>(P, p);
         else k_extend<false><<<ctx->gExtend, RB_TRAV_BLOCK, SMEM_EXTEND, s>>>(P, p);
         tm.toc();
         tm.tic(6); k_shade<4><<<ctx->gShade[4], RB_SHADE_BLOCK, 0, s>>>(P, p); tm.toc();
@@ -798,7 +849,8 @@ static int issue_waves(RB200Context* ctx, Engine& E, uint32_t count, uint32_t pa
         if (mats & 8u) { tm.tic(5); k_shade<3><<<ctx->gShade[3], RB_SHADE_BLOCK, 0, s>>>(P, p); tm.toc(); }
         if (nee) {
             tm.tic(7);
-            if (countBvh) k_shadow<true><<<ctx->gShadowC, RB_TRAV_BLOCK, SMEM_SHADOW, s>>>(P, p);
+            if (twoLevel) k_shadow_two_level<<<ctx->gTwoLevel[1], BLOCK, 0, s>>>(P, p);
+            else if (countBvh) k_shadow<true><<<ctx->gShadowC, RB_TRAV_BLOCK, SMEM_SHADOW, s>>>(P, p);
             else k_shadow<false><<<ctx->gShadow, RB_TRAV_BLOCK, SMEM_SHADOW, s>>>(P, p);
             tm.toc();
         }
@@ -1103,6 +1155,21 @@ __global__ void __launch_bounds__(BLOCK) k_trace_query(const WideNode* nodes, co
         nv, tt, ws[threadIdx.x >> 5]);
 }
 
+template <bool ANY>
+__global__ void __launch_bounds__(BLOCK) k_trace_query_two_level(DeviceScene S, uint32_t n, const float4* __restrict__ o,
+                                                                 const float4* __restrict__ d, RB200PrimaryHit* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o4 = o[i], d4 = d[i];
+        const TLHit h = trace_two_level<ANY>(S, rb_mk3(o4.x, o4.y, o4.z), rb_mk3(d4.x, d4.y, d4.z), o4.w);
+        RB200PrimaryHit r;
+        if (h.tri != 0xFFFFFFFFu) {
+            r.t = h.t; r.u = h.b1; r.v = h.b2; r.instance = h.inst;
+            r.primitive = __float_as_uint(__ldg(reinterpret_cast<const float4*>(S.tris + h.tri)).w);
+        } else { r.t = -1.0f; r.u = r.v = 0.f; r.primitive = r.instance = 0xFFFFFFFFu; }
+        out[i] = r;
+    }
+}
+
 static int sync_engines(RB200Context* ctx) {
     for (int e = 0; e < ctx->numEngines; e++) RB_CUDA(cudaStreamSynchronize(ctx->eng[e].stream));
     return RB200_OK;
@@ -1117,6 +1184,14 @@ struct DeviceBuf {          // frees on every return path
 static int launch_query(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float4* dO, const float4* dD, int any,
                         RB200PrimaryHit* dOut) {
     RB_CUDA(cudaMemsetAsync(ctx->queryCursor, 0, sizeof(uint32_t), ctx->stream));
+    if (scene->dev.tlasNodes) {
+        const int g2 = (int)std::min<uint64_t>((n + BLOCK - 1) / BLOCK, (uint64_t)ctx->gTwoLevel[any ? 1 : 0]);
+        if (any) k_trace_query_two_level<true><<<g2, BLOCK, 0, ctx->stream>>>(scene->dev, n, dO, dD, dOut);
+        else k_trace_query_two_level<false><<<g2, BLOCK, 0, ctx->stream>>>(scene->dev, n, dO, dD, dOut);
+        ctx->launches++;
+        RB_CUDA(cudaGetLastError());
+        return RB200_OK;
+    }
     const int grid = (int)std::min<uint64_t>((n + BLOCK - 1) / BLOCK, (uint64_t)ctx->gQuery[any ? 1 : 0]);
     constexpr size_t smAny = sizeof(WarpShared<true>) * (BLOCK / 32), smClosest = sizeof(WarpShared<false>) * (BLOCK / 32);
     if (any) k_trace_query<true><<<grid, BLOCK, smAny, ctx->stream>>>(scene->dev.nodes, scene->dev.tris, n, dO, dD, dOut, ctx->queryCursor);
@@ -1297,6 +1372,7 @@ __global__ void __launch_bounds__(RB_SHADE_BLOCK) k_shade_hits(WaveParams P, uin
 int shade_hits(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* o, const float* d, const uint32_t* rng,
                const uint32_t* inside, const float* acc, RB200ShadeResult* out) {
     if (n == 0) return RB200_OK;
+    if (scene->dev.tlasNodes) { set_error("rb200_shade_hits is a parity aid of the flattened path (context without RB200_FLAG_TWO_LEVEL)"); return RB200_ERR_INVALID_ARGUMENT; }
     int rc = sync_engines(ctx);
     if (rc != RB200_OK) return rc;
     std::vector<float> tmax(n, 10000.0f);
@@ -1361,6 +1437,8 @@ int configure_wave_kernels(RB200Context* ctx) {
     ctx->gFinish = persistent_grid(k_finish, ctx->numSMs);
     ctx->gQuery[0] = persistent_grid(k_trace_query<false>, ctx->numSMs, BLOCK, smClosest);
     ctx->gQuery[1] = persistent_grid(k_trace_query<true>, ctx->numSMs, BLOCK, smAny);
+    ctx->gTwoLevel[0] = persistent_grid(k_extend_two_level, ctx->numSMs, BLOCK);
+    ctx->gTwoLevel[1] = persistent_grid(k_shadow_two_level, ctx->numSMs, BLOCK);
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, k_generate);
     cudaFuncGetAttributes(&a, k_accumulate);

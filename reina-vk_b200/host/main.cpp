@@ -40,6 +40,8 @@ static void usage() {
         "  --gpus N             render on devices 0 .. N-1 of this machine: the BVH is replicated, device g renders sample batches\n"
         "                       g, g + N, ... and one NCCL reduce of the accumulation images closes every saved frame\n"
         "  --tiles              with --gpus: latency mode, every device renders its interleaved 32 x 32 tiles of every batch\n"
+        "  --two-level          keep one hierarchy per object and a top level over the instances (the reference's BLAS / TLAS,\n"
+        "                       src/scene/Scene.cpp:93-111) instead of flattening the instances: less memory, slower rays\n"
         "  --dump-pc FILE       write the 160-byte push-constant block of batch 0 to FILE\n"
         "  --quiet              no progress output\n");
 }
@@ -59,7 +61,7 @@ int main(int argc, char** argv) {
     nextMat.albedo = {0.8f, 0.8f, 0.8f};
     nextMat.interpNormals = true;
     long width = -1, height = -1, spp = 0, device = 0, gpus = 1;
-    bool tiles = false;
+    bool tiles = false, twoLevel = false;
     double seconds = 0.0;
     int nee = -1;
     bool quiet = false;
@@ -105,6 +107,7 @@ int main(int argc, char** argv) {
             else if (a == "--device") device = std::strtol(value(), nullptr, 10);
             else if (a == "--gpus") gpus = std::strtol(value(), nullptr, 10);
             else if (a == "--tiles") tiles = true;
+            else if (a == "--two-level") twoLevel = true;
             else if (a == "--dump-pc") dumpPc = value();
             else if (a == "--quiet") quiet = true;
             else throw std::runtime_error("unknown option " + a + " (see --help)");
@@ -137,7 +140,7 @@ int main(int argc, char** argv) {
         opt.quiet = quiet;
         if (gpus < 1) throw std::runtime_error("--gpus must be at least 1");
         if (gpus > 1 || tiles) {
-            GroupRenderer group(cfg.width, cfg.height, int(gpus), cfg.nee ? uint32_t(RB200_FLAG_NEE) : 0u, tiles);
+            GroupRenderer group(cfg.width, cfg.height, int(gpus), (cfg.nee ? uint32_t(RB200_FLAG_NEE) : 0u) | (twoLevel ? uint32_t(RB200_FLAG_TWO_LEVEL) : 0u), tiles);
             group.setScene(tables);
             if (!quiet) {
                 const RB200BvhInfo bvh = group.bvhInfo();
@@ -153,7 +156,7 @@ int main(int argc, char** argv) {
             return 0;
         }
 
-        Renderer renderer(cfg.width, cfg.height, int(device), cfg.nee ? uint32_t(RB200_FLAG_NEE) : 0u);
+        Renderer renderer(cfg.width, cfg.height, int(device), (cfg.nee ? uint32_t(RB200_FLAG_NEE) : 0u) | (twoLevel ? uint32_t(RB200_FLAG_TWO_LEVEL) : 0u));
         renderer.setScene(tables);
         if (!quiet) {
             const RB200BvhInfo bvh = renderer.bvhInfo();

@@ -37,6 +37,7 @@ def lib():
         _lib = C.CDLL(ORACLE_SO)
         _lib.oracle_scene_create.argtypes = [C.POINTER(abi.SceneDesc), C.c_int, C.POINTER(C.c_void_p)]
         _lib.oracle_scene_destroy.argtypes = [C.c_void_p]
+        _lib.oracle_scene_set_two_level.argtypes = [C.c_void_p, C.c_int]
         _lib.oracle_scene_num_triangles.argtypes = [C.c_void_p]
         _lib.oracle_scene_num_triangles.restype = C.c_uint32
         _lib.oracle_render_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(abi.RtPushConsts),
@@ -82,6 +83,12 @@ class OracleScene:
         d = tables.desc()
         rc = lib().oracle_scene_create(C.byref(d), bvh_threshold, C.byref(self._h))
         assert rc == 0
+
+    def set_two_level(self, bvh_threshold=1500):
+        """Two-level intersection: rays in object space per instance (Scene.cpp:93-111), see oracle/intersect.cpp."""
+        rc = lib().oracle_scene_set_two_level(self._h, bvh_threshold)
+        if rc != 0:
+            raise RuntimeError("oracle_scene_set_two_level failed: %d" % rc)
 
     def num_triangles(self):
         return lib().oracle_scene_num_triangles(self._h)
