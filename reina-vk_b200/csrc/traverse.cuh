@@ -53,6 +53,16 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
                           // 64 / 96 / 128 / 256 entries: -4 / -1 / 0 / +1 % on B200 with 4-byte entries
 #endif
 
+// RB_COOP_FILL=1: warp-cooperative fill of the pooled work list (see trace_queue): position p of the list is computed by
+// lane p % 32 from the lanes' group lists in shared memory, total / 32 rounds with all lanes instead of the per-lane loop's
+// ~17 iterations with 5.6 active lanes (11 % of the kernel's issued instructions, profiles/r02f SASS page). MEASURED ON
+// B200: SLOWER — k_extend 19.50 -> 20.13 ms, k_shadow 10.31 -> 10.75 ms per step (profiles/r02j_variant_sweep.txt), results
+// identical: the owner search, the walk over the owner's groups and the n-th-set-bit loop are chains of dependent
+// shared-memory loads, and the few issue slots the narrow loop wastes are cheaper than those stalls. Off.
+#ifndef RB_COOP_FILL
+#define RB_COOP_FILL 0
+#endif
+
 #ifndef RB_TRI_LDCG
 #define RB_TRI_LDCG 0     // 1: triangle records bypass L1 (ld.global.cg): measured -1 % closest-hit, -5 % any-hit on B200
                           // (neighbouring rays do re-use each other's triangles); ray records through L2 only: no change
@@ -425,6 +435,48 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
             uint32_t pos = incl - c;
             const unsigned long long seed = has ? hit_key(tr.best.t, tr.best.gid) : ~0ull;
             ws.bestKey[lane] = seed;
+#if RB_COOP_FILL
+            bool filled = false;
+            if constexpr (TStackShared<ANY>::value && RB_TSTACK_N >= RB_CHUNK) if (total <= (uint32_t)RB_WORK_CAP) {
+                filled = true;
+                // Cooperative fill of the work list: position p of the list is computed by lane p % 32, whoever owns the
+                // triangle. The per-lane loop below ran max-over-lanes iterations (~17) with 5.6 of 32 lanes active — a few
+                // rays own most of a chunk's triangles — and was 11 % of the kernel's issued instructions (profiles/r02f,
+                // SASS page); this takes total / 32 rounds (~3) with all lanes. The order of the list is irrelevant.
+                uint32_t* sc = reinterpret_cast<uint32_t*>(ws.payload);      // 128 words, free until the tests start:
+                const uint32_t excl = pos;                                  // [0..31] first position of each lane's triangles
+                sc[lane] = excl;
+                sc[32u + lane] = tr.tgroup.x;                                // [32..63], [64..95] the group a lane holds in registers
+                sc[64u + lane] = c ? tr.tgroup.y : 0u;
+                const uint32_t owners = __ballot_sync(0xffffffffu, c > 0u);
+                if (c) sc[96u + __popc(owners & ((1u << lane) - 1u))] = lane | ((uint32_t)tr.tsp << 8);   // [96..127] owners in order + their list length
+                __syncwarp();
+                for (uint32_t b = 0; b < total; b += 32u) {
+                    const uint32_t rel = excl - b;
+                    const uint32_t starts = __reduce_or_sync(0xffffffffu, (c > 0u && rel < 32u) ? (1u << rel) : 0u);
+                    const uint32_t before = (uint32_t)__popc(__ballot_sync(0xffffffffu, c > 0u && excl < b));
+                    const uint32_t p = b + lane;
+                    if (p < total) {
+                        const uint32_t ord = before + (uint32_t)__popc(starts & (0xFFFFFFFFu >> (31u - lane))) - 1u;
+                        const uint32_t info = sc[96u + ord];
+                        const uint32_t L = info & 31u;
+                        int k = (int)(info >> 8);
+                        uint32_t off = p - sc[L];
+                        uint32_t mask = sc[64u + L], base = sc[32u + L];
+                        uint32_t cnt = (uint32_t)__popc(mask);
+                        while (off >= cnt) {             // the register group first, then the lane's list from the top
+                            off -= cnt;
+                            const uint2 g = ws.tstack[--k][L];
+                            base = g.x; mask = g.y; cnt = (uint32_t)__popc(mask);
+                        }
+                        for (; off > 0u; off--) mask &= mask - 1u;
+                        ws.work[p] = ((base + (uint32_t)__ffs(mask) - 1u) << 5) | L;
+                    }
+                }
+                if (has) { tr.tcount = 0u; tr.tsp = 0; tr.tgroup.y = 0u; }
+            }
+            if (!filled)
+#endif
             while (has && tr.tcount > 0u && pos < (uint32_t)RB_WORK_CAP) ws.work[pos++] = (tr.take_tri(ws) << 5) | lane;
             __syncwarp();
             const uint32_t count = min(total, (uint32_t)RB_WORK_CAP);
