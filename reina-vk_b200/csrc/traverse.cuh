@@ -59,6 +59,10 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
 // B200: SLOWER — k_extend 19.50 -> 20.13 ms, k_shadow 10.31 -> 10.75 ms per step (profiles/r02j_variant_sweep.txt), results
 // identical: the owner search, the walk over the owner's groups and the n-th-set-bit loop are chains of dependent
 // shared-memory loads, and the few issue slots the narrow loop wastes are cheaper than those stalls. Off.
+#ifndef RB_STACK_IN_STRUCT
+#define RB_STACK_IN_STRUCT 0    // 1: the round-1 layout (deep stack array as a member of Traversal), kept for comparison
+#endif
+
 #ifndef RB_COOP_FILL
 #define RB_COOP_FILL 0
 #endif
@@ -195,7 +199,13 @@ struct Traversal {
     int sp, tsp;
     uint32_t tcount;              // triangles queued in tgroup + tstack
     RayHit best;
-    uint2 stack[TRAV_STACK];      // pending node groups (local memory)
+#if RB_STACK_IN_STRUCT
+    uint2 stack[TRAV_STACK];
+#else
+    uint2* stack;                 // pending node groups below the shared-memory entries: an array in local memory that
+                                  // lives OUTSIDE this struct, so that the scalar members stay in registers (with the array
+                                  // inside, ptxas kept ngroup / sp / tsp / tcount in the local frame: ~10 STL / LDL per node step)
+#endif
     // triangle groups produced by the node steps of the current chunk (see RB_TSTACK_SHARED)
     uint2 tstackLocal[TStackShared<ANY>::value ? (RB_TSTACK_N < RB_CHUNK ? RB_CHUNK - RB_TSTACK_N : 1) : RB_CHUNK];
     __device__ __forceinline__ uint2& tst(WarpShared<ANY>& ws, int k) {
@@ -381,6 +391,10 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                                             uint32_t& nodeVisits, uint32_t& triTests, WarpShared<ANY>& ws) {
     const uint32_t lane = threadIdx.x & 31u;
     Traversal<ANY, COUNT> tr;
+#if !RB_STACK_IN_STRUCT
+    uint2 deepStack[TRAV_STACK];
+    tr.stack = deepStack;
+#endif
     tr.tcount = 0;
     const unsigned long long pol = bvh_policy();
 
