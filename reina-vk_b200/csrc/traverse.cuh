@@ -136,6 +136,7 @@ __device__ __forceinline__ void ld_bvh2(const float4* p, float4& a, float4& b, u
 #ifndef RB_TSTACK_N
 #define RB_TSTACK_N RB_CHUNK
 #endif
+
 // Chunk length of the any-hit kernels (<= RB_CHUNK, which sizes the triangle-group lists): a shadow ray ends with its
 // first hit, so testing the queued triangles sooner saves node steps that a found hit makes useless. B200, headline
 // step, k_shadow ms: 3 / 4 / 5 / 6 steps 10.55 / 10.35 / 10.36 / 10.55.
@@ -145,12 +146,14 @@ __device__ __forceinline__ void ld_bvh2(const float4* p, float4& a, float4& b, u
 static_assert(RB_CHUNK_ANY <= RB_CHUNK, "the triangle-group lists hold RB_CHUNK entries");
 
 // per-warp staging area of the pooled triangle phase
-template <bool TSTACK> struct WarpTStack { };
-template <> struct WarpTStack<true> { uint2 tstack[RB_TSTACK_N][32]; };    // per lane: triangle groups of the current chunk
+template <bool TSTACK, int N> struct WarpTStack { };
+template <int N> struct WarpTStack<true, N> { uint2 tstack[N][32]; };    // per lane: triangle groups of the current chunk
+// a chunk of the any-hit kernels is RB_CHUNK_ANY node steps, so their lists need no more entries than that
+template <bool ANY> struct TStackEntries { static constexpr int value = (ANY && RB_TSTACK_N == RB_CHUNK) ? RB_CHUNK_ANY : RB_TSTACK_N; };
 template <int K> struct WarpStack { uint2 nstack[K][32]; };
 template <> struct WarpStack<0> { };
 template <bool ANY>
-struct WarpShared : WarpTStack<TStackShared<ANY>::value>, WarpStack<StackShared<ANY>::value> {
+struct WarpShared : WarpTStack<TStackShared<ANY>::value, TStackEntries<ANY>::value>, WarpStack<StackShared<ANY>::value> {
     float4 ray[32][3];                    // per lane: (o, tmax), (mx, Sz), (my, bits(kz)) — shear rows of rb_tri.h
     uint32_t work[RB_WORK_CAP];           // triangle index << 5 | owner lane (the build refuses >= 2^27 triangles)
     unsigned long long bestKey[32];       // per owner: min over candidates of (t bits << 32 | global primitive id)

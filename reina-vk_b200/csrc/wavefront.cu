@@ -36,6 +36,24 @@ static constexpr int BLOCK = 256;
 #ifndef RB_TRAV_MINBLOCKS
 #define RB_TRAV_MINBLOCKS (1024 / RB_TRAV_BLOCK)      // resident blocks per SM the traversal kernels are compiled for (register cap)
 #endif
+// The two traversal kernels want different shapes (B200, headline step, ms per step, profiles/r02l_variant_sweep.txt):
+//   256 threads x 4 blocks (1024 threads per SM, 64 registers): k_extend 19.13, k_shadow 9.49
+//   128 threads x 7 blocks ( 896 threads per SM, 72 registers, no spill): k_extend 18.37, k_shadow 9.82
+//   256 threads x 3 blocks ( 768 threads per SM, 80 registers): k_extend 19.36, k_shadow 10.52
+// The closest-hit kernel carries more live state (best hit, barycentrics, triangle id) and gains from eight more registers
+// what it loses with an eighth of its warps; the any-hit kernel does not.
+#ifndef RB_EXTEND_BLOCK
+#define RB_EXTEND_BLOCK 128
+#endif
+#ifndef RB_EXTEND_MINBLOCKS
+#define RB_EXTEND_MINBLOCKS 7
+#endif
+#ifndef RB_SHADOW_BLOCK
+#define RB_SHADOW_BLOCK RB_TRAV_BLOCK
+#endif
+#ifndef RB_SHADOW_MINBLOCKS
+#define RB_SHADOW_MINBLOCKS RB_TRAV_MINBLOCKS
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // queue helpers
@@ -180,13 +198,13 @@ __global__ void __launch_bounds__(BLOCK) k_generate(WaveParams P, uint32_t lane,
 // extend
 // ---------------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(RB_TRAV_BLOCK, RB_TRAV_MINBLOCKS) k_extend(WaveParams P, int parity) {
+__global__ void __launch_bounds__(RB_EXTEND_BLOCK, RB_EXTEND_MINBLOCKS) k_extend(WaveParams P, int parity) {
     uint32_t* cnt = P.counters + parity * CNT_SET;
     const uint32_t n = cnt[CNT_RAYS];
     const uint32_t* __restrict__ q = P.rayQ[parity];
     // (rays are counted per batch when their path ends: finish_slot)
     uint32_t nodeVisits = 0, triTests = 0;
-    extern __shared__ __align__(16) unsigned char rb_dyn_smem[];      // WarpShared<false>[RB_TRAV_BLOCK / 32]: may exceed the 48 KB static limit
+    extern __shared__ __align__(16) unsigned char rb_dyn_smem[];      // WarpShared<false>[RB_EXTEND_BLOCK / 32]: may exceed the 48 KB static limit
     WarpShared<false>* ws = reinterpret_cast<WarpShared<false>*>(rb_dyn_smem);
     trace_queue<false, COUNT>(
         P.S.nodes, P.S.tris, n, &cnt[CNT_CURSOR_EXTEND],
@@ -618,11 +636,11 @@ __global__ void __launch_bounds__(RB_SHADE_BLOCK, MAT == 3 ? RB_DISNEY_MINBLOCKS
 // shadow: shadowRayOccluded (nee.h.glsl:126-144) + the radiance update of rgen.glsl:174-177
 // ---------------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(RB_TRAV_BLOCK, RB_TRAV_MINBLOCKS) k_shadow(WaveParams P, int parity) {
+__global__ void __launch_bounds__(RB_SHADOW_BLOCK, RB_SHADOW_MINBLOCKS) k_shadow(WaveParams P, int parity) {
     uint32_t* cnt = P.counters + parity * CNT_SET;
     const uint32_t n = cnt[CNT_SHADOW];
     uint32_t nodeVisits = 0, triTests = 0;
-    extern __shared__ __align__(16) unsigned char rb_dyn_smem[];      // WarpShared<true>[RB_TRAV_BLOCK / 32]
+    extern __shared__ __align__(16) unsigned char rb_dyn_smem[];      // WarpShared<true>[RB_SHADOW_BLOCK / 32]
     WarpShared<true>* ws = reinterpret_cast<WarpShared<true>*>(rb_dyn_smem);
     trace_queue<true, COUNT>(
         P.S.nodes, P.S.tris, n, &cnt[CNT_CURSOR_SHADOW],
@@ -759,8 +777,8 @@ __global__ void k_resolve_sum(float4* image, uint32_t n, float inv) {
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-static constexpr size_t SMEM_EXTEND = sizeof(WarpShared<false>) * (RB_TRAV_BLOCK / 32);
-static constexpr size_t SMEM_SHADOW = sizeof(WarpShared<true>) * (RB_TRAV_BLOCK / 32);
+static constexpr size_t SMEM_EXTEND = sizeof(WarpShared<false>) * (RB_EXTEND_BLOCK / 32);
+static constexpr size_t SMEM_SHADOW = sizeof(WarpShared<true>) * (RB_SHADOW_BLOCK / 32);
 
 // Per-triangle shading records (DeviceScene::shadeBase / shadeFrame): one thread per triangle slot copies exactly the
 // floats hit_info() would gather for that triangle.
@@ -838,8 +856,8 @@ static int issue_waves(RB200Context* ctx, Engine& E, uint32_t count, uint32_t pa
         RB_CUDA(cudaMemsetAsync(P.counters + (p ^ 1) * CNT_SET, 0, CNT_SET * sizeof(uint32_t), s));
         tm.tic(1);
         if (twoLevel) k_extend_two_level<<<ctx->gTwoLevel[0], BLOCK, 0, s>>>(P, p);
-        else if (countBvh) k_extend<true><<<ctx->gExtendC, RB_TRAV_BLOCK, SMEM_EXTEND, s>>>(P, p);
-        else k_extend<false><<<ctx->gExtend, RB_TRAV_BLOCK, SMEM_EXTEND, s>>>(P, p);
+        else if (countBvh) k_extend<true><<<ctx->gExtendC, RB_EXTEND_BLOCK, SMEM_EXTEND, s>>>(P, p);
+        else k_extend<false><<<ctx->gExtend, RB_EXTEND_BLOCK, SMEM_EXTEND, s>>>(P, p);
         tm.toc();
         tm.tic(6); k_shade<4><<<ctx->gShade[4], RB_SHADE_BLOCK, 0, s>>>(P, p); tm.toc();
         // a material no instance uses has an empty queue in every wave: its kernel is not launched
@@ -850,8 +868,8 @@ static int issue_waves(RB200Context* ctx, Engine& E, uint32_t count, uint32_t pa
         if (nee) {
             tm.tic(7);
             if (twoLevel) k_shadow_two_level<<<ctx->gTwoLevel[1], BLOCK, 0, s>>>(P, p);
-            else if (countBvh) k_shadow<true><<<ctx->gShadowC, RB_TRAV_BLOCK, SMEM_SHADOW, s>>>(P, p);
-            else k_shadow<false><<<ctx->gShadow, RB_TRAV_BLOCK, SMEM_SHADOW, s>>>(P, p);
+            else if (countBvh) k_shadow<true><<<ctx->gShadowC, RB_SHADOW_BLOCK, SMEM_SHADOW, s>>>(P, p);
+            else k_shadow<false><<<ctx->gShadow, RB_SHADOW_BLOCK, SMEM_SHADOW, s>>>(P, p);
             tm.toc();
         }
         tm.tic(8); k_finish<<<ctx->gFinish, BLOCK, 0, s>>>(P, p); tm.toc();
@@ -1425,10 +1443,10 @@ template <class K> static int persistent_grid(K kernel, int numSMs, int block = 
 
 int configure_wave_kernels(RB200Context* ctx) {
     constexpr size_t smAny = sizeof(WarpShared<true>) * (BLOCK / 32), smClosest = sizeof(WarpShared<false>) * (BLOCK / 32);
-    ctx->gExtend = persistent_grid(k_extend<false>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_EXTEND);
-    ctx->gExtendC = persistent_grid(k_extend<true>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_EXTEND);
-    ctx->gShadow = persistent_grid(k_shadow<false>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_SHADOW);
-    ctx->gShadowC = persistent_grid(k_shadow<true>, ctx->numSMs, RB_TRAV_BLOCK, SMEM_SHADOW);
+    ctx->gExtend = persistent_grid(k_extend<false>, ctx->numSMs, RB_EXTEND_BLOCK, SMEM_EXTEND);
+    ctx->gExtendC = persistent_grid(k_extend<true>, ctx->numSMs, RB_EXTEND_BLOCK, SMEM_EXTEND);
+    ctx->gShadow = persistent_grid(k_shadow<false>, ctx->numSMs, RB_SHADOW_BLOCK, SMEM_SHADOW);
+    ctx->gShadowC = persistent_grid(k_shadow<true>, ctx->numSMs, RB_SHADOW_BLOCK, SMEM_SHADOW);
     ctx->gShade[0] = persistent_grid(k_shade<0>, ctx->numSMs, RB_SHADE_BLOCK);
     ctx->gShade[1] = persistent_grid(k_shade<1>, ctx->numSMs, RB_SHADE_BLOCK);
     ctx->gShade[2] = persistent_grid(k_shade<2>, ctx->numSMs, RB_SHADE_BLOCK);
