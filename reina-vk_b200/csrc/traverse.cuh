@@ -59,6 +59,10 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
 // B200: SLOWER — k_extend 19.50 -> 20.13 ms, k_shadow 10.31 -> 10.75 ms per step (profiles/r02j_variant_sweep.txt), results
 // identical: the owner search, the walk over the owner's groups and the n-th-set-bit loop are chains of dependent
 // shared-memory loads, and the few issue slots the narrow loop wastes are cheaper than those stalls. Off.
+#ifndef RB_LEAN_FILL
+#define RB_LEAN_FILL 1       // nested-loop fill of the pooled work list when a chunk's triangles fit (see trace_queue)
+#endif
+
 #ifndef RB_STACK_IN_STRUCT
 #define RB_STACK_IN_STRUCT 0    // 1: the round-1 layout (deep stack array as a member of Traversal), kept for comparison
 #endif
@@ -493,6 +497,30 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                 if (has) { tr.tcount = 0u; tr.tsp = 0; tr.tgroup.y = 0u; }
             }
             if (!filled)
+#endif
+#if RB_LEAN_FILL
+            if (total <= (uint32_t)RB_WORK_CAP) {
+                // Everything fits (the common case): two nested loops — groups, then the bits of a group — without the
+                // per-triangle bookkeeping of take_tri (group reload test, tcount, list bound): 8 instructions per
+                // triangle instead of 21. The loop runs max-over-lanes iterations with ~6 of 32 lanes active (a few rays
+                // own most of a chunk's triangles) and was 11 % of the kernel's issued instructions (profiles/r02f).
+                if (c) {
+                    uint32_t* w = &ws.work[pos];
+                    uint2 g = tr.tgroup;
+                    int k = tr.tsp;
+                    for (;;) {
+                        const uint32_t tag = (g.x << 5) | lane;
+                        while (g.y) {
+                            const uint32_t ti = 31u - (uint32_t)__clz(g.y);
+                            g.y ^= 1u << ti;
+                            *w++ = tag + (ti << 5);
+                        }
+                        if (k == 0) break;
+                        g = tr.tst(ws, --k);
+                    }
+                    tr.tcount = 0u; tr.tsp = 0; tr.tgroup.y = 0u;
+                }
+            } else
 #endif
             while (has && tr.tcount > 0u && pos < (uint32_t)RB_WORK_CAP) ws.work[pos++] = (tr.take_tri(ws) << 5) | lane;
             __syncwarp();
