@@ -17,11 +17,14 @@ Same stages and names as the reference:
   loadScene              :440-456   the stages in the reference's order: meshes, textures, materials, instances
 
 The reference parses with fastgltf@42d26b2 and computes missing tangents with MikkTSpace@3e895b4; neither is
-vendored in the reference tree (parity unpinned), and its MikkTSpace call reads the vertex array as an un-indexed
-triangle soup before TEXCOORD_0 has been loaded (:213-229 run before :232-249), so what it yields for indexed meshes is
-an accident of that call, not a specification. Rules of this importer where the reference leaves a choice:
+vendored in the reference tree (parity unpinned). Its MikkTSpace call (:207-222) reads the vertex array as an
+un-indexed triangle soup BEFORE TEXCOORD_0 and the indices have been loaded (:225-249 run afterwards), so every UV it
+sees is (0, 0) — and for that input MikkTSpace's published algorithm has exactly one outcome, which
+`mikktspace_as_called` below restates: tangent (1, 0, 0) and bitangent (0, 1, 0) for every vertex of a complete
+triple, zeros for the one or two left over. That is what `tangents="reference"` (the default) yields; `tangents="uv"`
+derives per-vertex frames from the UV derivatives instead (meshes._tangent_frames: what the call was presumably
+meant to do). Rules of this importer where the reference leaves a choice:
   * used meshes are defined in ascending mesh index (the reference iterates an unordered_set);
-  * TANGENT absent: per-vertex tangent frames from the UV derivatives, the importer's own rule (meshes._tangent_frames);
   * TRS node transforms are composed in float64 (T * R * S, quaternion -> matrix by the standard formula), products
     are accumulated in float64 in a fixed order and rounded to float32 once per instance;
   * images: PNG and baseline / progressive JPEG (CMYK JPEG is refused loudly);
@@ -205,6 +208,32 @@ class Primitive:
         return meshes.make_model(self.position, self.uv, self.normal, tris, tbn=tbn)
 
 
+def mikktspace_as_called(n):
+    """What genTangSpaceDefault (MikkTSpace@3e895b4, mikktspace.c) writes through the reference's callbacks
+    (gltfloader.cpp:16-67, 207-222) for a primitive of n vertices. Returns (tangent, bitangent), float32 [n, 3].
+
+    The call sees faces f = vertices 3f .. 3f+2 (getNumFaces = n / 3, no indices) whose texture coordinates are all
+    (0, 0): `m.vertices.resize(count)` value-initialises VertexTBN and TEXCOORD_0 is only read afterwards. Following
+    genTangSpace step by step with that input:
+      * InitTriInfo marks every triangle GROUP_WITH_ANY ("assumed bad") and clears the mark only where the signed UV
+        area t21x * t31y - t21y * t31x is non-zero — here it is 0 for every triangle, so vOs = vOt = 0 and the mark stays;
+      * Build4RuleGroups opens a group only at a triangle WITHOUT that mark: no group is ever opened, so
+        GenerateTSpaces has nothing to evaluate;
+      * every per-corner tangent space therefore keeps the value it was initialised with before GenerateTSpaces:
+        vOs = (1, 0, 0), vOt = (0, 1, 0), fMagS = fMagT = 1; DegenEpilogue copies such a space between corners of
+        position-degenerate triangles (same values) and the final loop hands vOs / vOt to setTSpace for the three
+        corners of every face.
+    Vertices 3 * (n / 3) .. n - 1 belong to no face and keep the zeros of the value-initialisation; with n < 3 the
+    call returns before writing anything. Positions, normals, welding and the angular threshold cannot change any of
+    this: they only enter through groups, and there are none."""
+    t = np.zeros((n, 3), np.float32)
+    b = np.zeros((n, 3), np.float32)
+    full = 3 * (n // 3)
+    t[:full, 0] = 1.0
+    b[:full, 1] = 1.0
+    return t, b
+
+
 def _cross32(a, b):
     return np.stack([a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1], a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2],
                      a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]], axis=1).astype(np.float32)
@@ -267,9 +296,15 @@ def _local_matrix(node):
     return m
 
 
-def loadPrimitives(asset):
+TANGENT_RULES = ("reference", "uv")
+
+
+def loadPrimitives(asset, tangents="reference"):
     """gltfloader.cpp:122-255. Returns {mesh index: [Primitive, ...]} for the meshes the default scene uses, in
-    ascending mesh index."""
+    ascending mesh index. `tangents`: what a primitive without TANGENT gets — "reference": the outcome of the reference's
+    MikkTSpace call as written (mikktspace_as_called), "uv": frames from the UV derivatives."""
+    if tangents not in TANGENT_RULES:
+        raise ValueError("tangents must be one of " + ", ".join(TANGENT_RULES))
     doc = asset.doc
     used = set()
     _walk(doc, lambda node, world: used.add(node["mesh"]) if "mesh" in node else None)
@@ -306,6 +341,8 @@ def loadPrimitives(asset):
                 m.tangent = np.ascontiguousarray(t[:, :3], np.float32)
                 w = t[:, 3] if t.shape[1] >= 4 else np.ones(n, np.float32)     # Vec3: assume w = +1
                 m.bitangent = (_cross32(m.normal, m.tangent) * w[:, None].astype(np.float32)).astype(np.float32)
+            elif tangents == "reference":
+                m.tangent, m.bitangent = mikktspace_as_called(n)
             else:
                 tb = meshes._tangent_frames(m.position, m.uv, m.normal, m.indices.reshape(-1, 3))
                 m.tangent, m.bitangent = tb[:, 0, :].copy(), tb[:, 1, :].copy()
@@ -415,10 +452,10 @@ def addInstancesToScene(asset, scene, gltfIdToSceneId, gltfModelIdToMaterials):
     _walk(asset.doc, visit)
 
 
-def loadScene(filepath):
+def loadScene(filepath, tangents="reference"):
     """gltfloader.cpp:440-456 without the Vulkan handles; the caller builds the tables (Scene.build)."""
     asset = loadGltf(filepath)
-    prims = loadPrimitives(asset)
+    prims = loadPrimitives(asset, tangents)
     scene = Scene()
     model_ids = addMeshesToScene(scene, prims)
     tex_ids = addTexturesToScene(asset, scene)

@@ -90,6 +90,15 @@ int rbhost_tables_gltf(const char* path, int requireEmitter, SceneTables** out) 
     });
 }
 
+// tangentRule: 0 = the reference's MikkTSpace call as written, 1 = frames from the UV derivatives (host/gltf.h)
+int rbhost_tables_gltf_tangents(const char* path, int requireEmitter, int tangentRule, SceneTables** out) {
+    return guarded([&] {
+        if (tangentRule != 0 && tangentRule != 1) throw std::runtime_error("tangentRule must be 0 (reference) or 1 (uv)");
+        Scene s = load_gltf_scene(path, nullptr, tangentRule == 0 ? GltfTangents::Reference : GltfTangents::Uv);
+        *out = new SceneTables(s.build(requireEmitter != 0));
+    });
+}
+
 int rbhost_tables_desc(SceneTables* t, RB200SceneDesc* out, float* totalEmissiveWeight) {
     return guarded([&] {
         *out = t->desc();

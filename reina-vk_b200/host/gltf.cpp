@@ -458,9 +458,22 @@ struct Primitive {
     long materialIdx = -1;
     bool hasTangents = false;
 
+    // What genTangSpaceDefault (MikkTSpace@3e895b4) writes through the reference's callbacks (gltfloader.cpp:16-67,
+    // 207-222): the call sees faces f = vertices 3f .. 3f+2 whose UVs are all (0, 0) (TEXCOORD_0 is read afterwards), so
+    // every triangle keeps InitTriInfo's GROUP_WITH_ANY mark, Build4RuleGroups opens no group and every corner keeps the
+    // tangent space it was initialised with — (1, 0, 0) / (0, 1, 0); vertices beyond the last complete triple keep the zeros
+    // of their value-initialisation. The derivation is written out in reina-vk_b200/gltf.py (mikktspace_as_called).
+    void mikktspace_as_called() {
+        const size_t n = position.size() / 3, full = 3 * (n / 3);
+        tangent.assign(n * 3, 0.0f);
+        bitangent.assign(n * 3, 0.0f);
+        for (size_t v = 0; v < full; v++) { tangent[3 * v] = 1.0f; bitangent[3 * v + 1] = 1.0f; }
+        hasTangents = true;
+    }
+
     // toModelData, gltfloader.cpp:257-285
     ModelData toModelData() const {
-        if (!hasTangents) return make_model(position, uv, normal, indices);     // the importer's own tangent rule
+        if (!hasTangents) return make_model(position, uv, normal, indices);     // GltfTangents::Uv: frames from the UV derivatives
         const size_t n = position.size() / 3;
         ModelData md;
         md.vertices.resize(n * 4);
@@ -542,7 +555,7 @@ void walk(const Json& doc, F&& visit) {
 }
 
 // loadPrimitives, gltfloader.cpp:122-255
-std::map<long, std::vector<Primitive>> load_primitives(const Asset& a) {
+std::map<long, std::vector<Primitive>> load_primitives(const Asset& a, GltfTangents tangents) {
     std::set<long> used;
     walk(a.doc, [&](const Json& node, const M4&) { if (const Json* m = node.find("mesh")) used.insert(m->integer()); });
     std::map<long, std::vector<Primitive>> out;
@@ -597,6 +610,8 @@ std::map<long, std::vector<Primitive>> load_primitives(const Asset& a) {
                     const float cx = ny * tz - nz * ty, cy = nz * tx - nx * tz, cz = nx * ty - ny * tx;
                     m.bitangent[3 * i] = cx * w; m.bitangent[3 * i + 1] = cy * w; m.bitangent[3 * i + 2] = cz * w;
                 }
+            } else if (tangents == GltfTangents::Reference) {
+                m.mikktspace_as_called();
             }
             prims.push_back(std::move(m));
         }
@@ -692,9 +707,9 @@ Material material_of(const Asset& a, const Primitive& p, const std::map<long, in
 
 }  // namespace
 
-Scene load_gltf_scene(const std::string& path, bool* hasEmitter) {
+Scene load_gltf_scene(const std::string& path, bool* hasEmitter, GltfTangents tangents) {
     const Asset asset = load_gltf(path);
-    const std::map<long, std::vector<Primitive>> prims = load_primitives(asset);
+    const std::map<long, std::vector<Primitive>> prims = load_primitives(asset, tangents);
     Scene scene;
     std::map<long, std::vector<uint32_t>> objectIds;                      // addMeshesToScene, :345-355
     for (const auto& kv : prims)

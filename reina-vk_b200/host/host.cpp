@@ -105,9 +105,9 @@ Scene make_obj_scene(const std::vector<ObjRequest>& objs, bool addLight) {
     return s;
 }
 
-Scene make_gltf_scene(const std::string& path, bool addLightIfDark) {
+Scene make_gltf_scene(const std::string& path, bool addLightIfDark, bool tangentsFromUv) {
     bool emits = false;
-    Scene s = load_gltf_scene(path, &emits);
+    Scene s = load_gltf_scene(path, &emits, tangentsFromUv ? GltfTangents::Uv : GltfTangents::Reference);
     if (!emits && addLightIfDark) {
         std::fprintf(stderr, "warning: %s has no emissive material; adding the Cornell light panel so that next-event "
                              "estimation has an emitter\n", path.c_str());

@@ -53,7 +53,7 @@ Scene make_obj_scene(const std::vector<ObjRequest>& objs, bool addLight);
 // reina::scene::gltf::loadScene (src/scene/gltf/gltfloader.cpp:440-456): the default scene of a .gltf / .glb file.
 // The reference leaves the light panel commented out (:452) and then fails in Scene::build when nothing emits; here
 // the Cornell light panel is added in that case when addLightIfDark is set (a warning says so).
-Scene make_gltf_scene(const std::string& path, bool addLightIfDark);
+Scene make_gltf_scene(const std::string& path, bool addLightIfDark, bool tangentsFromUv = false);
 
 // RAII over RB200Context / RB200Scene; every failing call throws std::runtime_error(rb200_last_error())
 class Renderer {

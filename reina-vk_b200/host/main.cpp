@@ -24,6 +24,8 @@ static void usage() {
         "  --obj FILE           render this OBJ instead of a built-in scene (repeatable); the Cornell light panel is added\n"
         "  --gltf FILE          render the default scene of a glTF 2.0 file (.gltf or .glb), the reference's default scene path;\n"
         "                       when none of its materials emits and NEE is on, the Cornell light panel is added\n"
+        "  --gltf-tangents RULE tangent frames of glTF primitives without TANGENT: reference (default: what the reference's\n"
+        "                       MikkTSpace call yields as written, the constant frame (1,0,0) / (0,1,0)) | uv (from the UV derivatives)\n"
         "  --material NAME      material of the following --obj: lambertian | metal | dielectric | disney (default lambertian)\n"
         "  --albedo R,G,B       albedo of the following --obj (default 0.8,0.8,0.8)\n"
         "  --roughness X  --ior X  --metallic X     parameters of the following --obj\n"
@@ -55,6 +57,7 @@ static bool parse_vec3(const char* s, std::array<float, 3>& out) {
 
 int main(int argc, char** argv) {
     std::string configPath = "config/config.toml", sceneName, finalOut, outDir = ".", dumpPc, gltfPath;
+    bool gltfTangentsUv = false;
     std::vector<ObjRequest> objs;
     std::string nextTexture, nextNormalMap, nextBumpMap;
     Material nextMat;
@@ -81,6 +84,12 @@ int main(int argc, char** argv) {
                 nextTexture.clear(); nextNormalMap.clear(); nextBumpMap.clear();
             }
             else if (a == "--gltf") gltfPath = value();
+            else if (a == "--gltf-tangents") {
+                const std::string r = value();
+                if (r == "reference") gltfTangentsUv = false;
+                else if (r == "uv") gltfTangentsUv = true;
+                else throw std::runtime_error("--gltf-tangents: reference | uv");
+            }
             else if (a == "--texture") nextTexture = value();
             else if (a == "--normal-map") nextNormalMap = value();
             else if (a == "--bump-map") nextBumpMap = value();
@@ -121,7 +130,7 @@ int main(int argc, char** argv) {
         if (spp < 0 || seconds < 0) throw std::runtime_error("--spp and --seconds must not be negative");
 
         if (!gltfPath.empty() && !objs.empty()) throw std::runtime_error("--gltf and --obj cannot be combined");
-        Scene scene = !gltfPath.empty() ? make_gltf_scene(gltfPath, cfg.nee)
+        Scene scene = !gltfPath.empty() ? make_gltf_scene(gltfPath, cfg.nee, gltfTangentsUv)
                       : objs.empty()    ? make_builtin_scene(cfg.scene)
                                         : make_obj_scene(objs, true);
         SceneTables tables = scene.build(cfg.nee);

@@ -341,3 +341,47 @@ def test_emissive_cdf_sharing_is_reproduced_as_written(host, rb, gl, tmp_path):
         gl.loadScene(path).build(require_emitter=True)
     h = C.c_void_p()
     assert host.rbhost_tables_gltf(path.encode(), 1, C.byref(h)) != 0 and "unordered_map::at" in err(host)
+
+
+@pytest.mark.filterwarnings("ignore:falling back to UV")
+def test_missing_tangents_follow_the_reference_call_as_written(host, rb, gl, tmp_path):
+    """gltfloader.cpp:207-222 hands MikkTSpace the vertex array as un-indexed triples whose UVs are still all zero
+    (TEXCOORD_0 is read at :225-249). For that input the algorithm opens no group and every corner keeps its initial
+    tangent space (gltf.mikktspace_as_called): tangent (1,0,0), bitangent (0,1,0) for the vertices of complete triples,
+    zeros for the left-over ones; the normal row is the vertex normal. Default rule of both importers; "uv" is the
+    importer's own rule and both importers agree on it too."""
+    t, b = gl.mikktspace_as_called(8)
+    assert (t[:6] == (1, 0, 0)).all() and (b[:6] == (0, 1, 0)).all() and not t[6:].any() and not b[6:].any()
+    t, b = gl.mikktspace_as_called(2)                   # fewer than three vertices: genTangSpace returns before writing
+    assert not t.any() and not b.any()
+
+    path, _ = gf.build(tmp_path)
+    asset = gl.loadGltf(path)
+    doc_prims = [p for mi in (0, 1, 2) for p in asset.doc["meshes"][mi]["primitives"]]
+    prims = [p for _, ps in sorted(gl.loadPrimitives(asset).items()) for p in ps]
+    uvprims = [p for _, ps in sorted(gl.loadPrimitives(asset, tangents="uv").items()) for p in ps]
+    seen = 0
+    for dp, p, q in zip(doc_prims, prims, uvprims):
+        if "TANGENT" in dp["attributes"]:
+            assert (p.tangent == q.tangent).all() and (p.bitangent == q.bitangent).all()
+            continue
+        seen += 1
+        n = p.position.shape[0]
+        full = 3 * (n // 3)
+        assert (p.tangent[:full] == np.float32([1, 0, 0])).all() and (p.bitangent[:full] == np.float32([0, 1, 0])).all()
+        assert not p.tangent[full:].any() and not p.bitangent[full:].any()
+        tbn = p.toModelData().tbns.reshape(-1, 3, 3)
+        assert (tbn[:, 2, :] == p.normal).all() and (tbn[:full, 0, :] == (1, 0, 0)).all()
+        assert np.abs(q.tangent - p.tangent).max() > 0.1        # the UV rule really is a different frame
+    assert seen >= 2
+    with pytest.raises(ValueError):
+        gl.loadPrimitives(asset, tangents="mikk")
+
+    host.rbhost_tables_gltf_tangents.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    for rule, name in ((0, "reference"), (1, "uv")):
+        h = C.c_void_p()
+        assert host.rbhost_tables_gltf_tangents(path.encode(), 1, rule, C.byref(h)) == 0, err(host)
+        assert_tables_identical(cpp_tables(host, rb, h), py_tables(gl.loadScene(path, tangents=name).build(require_emitter=True)))
+        host.rbhost_tables_free(h)
+    h = C.c_void_p()
+    assert host.rbhost_tables_gltf_tangents(path.encode(), 1, 2, C.byref(h)) != 0
