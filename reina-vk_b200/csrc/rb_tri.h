@@ -53,9 +53,12 @@ RB_HD rb_ray_shear rb_ray_prepare(rb_v3 d) {
 /* m . p with a fixed evaluation order (one multiply, two fused multiply-adds) */
 RB_HD float rb_row3(rb_v3 m, rb_v3 p) { return fmaf(m.z, p.z, fmaf(m.y, p.y, m.x * p.x)); }
 
-/* Returns true when the (infinite) ray line crosses the triangle with det != 0; outputs t, b1, b2. */
-RB_HD bool rb_tri_intersect(rb_v3 org, const rb_ray_shear& s, rb_v3 v0, rb_v3 v1, rb_v3 v2,
-                            float* t_out, float* b1_out, float* b2_out) {
+/* The test up to (not including) its three divisions: returns true when the (infinite) ray line crosses the triangle
+ * with det != 0 and yields det, T and the edge functions V, W: t = T / det, (b1, b2) = (V, W) / det. Split out so that
+ * the traversal kernel can postpone the barycentric divisions to the one candidate that ends up closest; the
+ * operands, and therefore the quotients, are the same either way. */
+RB_HD bool rb_tri_edges(rb_v3 org, const rb_ray_shear& s, rb_v3 v0, rb_v3 v1, rb_v3 v2,
+                        float* det_out, float* T_out, float* V_out, float* W_out) {
     const rb_v3 A = v0 - org, B = v1 - org, C = v2 - org;
     const float Ax = rb_row3(s.mx, A), Ay = rb_row3(s.my, A);
     const float Bx = rb_row3(s.mx, B), By = rb_row3(s.my, B);
@@ -80,7 +83,16 @@ RB_HD bool rb_tri_intersect(rb_v3 org, const rb_ray_shear& s, rb_v3 v0, rb_v3 v1
     if (det == 0.0f) return false;
 
     const float Az = rb_row3(s.mz, A), Bz = rb_row3(s.mz, B), Cz = rb_row3(s.mz, C);
-    const float T = U * Az + V * Bz + W * Cz;
+    *T_out = U * Az + V * Bz + W * Cz;
+    *det_out = det; *V_out = V; *W_out = W;
+    return true;
+}
+
+/* Returns true when the (infinite) ray line crosses the triangle with det != 0; outputs t, b1, b2. */
+RB_HD bool rb_tri_intersect(rb_v3 org, const rb_ray_shear& s, rb_v3 v0, rb_v3 v1, rb_v3 v2,
+                            float* t_out, float* b1_out, float* b2_out) {
+    float det, T, V, W;
+    if (!rb_tri_edges(org, s, v0, v1, v2, &det, &T, &V, &W)) return false;
     *t_out = T / det;
     *b1_out = V / det;
     *b2_out = W / det;

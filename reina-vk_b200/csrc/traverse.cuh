@@ -63,6 +63,31 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
 #define RB_LEAN_FILL 1       // nested-loop fill of the pooled work list when a chunk's triangles fit (see trace_queue)
 #endif
 
+// RB_DEFER_BARY=1 (closest hit): a candidate's barycentric divisions V / det, W / det are postponed to the commit of the
+// ray. The warp's payload row of a ray keeps (V, W, triangle, det) of its current best — it is only ever rewritten by a
+// better candidate of the same ray, so it survives from pass to pass — and the lane keeps just (t, primitive id) in
+// registers. Two IEEE divisions (~30 instructions) leave every round of the pooled triangle phase, three registers
+// (b1, b2, tri) leave the lane's persistent state (k_extend then fits 64 registers without spilling); the quotients are
+// the same operands divided once, later. MEASURED ON B200 (profiles/r02m_variant_sweep.txt), bit-identical (46 parity
+// tests): SLOWER — k_extend 18.17 -> 18.86 ms per step at 7 x 128 threads, 18.18 at 8 x 128 / 4 x 256 with 64 registers:
+// the divisions of a round are already skipped when no lane's line crosses its triangle, and the commit — which runs
+// with ~6 lanes — now carries two divisions and a shared-memory read. Off.
+#ifndef RB_DEFER_BARY
+#define RB_DEFER_BARY 0
+#endif
+// RB_FAST_RCP=1: 1 / d for the BOX tests from MUFU.RCP (1 ulp) instead of the IEEE sequence (~12 instructions each): the
+// slack of node_step (2^-20 relative on every plane) covers a 2^-23 relative change of all planes of an axis; the
+// triangle test's shear constants stay IEEE. B200: k_extend 18.86 -> 18.57 ms (with RB_DEFER_BARY=1).
+#ifndef RB_FAST_RCP
+#define RB_FAST_RCP 0
+#endif
+// RB_DOM_AXIS=1: the ray's dominant axis for the culling margin (node_step) is found once per ray and kept in bits 8..9
+// of oct_inv instead of three compares per node step. B200: SLOWER, k_extend 18.86 -> 19.24 ms (the extra live bits cost
+// more in the node step's register allocation than the compares). Off.
+#ifndef RB_DOM_AXIS
+#define RB_DOM_AXIS 0
+#endif
+
 #ifndef RB_STACK_IN_STRUCT
 #define RB_STACK_IN_STRUCT 0    // 1: the round-1 layout (deep stack array as a member of Traversal), kept for comparison
 #endif
@@ -195,6 +220,12 @@ __device__ __forceinline__ float byte_f(uint32_t w, int j, uint32_t biasWord) {
 #define RB_ORIGIN_FROM_STAGE 1
 #endif
 
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 template <bool ANY, bool COUNT>
 struct Traversal {
 #if !RB_ORIGIN_FROM_STAGE
@@ -202,6 +233,13 @@ struct Traversal {
 #endif
     float idx, idy, idz;
     uint32_t oct_inv;
+    __device__ __forceinline__ uint32_t oct3() const {
+#if RB_DOM_AXIS
+        return oct_inv & 7u;
+#else
+        return oct_inv;
+#endif
+    }
     uint2 ngroup, tgroup;
     int sp, tsp;
     uint32_t tcount;              // triangles queued in tgroup + tstack
@@ -238,12 +276,25 @@ struct Traversal {
 #if !RB_ORIGIN_FROM_STAGE
         o = org;
 #endif
-        best.t = tmax_; best.b1 = 0.f; best.b2 = 0.f; best.tri = 0xFFFFFFFFu; best.gid = 0xFFFFFFFFu;
+        best.t = tmax_; best.gid = 0xFFFFFFFFu;
+        if (ANY || !RB_DEFER_BARY) { best.b1 = 0.f; best.b2 = 0.f; best.tri = 0xFFFFFFFFu; }
         const float ooeps = 8.2718061e-25f;   // 2^-80: keeps 1/d finite for axis-parallel rays (box tests only)
+#if RB_FAST_RCP
+        idx = fast_rcp(fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+        idy = fast_rcp(fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+        idz = fast_rcp(fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+#else
         idx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
         idy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
         idz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+#endif
         oct_inv = (idx < 0.f ? 0u : 4u) | (idy < 0.f ? 0u : 2u) | (idz < 0.f ? 0u : 1u);
+#if RB_DOM_AXIS
+        {
+            const float ax = fabsf(idx), ay = fabsf(idy), az = fabsf(idz);
+            oct_inv |= ((ax <= ay && ax <= az) ? 0u : (ay <= az ? 1u : 2u)) << 8;
+        }
+#endif
         const rb_ray_shear sh = rb_ray_prepare(d);
         rayStage[0] = make_float4(org.x, org.y, org.z, tmax_);
         rayStage[1] = make_float4(sh.mx.x, sh.mx.y, sh.mx.z, sh.Sz);
@@ -284,7 +335,7 @@ struct Traversal {
         const uint32_t base = ngroup.x;
         ngroup.y &= ~(1u << bitIndex);
         if (ngroup.y > 0x00FFFFFFu) push(ngroup, ws);
-        const uint32_t slot = (bitIndex - 24u) ^ oct_inv;
+        const uint32_t slot = (bitIndex - 24u) ^ oct3();
         const uint32_t rel = __popc(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
         const float4* np = reinterpret_cast<const float4*>(nodes + (base + rel));
 #if RB_WIDE_LOADS
@@ -319,14 +370,20 @@ struct Traversal {
         // less than 1e-4 of a node's size.
         // (the vertices' ray parameters are measured along the ray's dominant axis — the one with the smallest |1/d| —, so the
         // node's slab along THAT axis bounds them; the other axes' slabs can be arbitrarily wide for a nearly parallel ray)
+#if RB_DOM_AXIS
+        const uint32_t dom = oct_inv >> 8;
+        const float es = dom == 0u ? sx : (dom == 1u ? sy : sz), ec = dom == 0u ? cx : (dom == 1u ? cy : cz);
+        const float margin = RB_CULL_MARGIN * fmaf(256.0f, fabsf(es), fabsf(ec));
+#else
         const float ax = fabsf(idx), ay = fabsf(idy), az = fabsf(idz);
         const float ex = fmaf(256.0f, fabsf(sx), fabsf(cx)), ey = fmaf(256.0f, fabsf(sy), fabsf(cy)), ez = fmaf(256.0f, fabsf(sz), fabsf(cz));
         const float margin = RB_CULL_MARGIN * ((ax <= ay && ax <= az) ? ex : (ay <= az ? ey : ez));
+#endif
         const float kx = jx + margin, ky = jy + margin, kz = jz + margin;
         const float cnx = fmaf(-BYTE_BIAS, sx, cx - kx), cfx = fmaf(-BYTE_BIAS, sx, cx + kx);
         const float cny = fmaf(-BYTE_BIAS, sy, cy - ky), cfy = fmaf(-BYTE_BIAS, sy, cy + ky);
         const float cnz = fmaf(-BYTE_BIAS, sz, cz - kz), cfz = fmaf(-BYTE_BIAS, sz, cz + kz);
-        const uint32_t oct_inv4 = oct_inv * 0x01010101u;
+        const uint32_t oct_inv4 = oct3() * 0x01010101u;
         const uint32_t kb = c_byteBiasWord;
 
         ngroup.x = __float_as_uint(n1.x);
@@ -370,7 +427,7 @@ struct Traversal {
         // queued triangle (the traversal kernels stall mostly on these dependent fetches)
         if (ngroup.y > 0x00FFFFFFu) {
             const uint32_t nb = 31u - (uint32_t)__clz(ngroup.y);
-            const uint32_t nslot = (nb - 24u) ^ oct_inv;
+            const uint32_t nslot = (nb - 24u) ^ oct3();
             const uint32_t nrel = __popc(ngroup.y & ~(0xFFFFFFFFu << nslot) & 0xFFu);
             const char* pn = reinterpret_cast<const char*>(nodes + (ngroup.x + nrel));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(pn));
@@ -457,6 +514,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
             const unsigned long long seed = has ? hit_key(tr.best.t, tr.best.gid) : ~0ull;
             ws.bestKey[lane] = seed;
 #if RB_COOP_FILL
+            static_assert(!RB_DEFER_BARY, "the cooperative fill uses the payload rows as scratch; RB_DEFER_BARY keeps the best candidate there");
             bool filled = false;
             if constexpr (TStackShared<ANY>::value && RB_TSTACK_N >= RB_CHUNK) if (total <= (uint32_t)RB_WORK_CAP) {
                 filled = true;
@@ -529,7 +587,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                 bool cand = false;
                 unsigned long long mykey = 0ull;
                 uint32_t owner = 0, triIdx = 0;
-                float b1 = 0.f, b2 = 0.f;
+                float b1 = 0.f, b2 = 0.f, det = 0.f;
                 if (b + lane < count) {
                     const uint32_t item = ws.work[b + lane];
                     triIdx = item >> 5; owner = item & 31u;
@@ -548,8 +606,16 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                     rb_ray_shear sh;
                     sh.mx = rb_mk3(r1.x, r1.y, r1.z); sh.my = rb_mk3(r2.x, r2.y, r2.z); sh.mz = rb_axis3(__float_as_int(r2.w), r1.w);
                     float t;
-                    if (rb_tri_intersect(rb_mk3(r0.x, r0.y, r0.z), sh, rb_mk3(va.x, va.y, va.z), rb_mk3(vb.x, vb.y, vb.z),
-                                         rb_mk3(vc.x, vc.y, vc.z), &t, &b1, &b2)) {
+#if RB_DEFER_BARY
+                    float T;
+                    const bool crosses = rb_tri_edges(rb_mk3(r0.x, r0.y, r0.z), sh, rb_mk3(va.x, va.y, va.z), rb_mk3(vb.x, vb.y, vb.z),
+                                                      rb_mk3(vc.x, vc.y, vc.z), &det, &T, &b1, &b2);      // b1, b2 hold V, W until the commit
+                    if (crosses) t = T / det;
+#else
+                    const bool crosses = rb_tri_intersect(rb_mk3(r0.x, r0.y, r0.z), sh, rb_mk3(va.x, va.y, va.z), rb_mk3(vb.x, vb.y, vb.z),
+                                                          rb_mk3(vc.x, vc.y, vc.z), &t, &b1, &b2);
+#endif
+                    if (crosses) {
                         if (t > 0.0f && t < r0.w) {
                             mykey = hit_key(t, __float_as_uint(vc.w));
                             atomicMin(&ws.bestKey[owner], mykey);
@@ -559,7 +625,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                 }
                 if (!ANY) {
                     __syncwarp();
-                    if (cand && ws.bestKey[owner] == mykey) ws.payload[owner] = make_float4(b1, b2, __uint_as_float(triIdx), 0.f);
+                    if (cand && ws.bestKey[owner] == mykey) ws.payload[owner] = make_float4(b1, b2, __uint_as_float(triIdx), det);
                 }
             }
             __syncwarp();
@@ -568,9 +634,11 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                 if (k != seed) {
                     if (ANY) anyHitFound = true;
                     else {
-                        const float4 p = ws.payload[lane];
                         tr.best.t = __uint_as_float((uint32_t)(k >> 32)); tr.best.gid = (uint32_t)k;
+#if !RB_DEFER_BARY
+                        const float4 p = ws.payload[lane];
                         tr.best.b1 = p.x; tr.best.b2 = p.y; tr.best.tri = __float_as_uint(p.z);
+#endif
                     }
                 }
             }
@@ -584,6 +652,16 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                 tr.best.tri = 0u;     // any-hit: only "occluded or not" is meaningful
                 commit(rayIdx, tr.best); has = false; tr.tcount = 0u;
             } else if (!tr.want_node() && tr.stack_empty() && tr.tcount == 0u) {
+#if RB_DEFER_BARY
+                if (!ANY) {
+                    // the payload row still holds (V, W, triangle, det) of the candidate that set the final key
+                    tr.best.b1 = 0.f; tr.best.b2 = 0.f; tr.best.tri = 0xFFFFFFFFu;
+                    if (tr.best.gid != 0xFFFFFFFFu) {
+                        const float4 p = ws.payload[lane];
+                        tr.best.b1 = p.x / p.w; tr.best.b2 = p.y / p.w; tr.best.tri = __float_as_uint(p.z);
+                    }
+                }
+#endif
                 commit(rayIdx, tr.best); has = false;
             }
         }
