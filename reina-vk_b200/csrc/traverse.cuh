@@ -77,9 +77,10 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
 #endif
 // RB_FAST_RCP=1: 1 / d for the BOX tests from MUFU.RCP (1 ulp) instead of the IEEE sequence (~12 instructions each): the
 // slack of node_step (2^-20 relative on every plane) covers a 2^-23 relative change of all planes of an axis; the
-// triangle test's shear constants stay IEEE. B200: k_extend 18.86 -> 18.57 ms (with RB_DEFER_BARY=1).
+// triangle test's shear constants stay IEEE. B200: k_extend 18.20 -> 18.06 ms, k_shadow 9.61 -> 9.53 ms per step,
+// results bit-identical (46 parity tests). On.
 #ifndef RB_FAST_RCP
-#define RB_FAST_RCP 0
+#define RB_FAST_RCP 1
 #endif
 // RB_DOM_AXIS=1: the ray's dominant axis for the culling margin (node_step) is found once per ray and kept in bits 8..9
 // of oct_inv instead of three compares per node step. B200: SLOWER, k_extend 18.86 -> 19.24 ms (the extra live bits cost
@@ -122,11 +123,16 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
 #endif
 template <bool ANY> struct TStackShared { static constexpr bool value = ((RB_TSTACK_SHARED >> (ANY ? 0 : 1)) & 1) != 0; };
 // The first RB_STACK_SHARED_* entries of the node-group stack live in shared memory, deeper ones in local memory.
+// With 128-thread blocks of k_extend (7 per SM) and no payload rows in the any-hit stage, the blocks of either kernel need
+// 160-172 KB per SM, and the carve-out the driver picks for that (196 KB) has room for deeper shared stacks at no cost in
+// L1 (B200, headline step, profiles/r02n_variant_sweep.txt): closest hit 4 / 5 / 6 / 7 entries: k_extend 18.07 / 17.95 /
+// 17.68 / 17.63 ms; any hit 4 / 5 / 6: k_shadow 9.49 / 9.42 / 9.54 ms. (Forcing the 228 KB carve-out instead — 28 KB of L1 —
+// costs k_extend 3 % and k_shadow 9 %; a 5-entry triangle-group list that would fit the 164 KB carve-out costs 10 %.)
 #ifndef RB_STACK_SHARED_ANY
-#define RB_STACK_SHARED_ANY 4
+#define RB_STACK_SHARED_ANY 5
 #endif
 #ifndef RB_STACK_SHARED_CLOSEST
-#define RB_STACK_SHARED_CLOSEST 4
+#define RB_STACK_SHARED_CLOSEST 6
 #endif
 template <bool ANY> struct StackShared { static constexpr int value = ANY ? RB_STACK_SHARED_ANY : RB_STACK_SHARED_CLOSEST; };
 
@@ -181,12 +187,15 @@ template <int N> struct WarpTStack<true, N> { uint2 tstack[N][32]; };    // per 
 template <bool ANY> struct TStackEntries { static constexpr int value = (ANY && RB_TSTACK_N == RB_CHUNK) ? RB_CHUNK_ANY : RB_TSTACK_N; };
 template <int K> struct WarpStack { uint2 nstack[K][32]; };
 template <> struct WarpStack<0> { };
+// per owner: b1, b2, bits(triangle index) of the current best — closest hit only (an any-hit ray has no use for it, and
+// without these 512 bytes four 256-thread blocks of k_shadow need 160 KB instead of 176 KB of the SM's shared memory)
+template <bool ANY> struct WarpPayload { float4 payload[32]; };
+template <> struct WarpPayload<true> { };
 template <bool ANY>
-struct WarpShared : WarpTStack<TStackShared<ANY>::value, TStackEntries<ANY>::value>, WarpStack<StackShared<ANY>::value> {
+struct WarpShared : WarpTStack<TStackShared<ANY>::value, TStackEntries<ANY>::value>, WarpStack<StackShared<ANY>::value>, WarpPayload<ANY> {
     float4 ray[32][3];                    // per lane: (o, tmax), (mx, Sz), (my, bits(kz)) — shear rows of rb_tri.h
     uint32_t work[RB_WORK_CAP];           // triangle index << 5 | owner lane (the build refuses >= 2^27 triangles)
     unsigned long long bestKey[32];       // per owner: min over candidates of (t bits << 32 | global primitive id)
-    float4 payload[32];                   // per owner: b1, b2, bits(triangle index) of the current best
 };
 
 // per byte: 0xFF if bit 7 is set, else 0x00 (prmt's sign-replicate mode; __byte_perm only honours 3 selector bits)
@@ -623,7 +632,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                         }
                     }
                 }
-                if (!ANY) {
+                if constexpr (!ANY) {
                     __syncwarp();
                     if (cand && ws.bestKey[owner] == mykey) ws.payload[owner] = make_float4(b1, b2, __uint_as_float(triIdx), det);
                 }
@@ -632,7 +641,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
             if (has) {
                 const unsigned long long k = ws.bestKey[lane];
                 if (k != seed) {
-                    if (ANY) anyHitFound = true;
+                    if constexpr (ANY) anyHitFound = true;
                     else {
                         tr.best.t = __uint_as_float((uint32_t)(k >> 32)); tr.best.gid = (uint32_t)k;
 #if !RB_DEFER_BARY
@@ -653,7 +662,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                 commit(rayIdx, tr.best); has = false; tr.tcount = 0u;
             } else if (!tr.want_node() && tr.stack_empty() && tr.tcount == 0u) {
 #if RB_DEFER_BARY
-                if (!ANY) {
+                if constexpr (!ANY) {
                     // the payload row still holds (V, W, triangle, det) of the candidate that set the final key
                     tr.best.b1 = 0.f; tr.best.b2 = 0.f; tr.best.tri = 0xFFFFFFFFu;
                     if (tr.best.gid != 0xFFFFFFFFu) {
