@@ -89,6 +89,19 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
 #define RB_DOM_AXIS 0
 #endif
 
+// RB_PRECLAIM=1: a lane whose ray has no node work left will be idle after the coming triangle phase, whatever the tests
+// say; it claims its NEXT ray before that phase (the aggregated atomic), reads the queue entry while the work list is
+// filled and requests the ray's record into L2 / L1 while the triangles are tested — so the refill's chain of three
+// dependent long-latency accesses (atomic -> queue entry -> ray record: a tenth of the kernel's stall samples,
+// profiles/r02a_k_extend_source_lines.csv, with the whole warp waiting) is off the critical path. Which lane traces which
+// ray changes; results do not depend on that. MEASURED ON B200 (profiles/r02p_variant_sweep.txt), bit-identical (46 parity
+// tests): SLOWER — k_extend 17.68 -> 17.91 ms, k_shadow 9.44 -> 9.68 ms per step: the second ballot / atomic / shuffle
+// sequence and the prefetches are issued by the same few lanes, and the other warps of the SM were already covering that
+// latency. Off.
+#ifndef RB_PRECLAIM
+#define RB_PRECLAIM 0
+#endif
+
 #ifndef RB_STACK_IN_STRUCT
 #define RB_STACK_IN_STRUCT 0    // 1: the round-1 layout (deep stack array as a member of Traversal), kept for comparison
 #endif
@@ -458,10 +471,15 @@ __device__ __forceinline__ unsigned long long hit_key(float t, uint32_t gid) {
 // Warp-cooperative persistent trace loop (see the header comment).
 //   fetch(i)      -> load ray i into (o, d, tmax); called for i < n
 //   commit(i, h)  -> consume the finished ray i
-template <bool ANY, bool COUNT, class Fetch, class Commit>
+//   look(i)       -> (RB_PRECLAIM) first half of a prefetch of ray i: returns what is needed to address its record
+//                    (the queue entry), request(v) -> second half: asks for the record itself (prefetch instructions)
+struct NoLook { __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return i; } };
+struct NoRequest { __device__ __forceinline__ void operator()(uint32_t) const { } };
+template <bool ANY, bool COUNT, class Fetch, class Commit, class Look = NoLook, class Request = NoRequest>
 __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, const TriRecord* __restrict__ tris,
                                             uint32_t n, uint32_t* cursor, Fetch fetch, Commit commit,
-                                            uint32_t& nodeVisits, uint32_t& triTests, WarpShared<ANY>& ws) {
+                                            uint32_t& nodeVisits, uint32_t& triTests, WarpShared<ANY>& ws,
+                                            Look look = Look(), Request request = Request()) {
     const uint32_t lane = threadIdx.x & 31u;
     Traversal<ANY, COUNT> tr;
 #if !RB_STACK_IN_STRUCT
@@ -474,9 +492,34 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
     bool has = false;
     bool exhausted = false;
     uint32_t rayIdx = 0;
+#if RB_PRECLAIM
+    uint32_t nextI = 0xFFFFFFFFu;        // index of the ray this lane claimed ahead of time (0xFFFFFFFF: none)
+#endif
     for (;;) {
         // ---- 1. refill ----
         uint32_t busy = __ballot_sync(0xffffffffu, has);
+#if RB_PRECLAIM
+        {
+            // idle lanes that claimed their next ray before the last triangle phase already hold its index
+            uint32_t idx = has ? 0xFFFFFFFFu : nextI;
+            nextI = 0xFFFFFFFFu;
+            const uint32_t need = __ballot_sync(0xffffffffu, !has && idx == 0xFFFFFFFFu);
+            if (!exhausted && need != 0u && __popc(busy) < RB_REFILL) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(need));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (!has && idx == 0xFFFFFFFFu) idx = base + __popc(need & ((1u << lane) - 1u));
+                if (base + (uint32_t)__popc(need) >= n) exhausted = true;
+            }
+            if (!has && idx < n) {
+                rb_v3 o, d; float tmax;
+                fetch(idx, o, d, tmax);
+                tr.init(o, d, tmax, ws.ray[lane]);
+                rayIdx = idx; has = true;
+            }
+            busy = __ballot_sync(0xffffffffu, has);
+        }
+#else
         if (!exhausted && __popc(busy) < RB_REFILL) {
             const uint32_t need = ~busy;
             uint32_t base = 0;
@@ -494,6 +537,7 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
             if (base + (uint32_t)__popc(need) >= n) exhausted = true;
             busy = __ballot_sync(0xffffffffu, has);
         }
+#endif
         if (busy == 0u) break;
 
         // ---- 2. a chunk of wide-node steps per lane ----
@@ -506,6 +550,27 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                 tr.node_step(nodes, tris, nodeVisits, ws, pol);
             }
         }
+
+#if RB_PRECLAIM
+        // ---- 2b. lanes that will be idle after the triangle phase claim their next ray now ----
+        uint32_t looked = 0u;
+        {
+            const bool leaving = has && !tr.want_node() && tr.stack_empty();
+            const uint32_t lv = __ballot_sync(0xffffffffu, leaving);
+            if (!exhausted && lv != 0u) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(lv));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (leaving) {
+                    nextI = base + __popc(lv & ((1u << lane) - 1u));
+                    if (nextI < n) looked = look(nextI);                 // the load is in flight while the work list is filled
+                    else nextI = 0xFFFFFFFFu;
+                }
+                if (base + (uint32_t)__popc(lv) >= n) exhausted = true;
+            }
+        }
+        bool requested = false;
+#endif
 
         // ---- 3. pooled triangle phase ----
         bool anyHitFound = false;
@@ -591,6 +656,9 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
 #endif
             while (has && tr.tcount > 0u && pos < (uint32_t)RB_WORK_CAP) ws.work[pos++] = (tr.take_tri(ws) << 5) | lane;
             __syncwarp();
+#if RB_PRECLAIM
+            if (!requested) { requested = true; if (nextI != 0xFFFFFFFFu) request(looked); }      // ... and the record while the triangles are tested
+#endif
             const uint32_t count = min(total, (uint32_t)RB_WORK_CAP);
             for (uint32_t b = 0; b < count; b += 32u) {
                 bool cand = false;
@@ -655,6 +723,9 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
             if (total <= (uint32_t)RB_WORK_CAP) break;
         }
 
+#if RB_PRECLAIM
+        if (!requested && nextI != 0xFFFFFFFFu) request(looked);      // no triangles were queued in this chunk
+#endif
         // ---- finished rays ----
         if (has) {
             if (ANY && anyHitFound) {

@@ -194,6 +194,8 @@ __global__ void __launch_bounds__(BLOCK) k_generate(WaveParams P, uint32_t lane,
     P.rayQ[parity][s_base + rank] = slot;
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // ---------------------------------------------------------------------------------------------------
 // extend
 // ---------------------------------------------------------------------------------------------------
@@ -245,7 +247,9 @@ __global__ void __launch_bounds__(RB_EXTEND_BLOCK, RB_EXTEND_MINBLOCKS) k_extend
                 if (bin == b) queue_push(P.matQ[b], &cnt[CNT_MAT0 + b], slot);
 #endif
         },
-        nodeVisits, triTests, ws[threadIdx.x >> 5]);
+        nodeVisits, triTests, ws[threadIdx.x >> 5],
+        [&](uint32_t i) { return q[i]; },
+        [&](uint32_t slot) { prefetch_l1(reinterpret_cast<const char*>(P.rayO.p + (size_t)slot * STATE_STRIDE)); });
     if (COUNT) {
         atomicAdd(&P.stats[ST_NODES], (unsigned long long)nodeVisits);
         atomicAdd(&P.stats[ST_TRIS], (unsigned long long)triTests);
@@ -666,7 +670,9 @@ __global__ void __launch_bounds__(RB_SHADOW_BLOCK, RB_SHADOW_MINBLOCKS) k_shadow
             const rb_v3 L = rb_mk3(L4.x, L4.y, L4.z) + combined * rb_mk3(T.x, T.y, T.z);
             P.rad[slot] = make_float4(L.x, L.y, L.z, 0.f);
         },
-        nodeVisits, triTests, ws[threadIdx.x >> 5]);
+        nodeVisits, triTests, ws[threadIdx.x >> 5],
+        [&](uint32_t i) { return i; },
+        [&](uint32_t i) { prefetch_l1(reinterpret_cast<const char*>(P.shO.p + i)); prefetch_l1(reinterpret_cast<const char*>(P.shD.p + i)); });
     if (COUNT) {      // the counting pass runs one lane (context_create), so lane 0's counters are the batch's
         atomicAdd(&P.stats[ST_NODES_SHADOW], (unsigned long long)nodeVisits);
         atomicAdd(&P.stats[ST_TRIS_SHADOW], (unsigned long long)triTests);
