@@ -383,6 +383,12 @@ RB200_API int rb200_group_create(uint32_t width, uint32_t height, const int* dev
                                  RB200Group** out);
 RB200_API int rb200_group_destroy(RB200Group* group);
 RB200_API int rb200_group_size(const RB200Group* group);
+/* 1 when the group runs latency mode (RB200_FLAG_GROUP_TILES) with peer stores: every device can address device 0's memory,
+ * so the kernel that folds a batch into the image (k_accumulate) stores each pixel its device owns into device 0's image
+ * over NVLink as well, and a presented frame needs no collective — device 0 waits for the others' "tiles done" events,
+ * snapshots its image and post-processes it. 0: one ncclReduce per presented frame (sample split; latency mode without
+ * peer access, or with RB200_GROUP_TILES_REDUCE=1 in the environment). Frames are bit-identical either way. */
+RB200_API int rb200_group_uses_peer_stores(const RB200Group* group);
 RB200_API int rb200_group_context(RB200Group* group, int index, RB200Context** out);       /* member context (not owned by the caller) */
 RB200_API int rb200_group_set_tile_size(RB200Group* group, uint32_t tileSize);             /* latency mode, before the first batch */
 /* Upload the tables and build the hierarchy on every device concurrently; fails if the replicas' hashes differ (the

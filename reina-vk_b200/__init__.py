@@ -272,6 +272,10 @@ class Group:
     def size(self):
         return int(self.lib.rb200_group_size(self._g))
 
+    def uses_peer_stores(self):
+        """Latency mode without a collective: the devices store their pixels into device 0's image over NVLink."""
+        return bool(self.lib.rb200_group_uses_peer_stores(self._g))
+
     def render_batches(self, pc, first_batch, batches_per_device):
         abi.check(self.lib, self.lib.rb200_group_render_batches(self._g, self._scene, C.byref(pc), first_batch, batches_per_device))
 

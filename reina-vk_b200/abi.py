@@ -190,6 +190,7 @@ SYMBOLS = {
     "rb200_group_create": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_int), C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]),
     "rb200_group_destroy": (C.c_int, [C.c_void_p]),
     "rb200_group_size": (C.c_int, [C.c_void_p]),
+    "rb200_group_uses_peer_stores": (C.c_int, [C.c_void_p]),
     "rb200_group_context": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "rb200_group_set_tile_size": (C.c_int, [C.c_void_p, C.c_uint32]),
     "rb200_group_scene_create": (C.c_int, [C.c_void_p, C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]),

@@ -237,6 +237,7 @@ struct RB200Context {
     // staggerWave: 0 = 5/32 of the batch's waves, -1 = off, else the wave.
     int staggerWave = 0;
     cudaEvent_t frontMark = nullptr;
+    float4* peerImage = nullptr;               // latency mode of a one-process group: device 0's image, written by k_accumulate over NVLink (group.cu)
     std::vector<cudaEvent_t> ldrPendingEvents; // completion events of the outstanding rb200_read_ldr_async copies, oldest first
     std::vector<cudaEvent_t> ldrEventPool;
     std::deque<cudaEvent_t> batchEvents;       // one per rb200_render_batch still in flight (rb200_wait_batches_pending)

@@ -172,12 +172,33 @@ struct Worker {
 
 using namespace rb200;
 
+// Host-side hand-shake of one presented frame in peer-store latency mode (see rb200_group_present): the members tell the
+// root that their "tiles done" events are recorded, the root tells the members that its snapshot event is recorded.
+struct PresentSync {
+    std::mutex m;
+    std::condition_variable cv;
+    uint64_t arrived = 0, released = 0;
+    void arrive() { { std::lock_guard<std::mutex> lk(m); arrived++; } cv.notify_all(); }
+    void wait_arrivals(uint64_t target) { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return arrived >= target; }); }
+    void release(uint64_t gen) { { std::lock_guard<std::mutex> lk(m); released = gen; } cv.notify_all(); }
+    void wait_release(uint64_t gen) { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return released >= gen; }); }
+};
+
 struct RB200Group {
     std::vector<int> devices;
     std::vector<RB200Context*> ctx;
     std::vector<Worker*> workers;
     uint32_t width = 0, height = 0, flags = 0;
     bool tiles = false;
+    // Latency mode with peer access between the devices: every member's k_accumulate stores the pixels it owns straight
+    // into device 0's image over NVLink (RB200Context::peerImage), so a presented frame needs no collective at all — the
+    // root waits for the members' "tiles done" events, snapshots its own image and post-processes the snapshot.
+    bool peerTiles = false;
+    std::vector<cudaEvent_t> tileDone;      // per member, recorded on its front-end stream
+    cudaEvent_t rootSnap = nullptr;         // root: its snapshot of the image has been taken
+    float4* rootSnapshot = nullptr;
+    uint64_t presentGen = 0;
+    PresentSync sync;
     uint64_t batchesRendered = 0;       // over all devices (sum mode: the divisor of the resolve)
     int n() const { return (int)devices.size(); }
     int wait_all() {
@@ -249,6 +270,14 @@ RB200_API int rb200_context_reduced_device_ptr(RB200Context* ctx, void** out_dev
 RB200_API int rb200_group_destroy(RB200Group* g) {
     if (!g) return RB200_OK;
     for (Worker* w : g->workers) { w->wait(); w->stop(); delete w; }
+    if (g->peerTiles) {
+        for (size_t i = 0; i < g->tileDone.size(); i++)
+            if (g->tileDone[i]) { cudaSetDevice(g->devices[i]); cudaStreamSynchronize(g->ctx[i]->stream); cudaEventDestroy(g->tileDone[i]); }
+        cudaSetDevice(g->devices[0]);
+        if (g->ctx[0]) cudaStreamSynchronize(g->ctx[0]->stream);
+        if (g->rootSnap) cudaEventDestroy(g->rootSnap);
+        if (g->rootSnapshot) cudaFree(g->rootSnapshot);
+    }
     for (RB200Context* c : g->ctx) if (c) { comm_detach(c); rb200_context_destroy(c); }
     delete g;
     return RB200_OK;
@@ -282,11 +311,44 @@ RB200_API int rb200_group_create(uint32_t width, uint32_t height, const int* dev
         for (int i = 0; i < numDevices; i++)
             if ((rc = comm_attach(g->ctx[i], comms[i], i, numDevices, 0)) != RB200_OK) { rb200_group_destroy(g); return rc; }
     }
+    // latency mode: peer stores instead of the reduce when every member can reach device 0's memory
+    // (RB200_GROUP_TILES_REDUCE=1 keeps the reduce, for comparison)
+    const char* forceReduce = getenv("RB200_GROUP_TILES_REDUCE");
+    if (g->tiles && numDevices > 1 && !(forceReduce && atoi(forceReduce) != 0)) {
+        bool all = true;
+        for (int i = 1; i < numDevices && all; i++) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[i], devices[0]) != cudaSuccess || !can) all = false;
+        }
+        if (all) {
+            g->tileDone.assign(numDevices, nullptr);
+            for (int i = 1; i < numDevices; i++)
+                g->workers[i]->post([g, i]() -> int {
+                    RB_CUDA(cudaSetDevice(g->devices[i]));
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(g->devices[0], 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                    else if (e != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", g->devices[i], g->devices[0], cudaGetErrorString(e)); return RB200_ERR_CUDA; }
+                    RB_CUDA(cudaEventCreateWithFlags(&g->tileDone[i], cudaEventDisableTiming));
+                    return RB200_OK;
+                });
+            g->workers[0]->post([g]() -> int {
+                RB_CUDA(cudaSetDevice(g->devices[0]));
+                RB_CUDA(cudaEventCreateWithFlags(&g->rootSnap, cudaEventDisableTiming));
+                RB_CUDA(cudaMalloc(&g->rootSnapshot, (size_t)g->width * g->height * sizeof(float4)));
+                return RB200_OK;
+            });
+            if ((rc = g->wait_all()) != RB200_OK) { rb200_group_destroy(g); return rc; }
+            for (int i = 1; i < numDevices; i++) g->ctx[i]->peerImage = g->ctx[0]->wp.image;
+            g->peerTiles = true;
+        }
+    }
     *out = g;
     return RB200_OK;
 }
 
 RB200_API int rb200_group_size(const RB200Group* g) { return g ? g->n() : 0; }
+
+RB200_API int rb200_group_uses_peer_stores(const RB200Group* g) { return g && g->peerTiles ? 1 : 0; }
 
 RB200_API int rb200_group_context(RB200Group* g, int index, RB200Context** out) {
     if (!g || !out || index < 0 || index >= g->n()) { set_error("invalid group member"); return RB200_ERR_INVALID_ARGUMENT; }
@@ -385,6 +447,36 @@ RB200_API int rb200_group_present(RB200Group* g, const RB200BloomPushConsts* blo
         else g->workers[0]->post([g, total, b, t] { return rb200_present_sum(g->ctx[0], nullptr, total, &b, &t); });
         return RB200_OK;
     }
+    if (g->peerTiles) {
+        // Every pixel of device 0's image was stored by its owner (k_accumulate, over NVLink for the other devices). A frame:
+        // members record "my tiles of everything queued so far are in" on their streams; the root waits for those events,
+        // snapshots its image and post-processes the snapshot; the members' streams wait for the snapshot, so the stores of
+        // later batches cannot tear the frame. The condition variables only order the host-side record / wait calls.
+        const uint64_t gen = ++g->presentGen;
+        const int n = g->n();
+        for (int i = 1; i < n; i++)
+            g->workers[i]->post([g, i, gen]() -> int {
+                cudaError_t e = cudaSetDevice(g->devices[i]);
+                if (e == cudaSuccess) e = cudaEventRecord(g->tileDone[i], g->ctx[i]->stream);
+                g->sync.arrive();
+                g->sync.wait_release(gen);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(g->ctx[i]->stream, g->rootSnap, 0);
+                if (e != cudaSuccess) { set_error("latency-mode present on device %d: %s", g->devices[i], cudaGetErrorString(e)); return RB200_ERR_CUDA; }
+                return RB200_OK;
+            });
+        g->workers[0]->post([g, b, t, gen, n]() -> int {
+            g->sync.wait_arrivals(gen * (uint64_t)(n - 1));
+            RB200Context* c = g->ctx[0];
+            cudaError_t e = cudaSetDevice(c->device);
+            for (int i = 1; i < n && e == cudaSuccess; i++) e = cudaStreamWaitEvent(c->stream, g->tileDone[i], 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(g->rootSnapshot, c->wp.image, (size_t)g->width * g->height * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(g->rootSnap, c->stream);
+            g->sync.release(gen);
+            if (e != cudaSuccess) { set_error("latency-mode present on device %d: %s", c->device, cudaGetErrorString(e)); return RB200_ERR_CUDA; }
+            return postprocess(c, &b, &t, g->rootSnapshot);
+        });
+        return RB200_OK;
+    }
     for (int i = 0; i < g->n(); i++)
         g->workers[i]->post([g, total, b, t, i] { return rb200_context_reduce_present(g->ctx[i], total, &b, &t); });
     return RB200_OK;
@@ -414,6 +506,19 @@ RB200_API int rb200_group_read_hdr(RB200Group* g, float* rgba32f) {
     if (rc != RB200_OK) return rc;
     const uint32_t total = (uint32_t)g->batchesRendered;
     const size_t n = (size_t)g->width * g->height;
+    if (g->peerTiles) {
+        // device 0's image is complete once every device has folded its batches: drain them all, then read it
+        for (int i = 0; i < g->n(); i++) g->workers[i]->post([g, i] { return rb200_synchronize(g->ctx[i]); });
+        if ((rc = g->wait_all()) != RB200_OK) return rc;
+        g->workers[0]->post([g, n, rgba32f]() -> int {
+            RB200Context* c = g->ctx[0];
+            RB_CUDA(cudaSetDevice(c->device));
+            RB_CUDA(cudaMemcpyAsync(rgba32f, c->wp.image, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+            RB_CUDA(cudaStreamSynchronize(c->stream));
+            return RB200_OK;
+        });
+        return g->workers[0]->wait();
+    }
     for (int i = 0; i < g->n(); i++)
         g->workers[i]->post([g, i, total, n, rgba32f]() -> int {
             RB200Context* c = g->ctx[i];

@@ -748,7 +748,10 @@ __global__ void __launch_bounds__(BLOCK) k_accumulate(float4* __restrict__ image
                                                       uint32_t sampleBatch, uint32_t flags,
                                                       const unsigned long long* __restrict__ laneStats,
                                                       unsigned long long* __restrict__ cumStats,
-                                                      unsigned long long* __restrict__ lastStats) {
+                                                      unsigned long long* __restrict__ lastStats, float4* __restrict__ peer) {
+    // peer (latency mode of a one-process group, group.cu): device 0's image. Every pixel has exactly one owner, so the
+    // owner stores its new value there as well — plain stores over NVLink from the kernel that produces the value, instead
+    // of a separate reduce of images that are zero outside each device's tiles.
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < ST_COUNT) { const unsigned long long v = laneStats[i]; cumStats[i] += v; lastStats[i] = v; }     // batches are folded one at a time, in order: no race
     if (i >= n) return;
@@ -757,7 +760,10 @@ __global__ void __launch_bounds__(BLOCK) k_accumulate(float4* __restrict__ image
     if (m.w == 0.f) {
         // documented deviation: the reference writes 0/0 and poisons the pixel; batch 0 writes black, later batches keep
         // the previous value, sum mode adds nothing
-        if (!(flags & RB200_FLAG_ACCUM_SUM) && sampleBatch == 0u) image[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+        if (!(flags & RB200_FLAG_ACCUM_SUM) && sampleBatch == 0u) {
+            image[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+            if (peer) peer[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+        }
         return;
     }
     rb_v3 fin = rb_mk3(m.x, m.y, m.z);
@@ -770,6 +776,7 @@ __global__ void __launch_bounds__(BLOCK) k_accumulate(float4* __restrict__ image
             fin = (rb_mk3(prev.x, prev.y, prev.z) * (float)sampleBatch + fin) / (float)(sampleBatch + 1u);
         }
         image[i] = make_float4(fin.x, fin.y, fin.z, 1.f);
+        if (peer) peer[i] = make_float4(fin.x, fin.y, fin.z, 1.f);
     }
 }
 
@@ -1114,7 +1121,8 @@ int render_batch(RB200Context* ctx, const RB200Scene* scene, const RB200RtPushCo
     if (prevEngine >= 0 && prevEngine != e) RB_CUDA(cudaStreamWaitEvent(s, ctx->eng[prevEngine].accumDone, 0));
     RB_CUDA(cudaStreamWaitEvent(s, ctx->frontMark, 0));
     k_accumulate<<<(P.N + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(P.image, P.mean.p + (size_t)hl * P.N, P.N, pc->sampleBatch, ctx->flags,
-                                                             P.stats + (size_t)hl * ST_COUNT, ctx->statsSnap, ctx->statsLast); nl++;
+                                                             P.stats + (size_t)hl * ST_COUNT, ctx->statsSnap, ctx->statsLast,
+                                                             (ctx->flags & RB200_FLAG_ACCUM_SUM) ? nullptr : ctx->peerImage); nl++;
     RB_CUDA(cudaEventRecord(E.accumDone, s));
     RB_CUDA(cudaStreamWaitEvent(ctx->stream, E.accumDone, 0));
     RB_CUDA(cudaGetLastError());

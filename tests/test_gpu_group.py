@@ -26,6 +26,11 @@ def sum_image(rb, wl, batches, device=0):
     return img
 
 
+def peer_access(a, b):
+    import torch
+    return torch.cuda.can_device_access_peer(b, a)
+
+
 def test_group_of_one_device_is_the_sum_mode_renderer(rb):
     wl = rb.configs.small_mixed(96, 72, nee=True, samples_per_pixel=2, max_bounces=6)
     g = rb.Group(wl.width, wl.height, wl.tables, [0], flags=rb.RB200_FLAG_NEE)
@@ -89,23 +94,41 @@ def test_two_devices_sample_split_reduces_exactly_the_two_partial_sums(ol, rb):
 
 
 @pytest.mark.skipif("device_count() < 2")
-def test_two_devices_interleaved_tiles_give_the_single_gpu_image_bit_for_bit(ol, rb):
-    """Latency mode: every device traces its 16 x 16 tiles of every batch (running average); the reduce of the two images
-    is the single-GPU image, HDR bit for bit and LDR byte for byte."""
+@pytest.mark.parametrize("reduce", [False, True])
+def test_two_devices_interleaved_tiles_give_the_single_gpu_image_bit_for_bit(ol, rb, reduce, monkeypatch):
+    """Latency mode: every device traces its 16 x 16 tiles of every batch (running average). With peer access the devices
+    store their pixels straight into device 0's image from k_accumulate (no collective); with RB200_GROUP_TILES_REDUCE=1
+    the images — zero outside a device's tiles — are added by one ncclReduce per frame. Either way every presented frame
+    (one per batch: the host-side hand-shake of the peer mode runs four times) is the single-GPU frame, HDR bit for bit
+    and LDR byte for byte."""
+    if reduce:
+        monkeypatch.setenv("RB200_GROUP_TILES_REDUCE", "1")
+    else:
+        monkeypatch.delenv("RB200_GROUP_TILES_REDUCE", raising=False)
     wl = rb.configs.small_mixed(96, 72, nee=True, samples_per_pixel=2, max_bounces=6)
     g = rb.Group(wl.width, wl.height, wl.tables, [0, 1], flags=rb.RB200_FLAG_NEE, tiles=True)
+    assert g.uses_peer_stores() == (False if reduce else peer_access(0, 1))
     rb.abi.check(g.lib, g.lib.rb200_group_set_tile_size(g._g, 16))
-    g.render_batches(wl.push_constants(0), 0, 3)
+    r = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE)
+    for b in range(4):
+        g.render_batches(wl.push_constants(0), b, 1)
+        g.present()
+        ldr = g.read_ldr()
+        r.render_batch(wl.push_constants(b))
+        r.postprocess()
+        assert (ldr == r.read_ldr()).all(), "frame %d" % b
     got = g.read_hdr()
+    g.render_batches(wl.push_constants(0), 4, 2)        # two batches behind one present
     g.present()
     ldr = g.read_ldr()
+    got2 = g.read_hdr()
     g.close()
-    r = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE)
-    for b in range(3):
-        r.render_batch(wl.push_constants(b))
     want = r.read_hdr()
+    for b in (4, 5):
+        r.render_batch(wl.push_constants(b))
     r.postprocess()
-    want_ldr = r.read_ldr()
+    want_ldr, want2 = r.read_ldr(), r.read_hdr()
     r.close()
     assert (bits(got[..., :3]) == bits(want[..., :3])).all()
+    assert (bits(got2[..., :3]) == bits(want2[..., :3])).all()
     assert (ldr == want_ldr).all()

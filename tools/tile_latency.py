@@ -1,5 +1,6 @@
 """Latency mode on N devices of one box, through rb200_group_* — one process, a context and a host
-thread per device, interleaved 32 x 32 tiles, one ncclReduce per presented frame.
+thread per device, interleaved 32 x 32 tiles; a frame is assembled by peer stores into device 0's image (default when the
+devices have peer access) or by one ncclReduce per presented frame (RB200_GROUP_TILES_REDUCE=1).
 
 For N in --gpus: time from queueing one batch (8 spp) to its tonemapped frame on the host, one frame at a time (the
 interactive case: nothing in flight behind it), and the frame rate of the same loop; the N-device frame must equal the
@@ -32,6 +33,7 @@ def main():
     for n in [int(x) for x in args.gpus.split(",")]:
         g = rb.Group(wl.width, wl.height, wl.tables, list(range(n)), flags=rb.RB200_FLAG_NEE, tiles=True)
         hashes = {g.bvh_info(i)["hash"] for i in range(n)}
+        peer = g.uses_peer_stores()
         # one frame at a time: batch b of every device's tiles -> reduce -> bloom + tonemap -> host
         lat = []
         for b in range(args.warmup + args.frames):
@@ -46,6 +48,8 @@ def main():
         if ref_ldr is None:
             ref_ldr, ref_hdr = ldr, hdr
         out = {"mode": "interleaved tiles 32x32 (rb200_group_*, RB200_FLAG_GROUP_TILES)", "config": args.config, "n_gpus": n,
+               "frame_assembly": "peer stores from k_accumulate into device 0's image (no collective)" if peer else
+                                 ("one ncclReduce per frame" if n > 1 else "single device"),
                "width": wl.width, "height": wl.height, "frames": args.frames, "spp_per_frame": bench.SPP,
                "frame_latency_ms_median": float(np.median(lat)), "frame_latency_ms_min": float(lat.min()),
                "frame_latency_ms_max": float(lat.max()), "frames_per_s": float(1e3 / lat.mean()),
