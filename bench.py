@@ -396,6 +396,7 @@ def main():
         out["roofline"] = roofline(rb, wl, local_rank, stream, nee_flag)
     if rank == 0 and world == 1 and not args.no_nee and not args.no_as_shipped:
         out["as_shipped"] = as_shipped(rb, wl, local_rank, stream, K)
+        out["null_shadow_rays_skipped"] = null_shadow_skip(rb, wl, local_rank, stream, K)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(rb, wl)
     if rank == 0:
@@ -430,6 +431,38 @@ def as_shipped(rb, wl, device, stream, steps):
     return {"value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms / steps, "rays_per_step": rays / steps,
             "spp_per_s": SPP * steps / (ms * 1e-3), "nee": False,
             "note": "flags = 0: no shadow rays, emission picked up by BRDF sampling only; same scene, camera, sample counts"}
+
+
+def null_shadow_skip(rb, wl, device, stream, steps):
+    """The same workload with RB200_FLAG_SKIP_NULL_SHADOW_RAYS (opt-in): shadow rays whose contribution is exactly zero before
+    the visibility test are answered without a traversal (bit-identical images, tests/test_gpu_parity2.py). `value` counts
+    only the rays that were traversed, so it can fall while spp/s rises."""
+    import torch
+    r = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE | rb.RB200_FLAG_SKIP_NULL_SHADOW_RAYS, device=device,
+                    stream=stream.cuda_stream)
+    engines, lanes, _ = r.engine_config()
+    fill = 3 * engines if lanes > 1 else engines
+    with torch.cuda.stream(stream):
+        for i in range(fill + 3):
+            r.render_batch(wl.push_constants(i))
+        r.synchronize()
+        _, c0 = r.stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            r.render_batch(wl.push_constants(fill + 3 + i))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        _, c1 = r.stats()
+    ms = e0.elapsed_time(e1)
+    r.close()
+    d = {k: c1[k] - c0[k] for k in ("extendRays", "shadowRays", "shadowRaysSkipped")}
+    rays = d["extendRays"] + d["shadowRays"] - d["shadowRaysSkipped"]
+    return {"value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s (traversed rays only)", "ms_per_step": ms / steps,
+            "rays_traversed_per_step": rays / steps, "shadow_rays_skipped_per_step": d["shadowRaysSkipped"] / steps,
+            "share_of_shadow_rays_skipped": d["shadowRaysSkipped"] / max(1, d["shadowRays"]),
+            "spp_per_s": SPP * steps / (ms * 1e-3),
+            "note": "opt-in flag; the headline value above traverses every shadow ray the reference's estimator casts"}
 
 
 def roofline(rb, wl, device, stream, nee_flag):

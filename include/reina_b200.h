@@ -67,6 +67,15 @@ enum {
                                        * tiles of every batch instead of every n-th batch of all pixels */
     RB200_FLAG_TIME_KERNELS = 1u << 3, /* bracket every kernel of rb200_render_batch with CUDA events (per-class device
                                         times for the roofline report; serialises nothing but adds event overhead) */
+    RB200_FLAG_SKIP_NULL_SHADOW_RAYS = 1u << 6, /* next-event estimation: a shadow ray whose `direct` term is exactly +0 in all
+                                        three channels BEFORE the visibility test (the light faces away from the hit point, or lies
+                                        below its horizon: cosThetai or the geometry term is max(., 0) = 0) is answered "not
+                                        occluded" without being traversed — raygen adds (occluded ? 0 : direct) * wNEE + ..., and
+                                        direct is +0 either way (shaders/raytrace/raytrace.rgen.glsl:43-95, 174-177). The wavefront
+                                        evaluates `direct` before the shadow stage, so it can tell; the reference traces first.
+                                        Images are bit-identical with and without the flag. Such rays stay in RB200Stats::shadowRays
+                                        (they are rays of the estimator) and are also counted in shadowRaysSkipped. Off by default,
+                                        so that the traced ray set is the reference's. Flattened scenes only. */
     RB200_FLAG_TWO_LEVEL = 1u << 5   /* scenes of this context keep the reference's two-level structure (src/scene/Scene.cpp:
                                         93-111: ONE hierarchy per distinct object, a top-level hierarchy over the instances;
                                         rays are moved into object space with the inverse instance transform, as the Vulkan
@@ -187,6 +196,9 @@ typedef struct RB200Stats {
     uint64_t kernelLaunches; /* kernels launched by the library */
     uint64_t shadowNodeVisits; /* the part of nodeVisits / triTests spent on any-hit (shadow) rays */
     uint64_t shadowTriTests;
+    uint64_t shadowRaysSkipped; /* RB200_FLAG_SKIP_NULL_SHADOW_RAYS: shadow rays (included in shadowRays) answered without a traversal.
+                                 * Cumulative only, and counted when the shadow stage runs — with batches in flight it can be ahead
+                                 * of shadowRays, which is counted when a path ends; differences over a steady-state window agree */
 } RB200Stats;
 
 /* Device time per kernel class of the launches issued by the last rb200_render_batch (needs RB200_FLAG_TIME_KERNELS).

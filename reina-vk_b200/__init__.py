@@ -14,11 +14,11 @@ import numpy as np
 
 from . import abi, camera, configs, gltf, meshes, scene
 from .abi import (RB200_FLAG_ACCUM_SUM, RB200_FLAG_COUNT_BVH, RB200_FLAG_GROUP_TILES, RB200_FLAG_NEE, RB200_FLAG_TIME_KERNELS,
-                  RB200_FLAG_TWO_LEVEL,
+                  RB200_FLAG_SKIP_NULL_SHADOW_RAYS, RB200_FLAG_TWO_LEVEL,
                   BloomPushConsts, RB200Error, RtPushConsts, TonemappingPushConsts, load_library)
 from .scene import Material, ModelData, Scene, SceneTables
 
-__all__ = ["Renderer", "Group", "comm_unique_id", "RB200_FLAG_GROUP_TILES", "RB200_FLAG_TWO_LEVEL", "Material", "ModelData", "Scene", "SceneTables", "RtPushConsts", "BloomPushConsts",
+__all__ = ["Renderer", "Group", "comm_unique_id", "RB200_FLAG_GROUP_TILES", "RB200_FLAG_TWO_LEVEL", "RB200_FLAG_SKIP_NULL_SHADOW_RAYS", "Material", "ModelData", "Scene", "SceneTables", "RtPushConsts", "BloomPushConsts",
            "TonemappingPushConsts", "RB200_FLAG_NEE", "RB200_FLAG_ACCUM_SUM", "RB200_FLAG_COUNT_BVH", "RB200_FLAG_TIME_KERNELS",
            "RB200Error",
            "abi", "camera", "configs", "gltf", "meshes", "scene", "load_library"]

@@ -18,6 +18,7 @@ RB200_FLAG_COUNT_BVH = 1 << 2
 RB200_FLAG_TIME_KERNELS = 1 << 3
 RB200_FLAG_GROUP_TILES = 1 << 4
 RB200_FLAG_TWO_LEVEL = 1 << 5
+RB200_FLAG_SKIP_NULL_SHADOW_RAYS = 1 << 6
 
 
 class InstanceProperties(C.Structure):
@@ -91,6 +92,7 @@ class Stats(C.Structure):
         ("extendRays", C.c_uint64), ("shadowRays", C.c_uint64), ("paths", C.c_uint64),
         ("nodeVisits", C.c_uint64), ("triTests", C.c_uint64), ("waves", C.c_uint64),
         ("kernelLaunches", C.c_uint64), ("shadowNodeVisits", C.c_uint64), ("shadowTriTests", C.c_uint64),
+        ("shadowRaysSkipped", C.c_uint64),
     ]
 
     def as_dict(self):

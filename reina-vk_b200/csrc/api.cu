@@ -163,6 +163,7 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
     // rb200_present_sum's staging image: allocated here in sum mode (cudaMalloc synchronises the device, which would
     // drain the engines if it happened on the first presented frame), on first use otherwise
     if (flags & RB200_FLAG_ACCUM_SUM) A(c->resolved, N);
+    for (int en = 0; en < c->numEngines; en++) c->eng[en].P.nullShadow = c->statsSnap + ST_SHADOW_SKIPPED;
     WaveParams& P = c->wp;
 #undef A
     CK(cudaMemsetAsync(c->statsSnap, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
@@ -634,7 +635,7 @@ RB200_API int rb200_get_stats(RB200Context* ctx, RB200Stats* last_batch, RB200St
     L.shadowNodeVisits = lastc[ST_NODES_SHADOW]; L.shadowTriTests = lastc[ST_TRIS_SHADOW];
     Cm.extendRays = cum[ST_EXTEND]; Cm.shadowRays = cum[ST_SHADOW]; Cm.paths = cum[ST_PATHS];
     Cm.nodeVisits = cum[ST_NODES] + cum[ST_NODES_SHADOW]; Cm.triTests = cum[ST_TRIS] + cum[ST_TRIS_SHADOW];
-    Cm.shadowNodeVisits = cum[ST_NODES_SHADOW]; Cm.shadowTriTests = cum[ST_TRIS_SHADOW]; Cm.kernelLaunches = ctx->launches;
+    Cm.shadowNodeVisits = cum[ST_NODES_SHADOW]; Cm.shadowTriTests = cum[ST_TRIS_SHADOW]; Cm.shadowRaysSkipped = cum[ST_SHADOW_SKIPPED]; Cm.kernelLaunches = ctx->launches;
     if (last_batch) *last_batch = L;
     if (cumulative) *cumulative = Cm;
     return RB200_OK;

@@ -24,7 +24,7 @@ namespace rb200 {
 // counters of one wave parity set
 enum { CNT_RAYS = 0, CNT_MAT0 = 1, CNT_MISS = 5, CNT_SHADOW = 6, CNT_END = 7, CNT_CURSOR_EXTEND = 8, CNT_CURSOR_SHADOW = 9, CNT_SET = 12 };
 // device statistics (unsigned long long each)
-enum { ST_EXTEND = 0, ST_SHADOW = 1, ST_PATHS = 2, ST_NODES = 3, ST_TRIS = 4, ST_NODES_SHADOW = 5, ST_TRIS_SHADOW = 6, ST_COUNT = 8 };
+enum { ST_EXTEND = 0, ST_SHADOW = 1, ST_PATHS = 2, ST_NODES = 3, ST_TRIS = 4, ST_NODES_SHADOW = 5, ST_TRIS_SHADOW = 6, ST_SHADOW_SKIPPED = 7 /* cumulative array only */, ST_COUNT = 8 };
 
 // path flags kept in PathState.st.y (low byte); the traced-segment counter lives in bits 8..31
 enum { F_INSIDE = 1u, F_FIRST = 2u, F_PREVSKIP = 4u };
@@ -131,6 +131,7 @@ struct WaveParams {
     unsigned long long* stats;     // [RB_MAX_LANES][ST_COUNT]: counters of the batch each lane is rendering
     StateArr<float4> mean;         // per slot: mean of this batch's valid samples (xyz), w = 1 if any sample was valid
     float4* image;                 // HDR accumulation image (shared by all engines and lanes)
+    unsigned long long* nullShadow; // RB200_FLAG_SKIP_NULL_SHADOW_RAYS: cumulative count of shadow rays answered without a traversal
 };
 
 } // namespace rb200

@@ -553,6 +553,7 @@ RB200_API int rb200_group_get_stats(RB200Group* g, RB200Stats* cumulative) {
         cumulative->extendRays += s.extendRays; cumulative->shadowRays += s.shadowRays; cumulative->paths += s.paths;
         cumulative->nodeVisits += s.nodeVisits; cumulative->triTests += s.triTests; cumulative->waves += s.waves;
         cumulative->kernelLaunches += s.kernelLaunches; cumulative->shadowNodeVisits += s.shadowNodeVisits; cumulative->shadowTriTests += s.shadowTriTests;
+        cumulative->shadowRaysSkipped += s.shadowRaysSkipped;
     }
     return RB200_OK;
 }

@@ -322,7 +322,10 @@ struct Traversal {
         rayStage[1] = make_float4(sh.mx.x, sh.mx.y, sh.mx.z, sh.Sz);
         rayStage[2] = make_float4(sh.my.x, sh.my.y, sh.my.z, __int_as_float(sh.kz));
         sp = 0; tsp = 0; tcount = 0;
-        ngroup = make_uint2(0u, 0x80000000u);
+        // any hit: nothing can lie in (0, tmax) when tmax <= 0 — no node work is queued and the ray finishes, unoccluded,
+        // with the iteration it was fetched in (the light sample closer than the 0.001 the reference subtracts; k_shadow's
+        // null-contribution rays). The closest-hit kernels pass a constant tmax > 0.
+        ngroup = make_uint2(0u, (ANY && !(tmax_ > 0.0f)) ? 0u : 0x80000000u);
         tgroup = make_uint2(0u, 0u);
     }
 

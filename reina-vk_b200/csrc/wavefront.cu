@@ -644,6 +644,12 @@ __global__ void __launch_bounds__(RB_SHADOW_BLOCK, RB_SHADOW_MINBLOCKS) k_shadow
     uint32_t* cnt = P.counters + parity * CNT_SET;
     const uint32_t n = cnt[CNT_SHADOW];
     uint32_t nodeVisits = 0, triTests = 0;
+    // RB200_FLAG_SKIP_NULL_SHADOW_RAYS: a record whose `direct` term is +0 in every channel adds the same radiance whether
+    // the light is visible or not (commit below: direct * wNEE with direct = occluded ? 0 : +0). Such a ray is handed to the
+    // traversal with tmax = 0, for which Traversal::init queues no node work: it is committed as "not occluded" at the
+    // end of the iteration, through the same code as every other ray.
+    const bool skipNull = (P.flags & RB200_FLAG_SKIP_NULL_SHADOW_RAYS) != 0u;
+    uint32_t skipped = 0;
     extern __shared__ __align__(16) unsigned char rb_dyn_smem[];      // WarpShared<true>[RB_SHADOW_BLOCK / 32]
     WarpShared<true>* ws = reinterpret_cast<WarpShared<true>*>(rb_dyn_smem);
     trace_queue<true, COUNT>(
@@ -655,6 +661,10 @@ __global__ void __launch_bounds__(RB_SHADOW_BLOCK, RB_SHADOW_MINBLOCKS) k_shadow
             const float4 o4 = P.shO[i], d4 = P.shD[i];
 #endif
             o = rb_mk3(o4.x, o4.y, o4.z); d = rb_mk3(d4.x, d4.y, d4.z); tmax = o4.w;
+            if (skipNull) {
+                const float4 A = P.shA[i];
+                if ((__float_as_uint(A.x) | __float_as_uint(A.y) | __float_as_uint(A.z)) == 0u) { tmax = 0.0f; skipped++; }
+            }
         },
         [&](uint32_t i, const RayHit& h) {
             const bool occluded = h.tri != 0xFFFFFFFFu;
@@ -673,6 +683,10 @@ __global__ void __launch_bounds__(RB_SHADOW_BLOCK, RB_SHADOW_MINBLOCKS) k_shadow
         nodeVisits, triTests, ws[threadIdx.x >> 5],
         [&](uint32_t i) { return i; },
         [&](uint32_t i) { prefetch_l1(reinterpret_cast<const char*>(P.shO.p + i)); prefetch_l1(reinterpret_cast<const char*>(P.shD.p + i)); });
+    if (skipNull) {
+        skipped = __reduce_add_sync(0xffffffffu, skipped);
+        if ((threadIdx.x & 31u) == 0u && skipped) atomicAdd(P.nullShadow, (unsigned long long)skipped);
+    }
     if (COUNT) {      // the counting pass runs one lane (context_create), so lane 0's counters are the batch's
         atomicAdd(&P.stats[ST_NODES_SHADOW], (unsigned long long)nodeVisits);
         atomicAdd(&P.stats[ST_TRIS_SHADOW], (unsigned long long)triTests);
@@ -753,7 +767,8 @@ __global__ void __launch_bounds__(BLOCK) k_accumulate(float4* __restrict__ image
     // owner stores its new value there as well — plain stores over NVLink from the kernel that produces the value, instead
     // of a separate reduce of images that are zero outside each device's tiles.
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ST_COUNT) { const unsigned long long v = laneStats[i]; cumStats[i] += v; lastStats[i] = v; }     // batches are folded one at a time, in order: no race
+    // batches are folded one at a time, in order: no race (the skipped-shadow-ray slot of the cumulative array is k_shadow's)
+    if (i < ST_COUNT && i != ST_SHADOW_SKIPPED) { const unsigned long long v = laneStats[i]; cumStats[i] += v; lastStats[i] = v; }
     if (i >= n) return;
     const float4 m = mean[i];
     if (m.w < 0.f) return;       // tile partition: another rank's pixel

@@ -44,6 +44,8 @@ static void usage() {
         "  --tiles              with --gpus: latency mode, every device renders its interleaved 32 x 32 tiles of every batch\n"
         "  --two-level          keep one hierarchy per object and a top level over the instances (the reference's BLAS / TLAS,\n"
         "                       src/scene/Scene.cpp:93-111) instead of flattening the instances: less memory, slower rays\n"
+        "  --skip-null-shadow-rays  with NEE: shadow rays whose contribution is exactly zero before the visibility test (light facing\n"
+        "                       away or below the horizon) are answered without a traversal; same image, less work\n"
         "  --dump-pc FILE       write the 160-byte push-constant block of batch 0 to FILE\n"
         "  --quiet              no progress output\n");
 }
@@ -64,7 +66,7 @@ int main(int argc, char** argv) {
     nextMat.albedo = {0.8f, 0.8f, 0.8f};
     nextMat.interpNormals = true;
     long width = -1, height = -1, spp = 0, device = 0, gpus = 1;
-    bool tiles = false, twoLevel = false;
+    bool tiles = false, twoLevel = false, skipNullShadow = false;
     double seconds = 0.0;
     int nee = -1;
     bool quiet = false;
@@ -117,6 +119,7 @@ int main(int argc, char** argv) {
             else if (a == "--gpus") gpus = std::strtol(value(), nullptr, 10);
             else if (a == "--tiles") tiles = true;
             else if (a == "--two-level") twoLevel = true;
+            else if (a == "--skip-null-shadow-rays") skipNullShadow = true;
             else if (a == "--dump-pc") dumpPc = value();
             else if (a == "--quiet") quiet = true;
             else throw std::runtime_error("unknown option " + a + " (see --help)");
@@ -149,7 +152,7 @@ int main(int argc, char** argv) {
         opt.quiet = quiet;
         if (gpus < 1) throw std::runtime_error("--gpus must be at least 1");
         if (gpus > 1 || tiles) {
-            GroupRenderer group(cfg.width, cfg.height, int(gpus), (cfg.nee ? uint32_t(RB200_FLAG_NEE) : 0u) | (twoLevel ? uint32_t(RB200_FLAG_TWO_LEVEL) : 0u), tiles);
+            GroupRenderer group(cfg.width, cfg.height, int(gpus), (cfg.nee ? uint32_t(RB200_FLAG_NEE) : 0u) | (twoLevel ? uint32_t(RB200_FLAG_TWO_LEVEL) : 0u) | (skipNullShadow ? uint32_t(RB200_FLAG_SKIP_NULL_SHADOW_RAYS) : 0u), tiles);
             group.setScene(tables);
             if (!quiet) {
                 const RB200BvhInfo bvh = group.bvhInfo();
@@ -165,7 +168,7 @@ int main(int argc, char** argv) {
             return 0;
         }
 
-        Renderer renderer(cfg.width, cfg.height, int(device), (cfg.nee ? uint32_t(RB200_FLAG_NEE) : 0u) | (twoLevel ? uint32_t(RB200_FLAG_TWO_LEVEL) : 0u));
+        Renderer renderer(cfg.width, cfg.height, int(device), (cfg.nee ? uint32_t(RB200_FLAG_NEE) : 0u) | (twoLevel ? uint32_t(RB200_FLAG_TWO_LEVEL) : 0u) | (skipNullShadow ? uint32_t(RB200_FLAG_SKIP_NULL_SHADOW_RAYS) : 0u));
         renderer.setScene(tables);
         if (!quiet) {
             const RB200BvhInfo bvh = renderer.bvhInfo();

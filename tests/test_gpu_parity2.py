@@ -228,3 +228,38 @@ def test_bloom_skips_dark_tiles_without_changing_a_bit(ol, rb):
         want = ol.postprocess(img, bloom=bloom)
         assert (got == want).all(), thr
     r.close()
+
+
+def test_null_shadow_rays_answered_without_a_traversal_leave_the_image_unchanged(ol, rb):
+    """RB200_FLAG_SKIP_NULL_SHADOW_RAYS: shadow rays whose `direct` term is exactly +0 before the visibility test (the
+    light faces away or lies below the horizon of the hit point, raytrace.rgen.glsl:84-92) are not traversed by k_shadow.
+    On a scene with every material, textures, skips and three batches: image and ray counters are bit-identical to the
+    oracle's (which traces them all, as the reference does) and to the library without the flag, and a sizeable share of
+    the shadow rays is answered that way. C2-class geometry at 480 x 270 as a second case."""
+    shares = []
+    for wl in (rb.configs.small_mixed(160, 120, nee=True, samples_per_pixel=3, max_bounces=7),
+               rb.configs.bunny(480, 270, levels=4, samples_per_pixel=2, max_bounces=8)):
+        r = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE | rb.RB200_FLAG_SKIP_NULL_SHADOW_RAYS)
+        plain = rb.Renderer(wl.width, wl.height, wl.tables, flags=rb.RB200_FLAG_NEE)
+        sc = ol.OracleScene(wl.tables)
+        hdr_o = np.zeros((wl.height, wl.width, 4), np.float32)
+        for b in range(3):
+            pc = wl.push_constants(b)
+            r.render_batch(pc)
+            plain.render_batch(pc)
+            hdr_o, cnt = sc.render_batch(wl.width, wl.height, rb.RB200_FLAG_NEE, pc, hdr_o)
+            last, _ = r.stats()
+            assert (last["extendRays"], last["shadowRays"], last["paths"]) == (cnt["extendRays"], cnt["shadowRays"], cnt["paths"])
+        _, cum = r.stats()
+        _, cump = plain.stats()
+        g, gp = r.read_hdr(), plain.read_hdr()
+        r.close()
+        plain.close()
+        sc.close()
+        assert cump["shadowRaysSkipped"] == 0 and cum["shadowRaysSkipped"] < cum["shadowRays"]
+        shares.append(cum["shadowRaysSkipped"] / cum["shadowRays"])
+        assert (bits(gp) == bits(hdr_o)).all()
+        assert (bits(g) == bits(hdr_o)).all(), "%d pixels differ" % int((bits(g) != bits(hdr_o)).any(axis=-1).sum())
+    # light panels that cull their back face: a sizeable share of the first scene's shadow rays cannot contribute (in the
+    # second one most hits are metal or glass, which cast no shadow rays; a few per cent of the rest qualify)
+    assert shares[0] > 0.05 and shares[1] > 0.0, shares
