@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(RB_SHADE_BLOCK, MAT == 3 ? RB_DISNEY_MINBLOCKS
 // ---------------------------------------------------------------------------------------------------
 // shadow: shadowRayOccluded (nee.h.glsl:126-144) + the radiance update of rgen.glsl:174-177
 // ---------------------------------------------------------------------------------------------------
-template <bool COUNT>
+template <bool COUNT, bool SKIPNULL = false>
 __global__ void __launch_bounds__(RB_SHADOW_BLOCK, RB_SHADOW_MINBLOCKS) k_shadow(WaveParams P, int parity) {
     uint32_t* cnt = P.counters + parity * CNT_SET;
     const uint32_t n = cnt[CNT_SHADOW];
@@ -648,7 +648,8 @@ __global__ void __launch_bounds__(RB_SHADOW_BLOCK, RB_SHADOW_MINBLOCKS) k_shadow
     // the light is visible or not (commit below: direct * wNEE with direct = occluded ? 0 : +0). Such a ray is handed to the
     // traversal with tmax = 0, for which Traversal::init queues no node work: it is committed as "not occluded" at the
     // end of the iteration, through the same code as every other ray.
-    const bool skipNull = (P.flags & RB200_FLAG_SKIP_NULL_SHADOW_RAYS) != 0u;
+    // (a separate instantiation, so that the kernel of the default path is exactly the one without this code)
+    constexpr bool skipNull = SKIPNULL;
     uint32_t skipped = 0;
     extern __shared__ __align__(16) unsigned char rb_dyn_smem[];      // WarpShared<true>[RB_SHADOW_BLOCK / 32]
     WarpShared<true>* ws = reinterpret_cast<WarpShared<true>*>(rb_dyn_smem);
@@ -896,6 +897,10 @@ static int issue_waves(RB200Context* ctx, Engine& E, uint32_t count, uint32_t pa
         if (nee) {
             tm.tic(7);
             if (twoLevel) k_shadow_two_level<<<ctx->gTwoLevel[1], BLOCK, 0, s>>>(P, p);
+            else if (ctx->flags & RB200_FLAG_SKIP_NULL_SHADOW_RAYS) {
+                if (countBvh) k_shadow<true, true><<<ctx->gShadowC, RB_SHADOW_BLOCK, SMEM_SHADOW, s>>>(P, p);
+                else k_shadow<false, true><<<ctx->gShadow, RB_SHADOW_BLOCK, SMEM_SHADOW, s>>>(P, p);
+            }
             else if (countBvh) k_shadow<true><<<ctx->gShadowC, RB_SHADOW_BLOCK, SMEM_SHADOW, s>>>(P, p);
             else k_shadow<false><<<ctx->gShadow, RB_SHADOW_BLOCK, SMEM_SHADOW, s>>>(P, p);
             tm.toc();
@@ -1476,6 +1481,10 @@ int configure_wave_kernels(RB200Context* ctx) {
     ctx->gExtendC = persistent_grid(k_extend<true>, ctx->numSMs, RB_EXTEND_BLOCK, SMEM_EXTEND);
     ctx->gShadow = persistent_grid(k_shadow<false>, ctx->numSMs, RB_SHADOW_BLOCK, SMEM_SHADOW);
     ctx->gShadowC = persistent_grid(k_shadow<true>, ctx->numSMs, RB_SHADOW_BLOCK, SMEM_SHADOW);
+    if (ctx->flags & RB200_FLAG_SKIP_NULL_SHADOW_RAYS) {       // same shape, register cap and shared memory: the grids above fit
+        ctx->gShadow = std::min(ctx->gShadow, persistent_grid(k_shadow<false, true>, ctx->numSMs, RB_SHADOW_BLOCK, SMEM_SHADOW));
+        ctx->gShadowC = std::min(ctx->gShadowC, persistent_grid(k_shadow<true, true>, ctx->numSMs, RB_SHADOW_BLOCK, SMEM_SHADOW));
+    }
     ctx->gShade[0] = persistent_grid(k_shade<0>, ctx->numSMs, RB_SHADE_BLOCK);
     ctx->gShade[1] = persistent_grid(k_shade<1>, ctx->numSMs, RB_SHADE_BLOCK);
     ctx->gShade[2] = persistent_grid(k_shade<2>, ctx->numSMs, RB_SHADE_BLOCK);
