@@ -102,6 +102,18 @@ static constexpr uint32_t TRAV_MAX_DEPTH = 22;
 #define RB_PRECLAIM 0
 #endif
 
+#ifndef RB_FILL_UNROLL2
+#define RB_FILL_UNROLL2 0    // the nested-loop fill writes two triangles per trip (see trace_queue). B200: k_extend 17.69 ->
+                             // 17.86 ms (profiles/r02q_variant_sweep.txt), same checksums. Off.
+#endif
+// RB_BARY_LATE=1 (closest hit): the barycentric divisions V / det, W / det of a crossing are made only after its t passed
+// the (0, tmax) test — same operands, same quotients; a round in which no crossing is in range skips them. B200: k_extend
+// 17.69 -> 18.58 ms, k_shadow 9.47 -> 9.91 ms, same checksums (the split form of the test schedules worse than the
+// divisions cost, as with RB_DEFER_BARY). Off.
+#ifndef RB_BARY_LATE
+#define RB_BARY_LATE 0
+#endif
+
 #ifndef RB_STACK_IN_STRUCT
 #define RB_STACK_IN_STRUCT 0    // 1: the round-1 layout (deep stack array as a member of Traversal), kept for comparison
 #endif
@@ -645,11 +657,24 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                     int k = tr.tsp;
                     for (;;) {
                         const uint32_t tag = (g.x << 5) | lane;
+#if RB_FILL_UNROLL2
+                        // two triangles per trip: the second store is predicated, the loop overhead is paid once per pair
+                        while (g.y) {
+                            const uint32_t ti = 31u - (uint32_t)__clz(g.y);
+                            g.y ^= 1u << ti;
+                            w[0] = tag + (ti << 5);
+                            const bool more = g.y != 0u;
+                            const uint32_t tj = 31u - (uint32_t)__clz(g.y | 1u);
+                            if (more) { g.y ^= 1u << tj; w[1] = tag + (tj << 5); }
+                            w += more ? 2 : 1;
+                        }
+#else
                         while (g.y) {
                             const uint32_t ti = 31u - (uint32_t)__clz(g.y);
                             g.y ^= 1u << ti;
                             *w++ = tag + (ti << 5);
                         }
+#endif
                         if (k == 0) break;
                         g = tr.tst(ws, --k);
                     }
@@ -691,12 +716,20 @@ __device__ __forceinline__ void trace_queue(const WideNode* __restrict__ nodes, 
                     const bool crosses = rb_tri_edges(rb_mk3(r0.x, r0.y, r0.z), sh, rb_mk3(va.x, va.y, va.z), rb_mk3(vb.x, vb.y, vb.z),
                                                       rb_mk3(vc.x, vc.y, vc.z), &det, &T, &b1, &b2);      // b1, b2 hold V, W until the commit
                     if (crosses) t = T / det;
+#elif RB_BARY_LATE
+                    float T;
+                    const bool crosses = rb_tri_edges(rb_mk3(r0.x, r0.y, r0.z), sh, rb_mk3(va.x, va.y, va.z), rb_mk3(vb.x, vb.y, vb.z),
+                                                      rb_mk3(vc.x, vc.y, vc.z), &det, &T, &b1, &b2);
+                    if (crosses) t = T / det;
 #else
                     const bool crosses = rb_tri_intersect(rb_mk3(r0.x, r0.y, r0.z), sh, rb_mk3(va.x, va.y, va.z), rb_mk3(vb.x, vb.y, vb.z),
                                                           rb_mk3(vc.x, vc.y, vc.z), &t, &b1, &b2);
 #endif
                     if (crosses) {
                         if (t > 0.0f && t < r0.w) {
+#if RB_BARY_LATE && !RB_DEFER_BARY
+                            if constexpr (!ANY) { b1 = b1 / det; b2 = b2 / det; }
+#endif
                             mykey = hit_key(t, __float_as_uint(vc.w));
                             atomicMin(&ws.bestKey[owner], mykey);
                             cand = true;
