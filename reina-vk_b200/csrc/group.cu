@@ -270,9 +270,14 @@ RB200_API int rb200_context_reduced_device_ptr(RB200Context* ctx, void** out_dev
 RB200_API int rb200_group_destroy(RB200Group* g) {
     if (!g) return RB200_OK;
     for (Worker* w : g->workers) { w->wait(); w->stop(); delete w; }
-    if (g->peerTiles) {
-        for (size_t i = 0; i < g->tileDone.size(); i++)
-            if (g->tileDone[i]) { cudaSetDevice(g->devices[i]); cudaStreamSynchronize(g->ctx[i]->stream); cudaEventDestroy(g->tileDone[i]); }
+    // peer-store latency mode (also after a failed set-up: whatever was created is released)
+    for (size_t i = 0; i < g->tileDone.size(); i++)
+        if (g->tileDone[i]) {
+            cudaSetDevice(g->devices[i]);
+            if (g->ctx[i]) cudaStreamSynchronize(g->ctx[i]->stream);
+            cudaEventDestroy(g->tileDone[i]);
+        }
+    if (g->rootSnap || g->rootSnapshot) {
         cudaSetDevice(g->devices[0]);
         if (g->ctx[0]) cudaStreamSynchronize(g->ctx[0]->stream);
         if (g->rootSnap) cudaEventDestroy(g->rootSnap);
