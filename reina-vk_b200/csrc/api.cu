@@ -81,13 +81,9 @@ static int validate_desc(const RB200SceneDesc* d) {
 
 using namespace rb200;
 
-extern "C" {
-
-RB200_API uint32_t rb200_version(void) { return (1u << 16) | 0u; }
-
-RB200_API const char* rb200_last_error(void) { return g_error.c_str(); }
-
-RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, uint32_t flags, RB200Context** out) {
+// lanesHint > 0: lanes per engine instead of the compiled default (the environment still overrides) — group.cu asks for more
+// lanes in latency mode, where a device traces 1 / n of the pixels and its launches would otherwise be thin
+int rb200::context_create(uint32_t width, uint32_t height, int device, uint32_t flags, int lanesHint, RB200Context** out) {
     if (!out || width == 0 || height == 0 || (uint64_t)width * height > 0x7FFFFFFFull) { set_error("invalid context size"); return RB200_ERR_INVALID_ARGUMENT; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device available (this library has no CPU path)"); return RB200_ERR_NO_DEVICE; }
@@ -105,7 +101,7 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
     const size_t N = (size_t)width * height;
     // engines x lanes (context.cuh): RB200_ENGINES / RB200_LANES override the compiled defaults; the counting pass renders
     // one batch at a time
-    c->numEngines = RB_ENGINES; c->numLanes = RB_LANES;
+    c->numEngines = RB_ENGINES; c->numLanes = lanesHint > 0 ? std::min(lanesHint, (int)RB_MAX_LANES) : RB_LANES;
     if (const char* e = getenv("RB200_ENGINES")) c->numEngines = atoi(e);
     if (const char* e = getenv("RB200_LANES")) c->numLanes = atoi(e);
     if (flags & RB200_FLAG_COUNT_BVH) { c->numEngines = 1; c->numLanes = 1; }
@@ -175,6 +171,17 @@ RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, 
     *out = c;
     return RB200_OK;
 }
+
+extern "C" {
+
+RB200_API uint32_t rb200_version(void) { return (1u << 16) | 0u; }
+
+RB200_API const char* rb200_last_error(void) { return g_error.c_str(); }
+
+RB200_API int rb200_context_create(uint32_t width, uint32_t height, int device, uint32_t flags, RB200Context** out) {
+    return rb200::context_create(width, height, device, flags, 0, out);
+}
+
 
 RB200_API int rb200_context_destroy(RB200Context* ctx) {
     if (!ctx) return RB200_OK;

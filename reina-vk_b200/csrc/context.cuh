@@ -277,6 +277,7 @@ int bench_trace(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const fl
                 uint32_t reps, float* outMs, uint64_t* outChecksum);
 int shade_hits(RB200Context* ctx, const RB200Scene* scene, uint32_t n, const float* o, const float* d, const uint32_t* rng,
                const uint32_t* inside, const float* acc, RB200ShadeResult* out);
+int context_create(uint32_t width, uint32_t height, int device, uint32_t flags, int lanesHint, RB200Context** out);   // api.cu
 int configure_wave_kernels(RB200Context* ctx);     // per device: shared-memory limits, persistent grids, code preload
 void invalidate_speculation(RB200Context* ctx);    // drains the engines and discards speculative batches
 // post.cu
