@@ -306,7 +306,10 @@ RB200_API int rb200_group_create(uint32_t width, uint32_t height, const int* dev
         // latency mode: a member traces 1 / n of the pixels, so twice the lanes keep its launches from getting thin (one device's
         // share of an 8-device frame, measured alone: 7.5 ms per batch with 8 lanes per engine, 6.05 ms with 16)
         g->workers[i]->post([g, i, numDevices] {
-            return rb200::context_create(g->width, g->height, g->devices[i], g->flags, g->tiles && numDevices > 1 ? 16 : 0, &g->ctx[i]);
+            // (path state is allocated per lane for the whole image: ~0.5 KB per pixel and lane over both engines, 16 GB per
+            // device at 1080p with 16 lanes; larger images keep the default)
+            const bool roomy = (uint64_t)g->width * g->height <= (4ull << 20);
+            return rb200::context_create(g->width, g->height, g->devices[i], g->flags, g->tiles && numDevices > 1 && roomy ? 16 : 0, &g->ctx[i]);
         });
     int rc = g->wait_all();
     if (rc != RB200_OK) { rb200_group_destroy(g); return rc; }
